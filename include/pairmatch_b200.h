@@ -1,0 +1,192 @@
+/*
+ * pairmatch_b200.h -- C ABI of the B200-native exhaustive pair matcher + epipolar filter.
+ *
+ * Drop-in boundary for ONE hot path of smileyenot983/reconstructor (paths below are relative
+ * to the reference tree):
+ *
+ *   SequentialReconstructor::matchFeatures(bool)   Mapper/libMapper/SequentialReconstructor.cpp:199-279
+ *     -> FeatureMatcher::matchFeatures             Mapper/libMapper/FeatureMatcher.h:18-22,
+ *        (FlannMatcher impl)                       Mapper/libMapper/FeatureMatcher.cpp:32-65
+ *     -> GeometricFilter::estimateFundamental      Mapper/libMapper/GeometricFilter.h:33-35,
+ *                                                  Mapper/libMapper/GeometricFilter.cpp:39-61
+ *
+ * The reference has no FFI (it is one C++ process); these are the entry points its plugin
+ * classes would bind (see INTEGRATION.md for the C++ shim a maintainer adds).  Plain C
+ * linkage, POD arguments only, no exceptions cross this boundary, no CPU fallback: every
+ * compute entry point fails with PM_ERR_NO_DEVICE when there is no CUDA device.
+ *
+ * Threading: every entry point taking a pm_handle is thread-safe (the reference calls its
+ * plugins from up to 4 OpenMP threads on one shared object, SequentialReconstructor.cpp:202).
+ */
+#ifndef PAIRMATCH_B200_H_
+#define PAIRMATCH_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pm_context* pm_handle;
+
+/* Status codes (0 = ok, negative = error; text via pm_last_error). */
+enum {
+  PM_OK = 0,
+  PM_ERR_INVALID = -1,      /* bad argument / inconsistent descriptor shape          */
+  PM_ERR_NO_DEVICE = -2,    /* no usable CUDA device (there is NO CPU fallback)      */
+  PM_ERR_CUDA = -3,         /* CUDA runtime / driver error                           */
+  PM_ERR_OOM = -4,          /* host or device allocation failed                      */
+  PM_ERR_STATE = -5,        /* e.g. image id not set                                 */
+  PM_ERR_UNSUPPORTED = -6   /* valid request this build does not implement           */
+};
+
+/* Descriptor element kinds.
+ *   PM_DESC_F32      dim floats per row; what FeatDesc::desc holds (datatypes.h:70-71).
+ *                    Rows that are integer-valued in [0,255] with dim == 128 (SIFT,
+ *                    FeatureDetector.cpp:20-24) take the exact fp16 tensor-core path.
+ *   PM_DESC_U8_BITS  dim BITS per row (dim/8 bytes), Hamming norm (ORB, 256 bits).
+ *   PM_DESC_U8       dim bytes per row, integer-valued L2 (SIFT shipped as bytes). */
+enum { PM_DESC_F32 = 0, PM_DESC_U8_BITS = 1, PM_DESC_U8 = 2 };
+
+/* Uniqueness after the ratio test.
+ *   PM_UNIQUE_FIRST_WINS  reference semantics, FeatureMatcher.cpp:58-62: in ascending query
+ *                         order the first query claiming a train index keeps it.
+ *   PM_MUTUAL_NN          cross-check: keep (q,t) iff q is also t's nearest query.
+ *   PM_UNIQUE_NONE        ratio test only. */
+enum { PM_UNIQUE_FIRST_WINS = 0, PM_MUTUAL_NN = 1, PM_UNIQUE_NONE = 2 };
+
+/* Residual of the epipolar filter.
+ *   PM_RESID_SYMMETRIC_EPIPOLAR  what cv::findFundamentalMat uses (GeometricFilter.cpp:47):
+ *                                max of the two squared point-to-epipolar-line distances.
+ *   PM_RESID_SAMPSON             first-order geometric error (north-star wording). */
+enum { PM_RESID_SYMMETRIC_EPIPOLAR = 0, PM_RESID_SAMPSON = 1 };
+
+/* Hypothesis sampler.  PM_SAMPLER_OPENCV_MWC replays cv::findFundamentalMat's fixed-seed
+ * multiply-with-carry stream, which makes inlier masks comparable with cv2 one to one. */
+enum { PM_SAMPLER_OPENCV_MWC = 0 };
+
+/* Per-pair outcome (pm_csr_result.status / pm_pair_result.status). */
+enum {
+  PM_PAIR_UNFILTERED = 0,   /* fewer than min_matches putative matches (or filter off): all kept,
+                               SequentialReconstructor.cpp:270-276                            */
+  PM_PAIR_FILTERED = 1,     /* F estimated, inlier flags valid, .cpp:259-267                  */
+  PM_PAIR_DROPPED = 2       /* F estimation failed: pair gets no entry, .cpp:253-256          */
+};
+
+typedef struct {
+  float   ratio;              /* Lowe ratio, FeatureMatcher.h:45 (0.7)                      */
+  int32_t unique_mode;        /* PM_UNIQUE_*                                                */
+  int32_t min_matches;        /* >= gate before the filter, SequentialReconstructor.cpp:237 */
+  int32_t do_filter;          /* matchFeatures(bool filter)                                 */
+  double  ransac_threshold;   /* cv::findFundamentalMat defaults: 3.0 px                    */
+  double  ransac_confidence;  /*                                  0.99                      */
+  int32_t ransac_max_iters;   /*                                  1000                      */
+  int32_t residual_mode;      /* PM_RESID_*                                                 */
+  int32_t sampler;            /* PM_SAMPLER_*                                               */
+  int32_t batch_pairs;        /* pairs per device batch, 0 = auto                           */
+  int64_t reserve_keypoints;  /* device arena rows to preallocate, 0 = grow on demand       */
+  int32_t debug_flags;        /* bit 0: force the SIMT fp32 L2 kernel (parity cross-check)  */
+  int32_t reserved;
+} pm_params;
+
+/* One pair, caller-allocated outputs (capacity = number of query keypoints). */
+typedef struct {
+  int32_t  capacity;          /* in: length of q/t/inlier                                   */
+  int32_t  n_matches;         /* out: putative matches after ratio + uniqueness             */
+  int32_t  n_inliers;         /* out: matches that survive the filter                       */
+  int32_t  status;            /* out: PM_PAIR_*                                             */
+  int32_t  ransac_iters;      /* out: hypotheses iterations actually consumed               */
+  int32_t* q;                 /* out: query indices, ascending                              */
+  int32_t* t;                 /* out: train indices                                         */
+  uint8_t* inlier;            /* out: 1 = kept                                              */
+  double   F[9];              /* out: row-major, zeros unless PM_PAIR_FILTERED              */
+} pm_pair_result;
+
+/* Batched result: flat CSR over pairs, library-allocated (free with pm_free_result). */
+typedef struct {
+  int64_t  n_pairs;
+  int32_t* pair_ij;           /* [n_pairs][2]  (query image, train image)                   */
+  int64_t* offsets;           /* [n_pairs+1]   into q/t/inlier                              */
+  int32_t* q;                 /* putative matches, ascending q inside a pair                */
+  int32_t* t;
+  uint8_t* inlier;            /* 1 = belongs to featureMatches[(i,j)]                       */
+  double*  F;                 /* [n_pairs][9]                                               */
+  int32_t* status;            /* [n_pairs]     PM_PAIR_*                                    */
+  int32_t* n_inliers;         /* [n_pairs]                                                  */
+  int32_t* ransac_iters;      /* [n_pairs]                                                  */
+  double   device_ms;         /* CUDA-event time of the whole call on the device            */
+  void*    owner_;            /* private                                                    */
+} pm_csr_result;
+
+typedef struct {
+  int64_t pairs_matched;
+  int64_t putative_matches;
+  int64_t inlier_matches;
+  int64_t kernel_launches;    /* launches of this library's own kernels                     */
+  int64_t h2d_bytes;
+  int64_t d2h_bytes;
+  double  knn_ms;             /* CUDA-event time of the dominant kNN kernel, summed         */
+  int64_t knn_launches;
+  double  knn_work;           /* algorithmic work of those launches: FLOP (L2) or popc32    */
+  int32_t device_id;
+  int32_t n_images;
+} pm_stats;
+
+void        pm_default_params(pm_params* p);
+/* device_ids == NULL / n_dev == 0: current device.  n_dev > 1: pairs are partitioned over the
+ * devices, descriptors replicated on each, one host thread per device. */
+int         pm_create(const pm_params* p, const int* device_ids, int n_dev, pm_handle* out);
+int         pm_destroy(pm_handle h);
+const char* pm_last_error(pm_handle h);          /* h may be NULL: last error of pm_create   */
+const char* pm_version(void);
+
+/* Packs + uploads one image once (replaces featDescToCV's per-pair cost,
+ * FeatureMatcher.cpp:11-25).  desc: n rows of `dim` elements of `dtype`, row-major, host
+ * memory.  xy: n x 2 int32 pixel coordinates (FeatCoord<int>, datatypes.h:12-25) or NULL.
+ * All images of one handle must share dim and dtype. */
+int pm_set_image(pm_handle h, int img_id, const void* desc, int n, int dim, int dtype,
+                 const int32_t* xy);
+/* Same, descriptors/xy already in DEVICE memory of the handle's device (ingest after an
+ * NCCL all-gather of sharded extraction).  Single-device handles only. */
+int pm_set_image_device(pm_handle h, int img_id, const void* d_desc, int n, int dim, int dtype,
+                        const int32_t* d_xy);
+int pm_num_keypoints(pm_handle h, int img_id);
+
+/* Raw 2-NN rows of pair (i -> j): what knnMatch(desc_i, desc_j, 2) returns as DMatch rows
+ * (FeatureMatcher.cpp:49).  idx/dist are [n_i][2]; missing neighbours are idx -1, dist +inf.
+ * dist is the float L2 norm (sqrt) or the Hamming count as float, like cv::DMatch::distance. */
+int pm_knn_pair(pm_handle h, int img_i, int img_j, int32_t* idx, float* dist);
+
+/* FeatureMatcher::matchFeatures for two resident images: kNN -> ratio -> uniqueness.
+ * Fills n_matches/q/t only (status = PM_PAIR_UNFILTERED). */
+int pm_match_pair(pm_handle h, int img_i, int img_j, pm_pair_result* out);
+/* Same from raw host descriptors (what the per-pair virtual call hands over). */
+int pm_match_descriptors(pm_handle h, const void* desc1, int n1, const void* desc2, int n2,
+                         int dim, int dtype, pm_pair_result* out);
+
+/* GeometricFilter::estimateFundamental: xy1/xy2 are M x 2 float pixel coordinates of
+ * already matched points.  status: PM_PAIR_FILTERED, or PM_PAIR_DROPPED when no model was
+ * found (the reference then returns Zero() and an empty mask, GeometricFilter.cpp:50-53). */
+int pm_filter_pair_F(pm_handle h, const float* xy1, const float* xy2, int M,
+                     double F[9], uint8_t* mask, int32_t* status, int32_t* iters);
+
+/* The whole pair body for one pair (match + gate + filter). */
+int pm_match_filter_pair(pm_handle h, int img_i, int img_j, pm_pair_result* out);
+
+/* The whole loop: pairs = [n_pairs][2] image ids (query, train), or NULL for all i < j over
+ * the images set so far.  Runs kNN -> ratio -> uniqueness -> F-RANSAC batched on the device(s)
+ * and returns CSR arrays in host memory. */
+int pm_match_all_pairs(pm_handle h, const int32_t* pairs, int64_t n_pairs, pm_csr_result** out);
+int pm_free_result(pm_csr_result* r);
+
+int pm_get_stats(pm_handle h, pm_stats* out);
+int pm_reset_stats(pm_handle h);
+
+/* popc32 / fp32 pipe micro-benchmarks used to measure the roofline denominators that
+ * MEASURED_PEAKS.json does not hold: returns ops per second. */
+int pm_measure_popc_peak(pm_handle h, double* popc32_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,313 @@
+"""ctypes binding of libpairmatch_b200.so (include/pairmatch_b200.h).
+
+Host-side mirror (Python flavour) of the reference's plugin interface for the hot path:
+
+  FeatureMatcher::matchFeatures              Mapper/libMapper/FeatureMatcher.h:18-22
+  GeometricFilter::estimateFundamental       Mapper/libMapper/GeometricFilter.h:33-35
+  SequentialReconstructor::matchFeatures     Mapper/libMapper/SequentialReconstructor.cpp:199-279
+
+The C++ flavour (what a maintainer of the reference links) is reconstructor_b200/cpp/.
+This module never imports the oracle and has no CPU path: if the CUDA library or a device
+is missing it raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpairmatch_b200.so")
+
+DESC_F32, DESC_U8_BITS, DESC_U8 = 0, 1, 2
+UNIQUE_FIRST_WINS, MUTUAL_NN, UNIQUE_NONE = 0, 1, 2
+RESID_SYMMETRIC_EPIPOLAR, RESID_SAMPSON = 0, 1
+PAIR_UNFILTERED, PAIR_FILTERED, PAIR_DROPPED = 0, 1, 2
+OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_OOM, ERR_STATE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
+
+EXPORTS = [
+    "pm_default_params", "pm_create", "pm_destroy", "pm_last_error", "pm_version", "pm_set_image",
+    "pm_set_image_device", "pm_num_keypoints", "pm_knn_pair", "pm_match_pair",
+    "pm_match_descriptors", "pm_filter_pair_F", "pm_match_filter_pair", "pm_match_all_pairs",
+    "pm_free_result", "pm_get_stats", "pm_reset_stats", "pm_measure_popc_peak",
+]
+
+
+class Params(C.Structure):
+    _fields_ = [("ratio", C.c_float), ("unique_mode", C.c_int32), ("min_matches", C.c_int32),
+                ("do_filter", C.c_int32), ("ransac_threshold", C.c_double),
+                ("ransac_confidence", C.c_double), ("ransac_max_iters", C.c_int32),
+                ("residual_mode", C.c_int32), ("sampler", C.c_int32), ("batch_pairs", C.c_int32),
+                ("reserve_keypoints", C.c_int64), ("debug_flags", C.c_int32), ("reserved", C.c_int32)]
+
+
+class PairResult(C.Structure):
+    _fields_ = [("capacity", C.c_int32), ("n_matches", C.c_int32), ("n_inliers", C.c_int32),
+                ("status", C.c_int32), ("ransac_iters", C.c_int32), ("q", C.POINTER(C.c_int32)),
+                ("t", C.POINTER(C.c_int32)), ("inlier", C.POINTER(C.c_uint8)), ("F", C.c_double * 9)]
+
+
+class CsrResult(C.Structure):
+    _fields_ = [("n_pairs", C.c_int64), ("pair_ij", C.POINTER(C.c_int32)),
+                ("offsets", C.POINTER(C.c_int64)), ("q", C.POINTER(C.c_int32)),
+                ("t", C.POINTER(C.c_int32)), ("inlier", C.POINTER(C.c_uint8)),
+                ("F", C.POINTER(C.c_double)), ("status", C.POINTER(C.c_int32)),
+                ("n_inliers", C.POINTER(C.c_int32)), ("ransac_iters", C.POINTER(C.c_int32)),
+                ("device_ms", C.c_double), ("owner_", C.c_void_p)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("pairs_matched", C.c_int64), ("putative_matches", C.c_int64),
+                ("inlier_matches", C.c_int64), ("kernel_launches", C.c_int64),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("knn_ms", C.c_double),
+                ("knn_launches", C.c_int64), ("knn_work", C.c_double), ("device_id", C.c_int32),
+                ("n_images", C.c_int32)]
+
+
+class PairMatchError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"pairmatch_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Loads the in-tree CUDA library; fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        lib.pm_last_error.restype = C.c_char_p
+        lib.pm_last_error.argtypes = [C.c_void_p]
+        lib.pm_version.restype = C.c_char_p
+        lib.pm_create.argtypes = [C.POINTER(Params), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
+        lib.pm_destroy.argtypes = [C.c_void_p]
+        lib.pm_set_image.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        lib.pm_set_image_device.argtypes = lib.pm_set_image.argtypes
+        lib.pm_num_keypoints.argtypes = [C.c_void_p, C.c_int]
+        lib.pm_knn_pair.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        lib.pm_debug_tc_dump.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.pm_match_pair.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(PairResult)]
+        lib.pm_match_filter_pair.argtypes = lib.pm_match_pair.argtypes
+        lib.pm_match_descriptors.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                             C.c_int, C.POINTER(PairResult)]
+        lib.pm_filter_pair_F.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                         C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        lib.pm_match_all_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_int64,
+                                           C.POINTER(C.POINTER(CsrResult))]
+        lib.pm_free_result.argtypes = [C.POINTER(CsrResult)]
+        lib.pm_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        lib.pm_reset_stats.argtypes = [C.c_void_p]
+        lib.pm_measure_popc_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        _lib = lib
+    return _lib
+
+
+def default_params() -> Params:
+    p = Params()
+    load_library().pm_default_params(C.byref(p))
+    return p
+
+
+def _desc_args(desc: np.ndarray, dtype: int | None):
+    """Maps a numpy descriptor matrix to (contiguous array, dim, dtype enum)."""
+    if dtype is None:
+        dtype = DESC_U8_BITS if desc.dtype == np.uint8 else DESC_F32
+    if dtype == DESC_U8_BITS:
+        a = np.ascontiguousarray(desc, np.uint8)
+        return a, a.shape[1] * 8, dtype
+    if dtype == DESC_U8:
+        a = np.ascontiguousarray(desc, np.uint8)
+        return a, a.shape[1], dtype
+    a = np.ascontiguousarray(desc, np.float32)
+    return a, a.shape[1], dtype
+
+
+class PairMatcher:
+    """Handle on the device pipeline (one per process; thread-safe like the reference's plugins)."""
+
+    def __init__(self, devices=None, **kw):
+        self.lib = load_library()
+        self.params = default_params()
+        for k, v in kw.items():
+            if not hasattr(self.params, k):
+                raise TypeError(f"unknown parameter {k}")
+            setattr(self.params, k, v)
+        self.h = C.c_void_p()
+        if devices is None:
+            rc = self.lib.pm_create(C.byref(self.params), None, 0, C.byref(self.h))
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self.lib.pm_create(C.byref(self.params), arr, len(devices), C.byref(self.h))
+        if rc != OK:
+            raise PairMatchError(rc, self.lib.pm_last_error(None).decode())
+        self._n = {}
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.pm_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != OK:
+            raise PairMatchError(rc, self.lib.pm_last_error(self.h).decode())
+
+    # -- ingest ---------------------------------------------------------------------------------
+    def set_image(self, img_id: int, desc: np.ndarray, xy: np.ndarray | None = None, dtype=None):
+        a, dim, dt = _desc_args(desc, dtype)
+        xyp = None
+        if xy is not None:
+            xy = np.ascontiguousarray(xy, np.int32)
+            assert xy.shape == (a.shape[0], 2)
+            xyp = xy.ctypes.data
+        self._check(self.lib.pm_set_image(self.h, img_id, a.ctypes.data, a.shape[0], dim, dt, xyp))
+        self._n[img_id] = a.shape[0]
+
+    def set_image_ptr(self, img_id: int, desc_ptr: int, n: int, dim: int, dtype: int, xy_ptr: int | None,
+                      on_device=False):
+        """Raw-pointer variant (pinned host buffers or device buffers)."""
+        f = self.lib.pm_set_image_device if on_device else self.lib.pm_set_image
+        self._check(f(self.h, img_id, desc_ptr, n, dim, dtype, xy_ptr))
+        self._n[img_id] = n
+
+    # -- per-pair (compat path of the virtual calls) ---------------------------------------------
+    def knn_pair(self, i: int, j: int):
+        n = self._n[i]
+        idx = np.empty((n, 2), np.int32); dist = np.empty((n, 2), np.float32)
+        self._check(self.lib.pm_knn_pair(self.h, i, j, idx.ctypes.data, dist.ctypes.data))
+        return idx, dist
+
+    def debug_tc_dump(self, i: int, j: int):
+        n = self._n[i]
+        idx = np.empty((n, 2), np.int32); dist = np.empty((n, 2), np.float32)
+        acc = np.zeros((256, 128), np.float32)
+        self._check(self.lib.pm_debug_tc_dump(self.h, i, j, idx.ctypes.data, dist.ctypes.data, acc.ctypes.data))
+        return idx, dist, acc
+
+    def _pair(self, fn, *args, cap):
+        q = np.empty(max(cap, 1), np.int32); t = np.empty(max(cap, 1), np.int32)
+        inl = np.zeros(max(cap, 1), np.uint8)
+        r = PairResult()
+        r.capacity = cap
+        r.q = q.ctypes.data_as(C.POINTER(C.c_int32)); r.t = t.ctypes.data_as(C.POINTER(C.c_int32))
+        r.inlier = inl.ctypes.data_as(C.POINTER(C.c_uint8))
+        self._check(fn(self.h, *args, C.byref(r)))
+        m = r.n_matches
+        return dict(q=q[:m].copy(), t=t[:m].copy(), inlier=inl[:m].copy(), status=r.status,
+                    n_inliers=r.n_inliers, iters=r.ransac_iters, F=np.array(r.F[:]).reshape(3, 3))
+
+    def match_pair(self, i: int, j: int):
+        """FeatureMatcher::matchFeatures for resident images -> dict(q, t)."""
+        return self._pair(self.lib.pm_match_pair, i, j, cap=self._n[i])
+
+    def match_filter_pair(self, i: int, j: int):
+        """Pair body of SequentialReconstructor::matchFeatures (match, >=7 gate, filter)."""
+        return self._pair(self.lib.pm_match_filter_pair, i, j, cap=self._n[i])
+
+    def match_descriptors(self, desc1: np.ndarray, desc2: np.ndarray, dtype=None):
+        a, dim, dt = _desc_args(desc1, dtype)
+        b, dim2, _ = _desc_args(desc2, dtype)
+        assert dim == dim2
+        return self._pair(self.lib.pm_match_descriptors, a.ctypes.data, a.shape[0], b.ctypes.data,
+                          b.shape[0], dim, dt, cap=a.shape[0])
+
+    def estimate_fundamental(self, xy1: np.ndarray, xy2: np.ndarray):
+        """GeometricFilter::estimateFundamental -> (F 3x3, mask uint8 [M], status, iters)."""
+        p1 = np.ascontiguousarray(xy1, np.float32); p2 = np.ascontiguousarray(xy2, np.float32)
+        m = p1.shape[0]
+        F = np.zeros(9, np.float64); mask = np.zeros(max(m, 1), np.uint8)
+        st = C.c_int32(0); it = C.c_int32(0)
+        self._check(self.lib.pm_filter_pair_F(self.h, p1.ctypes.data, p2.ctypes.data, m, F.ctypes.data,
+                                              mask.ctypes.data, C.byref(st), C.byref(it)))
+        return F.reshape(3, 3), mask[:m], st.value, it.value
+
+    # -- batched loop ----------------------------------------------------------------------------
+    def match_all_pairs(self, pairs: np.ndarray | None = None, copy=True):
+        """Whole pair loop.  Returns dict of numpy arrays (CSR): pair_ij, offsets, q, t, inlier, F,
+        status, n_inliers, ransac_iters, device_ms."""
+        res = C.POINTER(CsrResult)()
+        if pairs is None:
+            self._check(self.lib.pm_match_all_pairs(self.h, None, 0, C.byref(res)))
+        else:
+            pairs = np.ascontiguousarray(pairs, np.int32)
+            self._check(self.lib.pm_match_all_pairs(self.h, pairs.ctypes.data, pairs.shape[0], C.byref(res)))
+        r = res.contents
+        n = r.n_pairs
+
+        def arr(ptr, count, dt):
+            if count == 0:
+                return np.empty(0, dt)
+            a = np.ctypeslib.as_array(ptr, shape=(count,))
+            return a.copy() if copy else a
+        out = dict(n_pairs=n, device_ms=r.device_ms)
+        out["offsets"] = arr(r.offsets, n + 1, np.int64)
+        total = int(out["offsets"][n]) if n >= 0 else 0
+        out["pair_ij"] = arr(r.pair_ij, 2 * n, np.int32).reshape(-1, 2)
+        out["q"] = arr(r.q, total, np.int32); out["t"] = arr(r.t, total, np.int32)
+        out["inlier"] = arr(r.inlier, total, np.uint8)
+        out["F"] = arr(r.F, 9 * n, np.float64).reshape(-1, 3, 3)
+        out["status"] = arr(r.status, n, np.int32)
+        out["n_inliers"] = arr(r.n_inliers, n, np.int32)
+        out["ransac_iters"] = arr(r.ransac_iters, n, np.int32)
+        if copy:
+            self.lib.pm_free_result(res)
+        else:
+            out["_handle"] = res
+        return out
+
+    def free_result(self, out):
+        if "_handle" in out:
+            self.lib.pm_free_result(out.pop("_handle"))
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._check(self.lib.pm_get_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+    def reset_stats(self):
+        self._check(self.lib.pm_reset_stats(self.h))
+
+    def measure_popc_peak(self) -> float:
+        v = C.c_double(0)
+        self._check(self.lib.pm_measure_popc_peak(self.h, C.byref(v)))
+        return v.value
+
+
+def feature_matches_view(res: dict, mirror=True) -> dict:
+    """Materialises the reference's `featureMatches` container
+    (unordered_map<pair<int,int>, unordered_map<int,int>>, SequentialReconstructor.h:226) from the
+    CSR result: entries exist for (i,j) and, mirrored, for (j,i) (.cpp:219-227); dropped pairs
+    have no entry (.cpp:253-256); pairs without any surviving match have no entry either."""
+    fm = {}
+    off = res["offsets"]
+    for p in range(res["n_pairs"]):
+        if res["status"][p] == PAIR_DROPPED:
+            continue
+        a, b = int(off[p]), int(off[p + 1])
+        keep = res["inlier"][a:b].astype(bool)
+        q = res["q"][a:b][keep]; t = res["t"][a:b][keep]
+        if len(q) == 0:
+            continue
+        i, j = map(int, res["pair_ij"][p])
+        fm[(i, j)] = dict(zip(q.tolist(), t.tolist()))
+        if mirror:
+            fm[(j, i)] = dict(zip(t.tolist(), q.tolist()))
+    return fm

@@ -1,0 +1,65 @@
+// kernels.h -- host-side launchers of the pair-matching kernels (internal to the library).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace pm {
+
+struct RansacDev {
+  double confidence;
+  float thr;            // (float)(threshold * threshold)
+  int max_iters;
+  int residual_mode;
+  int min_matches;
+  int do_filter;
+};
+
+// K1 -- hamming.cu
+cudaError_t launch_hamming_top2(const uint32_t* bits, int words, const PairJob* jobs, int n_jobs,
+                                int max_nq, int2* idx, float2* dist, int stride, int variant,
+                                cudaStream_t st);
+cudaError_t launch_popc_peak(uint32_t* out, int blocks, int iters, cudaStream_t st);
+
+// K3 -- l2_simt.cu
+cudaError_t launch_l2_simt(const float* desc, int dim, const PairJob* jobs, int n_jobs, int max_nq,
+                           int2* idx, float2* dist, int stride, cudaStream_t st);
+
+// K2 -- l2_tc.cu (tcgen05 / TMEM / TMA), integer-valued 128-d descriptors
+static constexpr int TC_DIM = 128;        // descriptor length handled by the tensor path
+static constexpr int TC_KPAD = 144;       // 128 + one K=16 step carrying the train-row norm
+struct TcMaps {
+  CUtensorMap q_main, q_ext, t_main, t_ext;
+};
+cudaError_t tc_configure();               // one-time function attributes
+cudaError_t launch_l2_tc(const TcMaps& maps, const int32_t* qnorm, const PairJob* jobs, int n_jobs,
+                         int max_nq, int2* idx, float2* dist, int stride, int num_sms,
+                         float* debug_dump, cudaStream_t st);
+
+// pack.cu
+cudaError_t launch_pack_sift(const float* raw_f32, const uint8_t* raw_u8, int n, __half* qf,
+                             __half* tf, int32_t* qnorm, float* raw_out, int* not_integral,
+                             cudaStream_t st);
+cudaError_t launch_u8_to_f32(const uint8_t* src, float* dst, size_t n, cudaStream_t st);
+
+// K4 -- select.cu
+cudaError_t launch_select(const PairJob* jobs, int n_jobs, const int2* knn_idx,
+                          const float2* knn_dist, const int2* rev_idx, const int32_t* xy,
+                          int stride, float ratio, int mode, int32_t* owner, int32_t* match_q,
+                          int32_t* match_t, float2* pts1, float2* pts2, int32_t* count,
+                          cudaStream_t st);
+// exclusive scan of counts + gather of the per-slot slabs into contiguous arrays
+cudaError_t launch_compact(const int32_t* count, int n_jobs, int stride, const int32_t* match_q,
+                           const int32_t* match_t, const uint8_t* mask, int64_t* offsets,
+                           int32_t* out_q, int32_t* out_t, uint8_t* out_mask, cudaStream_t st);
+
+// K5/K6 -- ransac.cu
+cudaError_t launch_ransac(const float2* pts1, const float2* pts2, const int32_t* count, int n_jobs,
+                          int stride, const RansacDev& prm, uint8_t* mask, double* F,
+                          int32_t* status, int32_t* n_inliers, int32_t* iters, cudaStream_t st);
+
+}  // namespace pm

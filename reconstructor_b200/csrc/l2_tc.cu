@@ -1,0 +1,297 @@
+// l2_tc.cu -- K2: exact 2-NN under the L2 norm on the 5th-gen tensor cores (tcgen05 + TMEM + TMA)
+// for integer-valued 128-d descriptors (SIFT, FeatureDetector.cpp:20-24: 128 floats in [0,255]).
+//
+// Replaces knnMatch at Mapper/libMapper/FeatureMatcher.cpp:48-49.  Parity: cv::BFMatcher(NORM_L2),
+// bit-exact.  Why exact: operands are fp16 (integers <= 510 are exact), every product and every
+// partial sum is an integer of magnitude < 2^24, so the fp32 accumulator in TMEM holds the exact
+// integer  nb - 2 a.b  whatever the accumulation order.  d^2 = na + (nb - 2 a.b).
+//
+// The distance matrix is the dense contraction it is:
+//     acc[q][t] = sum_k (-2 a_qk) * b_tk   +   1*lo(nb_t) + 2048*mid(nb_t) + 2048*(2048*hi(nb_t))
+// i.e. the train-row norm rides in one extra K=16 MMA step (three fp16-exact pieces), so the
+// epilogue only has to select minima -- no per-element add.
+//
+// CTA = 12 warps, persistent, one per SM:
+//   warp 0      TMA producer: A (256 query rows, resident per work item) and a 4-stage ring of
+//               B tiles (128 train rows), SWIZZLE_128B for the two 64-wide K atoms and
+//               SWIZZLE_32B for the 16-wide norm block
+//   warp 1      MMA issuer: one thread, tcgen05.mma.kind::f16 M=128 N=128 K=16, 9 steps per
+//               (m-tile, B tile); four 128-column fp32 accumulators in TMEM (2 m-tiles x 2 stages)
+//   warp 2      TMEM allocator (512 columns)
+//   warps 4-11  epilogue: tcgen05.ld 32x32b.x32 -> registers, min-tree over 32 columns, rare
+//               slow path inserts into the per-row running top-2 (strict <, ascending columns
+//               => lowest index wins ties); overlaps the next tile's MMAs via the 2-deep
+//               accumulator ring
+// Work item = (pair, 256-row query super-tile); items are dealt round-robin to the CTAs so that
+// concurrently running CTAs share the same train image in L2.
+//
+// Algorithmic work: 2 * nq * nt * 128 FLOP per pair.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pm {
+
+static constexpr int TC_THREADS = 384;
+static constexpr int TC_BM = 128;             // rows per m-tile (UMMA M)
+static constexpr int TC_MT = 2;               // m-tiles per CTA
+static constexpr int TC_ROWS = TC_BM * TC_MT; // query rows per work item
+static constexpr int TC_BN = 128;             // train rows per B tile (UMMA N)
+static constexpr int TC_STAGES = 4;
+static constexpr int TC_ATOM_BYTES = TC_BM * 128;                 // 128 rows x 128 B  (SW128 atom column)
+static constexpr int TC_EXT_BYTES = TC_BM * 32;                   // 128 rows x 32 B   (SW32 block)
+static constexpr int TC_TILE_BYTES = 2 * TC_ATOM_BYTES + TC_EXT_BYTES;   // 36 KB
+static constexpr int TC_SMEM_A = TC_MT * TC_TILE_BYTES;           // 72 KB
+static constexpr int TC_SMEM_B = TC_STAGES * TC_TILE_BYTES;       // 144 KB
+static constexpr int TC_SMEM_BYTES = TC_SMEM_A + TC_SMEM_B + 1024 /*align slack*/ + 256 /*barriers*/;
+static constexpr uint32_t TC_TMEM_COLS = 512;
+
+// kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, N=128, M=128.
+static constexpr uint32_t TC_IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((TC_BN >> 3) << 17) |
+                                     ((TC_BM >> 4) << 24);
+
+// Shared-memory matrix descriptor, K-major, swizzled.  addr/SBO in bytes.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo, uint32_t layout) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);           // start address
+  d |= static_cast<uint64_t>(1) << 16;                            // LBO (unused for swizzled K-major)
+  d |= static_cast<uint64_t>((sbo >> 4) & 0x3FFF) << 32;          // stride between 8-row groups
+  d |= static_cast<uint64_t>(1) << 46;                            // descriptor version (sm_100)
+  d |= static_cast<uint64_t>(layout) << 61;                       // 2 = SWIZZLE_128B, 6 = SWIZZLE_32B
+  return d;
+}
+
+__device__ __forceinline__ void wait_bounded(uint64_t* bar, uint32_t parity) {
+  // A protocol bug must fault, not hang the GPU: ~seconds of spinning, then trap.
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
+    if (spin > (1u << 26)) __trap();
+  }
+}
+
+struct Top2 {
+  float m1, m2;
+  int i1, i2;
+};
+
+__device__ __forceinline__ void top2_push(Top2& s, float v, int col) {
+  if (v < s.m2) {
+    if (v < s.m1) { s.m2 = s.m1; s.i2 = s.i1; s.m1 = v; s.i1 = col; }
+    else { s.m2 = v; s.i2 = col; }
+  }
+}
+
+// Processes 32 consecutive columns held in registers.
+__device__ __forceinline__ void scan32(Top2& s, const uint32_t (&r)[32], int col0) {
+  float g[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    g[k] = fminf(fminf(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1])),
+                 fminf(__uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3])));
+  const float cm = fminf(fminf(fminf(g[0], g[1]), fminf(g[2], g[3])),
+                         fminf(fminf(g[4], g[5]), fminf(g[6], g[7])));
+  if (cm < s.m2) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (g[k] < s.m2) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) top2_push(s, __uint_as_float(r[4 * k + e]), col0 + 4 * k + e);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+l2_top2_tc_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant__ CUtensorMap q_ext,
+                  const __grid_constant__ CUtensorMap t_main, const __grid_constant__ CUtensorMap t_ext,
+                  const int32_t* __restrict__ qnorm, const PairJob* __restrict__ jobs, int n_jobs,
+                  int tiles_per_job, int2* __restrict__ knn_idx, float2* __restrict__ knn_dist,
+                  int stride, float* __restrict__ debug_dump) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + TC_SMEM_A;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_SMEM_A + TC_SMEM_B);
+  uint64_t* a_full = bars + 0;
+  uint64_t* a_empty = bars + 1;
+  uint64_t* b_full = bars + 2;                      // [TC_STAGES]
+  uint64_t* b_empty = bars + 2 + TC_STAGES;         // [TC_STAGES]
+  uint64_t* acc_full = bars + 2 + 2 * TC_STAGES;    // [2 stages][2 m-tiles]
+  uint64_t* acc_empty = acc_full + 4;               // [2][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&q_main); tma_prefetch_desc(&q_ext);
+    tma_prefetch_desc(&t_main); tma_prefetch_desc(&t_ext);
+    mbar_init(a_full, 1); mbar_init(a_empty, 1);
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TC_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_items = n_jobs * tiles_per_job;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      uint32_t ai = 0, bi = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int jb = item / tiles_per_job, r = item - jb * tiles_per_job;
+        const PairJob job = jobs[jb];
+        if (r * TC_ROWS >= job.nq) continue;
+        wait_bounded(a_empty, (ai & 1) ^ 1);
+        mbar_expect_tx(a_full, TC_SMEM_A);
+#pragma unroll
+        for (int m = 0; m < TC_MT; ++m) {
+          uint8_t* dst = sA + m * TC_TILE_BYTES;
+          const int row = job.q_row + r * TC_ROWS + m * TC_BM;
+          tma_load_2d(dst, &q_main, 0, row, a_full);
+          tma_load_2d(dst + TC_ATOM_BYTES, &q_main, 64, row, a_full);
+          tma_load_2d(dst + 2 * TC_ATOM_BYTES, &q_ext, TC_DIM, row, a_full);
+        }
+        ++ai;
+        const int n_tiles = (job.nt + TC_BN - 1) / TC_BN;
+        for (int n = 0; n < n_tiles; ++n, ++bi) {
+          const uint32_t st = bi % TC_STAGES;
+          wait_bounded(&b_empty[st], ((bi / TC_STAGES) & 1) ^ 1);
+          mbar_expect_tx(&b_full[st], TC_TILE_BYTES);
+          uint8_t* dst = sB + st * TC_TILE_BYTES;
+          const int row = job.t_row + n * TC_BN;
+          tma_load_2d(dst, &t_main, 0, row, &b_full[st]);
+          tma_load_2d(dst + TC_ATOM_BYTES, &t_main, 64, row, &b_full[st]);
+          tma_load_2d(dst + 2 * TC_ATOM_BYTES, &t_ext, TC_DIM, row, &b_full[st]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ====================================== MMA issuer ======================================
+    if (lane == 0) {
+      uint32_t ai = 0, bi = 0, ti = 0;
+      const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int jb = item / tiles_per_job, r = item - jb * tiles_per_job;
+        const PairJob job = jobs[jb];
+        if (r * TC_ROWS >= job.nq) continue;
+        wait_bounded(a_full, ai & 1);
+        ++ai;
+        const int n_tiles = (job.nt + TC_BN - 1) / TC_BN;
+        for (int n = 0; n < n_tiles; ++n, ++bi, ++ti) {
+          const uint32_t st = bi % TC_STAGES;
+          const uint32_t as = ti & 1, use = ti >> 1;
+          wait_bounded(&b_full[st], (bi / TC_STAGES) & 1);
+          const uint32_t b_base = sB_u + st * TC_TILE_BYTES;
+#pragma unroll
+          for (int m = 0; m < TC_MT; ++m) {
+            wait_bounded(&acc_empty[as * 2 + m], (use & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t a_base = sA_u + m * TC_TILE_BYTES;
+            const uint32_t d_tmem = tmem_base + (as * 2 + m) * TC_BN;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint32_t off = (k >> 2) * TC_ATOM_BYTES + (k & 3) * 32;
+              umma_f16(d_tmem, make_desc(a_base + off, 1024, 2), make_desc(b_base + off, 1024, 2),
+                       TC_IDESC, k > 0 ? 1u : 0u);
+            }
+            umma_f16(d_tmem, make_desc(a_base + 2 * TC_ATOM_BYTES, 256, 6),
+                     make_desc(b_base + 2 * TC_ATOM_BYTES, 256, 6), TC_IDESC, 1u);
+            umma_commit(&acc_full[as * 2 + m]);
+          }
+          umma_commit(&b_empty[st]);
+        }
+        umma_commit(a_empty);
+      }
+    }
+  } else if (warp >= 4) {
+    // ======================================= epilogue =======================================
+    const int m = (warp - 4) >> 2, quarter = warp & 3;
+    uint32_t ti = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int jb = item / tiles_per_job, r = item - jb * tiles_per_job;
+      const PairJob job = jobs[jb];
+      if (r * TC_ROWS >= job.nq) continue;
+      const int row = r * TC_ROWS + m * TC_BM + quarter * 32 + lane;
+      Top2 s;
+      s.m1 = s.m2 = __int_as_float(0x7f800000);
+      s.i1 = s.i2 = -1;
+      const int n_tiles = (job.nt + TC_BN - 1) / TC_BN;
+      for (int n = 0; n < n_tiles; ++n, ++ti) {
+        const uint32_t as = ti & 1, use = ti >> 1;
+        wait_bounded(&acc_full[as * 2 + m], use & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                               (as * 2 + m) * TC_BN;
+        const int valid = job.nt - n * TC_BN;          // columns of this tile that exist
+#pragma unroll
+        for (int c = 0; c < TC_BN / 32; ++c) {
+          uint32_t v[32];
+          __syncwarp();
+          tmem_ld_32x32b_x32(taddr + c * 32, v);      // includes tcgen05.wait::ld
+          if (c == TC_BN / 32 - 1) {                   // accumulator drained -> hand it back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as * 2 + m]);
+          }
+          if (debug_dump != nullptr && item == 0 && n == 0) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              debug_dump[static_cast<size_t>(m * TC_BM + quarter * 32 + lane) * TC_BN + c * 32 + e] =
+                  __uint_as_float(v[e]);
+          }
+          if (valid < (c + 1) * 32) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (c * 32 + e >= valid) v[e] = 0x7f800000u;
+          }
+          scan32(s, v, n * TC_BN + c * 32);
+        }
+      }
+      if (row < job.nq) {
+        const float na = static_cast<float>(qnorm[job.q_row + row]);
+        int2 oi;
+        float2 od;
+        oi.x = s.i1; oi.y = s.i2;
+        od.x = s.i1 < 0 ? s.m1 : __fsqrt_rn(fmaxf(__fadd_rn(s.m1, na), 0.f));
+        od.y = s.i2 < 0 ? s.m2 : __fsqrt_rn(fmaxf(__fadd_rn(s.m2, na), 0.f));
+        const size_t o = static_cast<size_t>(jb) * stride + row;
+        knn_idx[o] = oi;
+        knn_dist[o] = od;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+  }
+}
+
+cudaError_t tc_configure() {
+  return cudaFuncSetAttribute(l2_top2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              TC_SMEM_BYTES);
+}
+
+cudaError_t launch_l2_tc(const TcMaps& maps, const int32_t* qnorm, const PairJob* jobs, int n_jobs,
+                         int max_nq, int2* idx, float2* dist, int stride, int num_sms,
+                         float* debug_dump, cudaStream_t st) {
+  if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
+  const int tiles_per_job = (max_nq + TC_ROWS - 1) / TC_ROWS;
+  const int n_items = n_jobs * tiles_per_job;
+  const int grid = n_items < num_sms ? n_items : num_sms;
+  l2_top2_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(maps.q_main, maps.q_ext, maps.t_main,
+                                                             maps.t_ext, qnorm, jobs, n_jobs,
+                                                             tiles_per_job, idx, dist, stride,
+                                                             debug_dump);
+  return cudaGetLastError();
+}
+
+}  // namespace pm

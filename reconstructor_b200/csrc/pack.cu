@@ -1,0 +1,89 @@
+// pack.cu -- one-pass ingest of an image's descriptors into the device layouts of the kNN kernels.
+//
+// Replaces featDescToCV (Mapper/libMapper/FeatureMatcher.cpp:11-25), which the reference re-runs
+// for both images of every pair; here it runs once per image (pm_set_image).
+//
+// SIFT-like rows (128 values, integer-valued in [0,255]; FeatureDetector.cpp:20-24) are written
+// in the two operand forms of the tcgen05 kernel, 144 fp16 per row:
+//   query form  [ -2*a_0 .. -2*a_127 | 1, 2048, 2048, 0 x13 ]
+//   train form  [    b_0 ..    b_127 | lo, mid, 2048*hi, 0 x13 ]   with |b|^2 = lo + 2048*mid + 2048*2048*hi
+// so that the MMA accumulator equals |b|^2 - 2 a.b exactly (see l2_tc.cu).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pm {
+
+__global__ void __launch_bounds__(256)
+pack_sift_kernel(const float* __restrict__ raw_f32, const uint8_t* __restrict__ raw_u8, int n,
+                 __half* __restrict__ qf, __half* __restrict__ tf, int32_t* __restrict__ qnorm,
+                 float* __restrict__ raw_out, int* __restrict__ not_integral) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  float v[4];
+  if (raw_u8) {
+    const uchar4 u = *reinterpret_cast<const uchar4*>(raw_u8 + static_cast<size_t>(row) * TC_DIM + 4 * lane);
+    v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w;
+  } else {
+    const float4 f = *reinterpret_cast<const float4*>(raw_f32 + static_cast<size_t>(row) * TC_DIM + 4 * lane);
+    v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+  }
+  if (raw_out)
+    *reinterpret_cast<float4*>(raw_out + static_cast<size_t>(row) * TC_DIM + 4 * lane) =
+        make_float4(v[0], v[1], v[2], v[3]);
+  bool bad = false;
+  int nrm = 0;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    bad |= !(v[e] >= 0.f && v[e] <= 255.f && v[e] == rintf(v[e]));
+    const int iv = static_cast<int>(v[e]);
+    nrm += iv * iv;
+  }
+  if (__any_sync(0xffffffffu, bad)) {
+    if (lane == 0) atomicOr(not_integral, 1);
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, off);
+
+  __half2 q01 = __floats2half2_rn(-2.f * v[0], -2.f * v[1]);
+  __half2 q23 = __floats2half2_rn(-2.f * v[2], -2.f * v[3]);
+  __half2 t01 = __floats2half2_rn(v[0], v[1]);
+  __half2 t23 = __floats2half2_rn(v[2], v[3]);
+  __half* qrow = qf + static_cast<size_t>(row) * TC_KPAD;
+  __half* trow = tf + static_cast<size_t>(row) * TC_KPAD;
+  reinterpret_cast<__half2*>(qrow)[2 * lane] = q01;
+  reinterpret_cast<__half2*>(qrow)[2 * lane + 1] = q23;
+  reinterpret_cast<__half2*>(trow)[2 * lane] = t01;
+  reinterpret_cast<__half2*>(trow)[2 * lane + 1] = t23;
+  if (lane < 16) {
+    float qe = 0.f, te = 0.f;
+    if (lane == 0) { qe = 1.f; te = static_cast<float>(nrm & 2047); }
+    else if (lane == 1) { qe = 2048.f; te = static_cast<float>((nrm >> 11) & 2047); }
+    else if (lane == 2) { qe = 2048.f; te = 2048.f * static_cast<float>(nrm >> 22); }
+    qrow[TC_DIM + lane] = __float2half_rn(qe);
+    trow[TC_DIM + lane] = __float2half_rn(te);
+  }
+  if (lane == 0) qnorm[row] = nrm;
+}
+
+cudaError_t launch_pack_sift(const float* raw_f32, const uint8_t* raw_u8, int n, __half* qf,
+                             __half* tf, int32_t* qnorm, float* raw_out, int* not_integral,
+                             cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  pack_sift_kernel<<<(n + 7) / 8, 256, 0, st>>>(raw_f32, raw_u8, n, qf, tf, qnorm, raw_out,
+                                                not_integral);
+  return cudaGetLastError();
+}
+
+__global__ void u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = static_cast<float>(src[i]);
+}
+
+cudaError_t launch_u8_to_f32(const uint8_t* src, float* dst, size_t n, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  u8_to_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(src, dst, n);
+  return cudaGetLastError();
+}
+
+}  // namespace pm

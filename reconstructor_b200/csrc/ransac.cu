@@ -1,0 +1,377 @@
+// ransac.cu -- K5/K6: batched fundamental-matrix RANSAC, one CTA per image pair, one warp per
+// hypothesis for the inlier count.
+//
+// Replaces GeometricFilter::estimateFundamental (Mapper/libMapper/GeometricFilter.cpp:39-61),
+// i.e. cv::findFundamentalMat(p1, p2, mask) with its defaults (FM_RANSAC, 3 px, 0.99, 1000):
+//   * sampler: OpenCV's fixed-seed 64-bit multiply-with-carry stream, duplicate re-draw,
+//     last-point collinearity reject -- inherently sequential, one thread replays it;
+//   * minimal solver: un-normalised 7-point (7x9 null space -> cubic -> up to 3 models), one
+//     thread per hypothesis of the round, fp64;
+//   * score: symmetric epipolar distance (or Sampson), fp64 rounded to fp32 and compared with
+//     (float)(t*t); one warp per hypothesis, lanes stride over the matches;
+//   * selection: (iteration, model)-ordered scan, "strictly more inliers replaces", adaptive
+//     iteration bound -- identical to the sequential loop because hypotheses at or beyond
+//     the shrunken bound are discarded.
+// Rounds of 8, 16, then 32 iterations so easy pairs (95 % inliers need ~4) stop early.
+//
+// The arithmetic order follows the CPU filter of the parity tests operation for operation;
+// this translation unit MUST be compiled with -fmad=false (no fp contraction).
+#include <cfloat>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pm {
+
+static constexpr int RS_THREADS = 256;
+static constexpr int RS_WARPS = RS_THREADS / 32;
+static constexpr int RS_ROUND = 32;
+
+struct MwcRng {
+  unsigned long long s;
+  __device__ __forceinline__ unsigned int next() {
+    s = static_cast<unsigned long long>(static_cast<unsigned int>(s)) * 4164903690ull + (s >> 32);
+    return static_cast<unsigned int>(s);
+  }
+  __device__ __forceinline__ int uniform(int a, int b) {
+    return a == b ? a : static_cast<int>(next() % static_cast<unsigned int>(b - a)) + a;
+  }
+};
+
+__device__ bool last_point_collinear(const float2* p) {
+  const int i = 6;
+  for (int j = 0; j < i; ++j) {
+    const double dx1 = static_cast<double>(__fsub_rn(p[j].x, p[i].x));
+    const double dy1 = static_cast<double>(__fsub_rn(p[j].y, p[i].y));
+    for (int k = 0; k < j; ++k) {
+      const double dx2 = static_cast<double>(__fsub_rn(p[k].x, p[i].x));
+      const double dy2 = static_cast<double>(__fsub_rn(p[k].y, p[i].y));
+      if (fabs(dx2 * dy1 - dy2 * dx1) <=
+          static_cast<double>(FLT_EPSILON) * (fabs(dx1) + fabs(dy1) + fabs(dx2) + fabs(dy2)))
+        return true;
+    }
+  }
+  return false;
+}
+
+// Draws one 7-subset exactly like the sequential sampler; returns false after max_attempts.
+__device__ bool get_subset(const float2* __restrict__ p1, const float2* __restrict__ p2, int n,
+                           MwcRng& rng, int max_attempts, int* idx) {
+  int iters = 0, i = 0;
+  float2 s1[7], s2[7];
+  for (; iters < max_attempts; ++iters) {
+    for (i = 0; i < 7 && iters < max_attempts;) {
+      const int v = rng.uniform(0, n);
+      int j = 0;
+      for (; j < i; ++j)
+        if (v == idx[j]) break;
+      if (j < i) continue;
+      idx[i] = v;
+      s1[i] = p1[v];
+      s2[i] = p2[v];
+      ++i;
+    }
+    if (i == 7 && (last_point_collinear(s1) || last_point_collinear(s2))) continue;
+    break;
+  }
+  return i == 7 && iters < max_attempts;
+}
+
+__device__ int update_num_iters(double p, double ep, int model_points, int max_iters) {
+  p = p < 0 ? 0 : (p > 1 ? 1 : p);
+  ep = ep < 0 ? 0 : (ep > 1 ? 1 : ep);
+  double num = 1 - p;
+  if (num < DBL_MIN) num = DBL_MIN;
+  double den = 1 - pow(1 - ep, static_cast<double>(model_points));
+  if (den < DBL_MIN) return 0;
+  num = log(num);
+  den = log(den);
+  if (den >= 0 || -num >= max_iters * (-den)) return max_iters;
+  return static_cast<int>(llrint(num / den));
+}
+
+__device__ int solve_cubic(const double* c, double* x) {
+  double a0 = c[0], a1 = c[1], a2 = c[2], a3 = c[3];
+  int n = 0;
+  double x0 = 0, x1 = 0, x2 = 0;
+  if (a0 == 0) {
+    if (a1 == 0) {
+      if (a2 == 0) n = a3 == 0 ? -1 : 0;
+      else { x0 = -a3 / a2; n = 1; }
+    } else {
+      double d = a2 * a2 - 4 * a1 * a3;
+      if (d >= 0) {
+        d = sqrt(d);
+        const double q1 = (-a2 + d) * 0.5, q2 = (a2 + d) * -0.5;
+        if (fabs(q1) > fabs(q2)) { x0 = q1 / a1; x1 = a3 / q1; }
+        else { x0 = q2 / a1; x1 = a3 / q2; }
+        n = d > 0 ? 2 : 1;
+      }
+    }
+  } else {
+    a0 = 1. / a0; a1 *= a0; a2 *= a0; a3 *= a0;
+    const double Q = (a1 * a1 - 3 * a2) * (1. / 9);
+    const double R = (2 * a1 * a1 * a1 - 9 * a1 * a2 + 27 * a3) * (1. / 54);
+    const double Qcubed = Q * Q * Q;
+    double d = Qcubed - R * R;
+    if (d > 0) {
+      const double theta = acos(R / sqrt(Qcubed));
+      const double sqrtQ = sqrt(Q);
+      const double t0 = -2 * sqrtQ, t1 = theta * (1. / 3), t2 = a1 * (1. / 3);
+      x0 = t0 * cos(t1) - t2;
+      x1 = t0 * cos(t1 + (2. * 3.14159265358979323846 / 3)) - t2;
+      x2 = t0 * cos(t1 + (4. * 3.14159265358979323846 / 3)) - t2;
+      n = 3;
+    } else if (d == 0) {
+      if (R >= 0) { x0 = -2 * pow(R, 1. / 3) - a1 / 3; x1 = pow(R, 1. / 3) - a1 / 3; }
+      else { x0 = 2 * pow(-R, 1. / 3) - a1 / 3; x1 = -pow(-R, 1. / 3) - a1 / 3; }
+      n = x0 == x1 ? 1 : 2;
+    } else {
+      d = sqrt(-d);
+      double e = pow(d + fabs(R), 1. / 3);
+      if (R > 0) e = -e;
+      x0 = (e + Q / e) - a1 * (1. / 3);
+      n = 1;
+    }
+  }
+  x[0] = x0; x[1] = x1; x[2] = x2;
+  return n;
+}
+
+// 7-point solver; m1/m2 are the 7 sampled correspondences.  F receives up to 3 models.
+__device__ int seven_point(const float2* m1, const float2* m2, double* F) {
+  // B = A^T (9 x 7); Householder vectors are kept in place (column k, rows k..8).
+  double B[9][7], vn2[7];
+  for (int i = 0; i < 7; ++i) {
+    const double x0 = m1[i].x, y0 = m1[i].y, x1 = m2[i].x, y1 = m2[i].y;
+    B[0][i] = x1 * x0; B[1][i] = x1 * y0; B[2][i] = x1;
+    B[3][i] = y1 * x0; B[4][i] = y1 * y0; B[5][i] = y1;
+    B[6][i] = x0;      B[7][i] = y0;      B[8][i] = 1.0;
+  }
+  for (int k = 0; k < 7; ++k) {
+    double nrm2 = 0;
+    for (int i = k; i < 9; ++i) nrm2 += B[i][k] * B[i][k];
+    const double nrm = sqrt(nrm2);
+    if (!(nrm > 0)) return 0;
+    const double alpha = B[k][k] > 0 ? -nrm : nrm;
+    B[k][k] -= alpha;                                  // column k now holds v_k
+    double s2 = 0;
+    for (int i = k; i < 9; ++i) s2 += B[i][k] * B[i][k];
+    vn2[k] = s2;
+    if (!(s2 > 0)) return 0;
+    for (int j = k + 1; j < 7; ++j) {
+      double s = 0;
+      for (int i = k; i < 9; ++i) s += B[i][k] * B[i][j];
+      const double f = 2 * s / s2;
+      for (int i = k; i < 9; ++i) B[i][j] -= f * B[i][k];
+    }
+  }
+  double f1[9], f2[9];
+  for (int e = 0; e < 2; ++e) {
+    double y[9];
+    for (int i = 0; i < 9; ++i) y[i] = 0.0;
+    y[7 + e] = 1.0;
+    for (int k = 6; k >= 0; --k) {
+      double s = 0;
+      for (int i = k; i < 9; ++i) s += B[i][k] * y[i];
+      const double f = 2 * s / vn2[k];
+      for (int i = k; i < 9; ++i) y[i] -= f * B[i][k];
+    }
+    for (int i = 0; i < 9; ++i) (e == 0 ? f1 : f2)[i] = y[i];
+  }
+  for (int i = 0; i < 9; ++i) f1[i] -= f2[i];
+
+  double c[4], r[3];
+  double t0 = f2[4] * f2[8] - f2[5] * f2[7];
+  double t1 = f2[3] * f2[8] - f2[5] * f2[6];
+  double t2 = f2[3] * f2[7] - f2[4] * f2[6];
+  c[3] = f2[0] * t0 - f2[1] * t1 + f2[2] * t2;
+  c[2] = f1[0] * t0 - f1[1] * t1 + f1[2] * t2 -
+         f1[3] * (f2[1] * f2[8] - f2[2] * f2[7]) +
+         f1[4] * (f2[0] * f2[8] - f2[2] * f2[6]) -
+         f1[5] * (f2[0] * f2[7] - f2[1] * f2[6]) +
+         f1[6] * (f2[1] * f2[5] - f2[2] * f2[4]) -
+         f1[7] * (f2[0] * f2[5] - f2[2] * f2[3]) +
+         f1[8] * (f2[0] * f2[4] - f2[1] * f2[3]);
+  t0 = f1[4] * f1[8] - f1[5] * f1[7];
+  t1 = f1[3] * f1[8] - f1[5] * f1[6];
+  t2 = f1[3] * f1[7] - f1[4] * f1[6];
+  c[1] = f2[0] * t0 - f2[1] * t1 + f2[2] * t2 -
+         f2[3] * (f1[1] * f1[8] - f1[2] * f1[7]) +
+         f2[4] * (f1[0] * f1[8] - f1[2] * f1[6]) -
+         f2[5] * (f1[0] * f1[7] - f1[1] * f1[6]) +
+         f2[6] * (f1[1] * f1[5] - f1[2] * f1[4]) -
+         f2[7] * (f1[0] * f1[5] - f1[2] * f1[3]) +
+         f2[8] * (f1[0] * f1[4] - f1[1] * f1[3]);
+  c[0] = f1[0] * t0 - f1[1] * t1 + f1[2] * t2;
+
+  const int n = solve_cubic(c, r);
+  if (n < 1 || n > 3) return 0;
+  for (int k = 0; k < n; ++k) {
+    double lambda = r[k], mu = 1.0;
+    const double s = f1[8] * r[k] + f2[8];
+    double* Fk = F + 9 * k;
+    if (fabs(s) > DBL_EPSILON) { mu = 1. / s; lambda *= mu; Fk[8] = 1.0; }
+    else Fk[8] = 0.0;
+    for (int i = 0; i < 8; ++i) Fk[i] = f1[i] * lambda + f2[i] * mu;
+  }
+  return n;
+}
+
+__device__ __forceinline__ float residual(const double* F, float2 q1, float2 q2, int mode) {
+  const double x1 = q1.x, y1 = q1.y, x2 = q2.x, y2 = q2.y;
+  double a = F[0] * x1 + F[1] * y1 + F[2];
+  double b = F[3] * x1 + F[4] * y1 + F[5];
+  double c = F[6] * x1 + F[7] * y1 + F[8];
+  const double g2 = a * a + b * b;
+  const double d2 = x2 * a + y2 * b + c;
+  a = F[0] * x2 + F[3] * y2 + F[6];
+  b = F[1] * x2 + F[4] * y2 + F[7];
+  c = F[2] * x2 + F[5] * y2 + F[8];
+  const double g1 = a * a + b * b;
+  const double d1 = x1 * a + y1 * b + c;
+  if (mode == 1) return static_cast<float>(d2 * d2 / (g1 + g2));
+  const double s2 = 1. / g2, s1 = 1. / g1;
+  const double e1 = d1 * d1 * s1, e2 = d2 * d2 * s2;
+  return static_cast<float>(e1 > e2 ? e1 : e2);
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+fmat_ransac_kernel(const float2* __restrict__ pts1, const float2* __restrict__ pts2,
+                   const int32_t* __restrict__ count, int stride, RansacDev prm,
+                   uint8_t* __restrict__ mask, double* __restrict__ F_out,
+                   int32_t* __restrict__ status, int32_t* __restrict__ n_inliers,
+                   int32_t* __restrict__ iters_out) {
+  const int slot = blockIdx.x;
+  const size_t base = static_cast<size_t>(slot) * stride;
+  const float2* p1 = pts1 + base;
+  const float2* p2 = pts2 + base;
+  uint8_t* msk = mask + base;
+  const int M = count[slot];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  __shared__ double sF[RS_ROUND][27];
+  __shared__ double bestF[9];
+  __shared__ int sSub[RS_ROUND][7];
+  __shared__ int sNm[RS_ROUND];
+  __shared__ int sCnt[RS_ROUND][3];
+  __shared__ int sGen, sStop, sIter, sNiters, sBest;
+
+  if (!prm.do_filter || M < prm.min_matches) {
+    for (int i = tid; i < M; i += RS_THREADS) msk[i] = 1;
+    if (tid == 0) {
+      status[slot] = 0; n_inliers[slot] = M; iters_out[slot] = 0;
+      for (int i = 0; i < 9; ++i) F_out[9 * slot + i] = 0.0;
+    }
+    return;
+  }
+
+  if (M == 7) {                       // direct 7-point, mask all ones, first solution kept
+    if (tid == 0) {
+      double Fm[27];
+      float2 a[7], b[7];
+      for (int i = 0; i < 7; ++i) { a[i] = p1[i]; b[i] = p2[i]; }
+      const int ns = seven_point(a, b, Fm);
+      for (int i = 0; i < 9; ++i) F_out[9 * slot + i] = ns > 0 ? Fm[i] : 0.0;
+      status[slot] = ns > 0 ? 1 : 2;
+      n_inliers[slot] = ns > 0 ? 7 : 0;
+      iters_out[slot] = 1;
+      for (int i = 0; i < 7; ++i) msk[i] = ns > 0 ? 1 : 0;
+    }
+    return;
+  }
+
+  __shared__ unsigned long long sRng;
+  if (tid == 0) { sRng = ~0ull; sIter = 0; sNiters = prm.max_iters; sBest = 0; sStop = 0; }
+  __syncthreads();
+
+  int round_size = 8;
+  while (true) {
+    // ---- sample (sequential stream) --------------------------------------------------------
+    if (tid == 0) {
+      MwcRng rng{sRng};
+      int g = 0;
+      for (; g < round_size; ++g) {
+        if (sIter + g >= sNiters) break;
+        if (!get_subset(p1, p2, M, rng, 10000, sSub[g])) { sStop = 1; break; }
+      }
+      sGen = g;
+      sRng = rng.s;
+    }
+    __syncthreads();
+    const int gen = sGen;
+    if (gen == 0) break;
+    // ---- solve: one thread per hypothesis --------------------------------------------------
+    if (tid < gen) {
+      float2 a[7], b[7];
+      for (int i = 0; i < 7; ++i) { a[i] = p1[sSub[tid][i]]; b[i] = p2[sSub[tid][i]]; }
+      sNm[tid] = seven_point(a, b, sF[tid]);
+    }
+    __syncthreads();
+    // ---- score: one warp per (iteration, model) -------------------------------------------
+    for (int h = warp; h < gen * 3; h += RS_WARPS) {
+      const int k = h / 3, m = h - 3 * k;
+      if (m >= sNm[k]) continue;
+      double F[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) F[i] = sF[k][9 * m + i];
+      int good = 0;
+      for (int i = lane; i < M; i += 32)
+        good += residual(F, p1[i], p2[i], prm.residual_mode) <= prm.thr ? 1 : 0;
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) good += __shfl_xor_sync(0xffffffffu, good, off);
+      if (lane == 0) sCnt[k][m] = good;
+    }
+    __syncthreads();
+    // ---- select: ordered scan with the strict-improvement rule ---------------------------
+    if (tid == 0) {
+      int k = 0;
+      for (; k < gen; ++k) {
+        if (sIter + k >= sNiters) break;
+        for (int m = 0; m < sNm[k]; ++m) {
+          const int good = sCnt[k][m];
+          if (good > (sBest > 6 ? sBest : 6)) {
+            sBest = good;
+            for (int i = 0; i < 9; ++i) bestF[i] = sF[k][9 * m + i];
+            sNiters = update_num_iters(prm.confidence, static_cast<double>(M - good) / M, 7,
+                                       sNiters);
+          }
+        }
+      }
+      sIter += k;
+      if (sIter >= sNiters) sStop = 1;
+    }
+    __syncthreads();
+    if (sStop) break;
+    round_size = round_size < RS_ROUND ? round_size * 2 : RS_ROUND;
+  }
+  __syncthreads();
+
+  const int best = sBest;
+  if (best > 0) {
+    double F[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) F[i] = bestF[i];
+    for (int i = tid; i < M; i += RS_THREADS)
+      msk[i] = residual(F, p1[i], p2[i], prm.residual_mode) <= prm.thr ? 1 : 0;
+  } else {
+    for (int i = tid; i < M; i += RS_THREADS) msk[i] = 0;
+  }
+  if (tid == 0) {
+    status[slot] = best > 0 ? 1 : 2;
+    n_inliers[slot] = best;
+    iters_out[slot] = sIter;
+    for (int i = 0; i < 9; ++i) F_out[9 * slot + i] = best > 0 ? bestF[i] : 0.0;
+  }
+}
+
+cudaError_t launch_ransac(const float2* pts1, const float2* pts2, const int32_t* count, int n_jobs,
+                          int stride, const RansacDev& prm, uint8_t* mask, double* F,
+                          int32_t* status, int32_t* n_inliers, int32_t* iters, cudaStream_t st) {
+  if (n_jobs <= 0) return cudaSuccess;
+  fmat_ransac_kernel<<<n_jobs, RS_THREADS, 0, st>>>(pts1, pts2, count, stride, prm, mask, F, status,
+                                                    n_inliers, iters);
+  return cudaGetLastError();
+}
+
+}  // namespace pm

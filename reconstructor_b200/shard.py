@@ -1,0 +1,33 @@
+"""Multi-GPU partition of the pair loop: image pairs are independent units, so the
+pair list is split into contiguous, equally sized shares -- one per rank / device -- with every
+descriptor set replicated on every GPU and NO data-path collective.  A pair's result does not
+depend on which GPU ran it (the RANSAC stream is a function of the pair's own matches only)."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def images_for_world(world: int, base_images: int = 100) -> int:
+    """Weak scaling: smallest image count whose all-pairs list holds >= world * C(base,2) pairs,
+    i.e. the per-GPU share stays ~ C(base,2) pairs (4,950 for the 100-image config)."""
+    target = world * base_images * (base_images - 1) // 2
+    n = base_images
+    while n * (n - 1) // 2 < target:
+        n += 1
+    return n
+
+
+def all_pairs(n_images: int) -> np.ndarray:
+    """Canonical pair list, query = lower image id (SequentialReconstructor.cpp:203-227 run
+    sequentially visits (i,j), i<j first and mirrors (j,i))."""
+    i, j = np.triu_indices(n_images, k=1)
+    return np.stack([i, j], axis=1).astype(np.int32)
+
+
+def shard_bounds(n_pairs: int, world: int) -> np.ndarray:
+    return (np.arange(world + 1, dtype=np.int64) * n_pairs) // world
+
+
+def shard_pairs(pairs: np.ndarray, rank: int, world: int) -> np.ndarray:
+    b = shard_bounds(len(pairs), world)
+    return pairs[b[rank]:b[rank + 1]]

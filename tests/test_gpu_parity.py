@@ -1,0 +1,368 @@
+"""GPU parity tests: the CUDA path through the C ABI vs the oracle and the committed goldens.
+
+Bar: bit-exact for integer / byte / index work (Hamming, integer-valued SIFT, match lists,
+inlier masks); L2 distances of real-valued descriptors within 1e-5 relative (tolerance of the
+north star), their indices equal to the fp64 brute force except at fp64 near-ties (< 1e-6 rel).
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import orc  # noqa: E402  (the checker)
+from reconstructor_b200 import api, synth  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def knn(golden_dir):
+    return np.load(os.path.join(golden_dir, "knn_pairs.npz"))
+
+
+@pytest.fixture(scope="module")
+def scenes(golden_dir):
+    return np.load(os.path.join(golden_dir, "fmat_scenes.npz"))
+
+
+@pytest.fixture(scope="module")
+def fountain(golden_dir):
+    return np.load(os.path.join(golden_dir, "fountain.npz"))
+
+
+def _load3(pm, g, kind, ties=False):
+    for i in range(3):
+        d = g[f"{kind}_desc{i}"]
+        if ties and i == 1:
+            d = g[f"{kind}_desc1_ties"]
+        if kind == "sift":
+            d = d.astype(np.float32)
+        pm.set_image(i, d, g[f"{kind}_xy{i}"])
+
+
+# ---------------------------------------------------------------------------------------------
+# kNN
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", [0, 2])
+def test_hamming_knn_bit_exact(knn, variant):
+    with api.PairMatcher(debug_flags=variant) as pm:
+        _load3(pm, knn, "orb")
+        for tag, a, b in (("01", 0, 1), ("02", 0, 2), ("12", 1, 2)):
+            idx, dist = pm.knn_pair(a, b)
+            assert np.array_equal(idx, knn[f"orb_{tag}_idx"])
+            assert np.array_equal(dist, knn[f"orb_{tag}_dist"])
+
+
+@pytest.mark.parametrize("force_simt", [0, 1])
+def test_l2_sift_knn_bit_exact(knn, force_simt):
+    """force_simt=0 is the tcgen05 path, 1 the fp32 SIMT kernel; both must equal cv::BFMatcher."""
+    with api.PairMatcher(debug_flags=force_simt) as pm:
+        _load3(pm, knn, "sift")
+        for tag, a, b in (("01", 0, 1), ("02", 0, 2), ("12", 1, 2)):
+            idx, dist = pm.knn_pair(a, b)
+            bad = np.nonzero((idx != knn[f"sift_{tag}_idx"]).any(axis=1))[0]
+            assert len(bad) == 0, (tag, bad[:10], idx[bad[:5]], knn[f"sift_{tag}_idx"][bad[:5]])
+            assert np.array_equal(dist, knn[f"sift_{tag}_dist"])
+
+
+def test_l2_sift_u8_dtype_matches_f32(knn):
+    with api.PairMatcher() as pm:
+        for i in range(3):
+            pm.set_image(i, knn[f"sift_desc{i}"], knn[f"sift_xy{i}"], dtype=api.DESC_U8)
+        idx, dist = pm.knn_pair(0, 1)
+        assert np.array_equal(idx, knn["sift_01_idx"]) and np.array_equal(dist, knn["sift_01_dist"])
+
+
+@pytest.mark.parametrize("kind,flags", [("orb", 0), ("sift", 0), ("sift", 1)])
+def test_knn_ties_lowest_index(knn, kind, flags):
+    with api.PairMatcher(debug_flags=flags) as pm:
+        _load3(pm, knn, kind, ties=True)
+        idx, dist = pm.knn_pair(0, 1)
+        assert np.array_equal(idx, knn[f"{kind}_ties_idx"])
+        assert np.array_equal(dist, knn[f"{kind}_ties_dist"])
+        assert tuple(idx[10]) == (5, 77) and tuple(idx[20]) == (31, 300)
+
+
+def test_l2_superpoint_within_tolerance(knn):
+    with api.PairMatcher() as pm:
+        _load3(pm, knn, "superpoint")
+        for tag, a, b in (("01", 0, 1), ("12", 1, 2)):
+            idx, dist = pm.knn_pair(a, b)
+            oi, o2 = orc.knn2_l2(knn[f"superpoint_desc{a}"], knn[f"superpoint_desc{b}"])
+            np.testing.assert_allclose(dist, np.sqrt(o2), rtol=1e-5)          # north-star tolerance
+            np.testing.assert_allclose(dist, knn[f"superpoint_{tag}_dist"], rtol=1e-5)
+            for r in np.nonzero((idx != oi).any(axis=1))[0]:                    # only fp64 near-ties
+                assert abs(o2[r, 1] - o2[r, 0]) <= 1e-6 * o2[r, 1]
+
+
+def test_tc_accumulators_exact(knn):
+    """The raw TMEM accumulators of the first 256x128 block equal nb - 2 a.b as integers."""
+    a = knn["sift_desc0"].astype(np.int64); b = knn["sift_desc1"].astype(np.int64)
+    with api.PairMatcher() as pm:
+        _load3(pm, knn, "sift")
+        idx, dist, acc = pm.debug_tc_dump(0, 1)
+    want = (b[:128] ** 2).sum(1)[None, :] - 2 * (a[:256] @ b[:128].T)
+    got = acc.astype(np.int64)
+    bad = np.argwhere(got != want)
+    assert len(bad) == 0, (len(bad), bad[:8], got[tuple(bad[0])], want[tuple(bad[0])])
+
+
+def test_l2_sift_extreme_values_exact():
+    """All-255 / all-0 rows: 2*a.b reaches 16,646,400 < 2^24 -- the fp32 accumulator limit."""
+    rng = np.random.default_rng(3)
+    q = rng.integers(0, 256, (300, 128)).astype(np.float32)
+    t = rng.integers(0, 256, (260, 128)).astype(np.float32)
+    q[:40] = 255; t[:30] = 255; q[40:60] = 0; t[30:50] = 0
+    t[100] = q[7]
+    oi, o2 = orc.knn2_l2(q, t)
+    with api.PairMatcher() as pm:
+        pm.set_image(0, q); pm.set_image(1, t)
+        idx, dist = pm.knn_pair(0, 1)
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(dist, np.sqrt(o2).astype(np.float32))
+
+
+@pytest.mark.parametrize("kind", ["orb", "sift", "superpoint"])
+def test_knn_ragged_and_tiny(kind):
+    """Ragged sizes (not multiples of any tile), 1-row and 2-row train sets, empty images."""
+    w = synth.World(kind, 700, seed=11)
+    full = [w.image(i, 4)[0] for i in range(2)]
+    cases = [(1, 1), (5, 1), (3, 2), (129, 127), (257, 300), (700, 513), (511, 700)]
+    with api.PairMatcher() as pm:
+        for nq, nt in cases:
+            q, t = full[0][:nq], full[1][:nt]
+            pm.set_image(0, q); pm.set_image(1, t)
+            idx, dist = pm.knn_pair(0, 1)
+            if kind == "orb":
+                oi, od = orc.knn2_hamming(q, t)
+                od = od.astype(np.float32)
+                od[oi < 0] = np.inf
+                assert np.array_equal(idx, oi) and np.array_equal(dist, od), (nq, nt)
+            else:
+                oi, o2 = orc.knn2_l2(q, t)
+                od = np.sqrt(o2).astype(np.float32)
+                if kind == "sift":
+                    assert np.array_equal(idx, oi) and np.array_equal(dist, od), (nq, nt)
+                else:
+                    assert np.array_equal(idx, oi), (nq, nt)
+                    np.testing.assert_allclose(dist, od, rtol=1e-5)
+        # empty query image: nothing to do, empty train image: no neighbours
+        pm.set_image(2, full[0][:0]); pm.set_image(3, full[1][:10])
+        r = pm.match_pair(2, 3)
+        assert len(r["q"]) == 0
+        pm.set_image(4, full[0][:10]); pm.set_image(5, full[1][:0])
+        idx, dist = pm.knn_pair(4, 5)
+        assert (idx == -1).all() and np.isinf(dist).all()
+        assert len(pm.match_pair(4, 5)["q"]) == 0
+
+
+# ---------------------------------------------------------------------------------------------
+# ratio + uniqueness
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["orb", "sift", "superpoint"])
+@pytest.mark.parametrize("mode", [api.UNIQUE_FIRST_WINS, api.MUTUAL_NN, api.UNIQUE_NONE])
+def test_ratio_unique_modes(knn, kind, mode):
+    d0, d1 = knn[f"{kind}_desc0"], knn[f"{kind}_desc1"]
+    if kind != "orb":
+        d0, d1 = d0.astype(np.float32), d1.astype(np.float32)
+    if kind == "orb":
+        oi, od = orc.knn2_hamming(d0, d1); od = od.astype(np.float32)
+    else:
+        oi, o2 = orc.knn2_l2(d0, d1); od = np.sqrt(o2).astype(np.float32)
+    bq = orc.best_query(d0, d1) if mode == api.MUTUAL_NN else None
+    wq, wt = orc.ratio_unique(oi, od, d1.shape[0], 0.7, mode, bq)
+    with api.PairMatcher(unique_mode=mode) as pm:
+        pm.set_image(0, d0); pm.set_image(1, d1)
+        r = pm.match_pair(0, 1)
+    assert np.array_equal(r["q"], wq) and np.array_equal(r["t"], wt)
+    assert len(wq) > 20
+
+
+# ---------------------------------------------------------------------------------------------
+# epipolar filter
+# ---------------------------------------------------------------------------------------------
+def test_fmat_masks_identical_to_cv2_and_oracle(scenes):
+    n_sc = int(scenes["n_scenes"])
+    checked = 0
+    with api.PairMatcher() as pm:
+        for k in range(n_sc):
+            p1, p2 = scenes[f"s{k}_p1"], scenes[f"s{k}_p2"]
+            n = p1.shape[0]
+            F, mask, st, it = pm.estimate_fundamental(p1, p2)
+            ns, Fo, mo, tr = orc.find_fundamental(p1, p2)
+            # GPU <-> repo CPU filter: identical in every regime
+            assert (st == api.PAIR_FILTERED) == (ns > 0), k
+            if ns > 0:
+                assert np.array_equal(mask, mo), (k, n, int(mask.sum()), int(mo.sum()))
+                if n > 7:
+                    assert it == tr.iters_run, (k, it, tr.iters_run)
+                    np.testing.assert_allclose(F, Fo[0], rtol=0, atol=1e-9 * max(1.0, np.abs(Fo[0]).max()))
+            # GPU <-> cv2.findFundamentalMat for N >= 15 (RANSAC regime of OpenCV)
+            if n >= 15 and int(scenes[f"s{k}_ok"]):
+                assert np.array_equal(mask, scenes[f"s{k}_mask"]), k
+                checked += 1
+    assert checked >= 40
+
+
+def test_fmat_degenerate_and_small(scenes):
+    with api.PairMatcher() as pm:
+        for name in ("same", "line"):
+            F, mask, st, it = pm.estimate_fundamental(scenes[f"deg_{name}_p1"], scenes[f"deg_{name}_p2"])
+            assert st == api.PAIR_DROPPED and not mask.any() and not F.any()
+        F, mask, st, it = pm.estimate_fundamental(np.zeros((6, 2), np.float32), np.ones((6, 2), np.float32))
+        assert st == api.PAIR_DROPPED
+        F, mask, st, it = pm.estimate_fundamental(np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32))
+        assert st == api.PAIR_DROPPED
+
+
+def test_fmat_sampson_mode_matches_oracle(scenes):
+    prm = orc.default_params(residual_mode=orc.RESID_SAMPSON)
+    with api.PairMatcher(residual_mode=api.RESID_SAMPSON) as pm:
+        for k in (20, 24, 30, 38, 44, 50):
+            p1, p2 = scenes[f"s{k}_p1"], scenes[f"s{k}_p2"]
+            F, mask, st, it = pm.estimate_fundamental(p1, p2)
+            ns, Fo, mo, tr = orc.find_fundamental(p1, p2, prm)
+            assert (st == api.PAIR_FILTERED) == (ns > 0)
+            assert np.array_equal(mask, mo), k
+
+
+# ---------------------------------------------------------------------------------------------
+# whole pair body / batched loop
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["orb", "sift", "superpoint"])
+def test_pair_body_matches_cv2_golden(knn, kind):
+    with api.PairMatcher() as pm:
+        _load3(pm, knn, kind)
+        for tag, a, b in (("01", 0, 1), ("02", 0, 2), ("12", 1, 2)):
+            r = pm.match_filter_pair(a, b)
+            assert len(r["q"]) == int(knn[f"{kind}_{tag}_nput"])
+            assert (r["status"] != api.PAIR_DROPPED) == bool(knn[f"{kind}_{tag}_status"])
+            keep = r["inlier"].astype(bool)
+            assert np.array_equal(r["q"][keep], knn[f"{kind}_{tag}_q"])
+            assert np.array_equal(r["t"][keep], knn[f"{kind}_{tag}_t"])
+
+
+def test_fountain_real_images(fountain):
+    """SIFT features of the reference's own sample images data/0000-0002.jpg."""
+    with api.PairMatcher() as pm:
+        for i in range(3):
+            pm.set_image(i, fountain[f"desc{i}"].astype(np.float32), fountain[f"xy{i}"])
+        res = pm.match_all_pairs()
+        fm = api.feature_matches_view(res)
+        for p, (tag, a, b) in enumerate((("01", 0, 1), ("02", 0, 2), ("12", 1, 2))):
+            assert tuple(res["pair_ij"][p]) == (a, b)
+            idx, dist = pm.knn_pair(a, b)
+            assert np.array_equal(idx, fountain[f"{tag}_idx"]) and np.array_equal(dist, fountain[f"{tag}_dist"])
+            want = dict(zip(fountain[f"{tag}_q"].tolist(), fountain[f"{tag}_t"].tolist()))
+            assert fm[(a, b)] == want
+            assert fm[(b, a)] == {t: q for q, t in want.items()}
+
+
+@pytest.mark.parametrize("kind,n_img,n_kp", [("orb", 6, 700), ("sift", 6, 650), ("superpoint", 4, 400)])
+def test_match_all_pairs_equals_oracle(kind, n_img, n_kp):
+    w = synth.World(kind, n_kp, seed=21)
+    imgs = []
+    for i in range(n_img):
+        d, xy, _ = w.image(i, n_img, outlier_frac=0.3 if i % 2 else 0.0)
+        cut = n_kp - 37 * i                       # ragged keypoint counts
+        imgs.append((d[:cut], xy[:cut]))
+    with api.PairMatcher(batch_pairs=4) as pm:    # several batches in flight
+        for i, (d, xy) in enumerate(imgs):
+            pm.set_image(i, d, xy)
+        res = pm.match_all_pairs()
+        assert res["n_pairs"] == n_img * (n_img - 1) // 2
+        for p, (i, j) in enumerate(res["pair_ij"]):
+            ref = orc.match_pair(imgs[i][0], imgs[i][1], imgs[j][0], imgs[j][1])
+            a, b = res["offsets"][p], res["offsets"][p + 1]
+            assert b - a == ref["n_putative"], (p, b - a, ref["n_putative"])
+            assert (res["status"][p] == api.PAIR_DROPPED) == (ref["status"] == "dropped")
+            keep = res["inlier"][a:b].astype(bool)
+            assert np.array_equal(res["q"][a:b][keep], ref["q"]), p
+            assert np.array_equal(res["t"][a:b][keep], ref["t"]), p
+        # explicit pair list incl. a reversed pair and a repeated pair
+        sub = np.array([[2, 1], [0, 3], [0, 3]], np.int32)
+        r2 = pm.match_all_pairs(sub)
+        ref = orc.match_pair(imgs[2][0], imgs[2][1], imgs[1][0], imgs[1][1])
+        a, b = r2["offsets"][0], r2["offsets"][1]
+        assert np.array_equal(r2["q"][a:b][r2["inlier"][a:b].astype(bool)], ref["q"])
+        a1, b1, b2 = r2["offsets"][1], r2["offsets"][2], r2["offsets"][3]
+        assert np.array_equal(r2["q"][a1:b1], r2["q"][b1:b2])
+
+
+def test_min_matches_gate_and_unfiltered_branch():
+    """< 7 putative matches: everything is kept unfiltered (SequentialReconstructor.cpp:270-276)."""
+    w = synth.World("orb", 400, seed=5)
+    d0, xy0, _ = w.image(0, 2); d1, xy1, _ = w.image(1, 2)
+    with api.PairMatcher() as pm:
+        pm.set_image(0, d0[:12], xy0[:12]); pm.set_image(1, d1, xy1)
+        r = pm.match_filter_pair(0, 1)
+        ref = orc.match_pair(d0[:12], xy0[:12], d1, xy1)
+        assert len(r["q"]) == ref["n_putative"] < 7
+        assert r["status"] == api.PAIR_UNFILTERED and r["inlier"].all()
+        assert np.array_equal(r["q"], ref["q"])
+    with api.PairMatcher(do_filter=0) as pm:
+        pm.set_image(0, d0, xy0); pm.set_image(1, d1, xy1)
+        r = pm.match_filter_pair(0, 1)
+        assert r["status"] == api.PAIR_UNFILTERED and r["inlier"].all() and len(r["q"]) > 20
+
+
+def test_match_descriptors_compat_call(knn):
+    d0, d1 = knn["orb_desc0"], knn["orb_desc1"]
+    with api.PairMatcher() as pm:
+        r = pm.match_descriptors(d0, d1)
+        oi, od = orc.knn2_hamming(d0, d1)
+        wq, wt = orc.ratio_unique(oi, od.astype(np.float32), d1.shape[0])
+        assert np.array_equal(r["q"], wq) and np.array_equal(r["t"], wt)
+        r2 = pm.match_descriptors(d1[:100], d0)           # smaller re-use of the temp slots
+        oi, od = orc.knn2_hamming(d1[:100], d0)
+        wq, wt = orc.ratio_unique(oi, od.astype(np.float32), d0.shape[0])
+        assert np.array_equal(r2["q"], wq) and np.array_equal(r2["t"], wt)
+
+
+def test_errors_are_reported_not_thrown(knn):
+    with api.PairMatcher() as pm:
+        pm.set_image(0, knn["orb_desc0"])
+        with pytest.raises(api.PairMatchError) as e:
+            pm.set_image(1, knn["sift_desc1"].astype(np.float32))      # shape/dtype mismatch
+        assert e.value.code == api.ERR_INVALID
+        with pytest.raises(api.PairMatchError) as e:
+            pm._n[9] = 4
+            pm.knn_pair(0, 9)                                           # image not set
+        assert e.value.code == api.ERR_STATE
+
+
+# ---------------------------------------------------------------------------------------------
+# full size (BASELINE.json configs): oracle on one pair + size-independent properties
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["sift", "orb"])
+def test_full_size_8192_pair(kind):
+    w = synth.World(kind, 8192, seed=0xB200)
+    imgs = [w.image(i, 100)[:2] for i in range(3)]
+    flags = [0, 1] if kind == "sift" else [0, 2]
+    outs = []
+    for f in flags:
+        with api.PairMatcher(debug_flags=f) as pm:
+            for i, (d, xy) in enumerate(imgs):
+                pm.set_image(i, d, xy)
+            outs.append(pm.knn_pair(0, 1))
+            if f == 0:
+                res = pm.match_all_pairs()
+    # tensor path == SIMT path (sift) / popc == carry-save popc (orb), bit for bit
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    # against the oracle on the same pair
+    if kind == "orb":
+        oi, od = orc.knn2_hamming(imgs[0][0], imgs[1][0]); od = od.astype(np.float32)
+    else:
+        oi, o2 = orc.knn2_l2(imgs[0][0], imgs[1][0]); od = np.sqrt(o2).astype(np.float32)
+    assert np.array_equal(outs[0][0], oi) and np.array_equal(outs[0][1], od)
+    ref = orc.match_pair(imgs[0][0], imgs[0][1], imgs[1][0], imgs[1][1])
+    a, b = res["offsets"][0], res["offsets"][1]
+    keep = res["inlier"][a:b].astype(bool)
+    assert b - a == ref["n_putative"]
+    assert np.array_equal(res["q"][a:b][keep], ref["q"]) and np.array_equal(res["t"][a:b][keep], ref["t"])
+    # properties: ascending unique queries, unique trains, planted overlap recovered
+    for p in range(3):
+        a, b = res["offsets"][p], res["offsets"][p + 1]
+        q, t = res["q"][a:b], res["t"][a:b]
+        assert (np.diff(q) > 0).all() and len(np.unique(t)) == len(t)
+        assert b - a > 1500 and res["n_inliers"][p] > 0.85 * (b - a)
