@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--debug-flags", type=int, default=0, help="pm_params.debug_flags (kernel variants)")
+    ap.add_argument("--batch-pairs", type=int, default=0)
     return ap.parse_args()
 
 
@@ -177,7 +179,8 @@ def main():
     pairs = shard.all_pairs(n_img)
     cfg = dict(workload=workload_name(a, n_img, len(pairs)), images=n_img, keypoints=a.kp, kind=a.kind,
                pairs=int(len(pairs)), partition=f"pairs sharded over {n_gpus} GPU(s), descriptors replicated",
-               l2="inputs larger than L2 (no flush needed)", outlier_frac=a.outlier_frac)
+               l2="inputs larger than L2 (no flush needed)", outlier_frac=a.outlier_frac,
+               debug_flags=a.debug_flags)
 
     if a.impl == "reference":
         if rank != 0:
@@ -243,7 +246,8 @@ def main():
     dim = imgs[0][0].shape[1] * (8 if a.kind == "orb" else 1)
     dt = api.DESC_U8_BITS if a.kind == "orb" else api.DESC_F32
 
-    pm = api.PairMatcher(devices=[local], reserve_keypoints=n_img * a.kp)
+    pm = api.PairMatcher(devices=[local], reserve_keypoints=n_img * a.kp, debug_flags=a.debug_flags,
+                         batch_pairs=a.batch_pairs)
 
     def ingest():
         for i, (td, tx) in enumerate(pinned):

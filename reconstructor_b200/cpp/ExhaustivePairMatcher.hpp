@@ -1,0 +1,73 @@
+// ExhaustivePairMatcher.hpp -- batched replacement of SequentialReconstructor::matchFeatures(bool)
+// (Mapper/libMapper/SequentialReconstructor.cpp:199-279): ONE pm_match_all_pairs call instead of the
+// OpenMP double loop, then a `featureMatches`-shaped view (SequentialReconstructor.h:226) with both
+// (i,j) and the mirrored (j,i) entries.  Fixes the reference's unsynchronised writes to the shared
+// map and its schedule-dependent choice of which direction gets matched: query = lower image id.
+#pragma once
+
+#include <algorithm>
+#include <unordered_map>
+#include <vector>
+
+#include "CudaFeatureMatcher.hpp"
+
+namespace reconstructor::Core {
+
+struct pm_pair_hash {      // not the reference's h1 ^ h2 (SequentialReconstructor.h:51-62): (i,j)/(j,i) collide there
+  size_t operator()(const std::pair<int, int>& p) const {
+    return std::hash<long long>{}((static_cast<long long>(p.first) << 32) ^ static_cast<unsigned>(p.second));
+  }
+};
+template <class Hash = pm_pair_hash>
+using FeatureMatchesT = std::unordered_map<std::pair<int, int>, std::unordered_map<int, int>, Hash>;
+
+class ExhaustivePairMatcher {
+ public:
+  explicit ExhaustivePairMatcher(std::shared_ptr<PairMatchDevice> dev = nullptr)
+      : dev_(dev ? std::move(dev) : std::make_shared<PairMatchDevice>()) {}
+
+  // features: imgId -> features;  imgMatches: imgId -> matched image ids (FakeImgMatcher: all others).
+  // Returns a pm status; on success featureMatches holds what the reference's loop would hold.
+  template <class Hash>
+  int matchFeatures(const std::unordered_map<int, std::vector<FeaturePtr<>>>& features,
+                    const std::unordered_map<int, std::vector<int>>& imgMatches,
+                    FeatureMatchesT<Hash>& featureMatches) {
+    for (const auto& kv : features) {
+      const int rc = dev_->upload(kv.first, kv.second);
+      if (rc != PM_OK) return rc;
+    }
+    std::vector<int32_t> pairs;
+    for (const auto& kv : imgMatches)
+      for (int j : kv.second) {
+        const int i = kv.first;
+        if (i == j) continue;
+        const auto back = imgMatches.find(j);
+        const bool mirrored = back != imgMatches.end() &&
+                              std::find(back->second.begin(), back->second.end(), i) != back->second.end();
+        if (i < j || !mirrored) { pairs.push_back(i); pairs.push_back(j); }   // canonical direction once
+      }
+    pm_csr_result* res = nullptr;
+    const int rc = pm_match_all_pairs(dev_->handle(), pairs.data(), static_cast<int64_t>(pairs.size() / 2), &res);
+    if (rc != PM_OK) return rc;
+    for (int64_t p = 0; p < res->n_pairs; ++p) {
+      if (res->status[p] == PM_PAIR_DROPPED) continue;                         // .cpp:253-256
+      const int i = res->pair_ij[2 * p], j = res->pair_ij[2 * p + 1];
+      for (int64_t k = res->offsets[p]; k < res->offsets[p + 1]; ++k) {
+        if (!res->inlier[k]) continue;
+        featureMatches[{i, j}][res->q[k]] = res->t[k];                         // .cpp:259-267 / :272-275
+        featureMatches[{j, i}][res->t[k]] = res->q[k];                         // mirror, .cpp:219-227
+      }
+    }
+    last_device_ms_ = res->device_ms;
+    pm_free_result(res);
+    return PM_OK;
+  }
+  double lastDeviceMs() const { return last_device_ms_; }
+  const std::shared_ptr<PairMatchDevice>& device() const { return dev_; }
+
+ private:
+  std::shared_ptr<PairMatchDevice> dev_;
+  double last_device_ms_ = 0;
+};
+
+}  // namespace reconstructor::Core

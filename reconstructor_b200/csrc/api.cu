@@ -56,7 +56,7 @@ struct Slot {
   int cap_pairs = 0, stride = 0;
   bool mutual = false;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev_done = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+  cudaEvent_t ev_done = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_jobs = nullptr, ev_knn = nullptr;
   // device
   PairJob *d_jobs = nullptr, *d_rjobs = nullptr;
   int2 *knn_idx = nullptr, *rev_idx = nullptr;
@@ -99,7 +99,9 @@ struct Slot {
     if (ev_done) cudaEventDestroy(ev_done);
     if (ev_k0) cudaEventDestroy(ev_k0);
     if (ev_k1) cudaEventDestroy(ev_k1);
-    stream = nullptr; ev_done = ev_k0 = ev_k1 = nullptr;
+    if (ev_jobs) cudaEventDestroy(ev_jobs);
+    if (ev_knn) cudaEventDestroy(ev_knn);
+    stream = nullptr; ev_done = ev_k0 = ev_k1 = ev_jobs = ev_knn = nullptr;
   }
 };
 
@@ -131,6 +133,7 @@ struct DeviceCtx {
   std::vector<Slot> slots;
   Slot single;
   cudaStream_t ingest = nullptr;
+  cudaStream_t knn_stream = nullptr;   // all kNN kernels run back to back on this stream
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
   float* d_dump = nullptr;
 
@@ -160,6 +163,7 @@ struct DeviceCtx {
                   prop.major, prop.minor);
     num_sms = prop.multiProcessorCount;
     PM_CUDA(cudaStreamCreateWithFlags(&ingest, cudaStreamNonBlocking));
+    PM_CUDA(cudaStreamCreateWithFlags(&knn_stream, cudaStreamNonBlocking));
     PM_CUDA(cudaEventCreate(&ev_a));
     PM_CUDA(cudaEventCreate(&ev_b));
     PM_CUDA(cudaMalloc(&d_flag, sizeof(int)));
@@ -178,6 +182,7 @@ struct DeviceCtx {
     fd(raw); fd(qf); fd(tf); fd(qnorm); fd(bits); fd(xy); fd(d_flag); fd(stage); fd(d_dump);
     if (h_flag) cudaFreeHost(h_flag);
     if (ingest) cudaStreamDestroy(ingest);
+    if (knn_stream) cudaStreamDestroy(knn_stream);
     if (ev_a) cudaEventDestroy(ev_a);
     if (ev_b) cudaEventDestroy(ev_b);
   }
@@ -348,6 +353,8 @@ struct DeviceCtx {
       PM_CUDA(cudaEventCreate(&s.ev_done));
       PM_CUDA(cudaEventCreate(&s.ev_k0));
       PM_CUDA(cudaEventCreate(&s.ev_k1));
+      PM_CUDA(cudaEventCreateWithFlags(&s.ev_jobs, cudaEventDisableTiming));
+      PM_CUDA(cudaEventCreateWithFlags(&s.ev_knn, cudaEventDisableTiming));
     }
     if (pairs <= s.cap_pairs && stride <= s.stride && (!mutual || s.mutual)) return PM_OK;
     PM_CUDA(cudaStreamSynchronize(s.stream));
@@ -422,33 +429,42 @@ struct DeviceCtx {
     if (dtype != PM_DESC_U8_BITS) {
       for (int i = 0; i < n && all_integral; ++i) all_integral = job_integral[i];
     }
-    if (timed) PM_CUDA(cudaEventRecord(s.ev_k0, s.stream));
+    // The kNN kernels of all batches are serialised on one stream (they fill the machine anyway);
+    // the slot's own stream carries the small tail kernels and the D2H, overlapping the next kNN.
+    PM_CUDA(cudaEventRecord(s.ev_jobs, s.stream));
+    PM_CUDA(cudaStreamWaitEvent(knn_stream, s.ev_jobs, 0));
+    const int epi = (prm.debug_flags >> 2) & 3;
+    const int variant = (prm.debug_flags >> 1) & 1;
+    const bool use_tc = tc_ready && all_integral && !(prm.debug_flags & 1);
+    if (timed) PM_CUDA(cudaEventRecord(s.ev_k0, knn_stream));
     if (dtype == PM_DESC_U8_BITS) {
-      PM_CUDA(launch_hamming_top2(bits, words, s.d_jobs, n, max_nq, s.knn_idx, s.knn_dist, s.stride,
-                                  (prm.debug_flags >> 1) & 1, s.stream));
+      PM_CUDA(launch_hamming_top2(bits, words, s.d_jobs, n, max_nq, s.knn_idx, s.knn_dist, s.stride, variant,
+                                  knn_stream));
       s.knn_work = work * words;
-    } else if (tc_ready && all_integral && !(prm.debug_flags & 1)) {
+    } else if (use_tc) {
       PM_CUDA(launch_l2_tc(maps, qnorm, s.d_jobs, n, max_nq, s.knn_idx, s.knn_dist, s.stride, num_sms, dump,
-                           s.stream));
+                           epi, knn_stream));
       s.knn_work = work * 2.0 * dim;
     } else {
-      PM_CUDA(launch_l2_simt(raw, dim, s.d_jobs, n, max_nq, s.knn_idx, s.knn_dist, s.stride, s.stream));
+      PM_CUDA(launch_l2_simt(raw, dim, s.d_jobs, n, max_nq, s.knn_idx, s.knn_dist, s.stride, knn_stream));
       s.knn_work = work * 2.0 * dim;
     }
-    if (timed) PM_CUDA(cudaEventRecord(s.ev_k1, s.stream));
+    if (timed) PM_CUDA(cudaEventRecord(s.ev_k1, knn_stream));
     s.timed = timed;
     ++stats.kernel_launches;
     if (want_rev) {
       if (dtype == PM_DESC_U8_BITS)
-        PM_CUDA(launch_hamming_top2(bits, words, s.d_rjobs, n, max_nt, s.rev_idx, s.rev_dist, s.stride,
-                                    (prm.debug_flags >> 1) & 1, s.stream));
-      else if (tc_ready && all_integral && !(prm.debug_flags & 1))
+        PM_CUDA(launch_hamming_top2(bits, words, s.d_rjobs, n, max_nt, s.rev_idx, s.rev_dist, s.stride, variant,
+                                    knn_stream));
+      else if (use_tc)
         PM_CUDA(launch_l2_tc(maps, qnorm, s.d_rjobs, n, max_nt, s.rev_idx, s.rev_dist, s.stride, num_sms,
-                             nullptr, s.stream));
+                             nullptr, epi, knn_stream));
       else
-        PM_CUDA(launch_l2_simt(raw, dim, s.d_rjobs, n, max_nt, s.rev_idx, s.rev_dist, s.stride, s.stream));
+        PM_CUDA(launch_l2_simt(raw, dim, s.d_rjobs, n, max_nt, s.rev_idx, s.rev_dist, s.stride, knn_stream));
       ++stats.kernel_launches;
     }
+    PM_CUDA(cudaEventRecord(s.ev_knn, knn_stream));
+    PM_CUDA(cudaStreamWaitEvent(s.stream, s.ev_knn, 0));
     return PM_OK;
   }
   std::vector<char> job_integral;   // per job of the batch being built
@@ -545,7 +561,7 @@ struct DeviceCtx {
       const int rc = ensure_slot(slots[s], B, stride, mutual);
       if (rc != PM_OK) return rc;
     }
-    PM_CUDA(cudaEventRecord(ev_a, slots[0].stream));
+    PM_CUDA(cudaEventRecord(ev_a, knn_stream));
     int64_t done = 0;
     int b = 0;
     // results must be appended in pair order: retrieve slots in issue order
@@ -557,9 +573,6 @@ struct DeviceCtx {
       for (int k = 0; k < n; ++k) {
         rc = fill_job(s, k, pairs[2 * (done + k)], pairs[2 * (done + k) + 1]);
         if (rc != PM_OK) return rc;
-      }
-      if (b > 0 && b < S) {   // chain the first use of every stream behind ev_a for the device clock
-        PM_CUDA(cudaStreamWaitEvent(s.stream, ev_a, 0));
       }
       if ((rc = enqueue_knn(s, n, mutual, true)) != PM_OK) return rc;
       if ((rc = enqueue_tail(s, n, prm.do_filter != 0)) != PM_OK) return rc;

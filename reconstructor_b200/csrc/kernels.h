@@ -38,7 +38,7 @@ struct TcMaps {
 cudaError_t tc_configure();               // one-time function attributes
 cudaError_t launch_l2_tc(const TcMaps& maps, const int32_t* qnorm, const PairJob* jobs, int n_jobs,
                          int max_nq, int2* idx, float2* dist, int stride, int num_sms,
-                         float* debug_dump, cudaStream_t st);
+                         float* debug_dump, int epi, cudaStream_t st);
 
 // pack.cu
 cudaError_t launch_pack_sift(const float* raw_f32, const uint8_t* raw_u8, int n, __half* qf,

@@ -79,8 +79,9 @@ __device__ __forceinline__ void top2_push(Top2& s, float v, int col) {
   }
 }
 
-// Processes 32 consecutive columns held in registers.
-__device__ __forceinline__ void scan32(Top2& s, const uint32_t (&r)[32], int col0) {
+// Processes 32 consecutive columns held in registers (r must resolve to registers: call sites are
+// fully unrolled with compile-time offsets).
+__device__ __forceinline__ void scan32(Top2& s, const uint32_t* r, int col0) {
   float g[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k)
@@ -99,6 +100,7 @@ __device__ __forceinline__ void scan32(Top2& s, const uint32_t (&r)[32], int col
   }
 }
 
+template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 l2_top2_tc_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant__ CUtensorMap q_ext,
                   const __grid_constant__ CUtensorMap t_main, const __grid_constant__ CUtensorMap t_ext,
@@ -173,41 +175,50 @@ l2_top2_tc_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_const
     }
   } else if (warp == 1) {
     // ====================================== MMA issuer ======================================
-    if (lane == 0) {
-      uint32_t ai = 0, bi = 0, ti = 0;
-      const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int jb = item / tiles_per_job, r = item - jb * tiles_per_job;
-        const PairJob job = jobs[jb];
-        if (r * TC_ROWS >= job.nq) continue;
-        wait_bounded(a_full, ai & 1);
-        ++ai;
-        const int n_tiles = (job.nt + TC_BN - 1) / TC_BN;
-        for (int n = 0; n < n_tiles; ++n, ++bi, ++ti) {
-          const uint32_t st = bi % TC_STAGES;
-          const uint32_t as = ti & 1, use = ti >> 1;
-          wait_bounded(&b_full[st], (bi / TC_STAGES) & 1);
-          const uint32_t b_base = sB_u + st * TC_TILE_BYTES;
+    // The whole warp walks the loop (all values stay warp-uniform -> uniform registers, no
+    // R2UR round trips); one elected lane issues the MMAs and commits.
+    uint32_t ai = 0, bi = 0, ti = 0;
+    constexpr uint32_t HI128 = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO | version | SWIZZLE_128B
+    constexpr uint32_t HI32 = (256u >> 4) | (1u << 14) | (6u << 29);     // SBO | version | SWIZZLE_32B
+    const uint32_t a_lo0 = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (1u << 16);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int jb = item / tiles_per_job, r = item - jb * tiles_per_job;
+      const int job_nq = jobs[jb].nq, job_nt = jobs[jb].nt;
+      if (r * TC_ROWS >= job_nq) continue;
+      wait_bounded(a_full, ai & 1);
+      ++ai;
+      const int n_tiles = (job_nt + TC_BN - 1) / TC_BN;
+      for (int n = 0; n < n_tiles; ++n, ++bi, ++ti) {
+        const uint32_t st = bi % TC_STAGES;
+        const uint32_t as = ti & 1, use = ti >> 1;
+        wait_bounded(&b_full[st], (bi / TC_STAGES) & 1);
+        const uint32_t b_lo = b_lo0 + st * (TC_TILE_BYTES >> 4);
 #pragma unroll
-          for (int m = 0; m < TC_MT; ++m) {
-            wait_bounded(&acc_empty[as * 2 + m], (use & 1) ^ 1);
-            tc_fence_after();
-            const uint32_t a_base = sA_u + m * TC_TILE_BYTES;
+        for (int m = 0; m < TC_MT; ++m) {
+          wait_bounded(&acc_empty[as * 2 + m], (use & 1) ^ 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_lo = a_lo0 + m * (TC_TILE_BYTES >> 4);
             const uint32_t d_tmem = tmem_base + (as * 2 + m) * TC_BN;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              const uint32_t off = (k >> 2) * TC_ATOM_BYTES + (k & 3) * 32;
-              umma_f16(d_tmem, make_desc(a_base + off, 1024, 2), make_desc(b_base + off, 1024, 2),
-                       TC_IDESC, k > 0 ? 1u : 0u);
+              const uint32_t off = ((k >> 2) * TC_ATOM_BYTES + (k & 3) * 32) >> 4;
+              umma_f16(d_tmem, (static_cast<uint64_t>(HI128) << 32) | (a_lo + off),
+                       (static_cast<uint64_t>(HI128) << 32) | (b_lo + off), TC_IDESC, k > 0 ? 1u : 0u);
             }
-            umma_f16(d_tmem, make_desc(a_base + 2 * TC_ATOM_BYTES, 256, 6),
-                     make_desc(b_base + 2 * TC_ATOM_BYTES, 256, 6), TC_IDESC, 1u);
+            constexpr uint32_t xoff = (2 * TC_ATOM_BYTES) >> 4;
+            umma_f16(d_tmem, (static_cast<uint64_t>(HI32) << 32) | (a_lo + xoff),
+                     (static_cast<uint64_t>(HI32) << 32) | (b_lo + xoff), TC_IDESC, 1u);
             umma_commit(&acc_full[as * 2 + m]);
           }
-          umma_commit(&b_empty[st]);
+          __syncwarp();
         }
-        umma_commit(a_empty);
+        if (elect_one()) umma_commit(&b_empty[st]);
+        __syncwarp();
       }
+      if (elect_one()) umma_commit(a_empty);
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ======================================= epilogue =======================================
@@ -229,28 +240,63 @@ l2_top2_tc_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_const
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                (as * 2 + m) * TC_BN;
         const int valid = job.nt - n * TC_BN;          // columns of this tile that exist
-#pragma unroll
-        for (int c = 0; c < TC_BN / 32; ++c) {
-          uint32_t v[32];
+        const int col_base = n * TC_BN;
+        auto release = [&]() {                         // accumulator drained -> hand it back to the MMA warp
+          tc_fence_before();
           __syncwarp();
-          tmem_ld_32x32b_x32(taddr + c * 32, v);      // includes tcgen05.wait::ld
-          if (c == TC_BN / 32 - 1) {                   // accumulator drained -> hand it back
-            tc_fence_before();
+          if (lane == 0) mbar_arrive(&acc_empty[as * 2 + m]);
+        };
+        if constexpr (EPI == 0) {
+#pragma unroll
+          for (int c = 0; c < TC_BN / 32; ++c) {
+            uint32_t v[32];
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[as * 2 + m]);
-          }
-          if (debug_dump != nullptr && item == 0 && n == 0) {
+            tmem_ld_32x32b_x32(taddr + c * 32, v);      // includes tcgen05.wait::ld
+            if (c == TC_BN / 32 - 1) release();
+            if (debug_dump != nullptr && item == 0 && n == 0) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e)
-              debug_dump[static_cast<size_t>(m * TC_BM + quarter * 32 + lane) * TC_BN + c * 32 + e] =
-                  __uint_as_float(v[e]);
-          }
-          if (valid < (c + 1) * 32) {
+              for (int e = 0; e < 32; ++e)
+                debug_dump[static_cast<size_t>(m * TC_BM + quarter * 32 + lane) * TC_BN + c * 32 + e] =
+                    __uint_as_float(v[e]);
+            }
+            if (valid < (c + 1) * 32) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (c * 32 + e >= valid) v[e] = 0x7f800000u;
+              for (int e = 0; e < 32; ++e)
+                if (c * 32 + e >= valid) v[e] = 0x7f800000u;
+            }
+            scan32(s, v, col_base + c * 32);
           }
-          scan32(s, v, n * TC_BN + c * 32);
+        } else {
+          uint32_t va[64], vb[64];
+          __syncwarp();
+          tmem_ld_32x32b_x64_async(taddr, va);
+          if constexpr (EPI == 2) {
+            tmem_ld_32x32b_x64_async(taddr + 64, vb);   // both halves in flight
+            tmem_wait_pin(va);
+            tmem_wait_pin(vb);
+            release();
+          } else {
+            tmem_wait_pin(va);
+          }
+          if (valid < 64) {
+#pragma unroll
+            for (int e = 0; e < 64; ++e)
+              if (e >= valid) va[e] = 0x7f800000u;
+          }
+          if constexpr (EPI == 1) tmem_ld_32x32b_x64_async(taddr + 64, vb);   // lands while va is scanned
+          scan32(s, &va[0], col_base);
+          scan32(s, &va[32], col_base + 32);
+          if constexpr (EPI == 1) {
+            tmem_wait_pin(vb);
+            release();
+          }
+          if (valid < 128) {
+#pragma unroll
+            for (int e = 0; e < 64; ++e)
+              if (64 + e >= valid) vb[e] = 0x7f800000u;
+          }
+          scan32(s, &vb[0], col_base + 64);
+          scan32(s, &vb[32], col_base + 96);
         }
       }
       if (row < job.nq) {
@@ -276,21 +322,27 @@ l2_top2_tc_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_const
 }
 
 cudaError_t tc_configure() {
-  return cudaFuncSetAttribute(l2_top2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              TC_SMEM_BYTES);
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(l2_top2_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(l2_top2_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(l2_top2_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
 }
 
 cudaError_t launch_l2_tc(const TcMaps& maps, const int32_t* qnorm, const PairJob* jobs, int n_jobs,
                          int max_nq, int2* idx, float2* dist, int stride, int num_sms,
-                         float* debug_dump, cudaStream_t st) {
+                         float* debug_dump, int epi, cudaStream_t st) {
   if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
   const int tiles_per_job = (max_nq + TC_ROWS - 1) / TC_ROWS;
   const int n_items = n_jobs * tiles_per_job;
   const int grid = n_items < num_sms ? n_items : num_sms;
-  l2_top2_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(maps.q_main, maps.q_ext, maps.t_main,
-                                                             maps.t_ext, qnorm, jobs, n_jobs,
-                                                             tiles_per_job, idx, dist, stride,
-                                                             debug_dump);
+#define PM_TC_LAUNCH(E)                                                                         \
+  l2_top2_tc_kernel<E><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(                                \
+      maps.q_main, maps.q_ext, maps.t_main, maps.t_ext, qnorm, jobs, n_jobs, tiles_per_job, idx, \
+      dist, stride, debug_dump)
+  if (debug_dump != nullptr || epi == 0) PM_TC_LAUNCH(0);
+  else if (epi == 1) PM_TC_LAUNCH(1);
+  else PM_TC_LAUNCH(2);
+#undef PM_TC_LAUNCH
   return cudaGetLastError();
 }
 

@@ -53,9 +53,10 @@ def test_hamming_knn_bit_exact(knn, variant):
             assert np.array_equal(dist, knn[f"orb_{tag}_dist"])
 
 
-@pytest.mark.parametrize("force_simt", [0, 1])
+@pytest.mark.parametrize("force_simt", [0, 1, 4, 8])
 def test_l2_sift_knn_bit_exact(knn, force_simt):
-    """force_simt=0 is the tcgen05 path, 1 the fp32 SIMT kernel; both must equal cv::BFMatcher."""
+    """flags 0/4/8 are the tcgen05 path (three epilogue variants), 1 the fp32 SIMT kernel; all must
+    equal cv::BFMatcher."""
     with api.PairMatcher(debug_flags=force_simt) as pm:
         _load3(pm, knn, "sift")
         for tag, a, b in (("01", 0, 1), ("02", 0, 2), ("12", 1, 2)):
@@ -122,13 +123,15 @@ def test_l2_sift_extreme_values_exact():
     assert np.array_equal(dist, np.sqrt(o2).astype(np.float32))
 
 
-@pytest.mark.parametrize("kind", ["orb", "sift", "superpoint"])
+@pytest.mark.parametrize("kind", ["orb", "sift", "sift-epi1", "sift-epi2", "superpoint"])
 def test_knn_ragged_and_tiny(kind):
     """Ragged sizes (not multiples of any tile), 1-row and 2-row train sets, empty images."""
+    flags = {"sift-epi1": 4, "sift-epi2": 8}.get(kind, 0)
+    kind = kind.split("-")[0]
     w = synth.World(kind, 700, seed=11)
     full = [w.image(i, 4)[0] for i in range(2)]
-    cases = [(1, 1), (5, 1), (3, 2), (129, 127), (257, 300), (700, 513), (511, 700)]
-    with api.PairMatcher() as pm:
+    cases = [(1, 1), (5, 1), (3, 2), (129, 127), (257, 300), (700, 513), (511, 700), (300, 65), (260, 190)]
+    with api.PairMatcher(debug_flags=flags) as pm:
         for nq, nt in cases:
             q, t = full[0][:nq], full[1][:nt]
             pm.set_image(0, q); pm.set_image(1, t)
@@ -338,7 +341,7 @@ def test_errors_are_reported_not_thrown(knn):
 def test_full_size_8192_pair(kind):
     w = synth.World(kind, 8192, seed=0xB200)
     imgs = [w.image(i, 100)[:2] for i in range(3)]
-    flags = [0, 1] if kind == "sift" else [0, 2]
+    flags = [0, 1, 4, 8] if kind == "sift" else [0, 2]
     outs = []
     for f in flags:
         with api.PairMatcher(debug_flags=f) as pm:
@@ -348,7 +351,8 @@ def test_full_size_8192_pair(kind):
             if f == 0:
                 res = pm.match_all_pairs()
     # tensor path == SIMT path (sift) / popc == carry-save popc (orb), bit for bit
-    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    for o in outs[1:]:
+        assert np.array_equal(outs[0][0], o[0]) and np.array_equal(outs[0][1], o[1])
     # against the oracle on the same pair
     if kind == "orb":
         oi, od = orc.knn2_hamming(imgs[0][0], imgs[1][0]); od = od.astype(np.float32)
