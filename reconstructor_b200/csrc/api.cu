@@ -37,12 +37,73 @@ struct Image {
 
 constexpr int kTmpA = INT32_MIN, kTmpB = INT32_MIN + 1;
 
+// Pinned host buffers are expensive to create, so results recycle them through a pool that
+// outlives the handle if a result is freed late.
+struct PinnedPool {
+  std::mutex mu;
+  std::vector<std::pair<void*, size_t>> free_list;
+  void* acquire(size_t bytes, size_t* got) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      size_t best = free_list.size();
+      for (size_t i = 0; i < free_list.size(); ++i)
+        if (free_list[i].second >= bytes && (best == free_list.size() || free_list[i].second < free_list[best].second))
+          best = i;
+      if (best != free_list.size()) {
+        auto pr = free_list[best];
+        free_list.erase(free_list.begin() + best);
+        *got = pr.second;
+        return pr.first;
+      }
+    }
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    *got = bytes;
+    return p;
+  }
+  void release(void* p, size_t bytes) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(mu);
+    free_list.emplace_back(p, bytes);
+  }
+  ~PinnedPool() {
+    for (auto& pr : free_list) cudaFreeHost(pr.first);
+  }
+};
+
 struct Result {  // owner of a pm_csr_result
   pm_csr_result pub{};
-  std::vector<int32_t> pair_ij, q, t, status, n_inliers, iters;
+  std::vector<int32_t> pair_ij, status, n_inliers, iters;
   std::vector<int64_t> offsets;
-  std::vector<uint8_t> inlier;
   std::vector<double> F;
+  // match arrays live in pinned memory: the device compacted arrays are copied straight into them
+  std::shared_ptr<PinnedPool> pool;
+  int32_t *q = nullptr, *t = nullptr;
+  uint8_t* inlier = nullptr;
+  size_t q_bytes = 0, t_bytes = 0, inl_bytes = 0;
+  int64_t cap = 0, size = 0;
+
+  bool reserve(int64_t want) {      // caller guarantees no copy into the old buffers is in flight
+    if (want <= cap) return true;
+    const int64_t nc = std::max<int64_t>(want, cap * 2);
+    size_t gq = 0, gt = 0, gi = 0;
+    int32_t* nq = static_cast<int32_t*>(pool->acquire(4 * static_cast<size_t>(nc), &gq));
+    int32_t* nt = static_cast<int32_t*>(pool->acquire(4 * static_cast<size_t>(nc), &gt));
+    uint8_t* ni = static_cast<uint8_t*>(pool->acquire(static_cast<size_t>(nc), &gi));
+    if (!nq || !nt || !ni) return false;
+    if (size > 0) {
+      std::memcpy(nq, q, 4 * static_cast<size_t>(size));
+      std::memcpy(nt, t, 4 * static_cast<size_t>(size));
+      std::memcpy(ni, inlier, static_cast<size_t>(size));
+    }
+    pool->release(q, q_bytes); pool->release(t, t_bytes); pool->release(inlier, inl_bytes);
+    q = nq; t = nt; inlier = ni; q_bytes = gq; t_bytes = gt; inl_bytes = gi;
+    cap = std::min<int64_t>({static_cast<int64_t>(gq / 4), static_cast<int64_t>(gt / 4), static_cast<int64_t>(gi)});
+    return true;
+  }
+  ~Result() {
+    if (pool) { pool->release(q, q_bytes); pool->release(t, t_bytes); pool->release(inlier, inl_bytes); }
+  }
 };
 
 #define PM_CUDA(call)                                                                   \
@@ -130,6 +191,7 @@ struct DeviceCtx {
   size_t stage_bytes = 0;
 
   std::unordered_map<int, Image> images;
+  std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
   std::vector<Slot> slots;
   Slot single;
   cudaStream_t ingest = nullptr;
@@ -389,9 +451,6 @@ struct DeviceCtx {
     PM_CUDA(cudaMallocHost(&s.h_jobs, sizeof(PairJob) * pairs));
     PM_CUDA(cudaMallocHost(&s.h_rjobs, sizeof(PairJob) * pairs));
     PM_CUDA(cudaMallocHost(&s.h_offsets, 8 * (pairs + 1)));
-    PM_CUDA(cudaMallocHost(&s.h_q, 4 * ps));
-    PM_CUDA(cudaMallocHost(&s.h_t, 4 * ps));
-    PM_CUDA(cudaMallocHost(&s.h_mask, ps));
     PM_CUDA(cudaMallocHost(&s.h_F, 72 * pairs));
     PM_CUDA(cudaMallocHost(&s.h_status, 4 * pairs));
     PM_CUDA(cudaMallocHost(&s.h_ninl, 4 * pairs));
@@ -506,19 +565,27 @@ struct DeviceCtx {
     return PM_OK;
   }
 
-  // Waits for the batch in slot s, pulls its compacted matches and appends to the result.
+  // Waits for the batch's per-pair metadata, then queues the D2H of its compacted matches straight
+  // into the (pinned) result arrays; nothing is copied on the host.
   int retrieve(Slot& s, Result& R) {
     if (!s.busy) return PM_OK;
     PM_CUDA(cudaEventSynchronize(s.ev_done));
     const int n = s.n_jobs;
     const int64_t total = s.h_offsets[n];
+    const int64_t base = R.size;
+    if (base + total > R.cap) {
+      // growing moves the arrays: drain every copy that targets the old ones first
+      for (auto& o : slots) if (o.stream) PM_CUDA(cudaStreamSynchronize(o.stream));
+      if (single.stream) PM_CUDA(cudaStreamSynchronize(single.stream));
+      if (!R.reserve(base + total)) return fail(PM_ERR_OOM, "pinned result buffers (%lld matches)", static_cast<long long>(base + total));
+    }
     if (total > 0) {
-      PM_CUDA(cudaMemcpyAsync(s.h_q, s.out_q, 4 * total, cudaMemcpyDeviceToHost, s.stream));
-      PM_CUDA(cudaMemcpyAsync(s.h_t, s.out_t, 4 * total, cudaMemcpyDeviceToHost, s.stream));
-      PM_CUDA(cudaMemcpyAsync(s.h_mask, s.out_mask, total, cudaMemcpyDeviceToHost, s.stream));
-      PM_CUDA(cudaStreamSynchronize(s.stream));
+      PM_CUDA(cudaMemcpyAsync(R.q + base, s.out_q, 4 * total, cudaMemcpyDeviceToHost, s.stream));
+      PM_CUDA(cudaMemcpyAsync(R.t + base, s.out_t, 4 * total, cudaMemcpyDeviceToHost, s.stream));
+      PM_CUDA(cudaMemcpyAsync(R.inlier + base, s.out_mask, total, cudaMemcpyDeviceToHost, s.stream));
       stats.d2h_bytes += 9 * total;
     }
+    R.size = base + total;
     if (s.timed) {
       float ms = 0;
       PM_CUDA(cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
@@ -526,10 +593,6 @@ struct DeviceCtx {
       stats.knn_launches += 1;
       stats.knn_work += s.knn_work;
     }
-    const int64_t base = static_cast<int64_t>(R.q.size());
-    R.q.insert(R.q.end(), s.h_q, s.h_q + total);
-    R.t.insert(R.t.end(), s.h_t, s.h_t + total);
-    R.inlier.insert(R.inlier.end(), s.h_mask, s.h_mask + total);
     for (int k = 0; k < n; ++k) {
       const int64_t p = s.first_pair + k;
       R.offsets[p + 1] = base + s.h_offsets[k + 1];
@@ -554,13 +617,15 @@ struct DeviceCtx {
     const int stride = (maxn + 255) / 256 * 256;
     int B = prm.batch_pairs > 0 ? prm.batch_pairs : static_cast<int>(std::clamp<int64_t>((2 << 20) / stride, 32, 2048));
     B = static_cast<int>(std::min<int64_t>(B, n_pairs));
-    const int S = n_pairs > B ? 3 : 1;
+    const int S = n_pairs > B ? 4 : 1;
     const bool mutual = prm.unique_mode == PM_MUTUAL_NN;
     if (static_cast<int>(slots.size()) < S) slots.resize(S);
     for (int s = 0; s < S; ++s) {
       const int rc = ensure_slot(slots[s], B, stride, mutual);
       if (rc != PM_OK) return rc;
     }
+    if (!R.reserve(R.size + std::max<int64_t>(1024, n_pairs * static_cast<int64_t>(stride) * 3 / 10)))
+      return fail(PM_ERR_OOM, "pinned result buffers");
     PM_CUDA(cudaEventRecord(ev_a, knn_stream));
     int64_t done = 0;
     int b = 0;
@@ -586,7 +651,7 @@ struct DeviceCtx {
       const int rc = retrieve(s, R);
       if (rc != PM_OK) return rc;
     }
-    // device clock: from ev_a to the completion of every stream
+    // device clock: from ev_a to the completion of every stream (incl. the last D2H copies)
     for (int s = 1; s < S; ++s) {
       PM_CUDA(cudaEventRecord(slots[s].ev_done, slots[s].stream));
       PM_CUDA(cudaStreamWaitEvent(slots[0].stream, slots[s].ev_done, 0));
@@ -771,19 +836,21 @@ static int pair_single(pm_context* h, DeviceCtx& d, int i, int j, bool do_filter
   if ((rc = d.enqueue_tail(s, 1, do_filter)) != PM_OK) return h->from(d, rc);
   s.busy = true; s.n_jobs = 1; s.first_pair = 0; s.timed = false;
   Result R;
+  R.pool = d.pool;
   R.offsets.assign(2, 0); R.status.assign(1, 0); R.n_inliers.assign(1, 0); R.iters.assign(1, 0);
   R.F.assign(9, 0.0);
   if ((rc = d.retrieve(s, R)) != PM_OK) return h->from(d, rc);
-  const int m = static_cast<int>(R.q.size());
+  if (cudaStreamSynchronize(s.stream) != cudaSuccess) return h->from(d, d.fail(PM_ERR_CUDA, "pair D2H failed"));
+  const int m = static_cast<int>(R.size);
   out->n_matches = m;
   out->status = R.status[0];
   out->n_inliers = R.status[0] == PM_PAIR_DROPPED ? 0 : R.n_inliers[0];
   out->ransac_iters = R.iters[0];
   std::memcpy(out->F, R.F.data(), 72);
   if (m > 0) {
-    if (out->q) std::memcpy(out->q, R.q.data(), 4 * static_cast<size_t>(m));
-    if (out->t) std::memcpy(out->t, R.t.data(), 4 * static_cast<size_t>(m));
-    if (out->inlier) std::memcpy(out->inlier, R.inlier.data(), static_cast<size_t>(m));
+    if (out->q) std::memcpy(out->q, R.q, 4 * static_cast<size_t>(m));
+    if (out->t) std::memcpy(out->t, R.t, 4 * static_cast<size_t>(m));
+    if (out->inlier) std::memcpy(out->inlier, R.inlier, static_cast<size_t>(m));
   }
   return PM_OK;
 }
@@ -854,6 +921,7 @@ int pm_match_all_pairs(pm_handle h, const int32_t* pairs, int64_t n_pairs, pm_cs
   *out = nullptr;
   std::lock_guard<std::mutex> lk(h->mu);
   auto R = std::make_unique<Result>();
+  R->pool = h->devs[0]->pool;
   if (!pairs) {   // all i < j over the images set so far: the FakeImgMatcher pair list (ImageMatcher.cpp:6-24)
     std::vector<int> ids;
     for (auto& kv : h->devs[0]->images)
@@ -884,6 +952,7 @@ int pm_match_all_pairs(pm_handle h, const int32_t* pairs, int64_t n_pairs, pm_cs
     for (int k = 0; k <= nd; ++k) lo[k] = n_pairs * k / nd;
     for (int k = 0; k < nd; ++k) {
       part[k] = std::make_unique<Result>();
+      part[k]->pool = h->devs[k]->pool;
       const int64_t n = lo[k + 1] - lo[k];
       part[k]->offsets.assign(n + 1, 0);
       part[k]->status.assign(n, 0); part[k]->n_inliers.assign(n, 0); part[k]->iters.assign(n, 0);
@@ -897,10 +966,14 @@ int pm_match_all_pairs(pm_handle h, const int32_t* pairs, int64_t n_pairs, pm_cs
       if (rcs[k] != PM_OK) return h->from(*h->devs[k], rcs[k]);
     for (int k = 0; k < nd; ++k) {
       Result& P = *part[k];
-      const int64_t base = static_cast<int64_t>(R->q.size());
-      R->q.insert(R->q.end(), P.q.begin(), P.q.end());
-      R->t.insert(R->t.end(), P.t.begin(), P.t.end());
-      R->inlier.insert(R->inlier.end(), P.inlier.begin(), P.inlier.end());
+      const int64_t base = R->size;
+      if (!R->reserve(base + P.size)) return h->fail(PM_ERR_OOM, "pinned result buffers");
+      if (P.size > 0) {
+        std::memcpy(R->q + base, P.q, 4 * static_cast<size_t>(P.size));
+        std::memcpy(R->t + base, P.t, 4 * static_cast<size_t>(P.size));
+        std::memcpy(R->inlier + base, P.inlier, static_cast<size_t>(P.size));
+      }
+      R->size = base + P.size;
       const int64_t n = lo[k + 1] - lo[k];
       for (int64_t p = 0; p < n; ++p) {
         R->offsets[lo[k] + p + 1] = base + P.offsets[p + 1];
@@ -915,7 +988,7 @@ int pm_match_all_pairs(pm_handle h, const int32_t* pairs, int64_t n_pairs, pm_cs
   R->pub.n_pairs = n_pairs;
   R->pub.pair_ij = R->pair_ij.data();
   R->pub.offsets = R->offsets.data();
-  R->pub.q = R->q.data(); R->pub.t = R->t.data(); R->pub.inlier = R->inlier.data();
+  R->pub.q = R->q; R->pub.t = R->t; R->pub.inlier = R->inlier;
   R->pub.F = R->F.data(); R->pub.status = R->status.data();
   R->pub.n_inliers = R->n_inliers.data(); R->pub.ransac_iters = R->iters.data();
   R->pub.device_ms = ms;

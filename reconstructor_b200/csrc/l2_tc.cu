@@ -31,7 +31,6 @@
 
 namespace pm {
 
-static constexpr int TC_THREADS = 384;
 static constexpr int TC_BM = 128;             // rows per m-tile (UMMA M)
 static constexpr int TC_MT = 2;               // m-tiles per CTA
 static constexpr int TC_ROWS = TC_BM * TC_MT; // query rows per work item
@@ -42,7 +41,11 @@ static constexpr int TC_EXT_BYTES = TC_BM * 32;                   // 128 rows x 
 static constexpr int TC_TILE_BYTES = 2 * TC_ATOM_BYTES + TC_EXT_BYTES;   // 36 KB
 static constexpr int TC_SMEM_A = TC_MT * TC_TILE_BYTES;           // 72 KB
 static constexpr int TC_SMEM_B = TC_STAGES * TC_TILE_BYTES;       // 144 KB
-static constexpr int TC_SMEM_BYTES = TC_SMEM_A + TC_SMEM_B + 1024 /*align slack*/ + 256 /*barriers*/;
+static constexpr int TC_XCHG_BYTES = 8 * 32 * 16;               // top-2 hand-over between column-split warps
+static constexpr int TC_SMEM_BYTES = TC_SMEM_A + TC_SMEM_B + 1024 /*align slack*/ + 256 /*barriers*/ + TC_XCHG_BYTES;
+// EPI 0..2: 8 epilogue warps (one per m-tile x lane quarter); EPI 3: 16 epilogue warps, the two
+// warps of a (m-tile, quarter) split the 128 columns of a tile in halves.
+__host__ __device__ constexpr int tc_threads(int epi) { return epi == 3 ? 640 : 384; }
 static constexpr uint32_t TC_TMEM_COLS = 512;
 
 // kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, N=128, M=128.
@@ -101,7 +104,7 @@ __device__ __forceinline__ void scan32(Top2& s, const uint32_t* r, int col0) {
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(tc_threads(EPI), 1)
 l2_top2_tc_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant__ CUtensorMap q_ext,
                   const __grid_constant__ CUtensorMap t_main, const __grid_constant__ CUtensorMap t_ext,
                   const int32_t* __restrict__ qnorm, const PairJob* __restrict__ jobs, int n_jobs,
@@ -119,6 +122,8 @@ l2_top2_tc_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_const
   uint64_t* acc_full = bars + 2 + 2 * TC_STAGES;    // [2 stages][2 m-tiles]
   uint64_t* acc_empty = acc_full + 4;               // [2][2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 4);
+  float4* xchg = reinterpret_cast<float4*>(smem + TC_SMEM_A + TC_SMEM_B + 256);
+  constexpr uint32_t kEpiArrivals = EPI == 3 ? 8 : 4;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -127,7 +132,7 @@ l2_top2_tc_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_const
     tma_prefetch_desc(&t_main); tma_prefetch_desc(&t_ext);
     mbar_init(a_full, 1); mbar_init(a_empty, 1);
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 4; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiArrivals); }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -222,7 +227,8 @@ l2_top2_tc_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_const
     }
   } else if (warp >= 4) {
     // ======================================= epilogue =======================================
-    const int m = (warp - 4) >> 2, quarter = warp & 3;
+    const int m = ((warp - 4) >> 2) & 1, quarter = warp & 3;
+    const int half = (warp - 4) >> 3;                 // EPI 3 only: which 64-column half of a tile
     uint32_t ti = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int jb = item / tiles_per_job, r = item - jb * tiles_per_job;
@@ -246,7 +252,22 @@ l2_top2_tc_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_const
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[as * 2 + m]);
         };
-        if constexpr (EPI == 0) {
+        if constexpr (EPI == 3) {
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            const int coff = half * 64 + c * 32;
+            __syncwarp();
+            tmem_ld_32x32b_x32(taddr + coff, v);        // includes tcgen05.wait::ld
+            if (c == 1) release();
+            if (valid < coff + 32) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e)
+                if (coff + e >= valid) v[e] = 0x7f800000u;
+            }
+            scan32(s, v, col_base + coff);
+          }
+        } else if constexpr (EPI == 0) {
 #pragma unroll
           for (int c = 0; c < TC_BN / 32; ++c) {
             uint32_t v[32];
@@ -299,7 +320,33 @@ l2_top2_tc_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_const
           scan32(s, &vb[32], col_base + 96);
         }
       }
-      if (row < job.nq) {
+      if constexpr (EPI == 3) {
+        // the two column-split warps of this (m-tile, quarter) merge their top-2 through smem
+        float4* slot = xchg + ((m * 4 + quarter) * 32 + lane);
+        const int bar_id = 1 + m * 4 + quarter;
+        if (half == 1) *slot = make_float4(s.m1, __int_as_float(s.i1), s.m2, __int_as_float(s.i2));
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        if (half == 0) {
+          const float4 o = *slot;
+          const float om1 = o.x, om2 = o.z;
+          const int oi1 = __float_as_int(o.y), oi2 = __float_as_int(o.w);
+          // ordered by (value, index); each list is already sorted and indices are distinct
+          auto less = [](float va, int ia, float vb, int ib) { return va < vb || (va == vb && ia < ib); };
+          Top2 t;
+          if (oi1 >= 0 && (s.i1 < 0 || less(om1, oi1, s.m1, s.i1))) {
+            t.m1 = om1; t.i1 = oi1;
+            if (oi2 >= 0 && (s.i1 < 0 || less(om2, oi2, s.m1, s.i1))) { t.m2 = om2; t.i2 = oi2; }
+            else { t.m2 = s.m1; t.i2 = s.i1; }
+          } else {
+            t.m1 = s.m1; t.i1 = s.i1;
+            if (oi1 >= 0 && (s.i2 < 0 || less(om1, oi1, s.m2, s.i2))) { t.m2 = om1; t.i2 = oi1; }
+            else { t.m2 = s.m2; t.i2 = s.i2; }
+          }
+          s = t;
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+      }
+      if ((EPI != 3 || half == 0) && row < job.nq) {
         const float na = static_cast<float>(qnorm[job.q_row + row]);
         int2 oi;
         float2 od;
@@ -325,6 +372,7 @@ cudaError_t tc_configure() {
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(l2_top2_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(l2_top2_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(l2_top2_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) != cudaSuccess) return e;
   return cudaFuncSetAttribute(l2_top2_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
 }
 
@@ -336,12 +384,13 @@ cudaError_t launch_l2_tc(const TcMaps& maps, const int32_t* qnorm, const PairJob
   const int n_items = n_jobs * tiles_per_job;
   const int grid = n_items < num_sms ? n_items : num_sms;
 #define PM_TC_LAUNCH(E)                                                                         \
-  l2_top2_tc_kernel<E><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(                                \
+  l2_top2_tc_kernel<E><<<grid, tc_threads(E), TC_SMEM_BYTES, st>>>(                             \
       maps.q_main, maps.q_ext, maps.t_main, maps.t_ext, qnorm, jobs, n_jobs, tiles_per_job, idx, \
       dist, stride, debug_dump)
   if (debug_dump != nullptr || epi == 0) PM_TC_LAUNCH(0);
   else if (epi == 1) PM_TC_LAUNCH(1);
-  else PM_TC_LAUNCH(2);
+  else if (epi == 2) PM_TC_LAUNCH(2);
+  else PM_TC_LAUNCH(3);
 #undef PM_TC_LAUNCH
   return cudaGetLastError();
 }

@@ -236,7 +236,7 @@ __device__ __forceinline__ float residual(const double* F, float2 q1, float2 q2,
   return static_cast<float>(e1 > e2 ? e1 : e2);
 }
 
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, 2)
 fmat_ransac_kernel(const float2* __restrict__ pts1, const float2* __restrict__ pts2,
                    const int32_t* __restrict__ count, int stride, RansacDev prm,
                    uint8_t* __restrict__ mask, double* __restrict__ F_out,

@@ -3,8 +3,8 @@
 # list of the bench and one ncu --set full capture of the tensor kernel.
 mkdir -p gpurun_out
 PY="python -m pytest tests/test_gpu_parity.py -q --timeout 300 -p no:cacheprovider"
-timeout 900 $PY -k "sift or full_size" > gpurun_out/tests_tc.log 2>&1; echo "tc tests exit $?"; tail -4 gpurun_out/tests_tc.log
-for f in 0 4 8; do
+timeout 900 $PY > gpurun_out/tests_tc.log 2>&1; echo "tc tests exit $?"; tail -4 gpurun_out/tests_tc.log
+for f in ${FLAG_LIST:-4 12}; do
   timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-e2e --debug-flags $f > gpurun_out/bench_f$f.log 2>gpurun_out/bench_f$f.err; echo "bench flags=$f exit $?"
   python - <<PYEOF
 import json
@@ -14,7 +14,7 @@ try:
 except Exception as e: print("parse fail", e)
 PYEOF
 done
-BEST=${BEST_FLAGS:-4}
+BEST=${BEST_FLAGS:-12}
 CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --debug-flags $BEST"
 $CMD > gpurun_out/plain_launches.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
