@@ -231,6 +231,7 @@ struct DeviceCtx {
     PM_CUDA(cudaMalloc(&d_flag, sizeof(int)));
     PM_CUDA(cudaMallocHost(&h_flag, sizeof(int)));
     PM_CUDA(tc_configure());
+    PM_CUDA(tc2_configure());
     stats.device_id = dev;
     return PM_OK;
   }
@@ -492,7 +493,7 @@ struct DeviceCtx {
     // the slot's own stream carries the small tail kernels and the D2H, overlapping the next kNN.
     PM_CUDA(cudaEventRecord(s.ev_jobs, s.stream));
     PM_CUDA(cudaStreamWaitEvent(knn_stream, s.ev_jobs, 0));
-    const int epi = (prm.debug_flags >> 2) & 3;
+    const int epi = (prm.debug_flags >> 2) & 7;
     const int variant = (prm.debug_flags >> 1) & 1;
     const bool use_tc = tc_ready && all_integral && !(prm.debug_flags & 1);
     if (timed) PM_CUDA(cudaEventRecord(s.ev_k0, knn_stream));
@@ -501,8 +502,12 @@ struct DeviceCtx {
                                   knn_stream));
       s.knn_work = work * words;
     } else if (use_tc) {
-      PM_CUDA(launch_l2_tc(maps, qnorm, s.d_jobs, n, max_nq, s.knn_idx, s.knn_dist, s.stride, num_sms, dump,
-                           epi, knn_stream));
+      if (epi >= 5 && !dump)
+        PM_CUDA(launch_l2_tc2(maps, qnorm, s.d_jobs, n, max_nq, s.knn_idx, s.knn_dist, s.stride, num_sms, epi == 6,
+                              knn_stream));
+      else
+        PM_CUDA(launch_l2_tc(maps, qnorm, s.d_jobs, n, max_nq, s.knn_idx, s.knn_dist, s.stride, num_sms, dump,
+                             epi, knn_stream));
       s.knn_work = work * 2.0 * dim;
     } else {
       PM_CUDA(launch_l2_simt(raw, dim, s.d_jobs, n, max_nq, s.knn_idx, s.knn_dist, s.stride, knn_stream));
@@ -516,8 +521,12 @@ struct DeviceCtx {
         PM_CUDA(launch_hamming_top2(bits, words, s.d_rjobs, n, max_nt, s.rev_idx, s.rev_dist, s.stride, variant,
                                     knn_stream));
       else if (use_tc)
-        PM_CUDA(launch_l2_tc(maps, qnorm, s.d_rjobs, n, max_nt, s.rev_idx, s.rev_dist, s.stride, num_sms,
-                             nullptr, epi, knn_stream));
+        if (epi >= 5)
+          PM_CUDA(launch_l2_tc2(maps, qnorm, s.d_rjobs, n, max_nt, s.rev_idx, s.rev_dist, s.stride, num_sms, 0,
+                                knn_stream));
+        else
+          PM_CUDA(launch_l2_tc(maps, qnorm, s.d_rjobs, n, max_nt, s.rev_idx, s.rev_dist, s.stride, num_sms,
+                               nullptr, epi, knn_stream));
       else
         PM_CUDA(launch_l2_simt(raw, dim, s.d_rjobs, n, max_nt, s.rev_idx, s.rev_dist, s.stride, knn_stream));
       ++stats.kernel_launches;

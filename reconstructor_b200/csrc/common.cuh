@@ -55,6 +55,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or
+// the hint expires), so a waiting warp does not burn issue slots polling.
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(0x989680u)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }

@@ -40,6 +40,11 @@ cudaError_t launch_l2_tc(const TcMaps& maps, const int32_t* qnorm, const PairJob
                          int max_nq, int2* idx, float2* dist, int stride, int num_sms,
                          float* debug_dump, int epi, cudaStream_t st);
 
+// K2, CTA-pair version -- l2_tc2.cu (tcgen05 cta_group::2)
+cudaError_t tc2_configure();
+cudaError_t launch_l2_tc2(const TcMaps& maps, const int32_t* qnorm, const PairJob* jobs, int n_jobs, int max_nq,
+                          int2* idx, float2* dist, int stride, int num_sms, int probe, cudaStream_t st);
+
 // pack.cu
 cudaError_t launch_pack_sift(const float* raw_f32, const uint8_t* raw_u8, int n, __half* qf,
                              __half* tf, int32_t* qnorm, float* raw_out, int* not_integral,

@@ -45,7 +45,7 @@ static constexpr int TC_XCHG_BYTES = 8 * 32 * 16;               // top-2 hand-ov
 static constexpr int TC_SMEM_BYTES = TC_SMEM_A + TC_SMEM_B + 1024 /*align slack*/ + 256 /*barriers*/ + TC_XCHG_BYTES;
 // EPI 0..2: 8 epilogue warps (one per m-tile x lane quarter); EPI 3: 16 epilogue warps, the two
 // warps of a (m-tile, quarter) split the 128 columns of a tile in halves.
-__host__ __device__ constexpr int tc_threads(int epi) { return epi == 3 ? 640 : 384; }
+__host__ __device__ constexpr int tc_threads(int epi) { return epi >= 3 ? 640 : 384; }
 static constexpr uint32_t TC_TMEM_COLS = 512;
 
 // kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, N=128, M=128.
@@ -82,8 +82,46 @@ __device__ __forceinline__ void top2_push(Top2& s, float v, int col) {
   }
 }
 
+// One group of 4 columns whose minimum g is known to be below s.m2.  Common case: exactly one
+// element of the group enters the top-2 -- locate the first element equal to g (lowest column on
+// ties), insert it with two min/max and two selects, and check with the group's second-smallest
+// value that nothing else qualifies.  Otherwise (rare) redo the group element by element.
+__device__ __forceinline__ void group4_insert(Top2& s, float v0, float v1, float v2, float v3, float g,
+                                              int col) {
+  int pos = 3;
+  pos = v2 == g ? 2 : pos;
+  pos = v1 == g ? 1 : pos;
+  pos = v0 == g ? 0 : pos;
+  const float second = fminf(fmaxf(fminf(v0, v1), fminf(v2, v3)),
+                             fminf(fmaxf(v0, v1), fmaxf(v2, v3)));
+  const float nm2 = fmaxf(g, s.m1);                 // g < s.m2  =>  new second = max(g, old first)
+  if (second < nm2) {                               // another element also enters: generic path
+    top2_push(s, v0, col); top2_push(s, v1, col + 1); top2_push(s, v2, col + 2); top2_push(s, v3, col + 3);
+  } else {
+    const bool first = g < s.m1;
+    const int c = col + pos;
+    s.i2 = first ? s.i1 : c;
+    s.i1 = first ? c : s.i1;
+    s.m2 = nm2;
+    s.m1 = fminf(g, s.m1);
+  }
+}
+
+// Rare generic path of a group (two or more elements enter the top-2); kept out of line so the hot
+// code stays small in the instruction cache.
+__device__ __noinline__ void group4_generic(Top2* sp, float v0, float v1, float v2, float v3, int col) {
+  Top2 s = *sp;
+  top2_push(s, v0, col); top2_push(s, v1, col + 1); top2_push(s, v2, col + 2); top2_push(s, v3, col + 3);
+  *sp = s;
+}
+
 // Processes 32 consecutive columns held in registers (r must resolve to registers: call sites are
 // fully unrolled with compile-time offsets).
+//   MODE 0: nested tests, element-wise inserts (baseline)
+//   MODE 1: nested tests, single-insert group body
+//   MODE 2: per-lane hit mask over the 8 groups, then one shared group body per set bit -- replaces
+//           the chain of 8 dependent test-and-branch steps by independent compares plus a short loop
+template <int MODE = 0>
 __device__ __forceinline__ void scan32(Top2& s, const uint32_t* r, int col0) {
   float g[8];
 #pragma unroll
@@ -93,17 +131,66 @@ __device__ __forceinline__ void scan32(Top2& s, const uint32_t* r, int col0) {
   const float cm = fminf(fminf(fminf(g[0], g[1]), fminf(g[2], g[3])),
                          fminf(fminf(g[4], g[5]), fminf(g[6], g[7])));
   if (cm < s.m2) {
+    if constexpr (MODE == 2) {
+      uint32_t mask = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if (g[k] < s.m2) {
+      for (int k = 0; k < 8; ++k) mask |= (g[k] < s.m2 ? 1u : 0u) << k;
+      do {
+        const int k = __ffs(mask) - 1;
+        mask &= mask - 1;
+        float v0, v1, v2, v3, gk;
+        switch (k) {
+#define PM_CASE(K)                                                                               \
+  case K:                                                                                        \
+    v0 = __uint_as_float(r[4 * K]); v1 = __uint_as_float(r[4 * K + 1]);                           \
+    v2 = __uint_as_float(r[4 * K + 2]); v3 = __uint_as_float(r[4 * K + 3]); gk = g[K];            \
+    break;
+          PM_CASE(0) PM_CASE(1) PM_CASE(2) PM_CASE(3) PM_CASE(4) PM_CASE(5) PM_CASE(6)
+          default:
+            v0 = __uint_as_float(r[28]); v1 = __uint_as_float(r[29]);
+            v2 = __uint_as_float(r[30]); v3 = __uint_as_float(r[31]); gk = g[7];
+            break;
+#undef PM_CASE
+        }
+        if (gk < s.m2) {                      // an earlier insert of this loop may have tightened m2
+          const int col = col0 + 4 * k;
+          int pos = 3;
+          pos = v2 == gk ? 2 : pos;
+          pos = v1 == gk ? 1 : pos;
+          pos = v0 == gk ? 0 : pos;
+          const float second = fminf(fmaxf(fminf(v0, v1), fminf(v2, v3)),
+                                     fminf(fmaxf(v0, v1), fmaxf(v2, v3)));
+          const float nm2 = fmaxf(gk, s.m1);
+          if (second < nm2) {
+            group4_generic(&s, v0, v1, v2, v3, col);
+          } else {
+            const bool first = gk < s.m1;
+            const int c = col + pos;
+            s.i2 = first ? s.i1 : c;
+            s.i1 = first ? c : s.i1;
+            s.m2 = nm2;
+            s.m1 = fminf(gk, s.m1);
+          }
+        }
+      } while (mask);
+    } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) top2_push(s, __uint_as_float(r[4 * k + e]), col0 + 4 * k + e);
+      for (int k = 0; k < 8; ++k) {
+        if (g[k] < s.m2) {
+          if constexpr (MODE == 1) {
+            group4_insert(s, __uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]),
+                          __uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3]), g[k], col0 + 4 * k);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) top2_push(s, __uint_as_float(r[4 * k + e]), col0 + 4 * k + e);
+          }
+        }
       }
     }
   }
 }
 
-template <int EPI>
+template <int EPI, int SCAN = (EPI == 3 ? 2 : 0)>
 __global__ void __launch_bounds__(tc_threads(EPI), 1)
 l2_top2_tc_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant__ CUtensorMap q_ext,
                   const __grid_constant__ CUtensorMap t_main, const __grid_constant__ CUtensorMap t_ext,
@@ -123,7 +210,7 @@ l2_top2_tc_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_const
   uint64_t* acc_empty = acc_full + 4;               // [2][2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 4);
   float4* xchg = reinterpret_cast<float4*>(smem + TC_SMEM_A + TC_SMEM_B + 256);
-  constexpr uint32_t kEpiArrivals = EPI == 3 ? 8 : 4;
+  constexpr uint32_t kEpiArrivals = EPI >= 3 ? 8 : 4;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -241,7 +328,9 @@ l2_top2_tc_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_const
       const int n_tiles = (job.nt + TC_BN - 1) / TC_BN;
       for (int n = 0; n < n_tiles; ++n, ++ti) {
         const uint32_t as = ti & 1, use = ti >> 1;
-        wait_bounded(&acc_full[as * 2 + m], use & 1);
+        // (the producer and MMA warps keep bounded waits: a protocol bug still traps there)
+        if constexpr (EPI >= 3) mbar_wait_hint(&acc_full[as * 2 + m], use & 1);
+        else wait_bounded(&acc_full[as * 2 + m], use & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                (as * 2 + m) * TC_BN;
@@ -252,20 +341,38 @@ l2_top2_tc_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_const
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[as * 2 + m]);
         };
-        if constexpr (EPI == 3) {
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            uint32_t v[32];
-            const int coff = half * 64 + c * 32;
-            __syncwarp();
-            tmem_ld_32x32b_x32(taddr + coff, v);        // includes tcgen05.wait::ld
-            if (c == 1) release();
-            if (valid < coff + 32) {
+        if constexpr (EPI == 4) {
+          // PROBE ONLY (results are garbage): hand the accumulator straight back, to time the
+          // TMA + MMA pipeline without any epilogue work.
+          tc_fence_before();
+          if (lane == 0) mbar_arrive(&acc_empty[as * 2 + m]);
+        } else if constexpr (EPI == 3) {
+          // lean path: this warp owns 64 of the tile's 128 columns, two 32-column loads; the
+          // masked variant only runs for a ragged last tile (warp-uniform branch).
+          const uint32_t t0 = taddr + half * 64;
+          const int c0 = col_base + half * 64;
+          uint32_t v[32];
+          if (valid >= TC_BN) {
+            tmem_ld_32x32b_x32(t0, v);
+            scan32<SCAN>(s, v, c0);
+            tmem_ld_32x32b_x32(t0 + 32, v);
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(&acc_empty[as * 2 + m]);
+            scan32<SCAN>(s, v, c0 + 32);
+          } else {
+            const int lim = valid - half * 64;           // columns of this half that exist
+            tmem_ld_32x32b_x32(t0, v);
 #pragma unroll
-              for (int e = 0; e < 32; ++e)
-                if (coff + e >= valid) v[e] = 0x7f800000u;
-            }
-            scan32(s, v, col_base + coff);
+            for (int e = 0; e < 32; ++e)
+              if (e >= lim) v[e] = 0x7f800000u;
+            scan32(s, v, c0);
+            tmem_ld_32x32b_x32(t0 + 32, v);
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(&acc_empty[as * 2 + m]);
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (32 + e >= lim) v[e] = 0x7f800000u;
+            scan32(s, v, c0 + 32);
           }
         } else if constexpr (EPI == 0) {
 #pragma unroll
@@ -320,7 +427,7 @@ l2_top2_tc_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_const
           scan32(s, &vb[32], col_base + 96);
         }
       }
-      if constexpr (EPI == 3) {
+      if constexpr (EPI >= 3) {
         // the two column-split warps of this (m-tile, quarter) merge their top-2 through smem
         float4* slot = xchg + ((m * 4 + quarter) * 32 + lane);
         const int bar_id = 1 + m * 4 + quarter;
@@ -346,7 +453,7 @@ l2_top2_tc_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_const
         }
         asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
       }
-      if ((EPI != 3 || half == 0) && row < job.nq) {
+      if ((EPI < 3 || half == 0) && row < job.nq) {
         const float na = static_cast<float>(qnorm[job.q_row + row]);
         int2 oi;
         float2 od;
@@ -373,6 +480,7 @@ cudaError_t tc_configure() {
   if ((e = cudaFuncSetAttribute(l2_top2_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(l2_top2_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(l2_top2_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(l2_top2_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) != cudaSuccess) return e;
   return cudaFuncSetAttribute(l2_top2_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
 }
 
@@ -390,7 +498,8 @@ cudaError_t launch_l2_tc(const TcMaps& maps, const int32_t* qnorm, const PairJob
   if (debug_dump != nullptr || epi == 0) PM_TC_LAUNCH(0);
   else if (epi == 1) PM_TC_LAUNCH(1);
   else if (epi == 2) PM_TC_LAUNCH(2);
-  else PM_TC_LAUNCH(3);
+  else if (epi == 3) PM_TC_LAUNCH(3);
+  else PM_TC_LAUNCH(4);
 #undef PM_TC_LAUNCH
   return cudaGetLastError();
 }

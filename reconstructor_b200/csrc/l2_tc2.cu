@@ -1,0 +1,401 @@
+// l2_tc2.cu -- K2 (CTA-pair version): exact L2 2-NN for integer-valued 128-d descriptors on tcgen05
+// with cta_group::2 -- two SMs of one TPC cooperate on a 256 x 256 output tile per MMA.
+//
+// Why pairs: with one CTA per tile an M=128 x N=128 x K=16 MMA needs 8 KB of shared-memory operands
+// every 64 cycles, i.e. the full 128 B/clk of the SM; measured, the single-CTA kernel (l2_tc.cu) tops
+// out at ~77 % of the tensor pipe even with an empty epilogue.  In pair mode each SM supplies its own
+// 128 query rows (A) and HALF of the train tile (B, 128 of 256 columns): 8 KB per 128 cycles.
+//
+// Same arithmetic and the same exactness argument as l2_tc.cu (fp16 operands, integer partial sums
+// < 2^24 in the fp32 accumulator, train-row norm folded in as a 9th K=16 step).  Replaces knnMatch at
+// Mapper/libMapper/FeatureMatcher.cpp:48-49; parity: cv::BFMatcher(NORM_L2), bit-exact.
+//
+// Per CTA: 20 warps.
+//   warp 0      TMA producer: its 128 query rows (resident per work item) and a ring of its halves of
+//               the train tiles; completion is signalled on the LEADER CTA's mbarriers
+//   warp 1      MMA issuer (leader CTA only): 9 x tcgen05.mma.cta_group::2 M=256 N=256 K=16 per tile,
+//               accumulator = 128 lanes x 256 columns in each CTA's TMEM, 2 stages
+//   warp 2      TMEM allocator (cta_group::2, 512 columns)
+//   warps 4-19  epilogue: warp = (lane quarter, 64-column slice); tcgen05.ld 32x32b.x32, min tree,
+//               running top-2 per row; slices merged through shared memory once per work item
+// Work item = (pair, 256-row query super-tile), dealt round-robin to the clusters.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pm {
+
+static constexpr int T2_THREADS = 640;
+static constexpr int T2_BM = 128;               // query rows per CTA
+static constexpr int T2_ROWS = 2 * T2_BM;       // per cluster work item
+static constexpr int T2_BN = 256;               // train rows per tile (UMMA N)
+static constexpr int T2_BNH = 128;              // ... of which each CTA loads half
+static constexpr int T2_STAGES = 4;
+static constexpr int T2_ATOM = T2_BM * 128;     // 16 KB: 128 rows x 128 B (SWIZZLE_128B)
+static constexpr int T2_EXT = T2_BM * 32;       // 4 KB: 128 rows x 32 B (SWIZZLE_32B)
+static constexpr int T2_TILE = 2 * T2_ATOM + T2_EXT;     // 36 KB
+static constexpr int T2_SMEM_A = T2_TILE;
+static constexpr int T2_SMEM_B = T2_STAGES * T2_TILE;
+static constexpr int T2_XCHG = 4 * 3 * 32 * 16;           // top-2 hand-over between the 4 column slices
+static constexpr int T2_SMEM_BYTES = T2_SMEM_A + T2_SMEM_B + 1024 + 256 + T2_XCHG;
+static constexpr uint32_t T2_TMEM_COLS = 512;
+// kind::f16: D=f32, A=B=f16, K-major, N=256, M=256 (pair)
+static constexpr uint32_t T2_IDESC = (1u << 4) | ((T2_BN >> 3) << 17) | ((T2_ROWS >> 4) << 24);
+static constexpr uint32_t T2_PEER_MASK = 0xFEFFFFFFu;     // clears the CTA-rank bit of a shared::cluster address
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void wait_trap(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
+    if (spin > (1u << 26)) __trap();
+}
+// TMA load whose completion bytes land on the leader CTA's mbarrier.
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(tmap), "r"(smem_u32(bar) & T2_PEER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrives (once all prior MMAs of this thread completed) on the barrier at the same offset in both CTAs.
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+// Arrive on the barrier at the same offset in the leader CTA (rank 0) of the pair.
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
+
+struct Top2p {
+  float m1, m2;
+  int i1, i2;
+};
+__device__ __forceinline__ void t2_push(Top2p& s, float v, int col) {
+  if (v < s.m2) {
+    if (v < s.m1) { s.m2 = s.m1; s.i2 = s.i1; s.m1 = v; s.i1 = col; }
+    else { s.m2 = v; s.i2 = col; }
+  }
+}
+__device__ __noinline__ void t2_group_generic(Top2p* sp, float v0, float v1, float v2, float v3, int col) {
+  Top2p s = *sp;
+  t2_push(s, v0, col); t2_push(s, v1, col + 1); t2_push(s, v2, col + 2); t2_push(s, v3, col + 3);
+  *sp = s;
+}
+// 32 consecutive columns in registers -> running top-2 (strict <, ascending columns: lowest index
+// wins ties).  Minima of 8 groups of 4, one compare against the current 2nd best; on a hit a
+// per-lane mask selects the groups to visit, each handled by one shared single-insert body.
+__device__ __forceinline__ void t2_scan32(Top2p& s, const uint32_t* r, int col0) {
+  float g[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    g[k] = fminf(fminf(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1])),
+                 fminf(__uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3])));
+  const float cm = fminf(fminf(fminf(g[0], g[1]), fminf(g[2], g[3])), fminf(fminf(g[4], g[5]), fminf(g[6], g[7])));
+  if (cm < s.m2) {
+    uint32_t mask = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mask |= (g[k] < s.m2 ? 1u : 0u) << k;
+    do {
+      const int k = __ffs(mask) - 1;
+      mask &= mask - 1;
+      float v0, v1, v2, v3, gk;
+      switch (k) {
+#define PM_CASE(K)                                                                                 \
+  case K:                                                                                          \
+    v0 = __uint_as_float(r[4 * K]); v1 = __uint_as_float(r[4 * K + 1]);                             \
+    v2 = __uint_as_float(r[4 * K + 2]); v3 = __uint_as_float(r[4 * K + 3]); gk = g[K];              \
+    break;
+        PM_CASE(0) PM_CASE(1) PM_CASE(2) PM_CASE(3) PM_CASE(4) PM_CASE(5) PM_CASE(6)
+        default:
+          v0 = __uint_as_float(r[28]); v1 = __uint_as_float(r[29]);
+          v2 = __uint_as_float(r[30]); v3 = __uint_as_float(r[31]); gk = g[7];
+          break;
+#undef PM_CASE
+      }
+      if (gk < s.m2) {
+        const int col = col0 + 4 * k;
+        int pos = 3;
+        pos = v2 == gk ? 2 : pos;
+        pos = v1 == gk ? 1 : pos;
+        pos = v0 == gk ? 0 : pos;
+        const float second = fminf(fmaxf(fminf(v0, v1), fminf(v2, v3)), fminf(fmaxf(v0, v1), fmaxf(v2, v3)));
+        const float nm2 = fmaxf(gk, s.m1);
+        if (second < nm2) {
+          t2_group_generic(&s, v0, v1, v2, v3, col);
+        } else {
+          const bool first = gk < s.m1;
+          const int c = col + pos;
+          s.i2 = first ? s.i1 : c;
+          s.i1 = first ? c : s.i1;
+          s.m2 = nm2;
+          s.m1 = fminf(gk, s.m1);
+        }
+      }
+    } while (mask);
+  }
+}
+// ordered by (value, index)
+__device__ __forceinline__ bool t2_less(float va, int ia, float vb, int ib) { return va < vb || (va == vb && ia < ib); }
+__device__ __forceinline__ void t2_merge(Top2p& s, float om1, int oi1, float om2, int oi2) {
+  Top2p t;
+  if (oi1 >= 0 && (s.i1 < 0 || t2_less(om1, oi1, s.m1, s.i1))) {
+    t.m1 = om1; t.i1 = oi1;
+    if (oi2 >= 0 && (s.i1 < 0 || t2_less(om2, oi2, s.m1, s.i1))) { t.m2 = om2; t.i2 = oi2; }
+    else { t.m2 = s.m1; t.i2 = s.i1; }
+  } else {
+    t.m1 = s.m1; t.i1 = s.i1;
+    if (oi1 >= 0 && (s.i2 < 0 || t2_less(om1, oi1, s.m2, s.i2))) { t.m2 = om1; t.i2 = oi1; }
+    else { t.m2 = s.m2; t.i2 = s.i2; }
+  }
+  s = t;
+}
+
+template <int PROBE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
+l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant__ CUtensorMap q_ext,
+                   const __grid_constant__ CUtensorMap t_main, const __grid_constant__ CUtensorMap t_ext,
+                   const int32_t* __restrict__ qnorm, const PairJob* __restrict__ jobs, int n_jobs,
+                   int tiles_per_job, int2* __restrict__ knn_idx, float2* __restrict__ knn_dist, int stride) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + T2_SMEM_A;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T2_SMEM_A + T2_SMEM_B);
+  uint64_t* a_full = bars + 0;                       // leader: 1 arrival + 2 x 36 KB of tx
+  uint64_t* a_empty = bars + 1;                      // both: multicast commit
+  uint64_t* b_full = bars + 2;                       // [STAGES] leader
+  uint64_t* b_empty = bars + 2 + T2_STAGES;          // [STAGES] both
+  uint64_t* acc_full = bars + 2 + 2 * T2_STAGES;     // [2] both: multicast commit
+  uint64_t* acc_empty = acc_full + 2;                // [2] leader: 32 epilogue warps of the pair
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float4* xchg = reinterpret_cast<float4*>(smem + T2_SMEM_A + T2_SMEM_B + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&q_main); tma_prefetch_desc(&q_ext);
+    tma_prefetch_desc(&t_main); tma_prefetch_desc(&t_ext);
+    mbar_init(a_full, 1); mbar_init(a_empty, 1);
+    for (int s = 0; s < T2_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 32); }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(T2_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                // barriers of both CTAs initialised and visible
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_items = n_jobs * tiles_per_job;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ===================================== TMA producer (both CTAs) ==========================
+    if (lane == 0) {
+      uint32_t ai = 0, bi = 0;
+      for (int item = cluster_id; item < n_items; item += n_clusters) {
+        const int jb = item / tiles_per_job, r = item - jb * tiles_per_job;
+        const PairJob job = jobs[jb];
+        if (r * T2_ROWS >= job.nq) continue;
+        wait_trap(a_empty, (ai & 1) ^ 1);
+        if (leader) mbar_expect_tx(a_full, 2 * T2_TILE);
+        {
+          const int row = job.q_row + r * T2_ROWS + rank * T2_BM;
+          tma_load_2d_pair(sA, &q_main, 0, row, a_full);
+          tma_load_2d_pair(sA + T2_ATOM, &q_main, 64, row, a_full);
+          tma_load_2d_pair(sA + 2 * T2_ATOM, &q_ext, TC_DIM, row, a_full);
+        }
+        ++ai;
+        const int n_tiles = (job.nt + T2_BN - 1) / T2_BN;
+        for (int n = 0; n < n_tiles; ++n, ++bi) {
+          const uint32_t st = bi % T2_STAGES;
+          wait_trap(&b_empty[st], ((bi / T2_STAGES) & 1) ^ 1);
+          if (leader) mbar_expect_tx(&b_full[st], 2 * T2_TILE);
+          uint8_t* dst = sB + st * T2_TILE;
+          const int row = job.t_row + n * T2_BN + rank * T2_BNH;      // this CTA's half of the train tile
+          tma_load_2d_pair(dst, &t_main, 0, row, &b_full[st]);
+          tma_load_2d_pair(dst + T2_ATOM, &t_main, 64, row, &b_full[st]);
+          tma_load_2d_pair(dst + 2 * T2_ATOM, &t_ext, TC_DIM, row, &b_full[st]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ====================================== MMA issuer (leader CTA) ===========================
+    if (leader) {
+      uint32_t ai = 0, bi = 0, ti = 0;
+      constexpr uint32_t HI128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+      constexpr uint32_t HI32 = (256u >> 4) | (1u << 14) | (6u << 29);
+      const uint32_t a_lo = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (1u << 16);
+      for (int item = cluster_id; item < n_items; item += n_clusters) {
+        const int jb = item / tiles_per_job, r = item - jb * tiles_per_job;
+        const int job_nq = jobs[jb].nq, job_nt = jobs[jb].nt;
+        if (r * T2_ROWS >= job_nq) continue;
+        wait_trap(a_full, ai & 1);
+        ++ai;
+        const int n_tiles = (job_nt + T2_BN - 1) / T2_BN;
+        for (int n = 0; n < n_tiles; ++n, ++bi, ++ti) {
+          const uint32_t st = bi % T2_STAGES;
+          const uint32_t as = ti & 1, use = ti >> 1;
+          wait_trap(&b_full[st], (bi / T2_STAGES) & 1);
+          wait_trap(&acc_empty[as], (use & 1) ^ 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t b_lo = b_lo0 + st * (T2_TILE >> 4);
+            const uint32_t d_tmem = tmem_base + as * T2_BN;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint32_t off = ((k >> 2) * T2_ATOM + (k & 3) * 32) >> 4;
+              umma_f16_pair(d_tmem, (static_cast<uint64_t>(HI128) << 32) | (a_lo + off),
+                            (static_cast<uint64_t>(HI128) << 32) | (b_lo + off), T2_IDESC, k > 0 ? 1u : 0u);
+            }
+            constexpr uint32_t xoff = (2 * T2_ATOM) >> 4;
+            umma_f16_pair(d_tmem, (static_cast<uint64_t>(HI32) << 32) | (a_lo + xoff),
+                          (static_cast<uint64_t>(HI32) << 32) | (b_lo + xoff), T2_IDESC, 1u);
+            umma_commit_pair(&acc_full[as]);
+            umma_commit_pair(&b_empty[st]);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) umma_commit_pair(a_empty);
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    // ======================================= epilogue (both CTAs) =============================
+    const int quarter = warp & 3, slice = (warp - 4) >> 2;       // 64-column slice of the 256-column tile
+    uint32_t ti = 0;
+    for (int item = cluster_id; item < n_items; item += n_clusters) {
+      const int jb = item / tiles_per_job, r = item - jb * tiles_per_job;
+      const PairJob job = jobs[jb];
+      if (r * T2_ROWS >= job.nq) continue;
+      const int row = r * T2_ROWS + rank * T2_BM + quarter * 32 + lane;
+      Top2p s;
+      s.m1 = s.m2 = __int_as_float(0x7f800000);
+      s.i1 = s.i2 = -1;
+      const int n_tiles = (job.nt + T2_BN - 1) / T2_BN;
+      for (int n = 0; n < n_tiles; ++n, ++ti) {
+        const uint32_t as = ti & 1, use = ti >> 1;
+        wait_trap(&acc_full[as], use & 1);
+        tc_fence_after();
+        const uint32_t t0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * T2_BN + slice * 64;
+        const int c0 = n * T2_BN + slice * 64;
+        const int lim = job.nt - c0;                   // columns of this slice that exist
+        uint32_t v[32];
+        if (PROBE) {
+          tc_fence_before();
+          if (lane == 0) mbar_arrive_leader(&acc_empty[as]);
+        } else if (lim >= 64) {
+          tmem_ld_32x32b_x32(t0, v);
+          t2_scan32(s, v, c0);
+          tmem_ld_32x32b_x32(t0 + 32, v);
+          tc_fence_before();
+          if (lane == 0) mbar_arrive_leader(&acc_empty[as]);
+          t2_scan32(s, v, c0 + 32);
+        } else {
+          tmem_ld_32x32b_x32(t0, v);
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (e >= lim) v[e] = 0x7f800000u;
+          t2_scan32(s, v, c0);
+          tmem_ld_32x32b_x32(t0 + 32, v);
+          tc_fence_before();
+          if (lane == 0) mbar_arrive_leader(&acc_empty[as]);
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (32 + e >= lim) v[e] = 0x7f800000u;
+          t2_scan32(s, v, c0 + 32);
+        }
+      }
+      // merge the four column slices of this lane quarter: slices 1..3 publish, slice 0 merges
+      {
+        float4* slot = xchg + ((quarter * 3) * 32 + lane);
+        const int bar_id = 1 + quarter;
+        if (slice > 0) slot[(slice - 1) * 32] = make_float4(s.m1, __int_as_float(s.i1), s.m2, __int_as_float(s.i2));
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (slice == 0) {
+#pragma unroll
+          for (int o = 0; o < 3; ++o) {
+            const float4 x = slot[o * 32];
+            t2_merge(s, x.x, __float_as_int(x.y), x.z, __float_as_int(x.w));
+          }
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      }
+      if (slice == 0 && row < job.nq) {
+        const float na = static_cast<float>(qnorm[job.q_row + row]);
+        int2 oi;
+        float2 od;
+        oi.x = s.i1; oi.y = s.i2;
+        od.x = s.i1 < 0 ? s.m1 : __fsqrt_rn(fmaxf(__fadd_rn(s.m1, na), 0.f));
+        od.y = s.i2 < 0 ? s.m2 : __fsqrt_rn(fmaxf(__fadd_rn(s.m2, na), 0.f));
+        const size_t o = static_cast<size_t>(jb) * stride + row;
+        knn_idx[o] = oi;
+        knn_dist[o] = od;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                // no remote arrive / multicast may still be in flight
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(T2_TMEM_COLS) : "memory");
+  }
+}
+
+cudaError_t tc2_configure() {
+  cudaError_t e = cudaFuncSetAttribute(l2_top2_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(l2_top2_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES);
+}
+
+cudaError_t launch_l2_tc2(const TcMaps& maps, const int32_t* qnorm, const PairJob* jobs, int n_jobs, int max_nq,
+                          int2* idx, float2* dist, int stride, int num_sms, int probe, cudaStream_t st) {
+  if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
+  const int tiles_per_job = (max_nq + T2_ROWS - 1) / T2_ROWS;
+  const int n_items = n_jobs * tiles_per_job;
+  int clusters = num_sms / 2;
+  if (n_items < clusters) clusters = n_items;
+  const int grid = clusters * 2;
+  if (probe)
+    l2_top2_tc2_kernel<1><<<grid, T2_THREADS, T2_SMEM_BYTES, st>>>(maps.q_main, maps.q_ext, maps.t_main, maps.t_ext, qnorm,
+                                                                   jobs, n_jobs, tiles_per_job, idx, dist, stride);
+  else
+    l2_top2_tc2_kernel<0><<<grid, T2_THREADS, T2_SMEM_BYTES, st>>>(maps.q_main, maps.q_ext, maps.t_main, maps.t_ext, qnorm,
+                                                                   jobs, n_jobs, tiles_per_job, idx, dist, stride);
+  return cudaGetLastError();
+}
+
+}  // namespace pm
