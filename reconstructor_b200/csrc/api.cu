@@ -267,8 +267,8 @@ struct DeviceCtx {
     const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(TC_KPAD), static_cast<cuuint64_t>(cap_rows)};
     const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(TC_KPAD) * sizeof(__half)};
     const cuuint32_t estr[2] = {1, 1};
-    auto mk = [&](CUtensorMap* m, void* base, cuuint32_t box_k, CUtensorMapSwizzle sw) -> CUresult {
-      const cuuint32_t box[2] = {box_k, 128};
+    auto mk = [&](CUtensorMap* m, void* base, cuuint32_t box_k, CUtensorMapSwizzle sw, cuuint32_t rows = 128) -> CUresult {
+      const cuuint32_t box[2] = {box_k, rows};
       return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, gdim, gstr, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -277,7 +277,9 @@ struct DeviceCtx {
     if ((r = mk(&maps.q_main, qf, 64, CU_TENSOR_MAP_SWIZZLE_128B)) != CUDA_SUCCESS ||
         (r = mk(&maps.q_ext, qf, 16, CU_TENSOR_MAP_SWIZZLE_32B)) != CUDA_SUCCESS ||
         (r = mk(&maps.t_main, tf, 64, CU_TENSOR_MAP_SWIZZLE_128B)) != CUDA_SUCCESS ||
-        (r = mk(&maps.t_ext, tf, 16, CU_TENSOR_MAP_SWIZZLE_32B)) != CUDA_SUCCESS)
+        (r = mk(&maps.t_ext, tf, 16, CU_TENSOR_MAP_SWIZZLE_32B)) != CUDA_SUCCESS ||
+        (r = mk(&maps.t_main96, tf, 64, CU_TENSOR_MAP_SWIZZLE_128B, 96)) != CUDA_SUCCESS ||
+        (r = mk(&maps.t_ext96, tf, 16, CU_TENSOR_MAP_SWIZZLE_32B, 96)) != CUDA_SUCCESS)
       return fail(PM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
     tc_ready = true;
     return PM_OK;
@@ -503,8 +505,8 @@ struct DeviceCtx {
       s.knn_work = work * words;
     } else if (use_tc) {
       if (epi >= 5 && !dump)
-        PM_CUDA(launch_l2_tc2(maps, qnorm, s.d_jobs, n, max_nq, s.knn_idx, s.knn_dist, s.stride, num_sms, epi == 6,
-                              knn_stream));
+        PM_CUDA(launch_l2_tc2(maps, qnorm, s.d_jobs, n, max_nq, s.knn_idx, s.knn_dist, s.stride, num_sms, epi == 7,
+                              epi == 6 || ((prm.debug_flags >> 5) & 1), knn_stream));
       else
         PM_CUDA(launch_l2_tc(maps, qnorm, s.d_jobs, n, max_nq, s.knn_idx, s.knn_dist, s.stride, num_sms, dump,
                              epi, knn_stream));
@@ -522,7 +524,7 @@ struct DeviceCtx {
                                     knn_stream));
       else if (use_tc)
         if (epi >= 5)
-          PM_CUDA(launch_l2_tc2(maps, qnorm, s.d_rjobs, n, max_nt, s.rev_idx, s.rev_dist, s.stride, num_sms, 0,
+          PM_CUDA(launch_l2_tc2(maps, qnorm, s.d_rjobs, n, max_nt, s.rev_idx, s.rev_dist, s.stride, num_sms, epi == 7, 0,
                                 knn_stream));
         else
           PM_CUDA(launch_l2_tc(maps, qnorm, s.d_rjobs, n, max_nt, s.rev_idx, s.rev_dist, s.stride, num_sms,

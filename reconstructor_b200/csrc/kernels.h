@@ -33,7 +33,8 @@ cudaError_t launch_l2_simt(const float* desc, int dim, const PairJob* jobs, int 
 static constexpr int TC_DIM = 128;        // descriptor length handled by the tensor path
 static constexpr int TC_KPAD = 144;       // 128 + one K=16 step carrying the train-row norm
 struct TcMaps {
-  CUtensorMap q_main, q_ext, t_main, t_ext;
+  CUtensorMap q_main, q_ext, t_main, t_ext;   // boxes of 128 rows
+  CUtensorMap t_main96, t_ext96;              // boxes of 96 rows (pair kernel, 192-column tiles)
 };
 cudaError_t tc_configure();               // one-time function attributes
 cudaError_t launch_l2_tc(const TcMaps& maps, const int32_t* qnorm, const PairJob* jobs, int n_jobs,
@@ -43,7 +44,8 @@ cudaError_t launch_l2_tc(const TcMaps& maps, const int32_t* qnorm, const PairJob
 // K2, CTA-pair version -- l2_tc2.cu (tcgen05 cta_group::2)
 cudaError_t tc2_configure();
 cudaError_t launch_l2_tc2(const TcMaps& maps, const int32_t* qnorm, const PairJob* jobs, int n_jobs, int max_nq,
-                          int2* idx, float2* dist, int stride, int num_sms, int probe, cudaStream_t st);
+                          int2* idx, float2* dist, int stride, int num_sms, int variant, int probe,
+                          cudaStream_t st);
 
 // pack.cu
 cudaError_t launch_pack_sift(const float* raw_f32, const uint8_t* raw_u8, int n, __half* qf,

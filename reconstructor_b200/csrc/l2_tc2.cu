@@ -24,23 +24,34 @@
 
 namespace pm {
 
-static constexpr int T2_THREADS = 640;
 static constexpr int T2_BM = 128;               // query rows per CTA
 static constexpr int T2_ROWS = 2 * T2_BM;       // per cluster work item
-static constexpr int T2_BN = 256;               // train rows per tile (UMMA N)
-static constexpr int T2_BNH = 128;              // ... of which each CTA loads half
-static constexpr int T2_STAGES = 4;
 static constexpr int T2_ATOM = T2_BM * 128;     // 16 KB: 128 rows x 128 B (SWIZZLE_128B)
 static constexpr int T2_EXT = T2_BM * 32;       // 4 KB: 128 rows x 32 B (SWIZZLE_32B)
-static constexpr int T2_TILE = 2 * T2_ATOM + T2_EXT;     // 36 KB
+static constexpr int T2_TILE = 2 * T2_ATOM + T2_EXT;     // 36 KB (query tile of one CTA)
 static constexpr int T2_SMEM_A = T2_TILE;
-static constexpr int T2_SMEM_B = T2_STAGES * T2_TILE;
-static constexpr int T2_XCHG = 4 * 3 * 32 * 16;           // top-2 hand-over between the 4 column slices
-static constexpr int T2_SMEM_BYTES = T2_SMEM_A + T2_SMEM_B + 1024 + 256 + T2_XCHG;
 static constexpr uint32_t T2_TMEM_COLS = 512;
-// kind::f16: D=f32, A=B=f16, K-major, N=256, M=256 (pair)
-static constexpr uint32_t T2_IDESC = (1u << 4) | ((T2_BN >> 3) << 17) | ((T2_ROWS >> 4) << 24);
 static constexpr uint32_t T2_PEER_MASK = 0xFEFFFFFFu;     // clears the CTA-rank bit of a shared::cluster address
+
+// Geometry of a variant.  BN = train rows per tile (UMMA N); every epilogue warp owns CPW chunks of
+// 32 columns of its lane quarter, so there are BN / (32 * CPW) column slices and 4x that many
+// epilogue warps.
+//   BN = 256, CPW = 2: 16 epilogue warps (640 threads)
+//   BN = 192, CPW = 1: 24 epilogue warps (896 threads) -- more warps in flight per scheduler
+template <int BN, int CPW>
+struct T2Cfg {
+  static constexpr int kBN = BN, kBNH = BN / 2, kCPW = CPW;
+  static constexpr int kSlices = BN / (32 * CPW);
+  static constexpr int kEpiWarps = 4 * kSlices;
+  static constexpr int kThreads = 128 + 32 * kEpiWarps;
+  static constexpr int kBAtom = kBNH * 128, kBExt = kBNH * 32, kBTile = 2 * kBAtom + kBExt;
+  static constexpr int kStages = BN == 256 ? 4 : 5;
+  static constexpr int kSmemB = kStages * kBTile;
+  static constexpr int kXchg = 4 * (kSlices - 1) * 32 * 16;
+  static constexpr int kSmemBytes = T2_SMEM_A + kSmemB + 1024 + 256 + kXchg;
+  // kind::f16: D=f32, A=B=f16, K-major, N=BN, M=256 (pair)
+  static constexpr uint32_t kIdesc = (1u << 4) | ((BN >> 3) << 17) | ((T2_ROWS >> 4) << 24);
+};
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -172,12 +183,15 @@ __device__ __forceinline__ void t2_merge(Top2p& s, float om1, int oi1, float om2
   s = t;
 }
 
-template <int PROBE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
+template <class Cfg, int PROBE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::kThreads, 1)
 l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant__ CUtensorMap q_ext,
                    const __grid_constant__ CUtensorMap t_main, const __grid_constant__ CUtensorMap t_ext,
                    const int32_t* __restrict__ qnorm, const PairJob* __restrict__ jobs, int n_jobs,
                    int tiles_per_job, int2* __restrict__ knn_idx, float2* __restrict__ knn_dist, int stride) {
+  constexpr int T2_BN = Cfg::kBN, T2_BNH = Cfg::kBNH, T2_STAGES = Cfg::kStages, T2_SMEM_B = Cfg::kSmemB;
+  constexpr int T2_BATOM = Cfg::kBAtom, T2_BTILE = Cfg::kBTile, CPW = Cfg::kCPW, NSL = Cfg::kSlices;
+  constexpr uint32_t T2_IDESC = Cfg::kIdesc;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -201,7 +215,7 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
     tma_prefetch_desc(&t_main); tma_prefetch_desc(&t_ext);
     mbar_init(a_full, 1); mbar_init(a_empty, 1);
     for (int s = 0; s < T2_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 32); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 2 * Cfg::kEpiWarps); }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -240,12 +254,12 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
         for (int n = 0; n < n_tiles; ++n, ++bi) {
           const uint32_t st = bi % T2_STAGES;
           wait_trap(&b_empty[st], ((bi / T2_STAGES) & 1) ^ 1);
-          if (leader) mbar_expect_tx(&b_full[st], 2 * T2_TILE);
-          uint8_t* dst = sB + st * T2_TILE;
+          if (leader) mbar_expect_tx(&b_full[st], 2 * T2_BTILE);
+          uint8_t* dst = sB + st * T2_BTILE;
           const int row = job.t_row + n * T2_BN + rank * T2_BNH;      // this CTA's half of the train tile
           tma_load_2d_pair(dst, &t_main, 0, row, &b_full[st]);
-          tma_load_2d_pair(dst + T2_ATOM, &t_main, 64, row, &b_full[st]);
-          tma_load_2d_pair(dst + 2 * T2_ATOM, &t_ext, TC_DIM, row, &b_full[st]);
+          tma_load_2d_pair(dst + T2_BATOM, &t_main, 64, row, &b_full[st]);
+          tma_load_2d_pair(dst + 2 * T2_BATOM, &t_ext, TC_DIM, row, &b_full[st]);
         }
       }
     }
@@ -271,17 +285,17 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
           wait_trap(&acc_empty[as], (use & 1) ^ 1);
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t b_lo = b_lo0 + st * (T2_TILE >> 4);
+            const uint32_t b_lo = b_lo0 + st * (T2_BTILE >> 4);
             const uint32_t d_tmem = tmem_base + as * T2_BN;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              const uint32_t off = ((k >> 2) * T2_ATOM + (k & 3) * 32) >> 4;
-              umma_f16_pair(d_tmem, (static_cast<uint64_t>(HI128) << 32) | (a_lo + off),
-                            (static_cast<uint64_t>(HI128) << 32) | (b_lo + off), T2_IDESC, k > 0 ? 1u : 0u);
+              const uint32_t aoff = ((k >> 2) * T2_ATOM + (k & 3) * 32) >> 4;
+              const uint32_t boff = ((k >> 2) * T2_BATOM + (k & 3) * 32) >> 4;
+              umma_f16_pair(d_tmem, (static_cast<uint64_t>(HI128) << 32) | (a_lo + aoff),
+                            (static_cast<uint64_t>(HI128) << 32) | (b_lo + boff), T2_IDESC, k > 0 ? 1u : 0u);
             }
-            constexpr uint32_t xoff = (2 * T2_ATOM) >> 4;
-            umma_f16_pair(d_tmem, (static_cast<uint64_t>(HI32) << 32) | (a_lo + xoff),
-                          (static_cast<uint64_t>(HI32) << 32) | (b_lo + xoff), T2_IDESC, 1u);
+            umma_f16_pair(d_tmem, (static_cast<uint64_t>(HI32) << 32) | (a_lo + ((2 * T2_ATOM) >> 4)),
+                          (static_cast<uint64_t>(HI32) << 32) | (b_lo + ((2 * T2_BATOM) >> 4)), T2_IDESC, 1u);
             umma_commit_pair(&acc_full[as]);
             umma_commit_pair(&b_empty[st]);
           }
@@ -293,7 +307,7 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
     }
   } else if (warp >= 4) {
     // ======================================= epilogue (both CTAs) =============================
-    const int quarter = warp & 3, slice = (warp - 4) >> 2;       // 64-column slice of the 256-column tile
+    const int quarter = warp & 3, slice = (warp - 4) >> 2;       // which 32*CPW-column slice of the tile
     uint32_t ti = 0;
     for (int item = cluster_id; item < n_items; item += n_clusters) {
       const int jb = item / tiles_per_job, r = item - jb * tiles_per_job;
@@ -308,49 +322,52 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
         const uint32_t as = ti & 1, use = ti >> 1;
         wait_trap(&acc_full[as], use & 1);
         tc_fence_after();
-        const uint32_t t0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * T2_BN + slice * 64;
-        const int c0 = n * T2_BN + slice * 64;
+        const uint32_t t0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * T2_BN + slice * (32 * CPW);
+        const int c0 = n * T2_BN + slice * (32 * CPW);
         const int lim = job.nt - c0;                   // columns of this slice that exist
         uint32_t v[32];
         if (PROBE) {
           tc_fence_before();
           if (lane == 0) mbar_arrive_leader(&acc_empty[as]);
-        } else if (lim >= 64) {
-          tmem_ld_32x32b_x32(t0, v);
-          t2_scan32(s, v, c0);
-          tmem_ld_32x32b_x32(t0 + 32, v);
-          tc_fence_before();
-          if (lane == 0) mbar_arrive_leader(&acc_empty[as]);
-          t2_scan32(s, v, c0 + 32);
+        } else if (lim >= 32 * CPW) {
+#pragma unroll
+          for (int c = 0; c < CPW; ++c) {
+            tmem_ld_32x32b_x32(t0 + 32 * c, v);
+            if (c == CPW - 1) {                         // accumulator slice drained
+              tc_fence_before();
+              if (lane == 0) mbar_arrive_leader(&acc_empty[as]);
+            }
+            t2_scan32(s, v, c0 + 32 * c);
+          }
         } else {
-          tmem_ld_32x32b_x32(t0, v);
 #pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (e >= lim) v[e] = 0x7f800000u;
-          t2_scan32(s, v, c0);
-          tmem_ld_32x32b_x32(t0 + 32, v);
-          tc_fence_before();
-          if (lane == 0) mbar_arrive_leader(&acc_empty[as]);
+          for (int c = 0; c < CPW; ++c) {
+            tmem_ld_32x32b_x32(t0 + 32 * c, v);
+            if (c == CPW - 1) {
+              tc_fence_before();
+              if (lane == 0) mbar_arrive_leader(&acc_empty[as]);
+            }
 #pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (32 + e >= lim) v[e] = 0x7f800000u;
-          t2_scan32(s, v, c0 + 32);
+            for (int e = 0; e < 32; ++e)
+              if (32 * c + e >= lim) v[e] = 0x7f800000u;
+            t2_scan32(s, v, c0 + 32 * c);
+          }
         }
       }
-      // merge the four column slices of this lane quarter: slices 1..3 publish, slice 0 merges
+      // merge the column slices of this lane quarter: slices 1.. publish, slice 0 merges
       {
-        float4* slot = xchg + ((quarter * 3) * 32 + lane);
+        float4* slot = xchg + ((quarter * (NSL - 1)) * 32 + lane);
         const int bar_id = 1 + quarter;
         if (slice > 0) slot[(slice - 1) * 32] = make_float4(s.m1, __int_as_float(s.i1), s.m2, __int_as_float(s.i2));
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NSL) : "memory");
         if (slice == 0) {
 #pragma unroll
-          for (int o = 0; o < 3; ++o) {
+          for (int o = 0; o < NSL - 1; ++o) {
             const float4 x = slot[o * 32];
             t2_merge(s, x.x, __float_as_int(x.y), x.z, __float_as_int(x.w));
           }
         }
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NSL) : "memory");
       }
       if (slice == 0 && row < job.nq) {
         const float na = static_cast<float>(qnorm[job.q_row + row]);
@@ -375,26 +392,34 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
   }
 }
 
+using T2Wide = T2Cfg<256, 2>;     // 16 epilogue warps
+using T2Deep = T2Cfg<192, 1>;     // 24 epilogue warps
+
 cudaError_t tc2_configure() {
-  cudaError_t e = cudaFuncSetAttribute(l2_top2_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(l2_top2_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES);
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(l2_top2_tc2_kernel<T2Wide, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2Wide::kSmemBytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(l2_top2_tc2_kernel<T2Wide, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2Wide::kSmemBytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(l2_top2_tc2_kernel<T2Deep, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2Deep::kSmemBytes)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(l2_top2_tc2_kernel<T2Deep, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2Deep::kSmemBytes);
 }
 
+// variant 0: 256-column tiles / 16 epilogue warps; variant 1: 192-column tiles / 24 epilogue warps.
 cudaError_t launch_l2_tc2(const TcMaps& maps, const int32_t* qnorm, const PairJob* jobs, int n_jobs, int max_nq,
-                          int2* idx, float2* dist, int stride, int num_sms, int probe, cudaStream_t st) {
+                          int2* idx, float2* dist, int stride, int num_sms, int variant, int probe, cudaStream_t st) {
   if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
   const int tiles_per_job = (max_nq + T2_ROWS - 1) / T2_ROWS;
   const int n_items = n_jobs * tiles_per_job;
   int clusters = num_sms / 2;
   if (n_items < clusters) clusters = n_items;
   const int grid = clusters * 2;
-  if (probe)
-    l2_top2_tc2_kernel<1><<<grid, T2_THREADS, T2_SMEM_BYTES, st>>>(maps.q_main, maps.q_ext, maps.t_main, maps.t_ext, qnorm,
-                                                                   jobs, n_jobs, tiles_per_job, idx, dist, stride);
-  else
-    l2_top2_tc2_kernel<0><<<grid, T2_THREADS, T2_SMEM_BYTES, st>>>(maps.q_main, maps.q_ext, maps.t_main, maps.t_ext, qnorm,
-                                                                   jobs, n_jobs, tiles_per_job, idx, dist, stride);
+  const CUtensorMap& tm = variant == 1 ? maps.t_main96 : maps.t_main;
+  const CUtensorMap& te = variant == 1 ? maps.t_ext96 : maps.t_ext;
+#define PM_T2_LAUNCH(CFG, P)                                                                         \
+  l2_top2_tc2_kernel<CFG, P><<<grid, CFG::kThreads, CFG::kSmemBytes, st>>>(                          \
+      maps.q_main, maps.q_ext, tm, te, qnorm, jobs, n_jobs, tiles_per_job, idx, dist, stride)
+  if (variant == 1) { if (probe) PM_T2_LAUNCH(T2Deep, 1); else PM_T2_LAUNCH(T2Deep, 0); }
+  else { if (probe) PM_T2_LAUNCH(T2Wide, 1); else PM_T2_LAUNCH(T2Wide, 0); }
+#undef PM_T2_LAUNCH
   return cudaGetLastError();
 }
 

@@ -53,7 +53,7 @@ def test_hamming_knn_bit_exact(knn, variant):
             assert np.array_equal(dist, knn[f"orb_{tag}_dist"])
 
 
-@pytest.mark.parametrize("force_simt", [0, 1, 4, 8, 12, 20])
+@pytest.mark.parametrize("force_simt", [0, 1, 4, 8, 12, 20, 28])
 def test_l2_sift_knn_bit_exact(knn, force_simt):
     """flags 0/4/8/12 are the single-CTA tcgen05 path (four epilogue variants), 20 the CTA-pair kernel, 1 the fp32 SIMT kernel; all must
     equal cv::BFMatcher."""
@@ -74,7 +74,7 @@ def test_l2_sift_u8_dtype_matches_f32(knn):
         assert np.array_equal(idx, knn["sift_01_idx"]) and np.array_equal(dist, knn["sift_01_dist"])
 
 
-@pytest.mark.parametrize("kind,flags", [("orb", 0), ("sift", 0), ("sift", 1), ("sift", 4), ("sift", 12), ("sift", 20)])
+@pytest.mark.parametrize("kind,flags", [("orb", 0), ("sift", 0), ("sift", 1), ("sift", 4), ("sift", 12), ("sift", 20), ("sift", 28)])
 def test_knn_ties_lowest_index(knn, kind, flags):
     with api.PairMatcher(debug_flags=flags) as pm:
         _load3(pm, knn, kind, ties=True)
@@ -123,10 +123,10 @@ def test_l2_sift_extreme_values_exact():
     assert np.array_equal(dist, np.sqrt(o2).astype(np.float32))
 
 
-@pytest.mark.parametrize("kind", ["orb", "sift", "sift-epi1", "sift-epi2", "sift-epi3", "sift-pair", "superpoint"])
+@pytest.mark.parametrize("kind", ["orb", "sift", "sift-epi1", "sift-epi2", "sift-epi3", "sift-pair", "sift-pair192", "superpoint"])
 def test_knn_ragged_and_tiny(kind):
     """Ragged sizes (not multiples of any tile), 1-row and 2-row train sets, empty images."""
-    flags = {"sift-epi1": 4, "sift-epi2": 8, "sift-epi3": 12, "sift-pair": 20}.get(kind, 0)
+    flags = {"sift-epi1": 4, "sift-epi2": 8, "sift-epi3": 12, "sift-pair": 20, "sift-pair192": 28}.get(kind, 0)
     kind = kind.split("-")[0]
     w = synth.World(kind, 700, seed=11)
     full = [w.image(i, 4)[0] for i in range(2)]
@@ -341,7 +341,7 @@ def test_errors_are_reported_not_thrown(knn):
 def test_full_size_8192_pair(kind):
     w = synth.World(kind, 8192, seed=0xB200)
     imgs = [w.image(i, 100)[:2] for i in range(3)]
-    flags = [0, 1, 4, 8, 12, 20] if kind == "sift" else [0, 2]
+    flags = [0, 1, 4, 8, 12, 20, 28] if kind == "sift" else [0, 2]
     outs = []
     for f in flags:
         with api.PairMatcher(debug_flags=f) as pm:
