@@ -85,7 +85,8 @@ typedef struct {
   int32_t sampler;            /* PM_SAMPLER_*                                               */
   int32_t batch_pairs;        /* pairs per device batch, 0 = auto                           */
   int64_t reserve_keypoints;  /* device arena rows to preallocate, 0 = grow on demand       */
-  int32_t debug_flags;        /* bit 0: force the SIMT fp32 L2 kernel (parity cross-check)  */
+  int32_t debug_flags;        /* kernel-variant switches for parity cross-checks and probes;
+                                 0 = product defaults (see enqueue_knn in csrc/api.cu)      */
   int32_t reserved;
 } pm_params;
 

@@ -182,6 +182,7 @@ struct DeviceCtx {
   float* raw = nullptr;        // [rows][dim]    fp32 (F32 / U8 dtypes)
   __half *qf = nullptr, *tf = nullptr;   // [rows][144] tensor-path operand forms
   int32_t* qnorm = nullptr;    // [rows]
+  uint32_t* u8d = nullptr;     // [rows][32]     byte copy of integer-valued 128-d rows (fix-up kernel)
   uint32_t* bits = nullptr;    // [rows][words]  (U8_BITS)
   int32_t* xy = nullptr;       // [rows][2]
   TcMaps maps{};
@@ -242,7 +243,7 @@ struct DeviceCtx {
     for (auto& s : slots) s.destroy();
     single.destroy();
     auto fd = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
-    fd(raw); fd(qf); fd(tf); fd(qnorm); fd(bits); fd(xy); fd(d_flag); fd(stage); fd(d_dump);
+    fd(raw); fd(qf); fd(tf); fd(qnorm); fd(u8d); fd(bits); fd(xy); fd(d_flag); fd(stage); fd(d_dump);
     if (h_flag) cudaFreeHost(h_flag);
     if (ingest) cudaStreamDestroy(ingest);
     if (knn_stream) cudaStreamDestroy(knn_stream);
@@ -316,6 +317,7 @@ struct DeviceCtx {
         if ((rc = grow(qf, TC_KPAD, nc)) != PM_OK) return rc;
         if ((rc = grow(tf, TC_KPAD, nc)) != PM_OK) return rc;
         if ((rc = grow(qnorm, 1, nc)) != PM_OK) return rc;
+        if ((rc = grow(u8d, 32, nc)) != PM_OK) return rc;
       }
     }
     if ((rc = grow(xy, 2, nc)) != PM_OK) return rc;
@@ -395,7 +397,7 @@ struct DeviceCtx {
           PM_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), ingest));
           PM_CUDA(launch_pack_sift(u8src ? nullptr : rdst, u8src, n, qf + static_cast<size_t>(im.row) * TC_KPAD,
                                    tf + static_cast<size_t>(im.row) * TC_KPAD, qnorm + im.row,
-                                   u8src ? rdst : nullptr, d_flag, ingest));
+                                   u8src ? rdst : nullptr, u8d + static_cast<size_t>(im.row) * 32, d_flag, ingest));
           ++stats.kernel_launches;
           PM_CUDA(cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ingest));
         }
@@ -475,7 +477,7 @@ struct DeviceCtx {
   }
 
   // Queues the kNN kernel(s) of a batch whose jobs are already in s.h_jobs[0..n).
-  int enqueue_knn(Slot& s, int n, bool want_rev, bool timed, float* dump = nullptr) {
+  int enqueue_knn(Slot& s, int n, bool want_rev, bool timed, float* dump = nullptr, bool fast = false) {
     int max_nq = 0, max_nt = 0;
     bool all_integral = true;
     double work = 0;
@@ -495,46 +497,59 @@ struct DeviceCtx {
     // the slot's own stream carries the small tail kernels and the D2H, overlapping the next kNN.
     PM_CUDA(cudaEventRecord(s.ev_jobs, s.stream));
     PM_CUDA(cudaStreamWaitEvent(knn_stream, s.ev_jobs, 0));
-    const int epi = (prm.debug_flags >> 2) & 7;
+    // debug_flags (kernel variants; 0 = product defaults):
+    //   bit0      force the fp32 SIMT L2 kernel
+    //   bit1      Hamming: carry-save popc variant
+    //   bits2-4   GENERAL tensor kernel (exact top-2 with indices; raw kNN rows / single-pair calls):
+    //             0 single-CTA 16 epilogue warps (default), 1 x32 / 8 warps, 2 x64 overlapped, 3 x128,
+    //             4 timing probe, 5 CTA pair 256-col tiles, 6 pair probe, 7 CTA pair 192-col tiles
+    //   bit5      pair-192 timing probe
+    //   bit6      batched loop uses the general kernel instead of values-only kernel + fix-up
+    //   bits7-8   VALUES-ONLY kernel of the batched loop: 0 CTA pair 256-col (default), 1 single-CTA,
+    //             2 CTA pair 192-col
+    const int code = (prm.debug_flags >> 2) & 7;
+    const int fcode = (prm.debug_flags >> 7) & 3;
     const int variant = (prm.debug_flags >> 1) & 1;
     const bool use_tc = tc_ready && all_integral && !(prm.debug_flags & 1);
-    if (timed) PM_CUDA(cudaEventRecord(s.ev_k0, knn_stream));
-    if (dtype == PM_DESC_U8_BITS) {
-      PM_CUDA(launch_hamming_top2(bits, words, s.d_jobs, n, max_nq, s.knn_idx, s.knn_dist, s.stride, variant,
-                                  knn_stream));
-      s.knn_work = work * words;
-    } else if (use_tc) {
-      if (epi >= 5 && !dump)
-        PM_CUDA(launch_l2_tc2(maps, qnorm, s.d_jobs, n, max_nq, s.knn_idx, s.knn_dist, s.stride, num_sms, epi == 7,
-                              epi == 6 || ((prm.debug_flags >> 5) & 1), knn_stream));
-      else
-        PM_CUDA(launch_l2_tc(maps, qnorm, s.d_jobs, n, max_nq, s.knn_idx, s.knn_dist, s.stride, num_sms, dump,
-                             epi, knn_stream));
-      s.knn_work = work * 2.0 * dim;
-    } else {
-      PM_CUDA(launch_l2_simt(raw, dim, s.d_jobs, n, max_nq, s.knn_idx, s.knn_dist, s.stride, knn_stream));
-      s.knn_work = work * 2.0 * dim;
-    }
-    if (timed) PM_CUDA(cudaEventRecord(s.ev_k1, knn_stream));
-    s.timed = timed;
-    ++stats.kernel_launches;
-    if (want_rev) {
+    const bool use_fast = use_tc && fast && !dump && !((prm.debug_flags >> 6) & 1);
+    const int epi_of_code[5] = {3, 0, 1, 2, 4};
+    auto knn_main = [&](const PairJob* jobs_d, int mq, int2* oi, float2* od) -> cudaError_t {
       if (dtype == PM_DESC_U8_BITS)
-        PM_CUDA(launch_hamming_top2(bits, words, s.d_rjobs, n, max_nt, s.rev_idx, s.rev_dist, s.stride, variant,
-                                    knn_stream));
-      else if (use_tc)
-        if (epi >= 5)
-          PM_CUDA(launch_l2_tc2(maps, qnorm, s.d_rjobs, n, max_nt, s.rev_idx, s.rev_dist, s.stride, num_sms, epi == 7, 0,
-                                knn_stream));
-        else
-          PM_CUDA(launch_l2_tc(maps, qnorm, s.d_rjobs, n, max_nt, s.rev_idx, s.rev_dist, s.stride, num_sms,
-                               nullptr, epi, knn_stream));
-      else
-        PM_CUDA(launch_l2_simt(raw, dim, s.d_rjobs, n, max_nt, s.rev_idx, s.rev_dist, s.stride, knn_stream));
+        return launch_hamming_top2(bits, words, jobs_d, n, mq, oi, od, s.stride, variant, knn_stream);
+      if (!use_tc) return launch_l2_simt(raw, dim, jobs_d, n, mq, oi, od, s.stride, knn_stream);
+      if (use_fast) {
+        if (fcode == 1) return launch_l2_tc(maps, qnorm, jobs_d, n, mq, oi, od, s.stride, num_sms, nullptr, 5, knn_stream);
+        return launch_l2_tc2(maps, qnorm, jobs_d, n, mq, oi, od, s.stride, num_sms, fcode == 2, 2, knn_stream);
+      }
+      if (code >= 5 && !dump)
+        return launch_l2_tc2(maps, qnorm, jobs_d, n, mq, oi, od, s.stride, num_sms, code == 7,
+                             (code == 6 || ((prm.debug_flags >> 5) & 1)) ? 1 : 0, knn_stream);
+      return launch_l2_tc(maps, qnorm, jobs_d, n, mq, oi, od, s.stride, num_sms, dump,
+                          dump ? 0 : epi_of_code[code < 5 ? code : 0], knn_stream);
+    };
+    if (timed) PM_CUDA(cudaEventRecord(s.ev_k0, knn_stream));
+    PM_CUDA(knn_main(s.d_jobs, max_nq, s.knn_idx, s.knn_dist));
+    if (timed) PM_CUDA(cudaEventRecord(s.ev_k1, knn_stream));
+    ++stats.kernel_launches;
+    s.knn_work = dtype == PM_DESC_U8_BITS ? work * words : work * 2.0 * dim;
+    s.timed = timed;
+    if (want_rev) {
+      PM_CUDA(knn_main(s.d_rjobs, max_nt, s.rev_idx, s.rev_dist));
       ++stats.kernel_launches;
     }
     PM_CUDA(cudaEventRecord(s.ev_knn, knn_stream));
     PM_CUDA(cudaStreamWaitEvent(s.stream, s.ev_knn, 0));
+    if (use_fast) {
+      // exact indices / second neighbour, on the slot's stream so that it overlaps the next batch's
+      // tensor kernel: rows that can still pass the ratio test, and -- for the cross-check, which needs
+      // the nearest query of EVERY train row -- all rows of the reversed search
+      PM_CUDA(launch_l2_fixup(u8d, qnorm, s.d_jobs, n, max_nq, 0, s.knn_idx, s.knn_dist, s.stride, prm.ratio, 0, s.stream));
+      ++stats.kernel_launches;
+      if (want_rev) {
+        PM_CUDA(launch_l2_fixup(u8d, qnorm, s.d_rjobs, n, max_nt, 0, s.rev_idx, s.rev_dist, s.stride, prm.ratio, 1, s.stream));
+        ++stats.kernel_launches;
+      }
+    }
     return PM_OK;
   }
   std::vector<char> job_integral;   // per job of the batch being built
@@ -650,7 +665,7 @@ struct DeviceCtx {
         rc = fill_job(s, k, pairs[2 * (done + k)], pairs[2 * (done + k) + 1]);
         if (rc != PM_OK) return rc;
       }
-      if ((rc = enqueue_knn(s, n, mutual, true)) != PM_OK) return rc;
+      if ((rc = enqueue_knn(s, n, mutual, true, nullptr, true)) != PM_OK) return rc;
       if ((rc = enqueue_tail(s, n, prm.do_filter != 0)) != PM_OK) return rc;
       s.busy = true; s.n_jobs = n; s.first_pair = first + done;
       done += n;

@@ -44,13 +44,18 @@ cudaError_t launch_l2_tc(const TcMaps& maps, const int32_t* qnorm, const PairJob
 // K2, CTA-pair version -- l2_tc2.cu (tcgen05 cta_group::2)
 cudaError_t tc2_configure();
 cudaError_t launch_l2_tc2(const TcMaps& maps, const int32_t* qnorm, const PairJob* jobs, int n_jobs, int max_nq,
-                          int2* idx, float2* dist, int stride, int num_sms, int variant, int probe,
+                          int2* idx, float2* dist, int stride, int num_sms, int variant, int mode,
                           cudaStream_t st);
+
+// l2_fixup.cu -- exact index / 2nd-neighbour recovery after the branch-free tensor epilogue
+cudaError_t launch_l2_fixup(const uint32_t* u8desc, const int32_t* qnorm, const PairJob* jobs, int n_jobs,
+                            int max_nq, int reversed, int2* idx, float2* dist, int stride, float ratio,
+                            int all_rows, cudaStream_t st);
 
 // pack.cu
 cudaError_t launch_pack_sift(const float* raw_f32, const uint8_t* raw_u8, int n, __half* qf,
-                             __half* tf, int32_t* qnorm, float* raw_out, int* not_integral,
-                             cudaStream_t st);
+                             __half* tf, int32_t* qnorm, float* raw_out, uint32_t* u8_out,
+                             int* not_integral, cudaStream_t st);
 cudaError_t launch_u8_to_f32(const uint8_t* src, float* dst, size_t n, cudaStream_t st);
 
 // K4 -- select.cu

@@ -35,7 +35,7 @@ static constexpr int TC_BM = 128;             // rows per m-tile (UMMA M)
 static constexpr int TC_MT = 2;               // m-tiles per CTA
 static constexpr int TC_ROWS = TC_BM * TC_MT; // query rows per work item
 static constexpr int TC_BN = 128;             // train rows per B tile (UMMA N)
-static constexpr int TC_STAGES = 4;
+static constexpr int TC_STAGES = 3;   // 3 x 36 KB: leaves ~40 KB of shared memory per SM for the tail kernels to co-reside
 static constexpr int TC_ATOM_BYTES = TC_BM * 128;                 // 128 rows x 128 B  (SW128 atom column)
 static constexpr int TC_EXT_BYTES = TC_BM * 32;                   // 128 rows x 32 B   (SW32 block)
 static constexpr int TC_TILE_BYTES = 2 * TC_ATOM_BYTES + TC_EXT_BYTES;   // 36 KB
@@ -46,6 +46,8 @@ static constexpr int TC_SMEM_BYTES = TC_SMEM_A + TC_SMEM_B + 1024 /*align slack*
 // EPI 0..2: 8 epilogue warps (one per m-tile x lane quarter); EPI 3: 16 epilogue warps, the two
 // warps of a (m-tile, quarter) split the 128 columns of a tile in halves.
 __host__ __device__ constexpr int tc_threads(int epi) { return epi >= 3 ? 640 : 384; }
+// EPI 5: like EPI 3 (16 epilogue warps) but the epilogue only tracks values + winning chunk; exact
+// indices are recovered by l2_fixup.cu.
 static constexpr uint32_t TC_TMEM_COLS = 512;
 
 // kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, N=128, M=128.
@@ -190,6 +192,28 @@ __device__ __forceinline__ void scan32(Top2& s, const uint32_t* r, int col0) {
   }
 }
 
+// Minimum of 32 consecutive columns (branch-free; 3-input min where the compiler finds it).
+__device__ __forceinline__ float min32(const uint32_t* r) {
+  float g[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    g[k] = fminf(fminf(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1])),
+                 fminf(__uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3])));
+  return fminf(fminf(fminf(g[0], g[1]), fminf(g[2], g[3])), fminf(fminf(g[4], g[5]), fminf(g[6], g[7])));
+}
+// Values-only running state of the fast epilogue (EPI 5): smallest value, second smallest chunk
+// minimum, base column of the first chunk that attained the smallest value.  No branches.
+struct Fast2 {
+  float m1, m2;
+  int b1;
+};
+__device__ __forceinline__ void fast_update(Fast2& s, float cm, int cbase) {
+  const float t = fmaxf(cm, s.m1);
+  s.b1 = cm < s.m1 ? cbase : s.b1;                   // strict: the earliest chunk keeps a tie
+  s.m1 = fminf(cm, s.m1);
+  s.m2 = fminf(s.m2, t);
+}
+
 template <int EPI, int SCAN = (EPI == 3 ? 2 : 0)>
 __global__ void __launch_bounds__(tc_threads(EPI), 1)
 l2_top2_tc_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant__ CUtensorMap q_ext,
@@ -325,6 +349,9 @@ l2_top2_tc_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_const
       Top2 s;
       s.m1 = s.m2 = __int_as_float(0x7f800000);
       s.i1 = s.i2 = -1;
+      Fast2 fs;
+      fs.m1 = fs.m2 = __int_as_float(0x7f800000);
+      fs.b1 = -1;
       const int n_tiles = (job.nt + TC_BN - 1) / TC_BN;
       for (int n = 0; n < n_tiles; ++n, ++ti) {
         const uint32_t as = ti & 1, use = ti >> 1;
@@ -341,7 +368,33 @@ l2_top2_tc_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_const
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[as * 2 + m]);
         };
-        if constexpr (EPI == 4) {
+        if constexpr (EPI == 5) {
+          const uint32_t t0 = taddr + half * 64;
+          const int c0 = col_base + half * 64;
+          uint32_t v[32];
+          if (valid >= TC_BN) {
+            tmem_ld_32x32b_x32(t0, v);
+            fast_update(fs, min32(v), c0);
+            tmem_ld_32x32b_x32(t0 + 32, v);
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(&acc_empty[as * 2 + m]);
+            fast_update(fs, min32(v), c0 + 32);
+          } else {
+            const int lim = valid - half * 64;
+            tmem_ld_32x32b_x32(t0, v);
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (e >= lim) v[e] = 0x7f800000u;
+            if (lim > 0) fast_update(fs, min32(v), c0);
+            tmem_ld_32x32b_x32(t0 + 32, v);
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(&acc_empty[as * 2 + m]);
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (32 + e >= lim) v[e] = 0x7f800000u;
+            if (lim > 32) fast_update(fs, min32(v), c0 + 32);
+          }
+        } else if constexpr (EPI == 4) {
           // PROBE ONLY (results are garbage): hand the accumulator straight back, to time the
           // TMA + MMA pipeline without any epilogue work.
           tc_fence_before();
@@ -427,7 +480,28 @@ l2_top2_tc_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_const
           scan32(s, &vb[32], col_base + 96);
         }
       }
-      if constexpr (EPI >= 3) {
+      if constexpr (EPI == 5) {
+        float4* slot = xchg + ((m * 4 + quarter) * 32 + lane);
+        const int bar_id = 1 + m * 4 + quarter;
+        if (half == 1) *slot = make_float4(fs.m1, __int_as_float(fs.b1), fs.m2, 0.f);
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        if (half == 0) {
+          const float4 o = *slot;
+          const int ob = __float_as_int(o.y);
+          const bool take = ob >= 0 && (fs.b1 < 0 || o.x < fs.m1 || (o.x == fs.m1 && ob < fs.b1));
+          const float hi = fmaxf(fs.m1, o.x);
+          fs.m2 = fminf(fminf(fs.m2, o.z), hi);
+          fs.m1 = fminf(fs.m1, o.x);
+          fs.b1 = take ? ob : fs.b1;
+          if (row < job.nq) {
+            const float na = static_cast<float>(qnorm[job.q_row + row]);
+            const size_t o2 = static_cast<size_t>(jb) * stride + row;
+            knn_idx[o2] = make_int2(fs.b1, -2);                       // -2: "values only, run the fix-up"
+            knn_dist[o2] = make_float2(__fadd_rn(fs.m1, na), __fadd_rn(fs.m2, na));   // exact d^2 / bound
+          }
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+      } else if constexpr (EPI >= 3) {
         // the two column-split warps of this (m-tile, quarter) merge their top-2 through smem
         float4* slot = xchg + ((m * 4 + quarter) * 32 + lane);
         const int bar_id = 1 + m * 4 + quarter;
@@ -453,7 +527,7 @@ l2_top2_tc_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_const
         }
         asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
       }
-      if ((EPI < 3 || half == 0) && row < job.nq) {
+      if (EPI != 5 && (EPI < 3 || half == 0) && row < job.nq) {
         const float na = static_cast<float>(qnorm[job.q_row + row]);
         int2 oi;
         float2 od;
@@ -481,6 +555,7 @@ cudaError_t tc_configure() {
   if ((e = cudaFuncSetAttribute(l2_top2_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(l2_top2_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(l2_top2_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(l2_top2_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) != cudaSuccess) return e;
   return cudaFuncSetAttribute(l2_top2_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
 }
 
@@ -499,7 +574,8 @@ cudaError_t launch_l2_tc(const TcMaps& maps, const int32_t* qnorm, const PairJob
   else if (epi == 1) PM_TC_LAUNCH(1);
   else if (epi == 2) PM_TC_LAUNCH(2);
   else if (epi == 3) PM_TC_LAUNCH(3);
-  else PM_TC_LAUNCH(4);
+  else if (epi == 4) PM_TC_LAUNCH(4);
+  else PM_TC_LAUNCH(5);
 #undef PM_TC_LAUNCH
   return cudaGetLastError();
 }

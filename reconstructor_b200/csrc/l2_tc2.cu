@@ -45,7 +45,7 @@ struct T2Cfg {
   static constexpr int kEpiWarps = 4 * kSlices;
   static constexpr int kThreads = 128 + 32 * kEpiWarps;
   static constexpr int kBAtom = kBNH * 128, kBExt = kBNH * 32, kBTile = 2 * kBAtom + kBExt;
-  static constexpr int kStages = BN == 256 ? 4 : 5;
+  static constexpr int kStages = BN == 256 ? 3 : 4;
   static constexpr int kSmemB = kStages * kBTile;
   static constexpr int kXchg = 4 * (kSlices - 1) * 32 * 16;
   static constexpr int kSmemBytes = T2_SMEM_A + kSmemB + 1024 + 256 + kXchg;
@@ -167,6 +167,20 @@ __device__ __forceinline__ void t2_scan32(Top2p& s, const uint32_t* r, int col0)
     } while (mask);
   }
 }
+// Values-only update (MODE 2): branch-free; s.i1 carries the base column of the earliest chunk that
+// attained the minimum, s.m2 the second smallest chunk minimum (see l2_fixup.cu).
+__device__ __forceinline__ void t2_fast(Top2p& s, const uint32_t* r, int cbase) {
+  float g[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    g[k] = fminf(fminf(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1])),
+                 fminf(__uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3])));
+  const float cm = fminf(fminf(fminf(g[0], g[1]), fminf(g[2], g[3])), fminf(fminf(g[4], g[5]), fminf(g[6], g[7])));
+  const float t = fmaxf(cm, s.m1);
+  s.i1 = cm < s.m1 ? cbase : s.i1;
+  s.m1 = fminf(cm, s.m1);
+  s.m2 = fminf(s.m2, t);
+}
 // ordered by (value, index)
 __device__ __forceinline__ bool t2_less(float va, int ia, float vb, int ib) { return va < vb || (va == vb && ia < ib); }
 __device__ __forceinline__ void t2_merge(Top2p& s, float om1, int oi1, float om2, int oi2) {
@@ -183,7 +197,7 @@ __device__ __forceinline__ void t2_merge(Top2p& s, float om1, int oi1, float om2
   s = t;
 }
 
-template <class Cfg, int PROBE>
+template <class Cfg, int MODE>   // 0: exact top-2 with indices, 1: timing probe, 2: values-only (fix-up follows)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::kThreads, 1)
 l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant__ CUtensorMap q_ext,
                    const __grid_constant__ CUtensorMap t_main, const __grid_constant__ CUtensorMap t_ext,
@@ -316,7 +330,7 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
       const int row = r * T2_ROWS + rank * T2_BM + quarter * 32 + lane;
       Top2p s;
       s.m1 = s.m2 = __int_as_float(0x7f800000);
-      s.i1 = s.i2 = -1;
+      s.i1 = s.i2 = -1;                                // MODE 2: i1 = base column of the winning 32-column chunk
       const int n_tiles = (job.nt + T2_BN - 1) / T2_BN;
       for (int n = 0; n < n_tiles; ++n, ++ti) {
         const uint32_t as = ti & 1, use = ti >> 1;
@@ -326,7 +340,7 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
         const int c0 = n * T2_BN + slice * (32 * CPW);
         const int lim = job.nt - c0;                   // columns of this slice that exist
         uint32_t v[32];
-        if (PROBE) {
+        if (MODE == 1) {
           tc_fence_before();
           if (lane == 0) mbar_arrive_leader(&acc_empty[as]);
         } else if (lim >= 32 * CPW) {
@@ -337,7 +351,8 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
               tc_fence_before();
               if (lane == 0) mbar_arrive_leader(&acc_empty[as]);
             }
-            t2_scan32(s, v, c0 + 32 * c);
+            if (MODE == 2) t2_fast(s, v, c0 + 32 * c);
+            else t2_scan32(s, v, c0 + 32 * c);
           }
         } else {
 #pragma unroll
@@ -350,7 +365,8 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
 #pragma unroll
             for (int e = 0; e < 32; ++e)
               if (32 * c + e >= lim) v[e] = 0x7f800000u;
-            t2_scan32(s, v, c0 + 32 * c);
+            if (MODE == 2) { if (lim > 32 * c) t2_fast(s, v, c0 + 32 * c); }
+            else t2_scan32(s, v, c0 + 32 * c);
           }
         }
       }
@@ -364,12 +380,26 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
 #pragma unroll
           for (int o = 0; o < NSL - 1; ++o) {
             const float4 x = slot[o * 32];
-            t2_merge(s, x.x, __float_as_int(x.y), x.z, __float_as_int(x.w));
+            if (MODE == 2) {
+              const int ob = __float_as_int(x.y);
+              const bool take = ob >= 0 && (s.i1 < 0 || x.x < s.m1 || (x.x == s.m1 && ob < s.i1));
+              const float hi = fmaxf(s.m1, x.x);
+              s.m2 = fminf(fminf(s.m2, x.z), hi);
+              s.m1 = fminf(s.m1, x.x);
+              s.i1 = take ? ob : s.i1;
+            } else {
+              t2_merge(s, x.x, __float_as_int(x.y), x.z, __float_as_int(x.w));
+            }
           }
         }
         asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NSL) : "memory");
       }
-      if (slice == 0 && row < job.nq) {
+      if (MODE == 2 && slice == 0 && row < job.nq) {
+        const float na = static_cast<float>(qnorm[job.q_row + row]);
+        const size_t o = static_cast<size_t>(jb) * stride + row;
+        knn_idx[o] = make_int2(s.i1, -2);
+        knn_dist[o] = make_float2(__fadd_rn(s.m1, na), __fadd_rn(s.m2, na));
+      } else if (slice == 0 && row < job.nq) {
         const float na = static_cast<float>(qnorm[job.q_row + row]);
         int2 oi;
         float2 od;
@@ -397,15 +427,19 @@ using T2Deep = T2Cfg<192, 1>;     // 24 epilogue warps
 
 cudaError_t tc2_configure() {
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(l2_top2_tc2_kernel<T2Wide, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2Wide::kSmemBytes)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(l2_top2_tc2_kernel<T2Wide, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2Wide::kSmemBytes)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(l2_top2_tc2_kernel<T2Deep, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2Deep::kSmemBytes)) != cudaSuccess) return e;
-  return cudaFuncSetAttribute(l2_top2_tc2_kernel<T2Deep, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2Deep::kSmemBytes);
+#define PM_T2_ATTR(CFG, M)                                                                                       \
+  if ((e = cudaFuncSetAttribute(l2_top2_tc2_kernel<CFG, M>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                                CFG::kSmemBytes)) != cudaSuccess) return e
+  PM_T2_ATTR(T2Wide, 0); PM_T2_ATTR(T2Wide, 1); PM_T2_ATTR(T2Wide, 2);
+  PM_T2_ATTR(T2Deep, 0); PM_T2_ATTR(T2Deep, 1); PM_T2_ATTR(T2Deep, 2);
+#undef PM_T2_ATTR
+  return cudaSuccess;
 }
 
 // variant 0: 256-column tiles / 16 epilogue warps; variant 1: 192-column tiles / 24 epilogue warps.
+// mode 0: exact top-2 with indices; 1: timing probe (garbage results); 2: values only (run l2_fixup next).
 cudaError_t launch_l2_tc2(const TcMaps& maps, const int32_t* qnorm, const PairJob* jobs, int n_jobs, int max_nq,
-                          int2* idx, float2* dist, int stride, int num_sms, int variant, int probe, cudaStream_t st) {
+                          int2* idx, float2* dist, int stride, int num_sms, int variant, int mode, cudaStream_t st) {
   if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
   const int tiles_per_job = (max_nq + T2_ROWS - 1) / T2_ROWS;
   const int n_items = n_jobs * tiles_per_job;
@@ -414,11 +448,14 @@ cudaError_t launch_l2_tc2(const TcMaps& maps, const int32_t* qnorm, const PairJo
   const int grid = clusters * 2;
   const CUtensorMap& tm = variant == 1 ? maps.t_main96 : maps.t_main;
   const CUtensorMap& te = variant == 1 ? maps.t_ext96 : maps.t_ext;
-#define PM_T2_LAUNCH(CFG, P)                                                                         \
-  l2_top2_tc2_kernel<CFG, P><<<grid, CFG::kThreads, CFG::kSmemBytes, st>>>(                          \
+#define PM_T2_LAUNCH(CFG, M)                                                                         \
+  l2_top2_tc2_kernel<CFG, M><<<grid, CFG::kThreads, CFG::kSmemBytes, st>>>(                          \
       maps.q_main, maps.q_ext, tm, te, qnorm, jobs, n_jobs, tiles_per_job, idx, dist, stride)
-  if (variant == 1) { if (probe) PM_T2_LAUNCH(T2Deep, 1); else PM_T2_LAUNCH(T2Deep, 0); }
-  else { if (probe) PM_T2_LAUNCH(T2Wide, 1); else PM_T2_LAUNCH(T2Wide, 0); }
+  if (variant == 1) {
+    if (mode == 1) PM_T2_LAUNCH(T2Deep, 1); else if (mode == 2) PM_T2_LAUNCH(T2Deep, 2); else PM_T2_LAUNCH(T2Deep, 0);
+  } else {
+    if (mode == 1) PM_T2_LAUNCH(T2Wide, 1); else if (mode == 2) PM_T2_LAUNCH(T2Wide, 2); else PM_T2_LAUNCH(T2Wide, 0);
+  }
 #undef PM_T2_LAUNCH
   return cudaGetLastError();
 }

@@ -16,7 +16,7 @@ namespace pm {
 __global__ void __launch_bounds__(256)
 pack_sift_kernel(const float* __restrict__ raw_f32, const uint8_t* __restrict__ raw_u8, int n,
                  __half* __restrict__ qf, __half* __restrict__ tf, int32_t* __restrict__ qnorm,
-                 float* __restrict__ raw_out, int* __restrict__ not_integral) {
+                 float* __restrict__ raw_out, uint32_t* __restrict__ u8_out, int* __restrict__ not_integral) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
@@ -31,6 +31,12 @@ pack_sift_kernel(const float* __restrict__ raw_f32, const uint8_t* __restrict__ 
   if (raw_out)
     *reinterpret_cast<float4*>(raw_out + static_cast<size_t>(row) * TC_DIM + 4 * lane) =
         make_float4(v[0], v[1], v[2], v[3]);
+  // byte copy of the row (4 values per word) for the integer fix-up kernel
+  u8_out[static_cast<size_t>(row) * 32 + lane] =
+      static_cast<uint32_t>(static_cast<int>(fminf(fmaxf(v[0], 0.f), 255.f))) |
+      (static_cast<uint32_t>(static_cast<int>(fminf(fmaxf(v[1], 0.f), 255.f))) << 8) |
+      (static_cast<uint32_t>(static_cast<int>(fminf(fmaxf(v[2], 0.f), 255.f))) << 16) |
+      (static_cast<uint32_t>(static_cast<int>(fminf(fmaxf(v[3], 0.f), 255.f))) << 24);
   bool bad = false;
   int nrm = 0;
 #pragma unroll
@@ -67,10 +73,10 @@ pack_sift_kernel(const float* __restrict__ raw_f32, const uint8_t* __restrict__ 
 }
 
 cudaError_t launch_pack_sift(const float* raw_f32, const uint8_t* raw_u8, int n, __half* qf,
-                             __half* tf, int32_t* qnorm, float* raw_out, int* not_integral,
-                             cudaStream_t st) {
+                             __half* tf, int32_t* qnorm, float* raw_out, uint32_t* u8_out,
+                             int* not_integral, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
-  pack_sift_kernel<<<(n + 7) / 8, 256, 0, st>>>(raw_f32, raw_u8, n, qf, tf, qnorm, raw_out,
+  pack_sift_kernel<<<(n + 7) / 8, 256, 0, st>>>(raw_f32, raw_u8, n, qf, tf, qnorm, raw_out, u8_out,
                                                 not_integral);
   return cudaGetLastError();
 }

@@ -370,3 +370,48 @@ def test_full_size_8192_pair(kind):
         q, t = res["q"][a:b], res["t"][a:b]
         assert (np.diff(q) > 0).all() and len(np.unique(t)) == len(t)
         assert b - a > 1500 and res["n_inliers"][p] > 0.85 * (b - a)
+
+
+# ---------------------------------------------------------------------------------------------
+# values-only tensor epilogue + fix-up (the default batched path) vs the general kernels
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("flags", [0, 20])
+@pytest.mark.parametrize("mode", [api.UNIQUE_FIRST_WINS, api.MUTUAL_NN, api.UNIQUE_NONE])
+def test_batched_fast_path_equals_oracle_all_modes(mode, flags):
+    w = synth.World("sift", 900, seed=33)
+    imgs = []
+    for i in range(5):
+        d, xy, _ = w.image(i, 5, outlier_frac=0.2)
+        cut = 900 - 61 * i
+        d = d[:cut].copy(); xy = xy[:cut]
+        if i == 1:                       # duplicates: equal distances inside one 32-column chunk and across chunks
+            d[40] = d[7]; d[300] = d[7]; d[301] = d[7]
+        imgs.append((d, xy))
+    with api.PairMatcher(unique_mode=mode, batch_pairs=3, debug_flags=flags) as pm:
+        for i, (d, xy) in enumerate(imgs):
+            pm.set_image(i, d, xy)
+        res = pm.match_all_pairs()
+    for p, (i, j) in enumerate(res["pair_ij"]):
+        ref = orc.match_pair(imgs[i][0], imgs[i][1], imgs[j][0], imgs[j][1], unique_mode=mode)
+        a, b = res["offsets"][p], res["offsets"][p + 1]
+        assert b - a == ref["n_putative"], (mode, p, b - a, ref["n_putative"])
+        keep = res["inlier"][a:b].astype(bool)
+        assert np.array_equal(res["q"][a:b][keep], ref["q"]) and np.array_equal(res["t"][a:b][keep], ref["t"]), (mode, p)
+
+
+def test_batched_fast_path_equals_general_kernel_full_size():
+    """8192-keypoint images: the values-only kernel + fix-up must reproduce the general tensor kernel
+    and the SIMT kernel bit for bit (CSR arrays identical)."""
+    w = synth.World("sift", 8192, seed=0xB200 + 2)
+    imgs = [w.image(i, 100, outlier_frac=0.3 if i == 2 else 0.0)[:2] for i in range(6)]
+    outs = []
+    for flags in (0, 20, 28, 64, 1):   # fast single-CTA, fast CTA-pair (256 / 192 col), general tensor, SIMT
+        with api.PairMatcher(debug_flags=flags) as pm:
+            for i, (d, xy) in enumerate(imgs):
+                pm.set_image(i, d, xy)
+            outs.append(pm.match_all_pairs())
+    for o in outs[1:]:
+        for k in ("offsets", "q", "t", "inlier", "status", "n_inliers", "ransac_iters"):
+            assert np.array_equal(outs[0][k], o[k]), k
+        assert np.array_equal(outs[0]["F"], o["F"])
+    assert outs[0]["offsets"][-1] > 15 * 1500
