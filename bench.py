@@ -298,7 +298,7 @@ def main():
                     peak_source="MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if pk
                     else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)")
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof["kernel"] = {"sift": "l2_top2_tc_kernel", "orb": "hamming_top2_kernel", "superpoint": "l2_top2_simt_kernel"}[a.kind]
+    roof["kernel"] = {"sift": "l2_top2_tc2_kernel", "orb": "hamming_top2_kernel", "superpoint": "l2_top2_simt_kernel"}[a.kind]
     roof["launches"] = st["knn_launches"]
     roof["avg_launch_ms"] = st["knn_ms"] / max(st["knn_launches"], 1)
     roof["share_of_step"] = st["knn_ms"] / max(dev_ms, 1e-9) if world == 1 else None

@@ -375,7 +375,7 @@ def test_full_size_8192_pair(kind):
 # ---------------------------------------------------------------------------------------------
 # values-only tensor epilogue + fix-up (the default batched path) vs the general kernels
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("flags", [0, 20])
+@pytest.mark.parametrize("flags", [0, 128, 256])
 @pytest.mark.parametrize("mode", [api.UNIQUE_FIRST_WINS, api.MUTUAL_NN, api.UNIQUE_NONE])
 def test_batched_fast_path_equals_oracle_all_modes(mode, flags):
     w = synth.World("sift", 900, seed=33)
@@ -405,7 +405,9 @@ def test_batched_fast_path_equals_general_kernel_full_size():
     w = synth.World("sift", 8192, seed=0xB200 + 2)
     imgs = [w.image(i, 100, outlier_frac=0.3 if i == 2 else 0.0)[:2] for i in range(6)]
     outs = []
-    for flags in (0, 20, 28, 64, 1):   # fast single-CTA, fast CTA-pair (256 / 192 col), general tensor, SIMT
+    # values-only kernels (CTA pair 256-col = default, single-CTA, pair 192-col), general tensor kernels
+    # (single-CTA, CTA pair), fp32 SIMT
+    for flags in (0, 128, 256, 64, 64 + 20, 1):
         with api.PairMatcher(debug_flags=flags) as pm:
             for i, (d, xy) in enumerate(imgs):
                 pm.set_image(i, d, xy)
