@@ -192,17 +192,17 @@ __device__ __forceinline__ void scan32(Top2& s, const uint32_t* r, int col0) {
   }
 }
 
-// Minimum of 32 consecutive columns (branch-free; 3-input min where the compiler finds it).
-__device__ __forceinline__ float min32(const uint32_t* r) {
-  float g[8];
+// Minimum of 16 consecutive columns (branch-free; 3-input min where the compiler finds it).
+__device__ __forceinline__ float min16(const uint32_t* r) {
+  float g[4];
 #pragma unroll
-  for (int k = 0; k < 8; ++k)
+  for (int k = 0; k < 4; ++k)
     g[k] = fminf(fminf(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1])),
                  fminf(__uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3])));
-  return fminf(fminf(fminf(g[0], g[1]), fminf(g[2], g[3])), fminf(fminf(g[4], g[5]), fminf(g[6], g[7])));
+  return fminf(fminf(g[0], g[1]), fminf(g[2], g[3]));
 }
 // Values-only running state of the fast epilogue (EPI 5): smallest value, second smallest chunk
-// minimum, base column of the first chunk that attained the smallest value.  No branches.
+// minimum, base column of the first 16-column chunk that attained the smallest value.  No branches.
 struct Fast2 {
   float m1, m2;
   int b1;
@@ -374,25 +374,29 @@ l2_top2_tc_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_const
           uint32_t v[32];
           if (valid >= TC_BN) {
             tmem_ld_32x32b_x32(t0, v);
-            fast_update(fs, min32(v), c0);
+            fast_update(fs, min16(v), c0);
+            fast_update(fs, min16(v + 16), c0 + 16);
             tmem_ld_32x32b_x32(t0 + 32, v);
             tc_fence_before();
             if (lane == 0) mbar_arrive(&acc_empty[as * 2 + m]);
-            fast_update(fs, min32(v), c0 + 32);
+            fast_update(fs, min16(v), c0 + 32);
+            fast_update(fs, min16(v + 16), c0 + 48);
           } else {
             const int lim = valid - half * 64;
             tmem_ld_32x32b_x32(t0, v);
 #pragma unroll
             for (int e = 0; e < 32; ++e)
               if (e >= lim) v[e] = 0x7f800000u;
-            if (lim > 0) fast_update(fs, min32(v), c0);
+            if (lim > 0) fast_update(fs, min16(v), c0);
+            if (lim > 16) fast_update(fs, min16(v + 16), c0 + 16);
             tmem_ld_32x32b_x32(t0 + 32, v);
             tc_fence_before();
             if (lane == 0) mbar_arrive(&acc_empty[as * 2 + m]);
 #pragma unroll
             for (int e = 0; e < 32; ++e)
               if (32 + e >= lim) v[e] = 0x7f800000u;
-            if (lim > 32) fast_update(fs, min32(v), c0 + 32);
+            if (lim > 32) fast_update(fs, min16(v), c0 + 32);
+            if (lim > 48) fast_update(fs, min16(v + 16), c0 + 48);
           }
         } else if constexpr (EPI == 4) {
           // PROBE ONLY (results are garbage): hand the accumulator straight back, to time the

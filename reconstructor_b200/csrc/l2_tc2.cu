@@ -167,19 +167,23 @@ __device__ __forceinline__ void t2_scan32(Top2p& s, const uint32_t* r, int col0)
     } while (mask);
   }
 }
-// Values-only update (MODE 2): branch-free; s.i1 carries the base column of the earliest chunk that
-// attained the minimum, s.m2 the second smallest chunk minimum (see l2_fixup.cu).
-__device__ __forceinline__ void t2_fast(Top2p& s, const uint32_t* r, int cbase) {
-  float g[8];
+// Values-only update (MODE 2): branch-free; s.i1 carries the base column of the earliest 16-column
+// chunk that attained the minimum, s.m2 the second smallest chunk minimum (see l2_fixup.cu).
+__device__ __forceinline__ void t2_fast16(Top2p& s, const uint32_t* r, int cbase) {
+  float g[4];
 #pragma unroll
-  for (int k = 0; k < 8; ++k)
+  for (int k = 0; k < 4; ++k)
     g[k] = fminf(fminf(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1])),
                  fminf(__uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3])));
-  const float cm = fminf(fminf(fminf(g[0], g[1]), fminf(g[2], g[3])), fminf(fminf(g[4], g[5]), fminf(g[6], g[7])));
+  const float cm = fminf(fminf(g[0], g[1]), fminf(g[2], g[3]));
   const float t = fmaxf(cm, s.m1);
   s.i1 = cm < s.m1 ? cbase : s.i1;
   s.m1 = fminf(cm, s.m1);
   s.m2 = fminf(s.m2, t);
+}
+__device__ __forceinline__ void t2_fast(Top2p& s, const uint32_t* r, int cbase) {
+  t2_fast16(s, r, cbase);
+  t2_fast16(s, r + 16, cbase + 16);
 }
 // ordered by (value, index)
 __device__ __forceinline__ bool t2_less(float va, int ia, float vb, int ib) { return va < vb || (va == vb && ia < ib); }
@@ -365,7 +369,10 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
 #pragma unroll
             for (int e = 0; e < 32; ++e)
               if (32 * c + e >= lim) v[e] = 0x7f800000u;
-            if (MODE == 2) { if (lim > 32 * c) t2_fast(s, v, c0 + 32 * c); }
+            if (MODE == 2) {
+              if (lim > 32 * c) t2_fast16(s, v, c0 + 32 * c);
+              if (lim > 32 * c + 16) t2_fast16(s, v + 16, c0 + 32 * c + 16);
+            }
             else t2_scan32(s, v, c0 + 32 * c);
           }
         }

@@ -55,6 +55,8 @@ __device__ bool last_point_collinear(const float2* p) {
 }
 
 // Draws one 7-subset exactly like the sequential sampler; returns false after max_attempts.
+// The RNG stream is consumed index by index (duplicate re-draw), the 14 point loads of a complete
+// subset are then issued together -- same stream, same decisions, one memory latency instead of seven.
 __device__ bool get_subset(const float2* __restrict__ p1, const float2* __restrict__ p2, int n,
                            MwcRng& rng, int max_attempts, int* idx) {
   int iters = 0, i = 0;
@@ -67,11 +69,13 @@ __device__ bool get_subset(const float2* __restrict__ p1, const float2* __restri
         if (v == idx[j]) break;
       if (j < i) continue;
       idx[i] = v;
-      s1[i] = p1[v];
-      s2[i] = p2[v];
       ++i;
     }
-    if (i == 7 && (last_point_collinear(s1) || last_point_collinear(s2))) continue;
+    if (i == 7) {
+#pragma unroll
+      for (int k = 0; k < 7; ++k) { s1[k] = p1[idx[k]]; s2[k] = p2[idx[k]]; }
+      if (last_point_collinear(s1) || last_point_collinear(s2)) continue;
+    }
     break;
   }
   return i == 7 && iters < max_attempts;

@@ -1,0 +1,18 @@
+#!/bin/bash
+# Full round-end style check: every GPU test, smoke, default bench (both arms), launch list and one
+# ncu --set full capture of the dominant kernel.
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.max.sm,power.limit,memory.total --format=csv > gpurun_out/gpu_info.txt 2>&1
+lscpu | grep -E "Model name|^CPU\(s\)" > gpurun_out/cpu_info.txt 2>&1
+timeout 1500 python -m pytest tests -q -m gpu --timeout 600 -p no:cacheprovider > gpurun_out/tests_gpu.log 2>&1; echo "gpu tests exit $?"; tail -5 gpurun_out/tests_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -3 gpurun_out/smoke.log
+timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "reference arm exit $?"; cat gpurun_out/bench_reference.json
+timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench exit $?"; cat gpurun_out/bench_default.json; tail -3 gpurun_out/bench_default.err
+CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e"
+$CMD > gpurun_out/plain_launches.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+echo "ncu launches exit $?"
+CMD2="python bench.py --images 23 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e"
+$CMD2 > gpurun_out/plain_full.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:l2_top2_tc2 -s 1 -c 1 -o gpurun_out/prof_tc2 $CMD2 > gpurun_out/ncu_full.log 2>&1
+echo "ncu full exit $?"; tail -2 gpurun_out/ncu_full.log
