@@ -213,6 +213,8 @@ def main():
     from reconstructor_b200 import api
 
     torch.cuda.set_device(local)
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -302,12 +304,17 @@ def main():
     roof["launches"] = st["knn_launches"]
     roof["avg_launch_ms"] = st["knn_ms"] / max(st["knn_launches"], 1)
     roof["share_of_step"] = st["knn_ms"] / max(dev_ms, 1e-9) if world == 1 else None
-    traffic = None
+    # DRAM bytes per launch of that kernel from the committed ncu --set full capture, scaled to this
+    # run's pairs per launch (null when no capture exists for the kernel)
+    roof["traffic"] = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(roof["kernel"])
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(roof["kernel"])
+        if t:
+            pairs_per_launch = len(mine) * a.steps / max(st["knn_launches"], 1)
+            roof["traffic"] = t["bytes_per_launch"] * pairs_per_launch / t["pairs_per_launch"]
+            roof["traffic_source"] = t["source"]
     except Exception:
         pass
-    roof["traffic"] = traffic
 
     # ---- e2e: host buffers in, host CSR out, every step ---------------------------------------------
     e2e = None

@@ -499,7 +499,7 @@ struct DeviceCtx {
     PM_CUDA(cudaStreamWaitEvent(knn_stream, s.ev_jobs, 0));
     // debug_flags (kernel variants; 0 = product defaults):
     //   bit0      force the fp32 SIMT L2 kernel
-    //   bit1      Hamming: carry-save popc variant
+    //   bit1      Hamming: plain 8-popc variant instead of the carry-save one (default)
     //   bits2-4   GENERAL tensor kernel (exact top-2 with indices; raw kNN rows / single-pair calls):
     //             0 single-CTA 16 epilogue warps (default), 1 x32 / 8 warps, 2 x64 overlapped, 3 x128,
     //             4 timing probe, 5 CTA pair 256-col tiles, 6 pair probe, 7 CTA pair 192-col tiles
@@ -509,7 +509,7 @@ struct DeviceCtx {
     //             2 CTA pair 192-col
     const int code = (prm.debug_flags >> 2) & 7;
     const int fcode = (prm.debug_flags >> 7) & 3;
-    const int variant = (prm.debug_flags >> 1) & 1;
+    const int variant = ((prm.debug_flags >> 1) & 1) ^ 1;
     const bool use_tc = tc_ready && all_integral && !(prm.debug_flags & 1);
     const bool use_fast = use_tc && fast && !dump && !((prm.debug_flags >> 6) & 1);
     const int epi_of_code[5] = {3, 0, 1, 2, 4};

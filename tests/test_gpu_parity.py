@@ -417,3 +417,20 @@ def test_batched_fast_path_equals_general_kernel_full_size():
             assert np.array_equal(outs[0][k], o[k]), k
         assert np.array_equal(outs[0]["F"], o["F"])
     assert outs[0]["offsets"][-1] > 15 * 1500
+
+
+def test_multi_device_handle_matches_single_device():
+    """In-process multi-GPU: pairs dealt to one host thread per device, descriptors replicated."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    w = synth.World("orb", 1200, seed=9)
+    imgs = [w.image(i, 8)[:2] for i in range(8)]
+    outs = []
+    for devs in ([0], [0, 1]):
+        with api.PairMatcher(devices=devs, batch_pairs=5) as pm:
+            for i, (d, xy) in enumerate(imgs):
+                pm.set_image(i, d, xy)
+            outs.append(pm.match_all_pairs())
+    for k in ("pair_ij", "offsets", "q", "t", "inlier", "status", "n_inliers"):
+        assert np.array_equal(outs[0][k], outs[1][k]), k
