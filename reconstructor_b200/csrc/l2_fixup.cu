@@ -13,13 +13,15 @@
 // |a|^2 + |b|^2 - 2 a.b in integers) for the rows that can still pass Lowe's ratio test
 // (FeatureMatcher.cpp:55) -- or for all rows when the caller needs every nearest index -- and
 // rewrites the row in the (idx1, idx2 | dist1, dist2) form the selection kernel consumes.
-// A half-warp owns a row: lane l of the half computes the distance to column cb + l.
+// Pass 1 closes the rows that cannot pass and lists the others; in pass 2 a half-warp owns a row: lane l
+// of the half computes the distance to column cb + l.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace pm {
 
 static constexpr int FX_WARPS = 4;
+static constexpr int FX_SPAN = 256;  // rows per block
 static constexpr int FX_LD = 33;     // words per staged train row (32 + 1 pad: conflict-free column reads)
 
 __global__ void __launch_bounds__(FX_WARPS * 32)
@@ -27,33 +29,43 @@ l2_fixup_kernel(const uint32_t* __restrict__ u8desc, const int32_t* __restrict__
                 const PairJob* __restrict__ jobs, int2* __restrict__ knn_idx,
                 float2* __restrict__ knn_dist, int stride, float ratio, int all_rows) {
   __shared__ uint32_t stage[FX_WARPS * 2][16 * FX_LD];
+  __shared__ int list[FX_SPAN];
+  __shared__ int cnt;
   const PairJob jb = jobs[blockIdx.y];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int half = lane >> 4, l = lane & 15;
-  const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
+  const int span0 = blockIdx.x * FX_SPAN;
+  if (span0 >= jb.nq) return;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int hw = tid >> 4, l = lane & 15;
+  const unsigned hmask = (lane & 16) ? 0xffff0000u : 0x0000ffffu;
   const size_t base = static_cast<size_t>(blockIdx.y) * stride;
-  uint32_t* st = stage[warp * 2 + half];
   const float inf = __int_as_float(0x7f800000);
 
-  for (int row0 = (blockIdx.x * FX_WARPS + warp) * 2; row0 < jb.nq; row0 += gridDim.x * FX_WARPS * 2) {
-    const int row = row0 + half;
-    int2 id = make_int2(-1, -1);
-    float2 dd = make_float2(inf, inf);
-    if (row < jb.nq) { id = knn_idx[base + row]; dd = knn_dist[base + row]; }
-    const bool mine = row < jb.nq && id.y == -2;       // produced by a values-only kernel
-    const int cb = id.x;
-    bool need = mine && cb >= 0;
-    if (need && !all_rows)   // the true d2 is <= the bound: a row that fails with the bound fails for good
-      need = __fsqrt_rn(dd.x) < __fmul_rn(ratio, __fsqrt_rn(dd.y));
-    if (!__any_sync(0xffffffffu, need)) {
-      if (mine && l == 0) { knn_idx[base + row] = make_int2(-1, -1); knn_dist[base + row] = make_float2(inf, inf); }
-      continue;
-    }
-    int2 oi = make_int2(-1, -1);
-    float2 od = make_float2(inf, inf);
-    // stage the 16 train rows of the winning chunk (2 KB per half-warp, 16-byte loads)
-    const int ncol = need ? min(16, jb.nt - cb) : 0;
-    const uint4* src = reinterpret_cast<const uint4*>(u8desc + (static_cast<size_t>(jb.t_row) + (need ? cb : 0)) * 32);
+  // pass 1: one thread per row decides (coalesced reads); rows that cannot pass the ratio test with the
+  // bound on d2 fail for good (the true d2 is <= the bound) and are closed here
+  if (tid == 0) cnt = 0;
+  __syncthreads();
+  for (int r = tid; r < FX_SPAN; r += FX_WARPS * 32) {
+    const int row = span0 + r;
+    if (row >= jb.nq) break;
+    const int2 id = knn_idx[base + row];
+    if (id.y != -2) continue;                          // not produced by a values-only kernel
+    const float2 dd = knn_dist[base + row];
+    bool need = id.x >= 0;
+    if (need && !all_rows) need = __fsqrt_rn(dd.x) < __fmul_rn(ratio, __fsqrt_rn(dd.y));
+    if (need) list[atomicAdd(&cnt, 1)] = row;
+    else { knn_idx[base + row] = make_int2(-1, -1); knn_dist[base + row] = make_float2(inf, inf); }
+  }
+  __syncthreads();
+  const int n_need = cnt;
+
+  // pass 2: one half-warp per surviving row
+  uint32_t* st = stage[hw];
+  for (int e = hw; e < n_need; e += FX_WARPS * 2) {
+    const int row = list[e];
+    const int cb = knn_idx[base + row].x;
+    const float bound = knn_dist[base + row].y;        // second smallest chunk minimum (as d^2)
+    const int ncol = min(16, jb.nt - cb);
+    const uint4* src = reinterpret_cast<const uint4*>(u8desc + (static_cast<size_t>(jb.t_row) + cb) * 32);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int f = i * 16 + l;                        // 16-byte piece: train row f / 8, words (f % 8) * 4 ..
@@ -63,21 +75,18 @@ l2_fixup_kernel(const uint32_t* __restrict__ u8desc, const int32_t* __restrict__
       uint32_t* d = st + r * FX_LD + w;
       d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = x.w;
     }
-    uint32_t q0 = 0, q1 = 0;
-    if (need) {
-      const uint32_t* qs = u8desc + (static_cast<size_t>(jb.q_row) + row) * 32;
-      q0 = __ldg(qs + l); q1 = __ldg(qs + 16 + l);
-    }
-    __syncwarp();
+    const uint32_t* qs = u8desc + (static_cast<size_t>(jb.q_row) + row) * 32;
+    const uint32_t q0 = __ldg(qs + l), q1 = __ldg(qs + 16 + l);
+    __syncwarp(hmask);
     unsigned int dot = 0;
 #pragma unroll
     for (int w = 0; w < 16; ++w) {
-      const uint32_t a0 = __shfl_sync(0xffffffffu, q0, w, 16);
-      const uint32_t a1 = __shfl_sync(0xffffffffu, q1, w, 16);
+      const uint32_t a0 = __shfl_sync(hmask, q0, w, 16);
+      const uint32_t a1 = __shfl_sync(hmask, q1, w, 16);
       dot = __dp4a(a0, st[l * FX_LD + w], dot);
       dot = __dp4a(a1, st[l * FX_LD + 16 + w], dot);
     }
-    __syncwarp();
+    __syncwarp(hmask);
     unsigned int key = 0xFFFFFFFFu;                    // (d^2 << 4 | lane): d^2 <= 2 * 128 * 255^2 < 2^24
     if (l < ncol) {
       const int na = qnorm[jb.q_row + row];
@@ -87,20 +96,20 @@ l2_fixup_kernel(const uint32_t* __restrict__ u8desc, const int32_t* __restrict__
     }
     const unsigned int k1 = __reduce_min_sync(hmask, key);
     const unsigned int k2 = __reduce_min_sync(hmask, key == k1 ? 0xFFFFFFFFu : key);
-    if (need) {
+    if (l == 0) {
       const float d1 = static_cast<float>(k1 >> 4);
-      float d2 = dd.y;                                 // second smallest chunk minimum
+      float d2 = bound;
       int i2 = 0x7ffffffe;                             // somewhere outside the winning chunk
       if (k2 != 0xFFFFFFFFu && static_cast<float>(k2 >> 4) <= d2) {
         d2 = static_cast<float>(k2 >> 4);
         i2 = cb + static_cast<int>(k2 & 15u);
       }
+      int2 oi;
+      float2 od;
       oi.x = cb + static_cast<int>(k1 & 15u);
       oi.y = d2 < inf ? i2 : -1;                       // fewer than two train rows: no second neighbour
       od.x = __fsqrt_rn(d1);
       od.y = d2 < inf ? __fsqrt_rn(d2) : inf;
-    }
-    if (mine && l == 0) {
       knn_idx[base + row] = oi;
       knn_dist[base + row] = od;
     }
@@ -112,7 +121,7 @@ cudaError_t launch_l2_fixup(const uint32_t* u8desc, const int32_t* qnorm, const 
                             int all_rows, cudaStream_t st) {
   (void)reversed;   // callers pass already-swapped jobs for the reverse search
   if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
-  const int bx = min(256, (max_nq + FX_WARPS * 2 - 1) / (FX_WARPS * 2));
+  const int bx = (max_nq + FX_SPAN - 1) / FX_SPAN;
   dim3 grid(bx, n_jobs);
   l2_fixup_kernel<<<grid, FX_WARPS * 32, 0, st>>>(u8desc, qnorm, jobs, idx, dist, stride, ratio, all_rows);
   return cudaGetLastError();

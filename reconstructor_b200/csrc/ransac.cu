@@ -6,7 +6,7 @@
 //   * sampler: OpenCV's fixed-seed 64-bit multiply-with-carry stream, duplicate re-draw,
 //     last-point collinearity reject -- inherently sequential, one thread replays it;
 //   * minimal solver: un-normalised 7-point (7x9 null space -> cubic -> up to 3 models), one
-//     thread per hypothesis of the round, fp64;
+//     half-warp per hypothesis of the round (row-per-lane Householder QR), fp64;
 //   * score: symmetric epipolar distance (or Sampson), fp64 rounded to fp32 and compared with
 //     (float)(t*t); one warp per hypothesis, lanes stride over the matches;
 //   * selection: (iteration, model)-ordered scan, "strictly more inliers replaces", adaptive
@@ -222,6 +222,116 @@ __device__ int seven_point(const float2* m1, const float2* m2, double* F) {
   return n;
 }
 
+// ---- cooperative 7-point solver: one 16-lane half-warp per hypothesis ---------------------------
+// Lane i (0..8) holds row i of B = A^T in registers (static column indices after unrolling), so the
+// Householder sweeps touch no local memory.  Every inner product is still accumulated in the order
+// i = k..8 (the partial products are exchanged with shuffles and added by every lane in that order),
+// so all values are bit-identical to the scalar seven_point() above and to the CPU filter.
+template <int K>
+__device__ __forceinline__ double seq_sum(double p, unsigned mask) {
+  double s = __shfl_sync(mask, p, K, 16);
+#pragma unroll
+  for (int i = K + 1; i < 9; ++i) s += __shfl_sync(mask, p, i, 16);
+  return s;
+}
+
+template <int K>
+__device__ __forceinline__ void qr_step(double (&B)[7], double (&vn2)[7], int li, unsigned mask, bool& ok) {
+  const double x = B[K];
+  const double nrm2 = seq_sum<K>(x * x, mask);
+  const double nrm = sqrt(nrm2);
+  ok = ok && (nrm > 0);
+  const double bkk = __shfl_sync(mask, x, K, 16);
+  const double alpha = bkk > 0 ? -nrm : nrm;
+  if (li == K) B[K] -= alpha;                              // column K now holds v_K in rows K..8
+  const double s2 = seq_sum<K>(B[K] * B[K], mask);
+  vn2[K] = s2;
+  ok = ok && (s2 > 0);
+#pragma unroll
+  for (int j = K + 1; j < 7; ++j) {
+    const double sd = seq_sum<K>(B[K] * B[j], mask);
+    const double f = 2 * sd / s2;
+    if (li >= K) B[j] -= f * B[K];
+  }
+}
+
+template <int K>
+__device__ __forceinline__ void back_step(const double (&B)[7], const double (&vn2)[7], double& y, int li,
+                                          unsigned mask) {
+  const double sd = seq_sum<K>(B[K] * y, mask);
+  const double f = 2 * sd / vn2[K];
+  if (li >= K) y -= f * B[K];
+}
+
+// idx: the 7 sampled match indices (shared memory); F receives up to 3 models; returns their number
+// (valid in every lane of the half-warp).
+__device__ int seven_point_coop(const float2* __restrict__ p1, const float2* __restrict__ p2, const int* idx,
+                                double* F, int li, unsigned mask) {
+  double B[7], vn2[7];
+#pragma unroll
+  for (int c = 0; c < 7; ++c) {
+    const float2 a = p1[idx[c]], b = p2[idx[c]];
+    const double x0 = a.x, y0 = a.y, x1 = b.x, y1 = b.y;
+    const int r3 = li / 3, c3 = li - 3 * r3;
+    const double fa = r3 == 0 ? x1 : (r3 == 1 ? y1 : 1.0);
+    const double fb = c3 == 0 ? x0 : (c3 == 1 ? y0 : 1.0);
+    B[c] = li < 9 ? fa * fb : 0.0;                         // x*1.0 == x: same values as the scalar rows
+  }
+  bool ok = true;
+  qr_step<0>(B, vn2, li, mask, ok); qr_step<1>(B, vn2, li, mask, ok); qr_step<2>(B, vn2, li, mask, ok);
+  qr_step<3>(B, vn2, li, mask, ok); qr_step<4>(B, vn2, li, mask, ok); qr_step<5>(B, vn2, li, mask, ok);
+  qr_step<6>(B, vn2, li, mask, ok);
+  double y1v = li == 7 ? 1.0 : 0.0, y2v = li == 8 ? 1.0 : 0.0;
+  back_step<6>(B, vn2, y1v, li, mask); back_step<5>(B, vn2, y1v, li, mask); back_step<4>(B, vn2, y1v, li, mask);
+  back_step<3>(B, vn2, y1v, li, mask); back_step<2>(B, vn2, y1v, li, mask); back_step<1>(B, vn2, y1v, li, mask);
+  back_step<0>(B, vn2, y1v, li, mask);
+  back_step<6>(B, vn2, y2v, li, mask); back_step<5>(B, vn2, y2v, li, mask); back_step<4>(B, vn2, y2v, li, mask);
+  back_step<3>(B, vn2, y2v, li, mask); back_step<2>(B, vn2, y2v, li, mask); back_step<1>(B, vn2, y2v, li, mask);
+  back_step<0>(B, vn2, y2v, li, mask);
+  y1v -= y2v;                                              // f1 -= f2
+  double f1[9], f2[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { f1[i] = __shfl_sync(mask, y1v, i, 16); f2[i] = __shfl_sync(mask, y2v, i, 16); }
+  if (!ok) return 0;                                       // uniform within the half-warp
+
+  double c[4], r[3];
+  double t0 = f2[4] * f2[8] - f2[5] * f2[7];
+  double t1 = f2[3] * f2[8] - f2[5] * f2[6];
+  double t2 = f2[3] * f2[7] - f2[4] * f2[6];
+  c[3] = f2[0] * t0 - f2[1] * t1 + f2[2] * t2;
+  c[2] = f1[0] * t0 - f1[1] * t1 + f1[2] * t2 -
+         f1[3] * (f2[1] * f2[8] - f2[2] * f2[7]) +
+         f1[4] * (f2[0] * f2[8] - f2[2] * f2[6]) -
+         f1[5] * (f2[0] * f2[7] - f2[1] * f2[6]) +
+         f1[6] * (f2[1] * f2[5] - f2[2] * f2[4]) -
+         f1[7] * (f2[0] * f2[5] - f2[2] * f2[3]) +
+         f1[8] * (f2[0] * f2[4] - f2[1] * f2[3]);
+  t0 = f1[4] * f1[8] - f1[5] * f1[7];
+  t1 = f1[3] * f1[8] - f1[5] * f1[6];
+  t2 = f1[3] * f1[7] - f1[4] * f1[6];
+  c[1] = f2[0] * t0 - f2[1] * t1 + f2[2] * t2 -
+         f2[3] * (f1[1] * f1[8] - f1[2] * f1[7]) +
+         f2[4] * (f1[0] * f1[8] - f1[2] * f1[6]) -
+         f2[5] * (f1[0] * f1[7] - f1[1] * f1[6]) +
+         f2[6] * (f1[1] * f1[5] - f1[2] * f1[4]) -
+         f2[7] * (f1[0] * f1[5] - f1[2] * f1[3]) +
+         f2[8] * (f1[0] * f1[4] - f1[1] * f1[3]);
+  c[0] = f1[0] * t0 - f1[1] * t1 + f1[2] * t2;
+  const int n = solve_cubic(c, r);
+  if (n < 1 || n > 3) return 0;
+  if (li == 0) {
+    for (int k = 0; k < n; ++k) {
+      double lambda = r[k], mu = 1.0;
+      const double sc = f1[8] * r[k] + f2[8];
+      double* Fk = F + 9 * k;
+      if (fabs(sc) > DBL_EPSILON) { mu = 1. / sc; lambda *= mu; Fk[8] = 1.0; }
+      else Fk[8] = 0.0;
+      for (int i = 0; i < 8; ++i) Fk[i] = f1[i] * lambda + f2[i] * mu;
+    }
+  }
+  return n;
+}
+
 __device__ __forceinline__ float residual(const double* F, float2 q1, float2 q2, int mode) {
   const double x1 = q1.x, y1 = q1.y, x2 = q2.x, y2 = q2.y;
   double a = F[0] * x1 + F[1] * y1 + F[2];
@@ -305,11 +415,14 @@ fmat_ransac_kernel(const float2* __restrict__ pts1, const float2* __restrict__ p
     __syncthreads();
     const int gen = sGen;
     if (gen == 0) break;
-    // ---- solve: one thread per hypothesis --------------------------------------------------
-    if (tid < gen) {
-      float2 a[7], b[7];
-      for (int i = 0; i < 7; ++i) { a[i] = p1[sSub[tid][i]]; b[i] = p2[sSub[tid][i]]; }
-      sNm[tid] = seven_point(a, b, sF[tid]);
+    // ---- solve: one half-warp per hypothesis (row-per-lane Householder QR) ------------------
+    {
+      const int hw = tid >> 4, li = tid & 15;
+      const unsigned hmask = (lane & 16) ? 0xffff0000u : 0x0000ffffu;
+      for (int h = hw; h < gen; h += RS_THREADS / 16) {
+        const int nm = seven_point_coop(p1, p2, sSub[h], sF[h], li, hmask);
+        if (li == 0) sNm[h] = nm;
+      }
     }
     __syncthreads();
     // ---- score: one warp per (iteration, model) -------------------------------------------
