@@ -300,10 +300,12 @@ def main():
                     peak_source="MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if pk
                     else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)")
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof["kernel"] = {"sift": "l2_top2_tc2_kernel", "orb": "hamming_top2_kernel", "superpoint": "l2_top2_simt_kernel"}[a.kind]
+    roof["kernel"] = {"sift": "l2_top2_tc2_kernel", "orb": "hamming_top2_kernel", "superpoint": "l2_top2_tc2_kernel (MODE 3, fp16 scores + exact fp32 re-rank)"}[a.kind]
     roof["launches"] = st["knn_launches"]
     roof["avg_launch_ms"] = st["knn_ms"] / max(st["knn_launches"], 1)
     roof["share_of_step"] = st["knn_ms"] / max(dev_ms, 1e-9) if world == 1 else None
+    if a.kind == "superpoint":
+        roof["rerank"] = {k[7:]: st[k] for k in st if k.startswith("rerank_")}
     # DRAM bytes per launch of that kernel from the committed ncu --set full capture, scaled to this
     # run's pairs per launch (null when no capture exists for the kernel)
     roof["traffic"] = None
@@ -340,7 +342,7 @@ def main():
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=n_gpus, steps=a.steps, warmup=a.warmup,
                     ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype={"sift": "f16 operands / f32 accumulate (exact integers)", "orb": "u32 popc",
-                           "superpoint": "f32"}[a.kind],
+                           "superpoint": "f16 operands / f32 accumulate candidates + exact f32 re-rank"}[a.kind],
                     data="synthetic", config=cfg, wall_ms_per_step=wall_ms / a.steps,
                     putative_matches_per_step=matches, inliers_per_step=inliers,
                     roofline=roof, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks)

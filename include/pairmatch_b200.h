@@ -131,6 +131,11 @@ typedef struct {
   double  knn_work;           /* algorithmic work of those launches: FLOP (L2) or popc32    */
   int32_t device_id;
   int32_t n_images;
+  /* real-valued tensor path (approximate fp16 scores + exact fp32 re-rank, l2f_fixup.cu)       */
+  int64_t rerank_rows;        /* query rows whose candidate chunks were re-evaluated exactly */
+  int64_t rerank_chunks;      /* 16-column chunks re-evaluated                               */
+  int64_t rerank_overflow;    /* rows that needed the exhaustive exact scan                  */
+  double  rerank_worst_err;   /* max observed |approx - exact| / certified bound (must be < 1) */
 } pm_stats;
 
 void        pm_default_params(pm_params* p);

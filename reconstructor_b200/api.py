@@ -62,7 +62,8 @@ class Stats(C.Structure):
                 ("inlier_matches", C.c_int64), ("kernel_launches", C.c_int64),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("knn_ms", C.c_double),
                 ("knn_launches", C.c_int64), ("knn_work", C.c_double), ("device_id", C.c_int32),
-                ("n_images", C.c_int32)]
+                ("n_images", C.c_int32), ("rerank_rows", C.c_int64), ("rerank_chunks", C.c_int64),
+                ("rerank_overflow", C.c_int64), ("rerank_worst_err", C.c_double)]
 
 
 class PairMatchError(RuntimeError):

@@ -32,6 +32,8 @@ struct Image {
   int32_t n = 0;         // keypoints
   int32_t cap = 0;       // rows reserved
   bool integral = false; // u8-valued rows (exact tensor path allowed)
+  bool unit_ok = false;  // finite real-valued rows with |x|^2 <= L2F_MAX_NORM2 and fp16 forms packed
+  float maxn = 0.f;      // largest squared row norm
   bool has_xy = false;
 };
 
@@ -122,6 +124,7 @@ struct Slot {
   PairJob *d_jobs = nullptr, *d_rjobs = nullptr;
   int2 *knn_idx = nullptr, *rev_idx = nullptr;
   float2 *knn_dist = nullptr, *rev_dist = nullptr;
+  float2 *knn_extra = nullptr, *rev_extra = nullptr;   // 5th / 6th candidate keys of the real-valued tensor path
   int32_t *owner = nullptr, *match_q = nullptr, *match_t = nullptr, *count = nullptr;
   float2 *pts1 = nullptr, *pts2 = nullptr;
   uint8_t* mask = nullptr;
@@ -147,7 +150,7 @@ struct Slot {
   void release() {
     auto fd = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
     auto fh = [](auto*& p) { if (p) { cudaFreeHost(p); p = nullptr; } };
-    fd(d_jobs); fd(d_rjobs); fd(knn_idx); fd(rev_idx); fd(knn_dist); fd(rev_dist); fd(owner);
+    fd(d_jobs); fd(d_rjobs); fd(knn_idx); fd(rev_idx); fd(knn_dist); fd(rev_dist); fd(knn_extra); fd(rev_extra); fd(owner);
     fd(match_q); fd(match_t); fd(count); fd(pts1); fd(pts2); fd(mask); fd(F); fd(status);
     fd(n_inl); fd(iters); fd(offsets); fd(out_q); fd(out_t); fd(out_mask);
     fh(h_jobs); fh(h_rjobs); fh(h_offsets); fh(h_q); fh(h_t); fh(h_status); fh(h_ninl);
@@ -182,6 +185,13 @@ struct DeviceCtx {
   float* raw = nullptr;        // [rows][dim]    fp32 (F32 / U8 dtypes)
   __half *qf = nullptr, *tf = nullptr;   // [rows][144] tensor-path operand forms
   int32_t* qnorm = nullptr;    // [rows]
+  __half *fq = nullptr, *ft = nullptr;   // [rows][dim+16] operand forms of real-valued rows (dim 128 / 256)
+  float* fnorm = nullptr;      // [rows] fp32 squared norms of real-valued rows
+  TcMaps fmaps{};
+  bool tcf_ready = false;
+  unsigned int* d_fstats = nullptr;   // pack_float statistics of the image being ingested
+  unsigned int* h_fstats = nullptr;   // pinned
+  unsigned long long* d_l2f = nullptr;   // l2f_fixup counters
   uint32_t* u8d = nullptr;     // [rows][32]     byte copy of integer-valued 128-d rows (fix-up kernel)
   uint32_t* bits = nullptr;    // [rows][words]  (U8_BITS)
   int32_t* xy = nullptr;       // [rows][2]
@@ -231,6 +241,10 @@ struct DeviceCtx {
     PM_CUDA(cudaEventCreate(&ev_b));
     PM_CUDA(cudaMalloc(&d_flag, sizeof(int)));
     PM_CUDA(cudaMallocHost(&h_flag, sizeof(int)));
+    PM_CUDA(cudaMalloc(&d_fstats, 4 * sizeof(unsigned int)));
+    PM_CUDA(cudaMallocHost(&h_fstats, 4 * sizeof(unsigned int)));
+    PM_CUDA(cudaMalloc(&d_l2f, 4 * sizeof(unsigned long long)));
+    PM_CUDA(cudaMemset(d_l2f, 0, 4 * sizeof(unsigned long long)));
     PM_CUDA(tc_configure());
     PM_CUDA(tc2_configure());
     stats.device_id = dev;
@@ -244,7 +258,9 @@ struct DeviceCtx {
     single.destroy();
     auto fd = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
     fd(raw); fd(qf); fd(tf); fd(qnorm); fd(u8d); fd(bits); fd(xy); fd(d_flag); fd(stage); fd(d_dump);
+    fd(fq); fd(ft); fd(fnorm); fd(d_fstats); fd(d_l2f);
     if (h_flag) cudaFreeHost(h_flag);
+    if (h_fstats) cudaFreeHost(h_fstats);
     if (ingest) cudaStreamDestroy(ingest);
     if (knn_stream) cudaStreamDestroy(knn_stream);
     if (ev_a) cudaEventDestroy(ev_a);
@@ -252,9 +268,13 @@ struct DeviceCtx {
   }
 
   // ---- tensor maps -----------------------------------------------------------------------
+  bool float_tc_shape() const { return dtype == PM_DESC_F32 && (dim == 128 || dim == 256); }
+
   int build_maps() {
     tc_ready = false;
-    if (!(dim == TC_DIM && (dtype == PM_DESC_F32 || dtype == PM_DESC_U8))) return PM_OK;
+    tcf_ready = false;
+    const bool sift_shape = dim == TC_DIM && (dtype == PM_DESC_F32 || dtype == PM_DESC_U8);
+    if (!sift_shape && !float_tc_shape()) return PM_OK;
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -265,16 +285,28 @@ struct DeviceCtx {
     if (!fn || qres != cudaDriverEntryPointSuccess)
       return fail(PM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     EncodeFn encode = reinterpret_cast<EncodeFn>(fn);
-    const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(TC_KPAD), static_cast<cuuint64_t>(cap_rows)};
-    const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(TC_KPAD) * sizeof(__half)};
+    int kpad = TC_KPAD;
     const cuuint32_t estr[2] = {1, 1};
     auto mk = [&](CUtensorMap* m, void* base, cuuint32_t box_k, CUtensorMapSwizzle sw, cuuint32_t rows = 128) -> CUresult {
+      const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(kpad), static_cast<cuuint64_t>(cap_rows)};
+      const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(kpad) * sizeof(__half)};
       const cuuint32_t box[2] = {box_k, rows};
       return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, gdim, gstr, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     };
     CUresult r;
+    if (float_tc_shape()) {
+      kpad = dim + 16;
+      if ((r = mk(&fmaps.q_main, fq, 64, CU_TENSOR_MAP_SWIZZLE_128B)) != CUDA_SUCCESS ||
+          (r = mk(&fmaps.q_ext, fq, 16, CU_TENSOR_MAP_SWIZZLE_32B)) != CUDA_SUCCESS ||
+          (r = mk(&fmaps.t_main, ft, 64, CU_TENSOR_MAP_SWIZZLE_128B)) != CUDA_SUCCESS ||
+          (r = mk(&fmaps.t_ext, ft, 16, CU_TENSOR_MAP_SWIZZLE_32B)) != CUDA_SUCCESS)
+        return fail(PM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+      tcf_ready = true;
+      kpad = TC_KPAD;
+    }
+    if (!sift_shape) return PM_OK;
     if ((r = mk(&maps.q_main, qf, 64, CU_TENSOR_MAP_SWIZZLE_128B)) != CUDA_SUCCESS ||
         (r = mk(&maps.q_ext, qf, 16, CU_TENSOR_MAP_SWIZZLE_32B)) != CUDA_SUCCESS ||
         (r = mk(&maps.t_main, tf, 64, CU_TENSOR_MAP_SWIZZLE_128B)) != CUDA_SUCCESS ||
@@ -319,6 +351,11 @@ struct DeviceCtx {
         if ((rc = grow(qnorm, 1, nc)) != PM_OK) return rc;
         if ((rc = grow(u8d, 32, nc)) != PM_OK) return rc;
       }
+      if (float_tc_shape()) {
+        if ((rc = grow(fq, dim + 16, nc)) != PM_OK) return rc;
+        if ((rc = grow(ft, dim + 16, nc)) != PM_OK) return rc;
+        if ((rc = grow(fnorm, 1, nc)) != PM_OK) return rc;
+      }
     }
     if ((rc = grow(xy, 2, nc)) != PM_OK) return rc;
     cap_rows = nc;
@@ -359,6 +396,8 @@ struct DeviceCtx {
     im.n = n;
     im.has_xy = xy_ != nullptr;
     im.integral = false;
+    im.unit_ok = false;
+    im.maxn = 0.f;
     const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     if (n > 0) {
       if (dtype == PM_DESC_U8_BITS) {
@@ -409,6 +448,18 @@ struct DeviceCtx {
     }
     PM_CUDA(cudaStreamSynchronize(ingest));   // caller's buffers are free to change on return
     if (n > 0 && dtype != PM_DESC_U8_BITS && dim == TC_DIM) im.integral = (*h_flag == 0);
+    if (n > 0 && float_tc_shape() && !im.integral) {
+      // real-valued rows: fp16 operand forms + norms for the tensor-core search (l2_tc2.cu MODE 3)
+      const int kp = dim + 16;
+      PM_CUDA(cudaMemsetAsync(d_fstats, 0, 4 * sizeof(unsigned int), ingest));
+      PM_CUDA(launch_pack_float(raw + static_cast<size_t>(im.row) * dim, n, dim, fq + static_cast<size_t>(im.row) * kp,
+                                ft + static_cast<size_t>(im.row) * kp, fnorm + im.row, d_fstats, ingest));
+      ++stats.kernel_launches;
+      PM_CUDA(cudaMemcpyAsync(h_fstats, d_fstats, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ingest));
+      PM_CUDA(cudaStreamSynchronize(ingest));
+      std::memcpy(&im.maxn, &h_fstats[1], sizeof(float));
+      im.unit_ok = h_fstats[2] == 0 && im.maxn <= L2F_MAX_NORM2;
+    }
     stats.n_images = static_cast<int32_t>(images.size());
     return PM_OK;
   }
@@ -423,7 +474,8 @@ struct DeviceCtx {
       PM_CUDA(cudaEventCreateWithFlags(&s.ev_jobs, cudaEventDisableTiming));
       PM_CUDA(cudaEventCreateWithFlags(&s.ev_knn, cudaEventDisableTiming));
     }
-    if (pairs <= s.cap_pairs && stride <= s.stride && (!mutual || s.mutual)) return PM_OK;
+    const bool extra_ok = !float_tc_shape() || (s.knn_extra && (!mutual || s.rev_extra));
+    if (pairs <= s.cap_pairs && stride <= s.stride && (!mutual || s.mutual) && extra_ok) return PM_OK;
     PM_CUDA(cudaStreamSynchronize(s.stream));
     pairs = std::max(pairs, s.cap_pairs);
     stride = std::max(stride, s.stride);
@@ -434,9 +486,11 @@ struct DeviceCtx {
     PM_CUDA(cudaMalloc(&s.d_rjobs, sizeof(PairJob) * pairs));
     PM_CUDA(cudaMalloc(&s.knn_idx, sizeof(int2) * ps));
     PM_CUDA(cudaMalloc(&s.knn_dist, sizeof(float2) * ps));
+    if (float_tc_shape()) PM_CUDA(cudaMalloc(&s.knn_extra, sizeof(float2) * ps));
     if (mutual) {
       PM_CUDA(cudaMalloc(&s.rev_idx, sizeof(int2) * ps));
       PM_CUDA(cudaMalloc(&s.rev_dist, sizeof(float2) * ps));
+      if (float_tc_shape()) PM_CUDA(cudaMalloc(&s.rev_extra, sizeof(float2) * ps));
     }
     PM_CUDA(cudaMalloc(&s.owner, 4 * ps));
     PM_CUDA(cudaMalloc(&s.match_q, 4 * ps));
@@ -479,19 +533,21 @@ struct DeviceCtx {
   // Queues the kNN kernel(s) of a batch whose jobs are already in s.h_jobs[0..n).
   int enqueue_knn(Slot& s, int n, bool want_rev, bool timed, float* dump = nullptr, bool fast = false) {
     int max_nq = 0, max_nt = 0;
-    bool all_integral = true;
+    bool all_integral = true, all_unit = true;
     double work = 0;
     for (int i = 0; i < n; ++i) {
       max_nq = std::max(max_nq, s.h_jobs[i].nq);
       max_nt = std::max(max_nt, s.h_jobs[i].nt);
       work += static_cast<double>(s.h_jobs[i].nq) * s.h_jobs[i].nt;
-      s.h_rjobs[i] = PairJob{s.h_jobs[i].t_row, s.h_jobs[i].q_row, s.h_jobs[i].nt, s.h_jobs[i].nq};
+      s.h_rjobs[i] = PairJob{s.h_jobs[i].t_row, s.h_jobs[i].q_row, s.h_jobs[i].nt, s.h_jobs[i].nq,
+                             s.h_jobs[i].t_maxn, s.h_jobs[i].q_maxn};
     }
     PM_CUDA(cudaMemcpyAsync(s.d_jobs, s.h_jobs, sizeof(PairJob) * n, cudaMemcpyHostToDevice, s.stream));
     if (want_rev)
       PM_CUDA(cudaMemcpyAsync(s.d_rjobs, s.h_rjobs, sizeof(PairJob) * n, cudaMemcpyHostToDevice, s.stream));
     if (dtype != PM_DESC_U8_BITS) {
       for (int i = 0; i < n && all_integral; ++i) all_integral = job_integral[i];
+      for (int i = 0; i < n && all_unit; ++i) all_unit = job_unit[i];
     }
     // The kNN kernels of all batches are serialised on one stream (they fill the machine anyway);
     // the slot's own stream carries the small tail kernels and the D2H, overlapping the next kNN.
@@ -512,10 +568,15 @@ struct DeviceCtx {
     const int variant = ((prm.debug_flags >> 1) & 1) ^ 1;
     const bool use_tc = tc_ready && all_integral && !(prm.debug_flags & 1);
     const bool use_fast = use_tc && fast && !dump && !((prm.debug_flags >> 6) & 1);
+    // real-valued rows (SuperPoint): approximate tensor-core scores + exact fp32 re-rank (l2f_fixup.cu)
+    const bool use_tcf = !use_tc && tcf_ready && dtype == PM_DESC_F32 && all_unit && !dump &&
+                         max_nt <= L2F_MAX_NT &&
+                         (!want_rev || max_nq <= L2F_MAX_NT) && !(prm.debug_flags & 1);
     const int epi_of_code[5] = {3, 0, 1, 2, 4};
-    auto knn_main = [&](const PairJob* jobs_d, int mq, int2* oi, float2* od) -> cudaError_t {
+    auto knn_main = [&](const PairJob* jobs_d, int mq, int2* oi, float2* od, float2* ox) -> cudaError_t {
       if (dtype == PM_DESC_U8_BITS)
         return launch_hamming_top2(bits, words, jobs_d, n, mq, oi, od, s.stride, variant, knn_stream);
+      if (use_tcf) return launch_l2f_tc2(fmaps, dim, jobs_d, n, mq, oi, od, ox, s.stride, num_sms, knn_stream);
       if (!use_tc) return launch_l2_simt(raw, dim, jobs_d, n, mq, oi, od, s.stride, knn_stream);
       if (use_fast) {
         if (fcode == 1) return launch_l2_tc(maps, qnorm, jobs_d, n, mq, oi, od, s.stride, num_sms, nullptr, 5, knn_stream);
@@ -528,13 +589,13 @@ struct DeviceCtx {
                           dump ? 0 : epi_of_code[code < 5 ? code : 0], knn_stream);
     };
     if (timed) PM_CUDA(cudaEventRecord(s.ev_k0, knn_stream));
-    PM_CUDA(knn_main(s.d_jobs, max_nq, s.knn_idx, s.knn_dist));
+    PM_CUDA(knn_main(s.d_jobs, max_nq, s.knn_idx, s.knn_dist, s.knn_extra));
     if (timed) PM_CUDA(cudaEventRecord(s.ev_k1, knn_stream));
     ++stats.kernel_launches;
     s.knn_work = dtype == PM_DESC_U8_BITS ? work * words : work * 2.0 * dim;
     s.timed = timed;
     if (want_rev) {
-      PM_CUDA(knn_main(s.d_rjobs, max_nt, s.rev_idx, s.rev_dist));
+      PM_CUDA(knn_main(s.d_rjobs, max_nt, s.rev_idx, s.rev_dist, s.rev_extra));
       ++stats.kernel_launches;
     }
     PM_CUDA(cudaEventRecord(s.ev_knn, knn_stream));
@@ -550,17 +611,28 @@ struct DeviceCtx {
         ++stats.kernel_launches;
       }
     }
+    if (use_tcf) {
+      PM_CUDA(launch_l2f_fixup(raw, fnorm, dim, s.d_jobs, n, max_nq, s.knn_idx, s.knn_dist, s.knn_extra, s.stride,
+                               prm.ratio, fast ? L2F_NEED_RATIO : L2F_NEED_FULL, d_l2f, s.stream));
+      ++stats.kernel_launches;
+      if (want_rev) {
+        PM_CUDA(launch_l2f_fixup(raw, fnorm, dim, s.d_rjobs, n, max_nt, s.rev_idx, s.rev_dist, s.rev_extra, s.stride,
+                                 prm.ratio, fast ? L2F_NEED_NEAREST : L2F_NEED_FULL, d_l2f, s.stream));
+        ++stats.kernel_launches;
+      }
+    }
     return PM_OK;
   }
-  std::vector<char> job_integral;   // per job of the batch being built
+  std::vector<char> job_integral, job_unit;   // per job of the batch being built
 
   int fill_job(Slot& s, int k, int i, int j) {
     auto a = images.find(i), b = images.find(j);
     if (a == images.end() || b == images.end())
       return fail(PM_ERR_STATE, "image id %d not set", a == images.end() ? i : j);
-    s.h_jobs[k] = PairJob{a->second.row, b->second.row, a->second.n, b->second.n};
-    if (static_cast<int>(job_integral.size()) <= k) job_integral.resize(k + 1);
+    s.h_jobs[k] = PairJob{a->second.row, b->second.row, a->second.n, b->second.n, a->second.maxn, b->second.maxn};
+    if (static_cast<int>(job_integral.size()) <= k) { job_integral.resize(k + 1); job_unit.resize(k + 1); }
     job_integral[k] = a->second.integral && b->second.integral;
+    job_unit[k] = a->second.unit_ok && b->second.unit_ok;
     return PM_OK;
   }
 
@@ -1038,6 +1110,18 @@ int pm_get_stats(pm_handle h, pm_stats* out) {
     s.inlier_matches += d->stats.inlier_matches; s.kernel_launches += d->stats.kernel_launches;
     s.h2d_bytes += d->stats.h2d_bytes; s.d2h_bytes += d->stats.d2h_bytes;
     s.knn_ms += d->stats.knn_ms; s.knn_launches += d->stats.knn_launches; s.knn_work += d->stats.knn_work;
+    unsigned long long c[4] = {0, 0, 0, 0};
+    if (cudaSetDevice(d->dev) == cudaSuccess && d->d_l2f &&
+        cudaMemcpy(c, d->d_l2f, sizeof c, cudaMemcpyDeviceToHost) == cudaSuccess) {   // device-wide sync point
+      s.rerank_rows += static_cast<int64_t>(c[0]); s.rerank_chunks += static_cast<int64_t>(c[1]);
+      s.rerank_overflow += static_cast<int64_t>(c[2]);
+      float w;
+      const unsigned int wb = static_cast<unsigned int>(c[3]);
+      std::memcpy(&w, &wb, sizeof w);
+      s.rerank_worst_err = std::max(s.rerank_worst_err, static_cast<double>(w));
+    } else {
+      (void)cudaGetLastError();
+    }
   }
   s.device_id = h->devs[0]->dev;
   s.n_images = h->devs[0]->stats.n_images;
@@ -1052,6 +1136,7 @@ int pm_reset_stats(pm_handle h) {
     const int dev = d->stats.device_id, ni = d->stats.n_images;
     d->stats = pm_stats{};
     d->stats.device_id = dev; d->stats.n_images = ni;
+    if (cudaSetDevice(d->dev) == cudaSuccess && d->d_l2f) cudaMemset(d->d_l2f, 0, 4 * sizeof(unsigned long long));
   }
   return PM_OK;
 }

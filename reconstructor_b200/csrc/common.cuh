@@ -8,10 +8,12 @@ namespace pm {
 
 // One (query image, train image) job of a device batch.  Rows index the per-handle arenas.
 struct PairJob {
-  int32_t q_row;   // first arena row of the query image
-  int32_t t_row;   // first arena row of the train image
+  int32_t q_row;     // first arena row of the query image
+  int32_t t_row;     // first arena row of the train image
   int32_t nq;
   int32_t nt;
+  float q_maxn;      // largest squared row norm of the query / train image (real-valued tensor path)
+  float t_maxn;
 };
 
 // Outputs of the kNN kernels, [batch slot][stride] rows:

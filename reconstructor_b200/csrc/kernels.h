@@ -47,6 +47,20 @@ cudaError_t launch_l2_tc2(const TcMaps& maps, const int32_t* qnorm, const PairJo
                           int2* idx, float2* dist, int stride, int num_sms, int variant, int mode,
                           cudaStream_t st);
 
+// real-valued rows on the tensor cores: l2_tc2.cu (MODE 3) + l2f_fixup.cu
+cudaError_t launch_l2f_tc2(const TcMaps& maps, int dim, const PairJob* jobs, int n_jobs, int max_nq, int2* idx,
+                           float2* dist, float2* extra, int stride, int num_sms, cudaStream_t st);
+cudaError_t launch_pack_float(const float* raw, int n, int dim, __half* qh, __half* th, float* fnorm,
+                              unsigned int* stats, cudaStream_t st);
+// exact fp32 re-rank of the candidate chunks (l2f_fixup.cu).  need: 0 = rows that can pass the ratio test
+// (exact nearest index + exact test outcome), 1 = exact nearest index of every row, 2 = exact DMatch rows
+enum { L2F_NEED_RATIO = 0, L2F_NEED_NEAREST = 1, L2F_NEED_FULL = 2 };
+static constexpr int L2F_MAX_NT = 16384;   // chunk id = 10 bits of the key
+static constexpr float L2F_MAX_NORM2 = 1.01f;   // rows must satisfy |x|^2 <= this (scores stay positive)
+cudaError_t launch_l2f_fixup(const float* raw, const float* fnorm, int dim, const PairJob* jobs, int n_jobs,
+                             int max_nq, int2* idx, float2* dist, const float2* extra, int stride, float ratio,
+                             int need, unsigned long long* counters, cudaStream_t st);
+
 // l2_fixup.cu -- exact index / 2nd-neighbour recovery after the branch-free tensor epilogue
 cudaError_t launch_l2_fixup(const uint32_t* u8desc, const int32_t* qnorm, const PairJob* jobs, int n_jobs,
                             int max_nq, int reversed, int2* idx, float2* dist, int stride, float ratio,

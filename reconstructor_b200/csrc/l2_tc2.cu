@@ -28,8 +28,6 @@ static constexpr int T2_BM = 128;               // query rows per CTA
 static constexpr int T2_ROWS = 2 * T2_BM;       // per cluster work item
 static constexpr int T2_ATOM = T2_BM * 128;     // 16 KB: 128 rows x 128 B (SWIZZLE_128B)
 static constexpr int T2_EXT = T2_BM * 32;       // 4 KB: 128 rows x 32 B (SWIZZLE_32B)
-static constexpr int T2_TILE = 2 * T2_ATOM + T2_EXT;     // 36 KB (query tile of one CTA)
-static constexpr int T2_SMEM_A = T2_TILE;
 static constexpr uint32_t T2_TMEM_COLS = 512;
 static constexpr uint32_t T2_PEER_MASK = 0xFEFFFFFFu;     // clears the CTA-rank bit of a shared::cluster address
 
@@ -38,17 +36,19 @@ static constexpr uint32_t T2_PEER_MASK = 0xFEFFFFFFu;     // clears the CTA-rank
 // epilogue warps.
 //   BN = 256, CPW = 2: 16 epilogue warps (640 threads)
 //   BN = 192, CPW = 1: 24 epilogue warps (896 threads) -- more warps in flight per scheduler
-template <int BN, int CPW>
+//   KA = number of 64-wide K atoms of a row: 2 (128-d) or 4 (256-d); a row is 64*KA + 16 fp16.
+template <int BN, int CPW, int KA = 2>
 struct T2Cfg {
-  static constexpr int kBN = BN, kBNH = BN / 2, kCPW = CPW;
+  static constexpr int kBN = BN, kBNH = BN / 2, kCPW = CPW, kKA = KA;
+  static constexpr int kATile = KA * T2_ATOM + T2_EXT;          // query tile of one CTA (36 / 68 KB)
   static constexpr int kSlices = BN / (32 * CPW);
   static constexpr int kEpiWarps = 4 * kSlices;
   static constexpr int kThreads = 128 + 32 * kEpiWarps;
-  static constexpr int kBAtom = kBNH * 128, kBExt = kBNH * 32, kBTile = 2 * kBAtom + kBExt;
-  static constexpr int kStages = BN == 256 ? 3 : 4;
+  static constexpr int kBAtom = kBNH * 128, kBExt = kBNH * 32, kBTile = KA * kBAtom + kBExt;
+  static constexpr int kStages = KA == 4 ? 2 : (BN == 256 ? 3 : 4);
   static constexpr int kSmemB = kStages * kBTile;
-  static constexpr int kXchg = 4 * (kSlices - 1) * 32 * 16;
-  static constexpr int kSmemBytes = T2_SMEM_A + kSmemB + 1024 + 256 + kXchg;
+  static constexpr int kXchg = 4 * (kSlices - 1) * 32 * 32;   // two float4 per (quarter, slice, lane)
+  static constexpr int kSmemBytes = kATile + kSmemB + 1024 + 256 + kXchg;
   // kind::f16: D=f32, A=B=f16, K-major, N=BN, M=256 (pair)
   static constexpr uint32_t kIdesc = (1u << 4) | ((BN >> 3) << 17) | ((T2_ROWS >> 4) << 24);
 };
@@ -185,6 +185,35 @@ __device__ __forceinline__ void t2_fast(Top2p& s, const uint32_t* r, int cbase) 
   t2_fast16(s, r, cbase);
   t2_fast16(s, r + 16, cbase + 16);
 }
+// ---- MODE 3: six smallest chunk minima as keys ---------------------------------------------------
+// key = positive fp32 score with the low 10 mantissa bits replaced by the 16-column chunk id (the
+// scores are approximate anyway; l2f_fixup.cu widens its error bound by the 2^-13 relative truncation).
+// For positive floats, float order == integer order, so a min/max chain sorts (score, id) at once.
+struct Keys4 {                       // the six smallest keys, ascending
+  float k1, k2, k3, k4, k5, k6;
+};
+__device__ __forceinline__ void keys_insert(Keys4& s, float key) {
+  float lo = fminf(s.k1, key), hi = fmaxf(s.k1, key);
+  s.k1 = lo; key = hi;
+  lo = fminf(s.k2, key); hi = fmaxf(s.k2, key);
+  s.k2 = lo; key = hi;
+  lo = fminf(s.k3, key); hi = fmaxf(s.k3, key);
+  s.k3 = lo; key = hi;
+  lo = fminf(s.k4, key); hi = fmaxf(s.k4, key);
+  s.k4 = lo; key = hi;
+  lo = fminf(s.k5, key); hi = fmaxf(s.k5, key);
+  s.k5 = lo; key = hi;
+  s.k6 = fminf(s.k6, key);
+}
+__device__ __forceinline__ void keys_chunk16(Keys4& s, const uint32_t* r, int col) {
+  float g[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    g[k] = fminf(fminf(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1])),
+                 fminf(__uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3])));
+  const float cm = fminf(fminf(g[0], g[1]), fminf(g[2], g[3]));
+  keys_insert(s, __uint_as_float((__float_as_uint(cm) & 0xFFFFFC00u) | static_cast<uint32_t>(col >> 4)));
+}
 // ordered by (value, index)
 __device__ __forceinline__ bool t2_less(float va, int ia, float vb, int ib) { return va < vb || (va == vb && ia < ib); }
 __device__ __forceinline__ void t2_merge(Top2p& s, float om1, int oi1, float om2, int oi2) {
@@ -206,8 +235,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::kThreads, 1)
 l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant__ CUtensorMap q_ext,
                    const __grid_constant__ CUtensorMap t_main, const __grid_constant__ CUtensorMap t_ext,
                    const int32_t* __restrict__ qnorm, const PairJob* __restrict__ jobs, int n_jobs,
-                   int tiles_per_job, int2* __restrict__ knn_idx, float2* __restrict__ knn_dist, int stride) {
+                   int tiles_per_job, int2* __restrict__ knn_idx, float2* __restrict__ knn_dist, int stride,
+                   float2* __restrict__ extra_keys) {
+  // MODE 3 (real-valued rows): the accumulator is an APPROXIMATE score |b|^2 - 2 a.b + 2 (fp16 operands);
+  // the epilogue keeps the 6 smallest 16-column chunk minima as keys (score with the chunk id in the low
+  // 10 mantissa bits) and l2f_fixup.cu re-ranks exactly in fp32.  qnorm is unused in that mode.
   constexpr int T2_BN = Cfg::kBN, T2_BNH = Cfg::kBNH, T2_STAGES = Cfg::kStages, T2_SMEM_B = Cfg::kSmemB;
+  constexpr int KA = Cfg::kKA, T2_TILE = Cfg::kATile, T2_SMEM_A = Cfg::kATile, KDIM = 64 * KA;
   constexpr int T2_BATOM = Cfg::kBAtom, T2_BTILE = Cfg::kBTile, CPW = Cfg::kCPW, NSL = Cfg::kSlices;
   constexpr uint32_t T2_IDESC = Cfg::kIdesc;
   extern __shared__ uint8_t smem_raw[];
@@ -263,9 +297,9 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
         if (leader) mbar_expect_tx(a_full, 2 * T2_TILE);
         {
           const int row = job.q_row + r * T2_ROWS + rank * T2_BM;
-          tma_load_2d_pair(sA, &q_main, 0, row, a_full);
-          tma_load_2d_pair(sA + T2_ATOM, &q_main, 64, row, a_full);
-          tma_load_2d_pair(sA + 2 * T2_ATOM, &q_ext, TC_DIM, row, a_full);
+#pragma unroll
+          for (int a = 0; a < KA; ++a) tma_load_2d_pair(sA + a * T2_ATOM, &q_main, 64 * a, row, a_full);
+          tma_load_2d_pair(sA + KA * T2_ATOM, &q_ext, KDIM, row, a_full);
         }
         ++ai;
         const int n_tiles = (job.nt + T2_BN - 1) / T2_BN;
@@ -275,9 +309,9 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
           if (leader) mbar_expect_tx(&b_full[st], 2 * T2_BTILE);
           uint8_t* dst = sB + st * T2_BTILE;
           const int row = job.t_row + n * T2_BN + rank * T2_BNH;      // this CTA's half of the train tile
-          tma_load_2d_pair(dst, &t_main, 0, row, &b_full[st]);
-          tma_load_2d_pair(dst + T2_BATOM, &t_main, 64, row, &b_full[st]);
-          tma_load_2d_pair(dst + 2 * T2_BATOM, &t_ext, TC_DIM, row, &b_full[st]);
+#pragma unroll
+          for (int a = 0; a < KA; ++a) tma_load_2d_pair(dst + a * T2_BATOM, &t_main, 64 * a, row, &b_full[st]);
+          tma_load_2d_pair(dst + KA * T2_BATOM, &t_ext, KDIM, row, &b_full[st]);
         }
       }
     }
@@ -306,14 +340,14 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
             const uint32_t b_lo = b_lo0 + st * (T2_BTILE >> 4);
             const uint32_t d_tmem = tmem_base + as * T2_BN;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < 4 * KA; ++k) {
               const uint32_t aoff = ((k >> 2) * T2_ATOM + (k & 3) * 32) >> 4;
               const uint32_t boff = ((k >> 2) * T2_BATOM + (k & 3) * 32) >> 4;
               umma_f16_pair(d_tmem, (static_cast<uint64_t>(HI128) << 32) | (a_lo + aoff),
                             (static_cast<uint64_t>(HI128) << 32) | (b_lo + boff), T2_IDESC, k > 0 ? 1u : 0u);
             }
-            umma_f16_pair(d_tmem, (static_cast<uint64_t>(HI32) << 32) | (a_lo + ((2 * T2_ATOM) >> 4)),
-                          (static_cast<uint64_t>(HI32) << 32) | (b_lo + ((2 * T2_BATOM) >> 4)), T2_IDESC, 1u);
+            umma_f16_pair(d_tmem, (static_cast<uint64_t>(HI32) << 32) | (a_lo + ((KA * T2_ATOM) >> 4)),
+                          (static_cast<uint64_t>(HI32) << 32) | (b_lo + ((KA * T2_BATOM) >> 4)), T2_IDESC, 1u);
             umma_commit_pair(&acc_full[as]);
             umma_commit_pair(&b_empty[st]);
           }
@@ -334,7 +368,9 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
       const int row = r * T2_ROWS + rank * T2_BM + quarter * 32 + lane;
       Top2p s;
       s.m1 = s.m2 = __int_as_float(0x7f800000);
-      s.i1 = s.i2 = -1;                                // MODE 2: i1 = base column of the winning 32-column chunk
+      s.i1 = s.i2 = -1;                                // MODE 2: i1 = base column of the winning 16-column chunk
+      Keys4 ks;
+      ks.k1 = ks.k2 = ks.k3 = ks.k4 = ks.k5 = ks.k6 = __int_as_float(0x7f800000);
       const int n_tiles = (job.nt + T2_BN - 1) / T2_BN;
       for (int n = 0; n < n_tiles; ++n, ++ti) {
         const uint32_t as = ti & 1, use = ti >> 1;
@@ -355,7 +391,8 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
               tc_fence_before();
               if (lane == 0) mbar_arrive_leader(&acc_empty[as]);
             }
-            if (MODE == 2) t2_fast(s, v, c0 + 32 * c);
+            if (MODE == 3) { keys_chunk16(ks, v, c0 + 32 * c); keys_chunk16(ks, v + 16, c0 + 32 * c + 16); }
+            else if (MODE == 2) t2_fast(s, v, c0 + 32 * c);
             else t2_scan32(s, v, c0 + 32 * c);
           }
         } else {
@@ -369,7 +406,10 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
 #pragma unroll
             for (int e = 0; e < 32; ++e)
               if (32 * c + e >= lim) v[e] = 0x7f800000u;
-            if (MODE == 2) {
+            if (MODE == 3) {
+              if (lim > 32 * c) keys_chunk16(ks, v, c0 + 32 * c);
+              if (lim > 32 * c + 16) keys_chunk16(ks, v + 16, c0 + 32 * c + 16);
+            } else if (MODE == 2) {
               if (lim > 32 * c) t2_fast16(s, v, c0 + 32 * c);
               if (lim > 32 * c + 16) t2_fast16(s, v + 16, c0 + 32 * c + 16);
             }
@@ -379,15 +419,23 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
       }
       // merge the column slices of this lane quarter: slices 1.. publish, slice 0 merges
       {
-        float4* slot = xchg + ((quarter * (NSL - 1)) * 32 + lane);
+        float4* slot = xchg + ((quarter * (NSL - 1)) * 64 + lane);
         const int bar_id = 1 + quarter;
-        if (slice > 0) slot[(slice - 1) * 32] = make_float4(s.m1, __int_as_float(s.i1), s.m2, __int_as_float(s.i2));
+        if (slice > 0) {
+          slot[(slice - 1) * 64] = MODE == 3 ? make_float4(ks.k1, ks.k2, ks.k3, ks.k4)
+                                             : make_float4(s.m1, __int_as_float(s.i1), s.m2, __int_as_float(s.i2));
+          if (MODE == 3) slot[(slice - 1) * 64 + 32] = make_float4(ks.k5, ks.k6, 0.f, 0.f);
+        }
         asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NSL) : "memory");
         if (slice == 0) {
 #pragma unroll
           for (int o = 0; o < NSL - 1; ++o) {
-            const float4 x = slot[o * 32];
-            if (MODE == 2) {
+            const float4 x = slot[o * 64];
+            if (MODE == 3) {
+              const float4 x2 = slot[o * 64 + 32];
+              keys_insert(ks, x.x); keys_insert(ks, x.y); keys_insert(ks, x.z); keys_insert(ks, x.w);
+              keys_insert(ks, x2.x); keys_insert(ks, x2.y);
+            } else if (MODE == 2) {
               const int ob = __float_as_int(x.y);
               const bool take = ob >= 0 && (s.i1 < 0 || x.x < s.m1 || (x.x == s.m1 && ob < s.i1));
               const float hi = fmaxf(s.m1, x.x);
@@ -401,7 +449,12 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
         }
         asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NSL) : "memory");
       }
-      if (MODE == 2 && slice == 0 && row < job.nq) {
+      if (MODE == 3 && slice == 0 && row < job.nq) {
+        const size_t o = static_cast<size_t>(jb) * stride + row;
+        knn_dist[o] = make_float2(ks.k1, ks.k2);
+        knn_idx[o] = make_int2(__float_as_int(ks.k3), __float_as_int(ks.k4));
+        extra_keys[o] = make_float2(ks.k5, ks.k6);
+      } else if (MODE == 2 && slice == 0 && row < job.nq) {
         const float na = static_cast<float>(qnorm[job.q_row + row]);
         const size_t o = static_cast<size_t>(jb) * stride + row;
         knn_idx[o] = make_int2(s.i1, -2);
@@ -431,6 +484,8 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
 
 using T2Wide = T2Cfg<256, 2>;     // 16 epilogue warps
 using T2Deep = T2Cfg<192, 1>;     // 24 epilogue warps
+using T2F128 = T2Cfg<256, 2, 2>;  // real-valued rows, 128-d
+using T2F256 = T2Cfg<256, 2, 4>;  // real-valued rows, 256-d (SuperPoint)
 
 cudaError_t tc2_configure() {
   cudaError_t e;
@@ -439,6 +494,7 @@ cudaError_t tc2_configure() {
                                 CFG::kSmemBytes)) != cudaSuccess) return e
   PM_T2_ATTR(T2Wide, 0); PM_T2_ATTR(T2Wide, 1); PM_T2_ATTR(T2Wide, 2);
   PM_T2_ATTR(T2Deep, 0); PM_T2_ATTR(T2Deep, 1); PM_T2_ATTR(T2Deep, 2);
+  PM_T2_ATTR(T2F128, 3); PM_T2_ATTR(T2F256, 3);
 #undef PM_T2_ATTR
   return cudaSuccess;
 }
@@ -457,13 +513,34 @@ cudaError_t launch_l2_tc2(const TcMaps& maps, const int32_t* qnorm, const PairJo
   const CUtensorMap& te = variant == 1 ? maps.t_ext96 : maps.t_ext;
 #define PM_T2_LAUNCH(CFG, M)                                                                         \
   l2_top2_tc2_kernel<CFG, M><<<grid, CFG::kThreads, CFG::kSmemBytes, st>>>(                          \
-      maps.q_main, maps.q_ext, tm, te, qnorm, jobs, n_jobs, tiles_per_job, idx, dist, stride)
+      maps.q_main, maps.q_ext, tm, te, qnorm, jobs, n_jobs, tiles_per_job, idx, dist, stride, nullptr)
   if (variant == 1) {
     if (mode == 1) PM_T2_LAUNCH(T2Deep, 1); else if (mode == 2) PM_T2_LAUNCH(T2Deep, 2); else PM_T2_LAUNCH(T2Deep, 0);
   } else {
     if (mode == 1) PM_T2_LAUNCH(T2Wide, 1); else if (mode == 2) PM_T2_LAUNCH(T2Wide, 2); else PM_T2_LAUNCH(T2Wide, 0);
   }
 #undef PM_T2_LAUNCH
+  return cudaGetLastError();
+}
+
+// Real-valued rows (fp16 operand forms of 64*KA + 16 halfs per row): approximate scores, 4 best chunk
+// keys per query row in (knn_dist = k1,k2 | knn_idx = bits of k3,k4 | extra = k5,k6).  dim: 128 or 256.
+cudaError_t launch_l2f_tc2(const TcMaps& maps, int dim, const PairJob* jobs, int n_jobs, int max_nq, int2* idx,
+                           float2* dist, float2* extra, int stride, int num_sms, cudaStream_t st) {
+  if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
+  const int tiles_per_job = (max_nq + T2_ROWS - 1) / T2_ROWS;
+  const int n_items = n_jobs * tiles_per_job;
+  int clusters = num_sms / 2;
+  if (n_items < clusters) clusters = n_items;
+  const int grid = clusters * 2;
+  if (dim == 128)
+    l2_top2_tc2_kernel<T2F128, 3><<<grid, T2F128::kThreads, T2F128::kSmemBytes, st>>>(
+        maps.q_main, maps.q_ext, maps.t_main, maps.t_ext, nullptr, jobs, n_jobs, tiles_per_job, idx, dist, stride, extra);
+  else if (dim == 256)
+    l2_top2_tc2_kernel<T2F256, 3><<<grid, T2F256::kThreads, T2F256::kSmemBytes, st>>>(
+        maps.q_main, maps.q_ext, maps.t_main, maps.t_ext, nullptr, jobs, n_jobs, tiles_per_job, idx, dist, stride, extra);
+  else
+    return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
 

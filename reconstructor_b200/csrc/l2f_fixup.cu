@@ -1,0 +1,280 @@
+// l2f_fixup.cu -- exact fp32 re-rank behind the real-valued tensor-core search (l2_tc2.cu MODE 3).
+//
+// The tcgen05 kernel scores every (query, train) pair of a real-valued descriptor set (SuperPoint:
+// 256 floats of unit norm, FeatureSuperPoint.cpp:195-205) with fp16 operands:
+//     score(a, b) ~= |b|^2 - 2 a.b + 2         (= d^2 - |a|^2 + 2, always > 0 for |a|,|b| <= ~1)
+// and keeps, per query row, the SIX smallest 16-column chunk minima as keys (score with the chunk id in
+// the low 10 mantissa bits).  This kernel turns that into the exact answer of the brute-force search the
+// reference's knnMatch stands for (FeatureMatcher.cpp:48-49; exact arbiter = sum_k (a_k - b_k)^2 in fp32,
+// k ascending, fused multiply-add -- bit-identical to l2_top2_simt_kernel):
+//   * every column of a candidate chunk is re-evaluated exactly;
+//   * a rigorous bound eps on |key - exact score| (fp16 operand rounding 2^-9 |a||b|, tensor-core
+//     accumulation, key truncation 2^-13, fp32 evaluation error) gives a LOWER bound on the exact d^2 of
+//     every column that was not re-evaluated: lb(K_next) = K_next - eps + |a|^2 - 2;
+//   * chunks are evaluated in key order until the requested facts are certain:
+//       L2F_NEED_RATIO    nearest index + outcome of Lowe's test d1 < ratio * d2 (FeatureMatcher.cpp:55)
+//       L2F_NEED_NEAREST  nearest index (cross-check direction)
+//       L2F_NEED_FULL     (idx1, idx2, d1, d2) as cv::DMatch rows
+//   * a row that six chunks cannot certify is scanned exhaustively by the whole block (exact, rare).
+// Ties resolve to the lowest train index (cv::BFMatcher's rule): certification is strict (<), so an
+// unevaluated column can never tie with a reported one.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pm {
+
+static constexpr int FF_THREADS = 128;            // 8 half-warps
+static constexpr int FF_HW = FF_THREADS / 16;
+static constexpr int FF_SPAN = 128;               // query rows per block
+static constexpr int FF_MAXDIM = 256;
+static constexpr unsigned int FF_IDMASK = 0x3FFu;
+
+struct FfBound {          // per query row: exact_d2(col) is within [K - eps(K) + c, K + eps(K) + c]
+  double c, e0;
+  __device__ __forceinline__ double eps(float K) const { return 1.02 * (e0 + 1.2207031e-4 * K) + 1e-7; }
+  __device__ __forceinline__ float lb(float K) const {            // rounded down, >= 0; +inf stays +inf
+    if (K == __int_as_float(0x7f800000)) return K;
+    const double v = static_cast<double>(K) - eps(K) + c;
+    return v > 0.0 ? __double2float_rd(v) : 0.f;
+  }
+  __device__ __forceinline__ float ub(float K) const {
+    if (K == __int_as_float(0x7f800000)) return K;
+    const double v = static_cast<double>(K) + eps(K) + c;
+    return v > 0.0 ? __double2float_ru(v) : 0.f;
+  }
+};
+
+__device__ __forceinline__ FfBound ff_bound(float na2, float nb2max, int dim) {
+  FfBound b;
+  const double na = sqrt(static_cast<double>(na2)) * (1.0 + 1e-6);
+  const double nb = sqrt(static_cast<double>(nb2max)) * (1.0 + 1e-6);
+  const double sD = sqrt(static_cast<double>(dim));
+  const double u24 = 5.9604644775390625e-8;          // 2^-24
+  const double e_op = 1.002 * 1.953125e-3 * na * nb + 1.01 * u24 * sD * (na + nb);      // fp16 operands
+  const double e_acc = 1.52587890625e-5 * (nb * nb + 2.0 * na * nb + 2.0);              // 2^-16: accumulation
+  const double e_nrm = 3.814697265625e-6 * (na * na + nb * nb);                         // 2^-18: fp32 norms, fp16 split
+  const double e_f32 = 1.01 * (dim + 3) * u24 * (na + nb) * (na + nb);                  // exact side is fp32 too
+  b.e0 = e_op + e_acc + e_nrm + e_f32;
+  b.c = static_cast<double>(na2) - 2.0;
+  return b;
+}
+
+// exact fp32 squared distance in the SIMT kernel's operation order (l2_simt.cu: d = a - b; acc = fma(d, d, acc))
+__device__ __forceinline__ float ff_dist(const float* __restrict__ qs, const float* __restrict__ trow, int dim) {
+  float acc = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < dim; k += 4) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(trow + k));
+    const float4 a = *reinterpret_cast<const float4*>(qs + k);
+    float d = a.x - b.x; acc = fmaf(d, d, acc);
+    d = a.y - b.y; acc = fmaf(d, d, acc);
+    d = a.z - b.z; acc = fmaf(d, d, acc);
+    d = a.w - b.w; acc = fmaf(d, d, acc);
+  }
+  return acc;
+}
+
+__device__ __forceinline__ void ff_merge(unsigned long long& m1, unsigned long long& m2, unsigned long long o1,
+                                         unsigned long long o2) {
+  const unsigned long long lo = m1 < o1 ? m1 : o1;
+  const unsigned long long hi = m1 < o1 ? o1 : m1;
+  const unsigned long long s = m2 < o2 ? m2 : o2;
+  m1 = lo;
+  m2 = hi < s ? hi : s;
+}
+
+__device__ __forceinline__ void ff_write_exact(int2* knn_idx, float2* knn_dist, size_t o, unsigned long long e1,
+                                               unsigned long long e2) {
+  const float inf = __int_as_float(0x7f800000);
+  int2 oi;
+  float2 od;
+  oi.x = e1 == KEY_NONE64 ? -1 : static_cast<int>(e1 & 0xFFFFFFFFull);
+  oi.y = e2 == KEY_NONE64 ? -1 : static_cast<int>(e2 & 0xFFFFFFFFull);
+  od.x = e1 == KEY_NONE64 ? inf : __fsqrt_rn(__uint_as_float(static_cast<unsigned int>(e1 >> 32)));
+  od.y = e2 == KEY_NONE64 ? inf : __fsqrt_rn(__uint_as_float(static_cast<unsigned int>(e2 >> 32)));
+  knn_idx[o] = oi;
+  knn_dist[o] = od;
+}
+
+__global__ void __launch_bounds__(FF_THREADS)
+l2f_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm, int dim,
+                 const PairJob* __restrict__ jobs, int2* __restrict__ knn_idx, float2* __restrict__ knn_dist,
+                 const float2* __restrict__ extra, int stride, float ratio, int need,
+                 unsigned long long* __restrict__ counters) {
+  __shared__ __align__(16) float qs[FF_HW][FF_MAXDIM];
+  __shared__ float keys_s[FF_SPAN][6];
+  __shared__ int list[FF_SPAN];
+  __shared__ int ovf[FF_SPAN];
+  __shared__ unsigned long long red[FF_HW][2];
+  __shared__ int cnt, n_ovf;
+
+  const PairJob jb = jobs[blockIdx.y];
+  const int span0 = blockIdx.x * FF_SPAN;
+  if (span0 >= jb.nq) return;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int hw = tid >> 4, l = lane & 15;
+  const unsigned hmask = (lane & 16) ? 0xffff0000u : 0x0000ffffu;
+  const size_t base = static_cast<size_t>(blockIdx.y) * stride;
+  const float inf = __int_as_float(0x7f800000);
+  const float* tbase = raw + static_cast<size_t>(jb.t_row) * dim;
+
+  // ---- pass 1: one thread per row; close the rows whose outcome the keys already decide -----------
+  if (tid == 0) { cnt = 0; n_ovf = 0; }
+  __syncthreads();
+  {
+    const int row = span0 + tid;
+    if (row < jb.nq) {
+      const float2 k12 = knn_dist[base + row];
+      const int2 k34 = knn_idx[base + row];
+      const float2 k56 = extra[base + row];
+      const float K[6] = {k12.x, k12.y, __int_as_float(k34.x), __int_as_float(k34.y), k56.x, k56.y};
+      bool need_row = K[0] != inf;                                // no train rows at all: no neighbours
+      if (need_row && need == L2F_NEED_RATIO) {
+        const FfBound bd = ff_bound(fnorm[jb.q_row + row], jb.t_maxn, dim);
+        // true d1^2 >= lb(K1), true d2^2 <= ub(K2): the test fails for good when even these cannot pass
+        need_row = !(__fsqrt_rn(bd.lb(K[0])) >= __fmul_rn(ratio, __fsqrt_rn(bd.ub(K[1]))));
+      }
+      if (need_row) {
+        const int e = atomicAdd(&cnt, 1);
+        list[e] = tid;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) keys_s[tid][j] = K[j];
+      } else {
+        knn_idx[base + row] = make_int2(-1, -1);
+        knn_dist[base + row] = make_float2(inf, inf);
+      }
+    }
+  }
+  __syncthreads();
+  const int n_need = cnt;
+  unsigned int n_chunks = 0;
+  float worst = 0.f;
+
+  // ---- pass 2: one half-warp per surviving row, lane = column of the chunk under evaluation ---------
+  for (int e = hw; e < n_need; e += FF_HW) {
+    const int r = list[e];
+    const int row = span0 + r;
+    const float* qrow = raw + (static_cast<size_t>(jb.q_row) + row) * dim;
+    __syncwarp(hmask);
+    for (int k = 4 * l; k < dim; k += 64)
+      *reinterpret_cast<float4*>(&qs[hw][k]) = __ldg(reinterpret_cast<const float4*>(qrow + k));
+    __syncwarp(hmask);
+    const FfBound bd = ff_bound(fnorm[jb.q_row + row], jb.t_maxn, dim);
+    unsigned long long e1 = KEY_NONE64, e2 = KEY_NONE64;
+    bool done = false;
+    for (int j = 0; j < 6 && !done; ++j) {
+      const float Kj = keys_s[r][j];
+      if (Kj == inf) break;                              // (unreachable: the previous lbn was +inf)
+      const int cb = static_cast<int>(__float_as_uint(Kj) & FF_IDMASK) * 16;
+      const int ncol = min(16, jb.nt - cb);
+      unsigned long long k1 = KEY_NONE64, k2 = KEY_NONE64;
+      if (l < ncol) {
+        const float d2 = ff_dist(qs[hw], tbase + static_cast<size_t>(cb + l) * dim, dim);
+        k1 = (static_cast<unsigned long long>(__float_as_uint(d2)) << 32) | static_cast<unsigned int>(cb + l);
+      }
+      const unsigned long long own = k1;
+#pragma unroll
+      for (int off = 8; off >= 1; off >>= 1) {
+        const unsigned long long o1 = __shfl_xor_sync(hmask, k1, off, 16);
+        const unsigned long long o2 = __shfl_xor_sync(hmask, k2, off, 16);
+        ff_merge(k1, k2, o1, o2);
+      }
+      (void)own;
+      ++n_chunks;
+      {  // how tight is the bound?  |key - exact chunk minimum score| / eps  (statistics only)
+        const float ex = __uint_as_float(static_cast<unsigned int>(k1 >> 32));
+        const double err = fabs(static_cast<double>(Kj) - (static_cast<double>(ex) - bd.c));
+        worst = fmaxf(worst, static_cast<float>(err / bd.eps(Kj)));
+      }
+      ff_merge(e1, e2, k1, k2);
+      const float lbn = bd.lb(keys_s[r][j < 5 ? j + 1 : 5]);     // every column not evaluated so far is >= lbn
+      const float d1sq = __uint_as_float(static_cast<unsigned int>(e1 >> 32));
+      const float d2sq = e2 == KEY_NONE64 ? inf : __uint_as_float(static_cast<unsigned int>(e2 >> 32));
+      const size_t o = base + row;
+      if (need == L2F_NEED_FULL) {
+        if (d2sq < lbn || lbn == inf) { done = true; if (l == 0) ff_write_exact(knn_idx, knn_dist, o, e1, e2); }
+      } else if (need == L2F_NEED_NEAREST) {
+        if (d1sq < lbn || lbn == inf) {
+          done = true;
+          if (l == 0) {
+            knn_idx[o] = make_int2(static_cast<int>(e1 & 0xFFFFFFFFull), -1);
+            knn_dist[o] = make_float2(__fsqrt_rn(d1sq), inf);
+          }
+        }
+      } else {
+        const float D1 = __fsqrt_rn(d1sq);
+        if (lbn == inf || (d1sq < lbn && d2sq < lbn)) {
+          done = true;                                   // both neighbours certain
+          if (l == 0) ff_write_exact(knn_idx, knn_dist, o, e1, e2);
+        } else if (d1sq < lbn && D1 < __fmul_rn(ratio, __fsqrt_rn(lbn))) {
+          done = true;                                   // nearest certain, true d2 >= lbn: passes whatever d2 is
+          if (l == 0) {
+            knn_idx[o] = make_int2(static_cast<int>(e1 & 0xFFFFFFFFull), 0x7ffffffe);
+            knn_dist[o] = make_float2(D1, __fsqrt_rn(lbn));
+          }
+        } else if (__fsqrt_rn(fminf(d1sq, lbn)) >= __fmul_rn(ratio, __fsqrt_rn(d2sq))) {
+          done = true;                                   // true d1 >= min(d1sq, lbn), true d2 <= d2sq: fails
+          if (l == 0) { knn_idx[o] = make_int2(-1, -1); knn_dist[o] = make_float2(inf, inf); }
+        }
+      }
+    }
+    if (!done && l == 0) ovf[atomicAdd(&n_ovf, 1)] = r;
+  }
+  __syncthreads();
+
+  // ---- pass 3: rows the six chunks could not certify -- exhaustive exact scan by the whole block ----
+  const int n_over = n_ovf;
+  for (int e = 0; e < n_over; ++e) {
+    const int row = span0 + ovf[e];
+    const float* qrow = raw + (static_cast<size_t>(jb.q_row) + row) * dim;
+    __syncthreads();
+    for (int k = 4 * tid; k < dim; k += 4 * FF_THREADS)
+      *reinterpret_cast<float4*>(&qs[0][k]) = __ldg(reinterpret_cast<const float4*>(qrow + k));
+    __syncthreads();
+    unsigned long long m1 = KEY_NONE64, m2 = KEY_NONE64;
+    for (int col = tid; col < jb.nt; col += FF_THREADS) {
+      const float d2 = ff_dist(qs[0], tbase + static_cast<size_t>(col) * dim, dim);
+      const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(d2)) << 32) | static_cast<unsigned int>(col);
+      const unsigned long long hi = key > m1 ? key : m1;
+      m1 = key < m1 ? key : m1;
+      m2 = m2 < hi ? m2 : hi;
+    }
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1) {
+      const unsigned long long o1 = __shfl_xor_sync(hmask, m1, off, 16);
+      const unsigned long long o2 = __shfl_xor_sync(hmask, m2, off, 16);
+      ff_merge(m1, m2, o1, o2);
+    }
+    if (l == 0) { red[hw][0] = m1; red[hw][1] = m2; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int h = 1; h < FF_HW; ++h) ff_merge(m1, m2, red[h][0], red[h][1]);
+      ff_write_exact(knn_idx, knn_dist, base + row, m1, m2);
+    }
+  }
+
+  if (counters != nullptr) {
+    if (tid == 0) {
+      if (n_need) atomicAdd(&counters[0], static_cast<unsigned long long>(n_need));
+      if (n_over) atomicAdd(&counters[2], static_cast<unsigned long long>(n_over));
+    }
+    if (l == 0) {
+      if (n_chunks) atomicAdd(&counters[1], static_cast<unsigned long long>(n_chunks));
+      const unsigned int wb = __float_as_uint(worst);
+      if (wb > static_cast<unsigned int>(counters[3])) atomicMax(&counters[3], static_cast<unsigned long long>(wb));
+    }
+  }
+}
+
+cudaError_t launch_l2f_fixup(const float* raw, const float* fnorm, int dim, const PairJob* jobs, int n_jobs,
+                             int max_nq, int2* idx, float2* dist, const float2* extra, int stride, float ratio,
+                             int need, unsigned long long* counters, cudaStream_t st) {
+  if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
+  if (dim <= 0 || dim > FF_MAXDIM || (dim & 63)) return cudaErrorInvalidValue;
+  dim3 grid((max_nq + FF_SPAN - 1) / FF_SPAN, n_jobs);
+  l2f_fixup_kernel<<<grid, FF_THREADS, 0, st>>>(raw, fnorm, dim, jobs, idx, dist, extra, stride, ratio, need,
+                                                counters);
+  return cudaGetLastError();
+}
+
+}  // namespace pm

@@ -81,6 +81,71 @@ cudaError_t launch_pack_sift(const float* raw_f32, const uint8_t* raw_u8, int n,
   return cudaGetLastError();
 }
 
+// Real-valued rows (SuperPoint: 256 floats of unit norm, FeatureSuperPoint.cpp:195-205; or any float
+// descriptor of 128 / 256 elements with moderate magnitudes) -> fp16 operand forms of dim + 16 halfs:
+//   query form [ -2*a | 1, 1, 1, 1, 0 x12 ]      train form [ b | p0, p1, p2, 2, 0 x12 ]
+// with |b|^2 = p0 + p1 + p2 up to 2^-33 (three fp16 pieces of the fp32 norm) and +2 keeping every score
+// positive.  stats[0] = max |x| (float bits), stats[1] = max |row|^2 (float bits), stats[2] = non-finite seen.
+__global__ void __launch_bounds__(256)
+pack_float_kernel(const float* __restrict__ raw, int n, int dim, __half* __restrict__ qh, __half* __restrict__ th,
+                  float* __restrict__ fnorm, unsigned int* __restrict__ stats) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const int kp = dim + 16;
+  const float* src = raw + static_cast<size_t>(row) * dim;
+  __half* qrow = qh + static_cast<size_t>(row) * kp;
+  __half* trow = th + static_cast<size_t>(row) * kp;
+  float nrm = 0.f, amax = 0.f;
+  bool bad = false;
+  for (int k = 4 * lane; k < dim; k += 128) {
+    const float4 f = *reinterpret_cast<const float4*>(src + k);
+    const float v[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      bad |= !(fabsf(v[e]) <= 3.0e38f);
+      amax = fmaxf(amax, fabsf(v[e]));
+      nrm = fmaf(v[e], v[e], nrm);
+    }
+    reinterpret_cast<__half2*>(qrow + k)[0] = __floats2half2_rn(-2.f * v[0], -2.f * v[1]);
+    reinterpret_cast<__half2*>(qrow + k)[1] = __floats2half2_rn(-2.f * v[2], -2.f * v[3]);
+    reinterpret_cast<__half2*>(trow + k)[0] = __floats2half2_rn(v[0], v[1]);
+    reinterpret_cast<__half2*>(trow + k)[1] = __floats2half2_rn(v[2], v[3]);
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    nrm += __shfl_xor_sync(0xffffffffu, nrm, off);
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+  }
+  bad = __any_sync(0xffffffffu, bad);
+  if (lane < 16) {
+    float qe = 0.f, te = 0.f;
+    const float p0 = __half2float(__float2half_rn(nrm));
+    const float r1 = nrm - p0;
+    const float p1 = __half2float(__float2half_rn(r1));
+    const float p2 = r1 - p1;
+    if (lane == 0) { qe = 1.f; te = p0; }
+    else if (lane == 1) { qe = 1.f; te = p1; }
+    else if (lane == 2) { qe = 1.f; te = p2; }
+    else if (lane == 3) { qe = 1.f; te = 2.f; }
+    qrow[dim + lane] = __float2half_rn(qe);
+    trow[dim + lane] = __float2half_rn(te);
+  }
+  if (lane == 0) {
+    fnorm[row] = nrm;
+    atomicMax(&stats[0], __float_as_uint(amax));
+    atomicMax(&stats[1], __float_as_uint(nrm));
+    if (bad) atomicOr(&stats[2], 1u);
+  }
+}
+
+cudaError_t launch_pack_float(const float* raw, int n, int dim, __half* qh, __half* th, float* fnorm,
+                              unsigned int* stats, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  pack_float_kernel<<<(n + 7) / 8, 256, 0, st>>>(raw, n, dim, qh, th, fnorm, stats);
+  return cudaGetLastError();
+}
+
 __global__ void u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, size_t n) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = static_cast<float>(src[i]);

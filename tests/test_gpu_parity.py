@@ -434,3 +434,126 @@ def test_multi_device_handle_matches_single_device():
             outs.append(pm.match_all_pairs())
     for k in ("pair_ij", "offsets", "q", "t", "inlier", "status", "n_inliers"):
         assert np.array_equal(outs[0][k], outs[1][k]), k
+
+
+# ---------------------------------------------------------------------------------------------
+# real-valued rows on the tensor cores (fp16 scores + certified exact fp32 re-rank) vs the SIMT kernel
+# ---------------------------------------------------------------------------------------------
+def _unit_rows(rng, n, dim):
+    x = rng.standard_normal((n, dim)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True).astype(np.float32)
+    x *= np.float32(0.999)                      # |x|^2 <= 1 after fp32 rounding
+    return x
+
+
+@pytest.mark.parametrize("dim", [128, 256])
+def test_float_tensor_knn_equals_simt_bit_exact(dim):
+    """pm_knn_pair through MODE 3 + L2F_NEED_FULL equals the fp32 SIMT kernel bit for bit, incl. planted
+    duplicates (ties -> lowest index), ragged sizes and single-chunk train sets."""
+    rng = np.random.default_rng(dim)
+    base = _unit_rows(rng, 3000, dim)
+    q = base[:1500].copy()
+    t = (base[700:2900] + 0.02 * rng.standard_normal((2200, dim)).astype(np.float32)).astype(np.float32)
+    t /= (np.linalg.norm(t, axis=1, keepdims=True) * 1.001).astype(np.float32)
+    t[5] = t[900]; t[1700] = t[900]; t[901] = t[900]          # exact ties inside and across chunks
+    t[40] = q[3]; t[41] = q[3]                                  # zero distance, tie within a chunk
+    cases = [(1500, 2200), (257, 300), (129, 17), (5, 1), (3, 2), (700, 16), (64, 2049)]
+    got = {}
+    for flags in (0, 1):
+        with api.PairMatcher(debug_flags=flags) as pm:
+            for nq, nt in cases:
+                pm.set_image(0, q[:nq]); pm.set_image(1, t[:nt])
+                got[(flags, nq, nt)] = pm.knn_pair(0, 1)
+            st = pm.stats()
+        if flags == 0:
+            assert st["rerank_rows"] > 0, "tensor path did not run"
+            assert st["rerank_worst_err"] < 1.0, st
+        else:
+            assert st["rerank_rows"] == 0
+    for nq, nt in cases:
+        a, b = got[(0, nq, nt)], got[(1, nq, nt)]
+        bad = np.nonzero((a[0] != b[0]).any(axis=1))[0]
+        assert len(bad) == 0, (nq, nt, bad[:8], a[0][bad[:4]], b[0][bad[:4]])
+        assert np.array_equal(a[1], b[1]), (nq, nt)
+    oi, o2 = orc.knn2_l2(q, t)
+    idx, dist = got[(0, 1500, 2200)]
+    np.testing.assert_allclose(dist, np.sqrt(o2), rtol=1e-5)
+    for r in np.nonzero((idx != oi).any(axis=1))[0]:
+        assert abs(o2[r, 1] - o2[r, 0]) <= 1e-6 * o2[r, 1] or o2[r, 0] == 0
+
+
+@pytest.mark.parametrize("mode", [api.UNIQUE_FIRST_WINS, api.MUTUAL_NN, api.UNIQUE_NONE])
+def test_float_tensor_batched_equals_simt_all_modes(mode):
+    w = synth.World("superpoint", 1100, seed=77)
+    imgs = []
+    for i in range(5):
+        d, xy, _ = w.image(i, 5, outlier_frac=0.2)
+        cut = 1100 - 83 * i
+        d = d[:cut].copy(); xy = xy[:cut]
+        if i == 1:
+            d[40] = d[7]; d[300] = d[7]; d[301] = d[7]
+        if i == 3:
+            d[:] = d[0]                         # every row identical: all distances tie (certified to fail the ratio test)
+        imgs.append((d, xy))
+    outs = []
+    for flags in (0, 1):
+        with api.PairMatcher(unique_mode=mode, batch_pairs=3, debug_flags=flags) as pm:
+            for i, (d, xy) in enumerate(imgs):
+                pm.set_image(i, d, xy)
+            outs.append(pm.match_all_pairs())
+            st = pm.stats()
+            assert (st["rerank_rows"] > 0) == (flags == 0)
+            assert st["rerank_worst_err"] < 1.0
+    for k in ("offsets", "q", "t", "inlier", "status", "n_inliers", "ransac_iters", "F"):
+        assert np.array_equal(outs[0][k], outs[1][k]), (mode, k)
+    assert outs[0]["offsets"][-1] > 500
+
+
+def test_float_tensor_overflow_scan_and_fallbacks():
+    """Identical rows force the exhaustive scan in FULL mode; non-unit and non-finite images use the SIMT kernel."""
+    rng = np.random.default_rng(5)
+    q = _unit_rows(rng, 300, 256)
+    t = np.repeat(_unit_rows(rng, 1, 256), 400, axis=0)         # 25 chunks with the same score
+    with api.PairMatcher() as pm:
+        pm.set_image(0, q); pm.set_image(1, t)
+        idx, dist = pm.knn_pair(0, 1)
+        st = pm.stats()
+    assert st["rerank_overflow"] == 300
+    assert (idx[:, 0] == 0).all() and (idx[:, 1] == 1).all()
+    with api.PairMatcher(debug_flags=1) as pm:
+        pm.set_image(0, q); pm.set_image(1, t)
+        i2, d2 = pm.knn_pair(0, 1)
+    assert np.array_equal(idx, i2) and np.array_equal(dist, d2)
+    big = (3.0 * _unit_rows(rng, 200, 256)).astype(np.float32)
+    with api.PairMatcher() as pm:
+        pm.set_image(0, q); pm.set_image(1, big)
+        idx, dist = pm.knn_pair(0, 1)
+        assert pm.stats()["rerank_rows"] == 0                   # |x|^2 = 9 > bound: SIMT kernel
+    oi, o2 = orc.knn2_l2(q, big)
+    assert np.array_equal(idx, oi)
+    np.testing.assert_allclose(dist, np.sqrt(o2), rtol=1e-5)
+
+
+def test_float_tensor_full_size_superpoint():
+    """8192 x 8192 x 256-d (BASELINE config #4 shape): tensor path == SIMT path bit for bit, CSR identical."""
+    w = synth.World("superpoint", 8192, seed=0xB200 + 4)
+    imgs = [w.image(i, 100, outlier_frac=0.3 if i == 2 else 0.0)[:2] for i in range(4)]
+    outs, knn_rows = [], []
+    for flags in (0, 1):
+        with api.PairMatcher(debug_flags=flags) as pm:
+            for i, (d, xy) in enumerate(imgs):
+                pm.set_image(i, d, xy)
+            knn_rows.append(pm.knn_pair(0, 1))
+            outs.append(pm.match_all_pairs())
+            st = pm.stats()
+            if flags == 0:
+                assert st["rerank_rows"] > 0 and st["rerank_worst_err"] < 1.0, st
+                print("rerank stats", {k: st[k] for k in st if k.startswith("rerank")})
+    assert np.array_equal(knn_rows[0][0], knn_rows[1][0]) and np.array_equal(knn_rows[0][1], knn_rows[1][1])
+    for k in ("offsets", "q", "t", "inlier", "status", "n_inliers", "ransac_iters", "F"):
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+    oi, o2 = orc.knn2_l2(imgs[0][0], imgs[1][0])
+    np.testing.assert_allclose(knn_rows[0][1], np.sqrt(o2), rtol=1e-5)
+    for r in np.nonzero((knn_rows[0][0] != oi).any(axis=1))[0]:
+        assert abs(o2[r, 1] - o2[r, 0]) <= 1e-6 * o2[r, 1]
+    assert outs[0]["offsets"][-1] > 6 * 1500
