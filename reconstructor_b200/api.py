@@ -18,7 +18,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpairmatch_b200.so")
+# PM_B200_LIB: A/B runs of two builds on the same GPU box (development aid); default = the in-tree build
+LIB_PATH = os.environ.get("PM_B200_LIB") or os.path.join(_HERE, "libpairmatch_b200.so")
 
 DESC_F32, DESC_U8_BITS, DESC_U8 = 0, 1, 2
 UNIQUE_FIRST_WINS, MUTUAL_NN, UNIQUE_NONE = 0, 1, 2

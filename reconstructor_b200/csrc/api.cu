@@ -236,7 +236,13 @@ struct DeviceCtx {
                   prop.major, prop.minor);
     num_sms = prop.multiProcessorCount;
     PM_CUDA(cudaStreamCreateWithFlags(&ingest, cudaStreamNonBlocking));
-    PM_CUDA(cudaStreamCreateWithFlags(&knn_stream, cudaStreamNonBlocking));
+    {
+      // the persistent kNN kernels go first whenever SMs free up; the small tail kernels of earlier batches
+      // (default priority) fill whatever registers / shared memory the kNN kernel leaves
+      int prio_lo = 0, prio_hi = 0;
+      PM_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      PM_CUDA(cudaStreamCreateWithPriority(&knn_stream, cudaStreamNonBlocking, prio_hi));
+    }
     PM_CUDA(cudaEventCreate(&ev_a));
     PM_CUDA(cudaEventCreate(&ev_b));
     PM_CUDA(cudaMalloc(&d_flag, sizeof(int)));
@@ -247,6 +253,10 @@ struct DeviceCtx {
     PM_CUDA(cudaMemset(d_l2f, 0, 4 * sizeof(unsigned long long)));
     PM_CUDA(tc_configure());
     PM_CUDA(tc2_configure());
+    PM_CUDA(fixup_configure());
+    PM_CUDA(l2f_configure());
+    PM_CUDA(select_configure());
+    PM_CUDA(ransac_configure());
     stats.device_id = dev;
     return PM_OK;
   }
@@ -563,6 +573,7 @@ struct DeviceCtx {
     //   bit6      batched loop uses the general kernel instead of values-only kernel + fix-up
     //   bits7-8   VALUES-ONLY kernel of the batched loop: 0 CTA pair 256-col (default), 1 single-CTA,
     //             2 CTA pair 192-col
+    //   bit9      values-only CTA-pair kernel in its 64-register build (tail kernels co-resident)
     const int code = (prm.debug_flags >> 2) & 7;
     const int fcode = (prm.debug_flags >> 7) & 3;
     const int variant = ((prm.debug_flags >> 1) & 1) ^ 1;
@@ -580,7 +591,8 @@ struct DeviceCtx {
       if (!use_tc) return launch_l2_simt(raw, dim, jobs_d, n, mq, oi, od, s.stride, knn_stream);
       if (use_fast) {
         if (fcode == 1) return launch_l2_tc(maps, qnorm, jobs_d, n, mq, oi, od, s.stride, num_sms, nullptr, 5, knn_stream);
-        return launch_l2_tc2(maps, qnorm, jobs_d, n, mq, oi, od, s.stride, num_sms, fcode == 2, 2, knn_stream);
+        return launch_l2_tc2(maps, qnorm, jobs_d, n, mq, oi, od, s.stride, num_sms, fcode == 2,
+                             (fcode == 0 && ((prm.debug_flags >> 9) & 1)) ? 4 : 2, knn_stream);
       }
       if (code >= 5 && !dump)
         return launch_l2_tc2(maps, qnorm, jobs_d, n, mq, oi, od, s.stride, num_sms, code == 7,

@@ -61,6 +61,12 @@ cudaError_t launch_l2f_fixup(const float* raw, const float* fnorm, int dim, cons
                              int max_nq, int2* idx, float2* dist, const float2* extra, int stride, float ratio,
                              int need, unsigned long long* counters, cudaStream_t st);
 
+// shared-memory carve-out of the small tail kernels = the tensor kernel's, so that they can be co-resident
+cudaError_t fixup_configure();
+cudaError_t l2f_configure();
+cudaError_t select_configure();
+cudaError_t ransac_configure();
+
 // l2_fixup.cu -- exact index / 2nd-neighbour recovery after the branch-free tensor epilogue
 cudaError_t launch_l2_fixup(const uint32_t* u8desc, const int32_t* qnorm, const PairJob* jobs, int n_jobs,
                             int max_nq, int reversed, int2* idx, float2* dist, int stride, float ratio,

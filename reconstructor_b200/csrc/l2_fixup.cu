@@ -116,6 +116,10 @@ l2_fixup_kernel(const uint32_t* __restrict__ u8desc, const int32_t* __restrict__
   }
 }
 
+cudaError_t fixup_configure() {
+  return cudaFuncSetAttribute(l2_fixup_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 cudaError_t launch_l2_fixup(const uint32_t* u8desc, const int32_t* qnorm, const PairJob* jobs, int n_jobs,
                             int max_nq, int reversed, int2* idx, float2* dist, int stride, float ratio,
                             int all_rows, cudaStream_t st) {

@@ -44,8 +44,12 @@ struct T2Cfg {
   static constexpr int kSlices = BN / (32 * CPW);
   static constexpr int kEpiWarps = 4 * kSlices;
   static constexpr int kThreads = 128 + 32 * kEpiWarps;
-  static constexpr int kBAtom = kBNH * 128, kBExt = kBNH * 32, kBTile = KA * kBAtom + kBExt;
-  static constexpr int kStages = KA == 4 ? 2 : (BN == 256 ? 3 : 4);
+  // the train-tile ring is staged in K GROUPS of two 64-wide atoms (the norm block rides with the last
+  // group): one group per tile for 128-d rows, two for 256-d rows -- finer stages hide the TMA latency
+  // that two whole-tile stages of 68 KB could not
+  static constexpr int kBAtom = kBNH * 128, kBExt = kBNH * 32, kBTile = 2 * kBAtom + kBExt;   // one stage
+  static constexpr int kGroups = KA / 2;
+  static constexpr int kStages = KA == 4 ? 3 : (BN == 256 ? 3 : 4);
   static constexpr int kSmemB = kStages * kBTile;
   static constexpr int kXchg = 4 * (kSlices - 1) * 32 * 32;   // two float4 per (quarter, slice, lane)
   static constexpr int kSmemBytes = kATile + kSmemB + 1024 + 256 + kXchg;
@@ -230,8 +234,13 @@ __device__ __forceinline__ void t2_merge(Top2p& s, float om1, int oi1, float om2
   s = t;
 }
 
-template <class Cfg, int MODE>   // 0: exact top-2 with indices, 1: timing probe, 2: values-only (fix-up follows)
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::kThreads, 1)
+// MODE 0: exact top-2 with indices, 1: timing probe, 2: values-only (l2_fixup follows), 3: real-valued rows.
+// LEAN variants are compiled for <= 64 registers per thread (launch bound of 1024 threads; no spills):
+// 20 warps x 64 = 40,960 registers and <= 190 KB of shared memory per SM leave room for the small tail
+// kernels of the previous batch (re-rank / fix-up, select, RANSAC) to be co-resident with this persistent
+// kernel, which runs on a higher-priority stream.
+template <class Cfg, int MODE, bool LEAN = (MODE == 3)>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LEAN ? 1024 : Cfg::kThreads, 1)
 l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant__ CUtensorMap q_ext,
                    const __grid_constant__ CUtensorMap t_main, const __grid_constant__ CUtensorMap t_ext,
                    const int32_t* __restrict__ qnorm, const PairJob* __restrict__ jobs, int n_jobs,
@@ -243,6 +252,7 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
   constexpr int T2_BN = Cfg::kBN, T2_BNH = Cfg::kBNH, T2_STAGES = Cfg::kStages, T2_SMEM_B = Cfg::kSmemB;
   constexpr int KA = Cfg::kKA, T2_TILE = Cfg::kATile, T2_SMEM_A = Cfg::kATile, KDIM = 64 * KA;
   constexpr int T2_BATOM = Cfg::kBAtom, T2_BTILE = Cfg::kBTile, CPW = Cfg::kCPW, NSL = Cfg::kSlices;
+  constexpr int NGRP = Cfg::kGroups;
   constexpr uint32_t T2_IDESC = Cfg::kIdesc;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -303,15 +313,19 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
         }
         ++ai;
         const int n_tiles = (job.nt + T2_BN - 1) / T2_BN;
-        for (int n = 0; n < n_tiles; ++n, ++bi) {
-          const uint32_t st = bi % T2_STAGES;
-          wait_trap(&b_empty[st], ((bi / T2_STAGES) & 1) ^ 1);
-          if (leader) mbar_expect_tx(&b_full[st], 2 * T2_BTILE);
-          uint8_t* dst = sB + st * T2_BTILE;
+        for (int n = 0; n < n_tiles; ++n) {
           const int row = job.t_row + n * T2_BN + rank * T2_BNH;      // this CTA's half of the train tile
 #pragma unroll
-          for (int a = 0; a < KA; ++a) tma_load_2d_pair(dst + a * T2_BATOM, &t_main, 64 * a, row, &b_full[st]);
-          tma_load_2d_pair(dst + KA * T2_BATOM, &t_ext, KDIM, row, &b_full[st]);
+          for (int g = 0; g < NGRP; ++g, ++bi) {
+            const uint32_t st = bi % T2_STAGES;
+            wait_trap(&b_empty[st], ((bi / T2_STAGES) & 1) ^ 1);
+            const bool last = g == NGRP - 1;
+            if (leader) mbar_expect_tx(&b_full[st], 2 * (2 * T2_BATOM + (last ? Cfg::kBExt : 0)));
+            uint8_t* dst = sB + st * T2_BTILE;
+            tma_load_2d_pair(dst, &t_main, 128 * g, row, &b_full[st]);
+            tma_load_2d_pair(dst + T2_BATOM, &t_main, 128 * g + 64, row, &b_full[st]);
+            if (last) tma_load_2d_pair(dst + 2 * T2_BATOM, &t_ext, KDIM, row, &b_full[st]);
+          }
         }
       }
     }
@@ -330,28 +344,33 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
         wait_trap(a_full, ai & 1);
         ++ai;
         const int n_tiles = (job_nt + T2_BN - 1) / T2_BN;
-        for (int n = 0; n < n_tiles; ++n, ++bi, ++ti) {
-          const uint32_t st = bi % T2_STAGES;
+        for (int n = 0; n < n_tiles; ++n, ++ti) {
           const uint32_t as = ti & 1, use = ti >> 1;
-          wait_trap(&b_full[st], (bi / T2_STAGES) & 1);
           wait_trap(&acc_empty[as], (use & 1) ^ 1);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t b_lo = b_lo0 + st * (T2_BTILE >> 4);
-            const uint32_t d_tmem = tmem_base + as * T2_BN;
+          const uint32_t d_tmem = tmem_base + as * T2_BN;
 #pragma unroll
-            for (int k = 0; k < 4 * KA; ++k) {
-              const uint32_t aoff = ((k >> 2) * T2_ATOM + (k & 3) * 32) >> 4;
-              const uint32_t boff = ((k >> 2) * T2_BATOM + (k & 3) * 32) >> 4;
-              umma_f16_pair(d_tmem, (static_cast<uint64_t>(HI128) << 32) | (a_lo + aoff),
-                            (static_cast<uint64_t>(HI128) << 32) | (b_lo + boff), T2_IDESC, k > 0 ? 1u : 0u);
+          for (int g = 0; g < NGRP; ++g, ++bi) {
+            const uint32_t st = bi % T2_STAGES;
+            wait_trap(&b_full[st], (bi / T2_STAGES) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t b_lo = b_lo0 + st * (T2_BTILE >> 4);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const uint32_t aoff = ((2 * g + (k >> 2)) * T2_ATOM + (k & 3) * 32) >> 4;
+                const uint32_t boff = ((k >> 2) * T2_BATOM + (k & 3) * 32) >> 4;
+                umma_f16_pair(d_tmem, (static_cast<uint64_t>(HI128) << 32) | (a_lo + aoff),
+                              (static_cast<uint64_t>(HI128) << 32) | (b_lo + boff), T2_IDESC, (g > 0 || k > 0) ? 1u : 0u);
+              }
+              if (g == NGRP - 1) {
+                umma_f16_pair(d_tmem, (static_cast<uint64_t>(HI32) << 32) | (a_lo + ((KA * T2_ATOM) >> 4)),
+                              (static_cast<uint64_t>(HI32) << 32) | (b_lo + ((2 * T2_BATOM) >> 4)), T2_IDESC, 1u);
+                umma_commit_pair(&acc_full[as]);
+              }
+              umma_commit_pair(&b_empty[st]);
             }
-            umma_f16_pair(d_tmem, (static_cast<uint64_t>(HI32) << 32) | (a_lo + ((KA * T2_ATOM) >> 4)),
-                          (static_cast<uint64_t>(HI32) << 32) | (b_lo + ((KA * T2_BATOM) >> 4)), T2_IDESC, 1u);
-            umma_commit_pair(&acc_full[as]);
-            umma_commit_pair(&b_empty[st]);
+            __syncwarp();
           }
-          __syncwarp();
         }
         if (elect_one()) umma_commit_pair(a_empty);
         __syncwarp();
@@ -491,8 +510,14 @@ cudaError_t tc2_configure() {
   cudaError_t e;
 #define PM_T2_ATTR(CFG, M)                                                                                       \
   if ((e = cudaFuncSetAttribute(l2_top2_tc2_kernel<CFG, M>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
-                                CFG::kSmemBytes)) != cudaSuccess) return e
+                                CFG::kSmemBytes)) != cudaSuccess) return e;                                        \
+  if ((e = cudaFuncSetAttribute(l2_top2_tc2_kernel<CFG, M>, cudaFuncAttributePreferredSharedMemoryCarveout,           \
+                                cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e
   PM_T2_ATTR(T2Wide, 0); PM_T2_ATTR(T2Wide, 1); PM_T2_ATTR(T2Wide, 2);
+  if ((e = cudaFuncSetAttribute(l2_top2_tc2_kernel<T2Wide, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                T2Wide::kSmemBytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(l2_top2_tc2_kernel<T2Wide, 2, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
   PM_T2_ATTR(T2Deep, 0); PM_T2_ATTR(T2Deep, 1); PM_T2_ATTR(T2Deep, 2);
   PM_T2_ATTR(T2F128, 3); PM_T2_ATTR(T2F256, 3);
 #undef PM_T2_ATTR
@@ -500,7 +525,8 @@ cudaError_t tc2_configure() {
 }
 
 // variant 0: 256-column tiles / 16 epilogue warps; variant 1: 192-column tiles / 24 epilogue warps.
-// mode 0: exact top-2 with indices; 1: timing probe (garbage results); 2: values only (run l2_fixup next).
+// mode 0: exact top-2 with indices; 1: timing probe (garbage results); 2: values only (run l2_fixup next);
+// 4: as 2, 64-register build (256-column variant only).
 cudaError_t launch_l2_tc2(const TcMaps& maps, const int32_t* qnorm, const PairJob* jobs, int n_jobs, int max_nq,
                           int2* idx, float2* dist, int stride, int num_sms, int variant, int mode, cudaStream_t st) {
   if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
@@ -517,7 +543,12 @@ cudaError_t launch_l2_tc2(const TcMaps& maps, const int32_t* qnorm, const PairJo
   if (variant == 1) {
     if (mode == 1) PM_T2_LAUNCH(T2Deep, 1); else if (mode == 2) PM_T2_LAUNCH(T2Deep, 2); else PM_T2_LAUNCH(T2Deep, 0);
   } else {
-    if (mode == 1) PM_T2_LAUNCH(T2Wide, 1); else if (mode == 2) PM_T2_LAUNCH(T2Wide, 2); else PM_T2_LAUNCH(T2Wide, 0);
+    if (mode == 1) PM_T2_LAUNCH(T2Wide, 1);
+    else if (mode == 2) PM_T2_LAUNCH(T2Wide, 2);
+    else if (mode == 4)     // values-only, 64-register build (co-resident tail kernels)
+      l2_top2_tc2_kernel<T2Wide, 2, true><<<grid, T2Wide::kThreads, T2Wide::kSmemBytes, st>>>(
+          maps.q_main, maps.q_ext, tm, te, qnorm, jobs, n_jobs, tiles_per_job, idx, dist, stride, nullptr);
+    else PM_T2_LAUNCH(T2Wide, 0);
   }
 #undef PM_T2_LAUNCH
   return cudaGetLastError();

@@ -266,6 +266,10 @@ l2f_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm,
   }
 }
 
+cudaError_t l2f_configure() {
+  return cudaFuncSetAttribute(l2f_fixup_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 cudaError_t launch_l2f_fixup(const float* raw, const float* fnorm, int dim, const PairJob* jobs, int n_jobs,
                              int max_nq, int2* idx, float2* dist, const float2* extra, int stride, float ratio,
                              int need, unsigned long long* counters, cudaStream_t st) {

@@ -23,7 +23,7 @@
 
 namespace pm {
 
-static constexpr int RS_THREADS = 256;
+static constexpr int RS_THREADS = 128;   // 16 K registers per block: co-resident with the persistent tensor kernel
 static constexpr int RS_WARPS = RS_THREADS / 32;
 static constexpr int RS_ROUND = 32;
 
@@ -350,7 +350,7 @@ __device__ __forceinline__ float residual(const double* F, float2 q1, float2 q2,
   return static_cast<float>(e1 > e2 ? e1 : e2);
 }
 
-__global__ void __launch_bounds__(RS_THREADS, 2)
+__global__ void __launch_bounds__(RS_THREADS, 4)
 fmat_ransac_kernel(const float2* __restrict__ pts1, const float2* __restrict__ pts2,
                    const int32_t* __restrict__ count, int stride, RansacDev prm,
                    uint8_t* __restrict__ mask, double* __restrict__ F_out,
@@ -480,6 +480,10 @@ fmat_ransac_kernel(const float2* __restrict__ pts1, const float2* __restrict__ p
     iters_out[slot] = sIter;
     for (int i = 0; i < 9; ++i) F_out[9 * slot + i] = best > 0 ? bestF[i] : 0.0;
   }
+}
+
+cudaError_t ransac_configure() {
+  return cudaFuncSetAttribute(fmat_ransac_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 cudaError_t launch_ransac(const float2* pts1, const float2* pts2, const int32_t* count, int n_jobs,

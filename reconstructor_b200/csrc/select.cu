@@ -13,7 +13,7 @@
 
 namespace pm {
 
-static constexpr int SEL_THREADS = 1024;
+static constexpr int SEL_THREADS = 512;    // 16 K registers per block: co-resident with the persistent tensor kernel
 
 __global__ void __launch_bounds__(SEL_THREADS)
 ratio_unique_compact_kernel(const PairJob* __restrict__ jobs, const int2* __restrict__ knn_idx,
@@ -26,7 +26,8 @@ ratio_unique_compact_kernel(const PairJob* __restrict__ jobs, const int2* __rest
   const PairJob job = jobs[slot];
   const size_t base = static_cast<size_t>(slot) * stride;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  __shared__ int warp_cnt[32];
+  constexpr int NW = SEL_THREADS / 32;
+  __shared__ int warp_cnt[NW];
   __shared__ int run_base;
 
   int32_t* own = owner + base;
@@ -61,14 +62,14 @@ ratio_unique_compact_kernel(const PairJob* __restrict__ jobs, const int2* __rest
     if (lane == 0) warp_cnt[warp] = __popc(bal);
     __syncthreads();
     if (warp == 0) {
-      const int v = warp_cnt[lane];
+      const int v = lane < NW ? warp_cnt[lane] : 0;
       int s = v;
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
         const int o = __shfl_up_sync(0xffffffffu, s, off);
         if (lane >= off) s += o;
       }
-      warp_cnt[lane] = s - v;                 // exclusive prefix over the 32 warps
+      if (lane < NW) warp_cnt[lane] = s - v;  // exclusive prefix over the warps
     }
     __syncthreads();
     const int pos = run_base + warp_cnt[warp] + lane_off;
@@ -87,7 +88,7 @@ ratio_unique_compact_kernel(const PairJob* __restrict__ jobs, const int2* __rest
     }
     __syncthreads();
     // last thread of the chunk knows the chunk total: exclusive offset of warp 31 + its count
-    if (tid == SEL_THREADS - 1) run_base = run_base + warp_cnt[31] + __popc(bal);
+    if (tid == SEL_THREADS - 1) run_base = run_base + warp_cnt[NW - 1] + __popc(bal);
     __syncthreads();
   }
   if (tid == 0) count[slot] = run_base;
@@ -173,6 +174,13 @@ cudaError_t launch_compact(const int32_t* count, int n_jobs, int stride, const i
   gather_slabs_kernel<<<n_jobs, 256, 0, st>>>(count, stride, match_q, match_t, mask, offsets, out_q,
                                               out_t, out_mask);
   return cudaGetLastError();
+}
+
+cudaError_t select_configure() {
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(ratio_unique_compact_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(scan_counts_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(gather_slabs_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 }  // namespace pm
