@@ -86,6 +86,30 @@ def _c_oracle_pair(ij):
     return len(orc.match_pair(d1, x1, d2, x2)["q"])
 
 
+def _flann_sample(ij):
+    """FLANN top-1 indices and the reference body's final match set for one pair (recall report)."""
+    from oracle import cv2_ref
+    i, j = ij
+    (d1, x1), (d2, x2) = _CPU_IMGS[i], _CPU_IMGS[j]
+    f1, f2 = d1.astype(np.float32), d2.astype(np.float32)
+    idx, _ = cv2_ref.knn2_flann(f1, f2)
+    r = cv2_ref.match_pair(f1, x1, f2, x2, matcher="flann")
+    return idx[:, 0].copy(), np.stack([r["q"], r["t"]], axis=1)
+
+
+def flann_samples(imgs, sample_pairs):
+    """Runs before any CUDA context exists (fork).  Returns {pair: (top1, final (q,t))} or None."""
+    import multiprocessing as mp
+    global _CPU_IMGS
+    from oracle import cv2_ref
+    if not cv2_ref.have_cv2():
+        return None
+    _CPU_IMGS = imgs
+    with mp.get_context("fork").Pool(min(len(sample_pairs), 4)) as pool:
+        out = pool.map(_flann_sample, sample_pairs, chunksize=1)
+    return dict(zip(sample_pairs, out))
+
+
 def cpu_arm(imgs, pairs, seconds, steps=1, warmup=0, pairs_per_step=None):
     """Returns dict(value pairs/s, cores, kind, sample, ms_per_step)."""
     import multiprocessing as mp
@@ -207,6 +231,9 @@ def main():
         sub = np.array([(i, j) for x, i in enumerate(sub_ids) for j in sub_ids[x + 1:]], np.int32)
         r = cpu_arm({i: imgs[i] for i in sub_ids}, sub, a.cpu_seconds)
         cpu = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=r["sample"])
+        flann = flann_samples({i: imgs[i] for i in sub_ids}, [tuple(int(x) for x in sub[k]) for k in (0, 1, len(sub) // 2, len(sub) - 1)][:len(sub)])
+    else:
+        flann = None
 
     import torch
     import torch.distributed as dist
@@ -300,7 +327,7 @@ def main():
                     peak_source="MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if pk
                     else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)")
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof["kernel"] = {"sift": "l2_top2_tc2_kernel", "orb": "hamming_top2_kernel", "superpoint": "l2_top2_tc2_kernel (MODE 3, fp16 scores + exact fp32 re-rank)"}[a.kind]
+    roof["kernel"] = {"sift": "l2_top2_tc2_kernel", "orb": "hamming_top2_kernel", "superpoint": "l2_top2_tc2_kernel<T2Cfg<256,2,4>,3>"}[a.kind]
     roof["launches"] = st["knn_launches"]
     roof["avg_launch_ms"] = st["knn_ms"] / max(st["knn_launches"], 1)
     roof["share_of_step"] = st["knn_ms"] / max(dev_ms, 1e-9) if world == 1 else None
@@ -317,6 +344,21 @@ def main():
             roof["traffic_source"] = t["source"]
     except Exception:
         pass
+
+    # ---- recall of the reference's approximate FLANN search against this exact search ------
+    if cpu is not None and flann:
+        agree = tot = inter = union = 0
+        for (i, j), (top1, final) in flann.items():
+            gi, _ = pm.knn_pair(i, j)
+            agree += int((gi[:, 0] == top1).sum()); tot += len(top1)
+            g = pm.match_filter_pair(i, j)
+            keep = g["inlier"].astype(bool)
+            gs = set(zip(g["q"][keep].tolist(), g["t"][keep].tolist()))
+            fs = set(map(tuple, final.tolist()))
+            inter += len(gs & fs); union += len(gs | fs)
+        cpu["recall"] = dict(pairs=len(flann), flann_top1_agreement=agree / max(tot, 1),
+                             final_match_set_iou=inter / max(union, 1),
+                             note="reference FLANN (approximate) vs this library's exact search, same pairs")
 
     # ---- e2e: host buffers in, host CSR out, every step ---------------------------------------------
     e2e = None
