@@ -17,6 +17,14 @@
 // The arithmetic order follows the CPU filter of the parity tests operation for operation;
 // this translation unit MUST be compiled with -fmad=false (no fp contraction).
 #include <cfloat>
+#if defined(PM_RANSAC_PROFILE) || defined(PM_RANSAC_PARANOID)
+#include <cstdio>
+#endif
+#ifdef PM_RANSAC_PROFILE      // development build: per-phase cycle counts of the first CTAs (tools/ransac_prof.py)
+#define PM_PHASE(acc) do { const long long t1_ = clock64(); acc += t1_ - t0_; t0_ = t1_; } while (0)
+#else
+#define PM_PHASE(acc) do { } while (0)
+#endif
 
 #include "common.cuh"
 #include "kernels.h"
@@ -24,7 +32,6 @@
 namespace pm {
 
 static constexpr int RS_THREADS = 128;   // 16 K registers per block: co-resident with the persistent tensor kernel
-static constexpr int RS_WARPS = RS_THREADS / 32;
 static constexpr int RS_ROUND = 32;
 
 struct MwcRng {
@@ -332,7 +339,44 @@ __device__ int seven_point_coop(const float2* __restrict__ p1, const float2* __r
   return n;
 }
 
-__device__ __forceinline__ float residual(const double* F, float2 q1, float2 q2, int mode) {
+// Inlier test of cv::findFundamentalMat's RANSAC: (float)err <= (float)(thr * thr), err computed in fp64
+// without contraction (computeError) -- literal_inlier() below, the arbiter.
+//
+// Almost every point is far from the threshold, so the hot loop uses a CONSERVATIVE classifier first:
+// n = d^2 and g = a^2 + b^2 evaluated with fused multiply-adds and no division;
+//     n <  thr*(1-m)*g for both terms          -> inlier for sure
+//     n >= thr*(1+2.5e-7)*(1+m)*g for either   -> outlier for sure          (1 / 0 / 2 = undecided)
+// The margin m = 1e-9 + 4e-14 * max|coordinate| covers (a) the float rounding of err (< 1.2e-7 relative,
+// the 2.5e-7 factor), (b) the fp64 rounding of n * (1/g) (< 4e-16), (c) the difference between the fused
+// and the literal evaluation of d: a few ulps of the largest term, amplified by the cancellation
+// |x a| + |y b| + |c| <= ~2 (|x|+|y|) sqrt(g) at the decision boundary |d| = 3 sqrt(g).  Undecided points
+// (~1e-7 of all) go through literal_inlier(); the outcome is therefore identical by construction.
+// g = 0 / inf / NaN need no special case: the strict '<' fails for g = 0 and every comparison with NaN is
+// false, which lands in the literal formula's own behaviour (NaN compares false = outlier).
+struct Pt4 { double x1, y1, x2, y2; };
+template <int MODE>
+__device__ __forceinline__ int classify(const double* __restrict__ F, const Pt4& p, double lo, double hi) {
+  const double a2 = fma(F[0], p.x1, fma(F[1], p.y1, F[2]));
+  const double b2 = fma(F[3], p.x1, fma(F[4], p.y1, F[5]));
+  const double c2 = fma(F[6], p.x1, fma(F[7], p.y1, F[8]));
+  const double g2 = fma(a2, a2, b2 * b2);
+  const double d2 = fma(p.x2, a2, fma(p.y2, b2, c2));
+  const double a1 = fma(F[0], p.x2, fma(F[3], p.y2, F[6]));
+  const double b1 = fma(F[1], p.x2, fma(F[4], p.y2, F[7]));
+  const double g1 = fma(a1, a1, b1 * b1);
+  const double n2 = d2 * d2;
+  if (MODE == 1) {
+    const double g = g1 + g2;
+    return n2 < lo * g ? 1 : (n2 >= hi * g ? 0 : 2);
+  }
+  const double c1 = fma(F[2], p.x2, fma(F[5], p.y2, F[8]));
+  const double d1 = fma(p.x1, a1, fma(p.y1, b1, c1));
+  const double n1 = d1 * d1;
+  const bool in = n1 < lo * g1 && n2 < lo * g2;
+  const bool out = n1 >= hi * g1 || n2 >= hi * g2;
+  return in ? 1 : (out ? 0 : 2);
+}
+__device__ __noinline__ int literal_inlier(const double* F, float2 q1, float2 q2, int mode, float thr) {
   const double x1 = q1.x, y1 = q1.y, x2 = q2.x, y2 = q2.y;
   double a = F[0] * x1 + F[1] * y1 + F[2];
   double b = F[3] * x1 + F[4] * y1 + F[5];
@@ -344,10 +388,87 @@ __device__ __forceinline__ float residual(const double* F, float2 q1, float2 q2,
   c = F[2] * x2 + F[5] * y2 + F[8];
   const double g1 = a * a + b * b;
   const double d1 = x1 * a + y1 * b + c;
-  if (mode == 1) return static_cast<float>(d2 * d2 / (g1 + g2));
+  if (mode == 1) return static_cast<float>(d2 * d2 / (g1 + g2)) <= thr ? 1 : 0;
   const double s2 = 1. / g2, s1 = 1. / g1;
   const double e1 = d1 * d1 * s1, e2 = d2 * d2 * s2;
-  return static_cast<float>(e1 > e2 ? e1 : e2);
+  return static_cast<float>(e1 > e2 ? e1 : e2) <= thr ? 1 : 0;
+}
+__device__ __forceinline__ int inlier_of(const double* F, float2 q1, float2 q2, int mode, float thr, double lo,
+                                         double hi) {
+  const Pt4 p{q1.x, q1.y, q2.x, q2.y};
+  const int c = mode == 1 ? classify<1>(F, p, lo, hi) : classify<0>(F, p, lo, hi);
+  return c == 2 ? literal_inlier(F, q1, q2, mode, thr) : c;
+}
+
+// Adds, for every model of the round, the number of inliers among this thread's four points to sCnt.
+template <int MODE>
+__device__ __forceinline__ void score_models(const double (*sF)[27], const int* sNm, int (*sCnt)[3], int gen,
+                                             const float2 (&q1)[4], const float2 (&q2)[4], const bool (&valid)[4],
+                                             float thr, double lo, double hi, int lane) {
+  Pt4 p[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) p[u] = Pt4{q1[u].x, q1[u].y, q2[u].x, q2[u].y};
+  for (int k = 0; k < gen; ++k) {
+    const int nm = sNm[k];
+    for (int m = 0; m < nm; ++m) {
+      double F[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) F[i] = sF[k][9 * m + i];
+      int cls[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) cls[u] = classify<MODE>(F, p[u], lo, hi);
+#ifdef PM_RANSAC_PARANOID      // development build: every decided point is re-checked against the literal formula
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (valid[u] && cls[u] != 2 && literal_inlier(F, q1[u], q2[u], MODE, thr) != cls[u])
+          printf("RANSAC PARANOID MISMATCH k %d m %d cls %d pt (%g,%g)-(%g,%g)\n", k, m, cls[u], q1[u].x, q1[u].y,
+                 q2[u].x, q2[u].y);
+      if (lane == 0 && k == 0 && m == 0 && blockIdx.x == 0 && threadIdx.x == 0) printf("paranoid build active\n");
+#endif
+      int good = 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (cls[u] == 2 && valid[u]) cls[u] = literal_inlier(F, q1[u], q2[u], MODE, thr);
+        good += valid[u] ? cls[u] : 0;
+      }
+      const int total = __reduce_add_sync(0xffffffffu, good);
+      if (lane == 0 && total) atomicAdd(&sCnt[k][m], total);
+    }
+  }
+}
+
+// Index subset of one iteration WITHOUT the collinearity test (checked in parallel afterwards): the
+// sequential stream with duplicate re-draw.  uniform(0, n) = next() % n; the modulo is taken with a
+// precomputed reciprocal (inv = floor((2^32 - 1) / n): the quotient estimate is at most 2 short).
+__device__ __forceinline__ void draw7(MwcRng& rng, unsigned int n, unsigned int inv, int* idx) {
+  int v[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    while (true) {
+      const unsigned int raw = rng.next();
+      unsigned int r = raw - __umulhi(raw, inv) * n;
+      while (r >= n) r -= n;
+      bool dup = false;
+#pragma unroll
+      for (int j = 0; j < i; ++j) dup |= v[j] == static_cast<int>(r);
+      if (!dup) { v[i] = static_cast<int>(r); break; }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 7; ++i) idx[i] = v[i];
+}
+
+// (j, k) pair number t of the 15 pairs k < j < 6 tested against the last point (checkSubset)
+__device__ __forceinline__ bool pair_collinear(const float2* __restrict__ p, const int* idx, int t) {
+  int j = 1, k = t;
+  while (k >= j) { k -= j; ++j; }
+  const float2 pi = p[idx[6]], pj = p[idx[j]], pk = p[idx[k]];
+  const double dx1 = static_cast<double>(__fsub_rn(pj.x, pi.x));
+  const double dy1 = static_cast<double>(__fsub_rn(pj.y, pi.y));
+  const double dx2 = static_cast<double>(__fsub_rn(pk.x, pi.x));
+  const double dy2 = static_cast<double>(__fsub_rn(pk.y, pi.y));
+  return fabs(dx2 * dy1 - dy2 * dx1) <=
+         static_cast<double>(FLT_EPSILON) * (fabs(dx1) + fabs(dy1) + fabs(dx2) + fabs(dy2));
 }
 
 __global__ void __launch_bounds__(RS_THREADS, 4)
@@ -396,24 +517,69 @@ fmat_ransac_kernel(const float2* __restrict__ pts1, const float2* __restrict__ p
   }
 
   __shared__ unsigned long long sRng;
+  __shared__ unsigned long long sState[RS_ROUND + 1];   // RNG state in front of every subset of the round
+  __shared__ int sBad;
   if (tid == 0) { sRng = ~0ull; sIter = 0; sNiters = prm.max_iters; sBest = 0; sStop = 0; }
   __syncthreads();
+  const unsigned int inv_m = 0xFFFFFFFFu / static_cast<unsigned int>(M);
+  // margin of the conservative classifier (see classify()): scaled by the largest |coordinate| of the pair
+  __shared__ float sCmax;
+  if (tid == 0) sCmax = 0.f;
+  __syncthreads();
+  {
+    float cm = 0.f;
+    for (int i = tid; i < M; i += RS_THREADS) {
+      const float2 u = p1[i], v = p2[i];
+      cm = fmaxf(cm, fmaxf(fmaxf(fabsf(u.x), fabsf(u.y)), fmaxf(fabsf(v.x), fabsf(v.y))));
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, off));
+    if (lane == 0 && cm > 0.f) atomicMax(reinterpret_cast<int*>(&sCmax), __float_as_int(cm));   // non-negative floats
+  }
+  __syncthreads();
+  const double margin = 1e-9 + 4e-14 * static_cast<double>(sCmax);
+  const double thr_d = prm.thr, thr_lo = thr_d * (1.0 - margin), thr_hi = thr_d * (1.0 + 2.5e-7) * (1.0 + margin);
 
+#ifdef PM_RANSAC_PROFILE
+  long long tS = 0, tV = 0, tC = 0, tU = 0, t0_ = clock64();
+#endif
   int round_size = 8;
   while (true) {
-    // ---- sample (sequential stream) --------------------------------------------------------
+    // ---- sample: the sequential index stream (one thread), then the collinearity test of every
+    //      subset in parallel; a rejected subset (rare) re-plays the stream from its start -------------
     if (tid == 0) {
       MwcRng rng{sRng};
       int g = 0;
       for (; g < round_size; ++g) {
         if (sIter + g >= sNiters) break;
-        if (!get_subset(p1, p2, M, rng, 10000, sSub[g])) { sStop = 1; break; }
+        sState[g] = rng.s;
+        draw7(rng, static_cast<unsigned int>(M), inv_m, sSub[g]);
       }
       sGen = g;
       sRng = rng.s;
+      sBad = 0x7fffffff;
     }
     __syncthreads();
+    for (int w = tid; w < sGen * 30; w += RS_THREADS) {
+      const int h = w / 30, t = w - 30 * h;
+      if (pair_collinear(t < 15 ? p1 : p2, sSub[h], t < 15 ? t : t - 15)) atomicMin(&sBad, h);
+    }
+    __syncthreads();
+    if (sBad < sGen) {
+      if (tid == 0) {
+        MwcRng rng{sState[sBad]};
+        int g = sBad;
+        for (; g < round_size; ++g) {
+          if (sIter + g >= sNiters) break;
+          if (!get_subset(p1, p2, M, rng, 10000, sSub[g])) { sStop = 1; break; }
+        }
+        sGen = g;
+        sRng = rng.s;
+      }
+      __syncthreads();
+    }
     const int gen = sGen;
+    PM_PHASE(tS);
     if (gen == 0) break;
     // ---- solve: one half-warp per hypothesis (row-per-lane Householder QR) ------------------
     {
@@ -425,52 +591,88 @@ fmat_ransac_kernel(const float2* __restrict__ pts1, const float2* __restrict__ p
       }
     }
     __syncthreads();
-    // ---- score: one warp per (iteration, model) -------------------------------------------
-    for (int h = warp; h < gen * 3; h += RS_WARPS) {
-      const int k = h / 3, m = h - 3 * k;
-      if (m >= sNm[k]) continue;
-      double F[9];
+    PM_PHASE(tV);
+    // ---- score: every thread owns four matches at a time and visits all models of the round (the model
+    //      is a shared-memory broadcast, the points stay in registers as doubles) ---------------------
+    for (int w = tid; w < gen * 3; w += RS_THREADS) sCnt[w / 3][w % 3] = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < M; i0 += 4 * RS_THREADS) {
+      float2 q1[4], q2[4];
+      bool valid[4];
 #pragma unroll
-      for (int i = 0; i < 9; ++i) F[i] = sF[k][9 * m + i];
-      int good = 0;
-      for (int i = lane; i < M; i += 32)
-        good += residual(F, p1[i], p2[i], prm.residual_mode) <= prm.thr ? 1 : 0;
-#pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) good += __shfl_xor_sync(0xffffffffu, good, off);
-      if (lane == 0) sCnt[k][m] = good;
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * RS_THREADS + tid;
+        valid[u] = i < M;
+        const int ic = valid[u] ? i : M - 1;
+        q1[u] = p1[ic];
+        q2[u] = p2[ic];
+      }
+      if (prm.residual_mode == 1) score_models<1>(sF, sNm, sCnt, gen, q1, q2, valid, prm.thr, thr_lo, thr_hi, lane);
+      else score_models<0>(sF, sNm, sCnt, gen, q1, q2, valid, prm.thr, thr_lo, thr_hi, lane);
     }
     __syncthreads();
-    // ---- select: ordered scan with the strict-improvement rule ---------------------------
-    if (tid == 0) {
-      int k = 0;
-      for (; k < gen; ++k) {
-        if (sIter + k >= sNiters) break;
-        for (int m = 0; m < sNm[k]; ++m) {
-          const int good = sCnt[k][m];
-          if (good > (sBest > 6 ? sBest : 6)) {
-            sBest = good;
-            for (int i = 0; i < 9; ++i) bestF[i] = sF[k][9 * m + i];
-            sNiters = update_num_iters(prm.confidence, static_cast<double>(M - good) / M, 7,
-                                       sNiters);
+    PM_PHASE(tC);
+    // ---- select: (iteration, model)-ordered "strictly more inliers replaces" with the adaptive bound.
+    //      Improvements are rare, so warp 0 jumps from one improving iteration to the next. -----------
+    if (warp == 0) {
+      const int nm = lane < gen ? sNm[lane] : 0;
+      const int c0 = nm > 0 ? sCnt[lane][0] : -1, c1 = nm > 1 ? sCnt[lane][1] : -1, c2 = nm > 2 ? sCnt[lane][2] : -1;
+      const int cmax = max(c0, max(c1, c2));
+      int best = sBest, niters = sNiters;
+      const int iter0 = sIter;
+      int best_k = -1, best_m = -1;
+      unsigned alive = 0xffffffffu;
+      while (true) {
+        const unsigned imp = __ballot_sync(0xffffffffu, cmax > (best > 6 ? best : 6)) & alive;
+        if (!imp) break;
+        const int k = __ffs(imp) - 1;
+        if (iter0 + k >= niters) break;               // iteration k lies beyond the (shrunken) bound
+        int nb = best, nn = niters, bm = -1;
+        if (lane == k) {
+          for (int m = 0; m < nm; ++m) {
+            const int c = m == 0 ? c0 : (m == 1 ? c1 : c2);
+            if (c > (nb > 6 ? nb : 6)) {
+              nb = c; bm = m;
+              nn = update_num_iters(prm.confidence, static_cast<double>(M - c) / M, 7, nn);
+            }
           }
         }
+        best = __shfl_sync(0xffffffffu, nb, k);
+        niters = __shfl_sync(0xffffffffu, nn, k);
+        best_m = __shfl_sync(0xffffffffu, bm, k);
+        best_k = k;
+        alive = k >= 31 ? 0u : ~((2u << k) - 1u);
       }
-      sIter += k;
-      if (sIter >= sNiters) sStop = 1;
+      if (best_k >= 0 && lane < 9) bestF[lane] = sF[best_k][9 * best_m + lane];
+      if (lane == 0) {
+        // the sequential loop stops at the first k with iter0 + k >= niters; every iteration up to the last
+        // improving one was visited before the bound shrank
+        int kend = niters - iter0;
+        kend = kend < best_k + 1 ? best_k + 1 : kend;
+        kend = kend > gen ? gen : kend;
+        sBest = best; sNiters = niters; sIter = iter0 + kend;
+        if (iter0 + kend >= niters) sStop = 1;
+      }
     }
     __syncthreads();
+    PM_PHASE(tU);
     if (sStop) break;
     round_size = round_size < RS_ROUND ? round_size * 2 : RS_ROUND;
   }
   __syncthreads();
 
+#ifdef PM_RANSAC_PROFILE
+  if (tid == 0 && slot < 3)
+    printf("RANSAC slot %d M %d iters %d best %d | sample %lld solve %lld score %lld select %lld cycles\n", slot, M,
+           sIter, sBest, tS, tV, tC, tU);
+#endif
   const int best = sBest;
   if (best > 0) {
     double F[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) F[i] = bestF[i];
     for (int i = tid; i < M; i += RS_THREADS)
-      msk[i] = residual(F, p1[i], p2[i], prm.residual_mode) <= prm.thr ? 1 : 0;
+      msk[i] = static_cast<uint8_t>(inlier_of(F, p1[i], p2[i], prm.residual_mode, prm.thr, thr_lo, thr_hi));
   } else {
     for (int i = tid; i < M; i += RS_THREADS) msk[i] = 0;
   }
