@@ -189,6 +189,9 @@ struct DeviceCtx {
   float* fnorm = nullptr;      // [rows] fp32 squared norms of real-valued rows
   TcMaps fmaps{};
   bool tcf_ready = false;
+  uint8_t *hq = nullptr, *ht = nullptr;  // [rows][32*words+32] E4M3 operand forms of binary rows (256 / 512 bit)
+  TcMaps hmaps{};
+  bool tch_ready = false;
   unsigned int* d_fstats = nullptr;   // pack_float statistics of the image being ingested
   unsigned int* h_fstats = nullptr;   // pinned
   unsigned long long* d_l2f = nullptr;   // l2f_fixup counters
@@ -257,6 +260,7 @@ struct DeviceCtx {
     PM_CUDA(l2f_configure());
     PM_CUDA(select_configure());
     PM_CUDA(ransac_configure());
+    PM_CUDA(hamming_fixup_configure());
     stats.device_id = dev;
     return PM_OK;
   }
@@ -268,7 +272,7 @@ struct DeviceCtx {
     single.destroy();
     auto fd = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
     fd(raw); fd(qf); fd(tf); fd(qnorm); fd(u8d); fd(bits); fd(xy); fd(d_flag); fd(stage); fd(d_dump);
-    fd(fq); fd(ft); fd(fnorm); fd(d_fstats); fd(d_l2f);
+    fd(fq); fd(ft); fd(fnorm); fd(d_fstats); fd(d_l2f); fd(hq); fd(ht);
     if (h_flag) cudaFreeHost(h_flag);
     if (h_fstats) cudaFreeHost(h_fstats);
     if (ingest) cudaStreamDestroy(ingest);
@@ -279,12 +283,14 @@ struct DeviceCtx {
 
   // ---- tensor maps -----------------------------------------------------------------------
   bool float_tc_shape() const { return dtype == PM_DESC_F32 && (dim == 128 || dim == 256); }
+  bool bits_tc_shape() const { return dtype == PM_DESC_U8_BITS && (words == 8 || words == 16); }
 
   int build_maps() {
     tc_ready = false;
     tcf_ready = false;
+    tch_ready = false;
     const bool sift_shape = dim == TC_DIM && (dtype == PM_DESC_F32 || dtype == PM_DESC_U8);
-    if (!sift_shape && !float_tc_shape()) return PM_OK;
+    if (!sift_shape && !float_tc_shape() && !bits_tc_shape()) return PM_OK;
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -306,6 +312,23 @@ struct DeviceCtx {
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     };
     CUresult r;
+    if (bits_tc_shape()) {
+      const int kb = 32 * words + 32;
+      auto mkb = [&](CUtensorMap* m, void* base, cuuint32_t box_k, CUtensorMapSwizzle sw) -> CUresult {
+        const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(kb), static_cast<cuuint64_t>(cap_rows)};
+        const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(kb)};
+        const cuuint32_t box[2] = {box_k, 128};
+        return encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      };
+      if ((r = mkb(&hmaps.q_main, hq, 128, CU_TENSOR_MAP_SWIZZLE_128B)) != CUDA_SUCCESS ||
+          (r = mkb(&hmaps.q_ext, hq, 32, CU_TENSOR_MAP_SWIZZLE_32B)) != CUDA_SUCCESS ||
+          (r = mkb(&hmaps.t_main, ht, 128, CU_TENSOR_MAP_SWIZZLE_128B)) != CUDA_SUCCESS ||
+          (r = mkb(&hmaps.t_ext, ht, 32, CU_TENSOR_MAP_SWIZZLE_32B)) != CUDA_SUCCESS)
+        return fail(PM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+      tch_ready = true;
+      return PM_OK;
+    }
     if (float_tc_shape()) {
       kpad = dim + 16;
       if ((r = mk(&fmaps.q_main, fq, 64, CU_TENSOR_MAP_SWIZZLE_128B)) != CUDA_SUCCESS ||
@@ -353,6 +376,11 @@ struct DeviceCtx {
     int rc;
     if (dtype == PM_DESC_U8_BITS) {
       if ((rc = grow(bits, words, nc)) != PM_OK) return rc;
+      if (bits_tc_shape()) {
+        if ((rc = grow(hq, 32 * words + 32, nc)) != PM_OK) return rc;
+        if ((rc = grow(ht, 32 * words + 32, nc)) != PM_OK) return rc;
+        if ((rc = grow(qnorm, 1, nc)) != PM_OK) return rc;
+      }
     } else {
       if ((rc = grow(raw, dim, nc)) != PM_OK) return rc;
       if (dim == TC_DIM) {
@@ -414,6 +442,12 @@ struct DeviceCtx {
         const size_t bytes = static_cast<size_t>(n) * words * 4;
         PM_CUDA(cudaMemcpyAsync(bits + static_cast<size_t>(im.row) * words, desc, bytes, kind, ingest));
         if (!on_device) stats.h2d_bytes += bytes;
+        if (bits_tc_shape()) {
+          const size_t kb = 32 * static_cast<size_t>(words) + 32;
+          PM_CUDA(launch_pack_bits(bits + static_cast<size_t>(im.row) * words, n, words, hq + im.row * kb,
+                                   ht + im.row * kb, qnorm + im.row, ingest));
+          ++stats.kernel_launches;
+        }
       } else {
         float* rdst = raw + static_cast<size_t>(im.row) * dim;
         const uint8_t* u8src = nullptr;
@@ -584,7 +618,11 @@ struct DeviceCtx {
                          max_nt <= L2F_MAX_NT &&
                          (!want_rev || max_nq <= L2F_MAX_NT) && !(prm.debug_flags & 1);
     const int epi_of_code[5] = {3, 0, 1, 2, 4};
+    // binary rows: Hamming = |a| + |b| - 2 a.b on the tensor cores (E4M3 {0,1} operands) in the batched loop;
+    // debug_flags bit10 keeps the XOR/popc kernel there too (it always serves raw kNN rows / single pairs)
+    const bool use_tch = dtype == PM_DESC_U8_BITS && tch_ready && fast && !dump && !((prm.debug_flags >> 10) & 1);
     auto knn_main = [&](const PairJob* jobs_d, int mq, int2* oi, float2* od, float2* ox) -> cudaError_t {
+      if (use_tch) return launch_ham_tc2(hmaps, words, qnorm, jobs_d, n, mq, oi, od, s.stride, num_sms, knn_stream);
       if (dtype == PM_DESC_U8_BITS)
         return launch_hamming_top2(bits, words, jobs_d, n, mq, oi, od, s.stride, variant, knn_stream);
       if (use_tcf) return launch_l2f_tc2(fmaps, dim, jobs_d, n, mq, oi, od, ox, s.stride, num_sms, knn_stream);
@@ -620,6 +658,14 @@ struct DeviceCtx {
       ++stats.kernel_launches;
       if (want_rev) {
         PM_CUDA(launch_l2_fixup(u8d, qnorm, s.d_rjobs, n, max_nt, 0, s.rev_idx, s.rev_dist, s.stride, prm.ratio, 1, s.stream));
+        ++stats.kernel_launches;
+      }
+    }
+    if (use_tch) {
+      PM_CUDA(launch_hamming_fixup(bits, words, s.d_jobs, n, max_nq, s.knn_idx, s.knn_dist, s.stride, prm.ratio, 0, s.stream));
+      ++stats.kernel_launches;
+      if (want_rev) {
+        PM_CUDA(launch_hamming_fixup(bits, words, s.d_rjobs, n, max_nt, s.rev_idx, s.rev_dist, s.stride, prm.ratio, 1, s.stream));
         ++stats.kernel_launches;
       }
     }

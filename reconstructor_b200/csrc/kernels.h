@@ -47,6 +47,16 @@ cudaError_t launch_l2_tc2(const TcMaps& maps, const int32_t* qnorm, const PairJo
                           int2* idx, float2* dist, int stride, int num_sms, int variant, int mode,
                           cudaStream_t st);
 
+// binary descriptors on the tensor cores: Hamming = |a| + |b| - 2 a.b with E4M3 {0,1} operands (l2_tc2.cu,
+// kind::f8f6f4) + hamming_fixup.cu.  maps: UINT8 tensor maps over rows of 32*words + 32 bytes.
+cudaError_t launch_ham_tc2(const TcMaps& maps, int words, const int32_t* qnorm, const PairJob* jobs, int n_jobs,
+                           int max_nq, int2* idx, float2* dist, int stride, int num_sms, cudaStream_t st);
+cudaError_t launch_pack_bits(const uint32_t* bits, int n, int words, uint8_t* qb, uint8_t* tb, int32_t* popc,
+                             cudaStream_t st);
+cudaError_t launch_hamming_fixup(const uint32_t* bits, int words, const PairJob* jobs, int n_jobs, int max_nq,
+                                 int2* idx, float2* dist, int stride, float ratio, int all_rows, cudaStream_t st);
+cudaError_t hamming_fixup_configure();
+
 // real-valued rows on the tensor cores: l2_tc2.cu (MODE 3) + l2f_fixup.cu
 cudaError_t launch_l2f_tc2(const TcMaps& maps, int dim, const PairJob* jobs, int n_jobs, int max_nq, int2* idx,
                            float2* dist, float2* extra, int stride, int num_sms, cudaStream_t st);

@@ -77,14 +77,26 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tma
       "l"(tmap), "r"(smem_u32(bar) & T2_PEER_MASK), "r"(c0), "r"(c1)
       : "memory");
 }
+// KIND 0: kind::f16 (fp16 operands, K = 16 per instruction); KIND 1: kind::f8f6f4 with E4M3 operands (K = 32 per
+// instruction, twice the rate).  Both consume 32 bytes of a K-major row per instruction and share the
+// instruction-descriptor encoding used here (format field 0 = F16 resp. E4M3, D = F32).
+template <int KIND>
 __device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                               uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if (KIND == 1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 // Arrives (once all prior MMAs of this thread completed) on the barrier at the same offset in both CTAs.
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
@@ -239,7 +251,7 @@ __device__ __forceinline__ void t2_merge(Top2p& s, float om1, int oi1, float om2
 // 20 warps x 64 = 40,960 registers and <= 190 KB of shared memory per SM leave room for the small tail
 // kernels of the previous batch (re-rank / fix-up, select, RANSAC) to be co-resident with this persistent
 // kernel, which runs on a higher-priority stream.
-template <class Cfg, int MODE, bool LEAN = (MODE == 3)>
+template <class Cfg, int MODE, bool LEAN = (MODE == 3), int KIND = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LEAN ? 1024 : Cfg::kThreads, 1)
 l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant__ CUtensorMap q_ext,
                    const __grid_constant__ CUtensorMap t_main, const __grid_constant__ CUtensorMap t_ext,
@@ -250,7 +262,9 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
   // the epilogue keeps the 6 smallest 16-column chunk minima as keys (score with the chunk id in the low
   // 10 mantissa bits) and l2f_fixup.cu re-ranks exactly in fp32.  qnorm is unused in that mode.
   constexpr int T2_BN = Cfg::kBN, T2_BNH = Cfg::kBNH, T2_STAGES = Cfg::kStages, T2_SMEM_B = Cfg::kSmemB;
-  constexpr int KA = Cfg::kKA, T2_TILE = Cfg::kATile, T2_SMEM_A = Cfg::kATile, KDIM = 64 * KA;
+  constexpr int KA = Cfg::kKA, T2_TILE = Cfg::kATile, T2_SMEM_A = Cfg::kATile;
+  constexpr int KEL = KIND == 1 ? 128 : 64;        // tensor-map elements per 128-byte K atom (E4M3 bytes / fp16)
+  constexpr int KDIM = KEL * KA;
   constexpr int T2_BATOM = Cfg::kBAtom, T2_BTILE = Cfg::kBTile, CPW = Cfg::kCPW, NSL = Cfg::kSlices;
   constexpr int NGRP = Cfg::kGroups;
   constexpr uint32_t T2_IDESC = Cfg::kIdesc;
@@ -308,7 +322,7 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
         {
           const int row = job.q_row + r * T2_ROWS + rank * T2_BM;
 #pragma unroll
-          for (int a = 0; a < KA; ++a) tma_load_2d_pair(sA + a * T2_ATOM, &q_main, 64 * a, row, a_full);
+          for (int a = 0; a < KA; ++a) tma_load_2d_pair(sA + a * T2_ATOM, &q_main, KEL * a, row, a_full);
           tma_load_2d_pair(sA + KA * T2_ATOM, &q_ext, KDIM, row, a_full);
         }
         ++ai;
@@ -322,8 +336,8 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
             const bool last = g == NGRP - 1;
             if (leader) mbar_expect_tx(&b_full[st], 2 * (2 * T2_BATOM + (last ? Cfg::kBExt : 0)));
             uint8_t* dst = sB + st * T2_BTILE;
-            tma_load_2d_pair(dst, &t_main, 128 * g, row, &b_full[st]);
-            tma_load_2d_pair(dst + T2_BATOM, &t_main, 128 * g + 64, row, &b_full[st]);
+            tma_load_2d_pair(dst, &t_main, 2 * KEL * g, row, &b_full[st]);
+            tma_load_2d_pair(dst + T2_BATOM, &t_main, 2 * KEL * g + KEL, row, &b_full[st]);
             if (last) tma_load_2d_pair(dst + 2 * T2_BATOM, &t_ext, KDIM, row, &b_full[st]);
           }
         }
@@ -359,11 +373,11 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
               for (int k = 0; k < 8; ++k) {
                 const uint32_t aoff = ((2 * g + (k >> 2)) * T2_ATOM + (k & 3) * 32) >> 4;
                 const uint32_t boff = ((k >> 2) * T2_BATOM + (k & 3) * 32) >> 4;
-                umma_f16_pair(d_tmem, (static_cast<uint64_t>(HI128) << 32) | (a_lo + aoff),
+                umma_f16_pair<KIND>(d_tmem, (static_cast<uint64_t>(HI128) << 32) | (a_lo + aoff),
                               (static_cast<uint64_t>(HI128) << 32) | (b_lo + boff), T2_IDESC, (g > 0 || k > 0) ? 1u : 0u);
               }
               if (g == NGRP - 1) {
-                umma_f16_pair(d_tmem, (static_cast<uint64_t>(HI32) << 32) | (a_lo + ((KA * T2_ATOM) >> 4)),
+                umma_f16_pair<KIND>(d_tmem, (static_cast<uint64_t>(HI32) << 32) | (a_lo + ((KA * T2_ATOM) >> 4)),
                               (static_cast<uint64_t>(HI32) << 32) | (b_lo + ((2 * T2_BATOM) >> 4)), T2_IDESC, 1u);
                 umma_commit_pair(&acc_full[as]);
               }
@@ -520,6 +534,14 @@ cudaError_t tc2_configure() {
                                 cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
   PM_T2_ATTR(T2Deep, 0); PM_T2_ATTR(T2Deep, 1); PM_T2_ATTR(T2Deep, 2);
   PM_T2_ATTR(T2F128, 3); PM_T2_ATTR(T2F256, 3);
+  if ((e = cudaFuncSetAttribute(l2_top2_tc2_kernel<T2Wide, 2, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                T2Wide::kSmemBytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(l2_top2_tc2_kernel<T2Wide, 2, false, 1>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(l2_top2_tc2_kernel<T2F256, 2, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                T2F256::kSmemBytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(l2_top2_tc2_kernel<T2F256, 2, false, 1>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
 #undef PM_T2_ATTR
   return cudaSuccess;
 }
@@ -551,6 +573,27 @@ cudaError_t launch_l2_tc2(const TcMaps& maps, const int32_t* qnorm, const PairJo
     else PM_T2_LAUNCH(T2Wide, 0);
   }
 #undef PM_T2_LAUNCH
+  return cudaGetLastError();
+}
+
+// Binary descriptors (256 / 512 bit) as E4M3 rows of 32*words + 32 bytes (pack_bits_kernel): the accumulator is
+// |b| - 2 a.b, an exact integer; values-only epilogue (MODE 2), hamming_fixup follows.  qnorm = popcounts.
+cudaError_t launch_ham_tc2(const TcMaps& maps, int words, const int32_t* qnorm, const PairJob* jobs, int n_jobs,
+                           int max_nq, int2* idx, float2* dist, int stride, int num_sms, cudaStream_t st) {
+  if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
+  const int tiles_per_job = (max_nq + T2_ROWS - 1) / T2_ROWS;
+  const int n_items = n_jobs * tiles_per_job;
+  int clusters = num_sms / 2;
+  if (n_items < clusters) clusters = n_items;
+  const int grid = clusters * 2;
+  if (words == 8)
+    l2_top2_tc2_kernel<T2Wide, 2, false, 1><<<grid, T2Wide::kThreads, T2Wide::kSmemBytes, st>>>(
+        maps.q_main, maps.q_ext, maps.t_main, maps.t_ext, qnorm, jobs, n_jobs, tiles_per_job, idx, dist, stride, nullptr);
+  else if (words == 16)
+    l2_top2_tc2_kernel<T2F256, 2, false, 1><<<grid, T2F256::kThreads, T2F256::kSmemBytes, st>>>(
+        maps.q_main, maps.q_ext, maps.t_main, maps.t_ext, qnorm, jobs, n_jobs, tiles_per_job, idx, dist, stride, nullptr);
+  else
+    return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
 

@@ -146,6 +146,55 @@ cudaError_t launch_pack_float(const float* raw, int n, int dim, __half* qh, __ha
   return cudaGetLastError();
 }
 
+// Binary descriptors (ORB: 32 bytes, FeatureDetector.cpp:9,19) -> E4M3 operand rows of 32*W + 32 bytes for the
+// tensor-core Hamming search: Hamming(a, b) = |a| + |b| - 2 a.b, a dense contraction over {0,1} values.
+//   query form [ bit ? -2.0 : 0 | 256, 16, 1, 0 x29 ]     train form [ bit ? 1.0 : 0 | p2, p1, p0, 0 x29 ]
+// with |b| = 256 p2 + 16 p1 + p0 (p1, p0 <= 15, p2 <= 2: all exactly representable in E4M3), so the fp32
+// accumulator holds the exact integer |b| - 2 a.b.  One warp per row; popc[row] = |row|.
+__device__ __forceinline__ unsigned long long spread_bits8(unsigned int b) {     // byte i = bit i of b (0 / 1)
+  const unsigned long long t = (static_cast<unsigned long long>(b) * 0x0101010101010101ull) & 0x8040201008040201ull;
+  return ((t + 0x7F7F7F7F7F7F7F7Full) >> 7) & 0x0101010101010101ull;
+}
+__global__ void __launch_bounds__(256)
+pack_bits_kernel(const uint32_t* __restrict__ bits, int n, int words, uint8_t* __restrict__ qb,
+                 uint8_t* __restrict__ tb, int32_t* __restrict__ popc) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const int kp = 32 * words + 32;
+  const uint32_t w = lane < words ? bits[static_cast<size_t>(row) * words + lane] : 0u;
+  int cnt = __popc(w);
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+  uint8_t* qrow = qb + static_cast<size_t>(row) * kp;
+  uint8_t* trow = tb + static_cast<size_t>(row) * kp;
+  // lane l expands byte j of every word it is handed: 8 bits -> 8 operand bytes
+  for (int j = lane; j < 4 * words; j += 32) {
+    const uint32_t wj = __shfl_sync(0xffffffffu, w, j >> 2);
+    const unsigned long long ones = spread_bits8((wj >> (8 * (j & 3))) & 0xFFu);
+    *reinterpret_cast<unsigned long long*>(qrow + 8 * j) = ones * 0xC0ull;      // -2.0
+    *reinterpret_cast<unsigned long long*>(trow + 8 * j) = ones * 0x38ull;      //  1.0
+  }
+  {
+    const uint8_t e4m3_int[16] = {0x00, 0x38, 0x40, 0x44, 0x48, 0x4A, 0x4C, 0x4E,
+                                  0x50, 0x51, 0x52, 0x53, 0x54, 0x55, 0x56, 0x57};
+    uint8_t qe = 0, te = 0;
+    if (lane == 0) { qe = 0x78; te = e4m3_int[(cnt >> 8) & 15]; }          // 256
+    else if (lane == 1) { qe = 0x58; te = e4m3_int[(cnt >> 4) & 15]; }     // 16
+    else if (lane == 2) { qe = 0x38; te = e4m3_int[cnt & 15]; }            // 1
+    qrow[32 * words + lane] = qe;
+    trow[32 * words + lane] = te;
+  }
+  if (lane == 0) popc[row] = cnt;
+}
+
+cudaError_t launch_pack_bits(const uint32_t* bits, int n, int words, uint8_t* qb, uint8_t* tb, int32_t* popc,
+                             cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  pack_bits_kernel<<<(n + 7) / 8, 256, 0, st>>>(bits, n, words, qb, tb, popc);
+  return cudaGetLastError();
+}
+
 __global__ void u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, size_t n) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = static_cast<float>(src[i]);

@@ -557,3 +557,80 @@ def test_float_tensor_full_size_superpoint():
     for r in np.nonzero((knn_rows[0][0] != oi).any(axis=1))[0]:
         assert abs(o2[r, 1] - o2[r, 0]) <= 1e-6 * o2[r, 1]
     assert outs[0]["offsets"][-1] > 6 * 1500
+
+
+# ---------------------------------------------------------------------------------------------
+# binary descriptors on the tensor cores (E4M3 {0,1} operands, exact) vs the XOR/popc kernel and the oracle
+# ---------------------------------------------------------------------------------------------
+FORCE_POPC = 1 << 10
+
+
+@pytest.mark.parametrize("mode", [api.UNIQUE_FIRST_WINS, api.MUTUAL_NN, api.UNIQUE_NONE])
+def test_hamming_tensor_batched_equals_popc_and_oracle(mode):
+    w = synth.World("orb", 1000, seed=55)
+    imgs = []
+    for i in range(5):
+        d, xy, _ = w.image(i, 5, outlier_frac=0.2)
+        cut = 1000 - 71 * i
+        d = d[:cut].copy(); xy = xy[:cut]
+        if i == 1:                       # exact duplicates inside one 16-column chunk and across chunks
+            d[40] = d[7]; d[300] = d[7]; d[301] = d[7]
+        if i == 2:
+            d[5] = 0; d[6] = 255         # all-zero / all-one rows (|b| = 0 and 256)
+        imgs.append((d, xy))
+    outs = []
+    for flags in (0, FORCE_POPC):
+        with api.PairMatcher(unique_mode=mode, batch_pairs=3, debug_flags=flags) as pm:
+            for i, (d, xy) in enumerate(imgs):
+                pm.set_image(i, d, xy)
+            outs.append(pm.match_all_pairs())
+    for k in ("offsets", "q", "t", "inlier", "status", "n_inliers", "ransac_iters", "F"):
+        assert np.array_equal(outs[0][k], outs[1][k]), (mode, k)
+    res = outs[0]
+    for p, (i, j) in enumerate(res["pair_ij"]):
+        ref = orc.match_pair(imgs[i][0], imgs[i][1], imgs[j][0], imgs[j][1], unique_mode=mode)
+        a, b = res["offsets"][p], res["offsets"][p + 1]
+        assert b - a == ref["n_putative"], (mode, p, b - a, ref["n_putative"])
+        keep = res["inlier"][a:b].astype(bool)
+        assert np.array_equal(res["q"][a:b][keep], ref["q"]) and np.array_equal(res["t"][a:b][keep], ref["t"]), (mode, p)
+
+
+def test_hamming_tensor_512_bit_and_ragged():
+    rng = np.random.default_rng(12)
+    base = rng.integers(0, 256, (1500, 64), dtype=np.uint8)
+    imgs = []
+    for i, n in enumerate((700, 513, 129, 17, 1)):
+        ids = rng.permutation(1500)[:n]
+        d = base[ids].copy()
+        flip = rng.random((n, 64)) < 0.04
+        d ^= (flip * rng.integers(1, 256, (n, 64))).astype(np.uint8)
+        imgs.append(d)
+    outs = []
+    for flags in (0, FORCE_POPC):
+        with api.PairMatcher(debug_flags=flags, do_filter=0, batch_pairs=4) as pm:
+            for i, d in enumerate(imgs):
+                pm.set_image(i, d)
+            outs.append(pm.match_all_pairs())
+    for k in ("offsets", "q", "t", "status"):
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+    res = outs[0]
+    for p, (i, j) in enumerate(res["pair_ij"]):
+        oi, od = orc.knn2_hamming(imgs[i], imgs[j])
+        wq, wt = orc.ratio_unique(oi, od.astype(np.float32), imgs[j].shape[0])
+        a, b = res["offsets"][p], res["offsets"][p + 1]
+        assert np.array_equal(res["q"][a:b], wq) and np.array_equal(res["t"][a:b], wt), (i, j)
+    assert res["offsets"][-1] > 300
+
+
+def test_hamming_tensor_full_size_equals_popc():
+    w = synth.World("orb", 8192, seed=0xB200 + 3)
+    imgs = [w.image(i, 100, outlier_frac=0.3 if i == 2 else 0.0)[:2] for i in range(5)]
+    outs = []
+    for flags in (0, FORCE_POPC):
+        with api.PairMatcher(debug_flags=flags) as pm:
+            for i, (d, xy) in enumerate(imgs):
+                pm.set_image(i, d, xy)
+            outs.append(pm.match_all_pairs())
+    for k in ("offsets", "q", "t", "inlier", "status", "n_inliers", "ransac_iters", "F"):
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+    assert outs[0]["offsets"][-1] > 10 * 1500
