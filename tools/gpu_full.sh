@@ -14,5 +14,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 echo "ncu launches exit $?"
 CMD2="python bench.py --images 23 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e"
 $CMD2 > gpurun_out/plain_full.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:l2_top2_tc2 -s 1 -c 1 -o gpurun_out/prof_tc2 $CMD2 > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:l2_top2_tc2 -s 1 -c 1 -f -o gpurun_out/prof_tc2 $CMD2 > gpurun_out/ncu_full.log 2>&1
 echo "ncu full exit $?"; tail -2 gpurun_out/ncu_full.log
