@@ -185,6 +185,19 @@ int pm_match_filter_pair(pm_handle h, int img_i, int img_j, pm_pair_result* out)
 int pm_match_all_pairs(pm_handle h, const int32_t* pairs, int64_t n_pairs, pm_csr_result** out);
 int pm_free_result(pm_csr_result* r);
 
+/* On-disk cache (the reference's README lists "save intermediate steps" as a todo).
+ * One little-endian container format (layout: reconstructor_b200/cache.py) with a checksum; a file that
+ * fails magic / version / size / checksum validation is rejected with PM_ERR_INVALID.
+ *   pm_save_images / pm_load_images  every ingested image of the handle (descriptors as ingested + xy):
+ *                                    resume without re-running extraction, or ship sharded extraction.
+ *   pm_save_result / pm_load_result  a CSR result (featureMatches, SequentialReconstructor.h:226, in flat
+ *                                    form); loading needs no device.  Free with pm_free_result.
+ * Errors of the two handle-less calls are reported through pm_last_error(NULL). */
+int pm_save_images(pm_handle h, const char* path);
+int pm_load_images(pm_handle h, const char* path);
+int pm_save_result(const pm_csr_result* r, const char* path);
+int pm_load_result(const char* path, pm_csr_result** out);
+
 int pm_get_stats(pm_handle h, pm_stats* out);
 int pm_reset_stats(pm_handle h);
 

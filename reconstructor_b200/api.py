@@ -32,6 +32,7 @@ EXPORTS = [
     "pm_set_image_device", "pm_num_keypoints", "pm_knn_pair", "pm_match_pair",
     "pm_match_descriptors", "pm_filter_pair_F", "pm_match_filter_pair", "pm_match_all_pairs",
     "pm_free_result", "pm_get_stats", "pm_reset_stats", "pm_measure_popc_peak",
+    "pm_save_images", "pm_load_images", "pm_save_result", "pm_load_result",
 ]
 
 
@@ -107,6 +108,10 @@ def load_library() -> C.CDLL:
         lib.pm_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         lib.pm_reset_stats.argtypes = [C.c_void_p]
         lib.pm_measure_popc_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        lib.pm_save_images.argtypes = [C.c_void_p, C.c_char_p]
+        lib.pm_load_images.argtypes = [C.c_void_p, C.c_char_p]
+        lib.pm_save_result.argtypes = [C.POINTER(CsrResult), C.c_char_p]
+        lib.pm_load_result.argtypes = [C.c_char_p, C.POINTER(C.POINTER(CsrResult))]
         _lib = lib
     return _lib
 
@@ -242,38 +247,29 @@ class PairMatcher:
         return F.reshape(3, 3), mask[:m], st.value, it.value
 
     # -- batched loop ----------------------------------------------------------------------------
-    def match_all_pairs(self, pairs: np.ndarray | None = None, copy=True):
+    def match_all_pairs(self, pairs: np.ndarray | None = None, copy=True, save_to: str | None = None):
         """Whole pair loop.  Returns dict of numpy arrays (CSR): pair_ij, offsets, q, t, inlier, F,
-        status, n_inliers, ransac_iters, device_ms."""
+        status, n_inliers, ransac_iters, device_ms.  save_to: also write the result cache file."""
         res = C.POINTER(CsrResult)()
         if pairs is None:
             self._check(self.lib.pm_match_all_pairs(self.h, None, 0, C.byref(res)))
         else:
             pairs = np.ascontiguousarray(pairs, np.int32)
             self._check(self.lib.pm_match_all_pairs(self.h, pairs.ctypes.data, pairs.shape[0], C.byref(res)))
-        r = res.contents
-        n = r.n_pairs
+        if save_to is not None:
+            self._check(self.lib.pm_save_result(res, os.fsencode(save_to)))
+        return _csr_to_dict(self.lib, res, copy)
 
-        def arr(ptr, count, dt):
-            if count == 0:
-                return np.empty(0, dt)
-            a = np.ctypeslib.as_array(ptr, shape=(count,))
-            return a.copy() if copy else a
-        out = dict(n_pairs=n, device_ms=r.device_ms)
-        out["offsets"] = arr(r.offsets, n + 1, np.int64)
-        total = int(out["offsets"][n]) if n >= 0 else 0
-        out["pair_ij"] = arr(r.pair_ij, 2 * n, np.int32).reshape(-1, 2)
-        out["q"] = arr(r.q, total, np.int32); out["t"] = arr(r.t, total, np.int32)
-        out["inlier"] = arr(r.inlier, total, np.uint8)
-        out["F"] = arr(r.F, 9 * n, np.float64).reshape(-1, 3, 3)
-        out["status"] = arr(r.status, n, np.int32)
-        out["n_inliers"] = arr(r.n_inliers, n, np.int32)
-        out["ransac_iters"] = arr(r.ransac_iters, n, np.int32)
-        if copy:
-            self.lib.pm_free_result(res)
-        else:
-            out["_handle"] = res
-        return out
+    # -- on-disk cache ---------------------------------------------------------------------------
+    def save_images(self, path: str):
+        self._check(self.lib.pm_save_images(self.h, os.fsencode(path)))
+
+    def load_images(self, path: str):
+        """Ingests every image of a cache file (pm_save_images or cache.write_images)."""
+        self._check(self.lib.pm_load_images(self.h, os.fsencode(path)))
+        from . import cache
+        for rec in cache.read_images(path, headers_only=True):
+            self._n[rec["id"]] = rec["n"]
 
     def free_result(self, out):
         if "_handle" in out:
@@ -291,6 +287,42 @@ class PairMatcher:
         v = C.c_double(0)
         self._check(self.lib.pm_measure_popc_peak(self.h, C.byref(v)))
         return v.value
+
+
+def _csr_to_dict(lib, res, copy=True) -> dict:
+    r = res.contents
+    n = r.n_pairs
+
+    def arr(ptr, count, dt):
+        if count == 0:
+            return np.empty(0, dt)
+        a = np.ctypeslib.as_array(ptr, shape=(count,))
+        return a.copy() if copy else a
+    out = dict(n_pairs=n, device_ms=r.device_ms)
+    out["offsets"] = arr(r.offsets, n + 1, np.int64)
+    total = int(out["offsets"][n]) if n >= 0 else 0
+    out["pair_ij"] = arr(r.pair_ij, 2 * n, np.int32).reshape(-1, 2)
+    out["q"] = arr(r.q, total, np.int32); out["t"] = arr(r.t, total, np.int32)
+    out["inlier"] = arr(r.inlier, total, np.uint8)
+    out["F"] = arr(r.F, 9 * n, np.float64).reshape(-1, 3, 3)
+    out["status"] = arr(r.status, n, np.int32)
+    out["n_inliers"] = arr(r.n_inliers, n, np.int32)
+    out["ransac_iters"] = arr(r.ransac_iters, n, np.int32)
+    if copy:
+        lib.pm_free_result(res)
+    else:
+        out["_handle"] = res
+    return out
+
+
+def load_result(path: str) -> dict:
+    """Reads a result cache file through the C ABI (no device needed)."""
+    lib = load_library()
+    res = C.POINTER(CsrResult)()
+    rc = lib.pm_load_result(os.fsencode(path), C.byref(res))
+    if rc != 0:
+        raise PairMatchError(rc, lib.pm_last_error(None).decode())
+    return _csr_to_dict(lib, res, True)
 
 
 def feature_matches_view(res: dict, mirror=True) -> dict:

@@ -6,6 +6,7 @@
 #pragma once
 
 #include <algorithm>
+#include <string>
 #include <unordered_map>
 #include <vector>
 
@@ -59,15 +60,22 @@ class ExhaustivePairMatcher {
       }
     }
     last_device_ms_ = res->device_ms;
+    int src = PM_OK;
+    if (!result_cache_.empty()) src = pm_save_result(res, result_cache_.c_str());   // "save intermediate steps", README.md:39
     pm_free_result(res);
-    return PM_OK;
+    return src;
   }
+  // Optional on-disk cache of the match result (written after every matchFeatures call) and of the ingested images.
+  void setResultCache(std::string path) { result_cache_ = std::move(path); }
+  int saveImages(const std::string& path) { return pm_save_images(dev_->handle(), path.c_str()); }
+  int loadImages(const std::string& path) { return pm_load_images(dev_->handle(), path.c_str()); }
   double lastDeviceMs() const { return last_device_ms_; }
   const std::shared_ptr<PairMatchDevice>& device() const { return dev_; }
 
  private:
   std::shared_ptr<PairMatchDevice> dev_;
   double last_device_ms_ = 0;
+  std::string result_cache_;
 };
 
 }  // namespace reconstructor::Core

@@ -84,6 +84,8 @@ struct Result {  // owner of a pm_csr_result
   uint8_t* inlier = nullptr;
   size_t q_bytes = 0, t_bytes = 0, inl_bytes = 0;
   int64_t cap = 0, size = 0;
+  std::vector<int32_t> vq, vt;      // results loaded from a cache file live in plain host memory
+  std::vector<uint8_t> vin;
 
   bool reserve(int64_t want) {      // caller guarantees no copy into the old buffers is in flight
     if (want <= cap) return true;
@@ -1225,3 +1227,256 @@ int pm_measure_popc_peak(pm_handle h, double* popc32_per_s) {
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// On-disk cache (the reference's README lists "save intermediate steps" as a todo):
+// one little-endian container for (a) the ingested images of a handle and (b) a CSR match result.
+//   header  : magic "PMB200\0\1", u32 version, u32 kind (1 images, 2 result), u64 count, u64 payload bytes,
+//             u64 checksum of the payload (s1 ^ rotl(s2, 32), s1 = sum of u64 words, s2 = sum of (i+1)*word)
+//   payload : 8-byte aligned sections (layout in reconstructor_b200/cache.py, the host-side mirror)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct CacheHeader {
+  char magic[8];
+  uint32_t version, kind;
+  uint64_t count, payload_bytes, checksum;
+};
+static_assert(sizeof(CacheHeader) == 40, "CacheHeader layout");
+const char kCacheMagic[8] = {'P', 'M', 'B', '2', '0', '0', '\0', '\1'};
+
+struct Checksum {
+  uint64_t s1 = 0, s2 = 0, i = 0;
+  void add(const void* p, size_t bytes) {          // bytes % 8 == 0
+    const uint64_t* w = static_cast<const uint64_t*>(p);
+    for (size_t k = 0; k < bytes / 8; ++k) { uint64_t v; std::memcpy(&v, w + k, 8); s1 += v; s2 += (++i) * v; }
+  }
+  uint64_t value() const { return s1 ^ ((s2 << 32) | (s2 >> 32)); }
+};
+
+struct CacheWriter {
+  FILE* f = nullptr;
+  Checksum ck;
+  uint64_t bytes = 0;
+  bool ok = true;
+  bool open(const char* path) {
+    f = std::fopen(path, "wb");
+    if (!f) return false;
+    CacheHeader h{};
+    ok = std::fwrite(&h, sizeof h, 1, f) == 1;    // placeholder, rewritten by finish()
+    return ok;
+  }
+  void section(const void* p, size_t n) {          // pads to 8 bytes
+    if (!ok) return;
+    const size_t whole = n / 8 * 8;
+    if (whole) { ok = std::fwrite(p, 1, whole, f) == whole; ck.add(p, whole); }
+    if (ok && n > whole) {
+      unsigned char tail[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      std::memcpy(tail, static_cast<const unsigned char*>(p) + whole, n - whole);
+      ok = std::fwrite(tail, 1, 8, f) == 8;
+      ck.add(tail, 8);
+    }
+    bytes += (n + 7) / 8 * 8;
+  }
+  bool finish(uint32_t kind, uint64_t count) {
+    if (f && ok) {
+      CacheHeader h{};
+      std::memcpy(h.magic, kCacheMagic, 8);
+      h.version = 1; h.kind = kind; h.count = count; h.payload_bytes = bytes; h.checksum = ck.value();
+      ok = std::fseek(f, 0, SEEK_SET) == 0 && std::fwrite(&h, sizeof h, 1, f) == 1;
+    }
+    if (f) ok = (std::fclose(f) == 0) && ok;
+    f = nullptr;
+    return ok;
+  }
+};
+
+// Reads and verifies a whole cache file.  Returns PM_OK or an error code with g_create_error set.
+int read_cache(const char* path, uint32_t kind, CacheHeader* hdr, std::vector<unsigned char>* payload) {
+  FILE* f = std::fopen(path, "rb");
+  if (!f) { g_create_error = std::string("cannot open ") + path; return PM_ERR_INVALID; }
+  CacheHeader h{};
+  bool ok = std::fread(&h, sizeof h, 1, f) == 1 && std::memcmp(h.magic, kCacheMagic, 8) == 0 && h.version == 1 &&
+            h.kind == kind && h.payload_bytes % 8 == 0;
+  if (ok) {
+    try { payload->resize(h.payload_bytes); } catch (...) { std::fclose(f); g_create_error = "cache file too large"; return PM_ERR_OOM; }
+    ok = h.payload_bytes == 0 || std::fread(payload->data(), 1, h.payload_bytes, f) == h.payload_bytes;
+    unsigned char extra;
+    ok = ok && std::fread(&extra, 1, 1, f) == 0;   // nothing may follow the payload
+  }
+  std::fclose(f);
+  if (ok) {
+    Checksum ck;
+    ck.add(payload->data(), payload->size());
+    ok = ck.value() == h.checksum;
+  }
+  if (!ok) { g_create_error = std::string(path) + ": not a valid pairmatch_b200 cache file of the requested kind (magic / version / size / checksum)"; return PM_ERR_INVALID; }
+  *hdr = h;
+  return PM_OK;
+}
+
+struct Cursor {
+  const unsigned char* p;
+  size_t left;
+  bool take(void* dst, size_t n) {
+    const size_t padded = (n + 7) / 8 * 8;
+    if (padded > left) return false;
+    if (n) std::memcpy(dst, p, n);
+    p += padded; left -= padded;
+    return true;
+  }
+  const unsigned char* view(size_t n) {
+    const size_t padded = (n + 7) / 8 * 8;
+    if (padded > left) return nullptr;
+    const unsigned char* r = p;
+    p += padded; left -= padded;
+    return r;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+int pm_save_result(const pm_csr_result* r, const char* path) {
+  if (!r || !path || r->n_pairs < 0) { g_create_error = "pm_save_result: bad arguments"; return PM_ERR_INVALID; }
+  CacheWriter w;
+  if (!w.open(path)) { g_create_error = std::string("cannot create ") + path; return PM_ERR_INVALID; }
+  const int64_t np = r->n_pairs, nm = np > 0 ? r->offsets[np] : 0;
+  const int64_t head[4] = {np, nm, 0, 0};
+  w.section(head, sizeof head);
+  w.section(&r->device_ms, 8);
+  w.section(r->pair_ij, 8 * static_cast<size_t>(np));
+  const int64_t zero = 0;
+  w.section(np > 0 ? r->offsets : &zero, 8 * static_cast<size_t>(np + 1));
+  w.section(r->q, 4 * static_cast<size_t>(nm));
+  w.section(r->t, 4 * static_cast<size_t>(nm));
+  w.section(r->inlier, static_cast<size_t>(nm));
+  w.section(r->F, 72 * static_cast<size_t>(np));
+  w.section(r->status, 4 * static_cast<size_t>(np));
+  w.section(r->n_inliers, 4 * static_cast<size_t>(np));
+  w.section(r->ransac_iters, 4 * static_cast<size_t>(np));
+  if (!w.finish(2, static_cast<uint64_t>(np))) { g_create_error = std::string("write error on ") + path; return PM_ERR_INVALID; }
+  return PM_OK;
+}
+
+int pm_load_result(const char* path, pm_csr_result** out) {
+  if (!path || !out) { g_create_error = "pm_load_result: bad arguments"; return PM_ERR_INVALID; }
+  *out = nullptr;
+  CacheHeader h{};
+  std::vector<unsigned char> buf;
+  const int rc = read_cache(path, 2, &h, &buf);
+  if (rc != PM_OK) return rc;
+  Cursor c{buf.data(), buf.size()};
+  int64_t head[4];
+  double ms = 0;
+  bool ok = c.take(head, sizeof head) && c.take(&ms, 8);
+  const int64_t np = ok ? head[0] : 0, nm = ok ? head[1] : 0;
+  ok = ok && np >= 0 && nm >= 0 && static_cast<uint64_t>(np) == h.count;
+  auto R = std::make_unique<Result>();
+  if (ok) {
+    try {
+      R->pair_ij.resize(2 * np); R->offsets.resize(np + 1); R->vq.resize(nm); R->vt.resize(nm); R->vin.resize(nm);
+      R->F.resize(9 * np); R->status.resize(np); R->n_inliers.resize(np); R->iters.resize(np);
+    } catch (...) { g_create_error = "pm_load_result: out of memory"; return PM_ERR_OOM; }
+    ok = c.take(R->pair_ij.data(), 8 * static_cast<size_t>(np)) && c.take(R->offsets.data(), 8 * static_cast<size_t>(np + 1)) &&
+         c.take(R->vq.data(), 4 * static_cast<size_t>(nm)) && c.take(R->vt.data(), 4 * static_cast<size_t>(nm)) &&
+         c.take(R->vin.data(), static_cast<size_t>(nm)) && c.take(R->F.data(), 72 * static_cast<size_t>(np)) &&
+         c.take(R->status.data(), 4 * static_cast<size_t>(np)) && c.take(R->n_inliers.data(), 4 * static_cast<size_t>(np)) &&
+         c.take(R->iters.data(), 4 * static_cast<size_t>(np)) && c.left == 0;
+    ok = ok && R->offsets[0] == 0 && R->offsets[np] == nm;
+    for (int64_t p = 0; ok && p < np; ++p) ok = R->offsets[p] <= R->offsets[p + 1];
+  }
+  if (!ok) { g_create_error = std::string(path) + ": malformed result sections"; return PM_ERR_INVALID; }
+  R->size = nm;
+  R->pub.n_pairs = np;
+  R->pub.pair_ij = R->pair_ij.data(); R->pub.offsets = R->offsets.data();
+  R->pub.q = R->vq.data(); R->pub.t = R->vt.data(); R->pub.inlier = R->vin.data();
+  R->pub.F = R->F.data(); R->pub.status = R->status.data();
+  R->pub.n_inliers = R->n_inliers.data(); R->pub.ransac_iters = R->iters.data();
+  R->pub.device_ms = ms;
+  R->pub.owner_ = R.get();
+  *out = &R.release()->pub;
+  return PM_OK;
+}
+
+int pm_save_images(pm_handle h, const char* path) {
+  if (!h || !path) return PM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceCtx& d = *h->devs[0];
+  if (cudaSetDevice(d.dev) != cudaSuccess) return h->from(d, d.fail(PM_ERR_CUDA, "cudaSetDevice failed"));
+  std::vector<int> ids;
+  for (auto& kv : d.images)
+    if (kv.first != kTmpA && kv.first != kTmpB) ids.push_back(kv.first);
+  std::sort(ids.begin(), ids.end());
+  CacheWriter w;
+  if (!w.open(path)) return h->fail(PM_ERR_INVALID, std::string("cannot create ") + path);
+  std::vector<unsigned char> host;
+  std::vector<float> frow;
+  for (int id : ids) {
+    const Image& im = d.images[id];
+    const int32_t rec[6] = {id, im.n, d.dim, d.dtype, im.has_xy ? 1 : 0, 0};
+    w.section(rec, sizeof rec);
+    size_t bytes = 0;
+    cudaError_t e = cudaSuccess;
+    if (d.dtype == PM_DESC_U8_BITS) {
+      bytes = static_cast<size_t>(im.n) * d.words * 4;
+      host.resize(bytes);
+      if (bytes) e = cudaMemcpy(host.data(), d.bits + static_cast<size_t>(im.row) * d.words, bytes, cudaMemcpyDeviceToHost);
+    } else {
+      const size_t elems = static_cast<size_t>(im.n) * d.dim;
+      frow.resize(elems);
+      if (elems) e = cudaMemcpy(frow.data(), d.raw + static_cast<size_t>(im.row) * d.dim, elems * 4, cudaMemcpyDeviceToHost);
+      if (d.dtype == PM_DESC_U8) {                   // the arena keeps the byte values as floats
+        bytes = elems;
+        host.resize(bytes);
+        for (size_t k = 0; k < elems; ++k) host[k] = static_cast<unsigned char>(frow[k]);
+      } else {
+        bytes = elems * 4;
+        host.resize(bytes);
+        if (bytes) std::memcpy(host.data(), frow.data(), bytes);
+      }
+    }
+    if (e != cudaSuccess) { w.finish(1, 0); return h->from(d, d.fail_cuda(e, "pm_save_images D2H", __LINE__)); }
+    w.section(host.data(), bytes);
+    if (im.has_xy) {
+      host.resize(static_cast<size_t>(im.n) * 8);
+      if (im.n && (e = cudaMemcpy(host.data(), d.xy + 2 * static_cast<size_t>(im.row), host.size(), cudaMemcpyDeviceToHost)) != cudaSuccess) {
+        w.finish(1, 0);
+        return h->from(d, d.fail_cuda(e, "pm_save_images D2H", __LINE__));
+      }
+      w.section(host.data(), host.size());
+    }
+  }
+  if (!w.finish(1, ids.size())) return h->fail(PM_ERR_INVALID, std::string("write error on ") + path);
+  return PM_OK;
+}
+
+int pm_load_images(pm_handle h, const char* path) {
+  if (!h || !path) return PM_ERR_INVALID;
+  CacheHeader hdr{};
+  std::vector<unsigned char> buf;
+  int rc = read_cache(path, 1, &hdr, &buf);
+  if (rc != PM_OK) return h->fail(rc, g_create_error);
+  std::lock_guard<std::mutex> lk(h->mu);
+  Cursor c{buf.data(), buf.size()};
+  for (uint64_t k = 0; k < hdr.count; ++k) {
+    int32_t rec[6];
+    if (!c.take(rec, sizeof rec) || rec[1] < 0 || rec[2] <= 0) return h->fail(PM_ERR_INVALID, std::string(path) + ": malformed image record");
+    const size_t n = static_cast<size_t>(rec[1]);
+    const size_t bytes = rec[3] == PM_DESC_U8_BITS ? n * (rec[2] / 8) : (rec[3] == PM_DESC_U8 ? n * rec[2] : n * rec[2] * 4);
+    const unsigned char* desc = c.view(bytes);
+    const unsigned char* xy = rec[4] ? c.view(n * 8) : nullptr;
+    if (!desc || (rec[4] && !xy)) return h->fail(PM_ERR_INVALID, std::string(path) + ": truncated image record");
+    if (rec[0] == kTmpA || rec[0] == kTmpB) return h->fail(PM_ERR_INVALID, "reserved image id in cache file");
+    for (auto& d : h->devs) {
+      rc = d->set_image(rec[0], desc, rec[1], rec[2], rec[3], reinterpret_cast<const int32_t*>(xy), false);
+      if (rc != PM_OK) return h->from(*d, rc);
+    }
+  }
+  if (c.left != 0) return h->fail(PM_ERR_INVALID, std::string(path) + ": trailing bytes after the last image");
+  return PM_OK;
+}
+
+}  // extern "C"
+

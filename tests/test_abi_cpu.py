@@ -141,3 +141,81 @@ def test_two_rank_gloo_partition(tmp_path):
                        capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "GLOO_OK 2" in r.stdout
+
+
+# ---------------------------------------------------------------------------------------------
+# on-disk cache: the C ABI reader/writer against the numpy mirror (no device needed for results)
+# ---------------------------------------------------------------------------------------------
+def _fake_result(rng, n_pairs=7):
+    counts = rng.integers(0, 40, n_pairs)
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    m = int(off[-1])
+    return dict(n_pairs=n_pairs, device_ms=12.5, pair_ij=rng.integers(0, 9, (n_pairs, 2)).astype(np.int32), offsets=off,
+                q=rng.integers(0, 8192, m).astype(np.int32), t=rng.integers(0, 8192, m).astype(np.int32),
+                inlier=rng.integers(0, 2, m).astype(np.uint8), F=rng.standard_normal((n_pairs, 3, 3)),
+                status=rng.integers(0, 3, n_pairs).astype(np.int32), n_inliers=counts.astype(np.int32),
+                ransac_iters=rng.integers(0, 1000, n_pairs).astype(np.int32))
+
+
+def test_result_cache_roundtrip_c_abi_vs_numpy_mirror(tmp_path):
+    import ctypes as C
+
+    from reconstructor_b200 import api, cache
+    rng = np.random.default_rng(3)
+    for n_pairs in (7, 1, 0):
+        want = _fake_result(rng, n_pairs)
+        a, b = str(tmp_path / f"a{n_pairs}.pmb"), str(tmp_path / f"b{n_pairs}.pmb")
+        cache.write_result(a, want)                         # numpy writer -> C reader
+        got = api.load_result(a)
+        for k in ("pair_ij", "offsets", "q", "t", "inlier", "F", "status", "n_inliers", "ransac_iters"):
+            assert np.array_equal(got[k], want[k]), (n_pairs, k)
+        assert got["n_pairs"] == n_pairs and got["device_ms"] == 12.5
+        lib = api.load_library()                            # C reader -> C writer: byte-identical file
+        res = C.POINTER(api.CsrResult)()
+        assert lib.pm_load_result(a.encode(), C.byref(res)) == 0
+        assert lib.pm_save_result(res, b.encode()) == 0
+        lib.pm_free_result(res)
+        assert open(a, "rb").read() == open(b, "rb").read()
+        back = cache.read_result(b)                         # C writer -> numpy reader
+        assert np.array_equal(back["q"], want["q"]) and np.array_equal(back["F"], want["F"])
+
+
+def test_cache_rejects_corrupt_files(tmp_path):
+    from reconstructor_b200 import api, cache
+    rng = np.random.default_rng(4)
+    p = str(tmp_path / "r.pmb")
+    cache.write_result(p, _fake_result(rng))
+    raw = bytearray(open(p, "rb").read())
+    for mutate in ("flip", "truncate", "magic", "kind"):
+        bad = bytearray(raw)
+        if mutate == "flip":
+            bad[len(bad) // 2] ^= 0x10
+        elif mutate == "truncate":
+            bad = bad[:-8]
+        elif mutate == "magic":
+            bad[0] = ord("X")
+        else:
+            bad[12] = 1                                     # claims to be an image file
+        q = str(tmp_path / f"bad_{mutate}.pmb")
+        open(q, "wb").write(bytes(bad))
+        with pytest.raises(api.PairMatchError) as e:
+            api.load_result(q)
+        assert e.value.code == api.ERR_INVALID
+        with pytest.raises(ValueError):
+            cache.read_result(q)
+    with pytest.raises(api.PairMatchError):
+        api.load_result(str(tmp_path / "missing.pmb"))
+
+
+def test_image_cache_numpy_roundtrip(tmp_path):
+    from reconstructor_b200 import cache, synth
+    imgs = {}
+    for kind, i in (("orb", 3), ("orb", 1)):
+        d, xy = synth.make_set(kind, 1, 50 + i, seed=i)[0]
+        imgs[i] = (d, xy if i == 3 else None)
+    p = str(tmp_path / "img.pmb")
+    cache.write_images(p, imgs)
+    back = cache.read_images(p)
+    assert [r["id"] for r in back] == [1, 3] and back[0]["xy"] is None
+    assert np.array_equal(back[1]["desc"], imgs[3][0]) and np.array_equal(back[1]["xy"], imgs[3][1])
+    assert back[1]["dim"] == 256 and back[1]["dtype"] == cache.DESC_U8_BITS

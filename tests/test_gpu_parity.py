@@ -634,3 +634,43 @@ def test_hamming_tensor_full_size_equals_popc():
     for k in ("offsets", "q", "t", "inlier", "status", "n_inliers", "ransac_iters", "F"):
         assert np.array_equal(outs[0][k], outs[1][k]), k
     assert outs[0]["offsets"][-1] > 10 * 1500
+
+
+# ---------------------------------------------------------------------------------------------
+# on-disk cache: resume from files, identical results
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["orb", "sift", "sift-u8", "superpoint"])
+def test_cache_resume_gives_identical_results(kind, tmp_path):
+    from reconstructor_b200 import cache
+    base = kind.split("-")[0]
+    dt = api.DESC_U8 if kind == "sift-u8" else None
+    imgs = synth.make_set(base, 4, 500, seed=17)
+    if kind == "sift-u8":
+        imgs = [(d.astype(np.uint8), xy) for d, xy in imgs]
+    img_file, res_file = str(tmp_path / "images.pmb"), str(tmp_path / "result.pmb")
+    with api.PairMatcher() as pm:
+        for i, (d, xy) in enumerate(imgs):
+            pm.set_image(10 * i, d, xy if i != 2 else None, dtype=dt)       # sparse ids, one image without xy
+        first = pm.match_all_pairs(save_to=res_file)
+        pm.save_images(img_file)
+    # the file written by the library is readable by the numpy mirror and holds exactly what was ingested
+    recs = cache.read_images(img_file)
+    assert [r["id"] for r in recs] == [0, 10, 20, 30] and recs[2]["xy"] is None
+    for r, (d, xy) in zip(recs, imgs):
+        assert np.array_equal(r["desc"], d) and (r["xy"] is None or np.array_equal(r["xy"], xy))
+    # resume: fresh handle, images from the cache file
+    with api.PairMatcher() as pm:
+        pm.load_images(img_file)
+        again = pm.match_all_pairs()
+    saved = api.load_result(res_file)
+    for k in ("pair_ij", "offsets", "q", "t", "inlier", "F", "status", "n_inliers", "ransac_iters"):
+        assert np.array_equal(first[k], again[k]), (kind, k)
+        assert np.array_equal(first[k], saved[k]), (kind, k)
+    assert first["offsets"][-1] > 100
+    # a file produced WITHOUT the library (sharded extraction on another machine) ingests the same way
+    alt = str(tmp_path / "alt.pmb")
+    cache.write_images(alt, {10 * i: (d, xy if i != 2 else None) for i, (d, xy) in enumerate(imgs)}, dtype=dt)
+    with api.PairMatcher() as pm:
+        pm.load_images(alt)
+        third = pm.match_all_pairs()
+    assert np.array_equal(first["q"], third["q"]) and np.array_equal(first["t"], third["t"])
