@@ -49,6 +49,10 @@ def parse():
     ap.add_argument("--outlier-frac", type=float, default=0.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-stages", action="store_true", help="skip the matcher-only / RANSAC attribution pass")
+    ap.add_argument("--sharded-ingest", action="store_true",
+                    help="N>1: every rank owns images k = rank mod N, descriptors are all-gathered over NCCL and "
+                         "ingested from device memory (the exchange step of sharded extraction, SURVEY 8e)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--debug-flags", type=int, default=0, help="pm_params.debug_flags (kernel variants)")
     ap.add_argument("--batch-pairs", type=int, default=0)
@@ -110,7 +114,7 @@ def flann_samples(imgs, sample_pairs):
     return dict(zip(sample_pairs, out))
 
 
-def cpu_arm(imgs, pairs, seconds, steps=1, warmup=0, pairs_per_step=None):
+def cpu_arm(imgs, pairs, seconds, steps=1, warmup=0, pairs_per_step=None, workers=None):
     """Returns dict(value pairs/s, cores, kind, sample, ms_per_step)."""
     import multiprocessing as mp
     global _CPU_IMGS
@@ -119,7 +123,8 @@ def cpu_arm(imgs, pairs, seconds, steps=1, warmup=0, pairs_per_step=None):
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     use_cv2 = cv2_ref.have_cv2()
     fn = _cpu_pair if use_cv2 else _c_oracle_pair
-    workers = cores if use_cv2 else 1              # the C oracle is already OpenMP-parallel inside
+    if workers is None or not use_cv2:
+        workers = cores if use_cv2 else 1          # the C oracle is already OpenMP-parallel inside
     rng = np.random.default_rng(1)
     n_step = pairs_per_step or max(2 * workers, 16)
     ctx = mp.get_context("fork")
@@ -225,12 +230,18 @@ def main():
     # ---- CPU baseline first (fork before any CUDA context exists), rank 0 at N=1 only -----------
     cpu = None
     w = synth.World(a.kind, a.kp, seed=0xB200 + 2)
-    imgs = [w.image(i, n_img, a.outlier_frac)[:2] for i in range(n_img)]
+    sharded = a.sharded_ingest and world > 1
+    n_local = -(-n_img // world)                       # images per rank when extraction is sharded
+    own_ids = list(range(rank, n_local * world, world)) if sharded else list(range(n_img))
+    imgs = [w.image(i, n_img, a.outlier_frac)[:2] for i in own_ids]
     if n_gpus == 1 and rank == 0 and not a.no_cpu_baseline:
         sub_ids = list(range(min(n_img, 24)))
         sub = np.array([(i, j) for x, i in enumerate(sub_ids) for j in sub_ids[x + 1:]], np.int32)
         r = cpu_arm({i: imgs[i] for i in sub_ids}, sub, a.cpu_seconds)
         cpu = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=r["sample"])
+        if r["cores"] > 4:      # the reference's own thread cap (MAX_NUM_THREADS 4, SequentialReconstructor.h:17)
+            r4 = cpu_arm({i: imgs[i] for i in sub_ids}, sub, min(a.cpu_seconds, 6.0), workers=4)
+            cpu["at_4_workers"] = dict(value=r4["value"], unit=UNIT, cores=4, sample=r4["sample"])
         flann = flann_samples({i: imgs[i] for i in sub_ids}, [tuple(int(x) for x in sub[k]) for k in (0, 1, len(sub) // 2, len(sub) - 1)][:len(sub)])
     else:
         flann = None
@@ -278,9 +289,29 @@ def main():
     pm = api.PairMatcher(devices=[local], reserve_keypoints=n_img * a.kp, debug_flags=a.debug_flags,
                          batch_pairs=a.batch_pairs)
 
+    if sharded:
+        # sharded extraction: this rank "extracted" images rank, rank + N, ...; descriptors and keypoints are
+        # all-gathered over NCCL (equal counts per image) and ingested from device memory
+        d_own = torch.stack([td for td, _ in pinned]).pin_memory()
+        x_own = torch.stack([tx for _, tx in pinned]).pin_memory()
+        cfg["partition"] += "; extraction sharded by image id mod N, one NCCL all-gather of descriptors + keypoints per step"
+
     def ingest():
-        for i, (td, tx) in enumerate(pinned):
-            pm.set_image_ptr(i, td.data_ptr(), td.shape[0], dim, dt, tx.data_ptr())
+        if not sharded:
+            for i, (td, tx) in enumerate(pinned):
+                pm.set_image_ptr(i, td.data_ptr(), td.shape[0], dim, dt, tx.data_ptr())
+            return
+        d_dev = d_own.cuda(non_blocking=True); x_dev = x_own.cuda(non_blocking=True)
+        all_d = torch.empty((world,) + tuple(d_dev.shape), dtype=d_dev.dtype, device="cuda")
+        all_x = torch.empty((world,) + tuple(x_dev.shape), dtype=x_dev.dtype, device="cuda")
+        dist.all_gather_into_tensor(all_d, d_dev)
+        dist.all_gather_into_tensor(all_x, x_dev)
+        torch.cuda.synchronize()
+        for slot in range(n_local):
+            for r in range(world):
+                img = slot * world + r
+                if img < n_img:
+                    pm.set_image_ptr(img, all_d[r, slot].data_ptr(), a.kp, dim, dt, all_x[r, slot].data_ptr(), on_device=True)
 
     ingest()
     for _ in range(a.warmup):
@@ -356,6 +387,30 @@ def main():
     except Exception:
         pass
 
+    # ---- attribution: the same workload with the epipolar filter switched off (matcher only); the filter's cost
+    #      is the difference ("matcher-only and RANSAC-only pairs/s") -----------------------------
+    stages = None
+    if not a.no_stages and world == 1:
+        pm2 = api.PairMatcher(devices=[local], reserve_keypoints=n_img * a.kp, debug_flags=a.debug_flags,
+                              batch_pairs=a.batch_pairs, do_filter=0)
+        for i, (td, tx) in enumerate(pinned):
+            pm2.set_image_ptr(i, td.data_ptr(), td.shape[0], dim, dt, tx.data_ptr())
+        r = pm2.match_all_pairs(mine, copy=False); pm2.free_result(r)
+        torch.cuda.synchronize()
+        m_ms = 0.0
+        for _ in range(a.steps):
+            r = pm2.match_all_pairs(mine, copy=False)
+            m_ms += r["device_ms"]
+            pm2.free_result(r)
+        pm2.close()
+        m_ms /= a.steps
+        f_ms = max(ms_per_step - m_ms, 0.0)
+        stages = dict(matcher_only=dict(value=total_pairs / (m_ms * 1e-3), unit=UNIT, ms_per_step=m_ms,
+                                        what="kNN + ratio + uniqueness + CSR, do_filter = 0"),
+                      epipolar_filter=dict(ms_per_step=f_ms, value=(total_pairs / (f_ms * 1e-3)) if f_ms > 0 else None,
+                                           unit=UNIT, derived="full step minus matcher-only step",
+                                           share_of_step=f_ms / ms_per_step))
+
     # ---- recall of the reference's approximate FLANN search against this exact search ------
     if cpu is not None and flann:
         agree = tot = inter = union = 0
@@ -387,9 +442,12 @@ def main():
         e_ms = allmax(1e3 * (time.perf_counter() - t0)) / a.steps
         st2 = pm.stats()
         e2e = dict(value=total_pairs / (e_ms * 1e-3), unit=UNIT, ms_per_step=e_ms,
-                   h2d_bytes_per_step=int(allsum(st2["h2d_bytes"]) / a.steps),
+                   h2d_bytes_per_step=int(allsum(st2["h2d_bytes"]) / a.steps) +
+                   (int(allsum(d_own.numel() * d_own.element_size() + x_own.numel() * x_own.element_size())) if sharded else 0),
                    d2h_bytes_per_step=int(allsum(st2["d2h_bytes"]) / a.steps),
                    timing="host wall clock around set_image x images + match_all_pairs, max over ranks")
+        if sharded:
+            e2e["allgather_bytes_per_step"] = int(world * (d_own.numel() * d_own.element_size() + x_own.numel() * x_own.element_size()))
 
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=n_gpus, steps=a.steps, warmup=a.warmup,
@@ -398,7 +456,7 @@ def main():
                            "superpoint": "f16 operands / f32 accumulate candidates + exact f32 re-rank"}[a.kind],
                     data="synthetic", config=cfg, wall_ms_per_step=wall_ms / a.steps,
                     putative_matches_per_step=matches, inliers_per_step=inliers,
-                    roofline=roof, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks)
+                    roofline=roof, stages=stages, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks)
         print(json.dumps(line))
     pm.close()
     if world > 1:
