@@ -32,6 +32,7 @@ struct Image {
   int32_t n = 0;         // keypoints
   int32_t cap = 0;       // rows reserved
   bool integral = false; // u8-valued rows (exact tensor path allowed)
+  bool i8_ok = false;    // ... and every row norm fits the byte form's norm block (kind::i8 path allowed)
   bool unit_ok = false;  // finite real-valued rows with |x|^2 <= L2F_MAX_NORM2 and fp16 forms packed
   float maxn = 0.f;      // largest squared row norm
   bool has_xy = false;
@@ -198,6 +199,10 @@ struct DeviceCtx {
   unsigned int* h_fstats = nullptr;   // pinned
   unsigned long long* d_l2f = nullptr;   // l2f_fixup counters
   uint32_t* u8d = nullptr;     // [rows][32]     byte copy of integer-valued 128-d rows (fix-up kernel)
+  uint8_t *iq = nullptr, *it = nullptr;  // [rows][160] byte operand forms of integer-valued 128-d rows (kind::i8)
+  int32_t* qoff = nullptr;     // [rows] |a|^2 - 254 sum(a) (i8 form)
+  TcMaps imaps{};
+  bool tci_ready = false;
   uint32_t* bits = nullptr;    // [rows][words]  (U8_BITS)
   int32_t* xy = nullptr;       // [rows][2]
   TcMaps maps{};
@@ -274,7 +279,7 @@ struct DeviceCtx {
     single.destroy();
     auto fd = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
     fd(raw); fd(qf); fd(tf); fd(qnorm); fd(u8d); fd(bits); fd(xy); fd(d_flag); fd(stage); fd(d_dump);
-    fd(fq); fd(ft); fd(fnorm); fd(d_fstats); fd(d_l2f); fd(hq); fd(ht);
+    fd(fq); fd(ft); fd(fnorm); fd(d_fstats); fd(d_l2f); fd(hq); fd(ht); fd(iq); fd(it); fd(qoff);
     if (h_flag) cudaFreeHost(h_flag);
     if (h_fstats) cudaFreeHost(h_fstats);
     if (ingest) cudaStreamDestroy(ingest);
@@ -291,6 +296,7 @@ struct DeviceCtx {
     tc_ready = false;
     tcf_ready = false;
     tch_ready = false;
+    tci_ready = false;
     const bool sift_shape = dim == TC_DIM && (dtype == PM_DESC_F32 || dtype == PM_DESC_U8);
     if (!sift_shape && !float_tc_shape() && !bits_tc_shape()) return PM_OK;
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -314,15 +320,15 @@ struct DeviceCtx {
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     };
     CUresult r;
-    if (bits_tc_shape()) {
-      const int kb = 32 * words + 32;
-      auto mkb = [&](CUtensorMap* m, void* base, cuuint32_t box_k, CUtensorMapSwizzle sw) -> CUresult {
+    int kb = 32 * words + 32;
+    auto mkb = [&](CUtensorMap* m, void* base, cuuint32_t box_k, CUtensorMapSwizzle sw) -> CUresult {
         const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(kb), static_cast<cuuint64_t>(cap_rows)};
         const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(kb)};
         const cuuint32_t box[2] = {box_k, 128};
         return encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      };
+    };
+    if (bits_tc_shape()) {
       if ((r = mkb(&hmaps.q_main, hq, 128, CU_TENSOR_MAP_SWIZZLE_128B)) != CUDA_SUCCESS ||
           (r = mkb(&hmaps.q_ext, hq, 32, CU_TENSOR_MAP_SWIZZLE_32B)) != CUDA_SUCCESS ||
           (r = mkb(&hmaps.t_main, ht, 128, CU_TENSOR_MAP_SWIZZLE_128B)) != CUDA_SUCCESS ||
@@ -350,6 +356,13 @@ struct DeviceCtx {
         (r = mk(&maps.t_ext96, tf, 16, CU_TENSOR_MAP_SWIZZLE_32B, 96)) != CUDA_SUCCESS)
       return fail(PM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
     tc_ready = true;
+    kb = TC_I8_ROW;
+    if ((r = mkb(&imaps.q_main, iq, 128, CU_TENSOR_MAP_SWIZZLE_128B)) != CUDA_SUCCESS ||
+        (r = mkb(&imaps.q_ext, iq, 32, CU_TENSOR_MAP_SWIZZLE_32B)) != CUDA_SUCCESS ||
+        (r = mkb(&imaps.t_main, it, 128, CU_TENSOR_MAP_SWIZZLE_128B)) != CUDA_SUCCESS ||
+        (r = mkb(&imaps.t_ext, it, 32, CU_TENSOR_MAP_SWIZZLE_32B)) != CUDA_SUCCESS)
+      return fail(PM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+    tci_ready = true;
     return PM_OK;
   }
 
@@ -390,6 +403,9 @@ struct DeviceCtx {
         if ((rc = grow(tf, TC_KPAD, nc)) != PM_OK) return rc;
         if ((rc = grow(qnorm, 1, nc)) != PM_OK) return rc;
         if ((rc = grow(u8d, 32, nc)) != PM_OK) return rc;
+        if ((rc = grow(iq, TC_I8_ROW, nc)) != PM_OK) return rc;
+        if ((rc = grow(it, TC_I8_ROW, nc)) != PM_OK) return rc;
+        if ((rc = grow(qoff, 1, nc)) != PM_OK) return rc;
       }
       if (float_tc_shape()) {
         if ((rc = grow(fq, dim + 16, nc)) != PM_OK) return rc;
@@ -436,6 +452,7 @@ struct DeviceCtx {
     im.n = n;
     im.has_xy = xy_ != nullptr;
     im.integral = false;
+    im.i8_ok = false;
     im.unit_ok = false;
     im.maxn = 0.f;
     const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
@@ -482,7 +499,9 @@ struct DeviceCtx {
           PM_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), ingest));
           PM_CUDA(launch_pack_sift(u8src ? nullptr : rdst, u8src, n, qf + static_cast<size_t>(im.row) * TC_KPAD,
                                    tf + static_cast<size_t>(im.row) * TC_KPAD, qnorm + im.row,
-                                   u8src ? rdst : nullptr, u8d + static_cast<size_t>(im.row) * 32, d_flag, ingest));
+                                   u8src ? rdst : nullptr, u8d + static_cast<size_t>(im.row) * 32, d_flag,
+                                   iq + static_cast<size_t>(im.row) * TC_I8_ROW,
+                                   it + static_cast<size_t>(im.row) * TC_I8_ROW, qoff + im.row, ingest));
           ++stats.kernel_launches;
           PM_CUDA(cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ingest));
         }
@@ -493,7 +512,10 @@ struct DeviceCtx {
       }
     }
     PM_CUDA(cudaStreamSynchronize(ingest));   // caller's buffers are free to change on return
-    if (n > 0 && dtype != PM_DESC_U8_BITS && dim == TC_DIM) im.integral = (*h_flag == 0);
+    if (n > 0 && dtype != PM_DESC_U8_BITS && dim == TC_DIM) {
+      im.integral = (*h_flag & 1) == 0;
+      im.i8_ok = *h_flag == 0;
+    }
     if (n > 0 && float_tc_shape() && !im.integral) {
       // real-valued rows: fp16 operand forms + norms for the tensor-core search (l2_tc2.cu MODE 3)
       const int kp = dim + 16;
@@ -579,7 +601,7 @@ struct DeviceCtx {
   // Queues the kNN kernel(s) of a batch whose jobs are already in s.h_jobs[0..n).
   int enqueue_knn(Slot& s, int n, bool want_rev, bool timed, float* dump = nullptr, bool fast = false) {
     int max_nq = 0, max_nt = 0;
-    bool all_integral = true, all_unit = true;
+    bool all_integral = true, all_unit = true, all_i8 = true;
     double work = 0;
     for (int i = 0; i < n; ++i) {
       max_nq = std::max(max_nq, s.h_jobs[i].nq);
@@ -593,6 +615,7 @@ struct DeviceCtx {
       PM_CUDA(cudaMemcpyAsync(s.d_rjobs, s.h_rjobs, sizeof(PairJob) * n, cudaMemcpyHostToDevice, s.stream));
     if (dtype != PM_DESC_U8_BITS) {
       for (int i = 0; i < n && all_integral; ++i) all_integral = job_integral[i];
+      for (int i = 0; i < n && all_i8; ++i) all_i8 = job_i8[i];
       for (int i = 0; i < n && all_unit; ++i) all_unit = job_unit[i];
     }
     // The kNN kernels of all batches are serialised on one stream (they fill the machine anyway);
@@ -610,11 +633,17 @@ struct DeviceCtx {
     //   bits7-8   VALUES-ONLY kernel of the batched loop: 0 CTA pair 256-col (default), 1 single-CTA,
     //             2 CTA pair 192-col
     //   bit9      values-only CTA-pair kernel in its 64-register build (tail kernels co-resident)
+    //   bit11     batched loop keeps the fp16 form (kind::f16) instead of the byte form (kind::i8, default)
+    //   bits12-13 kind::i8 kernel: 1 / 2 = timing probes (no matches): TMA + MMA only / + accumulator loads without
+    //             the reduction; 3 = 64-register build (tail kernels co-resident)
     const int code = (prm.debug_flags >> 2) & 7;
     const int fcode = (prm.debug_flags >> 7) & 3;
     const int variant = ((prm.debug_flags >> 1) & 1) ^ 1;
     const bool use_tc = tc_ready && all_integral && !(prm.debug_flags & 1);
     const bool use_fast = use_tc && fast && !dump && !((prm.debug_flags >> 6) & 1);
+    // integer-valued 128-d rows as bytes on kind::i8: 5 K-steps per tile instead of 9 (l2_tc2.cu KIND 2)
+    const bool use_i8 = use_fast && tci_ready && all_i8 && fcode == 0 && !((prm.debug_flags >> 11) & 1);
+    const int i8_probe = (prm.debug_flags >> 12) & 3;
     // real-valued rows (SuperPoint): approximate tensor-core scores + exact fp32 re-rank (l2f_fixup.cu)
     const bool use_tcf = !use_tc && tcf_ready && dtype == PM_DESC_F32 && all_unit && !dump &&
                          max_nt <= L2F_MAX_NT &&
@@ -629,6 +658,13 @@ struct DeviceCtx {
         return launch_hamming_top2(bits, words, jobs_d, n, mq, oi, od, s.stride, variant, knn_stream);
       if (use_tcf) return launch_l2f_tc2(fmaps, dim, jobs_d, n, mq, oi, od, ox, s.stride, num_sms, knn_stream);
       if (!use_tc) return launch_l2_simt(raw, dim, jobs_d, n, mq, oi, od, s.stride, knn_stream);
+      if (use_i8) {
+        if (i8_probe == 1 || i8_probe == 2) {     // probes write nothing: every row reads "no neighbour"
+          cudaError_t e = cudaMemsetAsync(oi, 0xFF, sizeof(int2) * static_cast<size_t>(n) * s.stride, knn_stream);
+          if (e != cudaSuccess) return e;
+        }
+        return launch_l2i8_tc2(imaps, jobs_d, n, mq, oi, od, s.stride, num_sms, i8_probe, knn_stream);
+      }
       if (use_fast) {
         if (fcode == 1) return launch_l2_tc(maps, qnorm, jobs_d, n, mq, oi, od, s.stride, num_sms, nullptr, 5, knn_stream);
         return launch_l2_tc2(maps, qnorm, jobs_d, n, mq, oi, od, s.stride, num_sms, fcode == 2,
@@ -652,7 +688,16 @@ struct DeviceCtx {
     }
     PM_CUDA(cudaEventRecord(s.ev_knn, knn_stream));
     PM_CUDA(cudaStreamWaitEvent(s.stream, s.ev_knn, 0));
-    if (use_fast) {
+    if (use_i8) {
+      PM_CUDA(launch_l2_fixup_i8(u8d, qnorm, qoff, s.d_jobs, n, max_nq, s.knn_idx, s.knn_dist, s.stride, prm.ratio, 0,
+                                 d_l2f, s.stream));
+      ++stats.kernel_launches;
+      if (want_rev) {
+        PM_CUDA(launch_l2_fixup_i8(u8d, qnorm, qoff, s.d_rjobs, n, max_nt, s.rev_idx, s.rev_dist, s.stride, prm.ratio, 1,
+                                   d_l2f, s.stream));
+        ++stats.kernel_launches;
+      }
+    } else if (use_fast) {
       // exact indices / second neighbour, on the slot's stream so that it overlaps the next batch's
       // tensor kernel: rows that can still pass the ratio test, and -- for the cross-check, which needs
       // the nearest query of EVERY train row -- all rows of the reversed search
@@ -683,14 +728,15 @@ struct DeviceCtx {
     }
     return PM_OK;
   }
-  std::vector<char> job_integral, job_unit;   // per job of the batch being built
+  std::vector<char> job_integral, job_unit, job_i8;   // per job of the batch being built
 
   int fill_job(Slot& s, int k, int i, int j) {
     auto a = images.find(i), b = images.find(j);
     if (a == images.end() || b == images.end())
       return fail(PM_ERR_STATE, "image id %d not set", a == images.end() ? i : j);
     s.h_jobs[k] = PairJob{a->second.row, b->second.row, a->second.n, b->second.n, a->second.maxn, b->second.maxn};
-    if (static_cast<int>(job_integral.size()) <= k) { job_integral.resize(k + 1); job_unit.resize(k + 1); }
+    if (static_cast<int>(job_integral.size()) <= k) { job_integral.resize(k + 1); job_unit.resize(k + 1); job_i8.resize(k + 1); }
+    job_i8[k] = a->second.i8_ok && b->second.i8_ok;
     job_integral[k] = a->second.integral && b->second.integral;
     job_unit[k] = a->second.unit_ok && b->second.unit_ok;
     return PM_OK;

@@ -32,6 +32,11 @@ cudaError_t launch_l2_simt(const float* desc, int dim, const PairJob* jobs, int 
 // K2 -- l2_tc.cu (tcgen05 / TMEM / TMA), integer-valued 128-d descriptors
 static constexpr int TC_DIM = 128;        // descriptor length handled by the tensor path
 static constexpr int TC_KPAD = 144;       // 128 + one K=16 step carrying the train-row norm
+#ifndef PM_I8_CHUNK
+#define PM_I8_CHUNK 32
+#endif
+static constexpr int TC_I8_CHUNK = PM_I8_CHUNK;   // columns per candidate chunk of the i8 epilogue (16 or 32)
+static constexpr int TC_I8_ROW = 160;     // byte form: 128 x u8/s8 + one K=32 step carrying floor(|b|^2 / 2)
 struct TcMaps {
   CUtensorMap q_main, q_ext, t_main, t_ext;   // boxes of 128 rows
   CUtensorMap t_main96, t_ext96;              // boxes of 96 rows (pair kernel, 192-column tiles)
@@ -46,6 +51,14 @@ cudaError_t tc2_configure();
 cudaError_t launch_l2_tc2(const TcMaps& maps, const int32_t* qnorm, const PairJob* jobs, int n_jobs, int max_nq,
                           int2* idx, float2* dist, int stride, int num_sms, int variant, int mode,
                           cudaStream_t st);
+
+// integer-valued 128-d rows as bytes on kind::i8 (l2_tc2.cu KIND 2) + l2_fixup_i8 (l2_fixup.cu).  maps: UINT8
+// tensor maps over rows of TC_I8_ROW bytes.  counters: [0] rows re-evaluated, [2] rows rescanned exhaustively.
+cudaError_t launch_l2i8_tc2(const TcMaps& maps, const PairJob* jobs, int n_jobs, int max_nq, int2* idx, float2* dist,
+                            int stride, int num_sms, int probe, cudaStream_t st);
+cudaError_t launch_l2_fixup_i8(const uint32_t* u8desc, const int32_t* qnorm, const int32_t* qoff, const PairJob* jobs,
+                               int n_jobs, int max_nq, int2* idx, float2* dist, int stride, float ratio, int all_rows,
+                               unsigned long long* counters, cudaStream_t st);
 
 // binary descriptors on the tensor cores: Hamming = |a| + |b| - 2 a.b with E4M3 {0,1} operands (l2_tc2.cu,
 // kind::f8f6f4) + hamming_fixup.cu.  maps: UINT8 tensor maps over rows of 32*words + 32 bytes.
@@ -85,7 +98,7 @@ cudaError_t launch_l2_fixup(const uint32_t* u8desc, const int32_t* qnorm, const 
 // pack.cu
 cudaError_t launch_pack_sift(const float* raw_f32, const uint8_t* raw_u8, int n, __half* qf,
                              __half* tf, int32_t* qnorm, float* raw_out, uint32_t* u8_out,
-                             int* not_integral, cudaStream_t st);
+                             int* not_integral, uint8_t* iq, uint8_t* it, int32_t* qoff, cudaStream_t st);
 cudaError_t launch_u8_to_f32(const uint8_t* src, float* dst, size_t n, cudaStream_t st);
 
 // K4 -- select.cu

@@ -116,7 +116,191 @@ l2_fixup_kernel(const uint32_t* __restrict__ u8desc, const int32_t* __restrict__
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// I8 form (l2_tc2.cu KIND 2).  The tensor kernel tracked D' = 127*sum(a) - a.b + floor(|b|^2 / 2) instead of
+// the distance itself:  |a - b|^2 = qoff[a] + 2 D' + (|b|^2 & 1).  Per query row it left m1 = the smallest D',
+// m2' = the second smallest chunk minimum of D' (chunks of TC_I8_CHUNK columns) and the base column of the first chunk attaining m1.
+// With lo(x) = qoff + 2x every distance outside the winning chunk is >= lo(m2'), and the smallest of them is
+// lo(m2') or lo(m2') + 1.  After the winning chunk is recomputed exactly (d1 = its smallest distance, c2 = its
+// second smallest):
+//   * lo(m2') > d1  (always the case unless m2' == m1): the nearest neighbour is in the winning chunk, exact,
+//     lowest index on ties;
+//   * the second distance is c2 when c2 <= lo(m2'), else one of lo(m2'), lo(m2') + 1 -- the row is final when
+//     Lowe's test gives the same answer for both (or when only the nearest index is needed);
+//   * otherwise (m2' == m1, or a ratio test that hinges on one unit of d^2) the lane group rescans the whole
+//     train image exactly.  Counted in counters[2]; measured: a handful of rows per million.
+// CH = columns per chunk = lanes per group (16: half-warp, 32: warp); lane l of the group owns column cb + l.
+template <int CH>
+__device__ __forceinline__ unsigned int fx_chunk_key(uint32_t* st, const uint32_t* __restrict__ u8desc,
+                                                     const int32_t* __restrict__ qnorm, const PairJob& jb, int cb,
+                                                     int l, unsigned gmask, uint32_t q0, uint32_t q1, int na) {
+  const int ncol = min(CH, jb.nt - cb);
+  const uint4* src = reinterpret_cast<const uint4*>(u8desc + (static_cast<size_t>(jb.t_row) + cb) * 32);
+  __syncwarp(gmask);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int f = i * CH + l;                          // 16-byte piece: train row f / 8, words (f % 8) * 4 ..
+    const int r = f >> 3, w = (f & 7) * 4;
+    uint4 x = make_uint4(0, 0, 0, 0);
+    if (r < ncol) x = __ldg(src + f);
+    uint32_t* d = st + r * FX_LD + w;
+    d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = x.w;
+  }
+  __syncwarp(gmask);
+  unsigned int dot = 0;
+  if (CH == 16) {
+#pragma unroll
+    for (int w = 0; w < 16; ++w) {
+      const uint32_t a0 = __shfl_sync(gmask, q0, w, 16);
+      const uint32_t a1 = __shfl_sync(gmask, q1, w, 16);
+      dot = __dp4a(a0, st[l * FX_LD + w], dot);
+      dot = __dp4a(a1, st[l * FX_LD + 16 + w], dot);
+    }
+  } else {
+#pragma unroll
+    for (int w = 0; w < 32; ++w) dot = __dp4a(__shfl_sync(gmask, q0, w, 32), st[l * FX_LD + w], dot);
+  }
+  unsigned int key = 0xFFFFFFFFu;                      // (d^2 << 5 | lane): d^2 < 2^24
+  if (l < ncol) {
+    const int nb = qnorm[jb.t_row + cb + l];
+    key = (static_cast<unsigned int>(na + nb - 2 * static_cast<int>(dot)) << 5) | static_cast<unsigned int>(l);
+  }
+  return key;
+}
+
+static constexpr int FXI_INF = 0x7f800000;   // T2I_INF of l2_tc2.cu
+
+template <int CH>
+__global__ void __launch_bounds__(FX_WARPS * 32)
+l2_fixup_i8_kernel(const uint32_t* __restrict__ u8desc, const int32_t* __restrict__ qnorm,
+                   const int32_t* __restrict__ qoff, const PairJob* __restrict__ jobs, int2* __restrict__ knn_idx,
+                   float2* __restrict__ knn_dist, int stride, float ratio, int all_rows,
+                   unsigned long long* __restrict__ counters) {
+  constexpr int NG = FX_WARPS * 32 / CH;               // row groups per block
+  __shared__ uint32_t stage[NG][CH * FX_LD];
+  __shared__ int list[FX_SPAN];
+  __shared__ int cnt;
+  const PairJob jb = jobs[blockIdx.y];
+  const int span0 = blockIdx.x * FX_SPAN;
+  if (span0 >= jb.nq) return;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int grp = tid / CH, l = tid % CH;
+  const unsigned gmask = CH == 32 ? 0xffffffffu : ((lane & 16) ? 0xffff0000u : 0x0000ffffu);
+  const size_t base = static_cast<size_t>(blockIdx.y) * stride;
+  const float inf = __int_as_float(0x7f800000);
+
+  // pass 1: rows that cannot pass the ratio test even with the most favourable reading of (m1, m2') are closed
+  if (tid == 0) cnt = 0;
+  __syncthreads();
+  for (int r = tid; r < FX_SPAN; r += FX_WARPS * 32) {
+    const int row = span0 + r;
+    if (row >= jb.nq) break;
+    const int2 id = knn_idx[base + row];
+    if (id.y != -3) continue;                          // not produced by the i8 kernel
+    const float2 dd = knn_dist[base + row];
+    const int m1 = __float_as_int(dd.x), m2 = __float_as_int(dd.y);
+    bool need = id.x >= 0;
+    if (need && !all_rows && m2 != FXI_INF) {
+      const int qo = qoff[jb.q_row + row];
+      const float lo1 = static_cast<float>(max(qo + 2 * m1, 0));
+      const float hi2 = static_cast<float>(qo + 2 * m2 + 1);
+      need = __fsqrt_rn(lo1) < __fmul_rn(ratio, __fsqrt_rn(hi2));
+    }
+    if (need) list[atomicAdd(&cnt, 1)] = row;
+    else { knn_idx[base + row] = make_int2(-1, -1); knn_dist[base + row] = make_float2(inf, inf); }
+  }
+  __syncthreads();
+  const int n_need = cnt;
+
+  // pass 2: one lane group per surviving row
+  uint32_t* st = stage[grp];
+  unsigned int n_rescan = 0;
+  for (int e = grp; e < n_need; e += NG) {
+    const int row = list[e];
+    const int cb = knn_idx[base + row].x;
+    const int m2 = __float_as_int(knn_dist[base + row].y);
+    const int na = qnorm[jb.q_row + row];
+    const uint32_t* qs = u8desc + (static_cast<size_t>(jb.q_row) + row) * 32;
+    const uint32_t q0 = __ldg(qs + l), q1 = CH == 16 ? __ldg(qs + 16 + l) : 0u;
+    const unsigned int key = fx_chunk_key<CH>(st, u8desc, qnorm, jb, cb, l, gmask, q0, q1, na);
+    const unsigned int k1 = __reduce_min_sync(gmask, key);
+    const unsigned int k2 = __reduce_min_sync(gmask, key == k1 ? 0xFFFFFFFFu : key);
+    const int d1 = static_cast<int>(k1 >> 5);
+    int i1 = cb + static_cast<int>(k1 & 31u), i2 = -1, d2 = FXI_INF;
+    bool rescan = false;
+    if (m2 == FXI_INF) {                               // a single chunk: everything is in it
+      if (k2 != 0xFFFFFFFFu) { d2 = static_cast<int>(k2 >> 5); i2 = cb + static_cast<int>(k2 & 31u); }
+    } else {
+      const int others = qoff[jb.q_row + row] + 2 * m2;        // smallest outside distance is others or others + 1
+      const int c2 = k2 != 0xFFFFFFFFu ? static_cast<int>(k2 >> 5) : FXI_INF;
+      if (others <= d1) {
+        rescan = true;
+      } else if (c2 <= others) {
+        d2 = c2; i2 = cb + static_cast<int>(k2 & 31u);
+      } else {
+        d2 = others; i2 = 0x7ffffffe;                  // somewhere outside the winning chunk
+        if (!all_rows) {
+          const float s1 = __fsqrt_rn(static_cast<float>(d1));
+          const bool p_lo = s1 < __fmul_rn(ratio, __fsqrt_rn(static_cast<float>(others)));
+          const bool p_hi = s1 < __fmul_rn(ratio, __fsqrt_rn(static_cast<float>(min(c2, others + 1))));
+          rescan = p_lo != p_hi;
+        }
+      }
+    }
+    if (rescan) {                                      // uniform over the group
+      ++n_rescan;
+      unsigned long long b1 = KEY_NONE64, b2 = KEY_NONE64;     // (d^2 << 32 | column), per lane
+      for (int c = 0; c < jb.nt; c += CH) {
+        const unsigned int k = fx_chunk_key<CH>(st, u8desc, qnorm, jb, c, l, gmask, q0, q1, na);
+        if (k != 0xFFFFFFFFu) {
+          const unsigned long long kk = (static_cast<unsigned long long>(k >> 5) << 32) | static_cast<unsigned int>(c + l);
+          if (kk < b1) { b2 = b1; b1 = kk; } else if (kk < b2) b2 = kk;
+        }
+      }
+#pragma unroll
+      for (int off = CH / 2; off >= 1; off >>= 1) {
+        const unsigned long long o1 = __shfl_xor_sync(gmask, b1, off, CH);
+        const unsigned long long o2 = __shfl_xor_sync(gmask, b2, off, CH);
+        const unsigned long long lo = b1 < o1 ? b1 : o1, hi = b1 < o1 ? o1 : b1;
+        const unsigned long long m = b2 < o2 ? b2 : o2;
+        b1 = lo; b2 = hi < m ? hi : m;
+      }
+      i1 = static_cast<int>(b1 & 0xFFFFFFFFu);
+      const int dd1 = static_cast<int>(b1 >> 32);
+      if (b2 != KEY_NONE64) { d2 = static_cast<int>(b2 >> 32); i2 = static_cast<int>(b2 & 0xFFFFFFFFu); }
+      else { d2 = FXI_INF; i2 = -1; }
+      if (l == 0) {
+        knn_idx[base + row] = make_int2(i1, i2);
+        knn_dist[base + row] = make_float2(__fsqrt_rn(static_cast<float>(dd1)),
+                                           i2 >= 0 ? __fsqrt_rn(static_cast<float>(d2)) : inf);
+      }
+    } else if (l == 0) {
+      knn_idx[base + row] = make_int2(i1, d2 != FXI_INF ? i2 : -1);
+      knn_dist[base + row] = make_float2(__fsqrt_rn(static_cast<float>(d1)),
+                                         d2 != FXI_INF ? __fsqrt_rn(static_cast<float>(d2)) : inf);
+    }
+  }
+  if (counters) {
+    if (tid == 0 && n_need) atomicAdd(&counters[0], static_cast<unsigned long long>(n_need));
+    if (l == 0 && n_rescan) atomicAdd(&counters[2], static_cast<unsigned long long>(n_rescan));
+  }
+}
+
+cudaError_t launch_l2_fixup_i8(const uint32_t* u8desc, const int32_t* qnorm, const int32_t* qoff, const PairJob* jobs,
+                               int n_jobs, int max_nq, int2* idx, float2* dist, int stride, float ratio, int all_rows,
+                               unsigned long long* counters, cudaStream_t st) {
+  if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
+  const int bx = (max_nq + FX_SPAN - 1) / FX_SPAN;
+  dim3 grid(bx, n_jobs);
+  l2_fixup_i8_kernel<TC_I8_CHUNK><<<grid, FX_WARPS * 32, 0, st>>>(u8desc, qnorm, qoff, jobs, idx, dist, stride, ratio,
+                                                                  all_rows, counters);
+  return cudaGetLastError();
+}
+
 cudaError_t fixup_configure() {
+  cudaError_t e = cudaFuncSetAttribute(l2_fixup_i8_kernel<TC_I8_CHUNK>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(l2_fixup_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 

@@ -22,6 +22,19 @@
 #include "common.cuh"
 #include "kernels.h"
 
+// i8 epilogue schedule (A/B builds): 0 = load 64 columns, reduce; 1 = one tcgen05.ld in flight while 32 columns are
+// reduced; 2 = as 1, but never blocks on the next accumulator while a loaded chunk is still unreduced
+#ifndef PM_I8_EPI
+#define PM_I8_EPI 0
+#endif
+// timing-probe dissection (MODE 1 only, A/B builds): skip the accumulator hand-shake / the train-tile TMA
+#ifndef PM_PROBE_NOACC
+#define PM_PROBE_NOACC 0
+#endif
+#ifndef PM_PROBE_NOTMA
+#define PM_PROBE_NOTMA 0
+#endif
+
 namespace pm {
 
 static constexpr int T2_BM = 128;               // query rows per CTA
@@ -47,14 +60,19 @@ struct T2Cfg {
   // the train-tile ring is staged in K GROUPS of two 64-wide atoms (the norm block rides with the last
   // group): one group per tile for 128-d rows, two for 256-d rows -- finer stages hide the TMA latency
   // that two whole-tile stages of 68 KB could not
-  static constexpr int kBAtom = kBNH * 128, kBExt = kBNH * 32, kBTile = 2 * kBAtom + kBExt;   // one stage
-  static constexpr int kGroups = KA / 2;
-  static constexpr int kStages = KA == 4 ? 3 : (BN == 256 ? 3 : 4);
+  static constexpr int kAG = KA >= 2 ? 2 : 1;                    // 128-byte K atoms per stage
+  static constexpr int kBAtom = kBNH * 128, kBExt = kBNH * 32, kBTile = kAG * kBAtom + kBExt;   // one stage
+  static constexpr int kGroups = KA / kAG;
+  static constexpr int kStages = KA == 4 ? 3 : (KA == 1 ? 6 : (BN == 256 ? 3 : 4));
   static constexpr int kSmemB = kStages * kBTile;
   static constexpr int kXchg = 4 * (kSlices - 1) * 32 * 32;   // two float4 per (quarter, slice, lane)
   static constexpr int kSmemBytes = kATile + kSmemB + 1024 + 256 + kXchg;
   // kind::f16: D=f32, A=B=f16, K-major, N=BN, M=256 (pair)
-  static constexpr uint32_t kIdesc = (1u << 4) | ((BN >> 3) << 17) | ((T2_ROWS >> 4) << 24);
+  static constexpr uint32_t kShape = ((BN >> 3) << 17) | ((T2_ROWS >> 4) << 24);
+  static constexpr uint32_t kIdesc = (1u << 4) | kShape;
+  // kind::i8: D=s32 (c_format 2); main K-steps A=u8 (format 0), B=s8 (format 1); norm block A=B=u8
+  static constexpr uint32_t kIdescI8 = (2u << 4) | (1u << 10) | kShape;
+  static constexpr uint32_t kIdescI8Ext = (2u << 4) | kShape;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -80,10 +98,19 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tma
 // KIND 0: kind::f16 (fp16 operands, K = 16 per instruction); KIND 1: kind::f8f6f4 with E4M3 operands (K = 32 per
 // instruction, twice the rate).  Both consume 32 bytes of a K-major row per instruction and share the
 // instruction-descriptor encoding used here (format field 0 = F16 resp. E4M3, D = F32).
+// KIND 2: kind::i8 (u8 x s8 -> s32, K = 32 per instruction, the rate of kind::f8f6f4): integer-valued 128-d rows,
+// see the I8 FORM note above t2i_fast16.
 template <int KIND>
 __device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                               uint32_t accumulate) {
-  if (KIND == 1)
+  if (KIND == 2)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else if (KIND == 1)
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
@@ -201,6 +228,60 @@ __device__ __forceinline__ void t2_fast(Top2p& s, const uint32_t* r, int cbase) 
   t2_fast16(s, r, cbase);
   t2_fast16(s, r + 16, cbase + 16);
 }
+// ---- I8 FORM (KIND 2): integer-valued 128-d rows as bytes --------------------------------------------
+// query row  [ a_0 .. a_127 (u8) | 1, 255 x31 (u8) ]      train row [ 127 - b_k (s8) | r, e_1 .. e_31 (u8) ]
+// with h = floor(|b|^2 / 2) = r + 255 * (e_1 + .. + e_31).  The s32 accumulator is
+//     D' = a.(127 - b) + h = 127 * sum(a) - a.b + floor(|b|^2 / 2),
+// so |a - b|^2 = 2 D' + (|b|^2 & 1) + (|a|^2 - 254 * sum(a)): the order of the distances is the order of
+// (D', parity of |b|^2).  The values-only epilogue tracks D'; l2_fixup_i8_kernel resolves the parity exactly
+// (and rescans the rare rows where it could matter).  5 K-steps per tile instead of the fp16 form's 9.
+struct Top2i {
+  int m1, m2, i1;
+};
+static constexpr int T2I_INF = 0x7f800000;      // also what the column mask writes (bit pattern of +inf)
+__device__ __forceinline__ void t2i_fast16(Top2i& s, const uint32_t* r, int cbase) {
+  int g[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    g[k] = min(min(static_cast<int>(r[4 * k]), static_cast<int>(r[4 * k + 1])),
+               min(static_cast<int>(r[4 * k + 2]), static_cast<int>(r[4 * k + 3])));
+  const int cm = min(min(g[0], g[1]), min(g[2], g[3]));
+  const int t = max(cm, s.m1);
+  s.i1 = cm < s.m1 ? cbase : s.i1;
+  s.m1 = min(cm, s.m1);
+  s.m2 = min(s.m2, t);
+}
+// 32-column chunks: a tree of 3-input minima (16 instructions for 32 values) and a 4-instruction update
+__device__ __forceinline__ void t2i_fast32(Top2i& s, const uint32_t* r, int cbase) {
+  int a[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k)
+    a[k] = __vimin3_s32(static_cast<int>(r[3 * k]), static_cast<int>(r[3 * k + 1]), static_cast<int>(r[3 * k + 2]));
+  const int b0 = __vimin3_s32(a[0], a[1], a[2]), b1 = __vimin3_s32(a[3], a[4], a[5]);
+  const int b2 = __vimin3_s32(a[6], a[7], a[8]);
+  const int b3 = __vimin3_s32(a[9], static_cast<int>(r[30]), static_cast<int>(r[31]));
+  const int cm = min(__vimin3_s32(b0, b1, b2), b3);
+  bool keep;                                         // m1 <= cm: the earlier chunk stays the winner
+  const int nm1 = __vibmin_s32(s.m1, cm, &keep);
+  const int t = max(cm, s.m1);
+  s.i1 = keep ? s.i1 : cbase;
+  s.m1 = nm1;
+  s.m2 = min(s.m2, t);
+}
+// 32 columns starting at column c of the train image, of which the first `lim` exist
+__device__ __forceinline__ void t2i_chunk32(Top2i& s, uint32_t (&v)[32], int c, int lim) {
+  if (lim < 32) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e)
+      if (e >= lim) v[e] = static_cast<uint32_t>(T2I_INF);
+  }
+  if (TC_I8_CHUNK == 32) {
+    if (lim > 0) t2i_fast32(s, v, c);
+  } else {
+    if (lim > 0) t2i_fast16(s, v, c);
+    if (lim > 16) t2i_fast16(s, v + 16, c + 16);
+  }
+}
 // ---- MODE 3: six smallest chunk minima as keys ---------------------------------------------------
 // key = positive fp32 score with the low 10 mantissa bits replaced by the 16-column chunk id (the
 // scores are approximate anyway; l2f_fixup.cu widens its error bound by the 2^-13 relative truncation).
@@ -263,11 +344,15 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
   // 10 mantissa bits) and l2f_fixup.cu re-ranks exactly in fp32.  qnorm is unused in that mode.
   constexpr int T2_BN = Cfg::kBN, T2_BNH = Cfg::kBNH, T2_STAGES = Cfg::kStages, T2_SMEM_B = Cfg::kSmemB;
   constexpr int KA = Cfg::kKA, T2_TILE = Cfg::kATile, T2_SMEM_A = Cfg::kATile;
-  constexpr int KEL = KIND == 1 ? 128 : 64;        // tensor-map elements per 128-byte K atom (E4M3 bytes / fp16)
+  constexpr int KEL = KIND >= 1 ? 128 : 64;        // tensor-map elements per 128-byte K atom (bytes / fp16)
+  constexpr int AG = Cfg::kAG;
+  static_assert(KIND != 2 || MODE == 2 || MODE == 1 || MODE == 5, "the i8 form has a values-only epilogue");
+  static_assert(KIND != 2 || Cfg::kCPW == 2, "the pipelined i8 epilogue handles two 32-column chunks per warp");
   constexpr int KDIM = KEL * KA;
   constexpr int T2_BATOM = Cfg::kBAtom, T2_BTILE = Cfg::kBTile, CPW = Cfg::kCPW, NSL = Cfg::kSlices;
   constexpr int NGRP = Cfg::kGroups;
-  constexpr uint32_t T2_IDESC = Cfg::kIdesc;
+  constexpr uint32_t T2_IDESC = KIND == 2 ? Cfg::kIdescI8 : Cfg::kIdesc;
+  constexpr uint32_t T2_IDESC_EXT = KIND == 2 ? Cfg::kIdescI8Ext : Cfg::kIdesc;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -326,7 +411,7 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
           tma_load_2d_pair(sA + KA * T2_ATOM, &q_ext, KDIM, row, a_full);
         }
         ++ai;
-        const int n_tiles = (job.nt + T2_BN - 1) / T2_BN;
+        const int n_tiles = (MODE == 1 && PM_PROBE_NOTMA) ? 0 : (job.nt + T2_BN - 1) / T2_BN;
         for (int n = 0; n < n_tiles; ++n) {
           const int row = job.t_row + n * T2_BN + rank * T2_BNH;      // this CTA's half of the train tile
 #pragma unroll
@@ -334,11 +419,12 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
             const uint32_t st = bi % T2_STAGES;
             wait_trap(&b_empty[st], ((bi / T2_STAGES) & 1) ^ 1);
             const bool last = g == NGRP - 1;
-            if (leader) mbar_expect_tx(&b_full[st], 2 * (2 * T2_BATOM + (last ? Cfg::kBExt : 0)));
+            if (leader) mbar_expect_tx(&b_full[st], 2 * (AG * T2_BATOM + (last ? Cfg::kBExt : 0)));
             uint8_t* dst = sB + st * T2_BTILE;
-            tma_load_2d_pair(dst, &t_main, 2 * KEL * g, row, &b_full[st]);
-            tma_load_2d_pair(dst + T2_BATOM, &t_main, 2 * KEL * g + KEL, row, &b_full[st]);
-            if (last) tma_load_2d_pair(dst + 2 * T2_BATOM, &t_ext, KDIM, row, &b_full[st]);
+#pragma unroll
+            for (int a = 0; a < AG; ++a)
+              tma_load_2d_pair(dst + a * T2_BATOM, &t_main, (AG * g + a) * KEL, row, &b_full[st]);
+            if (last) tma_load_2d_pair(dst + AG * T2_BATOM, &t_ext, KDIM, row, &b_full[st]);
           }
         }
       }
@@ -360,28 +446,28 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
         const int n_tiles = (job_nt + T2_BN - 1) / T2_BN;
         for (int n = 0; n < n_tiles; ++n, ++ti) {
           const uint32_t as = ti & 1, use = ti >> 1;
-          wait_trap(&acc_empty[as], (use & 1) ^ 1);
+          if (!(MODE == 1 && PM_PROBE_NOACC)) wait_trap(&acc_empty[as], (use & 1) ^ 1);
           const uint32_t d_tmem = tmem_base + as * T2_BN;
 #pragma unroll
           for (int g = 0; g < NGRP; ++g, ++bi) {
             const uint32_t st = bi % T2_STAGES;
-            wait_trap(&b_full[st], (bi / T2_STAGES) & 1);
+            if (!(MODE == 1 && PM_PROBE_NOTMA)) wait_trap(&b_full[st], (bi / T2_STAGES) & 1);
             tc_fence_after();
             if (elect_one()) {
               const uint32_t b_lo = b_lo0 + st * (T2_BTILE >> 4);
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const uint32_t aoff = ((2 * g + (k >> 2)) * T2_ATOM + (k & 3) * 32) >> 4;
+              for (int k = 0; k < 4 * AG; ++k) {
+                const uint32_t aoff = ((AG * g + (k >> 2)) * T2_ATOM + (k & 3) * 32) >> 4;
                 const uint32_t boff = ((k >> 2) * T2_BATOM + (k & 3) * 32) >> 4;
                 umma_f16_pair<KIND>(d_tmem, (static_cast<uint64_t>(HI128) << 32) | (a_lo + aoff),
                               (static_cast<uint64_t>(HI128) << 32) | (b_lo + boff), T2_IDESC, (g > 0 || k > 0) ? 1u : 0u);
               }
               if (g == NGRP - 1) {
                 umma_f16_pair<KIND>(d_tmem, (static_cast<uint64_t>(HI32) << 32) | (a_lo + ((KA * T2_ATOM) >> 4)),
-                              (static_cast<uint64_t>(HI32) << 32) | (b_lo + ((2 * T2_BATOM) >> 4)), T2_IDESC, 1u);
+                              (static_cast<uint64_t>(HI32) << 32) | (b_lo + ((AG * T2_BATOM) >> 4)), T2_IDESC_EXT, 1u);
                 umma_commit_pair(&acc_full[as]);
               }
-              umma_commit_pair(&b_empty[st]);
+              if (!(MODE == 1 && PM_PROBE_NOTMA)) umma_commit_pair(&b_empty[st]);
             }
             __syncwarp();
           }
@@ -389,6 +475,7 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
         if (elect_one()) umma_commit_pair(a_empty);
         __syncwarp();
       }
+      if (MODE == 1 && PM_PROBE_NOACC && ai > 0) wait_trap(a_empty, (ai - 1) & 1);   // drain before the dealloc
     }
   } else if (warp >= 4) {
     // ======================================= epilogue (both CTAs) =============================
@@ -404,8 +491,48 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
       s.i1 = s.i2 = -1;                                // MODE 2: i1 = base column of the winning 16-column chunk
       Keys4 ks;
       ks.k1 = ks.k2 = ks.k3 = ks.k4 = ks.k5 = ks.k6 = __int_as_float(0x7f800000);
+      Top2i si;                                        // KIND 2
+      si.m1 = si.m2 = T2I_INF;
+      si.i1 = -1;
       const int n_tiles = (job.nt + T2_BN - 1) / T2_BN;
-      for (int n = 0; n < n_tiles; ++n, ++ti) {
+      if (KIND == 2 && (MODE == 2 || MODE == 5) && PM_I8_EPI >= 1) {
+        // software-pipelined: the tcgen05.ld of the next 32 columns is in flight while these 32 are reduced, so
+        // that the TMEM read port (64 B/clk per sub-partition: 512 of the tile's 640 MMA cycles) never idles
+        uint32_t va[32], vb[32];
+        const uint32_t tq = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + slice * 64;
+        wait_trap(&acc_full[ti & 1], (ti >> 1) & 1);
+        tc_fence_after();
+        tmem_ld_32x32b_x32_async(tq + (ti & 1) * T2_BN, va);
+        for (int n = 0; n < n_tiles; ++n, ++ti) {
+          const uint32_t as = ti & 1;
+          const int c0 = n * T2_BN + slice * 64;
+          const int lim = job.nt - c0;
+          tmem_wait_pin(va);
+          tmem_ld_32x32b_x32_async(tq + as * T2_BN + 32, vb);
+          if (MODE == 2) t2i_chunk32(si, va, c0, lim);
+          tmem_wait_pin(vb);
+          tc_fence_before();
+          if (lane == 0) mbar_arrive_leader(&acc_empty[as]);
+          const uint32_t t2 = ti + 1;
+          if (PM_I8_EPI == 2 && (n + 1 >= n_tiles || !mbar_try_wait(&acc_full[t2 & 1], (t2 >> 1) & 1))) {
+            // the next accumulator is not there yet: reduce first, then wait for it
+            if (MODE == 2) t2i_chunk32(si, vb, c0 + 32, lim - 32);
+            if (n + 1 < n_tiles) {
+              wait_trap(&acc_full[t2 & 1], (t2 >> 1) & 1);
+              tc_fence_after();
+              tmem_ld_32x32b_x32_async(tq + (t2 & 1) * T2_BN, va);
+            }
+          } else {
+            if (n + 1 < n_tiles) {
+              if (PM_I8_EPI != 2) wait_trap(&acc_full[t2 & 1], (t2 >> 1) & 1);
+              tc_fence_after();
+              tmem_ld_32x32b_x32_async(tq + (t2 & 1) * T2_BN, va);
+            }
+            if (MODE == 2) t2i_chunk32(si, vb, c0 + 32, lim - 32);
+          }
+        }
+      } else
+      for (int n = 0; n < ((MODE == 1 && PM_PROBE_NOACC) ? 0 : n_tiles); ++n, ++ti) {
         const uint32_t as = ti & 1, use = ti >> 1;
         wait_trap(&acc_full[as], use & 1);
         tc_fence_after();
@@ -425,6 +552,7 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
               if (lane == 0) mbar_arrive_leader(&acc_empty[as]);
             }
             if (MODE == 3) { keys_chunk16(ks, v, c0 + 32 * c); keys_chunk16(ks, v + 16, c0 + 32 * c + 16); }
+            else if (MODE == 2 && KIND == 2) t2i_chunk32(si, v, c0 + 32 * c, 32);
             else if (MODE == 2) t2_fast(s, v, c0 + 32 * c);
             else t2_scan32(s, v, c0 + 32 * c);
           }
@@ -442,6 +570,8 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
             if (MODE == 3) {
               if (lim > 32 * c) keys_chunk16(ks, v, c0 + 32 * c);
               if (lim > 32 * c + 16) keys_chunk16(ks, v + 16, c0 + 32 * c + 16);
+            } else if (MODE == 2 && KIND == 2) {
+              t2i_chunk32(si, v, c0 + 32 * c, lim - 32 * c);
             } else if (MODE == 2) {
               if (lim > 32 * c) t2_fast16(s, v, c0 + 32 * c);
               if (lim > 32 * c + 16) t2_fast16(s, v + 16, c0 + 32 * c + 16);
@@ -455,8 +585,10 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
         float4* slot = xchg + ((quarter * (NSL - 1)) * 64 + lane);
         const int bar_id = 1 + quarter;
         if (slice > 0) {
-          slot[(slice - 1) * 64] = MODE == 3 ? make_float4(ks.k1, ks.k2, ks.k3, ks.k4)
-                                             : make_float4(s.m1, __int_as_float(s.i1), s.m2, __int_as_float(s.i2));
+          slot[(slice - 1) * 64] =
+              MODE == 3   ? make_float4(ks.k1, ks.k2, ks.k3, ks.k4)
+              : KIND == 2 ? make_float4(__int_as_float(si.m1), __int_as_float(si.i1), __int_as_float(si.m2), 0.f)
+                          : make_float4(s.m1, __int_as_float(s.i1), s.m2, __int_as_float(s.i2));
           if (MODE == 3) slot[(slice - 1) * 64 + 32] = make_float4(ks.k5, ks.k6, 0.f, 0.f);
         }
         asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NSL) : "memory");
@@ -468,6 +600,13 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
               const float4 x2 = slot[o * 64 + 32];
               keys_insert(ks, x.x); keys_insert(ks, x.y); keys_insert(ks, x.z); keys_insert(ks, x.w);
               keys_insert(ks, x2.x); keys_insert(ks, x2.y);
+            } else if (MODE == 2 && KIND == 2) {
+              const int ob = __float_as_int(x.y), om1 = __float_as_int(x.x), om2 = __float_as_int(x.z);
+              const bool take = ob >= 0 && (si.i1 < 0 || om1 < si.m1 || (om1 == si.m1 && ob < si.i1));
+              const int hi = max(si.m1, om1);
+              si.m2 = min(min(si.m2, om2), hi);
+              si.m1 = min(si.m1, om1);
+              si.i1 = take ? ob : si.i1;
             } else if (MODE == 2) {
               const int ob = __float_as_int(x.y);
               const bool take = ob >= 0 && (s.i1 < 0 || x.x < s.m1 || (x.x == s.m1 && ob < s.i1));
@@ -487,12 +626,16 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
         knn_dist[o] = make_float2(ks.k1, ks.k2);
         knn_idx[o] = make_int2(__float_as_int(ks.k3), __float_as_int(ks.k4));
         extra_keys[o] = make_float2(ks.k5, ks.k6);
+      } else if (MODE == 2 && KIND == 2 && slice == 0 && row < job.nq) {
+        const size_t o = static_cast<size_t>(jb) * stride + row;
+        knn_idx[o] = make_int2(si.i1, -3);             // -3: D' values of the i8 form (l2_fixup_i8_kernel follows)
+        knn_dist[o] = make_float2(__int_as_float(si.m1), __int_as_float(si.m2));
       } else if (MODE == 2 && slice == 0 && row < job.nq) {
         const float na = static_cast<float>(qnorm[job.q_row + row]);
         const size_t o = static_cast<size_t>(jb) * stride + row;
         knn_idx[o] = make_int2(s.i1, -2);
         knn_dist[o] = make_float2(__fadd_rn(s.m1, na), __fadd_rn(s.m2, na));
-      } else if (slice == 0 && row < job.nq) {
+      } else if (KIND != 2 && slice == 0 && row < job.nq) {
         const float na = static_cast<float>(qnorm[job.q_row + row]);
         int2 oi;
         float2 od;
@@ -519,6 +662,7 @@ using T2Wide = T2Cfg<256, 2>;     // 16 epilogue warps
 using T2Deep = T2Cfg<192, 1>;     // 24 epilogue warps
 using T2F128 = T2Cfg<256, 2, 2>;  // real-valued rows, 128-d
 using T2F256 = T2Cfg<256, 2, 4>;  // real-valued rows, 256-d (SuperPoint)
+using T2I8 = T2Cfg<256, 2, 1>;    // integer-valued 128-d rows as bytes (kind::i8)
 
 cudaError_t tc2_configure() {
   cudaError_t e;
@@ -541,6 +685,18 @@ cudaError_t tc2_configure() {
   if ((e = cudaFuncSetAttribute(l2_top2_tc2_kernel<T2F256, 2, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 T2F256::kSmemBytes)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(l2_top2_tc2_kernel<T2F256, 2, false, 1>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(l2_top2_tc2_kernel<T2I8, 2, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                T2I8::kSmemBytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(l2_top2_tc2_kernel<T2I8, 2, false, 2>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(l2_top2_tc2_kernel<T2I8, 1, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                T2I8::kSmemBytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(l2_top2_tc2_kernel<T2I8, 5, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                T2I8::kSmemBytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(l2_top2_tc2_kernel<T2I8, 2, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                T2I8::kSmemBytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(l2_top2_tc2_kernel<T2I8, 2, true, 2>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                 cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
 #undef PM_T2_ATTR
   return cudaSuccess;
@@ -594,6 +750,32 @@ cudaError_t launch_ham_tc2(const TcMaps& maps, int words, const int32_t* qnorm, 
         maps.q_main, maps.q_ext, maps.t_main, maps.t_ext, qnorm, jobs, n_jobs, tiles_per_job, idx, dist, stride, nullptr);
   else
     return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+// Integer-valued 128-d rows in the i8 form (pack_sift_kernel): D' per row in (knn_idx = chunk base, -3 |
+// knn_dist = int bits of m1, m2'); l2_fixup_i8 follows.  probe: timing probes (no results): 1 = TMA + MMA only,
+// 2 = + tcgen05.ld of the accumulators.
+cudaError_t launch_l2i8_tc2(const TcMaps& maps, const PairJob* jobs, int n_jobs, int max_nq, int2* idx, float2* dist,
+                            int stride, int num_sms, int probe, cudaStream_t st) {
+  if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
+  const int tiles_per_job = (max_nq + T2_ROWS - 1) / T2_ROWS;
+  const int n_items = n_jobs * tiles_per_job;
+  int clusters = num_sms / 2;
+  if (n_items < clusters) clusters = n_items;
+  const int grid = clusters * 2;
+  if (probe == 3)     // 64-register build: the tail kernels of the previous batch can be co-resident
+    l2_top2_tc2_kernel<T2I8, 2, true, 2><<<grid, T2I8::kThreads, T2I8::kSmemBytes, st>>>(
+        maps.q_main, maps.q_ext, maps.t_main, maps.t_ext, nullptr, jobs, n_jobs, tiles_per_job, idx, dist, stride, nullptr);
+  else if (probe == 2)     // tcgen05.ld without the reduction
+    l2_top2_tc2_kernel<T2I8, 5, false, 2><<<grid, T2I8::kThreads, T2I8::kSmemBytes, st>>>(
+        maps.q_main, maps.q_ext, maps.t_main, maps.t_ext, nullptr, jobs, n_jobs, tiles_per_job, idx, dist, stride, nullptr);
+  else if (probe)
+    l2_top2_tc2_kernel<T2I8, 1, false, 2><<<grid, T2I8::kThreads, T2I8::kSmemBytes, st>>>(
+        maps.q_main, maps.q_ext, maps.t_main, maps.t_ext, nullptr, jobs, n_jobs, tiles_per_job, idx, dist, stride, nullptr);
+  else
+    l2_top2_tc2_kernel<T2I8, 2, false, 2><<<grid, T2I8::kThreads, T2I8::kSmemBytes, st>>>(
+        maps.q_main, maps.q_ext, maps.t_main, maps.t_ext, nullptr, jobs, n_jobs, tiles_per_job, idx, dist, stride, nullptr);
   return cudaGetLastError();
 }
 

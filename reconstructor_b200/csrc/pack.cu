@@ -8,6 +8,13 @@
 //   query form  [ -2*a_0 .. -2*a_127 | 1, 2048, 2048, 0 x13 ]
 //   train form  [    b_0 ..    b_127 | lo, mid, 2048*hi, 0 x13 ]   with |b|^2 = lo + 2048*mid + 2048*2048*hi
 // so that the MMA accumulator equals |b|^2 - 2 a.b exactly (see l2_tc.cu).
+//
+// The same rows are also written in the BYTE forms of the kind::i8 kernel (l2_tc2.cu KIND 2), 160 bytes per row:
+//   query form  [ a_0 .. a_127 (u8)        | 1, 255 x31 (u8) ]
+//   train form  [ 127 - b_0 .. (s8)        | r, e_1 .. e_31 (u8) ]   with floor(|b|^2 / 2) = r + 255 * sum(e_j)
+// and qoff[row] = |a|^2 - 254 * sum(a), so that |a - b|^2 = 2 * accumulator + (|b|^2 & 1) + qoff[a].
+// flag bit 1 is raised when a row's norm does not fit the 31 digits (|b|^2 > 4,032,059; impossible for
+// SIFT, whose rows have norm ~512): such an image stays on the fp16 form.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -16,7 +23,8 @@ namespace pm {
 __global__ void __launch_bounds__(256)
 pack_sift_kernel(const float* __restrict__ raw_f32, const uint8_t* __restrict__ raw_u8, int n,
                  __half* __restrict__ qf, __half* __restrict__ tf, int32_t* __restrict__ qnorm,
-                 float* __restrict__ raw_out, uint32_t* __restrict__ u8_out, int* __restrict__ not_integral) {
+                 float* __restrict__ raw_out, uint32_t* __restrict__ u8_out, int* __restrict__ not_integral,
+                 uint8_t* __restrict__ iq, uint8_t* __restrict__ it, int32_t* __restrict__ qoff) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
@@ -32,24 +40,48 @@ pack_sift_kernel(const float* __restrict__ raw_f32, const uint8_t* __restrict__ 
     *reinterpret_cast<float4*>(raw_out + static_cast<size_t>(row) * TC_DIM + 4 * lane) =
         make_float4(v[0], v[1], v[2], v[3]);
   // byte copy of the row (4 values per word) for the integer fix-up kernel
-  u8_out[static_cast<size_t>(row) * 32 + lane] =
+  const uint32_t w =
       static_cast<uint32_t>(static_cast<int>(fminf(fmaxf(v[0], 0.f), 255.f))) |
       (static_cast<uint32_t>(static_cast<int>(fminf(fmaxf(v[1], 0.f), 255.f))) << 8) |
       (static_cast<uint32_t>(static_cast<int>(fminf(fmaxf(v[2], 0.f), 255.f))) << 16) |
       (static_cast<uint32_t>(static_cast<int>(fminf(fmaxf(v[3], 0.f), 255.f))) << 24);
+  u8_out[static_cast<size_t>(row) * 32 + lane] = w;
   bool bad = false;
-  int nrm = 0;
+  int nrm = 0, sum = 0;
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     bad |= !(v[e] >= 0.f && v[e] <= 255.f && v[e] == rintf(v[e]));
     const int iv = static_cast<int>(v[e]);
     nrm += iv * iv;
+    sum += iv;
   }
   if (__any_sync(0xffffffffu, bad)) {
     if (lane == 0) atomicOr(not_integral, 1);
   }
 #pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, off);
+  for (int off = 16; off >= 1; off >>= 1) {
+    nrm += __shfl_xor_sync(0xffffffffu, nrm, off);
+    sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  }
+  if (iq) {
+    uint8_t* qrow = iq + static_cast<size_t>(row) * TC_I8_ROW;
+    uint8_t* trow = it + static_cast<size_t>(row) * TC_I8_ROW;
+    reinterpret_cast<uint32_t*>(qrow)[lane] = w;
+    // 127 - b as a two's-complement byte
+    const uint32_t b0 = w & 0xFFu, b1 = (w >> 8) & 0xFFu, b2 = (w >> 16) & 0xFFu, b3 = w >> 24;
+    reinterpret_cast<uint32_t*>(trow)[lane] = ((127u - b0) & 0xFFu) | (((127u - b1) & 0xFFu) << 8) |
+                                              (((127u - b2) & 0xFFu) << 16) | (((127u - b3) & 0xFFu) << 24);
+    const int h = nrm >> 1, qd = h / 255, r = h - 255 * qd;
+    int e = 0;
+    if (lane == 0) e = r;
+    else e = min(255, max(0, qd - 255 * (lane - 1)));
+    qrow[TC_DIM + lane] = lane == 0 ? 1 : 255;
+    trow[TC_DIM + lane] = static_cast<uint8_t>(e);
+    if (lane == 0) {
+      qoff[row] = nrm - 254 * sum;
+      if (qd > 31 * 255) atomicOr(not_integral, 2);
+    }
+  }
 
   __half2 q01 = __floats2half2_rn(-2.f * v[0], -2.f * v[1]);
   __half2 q23 = __floats2half2_rn(-2.f * v[2], -2.f * v[3]);
@@ -74,10 +106,10 @@ pack_sift_kernel(const float* __restrict__ raw_f32, const uint8_t* __restrict__ 
 
 cudaError_t launch_pack_sift(const float* raw_f32, const uint8_t* raw_u8, int n, __half* qf,
                              __half* tf, int32_t* qnorm, float* raw_out, uint32_t* u8_out,
-                             int* not_integral, cudaStream_t st) {
+                             int* not_integral, uint8_t* iq, uint8_t* it, int32_t* qoff, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   pack_sift_kernel<<<(n + 7) / 8, 256, 0, st>>>(raw_f32, raw_u8, n, qf, tf, qnorm, raw_out, u8_out,
-                                                not_integral);
+                                                not_integral, iq, it, qoff);
   return cudaGetLastError();
 }
 

@@ -375,7 +375,7 @@ def test_full_size_8192_pair(kind):
 # ---------------------------------------------------------------------------------------------
 # values-only tensor epilogue + fix-up (the default batched path) vs the general kernels
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("flags", [0, 128, 256])
+@pytest.mark.parametrize("flags", [0, 2048, 128, 256])
 @pytest.mark.parametrize("mode", [api.UNIQUE_FIRST_WINS, api.MUTUAL_NN, api.UNIQUE_NONE])
 def test_batched_fast_path_equals_oracle_all_modes(mode, flags):
     w = synth.World("sift", 900, seed=33)
@@ -405,9 +405,9 @@ def test_batched_fast_path_equals_general_kernel_full_size():
     w = synth.World("sift", 8192, seed=0xB200 + 2)
     imgs = [w.image(i, 100, outlier_frac=0.3 if i == 2 else 0.0)[:2] for i in range(6)]
     outs = []
-    # values-only kernels (CTA pair 256-col = default, single-CTA, pair 192-col), general tensor kernels
-    # (single-CTA, CTA pair), fp32 SIMT
-    for flags in (0, 128, 256, 64, 64 + 20, 1):
+    # values-only kernels (byte form on kind::i8 = default, fp16 form: CTA pair 256-col, single-CTA, pair 192-col),
+    # general tensor kernels (single-CTA, CTA pair), fp32 SIMT
+    for flags in (0, 2048, 128, 256, 64, 64 + 20, 1):
         with api.PairMatcher(debug_flags=flags) as pm:
             for i, (d, xy) in enumerate(imgs):
                 pm.set_image(i, d, xy)
@@ -635,6 +635,90 @@ def test_hamming_tensor_full_size_equals_popc():
         assert np.array_equal(outs[0][k], outs[1][k]), k
     assert outs[0]["offsets"][-1] > 10 * 1500
 
+
+
+# ---------------------------------------------------------------------------------------------
+# integer-valued 128-d rows as bytes on kind::i8 (default batched SIFT path) vs the fp16 form and the oracle
+# ---------------------------------------------------------------------------------------------
+FORCE_F16 = 1 << 11
+
+
+def _csr_equal(a, b, keys=("offsets", "q", "t", "inlier", "status", "n_inliers", "ransac_iters", "F")):
+    for k in keys:
+        assert np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("mode", [api.UNIQUE_FIRST_WINS, api.MUTUAL_NN, api.UNIQUE_NONE])
+def test_i8_form_parity_ties_force_rescans(mode):
+    """Tiny value range: many train rows tie in D' = 127*sum(a) - a.b + floor(|b|^2/2) with different parities of
+    |b|^2, and exact duplicates tie completely -- the fix-up must rescan those rows and still match the oracle."""
+    rng = np.random.default_rng(101 + mode)
+    imgs = []
+    for i, n in enumerate((700, 643, 300, 17, 1)):
+        d = rng.integers(0, 3, (n, 128)).astype(np.float32)
+        if n > 400:
+            d[1::7] = d[0]                                     # duplicates of one row all over the image
+            d[5] = 0
+        imgs.append(d)
+    imgs[1][:200] = imgs[0][:200]                              # exact matches (d = 0) between images 0 and 1
+    imgs[1][200:260] = np.minimum(imgs[0][200:260] + (rng.random((60, 128)) < 0.01), 255)   # d^2 = 0..3
+    imgs[1][300] = imgs[0][10]; imgs[1][500] = imgs[0][10]     # d = 0 in three chunks: D' ties, rescan for sure
+    outs = []
+    for flags in (0, FORCE_F16):
+        with api.PairMatcher(unique_mode=mode, batch_pairs=4, do_filter=0, debug_flags=flags) as pm:
+            for i, d in enumerate(imgs):
+                pm.set_image(i, d)
+            outs.append(pm.match_all_pairs())
+            st = pm.stats()
+        if flags == 0:
+            assert st["rerank_overflow"] > 0, st               # the rescan path ran
+    _csr_equal(outs[0], outs[1], ("offsets", "q", "t", "status"))
+    res = outs[0]
+    for p, (i, j) in enumerate(res["pair_ij"]):
+        oi, o2 = orc.knn2_l2(imgs[i], imgs[j])
+        od = np.sqrt(o2).astype(np.float32)
+        bq = orc.best_query(imgs[i], imgs[j]) if mode == api.MUTUAL_NN else None
+        wq, wt = orc.ratio_unique(oi, od, imgs[j].shape[0], 0.7, mode, bq)
+        a, b = res["offsets"][p], res["offsets"][p + 1]
+        assert np.array_equal(res["q"][a:b], wq) and np.array_equal(res["t"][a:b], wt), (mode, i, j)
+    assert res["offsets"][-1] > 100
+
+
+def test_i8_form_norm_limit_and_fallback():
+    """|b|^2 up to 4,032,059 rides in the 31-digit norm block; beyond it the image stays on the fp16 form."""
+    rng = np.random.default_rng(9)
+    def make(n, heavy):
+        d = rng.integers(0, 40, (n, 128)).astype(np.float32)
+        d[:heavy, :62] = 255                                   # 62 * 255^2 = 4,031,550 + small rest
+        d[:heavy, 62:] = rng.integers(0, 2, (heavy, 66))
+        return d
+    a, b = make(500, 40), make(450, 30)
+    b[100:140] = a[60:100]
+    c = a.copy(); c[3, :] = 255                                # one all-255 row: |b|^2 = 8.3 M -> no byte form
+    for imgs in ((a, b), (c, b)):
+        outs = []
+        for flags in (0, FORCE_F16, 1):
+            with api.PairMatcher(do_filter=0, debug_flags=flags) as pm:
+                for i, d in enumerate(imgs):
+                    pm.set_image(i, d)
+                outs.append(pm.match_all_pairs())
+        _csr_equal(outs[0], outs[1], ("offsets", "q", "t", "status"))
+        _csr_equal(outs[0], outs[2], ("offsets", "q", "t", "status"))
+        assert outs[0]["offsets"][-1] >= 40
+
+
+def test_i8_form_full_size_equals_f16_form_with_outliers_and_mutual():
+    w = synth.World("sift", 8192, seed=0xB200 + 7)
+    imgs = [w.image(i, 100, outlier_frac=0.5 if i == 1 else 0.0)[:2] for i in range(4)]
+    for mode in (api.UNIQUE_FIRST_WINS, api.MUTUAL_NN):
+        outs = []
+        for flags in (0, FORCE_F16):
+            with api.PairMatcher(unique_mode=mode, debug_flags=flags) as pm:
+                for i, (d, xy) in enumerate(imgs):
+                    pm.set_image(i, d, xy, dtype=api.DESC_U8 if flags == 0 else None)
+                outs.append(pm.match_all_pairs())
+        _csr_equal(outs[0], outs[1])
+        assert outs[0]["offsets"][-1] > 6 * 800
 
 # ---------------------------------------------------------------------------------------------
 # on-disk cache (SURVEY 8f rank 2): resume from files, identical results
