@@ -56,6 +56,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--debug-flags", type=int, default=0, help="pm_params.debug_flags (kernel variants)")
     ap.add_argument("--batch-pairs", type=int, default=0)
+    ap.add_argument("--dev-ratio", type=float, default=None, help="development: Lowe ratio of the main arm (a tiny value "
+                    "empties the tail kernels and isolates the kNN kernel)")
+    ap.add_argument("--dev-no-filter", action="store_true", help="development: main arm without the epipolar filter")
     return ap.parse_args()
 
 
@@ -286,8 +289,11 @@ def main():
     dim = imgs[0][0].shape[1] * (8 if a.kind == "orb" else 1)
     dt = api.DESC_U8_BITS if a.kind == "orb" else api.DESC_F32
 
+    dev_kw = {}
+    if a.dev_ratio is not None: dev_kw["ratio"] = a.dev_ratio
+    if a.dev_no_filter: dev_kw["do_filter"] = 0
     pm = api.PairMatcher(devices=[local], reserve_keypoints=n_img * a.kp, debug_flags=a.debug_flags,
-                         batch_pairs=a.batch_pairs)
+                         batch_pairs=a.batch_pairs, **dev_kw)
 
     if sharded:
         # sharded extraction: this rank "extracted" images rank, rank + N, ...; descriptors and keypoints are

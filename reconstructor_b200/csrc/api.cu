@@ -263,6 +263,7 @@ struct DeviceCtx {
     PM_CUDA(cudaMemset(d_l2f, 0, 4 * sizeof(unsigned long long)));
     PM_CUDA(tc_configure());
     PM_CUDA(tc2_configure());
+    PM_CUDA(i8x2_configure());
     PM_CUDA(fixup_configure());
     PM_CUDA(l2f_configure());
     PM_CUDA(select_configure());
@@ -635,7 +636,8 @@ struct DeviceCtx {
     //   bit9      values-only CTA-pair kernel in its 64-register build (tail kernels co-resident)
     //   bit11     batched loop keeps the fp16 form (kind::f16) instead of the byte form (kind::i8, default)
     //   bits12-13 kind::i8 kernel: 1 / 2 = timing probes (no matches): TMA + MMA only / + accumulator loads without
-    //             the reduction; 3 = 64-register build (tail kernels co-resident)
+    //             the reduction; 3 = the 64-register build
+    //   bit14     kind::i8: one query row set per cluster (l2_top2_tc2_kernel) instead of two (l2_i8x2_kernel)
     const int code = (prm.debug_flags >> 2) & 7;
     const int fcode = (prm.debug_flags >> 7) & 3;
     const int variant = ((prm.debug_flags >> 1) & 1) ^ 1;
@@ -663,7 +665,9 @@ struct DeviceCtx {
           cudaError_t e = cudaMemsetAsync(oi, 0xFF, sizeof(int2) * static_cast<size_t>(n) * s.stride, knn_stream);
           if (e != cudaSuccess) return e;
         }
-        return launch_l2i8_tc2(imaps, jobs_d, n, mq, oi, od, s.stride, num_sms, i8_probe, knn_stream);
+        if ((prm.debug_flags >> 14) & 1)
+          return launch_l2i8_tc2(imaps, jobs_d, n, mq, oi, od, s.stride, num_sms, i8_probe, knn_stream);
+        return launch_l2i8x2(imaps, jobs_d, n, mq, oi, od, s.stride, num_sms, i8_probe, knn_stream);
       }
       if (use_fast) {
         if (fcode == 1) return launch_l2_tc(maps, qnorm, jobs_d, n, mq, oi, od, s.stride, num_sms, nullptr, 5, knn_stream);

@@ -56,6 +56,11 @@ cudaError_t launch_l2_tc2(const TcMaps& maps, const int32_t* qnorm, const PairJo
 // tensor maps over rows of TC_I8_ROW bytes.  counters: [0] rows re-evaluated, [2] rows rescanned exhaustively.
 cudaError_t launch_l2i8_tc2(const TcMaps& maps, const PairJob* jobs, int n_jobs, int max_nq, int2* idx, float2* dist,
                             int stride, int num_sms, int probe, cudaStream_t st);
+// two query row sets per cluster: half the L2 traffic of launch_l2i8_tc2 (l2_tc2.cu, l2_i8x2_kernel).
+// variant: 0 = product (72-register build), 1 / 2 = timing probes, 3 = 64-register build
+cudaError_t i8x2_configure();
+cudaError_t launch_l2i8x2(const TcMaps& maps, const PairJob* jobs, int n_jobs, int max_nq, int2* idx, float2* dist,
+                          int stride, int num_sms, int variant, cudaStream_t st);
 cudaError_t launch_l2_fixup_i8(const uint32_t* u8desc, const int32_t* qnorm, const int32_t* qoff, const PairJob* jobs,
                                int n_jobs, int max_nq, int2* idx, float2* dist, int stride, float ratio, int all_rows,
                                unsigned long long* counters, cudaStream_t st);

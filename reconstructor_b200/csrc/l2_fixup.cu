@@ -170,6 +170,53 @@ __device__ __forceinline__ unsigned int fx_chunk_key(uint32_t* st, const uint32_
 
 static constexpr int FXI_INF = 0x7f800000;   // T2I_INF of l2_tc2.cu
 
+// Two-stage evaluation of a 32-column chunk (one warp, lane l owns column cb + l).  Stage 1 reads only the first
+// 32 of the 128 bytes of every candidate row and forms the partial distance over those 32 dimensions, a lower
+// bound of the full one.  With d1_hi = the largest value the nearest distance can take (the tensor kernel left
+// it up to one unit), a candidate is dropped when its partial distance exceeds d1_hi AND Lowe's test passes even
+// with d1_hi against that partial distance: such a column can neither be the nearest nor make the test fail, so
+// the outcome of the test and the nearest index computed from the survivors are exact (the stored second
+// distance may then be larger than the true one -- only its comparison is used downstream).  When every nearest
+// index is wanted (all_rows) only the first condition applies.  Stage 2 evaluates the survivors in full, one
+// coalesced 128-byte row at a time.  Typical SIFT row with a true match: 1 survivor, 1.1 KB read instead of 4 KB.
+#ifndef PM_I8_PREFIX
+#define PM_I8_PREFIX 1
+#endif
+__device__ __forceinline__ unsigned int fx_chunk_key_prefix(const uint32_t* __restrict__ u8desc,
+                                                            const int32_t* __restrict__ qnorm, const PairJob& jb,
+                                                            int cb, int l, uint32_t qw, const uint32_t* qs, int na,
+                                                            int d1_hi, float ratio, int all_rows) {
+  const int ncol = min(32, jb.nt - cb);
+  const uint32_t* trow = u8desc + (static_cast<size_t>(jb.t_row) + cb) * 32;
+  uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0;
+  if (l < ncol) {
+    const uint4* bp = reinterpret_cast<const uint4*>(trow + l * 32);
+    b0 = __ldg(bp); b1 = __ldg(bp + 1);
+  }
+  const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(qs)), a1 = __ldg(reinterpret_cast<const uint4*>(qs) + 1);
+  unsigned int pa = 0, pb = 0, pab = 0;
+#define PM_FX_W(A, B) pa = __dp4a(A, A, pa); pb = __dp4a(B, B, pb); pab = __dp4a(A, B, pab);
+  PM_FX_W(a0.x, b0.x) PM_FX_W(a0.y, b0.y) PM_FX_W(a0.z, b0.z) PM_FX_W(a0.w, b0.w)
+  PM_FX_W(a1.x, b1.x) PM_FX_W(a1.y, b1.y) PM_FX_W(a1.z, b1.z) PM_FX_W(a1.w, b1.w)
+#undef PM_FX_W
+  const int part = static_cast<int>(pa + pb) - 2 * static_cast<int>(pab);
+  bool surv = l < ncol;
+  if (surv && part > d1_hi)
+    surv = !all_rows && !(__fsqrt_rn(static_cast<float>(d1_hi)) < __fmul_rn(ratio, __fsqrt_rn(static_cast<float>(part))));
+  unsigned int alive = __ballot_sync(0xffffffffu, surv);
+  unsigned int key = 0xFFFFFFFFu;
+  while (alive) {
+    const int j = __ffs(alive) - 1;
+    alive &= alive - 1;
+    const uint32_t w = __ldg(trow + j * 32 + l);
+    const unsigned int dot = __reduce_add_sync(0xffffffffu, __dp4a(qw, w, 0u));
+    if (l == j)
+      key = (static_cast<unsigned int>(na + qnorm[jb.t_row + cb + j] - 2 * static_cast<int>(dot)) << 5) |
+            static_cast<unsigned int>(l);
+  }
+  return key;
+}
+
 template <int CH>
 __global__ void __launch_bounds__(FX_WARPS * 32)
 l2_fixup_i8_kernel(const uint32_t* __restrict__ u8desc, const int32_t* __restrict__ qnorm,
@@ -222,7 +269,13 @@ l2_fixup_i8_kernel(const uint32_t* __restrict__ u8desc, const int32_t* __restric
     const int na = qnorm[jb.q_row + row];
     const uint32_t* qs = u8desc + (static_cast<size_t>(jb.q_row) + row) * 32;
     const uint32_t q0 = __ldg(qs + l), q1 = CH == 16 ? __ldg(qs + 16 + l) : 0u;
-    const unsigned int key = fx_chunk_key<CH>(st, u8desc, qnorm, jb, cb, l, gmask, q0, q1, na);
+    unsigned int key;
+    if (CH == 32 && PM_I8_PREFIX) {
+      const int m1 = __float_as_int(knn_dist[base + row].x);
+      key = fx_chunk_key_prefix(u8desc, qnorm, jb, cb, l, q0, qs, na, qoff[jb.q_row + row] + 2 * m1 + 1, ratio, all_rows);
+    } else {
+      key = fx_chunk_key<CH>(st, u8desc, qnorm, jb, cb, l, gmask, q0, q1, na);
+    }
     const unsigned int k1 = __reduce_min_sync(gmask, key);
     const unsigned int k2 = __reduce_min_sync(gmask, key == k1 ? 0xFFFFFFFFu : key);
     const int d1 = static_cast<int>(k1 >> 5);

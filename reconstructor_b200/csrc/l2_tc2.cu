@@ -53,7 +53,8 @@ static constexpr uint32_t T2_PEER_MASK = 0xFEFFFFFFu;     // clears the CTA-rank
 template <int BN, int CPW, int KA = 2>
 struct T2Cfg {
   static constexpr int kBN = BN, kBNH = BN / 2, kCPW = CPW, kKA = KA;
-  static constexpr int kATile = KA * T2_ATOM + T2_EXT;          // query tile of one CTA (36 / 68 KB)
+  static constexpr int kATile = KA * T2_ATOM + T2_EXT;          // query tile of one CTA (20 / 36 / 68 KB)
+  static constexpr int kAStages = KA == 1 ? 2 : 1;              // the short byte form prefetches the next item's tile
   static constexpr int kSlices = BN / (32 * CPW);
   static constexpr int kEpiWarps = 4 * kSlices;
   static constexpr int kThreads = 128 + 32 * kEpiWarps;
@@ -66,7 +67,7 @@ struct T2Cfg {
   static constexpr int kStages = KA == 4 ? 3 : (KA == 1 ? 6 : (BN == 256 ? 3 : 4));
   static constexpr int kSmemB = kStages * kBTile;
   static constexpr int kXchg = 4 * (kSlices - 1) * 32 * 32;   // two float4 per (quarter, slice, lane)
-  static constexpr int kSmemBytes = kATile + kSmemB + 1024 + 256 + kXchg;
+  static constexpr int kSmemBytes = kAStages * kATile + kSmemB + 1024 + 256 + kXchg;
   // kind::f16: D=f32, A=B=f16, K-major, N=BN, M=256 (pair)
   static constexpr uint32_t kShape = ((BN >> 3) << 17) | ((T2_ROWS >> 4) << 24);
   static constexpr uint32_t kIdesc = (1u << 4) | kShape;
@@ -343,7 +344,7 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
   // the epilogue keeps the 6 smallest 16-column chunk minima as keys (score with the chunk id in the low
   // 10 mantissa bits) and l2f_fixup.cu re-ranks exactly in fp32.  qnorm is unused in that mode.
   constexpr int T2_BN = Cfg::kBN, T2_BNH = Cfg::kBNH, T2_STAGES = Cfg::kStages, T2_SMEM_B = Cfg::kSmemB;
-  constexpr int KA = Cfg::kKA, T2_TILE = Cfg::kATile, T2_SMEM_A = Cfg::kATile;
+  constexpr int KA = Cfg::kKA, T2_TILE = Cfg::kATile, T2_SMEM_A = Cfg::kAStages * Cfg::kATile, AST = Cfg::kAStages;
   constexpr int KEL = KIND >= 1 ? 128 : 64;        // tensor-map elements per 128-byte K atom (bytes / fp16)
   constexpr int AG = Cfg::kAG;
   static_assert(KIND != 2 || MODE == 2 || MODE == 1 || MODE == 5, "the i8 form has a values-only epilogue");
@@ -358,11 +359,11 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
   uint8_t* sA = smem;
   uint8_t* sB = smem + T2_SMEM_A;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T2_SMEM_A + T2_SMEM_B);
-  uint64_t* a_full = bars + 0;                       // leader: 1 arrival + 2 x 36 KB of tx
-  uint64_t* a_empty = bars + 1;                      // both: multicast commit
-  uint64_t* b_full = bars + 2;                       // [STAGES] leader
-  uint64_t* b_empty = bars + 2 + T2_STAGES;          // [STAGES] both
-  uint64_t* acc_full = bars + 2 + 2 * T2_STAGES;     // [2] both: multicast commit
+  uint64_t* a_full = bars + 0;                       // [2] leader: 1 arrival + 2 x tile of tx
+  uint64_t* a_empty = bars + 2;                      // [2] both: multicast commit
+  uint64_t* b_full = bars + 4;                       // [STAGES] leader
+  uint64_t* b_empty = bars + 4 + T2_STAGES;          // [STAGES] both
+  uint64_t* acc_full = bars + 4 + 2 * T2_STAGES;     // [2] both: multicast commit
   uint64_t* acc_empty = acc_full + 2;                // [2] leader: 32 epilogue warps of the pair
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float4* xchg = reinterpret_cast<float4*>(smem + T2_SMEM_A + T2_SMEM_B + 256);
@@ -374,7 +375,7 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&q_main); tma_prefetch_desc(&q_ext);
     tma_prefetch_desc(&t_main); tma_prefetch_desc(&t_ext);
-    mbar_init(a_full, 1); mbar_init(a_empty, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < T2_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 2 * Cfg::kEpiWarps); }
     fence_mbar_init();
@@ -402,13 +403,15 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
         const int jb = item / tiles_per_job, r = item - jb * tiles_per_job;
         const PairJob job = jobs[jb];
         if (r * T2_ROWS >= job.nq) continue;
-        wait_trap(a_empty, (ai & 1) ^ 1);
-        if (leader) mbar_expect_tx(a_full, 2 * T2_TILE);
         {
+          const uint32_t as = ai % AST, use = ai / AST;
+          wait_trap(&a_empty[as], (use & 1) ^ 1);
+          if (leader) mbar_expect_tx(&a_full[as], 2 * T2_TILE);
+          uint8_t* dstA = sA + as * T2_TILE;
           const int row = job.q_row + r * T2_ROWS + rank * T2_BM;
 #pragma unroll
-          for (int a = 0; a < KA; ++a) tma_load_2d_pair(sA + a * T2_ATOM, &q_main, KEL * a, row, a_full);
-          tma_load_2d_pair(sA + KA * T2_ATOM, &q_ext, KDIM, row, a_full);
+          for (int a = 0; a < KA; ++a) tma_load_2d_pair(dstA + a * T2_ATOM, &q_main, KEL * a, row, &a_full[as]);
+          tma_load_2d_pair(dstA + KA * T2_ATOM, &q_ext, KDIM, row, &a_full[as]);
         }
         ++ai;
         const int n_tiles = (MODE == 1 && PM_PROBE_NOTMA) ? 0 : (job.nt + T2_BN - 1) / T2_BN;
@@ -435,13 +438,15 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
       uint32_t ai = 0, bi = 0, ti = 0;
       constexpr uint32_t HI128 = (1024u >> 4) | (1u << 14) | (2u << 29);
       constexpr uint32_t HI32 = (256u >> 4) | (1u << 14) | (6u << 29);
-      const uint32_t a_lo = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t a_lo0 = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);
       const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (1u << 16);
       for (int item = cluster_id; item < n_items; item += n_clusters) {
         const int jb = item / tiles_per_job, r = item - jb * tiles_per_job;
         const int job_nq = jobs[jb].nq, job_nt = jobs[jb].nt;
         if (r * T2_ROWS >= job_nq) continue;
-        wait_trap(a_full, ai & 1);
+        const uint32_t a_st = ai % AST;
+        wait_trap(&a_full[a_st], (ai / AST) & 1);
+        const uint32_t a_lo = a_lo0 + a_st * (T2_TILE >> 4);
         ++ai;
         const int n_tiles = (job_nt + T2_BN - 1) / T2_BN;
         for (int n = 0; n < n_tiles; ++n, ++ti) {
@@ -472,10 +477,11 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
             __syncwarp();
           }
         }
-        if (elect_one()) umma_commit_pair(a_empty);
+        if (elect_one()) umma_commit_pair(&a_empty[a_st]);
         __syncwarp();
       }
-      if (MODE == 1 && PM_PROBE_NOACC && ai > 0) wait_trap(a_empty, (ai - 1) & 1);   // drain before the dealloc
+      if (MODE == 1 && PM_PROBE_NOACC && ai > 0)     // drain before the dealloc
+        wait_trap(&a_empty[(ai - 1) % AST], ((ai - 1) / AST) & 1);
     }
   } else if (warp >= 4) {
     // ======================================= epilogue (both CTAs) =============================
@@ -750,6 +756,279 @@ cudaError_t launch_ham_tc2(const TcMaps& maps, int words, const int32_t* qnorm, 
         maps.q_main, maps.q_ext, maps.t_main, maps.t_ext, qnorm, jobs, n_jobs, tiles_per_job, idx, dist, stride, nullptr);
   else
     return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+
+// =========================================================================================================
+// K2-i8x2: the byte form with TWO query row sets per cluster.  The one-set kernel above streams the whole
+// train image (8192 x 160 B = 1.3 MB) through L2 once per 256 query rows: 42 MB per pair, 7-8 TB/s at the
+// rate kind::i8 consumes it -- measured, that is the L2 ceiling of this GPU, and the tensor pipe waits.
+// Here a work item is 512 query rows: each CTA keeps TWO resident 128-row query tiles and every train tile
+// is multiplied with both (set 0 -> accumulator stage 0, set 1 -> stage 1), so L2 traffic per pair halves.
+// The two accumulator stages are double-buffered by construction: the epilogue reduces stage 0 while the
+// MMAs of set 1 run, and vice versa.  Everything else as in l2_top2_tc2_kernel<T2I8, 2, *, 2>.
+//   smem per CTA: query tiles 2 items x 2 sets x 20 KB, train ring 4 x 20 KB, barriers, slice exchange.
+// MODE 2: product; 1: TMA + MMA only; 5: + tcgen05.ld without the reduction (timing probes, no results).
+struct I8X2 {
+  static constexpr int kBN = 256, kBNH = 128, kSets = 2, kAStages = 2, kStages = 4;
+  static constexpr int kTile = T2_ATOM + T2_EXT;                 // 20 KB: 128 rows x (128 + 32) B
+  static constexpr int kSmemA = kAStages * kSets * kTile;        // 80 KB
+  static constexpr int kBTile = kBNH * 128 + kBNH * 32;          // 20 KB
+  static constexpr int kSmemB = kStages * kBTile;                // 80 KB
+  static constexpr int kSlices = 4, kEpiWarps = 16, kThreads = 128 + 32 * kEpiWarps;
+  static constexpr int kXchg = 4 * (kSlices - 1) * 32 * 32;
+  static constexpr int kSmemBytes = kSmemA + kSmemB + 1024 + 256 + kXchg;
+  static constexpr int kRows = kSets * T2_ROWS;                  // 512 query rows per work item
+  static constexpr uint32_t kShape = ((kBN >> 3) << 17) | ((T2_ROWS >> 4) << 24);
+  static constexpr uint32_t kIdesc = (2u << 4) | (1u << 10) | kShape;      // D = s32, A = u8, B = s8
+  static constexpr uint32_t kIdescExt = (2u << 4) | kShape;                // norm block: A = B = u8
+};
+
+template <int MODE, bool LEAN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LEAN ? 1024 : I8X2::kThreads, 1)
+l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant__ CUtensorMap q_ext,
+               const __grid_constant__ CUtensorMap t_main, const __grid_constant__ CUtensorMap t_ext,
+               const PairJob* __restrict__ jobs, int n_jobs, int blocks_per_job, int2* __restrict__ knn_idx,
+               float2* __restrict__ knn_dist, int stride) {
+  using C = I8X2;
+  constexpr int BN = C::kBN, BNH = C::kBNH, ST = C::kStages, TILE = C::kTile, BTILE = C::kBTile, NSL = C::kSlices;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + C::kSmemA;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kSmemA + C::kSmemB);
+  uint64_t* a_full = bars + 0;                       // [2] leader
+  uint64_t* a_empty = bars + 2;                      // [2] both (multicast commit)
+  uint64_t* b_full = bars + 4;                       // [ST] leader
+  uint64_t* b_empty = bars + 4 + ST;                 // [ST] both
+  uint64_t* acc_full = bars + 4 + 2 * ST;            // [2] both; stage = row set
+  uint64_t* acc_empty = acc_full + 2;                // [2] leader: 32 epilogue warps of the pair
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float4* xchg = reinterpret_cast<float4*>(smem + C::kSmemA + C::kSmemB + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&q_main); tma_prefetch_desc(&q_ext);
+    tma_prefetch_desc(&t_main); tma_prefetch_desc(&t_ext);
+    for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < ST; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 2 * C::kEpiWarps); }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(T2_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_items = n_jobs * blocks_per_job;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ===================================== TMA producer (both CTAs) ==========================
+    if (lane == 0) {
+      uint32_t ai = 0, bi = 0;
+      for (int item = cluster_id; item < n_items; item += n_clusters) {
+        const int jb = item / blocks_per_job, blk = item - jb * blocks_per_job;
+        const PairJob job = jobs[jb];
+        if (blk * C::kRows >= job.nq) continue;
+        const int nset = blk * C::kRows + T2_ROWS < job.nq ? 2 : 1;
+        {
+          const uint32_t as = ai & 1, use = ai >> 1;
+          wait_trap(&a_empty[as], (use & 1) ^ 1);
+          if (leader) mbar_expect_tx(&a_full[as], nset * 2 * TILE);
+          for (int set = 0; set < nset; ++set) {
+            uint8_t* dst = sA + (as * 2 + set) * TILE;
+            const int row = job.q_row + blk * C::kRows + set * T2_ROWS + rank * T2_BM;
+            tma_load_2d_pair(dst, &q_main, 0, row, &a_full[as]);
+            tma_load_2d_pair(dst + T2_ATOM, &q_ext, TC_DIM, row, &a_full[as]);
+          }
+        }
+        ++ai;
+        const int n_tiles = (job.nt + BN - 1) / BN;
+        for (int n = 0; n < n_tiles; ++n, ++bi) {
+          const int row = job.t_row + n * BN + rank * BNH;        // this CTA's half of the train tile
+          const uint32_t st = bi % ST;
+          wait_trap(&b_empty[st], ((bi / ST) & 1) ^ 1);
+          if (leader) mbar_expect_tx(&b_full[st], 2 * BTILE);
+          uint8_t* dst = sB + st * BTILE;
+          tma_load_2d_pair(dst, &t_main, 0, row, &b_full[st]);
+          tma_load_2d_pair(dst + BNH * 128, &t_ext, TC_DIM, row, &b_full[st]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ====================================== MMA issuer (leader CTA) ===========================
+    if (leader) {
+      uint32_t ai = 0, bi = 0, use[2] = {0, 0};
+      constexpr uint32_t HI128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+      constexpr uint32_t HI32 = (256u >> 4) | (1u << 14) | (6u << 29);
+      const uint32_t a_lo0 = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (1u << 16);
+      for (int item = cluster_id; item < n_items; item += n_clusters) {
+        const int jb = item / blocks_per_job, blk = item - jb * blocks_per_job;
+        const int job_nq = jobs[jb].nq, job_nt = jobs[jb].nt;
+        if (blk * C::kRows >= job_nq) continue;
+        const int nset = blk * C::kRows + T2_ROWS < job_nq ? 2 : 1;
+        const uint32_t a_st = ai & 1;
+        wait_trap(&a_full[a_st], (ai >> 1) & 1);
+        ++ai;
+        const int n_tiles = (job_nt + BN - 1) / BN;
+        for (int n = 0; n < n_tiles; ++n, ++bi) {
+          const uint32_t st = bi % ST;
+          wait_trap(&b_full[st], (bi / ST) & 1);
+          const uint32_t b_lo = b_lo0 + st * (BTILE >> 4);
+          for (int set = 0; set < nset; ++set) {
+            wait_trap(&acc_empty[set], (use[set] & 1) ^ 1);
+            ++use[set];
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t d_tmem = tmem_base + set * BN;
+              const uint32_t a_lo = a_lo0 + (a_st * 2 + set) * (TILE >> 4);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16_pair<2>(d_tmem, (static_cast<uint64_t>(HI128) << 32) | (a_lo + ((k * 32) >> 4)),
+                                 (static_cast<uint64_t>(HI128) << 32) | (b_lo + ((k * 32) >> 4)), C::kIdesc, k > 0 ? 1u : 0u);
+              umma_f16_pair<2>(d_tmem, (static_cast<uint64_t>(HI32) << 32) | (a_lo + (T2_ATOM >> 4)),
+                               (static_cast<uint64_t>(HI32) << 32) | (b_lo + ((BNH * 128) >> 4)), C::kIdescExt, 1u);
+              umma_commit_pair(&acc_full[set]);
+              if (set == nset - 1) umma_commit_pair(&b_empty[st]);
+            }
+            __syncwarp();
+          }
+        }
+        if (elect_one()) umma_commit_pair(&a_empty[a_st]);
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    // ======================================= epilogue (both CTAs) =============================
+    const int quarter = warp & 3, slice = (warp - 4) >> 2;       // 64-column slice of the tile
+    uint32_t use[2] = {0, 0};
+    const uint32_t tq = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + slice * 64;
+    for (int item = cluster_id; item < n_items; item += n_clusters) {
+      const int jb = item / blocks_per_job, blk = item - jb * blocks_per_job;
+      const PairJob job = jobs[jb];
+      if (blk * C::kRows >= job.nq) continue;
+      const int nset = blk * C::kRows + T2_ROWS < job.nq ? 2 : 1;
+      Top2i s0, s1;
+      s0.m1 = s0.m2 = s1.m1 = s1.m2 = T2I_INF;
+      s0.i1 = s1.i1 = -1;
+      const int n_tiles = (job.nt + BN - 1) / BN;
+      for (int n = 0; n < n_tiles; ++n) {
+        const int c0 = n * BN + slice * 64;
+        const int lim = job.nt - c0;
+#pragma unroll
+        for (int set = 0; set < 2; ++set) {
+          if (set < nset) {
+            wait_trap(&acc_full[set], use[set] & 1);
+            ++use[set];
+            tc_fence_after();
+            if (MODE == 1) {
+              tc_fence_before();
+              if (lane == 0) mbar_arrive_leader(&acc_empty[set]);
+            } else {
+              uint32_t v[32];
+              tmem_ld_32x32b_x32(tq + set * BN, v);
+              if (MODE == 2) t2i_chunk32(set ? s1 : s0, v, c0, lim);
+              tmem_ld_32x32b_x32(tq + set * BN + 32, v);
+              tc_fence_before();
+              if (lane == 0) mbar_arrive_leader(&acc_empty[set]);
+              if (MODE == 2) t2i_chunk32(set ? s1 : s0, v, c0 + 32, lim - 32);
+            }
+          }
+        }
+      }
+      // merge the column slices of this lane quarter (slices 1.. publish, slice 0 merges), one row set at a time
+      if (MODE == 2) {
+        float4* slot = xchg + ((quarter * (NSL - 1)) * 64 + lane);
+        const int bar_id = 1 + quarter;
+#pragma unroll
+        for (int set = 0; set < 2; ++set) {
+          if (set < nset) {
+            Top2i& s = set ? s1 : s0;
+            if (slice > 0)
+              slot[(slice - 1) * 64] = make_float4(__int_as_float(s.m1), __int_as_float(s.i1), __int_as_float(s.m2), 0.f);
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NSL) : "memory");
+            if (slice == 0) {
+#pragma unroll
+              for (int o = 0; o < NSL - 1; ++o) {
+                const float4 x = slot[o * 64];
+                const int ob = __float_as_int(x.y), om1 = __float_as_int(x.x), om2 = __float_as_int(x.z);
+                const bool take = ob >= 0 && (s.i1 < 0 || om1 < s.m1 || (om1 == s.m1 && ob < s.i1));
+                const int hi = max(s.m1, om1);
+                s.m2 = min(min(s.m2, om2), hi);
+                s.m1 = min(s.m1, om1);
+                s.i1 = take ? ob : s.i1;
+              }
+              const int row = blk * C::kRows + set * T2_ROWS + rank * T2_BM + quarter * 32 + lane;
+              if (row < job.nq) {
+                const size_t o = static_cast<size_t>(jb) * stride + row;
+                knn_idx[o] = make_int2(s.i1, -3);        // -3: D' values of the i8 form (l2_fixup_i8 follows)
+                knn_dist[o] = make_float2(__int_as_float(s.m1), __int_as_float(s.m2));
+              }
+            }
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NSL) : "memory");
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                // no remote arrive / multicast may still be in flight
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(T2_TMEM_COLS) : "memory");
+  }
+}
+
+template <int MODE, bool LEAN>
+static cudaError_t i8x2_attr() {
+  cudaError_t e = cudaFuncSetAttribute(l2_i8x2_kernel<MODE, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       I8X2::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(l2_i8x2_kernel<MODE, LEAN>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                              cudaSharedmemCarveoutMaxShared);
+}
+cudaError_t i8x2_configure() {
+  cudaError_t e;
+  if ((e = i8x2_attr<2, false>()) != cudaSuccess) return e;
+  if ((e = i8x2_attr<2, true>()) != cudaSuccess) return e;
+  if ((e = i8x2_attr<1, false>()) != cudaSuccess) return e;
+  return i8x2_attr<5, false>();
+}
+
+// variant: 0 = product (72 registers: the tail kernels of earlier batches stay co-resident), 1 = TMA + MMA probe,
+// 2 = + accumulator loads probe, 3 = 64-register build
+cudaError_t launch_l2i8x2(const TcMaps& maps, const PairJob* jobs, int n_jobs, int max_nq, int2* idx, float2* dist,
+                          int stride, int num_sms, int variant, cudaStream_t st) {
+  if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
+  const int blocks_per_job = (max_nq + I8X2::kRows - 1) / I8X2::kRows;
+  const int n_items = n_jobs * blocks_per_job;
+  int clusters = num_sms / 2;
+  if (n_items < clusters) clusters = n_items;
+  const int grid = clusters * 2;
+#define PM_I8X2_LAUNCH(M, L)                                                                                     \
+  l2_i8x2_kernel<M, L><<<grid, I8X2::kThreads, I8X2::kSmemBytes, st>>>(maps.q_main, maps.q_ext, maps.t_main,    \
+                                                                       maps.t_ext, jobs, n_jobs, blocks_per_job, \
+                                                                       idx, dist, stride)
+  if (variant == 1) PM_I8X2_LAUNCH(1, false);
+  else if (variant == 2) PM_I8X2_LAUNCH(5, false);
+  else if (variant == 3) PM_I8X2_LAUNCH(2, true);
+  else PM_I8X2_LAUNCH(2, false);
+#undef PM_I8X2_LAUNCH
   return cudaGetLastError();
 }
 
