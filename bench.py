@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--outlier-frac", type=float, default=0.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sync-ingest", action="store_true", help="e2e leg: pm_set_image instead of pm_set_image_async")
     ap.add_argument("--no-stages", action="store_true", help="skip the matcher-only / RANSAC attribution pass")
     ap.add_argument("--sharded-ingest", action="store_true",
                     help="N>1: every rank owns images k = rank mod N, descriptors are all-gathered over NCCL and "
@@ -302,10 +303,12 @@ def main():
         x_own = torch.stack([tx for _, tx in pinned]).pin_memory()
         cfg["partition"] += "; extraction sharded by image id mod N, one NCCL all-gather of descriptors + keypoints per step"
 
-    def ingest():
+    def ingest(asynchronous=False):
         if not sharded:
+            # asynchronous: pm_set_image_async from pinned buffers -- the uploads are queued and the first batches
+            # of pm_match_all_pairs run while the later images are still on their way (the pair list is ordered)
             for i, (td, tx) in enumerate(pinned):
-                pm.set_image_ptr(i, td.data_ptr(), td.shape[0], dim, dt, tx.data_ptr())
+                pm.set_image_ptr(i, td.data_ptr(), td.shape[0], dim, dt, tx.data_ptr(), asynchronous=asynchronous)
             return
         d_dev = d_own.cuda(non_blocking=True); x_dev = x_own.cuda(non_blocking=True)
         all_d = torch.empty((world,) + tuple(d_dev.shape), dtype=d_dev.dtype, device="cuda")
@@ -435,12 +438,13 @@ def main():
     # ---- e2e: host buffers in, host CSR out, every step ---------------------------------------------
     e2e = None
     if not a.no_e2e:
-        ingest(); r = pm.match_all_pairs(mine, copy=False); pm.free_result(r)      # warm
+        use_async = not a.sync_ingest
+        ingest(use_async); r = pm.match_all_pairs(mine, copy=False); pm.free_result(r)      # warm
         barrier()
         pm.reset_stats()
         t0 = time.perf_counter()
         for _ in range(a.steps):
-            ingest()
+            ingest(use_async)
             r = pm.match_all_pairs(mine, copy=False)
             _ = int(r["n_inliers"].sum())                     # the step's result is read on the host
             pm.free_result(r)
@@ -451,14 +455,16 @@ def main():
                    h2d_bytes_per_step=int(allsum(st2["h2d_bytes"]) / a.steps) +
                    (int(allsum(d_own.numel() * d_own.element_size() + x_own.numel() * x_own.element_size())) if sharded else 0),
                    d2h_bytes_per_step=int(allsum(st2["d2h_bytes"]) / a.steps),
-                   timing="host wall clock around set_image x images + match_all_pairs, max over ranks")
+                   timing="host wall clock around %s x images + match_all_pairs, max over ranks" %
+                          ("set_image_async" if use_async and not sharded else "set_image"))
         if sharded:
             e2e["allgather_bytes_per_step"] = int(world * (d_own.numel() * d_own.element_size() + x_own.numel() * x_own.element_size()))
 
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=n_gpus, steps=a.steps, warmup=a.warmup,
                     ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype={"sift": "f16 operands / f32 accumulate (exact integers)", "orb": "u32 popc" if (a.debug_flags & 1024) else "e4m3 {0,1} operands / f32 accumulate (exact integers)",
+                    dtype={"sift": "f16 operands / f32 accumulate (exact integers)" if (a.debug_flags & 2048) else
+                           "u8 x s8 operands / s32 accumulate (kind::i8, exact integers)", "orb": "u32 popc" if (a.debug_flags & 1024) else "e4m3 {0,1} operands / f32 accumulate (exact integers)",
                            "superpoint": "f16 operands / f32 accumulate candidates + exact f32 re-rank"}[a.kind],
                     data="synthetic", config=cfg, wall_ms_per_step=wall_ms / a.steps,
                     putative_matches_per_step=matches, inliers_per_step=inliers,

@@ -156,6 +156,16 @@ int pm_set_image(pm_handle h, int img_id, const void* desc, int n, int dim, int 
  * NCCL all-gather of sharded extraction).  Single-device handles only. */
 int pm_set_image_device(pm_handle h, int img_id, const void* d_desc, int n, int dim, int dtype,
                         const int32_t* d_xy);
+/* pm_set_image without the host synchronisation: the upload and the packing kernels are queued on the
+ * handle's ingest stream and the call returns.  desc / xy must stay valid and unchanged until
+ * pm_sync_images() or a matching call that uses the image returns (pinned host memory makes the copy
+ * truly asynchronous, so the first batches of pm_match_all_pairs overlap the upload of later images;
+ * pageable memory is staged by the driver and behaves like pm_set_image).  pm_match_all_pairs(ALL)
+ * visits every image against all earlier ones, so early batches need only the first images. */
+int pm_set_image_async(pm_handle h, int img_id, const void* desc, int n, int dim, int dtype,
+                       const int32_t* xy);
+/* Waits until every asynchronously ingested image is resident. */
+int pm_sync_images(pm_handle h);
 int pm_num_keypoints(pm_handle h, int img_id);
 
 /* Raw 2-NN rows of pair (i -> j): what knnMatch(desc_i, desc_j, 2) returns as DMatch rows

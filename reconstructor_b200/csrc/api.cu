@@ -36,6 +36,11 @@ struct Image {
   bool unit_ok = false;  // finite real-valued rows with |x|^2 <= L2F_MAX_NORM2 and fp16 forms packed
   float maxn = 0.f;      // largest squared row norm
   bool has_xy = false;
+  // asynchronous ingest (pm_set_image_async): the upload + packing kernels are queued on the ingest stream and
+  // the per-image facts (integral? unit norm?) arrive in a pinned record; resolved at first use
+  bool pending = false;
+  cudaEvent_t ready = nullptr;
+  int rec = -1;          // index of the pinned record
 };
 
 constexpr int kTmpA = INT32_MIN, kTmpB = INT32_MIN + 1;
@@ -208,6 +213,9 @@ struct DeviceCtx {
   TcMaps maps{};
   int* d_flag = nullptr;       // not-integral flag
   int* h_flag = nullptr;       // pinned
+  static constexpr int kRecInts = 8, kRecCap = 1 << 16;
+  int* h_recs = nullptr;       // pinned [kRecCap][kRecInts]: {flag, fstats[4]} of asynchronously ingested images
+  int next_rec = 0;
   void* stage = nullptr;       // device staging for u8 uploads
   size_t stage_bytes = 0;
 
@@ -257,6 +265,7 @@ struct DeviceCtx {
     PM_CUDA(cudaEventCreate(&ev_b));
     PM_CUDA(cudaMalloc(&d_flag, sizeof(int)));
     PM_CUDA(cudaMallocHost(&h_flag, sizeof(int)));
+    PM_CUDA(cudaMallocHost(&h_recs, sizeof(int) * kRecInts * kRecCap));
     PM_CUDA(cudaMalloc(&d_fstats, 4 * sizeof(unsigned int)));
     PM_CUDA(cudaMallocHost(&h_fstats, 4 * sizeof(unsigned int)));
     PM_CUDA(cudaMalloc(&d_l2f, 4 * sizeof(unsigned long long)));
@@ -282,6 +291,8 @@ struct DeviceCtx {
     fd(raw); fd(qf); fd(tf); fd(qnorm); fd(u8d); fd(bits); fd(xy); fd(d_flag); fd(stage); fd(d_dump);
     fd(fq); fd(ft); fd(fnorm); fd(d_fstats); fd(d_l2f); fd(hq); fd(ht); fd(iq); fd(it); fd(qoff);
     if (h_flag) cudaFreeHost(h_flag);
+    if (h_recs) cudaFreeHost(h_recs);
+    for (auto& kv : images) if (kv.second.ready) cudaEventDestroy(kv.second.ready);
     if (h_fstats) cudaFreeHost(h_fstats);
     if (ingest) cudaStreamDestroy(ingest);
     if (knn_stream) cudaStreamDestroy(knn_stream);
@@ -419,7 +430,43 @@ struct DeviceCtx {
     return build_maps();
   }
 
-  int set_image(int id, const void* desc, int n, int dim_, int dtype_, const int32_t* xy_, bool on_device) {
+  // Waits for an asynchronously ingested image and reads its facts from the pinned record.
+  int resolve(Image& im) {
+    if (!im.pending) return PM_OK;
+    PM_CUDA(cudaEventSynchronize(im.ready));
+    const int* rec = h_recs + static_cast<size_t>(im.rec) * kRecInts;
+    if (dtype != PM_DESC_U8_BITS && dim == TC_DIM) {
+      im.integral = (rec[0] & 1) == 0;
+      im.i8_ok = rec[0] == 0;
+    }
+    im.pending = false;
+    if (float_tc_shape() && !im.integral) {
+      if (dim == TC_DIM) {
+        // 128-d rows that turned out not to be integer-valued: their fp16 forms were not packed on speculation
+        int* rec2 = h_recs + static_cast<size_t>(im.rec) * kRecInts;
+        const int kp = dim + 16;
+        PM_CUDA(cudaMemsetAsync(d_fstats, 0, 4 * sizeof(unsigned int), ingest));
+        PM_CUDA(launch_pack_float(raw + static_cast<size_t>(im.row) * dim, im.n, dim, fq + static_cast<size_t>(im.row) * kp,
+                                  ft + static_cast<size_t>(im.row) * kp, fnorm + im.row, d_fstats, ingest));
+        ++stats.kernel_launches;
+        PM_CUDA(cudaMemcpyAsync(rec2 + 1, d_fstats, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ingest));
+        PM_CUDA(cudaStreamSynchronize(ingest));
+      }
+      std::memcpy(&im.maxn, &rec[2], sizeof(float));
+      im.unit_ok = rec[3] == 0 && im.maxn <= L2F_MAX_NORM2;
+    }
+    return PM_OK;
+  }
+  int resolve_all() {
+    for (auto& kv : images) {
+      const int rc = resolve(kv.second);
+      if (rc != PM_OK) return rc;
+    }
+    return PM_OK;
+  }
+
+  int set_image(int id, const void* desc, int n, int dim_, int dtype_, const int32_t* xy_, bool on_device,
+                bool async = false) {
     PM_CUDA(cudaSetDevice(dev));
     if (n < 0 || dim_ <= 0 || (n > 0 && !desc)) return fail(PM_ERR_INVALID, "set_image: bad arguments");
     if (dtype_ != PM_DESC_F32 && dtype_ != PM_DESC_U8_BITS && dtype_ != PM_DESC_U8)
@@ -443,6 +490,8 @@ struct DeviceCtx {
       return fail(PM_ERR_UNSUPPORTED, "binary path packs the train index in 16 bits: n must be <= 65535");
 
     Image& im = images[id];
+    if (im.pending) { const int rc = resolve(im); if (rc != PM_OK) return rc; }
+    if (async && (n == 0 || next_rec >= kRecCap || (dtype == PM_DESC_U8 && dim != TC_DIM))) async = false;
     if (n > im.cap) {
       const int rc = ensure_rows(used_rows + n);
       if (rc != PM_OK) { if (im.cap == 0) images.erase(id); return rc; }
@@ -511,6 +560,27 @@ struct DeviceCtx {
         PM_CUDA(cudaMemcpyAsync(xy + 2 * static_cast<size_t>(im.row), xy_, static_cast<size_t>(n) * 8, kind, ingest));
         if (!on_device) stats.h2d_bytes += static_cast<size_t>(n) * 8;
       }
+    }
+    if (async) {
+      // no host synchronisation: facts go to this image's pinned record, an event marks completion
+      int* rec = h_recs + static_cast<size_t>(next_rec) * kRecInts;
+      rec[0] = 0; rec[1] = rec[2] = rec[3] = rec[4] = 0;
+      if (dtype != PM_DESC_U8_BITS && dim == TC_DIM)
+        PM_CUDA(cudaMemcpyAsync(rec, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ingest));
+      if (float_tc_shape() && dtype == PM_DESC_F32 && dim != TC_DIM) {     // 128-d: packed in resolve() if needed
+        const int kp = dim + 16;
+        PM_CUDA(cudaMemsetAsync(d_fstats, 0, 4 * sizeof(unsigned int), ingest));
+        PM_CUDA(launch_pack_float(raw + static_cast<size_t>(im.row) * dim, n, dim, fq + static_cast<size_t>(im.row) * kp,
+                                  ft + static_cast<size_t>(im.row) * kp, fnorm + im.row, d_fstats, ingest));
+        ++stats.kernel_launches;
+        PM_CUDA(cudaMemcpyAsync(rec + 1, d_fstats, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ingest));
+      }
+      if (!im.ready) PM_CUDA(cudaEventCreateWithFlags(&im.ready, cudaEventDisableTiming));
+      PM_CUDA(cudaEventRecord(im.ready, ingest));
+      im.rec = next_rec++;
+      im.pending = true;
+      stats.n_images = static_cast<int32_t>(images.size());
+      return PM_OK;
     }
     PM_CUDA(cudaStreamSynchronize(ingest));   // caller's buffers are free to change on return
     if (n > 0 && dtype != PM_DESC_U8_BITS && dim == TC_DIM) {
@@ -738,6 +808,11 @@ struct DeviceCtx {
     auto a = images.find(i), b = images.find(j);
     if (a == images.end() || b == images.end())
       return fail(PM_ERR_STATE, "image id %d not set", a == images.end() ? i : j);
+    if (a->second.pending || b->second.pending) {
+      int rc = resolve(a->second);
+      if (rc == PM_OK) rc = resolve(b->second);
+      if (rc != PM_OK) return rc;
+    }
     s.h_jobs[k] = PairJob{a->second.row, b->second.row, a->second.n, b->second.n, a->second.maxn, b->second.maxn};
     if (static_cast<int>(job_integral.size()) <= k) { job_integral.resize(k + 1); job_unit.resize(k + 1); job_i8.resize(k + 1); }
     job_i8[k] = a->second.i8_ok && b->second.i8_ok;
@@ -977,6 +1052,29 @@ int pm_set_image(pm_handle h, int img_id, const void* desc, int n, int dim, int 
   return PM_OK;
 }
 
+int pm_set_image_async(pm_handle h, int img_id, const void* desc, int n, int dim, int dtype, const int32_t* xy) {
+  if (!h) return PM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (img_id == kTmpA || img_id == kTmpB) return h->fail(PM_ERR_INVALID, "reserved image id");
+  for (auto& d : h->devs) {
+    const int rc = d->set_image(img_id, desc, n, dim, dtype, xy, false, true);
+    if (rc != PM_OK) return h->from(*d, rc);
+  }
+  return PM_OK;
+}
+
+int pm_sync_images(pm_handle h) {
+  if (!h) return PM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  for (auto& d : h->devs) {
+    if (cudaSetDevice(d->dev) != cudaSuccess) return h->fail(PM_ERR_CUDA, "cudaSetDevice failed");
+    const int rc = d->resolve_all();
+    if (rc != PM_OK) return h->from(*d, rc);
+    if (cudaStreamSynchronize(d->ingest) != cudaSuccess) return h->fail(PM_ERR_CUDA, "ingest stream failed");
+  }
+  return PM_OK;
+}
+
 int pm_set_image_device(pm_handle h, int img_id, const void* d_desc, int n, int dim, int dtype,
                         const int32_t* d_xy) {
   if (!h) return PM_ERR_INVALID;
@@ -1135,8 +1233,11 @@ int pm_match_all_pairs(pm_handle h, const int32_t* pairs, int64_t n_pairs, pm_cs
     for (auto& kv : h->devs[0]->images)
       if (kv.first != kTmpA && kv.first != kTmpB) ids.push_back(kv.first);
     std::sort(ids.begin(), ids.end());
-    for (size_t a = 0; a < ids.size(); ++a)
-      for (size_t b = a + 1; b < ids.size(); ++b) { R->pair_ij.push_back(ids[a]); R->pair_ij.push_back(ids[b]); }
+    // every image against all EARLIER ones (query = lower id as at SequentialReconstructor.cpp:203-227): the first
+    // batches touch only the first few images, so they overlap the upload of the rest (pm_set_image_async), and
+    // consecutive pairs share their train image
+    for (size_t b = 1; b < ids.size(); ++b)
+      for (size_t a = 0; a < b; ++a) { R->pair_ij.push_back(ids[a]); R->pair_ij.push_back(ids[b]); }
     n_pairs = static_cast<int64_t>(R->pair_ij.size() / 2);
   } else {
     if (n_pairs < 0) return h->fail(PM_ERR_INVALID, "n_pairs < 0");

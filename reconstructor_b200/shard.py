@@ -19,8 +19,10 @@ def images_for_world(world: int, base_images: int = 100) -> int:
 
 def all_pairs(n_images: int) -> np.ndarray:
     """Canonical pair list, query = lower image id (SequentialReconstructor.cpp:203-227 run
-    sequentially visits (i,j), i<j first and mirrors (j,i))."""
-    i, j = np.triu_indices(n_images, k=1)
+    sequentially visits (i,j), i<j first and mirrors (j,i)).  Order: every image against all earlier
+    ones -- (0,1), (0,2), (1,2), (0,3), ... -- so that the first batches need only the first few images
+    (they overlap the asynchronous upload of the rest) and consecutive pairs share their train image."""
+    j, i = np.tril_indices(n_images, k=-1)
     return np.stack([i, j], axis=1).astype(np.int32)
 
 

@@ -720,6 +720,35 @@ def test_i8_form_full_size_equals_f16_form_with_outliers_and_mutual():
         _csr_equal(outs[0], outs[1])
         assert outs[0]["offsets"][-1] > 6 * 800
 
+
+@pytest.mark.parametrize("kind", ["sift", "orb", "superpoint", "sp128"])
+def test_async_ingest_gives_identical_results(kind):
+    """pm_set_image_async (no host synchronisation per image; facts resolved at first use) == pm_set_image."""
+    import torch
+    w = synth.World("superpoint" if kind == "sp128" else kind, 1200, seed=77)
+    imgs = [w.image(i, 6)[:2] for i in range(6)]
+    if kind == "sp128":                                        # real-valued 128-d rows: fp16 forms packed at first use
+        imgs = [(np.ascontiguousarray(d[:, :128] / np.linalg.norm(d[:, :128], axis=1, keepdims=True)).astype(np.float32), xy)
+                for d, xy in imgs]
+    pinned = [(torch.from_numpy(np.ascontiguousarray(d)).pin_memory(),
+               torch.from_numpy(np.ascontiguousarray(xy, dtype=np.int32)).pin_memory()) for d, xy in imgs]
+    dim = imgs[0][0].shape[1] * (8 if kind == "orb" else 1)
+    dt = api.DESC_U8_BITS if kind == "orb" else api.DESC_F32
+    outs = []
+    for asyn in (False, True):
+        with api.PairMatcher(batch_pairs=4) as pm:
+            for rep in range(2):                               # re-ingest over resident images too
+                for i, (td, tx) in enumerate(pinned):
+                    pm.set_image_ptr(i, td.data_ptr(), td.shape[0], dim, dt, tx.data_ptr(), asynchronous=asyn)
+                if rep == 0 and asyn:
+                    pm.sync_images()
+            outs.append(pm.match_all_pairs())
+            i1, d1 = pm.knn_pair(0, 1)
+            outs[-1]["knn"] = (i1, d1)
+    _csr_equal(outs[0], outs[1])
+    assert np.array_equal(outs[0]["knn"][0], outs[1]["knn"][0]) and np.array_equal(outs[0]["knn"][1], outs[1]["knn"][1])
+    assert outs[0]["offsets"][-1] > (15 * 200 if kind != "sp128" else 15 * 50)
+
 # ---------------------------------------------------------------------------------------------
 # on-disk cache (SURVEY 8f rank 2): resume from files, identical results
 # ---------------------------------------------------------------------------------------------
