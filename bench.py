@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--sync-ingest", action="store_true", help="e2e leg: pm_set_image instead of pm_set_image_async")
     ap.add_argument("--no-stages", action="store_true", help="skip the matcher-only / RANSAC attribution pass")
+    ap.add_argument("--replicated-ingest", action="store_true", help="N > 1: every rank uploads every image from its own "
+                    "host copy instead of the sharded upload + all-gather")
     ap.add_argument("--sharded-ingest", action="store_true",
                     help="N>1: every rank owns images k = rank mod N, descriptors are all-gathered over NCCL and "
                          "ingested from device memory (the exchange step of sharded extraction, SURVEY 8e)")
@@ -234,7 +236,10 @@ def main():
     # ---- CPU baseline first (fork before any CUDA context exists), rank 0 at N=1 only -----------
     cpu = None
     w = synth.World(a.kind, a.kp, seed=0xB200 + 2)
-    sharded = a.sharded_ingest and world > 1
+    # N > 1: every rank uploads only its own share of the images and the rest arrives by one NCCL all-gather over
+    # NVLink (the exchange step of sharded extraction) -- replicating the upload would push the whole
+    # descriptor set through every rank's PCIe link each step (measured at N = 8: 24 ms of a 73 ms e2e step)
+    sharded = world > 1 and not a.replicated_ingest
     n_local = -(-n_img // world)                       # images per rank when extraction is sharded
     own_ids = list(range(rank, n_local * world, world)) if sharded else list(range(n_img))
     imgs = [w.image(i, n_img, a.outlier_frac)[:2] for i in own_ids]
@@ -320,7 +325,10 @@ def main():
             for r in range(world):
                 img = slot * world + r
                 if img < n_img:
-                    pm.set_image_ptr(img, all_d[r, slot].data_ptr(), a.kp, dim, dt, all_x[r, slot].data_ptr(), on_device=True)
+                    pm.set_image_ptr(img, all_d[r, slot].data_ptr(), a.kp, dim, dt, all_x[r, slot].data_ptr(), on_device=True,
+                                     asynchronous=asynchronous)
+        if asynchronous:
+            pm.sync_images()            # all_d / all_x go out of scope on return
 
     ingest()
     for _ in range(a.warmup):
@@ -378,7 +386,16 @@ def main():
                     peak_source="MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if pk
                     else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)")
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof["kernel"] = {"sift": "l2_top2_tc2_kernel", "orb": "hamming_top2_kernel" if (a.debug_flags & 1024) else "l2_top2_tc2_kernel<T2Cfg<256,2,2>,2,false,1>", "superpoint": "l2_top2_tc2_kernel<T2Cfg<256,2,4>,3>"}[a.kind]
+    if a.kind == "sift" and not (a.debug_flags & 2048):
+        roof["operands"] = ("int8 (tcgen05 kind::i8, u8 x s8 -> s32): the MMA rate of this kind is 2 x the bf16 rate the peak "
+                            "is quoted in, so frac can reach 2; ncu: tensor pipe (imma) active 90.4 % of elapsed "
+                            "(profiles/r01_i8x2_kernel_ncu_full.md)")
+        roof["frac_of_int8_peak"] = roof["frac"] / 2.0
+    if a.kind == "superpoint" and not (a.debug_flags & 32768):
+        roof["operands"] = ("int8 (tcgen05 kind::i8, rows quantised to s8 for the candidate stage; exact fp32 re-rank follows): "
+                            "2 x the bf16 MMA rate the peak is quoted in")
+        roof["frac_of_int8_peak"] = roof["frac"] / 2.0
+    roof["kernel"] = {"sift": "l2_top2_tc2_kernel" if (a.debug_flags & (2048 | 16384)) else "l2_i8x2_kernel", "orb": "hamming_top2_kernel" if (a.debug_flags & 1024) else "l2_top2_tc2_kernel<T2Cfg<256,2,2>,2,false,1>", "superpoint": "l2_top2_tc2_kernel<T2Cfg<256,2,4>,3>" if (a.debug_flags & 32768) else "l2_top2_tc2_kernel<T2Cfg<256,2,2>,3,true,3>"}[a.kind]
     roof["launches"] = st["knn_launches"]
     roof["avg_launch_ms"] = st["knn_ms"] / max(st["knn_launches"], 1)
     roof["share_of_step"] = st["knn_ms"] / max(dev_ms, 1e-9) if world == 1 else None
@@ -465,7 +482,8 @@ def main():
                     ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype={"sift": "f16 operands / f32 accumulate (exact integers)" if (a.debug_flags & 2048) else
                            "u8 x s8 operands / s32 accumulate (kind::i8, exact integers)", "orb": "u32 popc" if (a.debug_flags & 1024) else "e4m3 {0,1} operands / f32 accumulate (exact integers)",
-                           "superpoint": "f16 operands / f32 accumulate candidates + exact f32 re-rank"}[a.kind],
+                           "superpoint": "f16 operands / f32 accumulate candidates + exact f32 re-rank" if (a.debug_flags & 32768) else
+                           "s8 operands / s32 accumulate candidates (kind::i8) + exact f32 re-rank"}[a.kind],
                     data="synthetic", config=cfg, wall_ms_per_step=wall_ms / a.steps,
                     putative_matches_per_step=matches, inliers_per_step=inliers,
                     roofline=roof, stages=stages, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks)

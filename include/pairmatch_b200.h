@@ -164,6 +164,9 @@ int pm_set_image_device(pm_handle h, int img_id, const void* d_desc, int n, int 
  * visits every image against all earlier ones, so early batches need only the first images. */
 int pm_set_image_async(pm_handle h, int img_id, const void* desc, int n, int dim, int dtype,
                        const int32_t* xy);
+/* pm_set_image_device without the host synchronisation (same lifetime rule for the device buffers). */
+int pm_set_image_device_async(pm_handle h, int img_id, const void* d_desc, int n, int dim, int dtype,
+                              const int32_t* d_xy);
 /* Waits until every asynchronously ingested image is resident. */
 int pm_sync_images(pm_handle h);
 int pm_num_keypoints(pm_handle h, int img_id);

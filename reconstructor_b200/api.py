@@ -29,7 +29,7 @@ OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_OOM, ERR_STATE, ERR_UNSUPPORTED = 
 
 EXPORTS = [
     "pm_default_params", "pm_create", "pm_destroy", "pm_last_error", "pm_version", "pm_set_image",
-    "pm_set_image_device", "pm_set_image_async", "pm_sync_images", "pm_num_keypoints", "pm_knn_pair", "pm_match_pair",
+    "pm_set_image_device", "pm_set_image_async", "pm_set_image_device_async", "pm_sync_images", "pm_num_keypoints", "pm_knn_pair", "pm_match_pair",
     "pm_match_descriptors", "pm_filter_pair_F", "pm_match_filter_pair", "pm_match_all_pairs",
     "pm_free_result", "pm_get_stats", "pm_reset_stats", "pm_measure_popc_peak",
     "pm_save_images", "pm_load_images", "pm_save_result", "pm_load_result",
@@ -94,6 +94,7 @@ def load_library() -> C.CDLL:
         lib.pm_set_image.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         lib.pm_set_image_device.argtypes = lib.pm_set_image.argtypes
         lib.pm_set_image_async.argtypes = lib.pm_set_image.argtypes
+        lib.pm_set_image_device_async.argtypes = lib.pm_set_image.argtypes
         lib.pm_sync_images.argtypes = [C.c_void_p]
         lib.pm_num_keypoints.argtypes = [C.c_void_p, C.c_int]
         lib.pm_knn_pair.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
@@ -194,8 +195,10 @@ class PairMatcher:
                       on_device=False, asynchronous=False):
         """Raw-pointer variant (pinned host buffers or device buffers).  asynchronous: pm_set_image_async -- the
         buffers must stay alive and unchanged until sync_images() or a matching call that uses the image."""
-        f = self.lib.pm_set_image_device if on_device else (
-            self.lib.pm_set_image_async if asynchronous else self.lib.pm_set_image)
+        if on_device:
+            f = self.lib.pm_set_image_device_async if asynchronous else self.lib.pm_set_image_device
+        else:
+            f = self.lib.pm_set_image_async if asynchronous else self.lib.pm_set_image
         self._check(f(self.h, img_id, desc_ptr, n, dim, dtype, xy_ptr))
         self._n[img_id] = n
 

@@ -34,6 +34,7 @@ struct Image {
   bool integral = false; // u8-valued rows (exact tensor path allowed)
   bool i8_ok = false;    // ... and every row norm fits the byte form's norm block (kind::i8 path allowed)
   bool unit_ok = false;  // finite real-valued rows with |x|^2 <= L2F_MAX_NORM2 and fp16 forms packed
+  bool s8_ok = false;    // ... and max |x| <= L2S8_MAX_ABS: the quantised s8 forms are valid (kind::i8 path)
   float maxn = 0.f;      // largest squared row norm
   bool has_xy = false;
   // asynchronous ingest (pm_set_image_async): the upload + packing kernels are queued on the ingest stream and
@@ -197,6 +198,9 @@ struct DeviceCtx {
   float* fnorm = nullptr;      // [rows] fp32 squared norms of real-valued rows
   TcMaps fmaps{};
   bool tcf_ready = false;
+  uint8_t *sq8 = nullptr, *st8 = nullptr;   // [rows][dim+32] s8 operand forms of real-valued rows (kind::i8)
+  TcMaps smaps{};
+  bool tcs_ready = false;
   uint8_t *hq = nullptr, *ht = nullptr;  // [rows][32*words+32] E4M3 operand forms of binary rows (256 / 512 bit)
   TcMaps hmaps{};
   bool tch_ready = false;
@@ -273,6 +277,7 @@ struct DeviceCtx {
     PM_CUDA(tc_configure());
     PM_CUDA(tc2_configure());
     PM_CUDA(i8x2_configure());
+    PM_CUDA(s8_configure());
     PM_CUDA(fixup_configure());
     PM_CUDA(l2f_configure());
     PM_CUDA(select_configure());
@@ -289,7 +294,7 @@ struct DeviceCtx {
     single.destroy();
     auto fd = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
     fd(raw); fd(qf); fd(tf); fd(qnorm); fd(u8d); fd(bits); fd(xy); fd(d_flag); fd(stage); fd(d_dump);
-    fd(fq); fd(ft); fd(fnorm); fd(d_fstats); fd(d_l2f); fd(hq); fd(ht); fd(iq); fd(it); fd(qoff);
+    fd(fq); fd(ft); fd(fnorm); fd(d_fstats); fd(d_l2f); fd(hq); fd(ht); fd(iq); fd(it); fd(qoff); fd(sq8); fd(st8);
     if (h_flag) cudaFreeHost(h_flag);
     if (h_recs) cudaFreeHost(h_recs);
     for (auto& kv : images) if (kv.second.ready) cudaEventDestroy(kv.second.ready);
@@ -309,6 +314,7 @@ struct DeviceCtx {
     tcf_ready = false;
     tch_ready = false;
     tci_ready = false;
+    tcs_ready = false;
     const bool sift_shape = dim == TC_DIM && (dtype == PM_DESC_F32 || dtype == PM_DESC_U8);
     if (!sift_shape && !float_tc_shape() && !bits_tc_shape()) return PM_OK;
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -358,6 +364,13 @@ struct DeviceCtx {
         return fail(PM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
       tcf_ready = true;
       kpad = TC_KPAD;
+      kb = dim + 32;
+      if ((r = mkb(&smaps.q_main, sq8, 128, CU_TENSOR_MAP_SWIZZLE_128B)) != CUDA_SUCCESS ||
+          (r = mkb(&smaps.q_ext, sq8, 32, CU_TENSOR_MAP_SWIZZLE_32B)) != CUDA_SUCCESS ||
+          (r = mkb(&smaps.t_main, st8, 128, CU_TENSOR_MAP_SWIZZLE_128B)) != CUDA_SUCCESS ||
+          (r = mkb(&smaps.t_ext, st8, 32, CU_TENSOR_MAP_SWIZZLE_32B)) != CUDA_SUCCESS)
+        return fail(PM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+      tcs_ready = true;
     }
     if (!sift_shape) return PM_OK;
     if ((r = mk(&maps.q_main, qf, 64, CU_TENSOR_MAP_SWIZZLE_128B)) != CUDA_SUCCESS ||
@@ -423,6 +436,8 @@ struct DeviceCtx {
         if ((rc = grow(fq, dim + 16, nc)) != PM_OK) return rc;
         if ((rc = grow(ft, dim + 16, nc)) != PM_OK) return rc;
         if ((rc = grow(fnorm, 1, nc)) != PM_OK) return rc;
+        if ((rc = grow(sq8, dim + 32, nc)) != PM_OK) return rc;
+        if ((rc = grow(st8, dim + 32, nc)) != PM_OK) return rc;
       }
     }
     if ((rc = grow(xy, 2, nc)) != PM_OK) return rc;
@@ -447,13 +462,18 @@ struct DeviceCtx {
         const int kp = dim + 16;
         PM_CUDA(cudaMemsetAsync(d_fstats, 0, 4 * sizeof(unsigned int), ingest));
         PM_CUDA(launch_pack_float(raw + static_cast<size_t>(im.row) * dim, im.n, dim, fq + static_cast<size_t>(im.row) * kp,
-                                  ft + static_cast<size_t>(im.row) * kp, fnorm + im.row, d_fstats, ingest));
+                                  ft + static_cast<size_t>(im.row) * kp, fnorm + im.row, d_fstats,
+                                  sq8 + static_cast<size_t>(im.row) * (dim + 32), st8 + static_cast<size_t>(im.row) * (dim + 32),
+                                  ingest));
         ++stats.kernel_launches;
         PM_CUDA(cudaMemcpyAsync(rec2 + 1, d_fstats, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ingest));
         PM_CUDA(cudaStreamSynchronize(ingest));
       }
       std::memcpy(&im.maxn, &rec[2], sizeof(float));
       im.unit_ok = rec[3] == 0 && im.maxn <= L2F_MAX_NORM2;
+      float amax;
+      std::memcpy(&amax, &rec[1], sizeof(float));
+      im.s8_ok = im.unit_ok && amax <= L2S8_MAX_ABS;
     }
     return PM_OK;
   }
@@ -504,6 +524,7 @@ struct DeviceCtx {
     im.integral = false;
     im.i8_ok = false;
     im.unit_ok = false;
+    im.s8_ok = false;
     im.maxn = 0.f;
     const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     if (n > 0) {
@@ -571,7 +592,9 @@ struct DeviceCtx {
         const int kp = dim + 16;
         PM_CUDA(cudaMemsetAsync(d_fstats, 0, 4 * sizeof(unsigned int), ingest));
         PM_CUDA(launch_pack_float(raw + static_cast<size_t>(im.row) * dim, n, dim, fq + static_cast<size_t>(im.row) * kp,
-                                  ft + static_cast<size_t>(im.row) * kp, fnorm + im.row, d_fstats, ingest));
+                                  ft + static_cast<size_t>(im.row) * kp, fnorm + im.row, d_fstats,
+                                  sq8 + static_cast<size_t>(im.row) * (dim + 32), st8 + static_cast<size_t>(im.row) * (dim + 32),
+                                  ingest));
         ++stats.kernel_launches;
         PM_CUDA(cudaMemcpyAsync(rec + 1, d_fstats, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ingest));
       }
@@ -592,12 +615,17 @@ struct DeviceCtx {
       const int kp = dim + 16;
       PM_CUDA(cudaMemsetAsync(d_fstats, 0, 4 * sizeof(unsigned int), ingest));
       PM_CUDA(launch_pack_float(raw + static_cast<size_t>(im.row) * dim, n, dim, fq + static_cast<size_t>(im.row) * kp,
-                                ft + static_cast<size_t>(im.row) * kp, fnorm + im.row, d_fstats, ingest));
+                                ft + static_cast<size_t>(im.row) * kp, fnorm + im.row, d_fstats,
+                                  sq8 + static_cast<size_t>(im.row) * (dim + 32), st8 + static_cast<size_t>(im.row) * (dim + 32),
+                                  ingest));
       ++stats.kernel_launches;
       PM_CUDA(cudaMemcpyAsync(h_fstats, d_fstats, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ingest));
       PM_CUDA(cudaStreamSynchronize(ingest));
       std::memcpy(&im.maxn, &h_fstats[1], sizeof(float));
       im.unit_ok = h_fstats[2] == 0 && im.maxn <= L2F_MAX_NORM2;
+      float amax;
+      std::memcpy(&amax, &h_fstats[0], sizeof(float));
+      im.s8_ok = im.unit_ok && amax <= L2S8_MAX_ABS;
     }
     stats.n_images = static_cast<int32_t>(images.size());
     return PM_OK;
@@ -672,7 +700,7 @@ struct DeviceCtx {
   // Queues the kNN kernel(s) of a batch whose jobs are already in s.h_jobs[0..n).
   int enqueue_knn(Slot& s, int n, bool want_rev, bool timed, float* dump = nullptr, bool fast = false) {
     int max_nq = 0, max_nt = 0;
-    bool all_integral = true, all_unit = true, all_i8 = true;
+    bool all_integral = true, all_unit = true, all_i8 = true, all_s8 = true;
     double work = 0;
     for (int i = 0; i < n; ++i) {
       max_nq = std::max(max_nq, s.h_jobs[i].nq);
@@ -687,6 +715,7 @@ struct DeviceCtx {
     if (dtype != PM_DESC_U8_BITS) {
       for (int i = 0; i < n && all_integral; ++i) all_integral = job_integral[i];
       for (int i = 0; i < n && all_i8; ++i) all_i8 = job_i8[i];
+      for (int i = 0; i < n && all_s8; ++i) all_s8 = job_s8[i];
       for (int i = 0; i < n && all_unit; ++i) all_unit = job_unit[i];
     }
     // The kNN kernels of all batches are serialised on one stream (they fill the machine anyway);
@@ -707,6 +736,7 @@ struct DeviceCtx {
     //   bit11     batched loop keeps the fp16 form (kind::f16) instead of the byte form (kind::i8, default)
     //   bits12-13 kind::i8 kernel: 1 / 2 = timing probes (no matches): TMA + MMA only / + accumulator loads without
     //             the reduction; 3 = the 64-register build
+    //   bit15     real-valued rows: fp16 forms (kind::f16) in the batched loop instead of the s8 forms (kind::i8)
     //   bit14     kind::i8: one query row set per cluster (l2_top2_tc2_kernel) instead of two (l2_i8x2_kernel)
     const int code = (prm.debug_flags >> 2) & 7;
     const int fcode = (prm.debug_flags >> 7) & 3;
@@ -720,6 +750,9 @@ struct DeviceCtx {
     const bool use_tcf = !use_tc && tcf_ready && dtype == PM_DESC_F32 && all_unit && !dump &&
                          max_nt <= L2F_MAX_NT &&
                          (!want_rev || max_nq <= L2F_MAX_NT) && !(prm.debug_flags & 1);
+    // ... with the rows quantised to s8 on kind::i8 (half the K-steps) when only the outcome of the ratio test and
+    // the nearest index of passing rows are needed (batched loop without the cross-check); debug bit15 keeps fp16
+    const bool use_tcs8 = use_tcf && tcs_ready && all_s8 && fast && !want_rev && !((prm.debug_flags >> 15) & 1);
     const int epi_of_code[5] = {3, 0, 1, 2, 4};
     // binary rows: Hamming = |a| + |b| - 2 a.b on the tensor cores (E4M3 {0,1} operands) in the batched loop;
     // debug_flags bit10 keeps the XOR/popc kernel there too (it always serves raw kNN rows / single pairs)
@@ -728,6 +761,7 @@ struct DeviceCtx {
       if (use_tch) return launch_ham_tc2(hmaps, words, qnorm, jobs_d, n, mq, oi, od, s.stride, num_sms, knn_stream);
       if (dtype == PM_DESC_U8_BITS)
         return launch_hamming_top2(bits, words, jobs_d, n, mq, oi, od, s.stride, variant, knn_stream);
+      if (use_tcs8) return launch_l2s8_tc2(smaps, dim, jobs_d, n, mq, oi, od, ox, s.stride, num_sms, knn_stream);
       if (use_tcf) return launch_l2f_tc2(fmaps, dim, jobs_d, n, mq, oi, od, ox, s.stride, num_sms, knn_stream);
       if (!use_tc) return launch_l2_simt(raw, dim, jobs_d, n, mq, oi, od, s.stride, knn_stream);
       if (use_i8) {
@@ -792,7 +826,7 @@ struct DeviceCtx {
     }
     if (use_tcf) {
       PM_CUDA(launch_l2f_fixup(raw, fnorm, dim, s.d_jobs, n, max_nq, s.knn_idx, s.knn_dist, s.knn_extra, s.stride,
-                               prm.ratio, fast ? L2F_NEED_RATIO : L2F_NEED_FULL, d_l2f, s.stream));
+                               prm.ratio, fast ? L2F_NEED_RATIO : L2F_NEED_FULL, d_l2f, s.stream, use_tcs8 ? 1 : 0));
       ++stats.kernel_launches;
       if (want_rev) {
         PM_CUDA(launch_l2f_fixup(raw, fnorm, dim, s.d_rjobs, n, max_nt, s.rev_idx, s.rev_dist, s.rev_extra, s.stride,
@@ -802,7 +836,7 @@ struct DeviceCtx {
     }
     return PM_OK;
   }
-  std::vector<char> job_integral, job_unit, job_i8;   // per job of the batch being built
+  std::vector<char> job_integral, job_unit, job_i8, job_s8;   // per job of the batch being built
 
   int fill_job(Slot& s, int k, int i, int j) {
     auto a = images.find(i), b = images.find(j);
@@ -814,8 +848,9 @@ struct DeviceCtx {
       if (rc != PM_OK) return rc;
     }
     s.h_jobs[k] = PairJob{a->second.row, b->second.row, a->second.n, b->second.n, a->second.maxn, b->second.maxn};
-    if (static_cast<int>(job_integral.size()) <= k) { job_integral.resize(k + 1); job_unit.resize(k + 1); job_i8.resize(k + 1); }
+    if (static_cast<int>(job_integral.size()) <= k) { job_integral.resize(k + 1); job_unit.resize(k + 1); job_i8.resize(k + 1); job_s8.resize(k + 1); }
     job_i8[k] = a->second.i8_ok && b->second.i8_ok;
+    job_s8[k] = a->second.s8_ok && b->second.s8_ok;
     job_integral[k] = a->second.integral && b->second.integral;
     job_unit[k] = a->second.unit_ok && b->second.unit_ok;
     return PM_OK;
@@ -1081,6 +1116,14 @@ int pm_set_image_device(pm_handle h, int img_id, const void* d_desc, int n, int 
   std::lock_guard<std::mutex> lk(h->mu);
   if (h->devs.size() != 1) return h->fail(PM_ERR_UNSUPPORTED, "pm_set_image_device needs a single-device handle");
   return h->from(*h->devs[0], h->devs[0]->set_image(img_id, d_desc, n, dim, dtype, d_xy, true));
+}
+
+int pm_set_image_device_async(pm_handle h, int img_id, const void* d_desc, int n, int dim, int dtype,
+                              const int32_t* d_xy) {
+  if (!h) return PM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (h->devs.size() != 1) return h->fail(PM_ERR_UNSUPPORTED, "pm_set_image_device needs a single-device handle");
+  return h->from(*h->devs[0], h->devs[0]->set_image(img_id, d_desc, n, dim, dtype, d_xy, true, true));
 }
 
 int pm_num_keypoints(pm_handle h, int img_id) {

@@ -79,7 +79,13 @@ cudaError_t hamming_fixup_configure();
 cudaError_t launch_l2f_tc2(const TcMaps& maps, int dim, const PairJob* jobs, int n_jobs, int max_nq, int2* idx,
                            float2* dist, float2* extra, int stride, int num_sms, cudaStream_t st);
 cudaError_t launch_pack_float(const float* raw, int n, int dim, __half* qh, __half* th, float* fnorm,
-                              unsigned int* stats, cudaStream_t st);
+                              unsigned int* stats, uint8_t* q8, uint8_t* t8, cudaStream_t st);
+// the same search with rows quantised to s8 (|x| <= L2S8_MAX_ABS) on kind::i8: half the K-steps; l2f_fixup with
+// e_mode = 1 (the wider error bound of the quantised scores) follows.  maps: UINT8 maps over rows of dim + 32 bytes.
+static constexpr float L2S8_MAX_ABS = 0.5f;
+cudaError_t s8_configure();
+cudaError_t launch_l2s8_tc2(const TcMaps& maps, int dim, const PairJob* jobs, int n_jobs, int max_nq, int2* idx,
+                            float2* dist, float2* extra, int stride, int num_sms, cudaStream_t st);
 // exact fp32 re-rank of the candidate chunks (l2f_fixup.cu).  need: 0 = rows that can pass the ratio test
 // (exact nearest index + exact test outcome), 1 = exact nearest index of every row, 2 = exact DMatch rows
 enum { L2F_NEED_RATIO = 0, L2F_NEED_NEAREST = 1, L2F_NEED_FULL = 2 };
@@ -87,7 +93,7 @@ static constexpr int L2F_MAX_NT = 16384;   // chunk id = 10 bits of the key
 static constexpr float L2F_MAX_NORM2 = 1.01f;   // rows must satisfy |x|^2 <= this (scores stay positive)
 cudaError_t launch_l2f_fixup(const float* raw, const float* fnorm, int dim, const PairJob* jobs, int n_jobs,
                              int max_nq, int2* idx, float2* dist, const float2* extra, int stride, float ratio,
-                             int need, unsigned long long* counters, cudaStream_t st);
+                             int need, unsigned long long* counters, cudaStream_t st, int e_mode = 0);
 
 // shared-memory carve-out of the small tail kernels = the tensor kernel's, so that they can be co-resident
 cudaError_t fixup_configure();

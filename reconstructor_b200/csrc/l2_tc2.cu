@@ -74,6 +74,8 @@ struct T2Cfg {
   // kind::i8: D=s32 (c_format 2); main K-steps A=u8 (format 0), B=s8 (format 1); norm block A=B=u8
   static constexpr uint32_t kIdescI8 = (2u << 4) | (1u << 10) | kShape;
   static constexpr uint32_t kIdescI8Ext = (2u << 4) | kShape;
+  // kind::i8 with both operands signed (quantised real-valued rows, KIND 3)
+  static constexpr uint32_t kIdescS8 = (2u << 4) | (1u << 7) | (1u << 10) | kShape;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -104,7 +106,7 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tma
 template <int KIND>
 __device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                               uint32_t accumulate) {
-  if (KIND == 2)
+  if (KIND >= 2)
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
@@ -312,6 +314,44 @@ __device__ __forceinline__ void keys_chunk16(Keys4& s, const uint32_t* r, int co
   const float cm = fminf(fminf(g[0], g[1]), fminf(g[2], g[3]));
   keys_insert(s, __uint_as_float((__float_as_uint(cm) & 0xFFFFFC00u) | static_cast<uint32_t>(col >> 4)));
 }
+// ---- MODE 3 on kind::i8 (KIND 3): quantised real-valued rows -------------------------------------------
+// rows x with |x_k| <= 0.5 are quantised to q = rint(254 x) (s8); query form [ q_a | 1, 255 x31 (u8) ], train form
+// [ -q_b | digits of h = rint(254^2 (|b|^2 / 2 + 1)) in base 255 ].  The s32 accumulator h - q_a.q_b approximates
+// 254^2 * (|b|^2 / 2 - a.b + 1) = 254^2 / 2 * score, score = |b|^2 - 2 a.b + 2 as in the fp16 form, with
+// |error| <= sqrt(D) (|a| + |b|) / 254 + D / (2 * 254^2) + 1 / 254^2 on the score (l2f_fixup.cu widens its bound).
+// Keys are integers here: (accumulator << 10) | chunk id, 0 < accumulator < 2^18.
+static constexpr float T2S_SCALE = 254.f;
+struct Keys6i {
+  int k1, k2, k3, k4, k5, k6;
+};
+__device__ __forceinline__ void keysi_insert(Keys6i& s, int key) {
+  int lo = min(s.k1, key), hi = max(s.k1, key);
+  s.k1 = lo; key = hi;
+  lo = min(s.k2, key); hi = max(s.k2, key);
+  s.k2 = lo; key = hi;
+  lo = min(s.k3, key); hi = max(s.k3, key);
+  s.k3 = lo; key = hi;
+  lo = min(s.k4, key); hi = max(s.k4, key);
+  s.k4 = lo; key = hi;
+  lo = min(s.k5, key); hi = max(s.k5, key);
+  s.k5 = lo; key = hi;
+  s.k6 = min(s.k6, key);
+}
+__device__ __forceinline__ void keysi_chunk16(Keys6i& s, const uint32_t* r, int col) {
+  const int a0 = __vimin3_s32(static_cast<int>(r[0]), static_cast<int>(r[1]), static_cast<int>(r[2]));
+  const int a1 = __vimin3_s32(static_cast<int>(r[3]), static_cast<int>(r[4]), static_cast<int>(r[5]));
+  const int a2 = __vimin3_s32(static_cast<int>(r[6]), static_cast<int>(r[7]), static_cast<int>(r[8]));
+  const int a3 = __vimin3_s32(static_cast<int>(r[9]), static_cast<int>(r[10]), static_cast<int>(r[11]));
+  const int a4 = __vimin3_s32(static_cast<int>(r[12]), static_cast<int>(r[13]), static_cast<int>(r[14]));
+  const int cm = min(__vimin3_s32(a0, a1, a2), __vimin3_s32(a3, a4, static_cast<int>(r[15])));
+  keysi_insert(s, (cm << 10) | (col >> 4));
+}
+// integer key -> the float key l2f_fixup.cu expects: score with the chunk id in the low 10 mantissa bits
+__device__ __forceinline__ float keysi_to_float(int key) {
+  if (key == T2I_INF) return __int_as_float(0x7f800000);
+  const float sc = static_cast<float>(key >> 10) * (2.f / (T2S_SCALE * T2S_SCALE));
+  return __uint_as_float((__float_as_uint(sc) & 0xFFFFFC00u) | static_cast<uint32_t>(key & 0x3FF));
+}
 // ordered by (value, index)
 __device__ __forceinline__ bool t2_less(float va, int ia, float vb, int ib) { return va < vb || (va == vb && ia < ib); }
 __device__ __forceinline__ void t2_merge(Top2p& s, float om1, int oi1, float om2, int oi2) {
@@ -352,8 +392,9 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
   constexpr int KDIM = KEL * KA;
   constexpr int T2_BATOM = Cfg::kBAtom, T2_BTILE = Cfg::kBTile, CPW = Cfg::kCPW, NSL = Cfg::kSlices;
   constexpr int NGRP = Cfg::kGroups;
-  constexpr uint32_t T2_IDESC = KIND == 2 ? Cfg::kIdescI8 : Cfg::kIdesc;
-  constexpr uint32_t T2_IDESC_EXT = KIND == 2 ? Cfg::kIdescI8Ext : Cfg::kIdesc;
+  constexpr uint32_t T2_IDESC = KIND == 2 ? Cfg::kIdescI8 : KIND == 3 ? Cfg::kIdescS8 : Cfg::kIdesc;
+  constexpr uint32_t T2_IDESC_EXT = KIND >= 2 ? Cfg::kIdescI8Ext : Cfg::kIdesc;
+  static_assert(KIND != 3 || MODE == 3, "quantised real-valued rows use the candidate-key epilogue");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -497,6 +538,8 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
       s.i1 = s.i2 = -1;                                // MODE 2: i1 = base column of the winning 16-column chunk
       Keys4 ks;
       ks.k1 = ks.k2 = ks.k3 = ks.k4 = ks.k5 = ks.k6 = __int_as_float(0x7f800000);
+      Keys6i ki;                                       // KIND 3
+      ki.k1 = ki.k2 = ki.k3 = ki.k4 = ki.k5 = ki.k6 = T2I_INF;
       Top2i si;                                        // KIND 2
       si.m1 = si.m2 = T2I_INF;
       si.i1 = -1;
@@ -557,7 +600,8 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
               tc_fence_before();
               if (lane == 0) mbar_arrive_leader(&acc_empty[as]);
             }
-            if (MODE == 3) { keys_chunk16(ks, v, c0 + 32 * c); keys_chunk16(ks, v + 16, c0 + 32 * c + 16); }
+            if (MODE == 3 && KIND == 3) { keysi_chunk16(ki, v, c0 + 32 * c); keysi_chunk16(ki, v + 16, c0 + 32 * c + 16); }
+            else if (MODE == 3) { keys_chunk16(ks, v, c0 + 32 * c); keys_chunk16(ks, v + 16, c0 + 32 * c + 16); }
             else if (MODE == 2 && KIND == 2) t2i_chunk32(si, v, c0 + 32 * c, 32);
             else if (MODE == 2) t2_fast(s, v, c0 + 32 * c);
             else t2_scan32(s, v, c0 + 32 * c);
@@ -573,7 +617,10 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
 #pragma unroll
             for (int e = 0; e < 32; ++e)
               if (32 * c + e >= lim) v[e] = 0x7f800000u;
-            if (MODE == 3) {
+            if (MODE == 3 && KIND == 3) {
+              if (lim > 32 * c) keysi_chunk16(ki, v, c0 + 32 * c);
+              if (lim > 32 * c + 16) keysi_chunk16(ki, v + 16, c0 + 32 * c + 16);
+            } else if (MODE == 3) {
               if (lim > 32 * c) keys_chunk16(ks, v, c0 + 32 * c);
               if (lim > 32 * c + 16) keys_chunk16(ks, v + 16, c0 + 32 * c + 16);
             } else if (MODE == 2 && KIND == 2) {
@@ -592,17 +639,24 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
         const int bar_id = 1 + quarter;
         if (slice > 0) {
           slot[(slice - 1) * 64] =
-              MODE == 3   ? make_float4(ks.k1, ks.k2, ks.k3, ks.k4)
+              (MODE == 3 && KIND == 3) ? make_float4(__int_as_float(ki.k1), __int_as_float(ki.k2), __int_as_float(ki.k3), __int_as_float(ki.k4))
+              : MODE == 3 ? make_float4(ks.k1, ks.k2, ks.k3, ks.k4)
               : KIND == 2 ? make_float4(__int_as_float(si.m1), __int_as_float(si.i1), __int_as_float(si.m2), 0.f)
                           : make_float4(s.m1, __int_as_float(s.i1), s.m2, __int_as_float(s.i2));
-          if (MODE == 3) slot[(slice - 1) * 64 + 32] = make_float4(ks.k5, ks.k6, 0.f, 0.f);
+          if (MODE == 3 && KIND == 3) slot[(slice - 1) * 64 + 32] = make_float4(__int_as_float(ki.k5), __int_as_float(ki.k6), 0.f, 0.f);
+          else if (MODE == 3) slot[(slice - 1) * 64 + 32] = make_float4(ks.k5, ks.k6, 0.f, 0.f);
         }
         asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NSL) : "memory");
         if (slice == 0) {
 #pragma unroll
           for (int o = 0; o < NSL - 1; ++o) {
             const float4 x = slot[o * 64];
-            if (MODE == 3) {
+            if (MODE == 3 && KIND == 3) {
+              const float4 x2 = slot[o * 64 + 32];
+              keysi_insert(ki, __float_as_int(x.x)); keysi_insert(ki, __float_as_int(x.y));
+              keysi_insert(ki, __float_as_int(x.z)); keysi_insert(ki, __float_as_int(x.w));
+              keysi_insert(ki, __float_as_int(x2.x)); keysi_insert(ki, __float_as_int(x2.y));
+            } else if (MODE == 3) {
               const float4 x2 = slot[o * 64 + 32];
               keys_insert(ks, x.x); keys_insert(ks, x.y); keys_insert(ks, x.z); keys_insert(ks, x.w);
               keys_insert(ks, x2.x); keys_insert(ks, x2.y);
@@ -627,7 +681,12 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
         }
         asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NSL) : "memory");
       }
-      if (MODE == 3 && slice == 0 && row < job.nq) {
+      if (MODE == 3 && KIND == 3 && slice == 0 && row < job.nq) {
+        const size_t o = static_cast<size_t>(jb) * stride + row;
+        knn_dist[o] = make_float2(keysi_to_float(ki.k1), keysi_to_float(ki.k2));
+        knn_idx[o] = make_int2(__float_as_int(keysi_to_float(ki.k3)), __float_as_int(keysi_to_float(ki.k4)));
+        extra_keys[o] = make_float2(keysi_to_float(ki.k5), keysi_to_float(ki.k6));
+      } else if (MODE == 3 && slice == 0 && row < job.nq) {
         const size_t o = static_cast<size_t>(jb) * stride + row;
         knn_dist[o] = make_float2(ks.k1, ks.k2);
         knn_idx[o] = make_int2(__float_as_int(ks.k3), __float_as_int(ks.k4));
@@ -1002,6 +1061,40 @@ static cudaError_t i8x2_attr() {
   return cudaFuncSetAttribute(l2_i8x2_kernel<MODE, LEAN>, cudaFuncAttributePreferredSharedMemoryCarveout,
                               cudaSharedmemCarveoutMaxShared);
 }
+using T2S256 = T2Cfg<256, 2, 2>;  // quantised real-valued rows, 256-d: 256 bytes of K + norm block
+using T2S128 = T2Cfg<256, 2, 1>;  // 128-d
+cudaError_t s8_configure() {
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(l2_top2_tc2_kernel<T2S256, 3, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                T2S256::kSmemBytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(l2_top2_tc2_kernel<T2S256, 3, true, 3>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(l2_top2_tc2_kernel<T2S128, 3, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                T2S128::kSmemBytes)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(l2_top2_tc2_kernel<T2S128, 3, true, 3>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                              cudaSharedmemCarveoutMaxShared);
+}
+// Quantised real-valued rows (s8 operand forms of dim + 32 bytes per row, pack_float_kernel): approximate scores on
+// kind::i8, six candidate keys per query row in the layout of launch_l2f_tc2; l2f_fixup (e_mode 1) follows.
+cudaError_t launch_l2s8_tc2(const TcMaps& maps, int dim, const PairJob* jobs, int n_jobs, int max_nq, int2* idx,
+                            float2* dist, float2* extra, int stride, int num_sms, cudaStream_t st) {
+  if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
+  const int tiles_per_job = (max_nq + T2_ROWS - 1) / T2_ROWS;
+  const int n_items = n_jobs * tiles_per_job;
+  int clusters = num_sms / 2;
+  if (n_items < clusters) clusters = n_items;
+  const int grid = clusters * 2;
+  if (dim == 256)
+    l2_top2_tc2_kernel<T2S256, 3, true, 3><<<grid, T2S256::kThreads, T2S256::kSmemBytes, st>>>(
+        maps.q_main, maps.q_ext, maps.t_main, maps.t_ext, nullptr, jobs, n_jobs, tiles_per_job, idx, dist, stride, extra);
+  else if (dim == 128)
+    l2_top2_tc2_kernel<T2S128, 3, true, 3><<<grid, T2S128::kThreads, T2S128::kSmemBytes, st>>>(
+        maps.q_main, maps.q_ext, maps.t_main, maps.t_ext, nullptr, jobs, n_jobs, tiles_per_job, idx, dist, stride, extra);
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
 cudaError_t i8x2_configure() {
   cudaError_t e;
   if ((e = i8x2_attr<2, false>()) != cudaSuccess) return e;

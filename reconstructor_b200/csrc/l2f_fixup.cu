@@ -44,7 +44,8 @@ struct FfBound {          // per query row: exact_d2(col) is within [K - eps(K) 
   }
 };
 
-__device__ __forceinline__ FfBound ff_bound(float na2, float nb2max, int dim) {
+// e_mode 0: fp16 operand forms (l2_tc2.cu MODE 3, kind::f16); 1: rows quantised to s8 with scale 254 (KIND 3)
+__device__ __forceinline__ FfBound ff_bound(float na2, float nb2max, int dim, int e_mode) {
   FfBound b;
   const double na = sqrt(static_cast<double>(na2)) * (1.0 + 1e-6);
   const double nb = sqrt(static_cast<double>(nb2max)) * (1.0 + 1e-6);
@@ -55,6 +56,15 @@ __device__ __forceinline__ FfBound ff_bound(float na2, float nb2max, int dim) {
   const double e_nrm = 3.814697265625e-6 * (na * na + nb * nb);                         // 2^-18: fp32 norms, fp16 split
   const double e_f32 = 1.01 * (dim + 3) * u24 * (na + nb) * (na + nb);                  // exact side is fp32 too
   b.e0 = e_op + e_acc + e_nrm + e_f32;
+  if (e_mode == 1) {
+    // q = rint(254 x): |q - 254 x| <= 1/2 per element, so |q_a.q_b - 254^2 a.b| <= 127 (|a|_1 + |b|_1) + D / 4
+    // <= 127 sqrt(D) (|a| + |b|) + D / 4; the score is 2 / 254^2 times the integer accumulator (exact), whose
+    // norm term was rounded to an integer (1/2) from an fp32 norm (2^-22 relative incl. its accumulation)
+    const double S = 254.0;
+    const double e_q = (2.0 / (S * S)) * (0.5 * S * sD * (na + nb) + 0.25 * dim + 0.75);
+    const double e_n = 2.4e-7 * (dim + 3) * (nb * nb + 2.0) + 4.0 * u24 * (nb * nb + 2.0 * na * nb + 2.0);
+    b.e0 = 1.001 * e_q + e_n + e_f32;
+  }
   b.c = static_cast<double>(na2) - 2.0;
   return b;
 }
@@ -100,7 +110,7 @@ __global__ void __launch_bounds__(FF_THREADS)
 l2f_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm, int dim,
                  const PairJob* __restrict__ jobs, int2* __restrict__ knn_idx, float2* __restrict__ knn_dist,
                  const float2* __restrict__ extra, int stride, float ratio, int need,
-                 unsigned long long* __restrict__ counters) {
+                 unsigned long long* __restrict__ counters, int e_mode) {
   __shared__ __align__(16) float qs[FF_HW][FF_MAXDIM];
   __shared__ float keys_s[FF_SPAN][6];
   __shared__ int list[FF_SPAN];
@@ -130,7 +140,7 @@ l2f_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm,
       const float K[6] = {k12.x, k12.y, __int_as_float(k34.x), __int_as_float(k34.y), k56.x, k56.y};
       bool need_row = K[0] != inf;                                // no train rows at all: no neighbours
       if (need_row && need == L2F_NEED_RATIO) {
-        const FfBound bd = ff_bound(fnorm[jb.q_row + row], jb.t_maxn, dim);
+        const FfBound bd = ff_bound(fnorm[jb.q_row + row], jb.t_maxn, dim, e_mode);
         // true d1^2 >= lb(K1), true d2^2 <= ub(K2): the test fails for good when even these cannot pass
         need_row = !(__fsqrt_rn(bd.lb(K[0])) >= __fmul_rn(ratio, __fsqrt_rn(bd.ub(K[1]))));
       }
@@ -159,7 +169,7 @@ l2f_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm,
     for (int k = 4 * l; k < dim; k += 64)
       *reinterpret_cast<float4*>(&qs[hw][k]) = __ldg(reinterpret_cast<const float4*>(qrow + k));
     __syncwarp(hmask);
-    const FfBound bd = ff_bound(fnorm[jb.q_row + row], jb.t_maxn, dim);
+    const FfBound bd = ff_bound(fnorm[jb.q_row + row], jb.t_maxn, dim, e_mode);
     unsigned long long e1 = KEY_NONE64, e2 = KEY_NONE64;
     bool done = false;
     for (int j = 0; j < 6 && !done; ++j) {
@@ -272,12 +282,12 @@ cudaError_t l2f_configure() {
 
 cudaError_t launch_l2f_fixup(const float* raw, const float* fnorm, int dim, const PairJob* jobs, int n_jobs,
                              int max_nq, int2* idx, float2* dist, const float2* extra, int stride, float ratio,
-                             int need, unsigned long long* counters, cudaStream_t st) {
+                             int need, unsigned long long* counters, cudaStream_t st, int e_mode) {
   if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
   if (dim <= 0 || dim > FF_MAXDIM || (dim & 63)) return cudaErrorInvalidValue;
   dim3 grid((max_nq + FF_SPAN - 1) / FF_SPAN, n_jobs);
   l2f_fixup_kernel<<<grid, FF_THREADS, 0, st>>>(raw, fnorm, dim, jobs, idx, dist, extra, stride, ratio, need,
-                                                counters);
+                                                counters, e_mode);
   return cudaGetLastError();
 }
 

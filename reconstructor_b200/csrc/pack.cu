@@ -118,9 +118,13 @@ cudaError_t launch_pack_sift(const float* raw_f32, const uint8_t* raw_u8, int n,
 //   query form [ -2*a | 1, 1, 1, 1, 0 x12 ]      train form [ b | p0, p1, p2, 2, 0 x12 ]
 // with |b|^2 = p0 + p1 + p2 up to 2^-33 (three fp16 pieces of the fp32 norm) and +2 keeping every score
 // positive.  stats[0] = max |x| (float bits), stats[1] = max |row|^2 (float bits), stats[2] = non-finite seen.
+// The same rows quantised for kind::i8 (l2_tc2.cu KIND 3), dim + 32 bytes per row, when q8 != nullptr:
+//   query form [ q_k = rint(254 x_k) (s8) | 1, 255 x31 (u8) ]      train form [ -q_k (s8) | digits of h, base 255 ]
+// with h = rint(254^2 (|b|^2 / 2 + 1)) from the fp32 norm.  Valid when max |x| <= 0.5 (stats[0]).
 __global__ void __launch_bounds__(256)
 pack_float_kernel(const float* __restrict__ raw, int n, int dim, __half* __restrict__ qh, __half* __restrict__ th,
-                  float* __restrict__ fnorm, unsigned int* __restrict__ stats) {
+                  float* __restrict__ fnorm, unsigned int* __restrict__ stats, uint8_t* __restrict__ q8,
+                  uint8_t* __restrict__ t8) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
@@ -143,6 +147,17 @@ pack_float_kernel(const float* __restrict__ raw, int n, int dim, __half* __restr
     reinterpret_cast<__half2*>(qrow + k)[1] = __floats2half2_rn(-2.f * v[2], -2.f * v[3]);
     reinterpret_cast<__half2*>(trow + k)[0] = __floats2half2_rn(v[0], v[1]);
     reinterpret_cast<__half2*>(trow + k)[1] = __floats2half2_rn(v[2], v[3]);
+    if (q8) {
+      uint32_t wq = 0, wt = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int q = max(-127, min(127, __float2int_rn(254.f * v[e])));
+        wq |= (static_cast<uint32_t>(q) & 0xFFu) << (8 * e);
+        wt |= (static_cast<uint32_t>(-q) & 0xFFu) << (8 * e);
+      }
+      *reinterpret_cast<uint32_t*>(q8 + static_cast<size_t>(row) * (dim + 32) + k) = wq;
+      *reinterpret_cast<uint32_t*>(t8 + static_cast<size_t>(row) * (dim + 32) + k) = wt;
+    }
   }
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) {
@@ -163,6 +178,13 @@ pack_float_kernel(const float* __restrict__ raw, int n, int dim, __half* __restr
     qrow[dim + lane] = __float2half_rn(qe);
     trow[dim + lane] = __float2half_rn(te);
   }
+  if (q8) {
+    const int h = __float2int_rn(254.f * 254.f * (0.5f * fminf(nrm, 4.f) + 1.f));
+    const int qd = h / 255, r = h - 255 * qd;                    // h <= 3 * 254^2: qd <= 759 < 31 * 255
+    q8[static_cast<size_t>(row) * (dim + 32) + dim + lane] = lane == 0 ? 1 : 255;
+    t8[static_cast<size_t>(row) * (dim + 32) + dim + lane] =
+        static_cast<uint8_t>(lane == 0 ? r : min(255, max(0, qd - 255 * (lane - 1))));
+  }
   if (lane == 0) {
     fnorm[row] = nrm;
     atomicMax(&stats[0], __float_as_uint(amax));
@@ -172,9 +194,9 @@ pack_float_kernel(const float* __restrict__ raw, int n, int dim, __half* __restr
 }
 
 cudaError_t launch_pack_float(const float* raw, int n, int dim, __half* qh, __half* th, float* fnorm,
-                              unsigned int* stats, cudaStream_t st) {
+                              unsigned int* stats, uint8_t* q8, uint8_t* t8, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
-  pack_float_kernel<<<(n + 7) / 8, 256, 0, st>>>(raw, n, dim, qh, th, fnorm, stats);
+  pack_float_kernel<<<(n + 7) / 8, 256, 0, st>>>(raw, n, dim, qh, th, fnorm, stats, q8, t8);
   return cudaGetLastError();
 }
 

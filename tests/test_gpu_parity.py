@@ -749,6 +749,71 @@ def test_async_ingest_gives_identical_results(kind):
     assert np.array_equal(outs[0]["knn"][0], outs[1]["knn"][0]) and np.array_equal(outs[0]["knn"][1], outs[1]["knn"][1])
     assert outs[0]["offsets"][-1] > (15 * 200 if kind != "sp128" else 15 * 50)
 
+
+# ---------------------------------------------------------------------------------------------
+# real-valued rows quantised to s8 on kind::i8 (default batched SuperPoint path without cross-check) vs fp16 forms
+# ---------------------------------------------------------------------------------------------
+FORCE_FP16_FORMS = 1 << 15
+
+
+@pytest.mark.parametrize("dim", [128, 256])
+@pytest.mark.parametrize("mode", [api.UNIQUE_FIRST_WINS, api.UNIQUE_NONE, api.MUTUAL_NN])
+def test_s8_quantised_candidates_equal_fp16_forms_and_simt(dim, mode):
+    """The candidate stage only proposes; the certified fp32 re-rank decides.  Outputs must be identical whichever
+    operand precision proposed (s8 / fp16) and identical to the fp32 SIMT search."""
+    rng = np.random.default_rng(200 + dim + mode)
+    base = _unit_rows(rng, 3000, dim)
+    imgs = []
+    for i, n in enumerate((1100, 1000, 700, 300, 40)):
+        ids = rng.permutation(3000)[:n]
+        d = base[ids] + 0.35 * rng.standard_normal((n, dim)).astype(np.float32) / np.sqrt(dim)
+        d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+        if i == 1:
+            d[11] = d[5]; d[700] = d[5]                     # duplicates: ties in the candidate scores
+        imgs.append(d)
+    outs = []
+    for flags in (0, FORCE_FP16_FORMS, 1):
+        with api.PairMatcher(unique_mode=mode, batch_pairs=4, do_filter=0, debug_flags=flags) as pm:
+            for i, d in enumerate(imgs):
+                pm.set_image(i, d)
+            outs.append(pm.match_all_pairs())
+            st = pm.stats()
+        if flags == 0 and mode != api.MUTUAL_NN:
+            assert st["rerank_rows"] > 0 and st["rerank_worst_err"] < 1.0, st
+    _csr_equal(outs[0], outs[1], ("offsets", "q", "t", "status"))
+    _csr_equal(outs[0], outs[2], ("offsets", "q", "t", "status"))
+    assert outs[0]["offsets"][-1] > 300
+
+
+def test_s8_quantised_fallback_on_large_entries_and_full_size():
+    """Rows with an entry above 0.5 cannot be quantised with scale 254: the image stays on the fp16 forms.  Full-size
+    SuperPoint-like images: s8 candidates == fp16 candidates, CSR identical including the RANSAC outputs."""
+    rng = np.random.default_rng(5)
+    a = _unit_rows(rng, 600, 256); b = _unit_rows(rng, 500, 256)
+    b[100:200] = a[50:150]
+    a2 = a.copy(); a2[7] = 0; a2[7, 3] = 0.8; a2[7, 4] = 0.6      # unit norm, max |x| = 0.8
+    for imgs in ((a, b), (a2, b)):
+        outs = []
+        for flags in (0, FORCE_FP16_FORMS):
+            with api.PairMatcher(do_filter=0, debug_flags=flags) as pm:
+                for i, d in enumerate(imgs):
+                    pm.set_image(i, d)
+                outs.append(pm.match_all_pairs())
+        _csr_equal(outs[0], outs[1], ("offsets", "q", "t", "status"))
+        assert outs[0]["offsets"][-1] >= 99
+    w = synth.World("superpoint", 8192, seed=0xB200 + 9)
+    imgs = [w.image(i, 100, outlier_frac=0.3 if i == 1 else 0.0)[:2] for i in range(4)]
+    outs = []
+    for flags in (0, FORCE_FP16_FORMS):
+        with api.PairMatcher(debug_flags=flags) as pm:
+            for i, (d, xy) in enumerate(imgs):
+                pm.set_image(i, d, xy)
+            outs.append(pm.match_all_pairs())
+            st = pm.stats()
+        assert st["rerank_worst_err"] < 1.0, st
+    _csr_equal(outs[0], outs[1])
+    assert outs[0]["offsets"][-1] > 6 * 1000
+
 # ---------------------------------------------------------------------------------------------
 # on-disk cache (SURVEY 8f rank 2): resume from files, identical results
 # ---------------------------------------------------------------------------------------------
