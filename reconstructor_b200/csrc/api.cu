@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -908,6 +909,13 @@ struct DeviceCtx {
       float ms = 0;
       PM_CUDA(cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
       stats.knn_ms += ms;
+      if (std::getenv("PM_TRACE")) {      // development: timeline of the batch relative to the call's first event
+        float t0 = 0, t1 = 0, t2 = 0;
+        cudaEventElapsedTime(&t0, ev_a, s.ev_k0); cudaEventElapsedTime(&t1, ev_a, s.ev_k1);
+        cudaEventElapsedTime(&t2, ev_a, s.ev_done);
+        std::fprintf(stderr, "[pm trace] batch pair0=%lld n=%d knn %.3f..%.3f ms tail done %.3f ms\n",
+                     static_cast<long long>(s.first_pair), s.n_jobs, t0, t1, t2);
+      }
       stats.knn_launches += 1;
       stats.knn_work += s.knn_work;
     }
@@ -935,7 +943,11 @@ struct DeviceCtx {
     const int stride = (maxn + 255) / 256 * 256;
     int B = prm.batch_pairs > 0 ? prm.batch_pairs : static_cast<int>(std::clamp<int64_t>((2 << 20) / stride, 32, 2048));
     B = static_cast<int>(std::min<int64_t>(B, n_pairs));
-    const int S = n_pairs > B ? 4 : 1;
+    // batches in flight: the kNN kernels run back to back on their own stream, up to S batches ahead of the tails
+    // (measured: 8 or 16 instead of 4 changes nothing -- where the tails cannot be co-resident at a useful occupancy
+    // they are throughput-bound, not latency-bound, once they get the machine).  PM_SLOTS overrides (development).
+    int S = n_pairs > B ? 4 : 1;
+    if (const char* e = std::getenv("PM_SLOTS")) S = n_pairs > B ? std::max(1, std::min(32, std::atoi(e))) : 1;
     const bool mutual = prm.unique_mode == PM_MUTUAL_NN;
     if (static_cast<int>(slots.size()) < S) slots.resize(S);
     for (int s = 0; s < S; ++s) {

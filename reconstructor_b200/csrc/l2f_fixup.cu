@@ -84,6 +84,28 @@ __device__ __forceinline__ float ff_dist(const float* __restrict__ qs, const flo
   return acc;
 }
 
+// The same chain, abandoned once it reaches thr (checked every 64 dimensions): every partial sum of the chain is a
+// lower bound of its final value (fp32 round-to-nearest is monotone and the addends are >= 0), so a column whose
+// partial sum reached thr is >= thr for certain.  Returns false (and no value) in that case.
+__device__ __forceinline__ bool ff_dist_below(const float* __restrict__ qs, const float* __restrict__ trow, int dim,
+                                              float thr, float* out) {
+  float acc = 0.f;
+  for (int k0 = 0; k0 < dim; k0 += 64) {
+#pragma unroll 4
+    for (int k = k0; k < k0 + 64; k += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(trow + k));
+      const float4 a = *reinterpret_cast<const float4*>(qs + k);
+      float d = a.x - b.x; acc = fmaf(d, d, acc);
+      d = a.y - b.y; acc = fmaf(d, d, acc);
+      d = a.z - b.z; acc = fmaf(d, d, acc);
+      d = a.w - b.w; acc = fmaf(d, d, acc);
+    }
+    if (acc >= thr) return false;
+  }
+  *out = acc;
+  return true;
+}
+
 __device__ __forceinline__ void ff_merge(unsigned long long& m1, unsigned long long& m2, unsigned long long o1,
                                          unsigned long long o2) {
   const unsigned long long lo = m1 < o1 ? m1 : o1;
@@ -172,33 +194,51 @@ l2f_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm,
     const FfBound bd = ff_bound(fnorm[jb.q_row + row], jb.t_maxn, dim, e_mode);
     unsigned long long e1 = KEY_NONE64, e2 = KEY_NONE64;
     bool done = false;
+    // first chunk of a ratio-test row: columns are abandoned as soon as their partial sum shows they cannot matter
+    // (see thr below).  A row that the first chunk cannot close re-evaluates it in full (rare) and goes on as before.
+    bool early = need == L2F_NEED_RATIO;
     for (int j = 0; j < 6 && !done; ++j) {
       const float Kj = keys_s[r][j];
       if (Kj == inf) break;                              // (unreachable: the previous lbn was +inf)
       const int cb = static_cast<int>(__float_as_uint(Kj) & FF_IDMASK) * 16;
       const int ncol = min(16, jb.nt - cb);
       unsigned long long k1 = KEY_NONE64, k2 = KEY_NONE64;
-      if (l < ncol) {
-        const float d2 = ff_dist(qs[hw], tbase + static_cast<size_t>(cb + l) * dim, dim);
-        k1 = (static_cast<unsigned long long>(__float_as_uint(d2)) << 32) | static_cast<unsigned int>(cb + l);
+      const bool use_thr = early && j == 0;
+      // abandon threshold of the first chunk: a column is of no further interest once it is >= lbn (the bound of
+      // everything outside the chunk) or >= ub(K1) / ratio^2 (then Lowe's test passes against it whatever the
+      // nearest distance turns out to be).  The threshold only saves work: every decision below is re-tested with
+      // `low`, the bound the abandoned columns actually satisfy.
+      float thr = inf;
+      if (use_thr) {
+        const float r2 = __fmul_rd(ratio, ratio);
+        thr = fminf(bd.lb(keys_s[r][1]), r2 > 0.f ? __fmul_ru(__fdiv_ru(bd.ub(Kj), r2), 1.0001f) : inf);
       }
-      const unsigned long long own = k1;
+      bool gave_up = false;
+      if (l < ncol) {
+        float d2;
+        if (use_thr) gave_up = !ff_dist_below(qs[hw], tbase + static_cast<size_t>(cb + l) * dim, dim, thr, &d2);
+        else d2 = ff_dist(qs[hw], tbase + static_cast<size_t>(cb + l) * dim, dim);
+        if (!gave_up)
+          k1 = (static_cast<unsigned long long>(__float_as_uint(d2)) << 32) | static_cast<unsigned int>(cb + l);
+      }
+      const bool any_gave_up = use_thr && __any_sync(hmask, gave_up);
+      const float low = any_gave_up ? thr : inf;         // every abandoned column is >= low
 #pragma unroll
       for (int off = 8; off >= 1; off >>= 1) {
         const unsigned long long o1 = __shfl_xor_sync(hmask, k1, off, 16);
         const unsigned long long o2 = __shfl_xor_sync(hmask, k2, off, 16);
         ff_merge(k1, k2, o1, o2);
       }
-      (void)own;
       ++n_chunks;
-      {  // how tight is the bound?  |key - exact chunk minimum score| / eps  (statistics only)
+      if (k1 != KEY_NONE64) {  // how tight is the bound?  |key - exact chunk minimum score| / eps  (statistics only;
+                               // an abandoned column is >= thr > every value kept, so k1 is still the chunk minimum)
         const float ex = __uint_as_float(static_cast<unsigned int>(k1 >> 32));
         const double err = fabs(static_cast<double>(Kj) - (static_cast<double>(ex) - bd.c));
         worst = fmaxf(worst, static_cast<float>(err / bd.eps(Kj)));
       }
       ff_merge(e1, e2, k1, k2);
       const float lbn = bd.lb(keys_s[r][j < 5 ? j + 1 : 5]);     // every column not evaluated so far is >= lbn
-      const float d1sq = __uint_as_float(static_cast<unsigned int>(e1 >> 32));
+      const float d1sq = e1 == KEY_NONE64 ? inf : __uint_as_float(static_cast<unsigned int>(e1 >> 32));
       const float d2sq = e2 == KEY_NONE64 ? inf : __uint_as_float(static_cast<unsigned int>(e2 >> 32));
       const size_t o = base + row;
       if (need == L2F_NEED_FULL) {
@@ -213,19 +253,26 @@ l2f_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm,
         }
       } else {
         const float D1 = __fsqrt_rn(d1sq);
-        if (lbn == inf || (d1sq < lbn && d2sq < lbn)) {
+        const float rest = fminf(lbn, low);              // every column that was not evaluated in full is >= rest
+        if ((lbn == inf && !any_gave_up) || (d1sq < rest && d2sq < rest)) {
           done = true;                                   // both neighbours certain
           if (l == 0) ff_write_exact(knn_idx, knn_dist, o, e1, e2);
-        } else if (d1sq < lbn && D1 < __fmul_rn(ratio, __fsqrt_rn(lbn))) {
-          done = true;                                   // nearest certain, true d2 >= lbn: passes whatever d2 is
+        } else if (d1sq < rest && D1 < __fmul_rn(ratio, __fsqrt_rn(fminf(rest, d2sq)))) {
+          done = true;                                   // nearest certain, true d2 >= min(rest, d2sq): passes whatever it is
           if (l == 0) {
             knn_idx[o] = make_int2(static_cast<int>(e1 & 0xFFFFFFFFull), 0x7ffffffe);
-            knn_dist[o] = make_float2(D1, __fsqrt_rn(lbn));
+            knn_dist[o] = make_float2(D1, __fsqrt_rn(fminf(rest, d2sq)));
           }
-        } else if (__fsqrt_rn(fminf(d1sq, lbn)) >= __fmul_rn(ratio, __fsqrt_rn(d2sq))) {
-          done = true;                                   // true d1 >= min(d1sq, lbn), true d2 <= d2sq: fails
+        } else if (__fsqrt_rn(fminf(d1sq, rest)) >= __fmul_rn(ratio, __fsqrt_rn(d2sq))) {
+          done = true;                                   // true d1 >= min(d1sq, rest), true d2 <= d2sq: fails
           if (l == 0) { knn_idx[o] = make_int2(-1, -1); knn_dist[o] = make_float2(inf, inf); }
         }
+      }
+      if (!done && any_gave_up) {                        // uniform over the half-warp: redo this chunk in full
+        early = false;
+        e1 = e2 = KEY_NONE64;
+        --n_chunks;
+        --j;
       }
     }
     if (!done && l == 0) ovf[atomicAdd(&n_ovf, 1)] = r;
