@@ -473,7 +473,7 @@ def main():
                    (int(allsum(d_own.numel() * d_own.element_size() + x_own.numel() * x_own.element_size())) if sharded else 0),
                    d2h_bytes_per_step=int(allsum(st2["d2h_bytes"]) / a.steps),
                    timing="host wall clock around %s x images + match_all_pairs, max over ranks" %
-                          ("set_image_async" if use_async and not sharded else "set_image"))
+                          ("set_image_async" if use_async and not sharded else "NCCL all-gather + set_image_device_async" if use_async else "set_image"))
         if sharded:
             e2e["allgather_bytes_per_step"] = int(world * (d_own.numel() * d_own.element_size() + x_own.numel() * x_own.element_size()))
 

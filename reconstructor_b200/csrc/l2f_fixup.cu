@@ -106,6 +106,51 @@ __device__ __forceinline__ bool ff_dist_below(const float* __restrict__ qs, cons
   return true;
 }
 
+// One 16-column chunk by a half-warp, lane l = column cb + l, same fp32 chain per column as ff_dist -- but the rows
+// travel through shared memory in blocks of 32 dimensions: the half-warp fetches two rows per load instruction as
+// contiguous 128-byte pieces (4 cache lines per warp instruction instead of the 32 that one-row-per-lane loads
+// touch: the kernel was bound by L1 request throughput) and each lane then runs its own chain out of the staged
+// tile.  With THR a column stops as soon as its partial sum reaches thr (see ff_dist_below) and its row is no
+// longer fetched.  Returns true when the lane holds a finished chain (*out); false for abandoned / absent columns.
+static constexpr int FF_BLK = 32;                 // dimensions per staged block
+static constexpr int FF_TLD = FF_BLK + 4;         // padded row of the staged tile (conflict-free float4 reads)
+template <bool THR>
+__device__ __forceinline__ bool ff_chunk_rows(float* __restrict__ ts, const float* __restrict__ qs,
+                                              const float* __restrict__ tbase, int cb, int ncol, int dim, int l,
+                                              unsigned hmask, float thr, float* out) {
+  float acc = 0.f;
+  bool alive = l < ncol;
+  const int sub = l >> 3, piece = l & 7;
+  const int shift = (hmask & 1u) ? 0 : 16;
+  for (int k0 = 0; k0 < dim; k0 += FF_BLK) {
+    const unsigned am = (__ballot_sync(hmask, alive) >> shift) & 0xFFFFu;
+    if (am == 0) break;
+    __syncwarp(hmask);                               // the previous block has been consumed
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = 2 * i + sub;
+      if ((am >> r) & 1u)
+        *reinterpret_cast<float4*>(ts + r * FF_TLD + 4 * piece) =
+            __ldg(reinterpret_cast<const float4*>(tbase + static_cast<size_t>(cb + r) * dim + k0) + piece);
+    }
+    __syncwarp(hmask);
+    if (alive) {
+#pragma unroll
+      for (int k = 0; k < FF_BLK; k += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(ts + l * FF_TLD + k);
+        const float4 a = *reinterpret_cast<const float4*>(qs + k0 + k);
+        float d = a.x - b.x; acc = fmaf(d, d, acc);
+        d = a.y - b.y; acc = fmaf(d, d, acc);
+        d = a.z - b.z; acc = fmaf(d, d, acc);
+        d = a.w - b.w; acc = fmaf(d, d, acc);
+      }
+      if (THR && acc >= thr) alive = false;
+    }
+  }
+  *out = acc;
+  return alive;
+}
+
 __device__ __forceinline__ void ff_merge(unsigned long long& m1, unsigned long long& m2, unsigned long long o1,
                                          unsigned long long o2) {
   const unsigned long long lo = m1 < o1 ? m1 : o1;
@@ -128,12 +173,13 @@ __device__ __forceinline__ void ff_write_exact(int2* knn_idx, float2* knn_dist, 
   knn_dist[o] = od;
 }
 
-__global__ void __launch_bounds__(FF_THREADS)
+__global__ void __launch_bounds__(FF_THREADS, 5)
 l2f_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm, int dim,
                  const PairJob* __restrict__ jobs, int2* __restrict__ knn_idx, float2* __restrict__ knn_dist,
                  const float2* __restrict__ extra, int stride, float ratio, int need,
                  unsigned long long* __restrict__ counters, int e_mode) {
   __shared__ __align__(16) float qs[FF_HW][FF_MAXDIM];
+  __shared__ __align__(16) float ts[FF_HW][16 * FF_TLD];
   __shared__ float keys_s[FF_SPAN][6];
   __shared__ int list[FF_SPAN];
   __shared__ int ovf[FF_SPAN];
@@ -214,11 +260,12 @@ l2f_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm,
         thr = fminf(bd.lb(keys_s[r][1]), r2 > 0.f ? __fmul_ru(__fdiv_ru(bd.ub(Kj), r2), 1.0001f) : inf);
       }
       bool gave_up = false;
-      if (l < ncol) {
+      {
         float d2;
-        if (use_thr) gave_up = !ff_dist_below(qs[hw], tbase + static_cast<size_t>(cb + l) * dim, dim, thr, &d2);
-        else d2 = ff_dist(qs[hw], tbase + static_cast<size_t>(cb + l) * dim, dim);
-        if (!gave_up)
+        const bool have = use_thr ? ff_chunk_rows<true>(ts[hw], qs[hw], tbase, cb, ncol, dim, l, hmask, thr, &d2)
+                                  : ff_chunk_rows<false>(ts[hw], qs[hw], tbase, cb, ncol, dim, l, hmask, thr, &d2);
+        gave_up = l < ncol && !have;
+        if (have)
           k1 = (static_cast<unsigned long long>(__float_as_uint(d2)) << 32) | static_cast<unsigned int>(cb + l);
       }
       const bool any_gave_up = use_thr && __any_sync(hmask, gave_up);
