@@ -31,7 +31,10 @@
 
 namespace pm {
 
-static constexpr int RS_THREADS = 128;   // 16 K registers per block: co-resident with the persistent tensor kernel
+#ifndef PM_RS_THREADS
+#define PM_RS_THREADS 128
+#endif
+static constexpr int RS_THREADS = PM_RS_THREADS;   // 128: 16 K registers per block, co-resident with the persistent tensor kernel
 static constexpr int RS_ROUND = 32;
 
 struct MwcRng {
@@ -402,15 +405,18 @@ __device__ __forceinline__ int inlier_of(const double* F, float2 q1, float2 q2, 
 
 // Adds, for every model of the round, the number of inliers among this thread's four points to sCnt.
 template <int MODE>
-__device__ __forceinline__ void score_models(const double (*sF)[27], const int* sNm, int (*sCnt)[3], int gen,
-                                             const float2 (&q1)[4], const float2 (&q2)[4], const bool (&valid)[4],
-                                             float thr, double lo, double hi, int lane) {
+__device__ __forceinline__ void score_models(const double (*sF)[27], const int* sNm, int (*sCnt)[3],
+                                             const unsigned* sDead, int gen, const float2 (&q1)[4],
+                                             const float2 (&q2)[4], const bool (&valid)[4], float thr, double lo,
+                                             double hi, int lane) {
   Pt4 p[4];
 #pragma unroll
   for (int u = 0; u < 4; ++u) p[u] = Pt4{q1[u].x, q1[u].y, q2[u].x, q2[u].y};
   for (int k = 0; k < gen; ++k) {
     const int nm = sNm[k];
+    const unsigned dead = sDead[k];
     for (int m = 0; m < nm; ++m) {
+      if ((dead >> m) & 1u) continue;                  // cannot beat the best model any more (see the caller)
       double F[9];
 #pragma unroll
       for (int i = 0; i < 9; ++i) F[i] = sF[k][9 * m + i];
@@ -471,7 +477,7 @@ __device__ __forceinline__ bool pair_collinear(const float2* __restrict__ p, con
          static_cast<double>(FLT_EPSILON) * (fabs(dx1) + fabs(dy1) + fabs(dx2) + fabs(dy2));
 }
 
-__global__ void __launch_bounds__(RS_THREADS, 4)
+__global__ void __launch_bounds__(RS_THREADS, 512 / RS_THREADS)
 fmat_ransac_kernel(const float2* __restrict__ pts1, const float2* __restrict__ pts2,
                    const int32_t* __restrict__ count, int stride, RansacDev prm,
                    uint8_t* __restrict__ mask, double* __restrict__ F_out,
@@ -490,6 +496,7 @@ fmat_ransac_kernel(const float2* __restrict__ pts1, const float2* __restrict__ p
   __shared__ int sSub[RS_ROUND][7];
   __shared__ int sNm[RS_ROUND];
   __shared__ int sCnt[RS_ROUND][3];
+  __shared__ unsigned sDead[RS_ROUND];                  // bit m: model m of the hypothesis is out of the race
   __shared__ int sGen, sStop, sIter, sNiters, sBest;
 
   if (!prm.do_filter || M < prm.min_matches) {
@@ -595,8 +602,20 @@ fmat_ransac_kernel(const float2* __restrict__ pts1, const float2* __restrict__ p
     // ---- score: every thread owns four matches at a time and visits all models of the round (the model
     //      is a shared-memory broadcast, the points stay in registers as doubles) ---------------------
     for (int w = tid; w < gen * 3; w += RS_THREADS) sCnt[w / 3][w % 3] = 0;
+    for (int w = tid; w < gen; w += RS_THREADS) sDead[w] = 0u;
     __syncthreads();
     for (int i0 = 0; i0 < M; i0 += 4 * RS_THREADS) {
+      if (i0 > 0) {
+        // A model replaces the best one only with STRICTLY more inliers (and more than 6).  Once its count so far
+        // plus all the matches not yet visited cannot exceed the best count from before this round, its exact
+        // count no longer matters: it is dropped from the remaining blocks.  Its partial count stays <= the
+        // bound, so the selection below ignores it exactly as it would ignore the full count.
+        __syncthreads();
+        const int bound = sBest > 6 ? sBest : 6;
+        for (int w = tid; w < gen * 3; w += RS_THREADS)
+          if (w % 3 < sNm[w / 3] && sCnt[w / 3][w % 3] + (M - i0) <= bound) atomicOr(&sDead[w / 3], 1u << (w % 3));
+        __syncthreads();
+      }
       float2 q1[4], q2[4];
       bool valid[4];
 #pragma unroll
@@ -607,8 +626,8 @@ fmat_ransac_kernel(const float2* __restrict__ pts1, const float2* __restrict__ p
         q1[u] = p1[ic];
         q2[u] = p2[ic];
       }
-      if (prm.residual_mode == 1) score_models<1>(sF, sNm, sCnt, gen, q1, q2, valid, prm.thr, thr_lo, thr_hi, lane);
-      else score_models<0>(sF, sNm, sCnt, gen, q1, q2, valid, prm.thr, thr_lo, thr_hi, lane);
+      if (prm.residual_mode == 1) score_models<1>(sF, sNm, sCnt, sDead, gen, q1, q2, valid, prm.thr, thr_lo, thr_hi, lane);
+      else score_models<0>(sF, sNm, sCnt, sDead, gen, q1, q2, valid, prm.thr, thr_lo, thr_hi, lane);
     }
     __syncthreads();
     PM_PHASE(tC);
