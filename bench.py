@@ -312,8 +312,12 @@ def main():
         if not sharded:
             # asynchronous: pm_set_image_async from pinned buffers -- the uploads are queued and the first batches
             # of pm_match_all_pairs run while the later images are still on their way (the pair list is ordered)
+            if asynchronous:
+                pm.set_images_ptr_async(list(range(len(pinned))), [td.data_ptr() for td, _ in pinned],
+                                        [td.shape[0] for td, _ in pinned], dim, dt, [tx.data_ptr() for _, tx in pinned])
+                return
             for i, (td, tx) in enumerate(pinned):
-                pm.set_image_ptr(i, td.data_ptr(), td.shape[0], dim, dt, tx.data_ptr(), asynchronous=asynchronous)
+                pm.set_image_ptr(i, td.data_ptr(), td.shape[0], dim, dt, tx.data_ptr())
             return
         d_dev = d_own.cuda(non_blocking=True); x_dev = x_own.cuda(non_blocking=True)
         all_d = torch.empty((world,) + tuple(d_dev.shape), dtype=d_dev.dtype, device="cuda")
@@ -473,7 +477,7 @@ def main():
                    (int(allsum(d_own.numel() * d_own.element_size() + x_own.numel() * x_own.element_size())) if sharded else 0),
                    d2h_bytes_per_step=int(allsum(st2["d2h_bytes"]) / a.steps),
                    timing="host wall clock around %s x images + match_all_pairs, max over ranks" %
-                          ("set_image_async" if use_async and not sharded else "NCCL all-gather + set_image_device_async" if use_async else "set_image"))
+                          ("set_images_async" if use_async and not sharded else "NCCL all-gather + set_image_device_async" if use_async else "set_image"))
         if sharded:
             e2e["allgather_bytes_per_step"] = int(world * (d_own.numel() * d_own.element_size() + x_own.numel() * x_own.element_size()))
 

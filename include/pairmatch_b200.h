@@ -164,6 +164,9 @@ int pm_set_image_device(pm_handle h, int img_id, const void* d_desc, int n, int 
  * visits every image against all earlier ones, so early batches need only the first images. */
 int pm_set_image_async(pm_handle h, int img_id, const void* desc, int n, int dim, int dtype,
                        const int32_t* xy);
+/* pm_set_image_async for a whole set in one call (descs[k]: ns[k] rows, xys may be NULL or hold NULLs). */
+int pm_set_images_async(pm_handle h, int n_images, const int* img_ids, const void* const* descs, const int* ns,
+                        int dim, int dtype, const int32_t* const* xys);
 /* pm_set_image_device without the host synchronisation (same lifetime rule for the device buffers). */
 int pm_set_image_device_async(pm_handle h, int img_id, const void* d_desc, int n, int dim, int dtype,
                               const int32_t* d_xy);

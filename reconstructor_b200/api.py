@@ -29,7 +29,7 @@ OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_OOM, ERR_STATE, ERR_UNSUPPORTED = 
 
 EXPORTS = [
     "pm_default_params", "pm_create", "pm_destroy", "pm_last_error", "pm_version", "pm_set_image",
-    "pm_set_image_device", "pm_set_image_async", "pm_set_image_device_async", "pm_sync_images", "pm_num_keypoints", "pm_knn_pair", "pm_match_pair",
+    "pm_set_image_device", "pm_set_image_async", "pm_set_images_async", "pm_set_image_device_async", "pm_sync_images", "pm_num_keypoints", "pm_knn_pair", "pm_match_pair",
     "pm_match_descriptors", "pm_filter_pair_F", "pm_match_filter_pair", "pm_match_all_pairs",
     "pm_free_result", "pm_get_stats", "pm_reset_stats", "pm_measure_popc_peak",
     "pm_save_images", "pm_load_images", "pm_save_result", "pm_load_result",
@@ -96,6 +96,8 @@ def load_library() -> C.CDLL:
         lib.pm_set_image_async.argtypes = lib.pm_set_image.argtypes
         lib.pm_set_image_device_async.argtypes = lib.pm_set_image.argtypes
         lib.pm_sync_images.argtypes = [C.c_void_p]
+        lib.pm_set_images_async.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                            C.c_void_p]
         lib.pm_num_keypoints.argtypes = [C.c_void_p, C.c_int]
         lib.pm_knn_pair.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         lib.pm_debug_tc_dump.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -201,6 +203,17 @@ class PairMatcher:
             f = self.lib.pm_set_image_async if asynchronous else self.lib.pm_set_image
         self._check(f(self.h, img_id, desc_ptr, n, dim, dtype, xy_ptr))
         self._n[img_id] = n
+
+    def set_images_ptr_async(self, ids, desc_ptrs, ns, dim: int, dtype: int, xy_ptrs=None):
+        """pm_set_images_async: one call for a whole image set held in (pinned) host buffers."""
+        n = len(ids)
+        a_ids = (C.c_int * n)(*ids)
+        a_desc = (C.c_void_p * n)(*desc_ptrs)
+        a_ns = (C.c_int * n)(*ns)
+        a_xy = (C.c_void_p * n)(*xy_ptrs) if xy_ptrs is not None else None
+        self._check(self.lib.pm_set_images_async(self.h, n, a_ids, a_desc, a_ns, dim, dtype, a_xy))
+        for i, k in zip(ids, ns):
+            self._n[i] = k
 
     def sync_images(self):
         self._check(self.lib.pm_sync_images(self.h))

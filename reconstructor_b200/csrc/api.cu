@@ -964,7 +964,10 @@ struct DeviceCtx {
       Slot& s = slots[b % S];
       int rc = retrieve(s, R);
       if (rc != PM_OK) return rc;
-      const int n = static_cast<int>(std::min<int64_t>(B, n_pairs - done));
+      // the first batches are short: with asynchronous ingest they need only the first few images (pair lists run
+      // image by image), so the device starts after a fraction of the upload
+      const int ramp = b < 3 ? std::max(16, B >> (3 - b)) : B;
+      const int n = static_cast<int>(std::min<int64_t>(std::min(B, ramp), n_pairs - done));
       for (int k = 0; k < n; ++k) {
         rc = fill_job(s, k, pairs[2 * (done + k)], pairs[2 * (done + k) + 1]);
         if (rc != PM_OK) return rc;
@@ -1106,6 +1109,21 @@ int pm_set_image_async(pm_handle h, int img_id, const void* desc, int n, int dim
   for (auto& d : h->devs) {
     const int rc = d->set_image(img_id, desc, n, dim, dtype, xy, false, true);
     if (rc != PM_OK) return h->from(*d, rc);
+  }
+  return PM_OK;
+}
+
+int pm_set_images_async(pm_handle h, int n_images, const int* img_ids, const void* const* descs, const int* ns,
+                        int dim, int dtype, const int32_t* const* xys) {
+  if (!h) return PM_ERR_INVALID;
+  if (n_images < 0 || (n_images > 0 && (!img_ids || !descs || !ns))) return h->fail(PM_ERR_INVALID, "set_images: bad arguments");
+  std::lock_guard<std::mutex> lk(h->mu);
+  for (int k = 0; k < n_images; ++k) {
+    if (img_ids[k] == kTmpA || img_ids[k] == kTmpB) return h->fail(PM_ERR_INVALID, "reserved image id");
+    for (auto& d : h->devs) {
+      const int rc = d->set_image(img_ids[k], descs[k], ns[k], dim, dtype, xys ? xys[k] : nullptr, false, true);
+      if (rc != PM_OK) return h->from(*d, rc);
+    }
   }
   return PM_OK;
 }

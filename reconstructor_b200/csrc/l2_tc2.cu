@@ -22,11 +22,6 @@
 #include "common.cuh"
 #include "kernels.h"
 
-// i8 epilogue schedule (A/B builds): 0 = load 64 columns, reduce; 1 = one tcgen05.ld in flight while 32 columns are
-// reduced; 2 = as 1, but never blocks on the next accumulator while a loaded chunk is still unreduced
-#ifndef PM_I8_EPI
-#define PM_I8_EPI 0
-#endif
 // timing-probe dissection (MODE 1 only, A/B builds): skip the accumulator hand-shake / the train-tile TMA
 #ifndef PM_PROBE_NOACC
 #define PM_PROBE_NOACC 0
@@ -387,9 +382,8 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
   constexpr int KA = Cfg::kKA, T2_TILE = Cfg::kATile, T2_SMEM_A = Cfg::kAStages * Cfg::kATile, AST = Cfg::kAStages;
   constexpr int KEL = KIND >= 1 ? 128 : 64;        // tensor-map elements per 128-byte K atom (bytes / fp16)
   constexpr int AG = Cfg::kAG;
-  static_assert(KIND != 2 || MODE == 2 || MODE == 1 || MODE == 5, "the i8 form has a values-only epilogue");
-  static_assert(KIND != 2 || Cfg::kCPW == 2, "the pipelined i8 epilogue handles two 32-column chunks per warp");
-  constexpr int KDIM = KEL * KA;
+  static_assert(KIND != 2 || MODE == 2 || MODE == 1, "the i8 form has a values-only epilogue");
+    constexpr int KDIM = KEL * KA;
   constexpr int T2_BATOM = Cfg::kBAtom, T2_BTILE = Cfg::kBTile, CPW = Cfg::kCPW, NSL = Cfg::kSlices;
   constexpr int NGRP = Cfg::kGroups;
   constexpr uint32_t T2_IDESC = KIND == 2 ? Cfg::kIdescI8 : KIND == 3 ? Cfg::kIdescS8 : Cfg::kIdesc;
@@ -544,43 +538,6 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
       si.m1 = si.m2 = T2I_INF;
       si.i1 = -1;
       const int n_tiles = (job.nt + T2_BN - 1) / T2_BN;
-      if (KIND == 2 && (MODE == 2 || MODE == 5) && PM_I8_EPI >= 1) {
-        // software-pipelined: the tcgen05.ld of the next 32 columns is in flight while these 32 are reduced, so
-        // that the TMEM read port (64 B/clk per sub-partition: 512 of the tile's 640 MMA cycles) never idles
-        uint32_t va[32], vb[32];
-        const uint32_t tq = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + slice * 64;
-        wait_trap(&acc_full[ti & 1], (ti >> 1) & 1);
-        tc_fence_after();
-        tmem_ld_32x32b_x32_async(tq + (ti & 1) * T2_BN, va);
-        for (int n = 0; n < n_tiles; ++n, ++ti) {
-          const uint32_t as = ti & 1;
-          const int c0 = n * T2_BN + slice * 64;
-          const int lim = job.nt - c0;
-          tmem_wait_pin(va);
-          tmem_ld_32x32b_x32_async(tq + as * T2_BN + 32, vb);
-          if (MODE == 2) t2i_chunk32(si, va, c0, lim);
-          tmem_wait_pin(vb);
-          tc_fence_before();
-          if (lane == 0) mbar_arrive_leader(&acc_empty[as]);
-          const uint32_t t2 = ti + 1;
-          if (PM_I8_EPI == 2 && (n + 1 >= n_tiles || !mbar_try_wait(&acc_full[t2 & 1], (t2 >> 1) & 1))) {
-            // the next accumulator is not there yet: reduce first, then wait for it
-            if (MODE == 2) t2i_chunk32(si, vb, c0 + 32, lim - 32);
-            if (n + 1 < n_tiles) {
-              wait_trap(&acc_full[t2 & 1], (t2 >> 1) & 1);
-              tc_fence_after();
-              tmem_ld_32x32b_x32_async(tq + (t2 & 1) * T2_BN, va);
-            }
-          } else {
-            if (n + 1 < n_tiles) {
-              if (PM_I8_EPI != 2) wait_trap(&acc_full[t2 & 1], (t2 >> 1) & 1);
-              tc_fence_after();
-              tmem_ld_32x32b_x32_async(tq + (t2 & 1) * T2_BN, va);
-            }
-            if (MODE == 2) t2i_chunk32(si, vb, c0 + 32, lim - 32);
-          }
-        }
-      } else
       for (int n = 0; n < ((MODE == 1 && PM_PROBE_NOACC) ? 0 : n_tiles); ++n, ++ti) {
         const uint32_t as = ti & 1, use = ti >> 1;
         wait_trap(&acc_full[as], use & 1);
@@ -756,8 +713,6 @@ cudaError_t tc2_configure() {
   if ((e = cudaFuncSetAttribute(l2_top2_tc2_kernel<T2I8, 2, false, 2>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                 cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(l2_top2_tc2_kernel<T2I8, 1, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                T2I8::kSmemBytes)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(l2_top2_tc2_kernel<T2I8, 5, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 T2I8::kSmemBytes)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(l2_top2_tc2_kernel<T2I8, 2, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 T2I8::kSmemBytes)) != cudaSuccess) return e;
@@ -1126,8 +1081,9 @@ cudaError_t launch_l2i8x2(const TcMaps& maps, const PairJob* jobs, int n_jobs, i
 }
 
 // Integer-valued 128-d rows in the i8 form (pack_sift_kernel): D' per row in (knn_idx = chunk base, -3 |
-// knn_dist = int bits of m1, m2'); l2_fixup_i8 follows.  probe: timing probes (no results): 1 = TMA + MMA only,
-// 2 = + tcgen05.ld of the accumulators.
+// knn_dist = int bits of m1, m2'); l2_fixup_i8 follows.  One query row set per cluster (the two-set kernel
+// l2_i8x2_kernel above is the default; this one is kept for A/B and parity).  probe: 1 / 2 = TMA + MMA timing probe
+// (no results), 3 = 64-register build.
 cudaError_t launch_l2i8_tc2(const TcMaps& maps, const PairJob* jobs, int n_jobs, int max_nq, int2* idx, float2* dist,
                             int stride, int num_sms, int probe, cudaStream_t st) {
   if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
@@ -1138,9 +1094,6 @@ cudaError_t launch_l2i8_tc2(const TcMaps& maps, const PairJob* jobs, int n_jobs,
   const int grid = clusters * 2;
   if (probe == 3)     // 64-register build: the tail kernels of the previous batch can be co-resident
     l2_top2_tc2_kernel<T2I8, 2, true, 2><<<grid, T2I8::kThreads, T2I8::kSmemBytes, st>>>(
-        maps.q_main, maps.q_ext, maps.t_main, maps.t_ext, nullptr, jobs, n_jobs, tiles_per_job, idx, dist, stride, nullptr);
-  else if (probe == 2)     // tcgen05.ld without the reduction
-    l2_top2_tc2_kernel<T2I8, 5, false, 2><<<grid, T2I8::kThreads, T2I8::kSmemBytes, st>>>(
         maps.q_main, maps.q_ext, maps.t_main, maps.t_ext, nullptr, jobs, n_jobs, tiles_per_job, idx, dist, stride, nullptr);
   else if (probe)
     l2_top2_tc2_kernel<T2I8, 1, false, 2><<<grid, T2I8::kThreads, T2I8::kSmemBytes, st>>>(

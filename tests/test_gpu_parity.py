@@ -407,7 +407,8 @@ def test_batched_fast_path_equals_general_kernel_full_size():
     outs = []
     # values-only kernels (byte form on kind::i8 = default, fp16 form: CTA pair 256-col, single-CTA, pair 192-col),
     # general tensor kernels (single-CTA, CTA pair), fp32 SIMT
-    for flags in (0, 2048, 128, 256, 64, 64 + 20, 1):
+    # + byte form with one query row set per cluster (16384) and its 64-register build
+    for flags in (0, 2048, 16384, 16384 + 12288, 12288, 128, 256, 64, 64 + 20, 1):
         with api.PairMatcher(debug_flags=flags) as pm:
             for i, (d, xy) in enumerate(imgs):
                 pm.set_image(i, d, xy)
@@ -738,8 +739,12 @@ def test_async_ingest_gives_identical_results(kind):
     for asyn in (False, True):
         with api.PairMatcher(batch_pairs=4) as pm:
             for rep in range(2):                               # re-ingest over resident images too
-                for i, (td, tx) in enumerate(pinned):
-                    pm.set_image_ptr(i, td.data_ptr(), td.shape[0], dim, dt, tx.data_ptr(), asynchronous=asyn)
+                if asyn and rep == 1:                          # the whole set in one call
+                    pm.set_images_ptr_async(list(range(len(pinned))), [td.data_ptr() for td, _ in pinned],
+                                            [td.shape[0] for td, _ in pinned], dim, dt, [tx.data_ptr() for _, tx in pinned])
+                else:
+                    for i, (td, tx) in enumerate(pinned):
+                        pm.set_image_ptr(i, td.data_ptr(), td.shape[0], dim, dt, tx.data_ptr(), asynchronous=asyn)
                 if rep == 0 and asyn:
                     pm.sync_images()
             outs.append(pm.match_all_pairs())
