@@ -850,10 +850,12 @@ struct DeviceCtx {
     }
     s.h_jobs[k] = PairJob{a->second.row, b->second.row, a->second.n, b->second.n, a->second.maxn, b->second.maxn};
     if (static_cast<int>(job_integral.size()) <= k) { job_integral.resize(k + 1); job_unit.resize(k + 1); job_i8.resize(k + 1); job_s8.resize(k + 1); }
-    job_i8[k] = a->second.i8_ok && b->second.i8_ok;
-    job_s8[k] = a->second.s8_ok && b->second.s8_ok;
-    job_integral[k] = a->second.integral && b->second.integral;
-    job_unit[k] = a->second.unit_ok && b->second.unit_ok;
+    // an empty image is compatible with every path (its pairs have no rows to search)
+    const Image &ia = a->second, &ib = b->second;
+    job_integral[k] = (ia.integral || ia.n == 0) && (ib.integral || ib.n == 0);
+    job_unit[k] = (ia.unit_ok || ia.n == 0) && (ib.unit_ok || ib.n == 0);
+    job_i8[k] = (ia.i8_ok || ia.n == 0) && (ib.i8_ok || ib.n == 0);
+    job_s8[k] = (ia.s8_ok || ia.n == 0) && (ib.s8_ok || ib.n == 0);
     return PM_OK;
   }
 

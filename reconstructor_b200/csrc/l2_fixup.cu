@@ -185,7 +185,7 @@ static constexpr int FXI_INF = 0x7f800000;   // T2I_INF of l2_tc2.cu
 __device__ __forceinline__ unsigned int fx_chunk_key_prefix(const uint32_t* __restrict__ u8desc,
                                                             const int32_t* __restrict__ qnorm, const PairJob& jb,
                                                             int cb, int l, uint32_t qw, const uint32_t* qs, int na,
-                                                            int d1_hi, float ratio, int all_rows) {
+                                                            int d1_hi, float ratio, int all_rows, int* elim_lo) {
   const int ncol = min(32, jb.nt - cb);
   const uint32_t* trow = u8desc + (static_cast<size_t>(jb.t_row) + cb) * 32;
   uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0;
@@ -204,6 +204,8 @@ __device__ __forceinline__ unsigned int fx_chunk_key_prefix(const uint32_t* __re
   if (surv && part > d1_hi)
     surv = !all_rows && !(__fsqrt_rn(static_cast<float>(d1_hi)) < __fmul_rn(ratio, __fsqrt_rn(static_cast<float>(part))));
   unsigned int alive = __ballot_sync(0xffffffffu, surv);
+  // smallest partial distance among the dropped columns (a lower bound of their distances that still passes the test)
+  *elim_lo = static_cast<int>(__reduce_min_sync(0xffffffffu, (l < ncol && !surv) ? static_cast<unsigned int>(part) : 0x7f800000u));
   unsigned int key = 0xFFFFFFFFu;
   while (alive) {
     const int j = __ffs(alive) - 1;
@@ -270,9 +272,11 @@ l2_fixup_i8_kernel(const uint32_t* __restrict__ u8desc, const int32_t* __restric
     const uint32_t* qs = u8desc + (static_cast<size_t>(jb.q_row) + row) * 32;
     const uint32_t q0 = __ldg(qs + l), q1 = CH == 16 ? __ldg(qs + 16 + l) : 0u;
     unsigned int key;
+    int elim_lo = FXI_INF;                             // FXI_INF: no column was dropped by the prefix filter
     if (CH == 32 && PM_I8_PREFIX) {
       const int m1 = __float_as_int(knn_dist[base + row].x);
-      key = fx_chunk_key_prefix(u8desc, qnorm, jb, cb, l, q0, qs, na, qoff[jb.q_row + row] + 2 * m1 + 1, ratio, all_rows);
+      key = fx_chunk_key_prefix(u8desc, qnorm, jb, cb, l, q0, qs, na, qoff[jb.q_row + row] + 2 * m1 + 1, ratio, all_rows,
+                                &elim_lo);
     } else {
       key = fx_chunk_key<CH>(st, u8desc, qnorm, jb, cb, l, gmask, q0, q1, na);
     }
@@ -283,6 +287,8 @@ l2_fixup_i8_kernel(const uint32_t* __restrict__ u8desc, const int32_t* __restric
     bool rescan = false;
     if (m2 == FXI_INF) {                               // a single chunk: everything is in it
       if (k2 != 0xFFFFFFFFu) { d2 = static_cast<int>(k2 >> 5); i2 = cb + static_cast<int>(k2 & 31u); }
+      else if (elim_lo != FXI_INF) { d2 = elim_lo; i2 = 0x7ffffffe; }   // second neighbour among the dropped columns:
+                                                       // it exists and Lowe's test passes against it whatever it is
     } else {
       const int others = qoff[jb.q_row + row] + 2 * m2;        // smallest outside distance is others or others + 1
       const int c2 = k2 != 0xFFFFFFFFu ? static_cast<int>(k2 >> 5) : FXI_INF;

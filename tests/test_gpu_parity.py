@@ -819,6 +819,79 @@ def test_s8_quantised_fallback_on_large_entries_and_full_size():
     _csr_equal(outs[0], outs[1])
     assert outs[0]["offsets"][-1] > 6 * 1000
 
+
+@pytest.mark.parametrize("kind", ["sift", "superpoint", "orb"])
+def test_batched_paths_edge_sizes_equal_reference_kernels(kind):
+    """Image sizes around every tiling boundary of the batched tensor paths (empty image, 1 row, 32-column chunks,
+    256-row tiles, the 512-row work item of the two-set kernel): default path == SIMT / popc path, array for array."""
+    rng = np.random.default_rng(31)
+    sizes = (1, 2, 31, 32, 33, 255, 256, 257, 511, 512, 513, 769, 0)
+    if kind == "sift":
+        base = rng.integers(0, 60, (1200, 128)).astype(np.float32)
+        noise = lambda n: rng.integers(-3, 4, (n, 128))
+        make = lambda ids: np.clip(base[ids] + noise(len(ids)), 0, 255).astype(np.float32)
+        ref_flags = 1
+    elif kind == "superpoint":
+        base = _unit_rows(rng, 1200, 256)
+        def make(ids):
+            d = base[ids] + 0.3 * rng.standard_normal((len(ids), 256)).astype(np.float32) / 16
+            return (0.999 * d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+        ref_flags = 1
+    else:
+        base = rng.integers(0, 256, (1200, 32), dtype=np.uint8)
+        def make(ids):
+            d = base[ids].copy()
+            d ^= ((rng.random(d.shape) < 0.05) * rng.integers(1, 256, d.shape)).astype(np.uint8)
+            return d
+        ref_flags = FORCE_POPC
+    imgs = [make(rng.permutation(1200)[:n]) if n else np.zeros((0, base.shape[1]), base.dtype) for n in sizes]
+    outs = []
+    for flags in (0, ref_flags):
+        with api.PairMatcher(do_filter=0, batch_pairs=16, debug_flags=flags) as pm:
+            for i, d in enumerate(imgs):
+                pm.set_image(i, d)
+            outs.append(pm.match_all_pairs())
+    _csr_equal(outs[0], outs[1], ("pair_ij", "offsets", "q", "t", "status"))
+    assert outs[0]["offsets"][-1] > 2000
+
+
+@pytest.mark.parametrize("seed", list(range(6)))
+@pytest.mark.parametrize("kind", ["sift", "superpoint"])
+def test_fuzz_batched_paths_vs_reference_kernels(kind, seed):
+    """Random image sizes, value ranges, duplicated and shared rows, all uniqueness modes: the default batched path
+    (byte / s8 forms on kind::i8 + fix-up / re-rank) must equal the fp32 SIMT path array for array."""
+    rng = np.random.default_rng(1000 * seed + (7 if kind == "sift" else 13))
+    n_img = int(rng.integers(3, 7))
+    pool = 1500
+    if kind == "sift":
+        hi = int(rng.choice([2, 4, 30, 120, 256]))
+        base = rng.integers(0, hi, (pool, 128)).astype(np.float32)
+    else:
+        base = _unit_rows(rng, pool, int(rng.choice([128, 256])))
+    imgs = []
+    for i in range(n_img):
+        n = int(rng.choice([1, 5, 31, 33, 64, 200, 257, 400, 700, 1030]))
+        ids = rng.integers(0, pool, n)                           # with repetition: duplicate rows inside an image
+        d = base[ids].copy()
+        if kind == "sift":
+            amp = int(rng.choice([0, 1, 3]))
+            if amp:
+                d = np.clip(d + rng.integers(-amp, amp + 1, d.shape), 0, 255).astype(np.float32)
+        else:
+            d = d + float(rng.choice([0.0, 0.05, 0.3])) * rng.standard_normal(d.shape).astype(np.float32) / np.sqrt(d.shape[1])
+            d = (0.999 * d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+        imgs.append(d)
+    mode = int(rng.choice([api.UNIQUE_FIRST_WINS, api.MUTUAL_NN, api.UNIQUE_NONE]))
+    ratio = float(rng.choice([0.7, 0.95, 0.5]))
+    outs = []
+    for flags in (0, 1):
+        with api.PairMatcher(unique_mode=mode, ratio=ratio, do_filter=0, batch_pairs=int(rng.choice([2, 5, 64])) if flags == 0 else 64,
+                             debug_flags=flags) as pm:
+            for i, d in enumerate(imgs):
+                pm.set_image(i, d)
+            outs.append(pm.match_all_pairs())
+    _csr_equal(outs[0], outs[1], ("pair_ij", "offsets", "q", "t", "status"))
+
 # ---------------------------------------------------------------------------------------------
 # on-disk cache (SURVEY 8f rank 2): resume from files, identical results
 # ---------------------------------------------------------------------------------------------
