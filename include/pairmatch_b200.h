@@ -156,7 +156,8 @@ int pm_set_image(pm_handle h, int img_id, const void* desc, int n, int dim, int 
  * NCCL all-gather of sharded extraction).  Single-device handles only. */
 int pm_set_image_device(pm_handle h, int img_id, const void* d_desc, int n, int dim, int dtype,
                         const int32_t* d_xy);
-/* pm_set_image without the host synchronisation: the upload and the packing kernels are queued on the
+/* pm_set_image (the once-per-image replacement of featDescToCV, FeatureMatcher.cpp:11-25) without the host
+ * synchronisation: the upload and the packing kernels are queued on the
  * handle's ingest stream and the call returns.  desc / xy must stay valid and unchanged until
  * pm_sync_images() or a matching call that uses the image returns (pinned host memory makes the copy
  * truly asynchronous, so the first batches of pm_match_all_pairs overlap the upload of later images;
