@@ -59,6 +59,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--debug-flags", type=int, default=0, help="pm_params.debug_flags (kernel variants)")
     ap.add_argument("--batch-pairs", type=int, default=0)
+    ap.add_argument("--max-pairs", type=int, default=0, help="time a seeded random sample of this many pairs of the all-pairs "
+                    "list instead of all of them (config #5: thousands of images, SURVEY 8d)")
     ap.add_argument("--dev-ratio", type=float, default=None, help="development: Lowe ratio of the main arm (a tiny value "
                     "empties the tail kernels and isolates the kNN kernel)")
     ap.add_argument("--dev-no-filter", action="store_true", help="development: main arm without the epipolar filter")
@@ -212,10 +214,18 @@ def main():
 
     n_img = a.images if n_gpus == 1 else shard.images_for_world(n_gpus, a.images)
     pairs = shard.all_pairs(n_img)
-    cfg = dict(workload=workload_name(a, n_img, len(pairs)), images=n_img, keypoints=a.kp, kind=a.kind,
+    n_all = len(pairs)
+    if a.max_pairs and a.max_pairs < n_all:
+        # pairs are iid here, so a random sample of the list is a steady-state sample of the whole job; sorted so that
+        # the list keeps its image-by-image order
+        pairs = pairs[np.sort(np.random.default_rng(0xB200).choice(n_all, a.max_pairs, replace=False))]
+    cfg = dict(workload=workload_name(a, n_img, n_all), images=n_img, keypoints=a.kp, kind=a.kind,
                pairs=int(len(pairs)), partition=f"pairs sharded over {n_gpus} GPU(s), descriptors replicated",
                l2="inputs larger than L2 (no flush needed)", outlier_frac=a.outlier_frac,
                debug_flags=a.debug_flags)
+    if len(pairs) < n_all:
+        cfg["pairs_timed"] = int(len(pairs))
+        cfg["sample"] = f"seeded random sample of {len(pairs)} of the {n_all} pairs per step"
 
     if a.impl == "reference":
         if rank != 0:
