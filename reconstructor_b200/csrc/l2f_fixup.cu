@@ -114,6 +114,15 @@ __device__ __forceinline__ bool ff_dist_below(const float* __restrict__ qs, cons
 // longer fetched.  Returns true when the lane holds a finished chain (*out); false for abandoned / absent columns.
 static constexpr int FF_BLK = 32;                 // dimensions per staged block
 static constexpr int FF_TLD = FF_BLK + 4;         // padded row of the staged tile (conflict-free float4 reads)
+__device__ __forceinline__ void ff_cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void ff_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void ff_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ts: two staged tiles of 16 x FF_TLD floats (double buffer): block k + 1 is on its way (cp.async) while block k is
+// consumed, so the chain of the surviving column does not wait for memory at every block.
 template <bool THR>
 __device__ __forceinline__ bool ff_chunk_rows(float* __restrict__ ts, const float* __restrict__ qs,
                                               const float* __restrict__ tbase, int cb, int ncol, int dim, int l,
@@ -122,22 +131,29 @@ __device__ __forceinline__ bool ff_chunk_rows(float* __restrict__ ts, const floa
   bool alive = l < ncol;
   const int sub = l >> 3, piece = l & 7;
   const int shift = (hmask & 1u) ? 0 : 16;
-  for (int k0 = 0; k0 < dim; k0 += FF_BLK) {
-    const unsigned am = (__ballot_sync(hmask, alive) >> shift) & 0xFFFFu;
-    if (am == 0) break;
-    __syncwarp(hmask);                               // the previous block has been consumed
+  const float* src = tbase + static_cast<size_t>(cb) * dim + 4 * piece;
+  auto fetch = [&](int k0, int buf, unsigned am) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int r = 2 * i + sub;
-      if ((am >> r) & 1u)
-        *reinterpret_cast<float4*>(ts + r * FF_TLD + 4 * piece) =
-            __ldg(reinterpret_cast<const float4*>(tbase + static_cast<size_t>(cb + r) * dim + k0) + piece);
+      if ((am >> r) & 1u) ff_cp_async16(ts + buf * (16 * FF_TLD) + r * FF_TLD + 4 * piece, src + static_cast<size_t>(r) * dim + k0);
     }
+    ff_cp_commit();
+  };
+  unsigned am = (__ballot_sync(hmask, alive) >> shift) & 0xFFFFu;
+  __syncwarp(hmask);                                 // the tiles are free (previous chunk consumed)
+  if (am) fetch(0, 0, am);
+  int buf = 0;
+  for (int k0 = 0; k0 < dim && am; k0 += FF_BLK, buf ^= 1) {
+    const bool more = k0 + FF_BLK < dim;
+    if (more) fetch(k0 + FF_BLK, buf ^ 1, am);       // for every column still alive BEFORE this block's check
+    if (more) ff_cp_wait<1>(); else ff_cp_wait<0>();
     __syncwarp(hmask);
     if (alive) {
+      const float* tl = ts + buf * (16 * FF_TLD) + l * FF_TLD;
 #pragma unroll
       for (int k = 0; k < FF_BLK; k += 4) {
-        const float4 b = *reinterpret_cast<const float4*>(ts + l * FF_TLD + k);
+        const float4 b = *reinterpret_cast<const float4*>(tl + k);
         const float4 a = *reinterpret_cast<const float4*>(qs + k0 + k);
         float d = a.x - b.x; acc = fmaf(d, d, acc);
         d = a.y - b.y; acc = fmaf(d, d, acc);
@@ -146,7 +162,9 @@ __device__ __forceinline__ bool ff_chunk_rows(float* __restrict__ ts, const floa
       }
       if (THR && acc >= thr) alive = false;
     }
+    am = (__ballot_sync(hmask, alive) >> shift) & 0xFFFFu;      // also: everyone is done with tile `buf`
   }
+  ff_cp_wait<0>();                                   // a prefetch for abandoned columns may still be in flight
   *out = acc;
   return alive;
 }
@@ -179,7 +197,7 @@ l2f_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm,
                  const float2* __restrict__ extra, int stride, float ratio, int need,
                  unsigned long long* __restrict__ counters, int e_mode) {
   __shared__ __align__(16) float qs[FF_HW][FF_MAXDIM];
-  __shared__ __align__(16) float ts[FF_HW][16 * FF_TLD];
+  extern __shared__ __align__(16) float ts_dyn[];       // [FF_HW][2][16 * FF_TLD]: double-buffered staged tiles
   __shared__ float keys_s[FF_SPAN][6];
   __shared__ int list[FF_SPAN];
   __shared__ int ovf[FF_SPAN];
@@ -262,8 +280,8 @@ l2f_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm,
       bool gave_up = false;
       {
         float d2;
-        const bool have = use_thr ? ff_chunk_rows<true>(ts[hw], qs[hw], tbase, cb, ncol, dim, l, hmask, thr, &d2)
-                                  : ff_chunk_rows<false>(ts[hw], qs[hw], tbase, cb, ncol, dim, l, hmask, thr, &d2);
+        const bool have = use_thr ? ff_chunk_rows<true>(ts_dyn + hw * (2 * 16 * FF_TLD), qs[hw], tbase, cb, ncol, dim, l, hmask, thr, &d2)
+                                  : ff_chunk_rows<false>(ts_dyn + hw * (2 * 16 * FF_TLD), qs[hw], tbase, cb, ncol, dim, l, hmask, thr, &d2);
         gave_up = l < ncol && !have;
         if (have)
           k1 = (static_cast<unsigned long long>(__float_as_uint(d2)) << 32) | static_cast<unsigned int>(cb + l);
@@ -370,7 +388,10 @@ l2f_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm,
   }
 }
 
+static constexpr int FF_DYN_SMEM = FF_HW * 2 * 16 * FF_TLD * static_cast<int>(sizeof(float));   // 36 KB
 cudaError_t l2f_configure() {
+  cudaError_t e = cudaFuncSetAttribute(l2f_fixup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_DYN_SMEM);
+  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(l2f_fixup_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
@@ -380,7 +401,7 @@ cudaError_t launch_l2f_fixup(const float* raw, const float* fnorm, int dim, cons
   if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
   if (dim <= 0 || dim > FF_MAXDIM || (dim & 63)) return cudaErrorInvalidValue;
   dim3 grid((max_nq + FF_SPAN - 1) / FF_SPAN, n_jobs);
-  l2f_fixup_kernel<<<grid, FF_THREADS, 0, st>>>(raw, fnorm, dim, jobs, idx, dist, extra, stride, ratio, need,
+  l2f_fixup_kernel<<<grid, FF_THREADS, FF_DYN_SMEM, st>>>(raw, fnorm, dim, jobs, idx, dist, extra, stride, ratio, need,
                                                 counters, e_mode);
   return cudaGetLastError();
 }
