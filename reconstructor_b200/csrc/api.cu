@@ -205,6 +205,9 @@ struct DeviceCtx {
   uint8_t *hq = nullptr, *ht = nullptr;  // [rows][32*words+32] E4M3 operand forms of binary rows (256 / 512 bit)
   TcMaps hmaps{};
   bool tch_ready = false;
+  uint8_t *hq8 = nullptr, *ht8 = nullptr;   // [rows][288] byte forms of 256-bit rows (kind::i8 two-set kernel)
+  TcMaps h8maps{};
+  bool tch8_ready = false;
   unsigned int* d_fstats = nullptr;   // pack_float statistics of the image being ingested
   unsigned int* h_fstats = nullptr;   // pinned
   unsigned long long* d_l2f = nullptr;   // l2f_fixup counters
@@ -295,7 +298,7 @@ struct DeviceCtx {
     single.destroy();
     auto fd = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
     fd(raw); fd(qf); fd(tf); fd(qnorm); fd(u8d); fd(bits); fd(xy); fd(d_flag); fd(stage); fd(d_dump);
-    fd(fq); fd(ft); fd(fnorm); fd(d_fstats); fd(d_l2f); fd(hq); fd(ht); fd(iq); fd(it); fd(qoff); fd(sq8); fd(st8);
+    fd(fq); fd(ft); fd(fnorm); fd(d_fstats); fd(d_l2f); fd(hq); fd(ht); fd(iq); fd(it); fd(qoff); fd(sq8); fd(st8); fd(hq8); fd(ht8);
     if (h_flag) cudaFreeHost(h_flag);
     if (h_recs) cudaFreeHost(h_recs);
     for (auto& kv : images) if (kv.second.ready) cudaEventDestroy(kv.second.ready);
@@ -316,6 +319,7 @@ struct DeviceCtx {
     tch_ready = false;
     tci_ready = false;
     tcs_ready = false;
+    tch8_ready = false;
     const bool sift_shape = dim == TC_DIM && (dtype == PM_DESC_F32 || dtype == PM_DESC_U8);
     if (!sift_shape && !float_tc_shape() && !bits_tc_shape()) return PM_OK;
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -354,6 +358,14 @@ struct DeviceCtx {
           (r = mkb(&hmaps.t_ext, ht, 32, CU_TENSOR_MAP_SWIZZLE_32B)) != CUDA_SUCCESS)
         return fail(PM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
       tch_ready = true;
+      if (words == 8) {
+        if ((r = mkb(&h8maps.q_main, hq8, 128, CU_TENSOR_MAP_SWIZZLE_128B)) != CUDA_SUCCESS ||
+            (r = mkb(&h8maps.q_ext, hq8, 32, CU_TENSOR_MAP_SWIZZLE_32B)) != CUDA_SUCCESS ||
+            (r = mkb(&h8maps.t_main, ht8, 128, CU_TENSOR_MAP_SWIZZLE_128B)) != CUDA_SUCCESS ||
+            (r = mkb(&h8maps.t_ext, ht8, 32, CU_TENSOR_MAP_SWIZZLE_32B)) != CUDA_SUCCESS)
+          return fail(PM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+        tch8_ready = true;
+      }
       return PM_OK;
     }
     if (float_tc_shape()) {
@@ -420,6 +432,10 @@ struct DeviceCtx {
       if (bits_tc_shape()) {
         if ((rc = grow(hq, 32 * words + 32, nc)) != PM_OK) return rc;
         if ((rc = grow(ht, 32 * words + 32, nc)) != PM_OK) return rc;
+        if (words == 8) {
+          if ((rc = grow(hq8, 32 * words + 32, nc)) != PM_OK) return rc;
+          if ((rc = grow(ht8, 32 * words + 32, nc)) != PM_OK) return rc;
+        }
         if ((rc = grow(qnorm, 1, nc)) != PM_OK) return rc;
       }
     } else {
@@ -536,7 +552,8 @@ struct DeviceCtx {
         if (bits_tc_shape()) {
           const size_t kb = 32 * static_cast<size_t>(words) + 32;
           PM_CUDA(launch_pack_bits(bits + static_cast<size_t>(im.row) * words, n, words, hq + im.row * kb,
-                                   ht + im.row * kb, qnorm + im.row, ingest));
+                                   ht + im.row * kb, qnorm + im.row, words == 8 ? hq8 + im.row * kb : nullptr,
+                                   words == 8 ? ht8 + im.row * kb : nullptr, ingest));
           ++stats.kernel_launches;
         }
       } else {
@@ -737,6 +754,7 @@ struct DeviceCtx {
     //   bit11     batched loop keeps the fp16 form (kind::f16) instead of the byte form (kind::i8, default)
     //   bits12-13 kind::i8 kernel: 1 / 2 = timing probes (no matches): TMA + MMA only / + accumulator loads without
     //             the reduction; 3 = the 64-register build
+    //   bit16     256-bit rows: kind::f8f6f4 kernel (E4M3 {0,1} forms) instead of the kind::i8 two-set kernel; bit17 = probe
     //   bit15     real-valued rows: fp16 forms (kind::f16) in the batched loop instead of the s8 forms (kind::i8)
     //   bit14     kind::i8: one query row set per cluster (l2_top2_tc2_kernel) instead of two (l2_i8x2_kernel)
     const int code = (prm.debug_flags >> 2) & 7;
@@ -758,7 +776,18 @@ struct DeviceCtx {
     // binary rows: Hamming = |a| + |b| - 2 a.b on the tensor cores (E4M3 {0,1} operands) in the batched loop;
     // debug_flags bit10 keeps the XOR/popc kernel there too (it always serves raw kNN rows / single pairs)
     const bool use_tch = dtype == PM_DESC_U8_BITS && tch_ready && fast && !dump && !((prm.debug_flags >> 10) & 1);
+    // 256-bit rows as bytes on kind::i8 with two query row sets per cluster (half the L2 traffic of the E4M3 kernel);
+    // debug bit16 keeps the kind::f8f6f4 kernel, bit17 = TMA + MMA timing probe of the i8 kernel
+    const bool use_tch8 = use_tch && tch8_ready && !((prm.debug_flags >> 16) & 1);
     auto knn_main = [&](const PairJob* jobs_d, int mq, int2* oi, float2* od, float2* ox) -> cudaError_t {
+      if (use_tch8) {
+        const int probe = (prm.debug_flags >> 17) & 1;
+        if (probe) {
+          cudaError_t e = cudaMemsetAsync(oi, 0xFF, sizeof(int2) * static_cast<size_t>(n) * s.stride, knn_stream);
+          if (e != cudaSuccess) return e;
+        }
+        return launch_ham_i8x2(h8maps, jobs_d, n, mq, oi, od, s.stride, num_sms, probe, knn_stream);
+      }
       if (use_tch) return launch_ham_tc2(hmaps, words, qnorm, jobs_d, n, mq, oi, od, s.stride, num_sms, knn_stream);
       if (dtype == PM_DESC_U8_BITS)
         return launch_hamming_top2(bits, words, jobs_d, n, mq, oi, od, s.stride, variant, knn_stream);
@@ -818,10 +847,12 @@ struct DeviceCtx {
       }
     }
     if (use_tch) {
-      PM_CUDA(launch_hamming_fixup(bits, words, s.d_jobs, n, max_nq, s.knn_idx, s.knn_dist, s.stride, prm.ratio, 0, s.stream));
+      PM_CUDA(launch_hamming_fixup(bits, words, s.d_jobs, n, max_nq, s.knn_idx, s.knn_dist, s.stride, prm.ratio, 0, s.stream,
+                                   use_tch8 ? 1 : 0));
       ++stats.kernel_launches;
       if (want_rev) {
-        PM_CUDA(launch_hamming_fixup(bits, words, s.d_rjobs, n, max_nt, s.rev_idx, s.rev_dist, s.stride, prm.ratio, 1, s.stream));
+        PM_CUDA(launch_hamming_fixup(bits, words, s.d_rjobs, n, max_nt, s.rev_idx, s.rev_dist, s.stride, prm.ratio, 1, s.stream,
+                                     use_tch8 ? 1 : 0));
         ++stats.kernel_launches;
       }
     }

@@ -70,9 +70,15 @@ cudaError_t launch_l2_fixup_i8(const uint32_t* u8desc, const int32_t* qnorm, con
 cudaError_t launch_ham_tc2(const TcMaps& maps, int words, const int32_t* qnorm, const PairJob* jobs, int n_jobs,
                            int max_nq, int2* idx, float2* dist, int stride, int num_sms, cudaStream_t st);
 cudaError_t launch_pack_bits(const uint32_t* bits, int n, int words, uint8_t* qb, uint8_t* tb, int32_t* popc,
-                             cudaStream_t st);
+                             uint8_t* q8, uint8_t* t8, cudaStream_t st);
+// ints = 0: float (m1, m2') of 16-column chunks (marker -2, kind::f8f6f4 kernel); ints = 1: integer values of
+// 32-column chunks (marker -3, kind::i8 two-set kernel, words == 8 only)
 cudaError_t launch_hamming_fixup(const uint32_t* bits, int words, const PairJob* jobs, int n_jobs, int max_nq,
-                                 int2* idx, float2* dist, int stride, float ratio, int all_rows, cudaStream_t st);
+                                 int2* idx, float2* dist, int stride, float ratio, int all_rows, cudaStream_t st,
+                                 int ints = 0);
+// 256-bit rows as bytes on kind::i8, two query row sets per cluster (l2_tc2.cu, l2_i8x2_kernel<.., 2>)
+cudaError_t launch_ham_i8x2(const TcMaps& maps, const PairJob* jobs, int n_jobs, int max_nq, int2* idx, float2* dist,
+                            int stride, int num_sms, int probe, cudaStream_t st);
 cudaError_t hamming_fixup_configure();
 
 // real-valued rows on the tensor cores: l2_tc2.cu (MODE 3) + l2f_fixup.cu

@@ -784,12 +784,16 @@ cudaError_t launch_ham_tc2(const TcMaps& maps, int words, const int32_t* qnorm, 
 // MMAs of set 1 run, and vice versa.  Everything else as in l2_top2_tc2_kernel<T2I8, 2, *, 2>.
 //   smem per CTA: query tiles 2 items x 2 sets x 20 KB, train ring 4 x 20 KB, barriers, slice exchange.
 // MODE 2: product; 1: TMA + MMA only; 5: + tcgen05.ld without the reduction (timing probes, no results).
-struct I8X2 {
-  static constexpr int kBN = 256, kBNH = 128, kSets = 2, kAStages = 2, kStages = 4;
-  static constexpr int kTile = T2_ATOM + T2_EXT;                 // 20 KB: 128 rows x (128 + 32) B
-  static constexpr int kSmemA = kAStages * kSets * kTile;        // 80 KB
-  static constexpr int kBTile = kBNH * 128 + kBNH * 32;          // 20 KB
-  static constexpr int kSmemB = kStages * kBTile;                // 80 KB
+template <int KA>
+struct I8X2Cfg {                                                 // KA = 128-byte K atoms per row: 1 (SIFT bytes), 2 (256-bit rows)
+  static constexpr int kKA = KA;
+  static constexpr int kBN = 256, kBNH = 128, kSets = 2;
+  static constexpr int kAStages = KA == 1 ? 2 : 1, kStages = KA == 1 ? 4 : 3;
+  static constexpr int kTile = KA * T2_ATOM + T2_EXT;            // 20 / 36 KB: 128 rows x (128 KA + 32) B
+  static constexpr int kSmemA = kAStages * kSets * kTile;        // 80 / 72 KB
+  static constexpr int kBAtom = kBNH * 128;
+  static constexpr int kBTile = KA * kBAtom + kBNH * 32;         // 20 / 36 KB
+  static constexpr int kSmemB = kStages * kBTile;                // 80 / 108 KB
   static constexpr int kSlices = 4, kEpiWarps = 16, kThreads = 128 + 32 * kEpiWarps;
   static constexpr int kXchg = 4 * (kSlices - 1) * 32 * 32;
   static constexpr int kSmemBytes = kSmemA + kSmemB + 1024 + 256 + kXchg;
@@ -798,15 +802,17 @@ struct I8X2 {
   static constexpr uint32_t kIdesc = (2u << 4) | (1u << 10) | kShape;      // D = s32, A = u8, B = s8
   static constexpr uint32_t kIdescExt = (2u << 4) | kShape;                // norm block: A = B = u8
 };
+using I8X2 = I8X2Cfg<1>;
 
-template <int MODE, bool LEAN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LEAN ? 1024 : I8X2::kThreads, 1)
+template <int MODE, bool LEAN, int KA = 1>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LEAN ? 1024 : I8X2Cfg<KA>::kThreads, 1)
 l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant__ CUtensorMap q_ext,
                const __grid_constant__ CUtensorMap t_main, const __grid_constant__ CUtensorMap t_ext,
                const PairJob* __restrict__ jobs, int n_jobs, int blocks_per_job, int2* __restrict__ knn_idx,
                float2* __restrict__ knn_dist, int stride) {
-  using C = I8X2;
+  using C = I8X2Cfg<KA>;
   constexpr int BN = C::kBN, BNH = C::kBNH, ST = C::kStages, TILE = C::kTile, BTILE = C::kBTile, NSL = C::kSlices;
+  constexpr int AST = C::kAStages, KDIM = 128 * KA, BATOM = C::kBAtom;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -858,14 +864,15 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
         if (blk * C::kRows >= job.nq) continue;
         const int nset = blk * C::kRows + T2_ROWS < job.nq ? 2 : 1;
         {
-          const uint32_t as = ai & 1, use = ai >> 1;
+          const uint32_t as = ai % AST, use = ai / AST;
           wait_trap(&a_empty[as], (use & 1) ^ 1);
           if (leader) mbar_expect_tx(&a_full[as], nset * 2 * TILE);
           for (int set = 0; set < nset; ++set) {
             uint8_t* dst = sA + (as * 2 + set) * TILE;
             const int row = job.q_row + blk * C::kRows + set * T2_ROWS + rank * T2_BM;
-            tma_load_2d_pair(dst, &q_main, 0, row, &a_full[as]);
-            tma_load_2d_pair(dst + T2_ATOM, &q_ext, TC_DIM, row, &a_full[as]);
+#pragma unroll
+            for (int a = 0; a < KA; ++a) tma_load_2d_pair(dst + a * T2_ATOM, &q_main, 128 * a, row, &a_full[as]);
+            tma_load_2d_pair(dst + KA * T2_ATOM, &q_ext, KDIM, row, &a_full[as]);
           }
         }
         ++ai;
@@ -876,8 +883,9 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
           wait_trap(&b_empty[st], ((bi / ST) & 1) ^ 1);
           if (leader) mbar_expect_tx(&b_full[st], 2 * BTILE);
           uint8_t* dst = sB + st * BTILE;
-          tma_load_2d_pair(dst, &t_main, 0, row, &b_full[st]);
-          tma_load_2d_pair(dst + BNH * 128, &t_ext, TC_DIM, row, &b_full[st]);
+#pragma unroll
+          for (int a = 0; a < KA; ++a) tma_load_2d_pair(dst + a * BATOM, &t_main, 128 * a, row, &b_full[st]);
+          tma_load_2d_pair(dst + KA * BATOM, &t_ext, KDIM, row, &b_full[st]);
         }
       }
     }
@@ -894,8 +902,8 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
         const int job_nq = jobs[jb].nq, job_nt = jobs[jb].nt;
         if (blk * C::kRows >= job_nq) continue;
         const int nset = blk * C::kRows + T2_ROWS < job_nq ? 2 : 1;
-        const uint32_t a_st = ai & 1;
-        wait_trap(&a_full[a_st], (ai >> 1) & 1);
+        const uint32_t a_st = ai % AST;
+        wait_trap(&a_full[a_st], (ai / AST) & 1);
         ++ai;
         const int n_tiles = (job_nt + BN - 1) / BN;
         for (int n = 0; n < n_tiles; ++n, ++bi) {
@@ -910,11 +918,13 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
               const uint32_t d_tmem = tmem_base + set * BN;
               const uint32_t a_lo = a_lo0 + (a_st * 2 + set) * (TILE >> 4);
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16_pair<2>(d_tmem, (static_cast<uint64_t>(HI128) << 32) | (a_lo + ((k * 32) >> 4)),
-                                 (static_cast<uint64_t>(HI128) << 32) | (b_lo + ((k * 32) >> 4)), C::kIdesc, k > 0 ? 1u : 0u);
-              umma_f16_pair<2>(d_tmem, (static_cast<uint64_t>(HI32) << 32) | (a_lo + (T2_ATOM >> 4)),
-                               (static_cast<uint64_t>(HI32) << 32) | (b_lo + ((BNH * 128) >> 4)), C::kIdescExt, 1u);
+              for (int k = 0; k < 4 * KA; ++k)
+                umma_f16_pair<2>(d_tmem,
+                                 (static_cast<uint64_t>(HI128) << 32) | (a_lo + (((k >> 2) * T2_ATOM + (k & 3) * 32) >> 4)),
+                                 (static_cast<uint64_t>(HI128) << 32) | (b_lo + (((k >> 2) * BATOM + (k & 3) * 32) >> 4)),
+                                 C::kIdesc, k > 0 ? 1u : 0u);
+              umma_f16_pair<2>(d_tmem, (static_cast<uint64_t>(HI32) << 32) | (a_lo + ((KA * T2_ATOM) >> 4)),
+                               (static_cast<uint64_t>(HI32) << 32) | (b_lo + ((KA * BATOM) >> 4)), C::kIdescExt, 1u);
               umma_commit_pair(&acc_full[set]);
               if (set == nset - 1) umma_commit_pair(&b_empty[st]);
             }
@@ -1008,12 +1018,12 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
   }
 }
 
-template <int MODE, bool LEAN>
+template <int MODE, bool LEAN, int KA = 1>
 static cudaError_t i8x2_attr() {
-  cudaError_t e = cudaFuncSetAttribute(l2_i8x2_kernel<MODE, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       I8X2::kSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(l2_i8x2_kernel<MODE, LEAN, KA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       I8X2Cfg<KA>::kSmemBytes);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(l2_i8x2_kernel<MODE, LEAN>, cudaFuncAttributePreferredSharedMemoryCarveout,
+  return cudaFuncSetAttribute(l2_i8x2_kernel<MODE, LEAN, KA>, cudaFuncAttributePreferredSharedMemoryCarveout,
                               cudaSharedmemCarveoutMaxShared);
 }
 using T2S256 = T2Cfg<256, 2, 2>;  // quantised real-valued rows, 256-d: 256 bytes of K + norm block
@@ -1055,7 +1065,30 @@ cudaError_t i8x2_configure() {
   if ((e = i8x2_attr<2, false>()) != cudaSuccess) return e;
   if ((e = i8x2_attr<2, true>()) != cudaSuccess) return e;
   if ((e = i8x2_attr<1, false>()) != cudaSuccess) return e;
+  if ((e = i8x2_attr<2, false, 2>()) != cudaSuccess) return e;
+  if ((e = i8x2_attr<1, false, 2>()) != cudaSuccess) return e;
   return i8x2_attr<5, false>();
+}
+
+// 256-bit binary rows as bytes (pack_bits_kernel: query bit -> 0 / 1 (u8), train bit -> +1 / -1 (s8), norm block =
+// popcount of the train row): the s32 accumulator IS the Hamming distance.  Two query row sets per cluster like the
+// SIFT kernel; hamming_fixup (32-column chunks, integer inputs) follows.  probe: TMA + MMA timing probe.
+cudaError_t launch_ham_i8x2(const TcMaps& maps, const PairJob* jobs, int n_jobs, int max_nq, int2* idx, float2* dist,
+                            int stride, int num_sms, int probe, cudaStream_t st) {
+  if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
+  using C = I8X2Cfg<2>;
+  const int blocks_per_job = (max_nq + C::kRows - 1) / C::kRows;
+  const int n_items = n_jobs * blocks_per_job;
+  int clusters = num_sms / 2;
+  if (n_items < clusters) clusters = n_items;
+  const int grid = clusters * 2;
+  if (probe)
+    l2_i8x2_kernel<1, false, 2><<<grid, C::kThreads, C::kSmemBytes, st>>>(maps.q_main, maps.q_ext, maps.t_main, maps.t_ext,
+                                                                          jobs, n_jobs, blocks_per_job, idx, dist, stride);
+  else
+    l2_i8x2_kernel<2, false, 2><<<grid, C::kThreads, C::kSmemBytes, st>>>(maps.q_main, maps.q_ext, maps.t_main, maps.t_ext,
+                                                                          jobs, n_jobs, blocks_per_job, idx, dist, stride);
+  return cudaGetLastError();
 }
 
 // variant: 0 = product (72 registers: the tail kernels of earlier batches stay co-resident), 1 = TMA + MMA probe,

@@ -209,9 +209,13 @@ __device__ __forceinline__ unsigned long long spread_bits8(unsigned int b) {    
   const unsigned long long t = (static_cast<unsigned long long>(b) * 0x0101010101010101ull) & 0x8040201008040201ull;
   return ((t + 0x7F7F7F7F7F7F7F7Full) >> 7) & 0x0101010101010101ull;
 }
+// With q8 / t8 (256-bit rows only) the same rows are also written as bytes for kind::i8 (l2_i8x2_kernel<.., 2>):
+//   query form [ bit (u8 0 / 1) | 1, 255 x31 (u8) ]     train form [ bit ? -1 : +1 (s8) | r, q, 0 x30 (u8) ], |b| = r + 255 q
+// so that the s32 accumulator is sum a (1 - 2 b) + |b| = |a| + |b| - 2 a.b, the Hamming distance itself.
 __global__ void __launch_bounds__(256)
 pack_bits_kernel(const uint32_t* __restrict__ bits, int n, int words, uint8_t* __restrict__ qb,
-                 uint8_t* __restrict__ tb, int32_t* __restrict__ popc) {
+                 uint8_t* __restrict__ tb, int32_t* __restrict__ popc, uint8_t* __restrict__ q8,
+                 uint8_t* __restrict__ t8) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
@@ -228,6 +232,16 @@ pack_bits_kernel(const uint32_t* __restrict__ bits, int n, int words, uint8_t* _
     const unsigned long long ones = spread_bits8((wj >> (8 * (j & 3))) & 0xFFu);
     *reinterpret_cast<unsigned long long*>(qrow + 8 * j) = ones * 0xC0ull;      // -2.0
     *reinterpret_cast<unsigned long long*>(trow + 8 * j) = ones * 0x38ull;      //  1.0
+    if (q8) {
+      *reinterpret_cast<unsigned long long*>(q8 + static_cast<size_t>(row) * kp + 8 * j) = ones;
+      // bit 1 -> 0xFF (-1), bit 0 -> 0x01 (+1):  0x01 + bit * 0xFE per byte
+      *reinterpret_cast<unsigned long long*>(t8 + static_cast<size_t>(row) * kp + 8 * j) = 0x0101010101010101ull + ones * 0xFEull;
+    }
+  }
+  if (q8) {
+    q8[static_cast<size_t>(row) * kp + 32 * words + lane] = lane == 0 ? 1 : 255;
+    t8[static_cast<size_t>(row) * kp + 32 * words + lane] =
+        static_cast<uint8_t>(lane == 0 ? cnt % 255 : (lane == 1 ? cnt / 255 : 0));
   }
   {
     const uint8_t e4m3_int[16] = {0x00, 0x38, 0x40, 0x44, 0x48, 0x4A, 0x4C, 0x4E,
@@ -243,9 +257,9 @@ pack_bits_kernel(const uint32_t* __restrict__ bits, int n, int words, uint8_t* _
 }
 
 cudaError_t launch_pack_bits(const uint32_t* bits, int n, int words, uint8_t* qb, uint8_t* tb, int32_t* popc,
-                             cudaStream_t st) {
+                             uint8_t* q8, uint8_t* t8, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
-  pack_bits_kernel<<<(n + 7) / 8, 256, 0, st>>>(bits, n, words, qb, tb, popc);
+  pack_bits_kernel<<<(n + 7) / 8, 256, 0, st>>>(bits, n, words, qb, tb, popc, q8, t8);
   return cudaGetLastError();
 }
 

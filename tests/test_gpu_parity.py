@@ -637,6 +637,45 @@ def test_hamming_tensor_full_size_equals_popc():
     assert outs[0]["offsets"][-1] > 10 * 1500
 
 
+FORCE_E4M3 = 1 << 16
+
+
+@pytest.mark.parametrize("mode", [api.UNIQUE_FIRST_WINS, api.MUTUAL_NN])
+def test_hamming_i8_two_set_kernel_sizes_around_row_sets(mode):
+    """256-bit rows as bytes on kind::i8 (default) vs the E4M3 form vs the XOR/popc kernel, with image sizes on both
+    sides of the 128 / 256 / 512-row boundaries of a work item (one or two resident query row sets) and of the
+    32-column fix-up chunks, duplicates inside and across chunks, all-zero and all-one rows."""
+    rng = np.random.default_rng(77 + mode)
+    base = rng.integers(0, 256, (1400, 32), dtype=np.uint8)
+    imgs = []
+    for i, n in enumerate((1025, 769, 513, 512, 511, 257, 256, 33, 31, 1)):
+        ids = rng.permutation(1400)[:n]
+        d = base[ids].copy()
+        flip = rng.random((n, 32)) < 0.05
+        d ^= (flip * rng.integers(1, 256, (n, 32))).astype(np.uint8)
+        if n > 300:
+            d[40] = d[7]; d[41] = d[7]; d[300] = d[7]
+            d[5] = 0; d[6] = 255
+        imgs.append(d)
+    outs = []
+    for flags in (0, FORCE_E4M3, FORCE_POPC):
+        with api.PairMatcher(unique_mode=mode, debug_flags=flags, do_filter=0, batch_pairs=7) as pm:
+            for i, d in enumerate(imgs):
+                pm.set_image(i, d)
+            outs.append(pm.match_all_pairs())
+    for o in outs[1:]:
+        for k in ("offsets", "q", "t", "status"):
+            assert np.array_equal(outs[0][k], o[k]), (mode, k)
+    res = outs[0]
+    for p, (i, j) in enumerate(res["pair_ij"]):
+        if mode != api.UNIQUE_FIRST_WINS or p % 4:
+            continue
+        oi, od = orc.knn2_hamming(imgs[i], imgs[j])
+        wq, wt = orc.ratio_unique(oi, od.astype(np.float32), imgs[j].shape[0])
+        a, b = res["offsets"][p], res["offsets"][p + 1]
+        assert np.array_equal(res["q"][a:b], wq) and np.array_equal(res["t"][a:b], wt), (i, j)
+    assert res["offsets"][-1] > 1000
+
 
 # ---------------------------------------------------------------------------------------------
 # integer-valued 128-d rows as bytes on kind::i8 (default batched SIFT path) vs the fp16 form and the oracle
