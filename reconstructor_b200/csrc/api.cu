@@ -208,6 +208,9 @@ struct DeviceCtx {
   uint8_t *hq8 = nullptr, *ht8 = nullptr;   // [rows][288] byte forms of 256-bit rows (kind::i8 two-set kernel)
   TcMaps h8maps{};
   bool tch8_ready = false;
+  uint8_t *hq4 = nullptr, *ht4 = nullptr;   // [rows][160] E2M1 forms of 256-bit rows (kind::mxf4 two-set kernel)
+  TcMaps h4maps{};
+  bool tch4_ready = false;
   unsigned int* d_fstats = nullptr;   // pack_float statistics of the image being ingested
   unsigned int* h_fstats = nullptr;   // pinned
   unsigned long long* d_l2f = nullptr;   // l2f_fixup counters
@@ -298,7 +301,7 @@ struct DeviceCtx {
     single.destroy();
     auto fd = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
     fd(raw); fd(qf); fd(tf); fd(qnorm); fd(u8d); fd(bits); fd(xy); fd(d_flag); fd(stage); fd(d_dump);
-    fd(fq); fd(ft); fd(fnorm); fd(d_fstats); fd(d_l2f); fd(hq); fd(ht); fd(iq); fd(it); fd(qoff); fd(sq8); fd(st8); fd(hq8); fd(ht8);
+    fd(fq); fd(ft); fd(fnorm); fd(d_fstats); fd(d_l2f); fd(hq); fd(ht); fd(iq); fd(it); fd(qoff); fd(sq8); fd(st8); fd(hq8); fd(ht8); fd(hq4); fd(ht4);
     if (h_flag) cudaFreeHost(h_flag);
     if (h_recs) cudaFreeHost(h_recs);
     for (auto& kv : images) if (kv.second.ready) cudaEventDestroy(kv.second.ready);
@@ -320,6 +323,7 @@ struct DeviceCtx {
     tci_ready = false;
     tcs_ready = false;
     tch8_ready = false;
+    tch4_ready = false;
     const bool sift_shape = dim == TC_DIM && (dtype == PM_DESC_F32 || dtype == PM_DESC_U8);
     if (!sift_shape && !float_tc_shape() && !bits_tc_shape()) return PM_OK;
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -344,10 +348,10 @@ struct DeviceCtx {
     };
     CUresult r;
     int kb = 32 * words + 32;
-    auto mkb = [&](CUtensorMap* m, void* base, cuuint32_t box_k, CUtensorMapSwizzle sw) -> CUresult {
+    auto mkb = [&](CUtensorMap* m, void* base, cuuint32_t box_k, CUtensorMapSwizzle sw, cuuint32_t rows = 128) -> CUresult {
         const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(kb), static_cast<cuuint64_t>(cap_rows)};
         const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(kb)};
-        const cuuint32_t box[2] = {box_k, 128};
+        const cuuint32_t box[2] = {box_k, rows};
         return encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     };
@@ -365,6 +369,13 @@ struct DeviceCtx {
             (r = mkb(&h8maps.t_ext, ht8, 32, CU_TENSOR_MAP_SWIZZLE_32B)) != CUDA_SUCCESS)
           return fail(PM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
         tch8_ready = true;
+        kb = TC_FP4_ROW;
+        if ((r = mkb(&h4maps.q_main, hq4, 128, CU_TENSOR_MAP_SWIZZLE_128B)) != CUDA_SUCCESS ||
+            (r = mkb(&h4maps.q_ext, hq4, 32, CU_TENSOR_MAP_SWIZZLE_32B)) != CUDA_SUCCESS ||
+            (r = mkb(&h4maps.t_main96, ht4, 128, CU_TENSOR_MAP_SWIZZLE_128B, 96)) != CUDA_SUCCESS ||
+            (r = mkb(&h4maps.t_ext96, ht4, 32, CU_TENSOR_MAP_SWIZZLE_32B, 96)) != CUDA_SUCCESS)
+          return fail(PM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+        tch4_ready = true;
       }
       return PM_OK;
     }
@@ -435,6 +446,8 @@ struct DeviceCtx {
         if (words == 8) {
           if ((rc = grow(hq8, 32 * words + 32, nc)) != PM_OK) return rc;
           if ((rc = grow(ht8, 32 * words + 32, nc)) != PM_OK) return rc;
+          if ((rc = grow(hq4, TC_FP4_ROW, nc)) != PM_OK) return rc;
+          if ((rc = grow(ht4, TC_FP4_ROW, nc)) != PM_OK) return rc;
         }
         if ((rc = grow(qnorm, 1, nc)) != PM_OK) return rc;
       }
@@ -553,7 +566,9 @@ struct DeviceCtx {
           const size_t kb = 32 * static_cast<size_t>(words) + 32;
           PM_CUDA(launch_pack_bits(bits + static_cast<size_t>(im.row) * words, n, words, hq + im.row * kb,
                                    ht + im.row * kb, qnorm + im.row, words == 8 ? hq8 + im.row * kb : nullptr,
-                                   words == 8 ? ht8 + im.row * kb : nullptr, ingest));
+                                   words == 8 ? ht8 + im.row * kb : nullptr,
+                                   words == 8 ? hq4 + static_cast<size_t>(im.row) * TC_FP4_ROW : nullptr,
+                                   words == 8 ? ht4 + static_cast<size_t>(im.row) * TC_FP4_ROW : nullptr, ingest));
           ++stats.kernel_launches;
         }
       } else {
@@ -754,7 +769,8 @@ struct DeviceCtx {
     //   bit11     batched loop keeps the fp16 form (kind::f16) instead of the byte form (kind::i8, default)
     //   bits12-13 kind::i8 kernel: 1 / 2 = timing probes (no matches): TMA + MMA only / + accumulator loads without
     //             the reduction; 3 = the 64-register build
-    //   bit16     256-bit rows: kind::f8f6f4 kernel (E4M3 {0,1} forms) instead of the kind::i8 two-set kernel; bit17 = probe
+    //   bit16     256-bit rows: kind::f8f6f4 kernel (E4M3 {0,1} forms) instead of the two-set kernels; bit17 = TMA + MMA probe
+    //   bit18     256-bit rows: kind::i8 two-set kernel (byte forms) instead of the kind::mxf4 two-set kernel (E2M1 forms)
     //   bit15     real-valued rows: fp16 forms (kind::f16) in the batched loop instead of the s8 forms (kind::i8)
     //   bit14     kind::i8: one query row set per cluster (l2_top2_tc2_kernel) instead of two (l2_i8x2_kernel)
     const int code = (prm.debug_flags >> 2) & 7;
@@ -778,14 +794,16 @@ struct DeviceCtx {
     const bool use_tch = dtype == PM_DESC_U8_BITS && tch_ready && fast && !dump && !((prm.debug_flags >> 10) & 1);
     // 256-bit rows as bytes on kind::i8 with two query row sets per cluster (half the L2 traffic of the E4M3 kernel);
     // debug bit16 keeps the kind::f8f6f4 kernel, bit17 = TMA + MMA timing probe of the i8 kernel
-    const bool use_tch8 = use_tch && tch8_ready && !((prm.debug_flags >> 16) & 1);
+    const bool use_tch4 = use_tch && tch4_ready && !((prm.debug_flags >> 16) & 1) && !((prm.debug_flags >> 18) & 1);
+    const bool use_tch8 = use_tch && tch8_ready && !((prm.debug_flags >> 16) & 1) && !use_tch4;
     auto knn_main = [&](const PairJob* jobs_d, int mq, int2* oi, float2* od, float2* ox) -> cudaError_t {
-      if (use_tch8) {
+      if (use_tch8 || use_tch4) {
         const int probe = (prm.debug_flags >> 17) & 1;
         if (probe) {
           cudaError_t e = cudaMemsetAsync(oi, 0xFF, sizeof(int2) * static_cast<size_t>(n) * s.stride, knn_stream);
           if (e != cudaSuccess) return e;
         }
+        if (use_tch4) return launch_ham_fp4x2(h4maps, jobs_d, n, mq, oi, od, s.stride, num_sms, probe, knn_stream);
         return launch_ham_i8x2(h8maps, jobs_d, n, mq, oi, od, s.stride, num_sms, probe, knn_stream);
       }
       if (use_tch) return launch_ham_tc2(hmaps, words, qnorm, jobs_d, n, mq, oi, od, s.stride, num_sms, knn_stream);
@@ -848,11 +866,11 @@ struct DeviceCtx {
     }
     if (use_tch) {
       PM_CUDA(launch_hamming_fixup(bits, words, s.d_jobs, n, max_nq, s.knn_idx, s.knn_dist, s.stride, prm.ratio, 0, s.stream,
-                                   use_tch8 ? 1 : 0));
+                                   use_tch4 ? 2 : (use_tch8 ? 1 : 0)));
       ++stats.kernel_launches;
       if (want_rev) {
         PM_CUDA(launch_hamming_fixup(bits, words, s.d_rjobs, n, max_nt, s.rev_idx, s.rev_dist, s.stride, prm.ratio, 1, s.stream,
-                                     use_tch8 ? 1 : 0));
+                                     use_tch4 ? 2 : (use_tch8 ? 1 : 0)));
         ++stats.kernel_launches;
       }
     }

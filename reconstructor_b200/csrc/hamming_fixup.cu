@@ -91,6 +91,8 @@ cudaError_t hamming_fixup_configure() {
                                 cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(hamming_fixup_kernel<8, 32, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                 cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(hamming_fixup_kernel<8, 32, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
   return cudaFuncSetAttribute(hamming_fixup_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout,
                               cudaSharedmemCarveoutMaxShared);
 }
@@ -100,7 +102,9 @@ cudaError_t launch_hamming_fixup(const uint32_t* bits, int words, const PairJob*
                                  int ints) {
   if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
   dim3 grid((max_nq + HF_SPAN - 1) / HF_SPAN, n_jobs);
-  if (ints && words == 8)
+  if (ints == 2 && words == 8)
+    hamming_fixup_kernel<8, 32, false><<<grid, HF_THREADS, 0, st>>>(bits, jobs, idx, dist, stride, ratio, all_rows);
+  else if (ints == 1 && words == 8)
     hamming_fixup_kernel<8, 32, true><<<grid, HF_THREADS, 0, st>>>(bits, jobs, idx, dist, stride, ratio, all_rows);
   else if (ints)
     return cudaErrorInvalidValue;

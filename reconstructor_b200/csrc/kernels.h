@@ -36,6 +36,7 @@ static constexpr int TC_KPAD = 144;       // 128 + one K=16 step carrying the tr
 #define PM_I8_CHUNK 32
 #endif
 static constexpr int TC_I8_CHUNK = PM_I8_CHUNK;   // columns per candidate chunk of the i8 epilogue (16 or 32)
+static constexpr int TC_FP4_ROW = 160;    // 256-bit rows as E2M1 values: 128 bytes + a 64-value (32-byte) norm block
 static constexpr int TC_I8_ROW = 160;     // byte form: 128 x u8/s8 + one K=32 step carrying floor(|b|^2 / 2)
 struct TcMaps {
   CUtensorMap q_main, q_ext, t_main, t_ext;   // boxes of 128 rows
@@ -70,15 +71,20 @@ cudaError_t launch_l2_fixup_i8(const uint32_t* u8desc, const int32_t* qnorm, con
 cudaError_t launch_ham_tc2(const TcMaps& maps, int words, const int32_t* qnorm, const PairJob* jobs, int n_jobs,
                            int max_nq, int2* idx, float2* dist, int stride, int num_sms, cudaStream_t st);
 cudaError_t launch_pack_bits(const uint32_t* bits, int n, int words, uint8_t* qb, uint8_t* tb, int32_t* popc,
-                             uint8_t* q8, uint8_t* t8, cudaStream_t st);
+                             uint8_t* q8, uint8_t* t8, uint8_t* q4, uint8_t* t4, cudaStream_t st);
 // ints = 0: float (m1, m2') of 16-column chunks (marker -2, kind::f8f6f4 kernel); ints = 1: integer values of
-// 32-column chunks (marker -3, kind::i8 two-set kernel, words == 8 only)
+// 32-column chunks (marker -3, kind::i8 two-set kernel, words == 8 only); ints = 2: float values of 32-column chunks
+// (marker -2, kind::mxf4 two-set kernel, words == 8 only)
 cudaError_t launch_hamming_fixup(const uint32_t* bits, int words, const PairJob* jobs, int n_jobs, int max_nq,
                                  int2* idx, float2* dist, int stride, float ratio, int all_rows, cudaStream_t st,
                                  int ints = 0);
 // 256-bit rows as bytes on kind::i8, two query row sets per cluster (l2_tc2.cu, l2_i8x2_kernel<.., 2>)
 cudaError_t launch_ham_i8x2(const TcMaps& maps, const PairJob* jobs, int n_jobs, int max_nq, int2* idx, float2* dist,
                             int stride, int num_sms, int probe, cudaStream_t st);
+// 256-bit rows as E2M1 values on kind::mxf4, 192-column train tiles (l2_tc2.cu, l2_i8x2_kernel<.., 1, 1>); maps: rows of
+// 160 bytes (128 bytes = 256 four-bit values + 32 bytes = 64-value norm block), t_main96 / t_ext96 boxes for the train side
+cudaError_t launch_ham_fp4x2(const TcMaps& maps, const PairJob* jobs, int n_jobs, int max_nq, int2* idx, float2* dist,
+                             int stride, int num_sms, int probe, cudaStream_t st);
 cudaError_t hamming_fixup_configure();
 
 // real-valued rows on the tensor cores: l2_tc2.cu (MODE 3) + l2f_fixup.cu

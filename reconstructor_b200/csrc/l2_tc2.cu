@@ -123,6 +123,26 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, 
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// kind::mxf4 (E2M1 operands packed two per byte, 64 values of K per instruction, UE8M0 scale factors per 32 values
+// read from TMEM at sfa / sfb).
+__device__ __forceinline__ void umma_mxf4_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t sfa, uint32_t sfb, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%5], [%6], p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa), "r"(sfb)
+      : "memory");
+}
+// 32 columns x this warp's 32 lanes of TMEM <- one value
+__device__ __forceinline__ void tmem_st_32x32b_x32_fill(uint32_t taddr, uint32_t v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+      "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
+      "r"(v)
+      : "memory");
+}
 // Arrives (once all prior MMAs of this thread completed) on the barrier at the same offset in both CTAs.
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
   asm volatile(
@@ -784,35 +804,39 @@ cudaError_t launch_ham_tc2(const TcMaps& maps, int words, const int32_t* qnorm, 
 // MMAs of set 1 run, and vice versa.  Everything else as in l2_top2_tc2_kernel<T2I8, 2, *, 2>.
 //   smem per CTA: query tiles 2 items x 2 sets x 20 KB, train ring 4 x 20 KB, barriers, slice exchange.
 // MODE 2: product; 1: TMA + MMA only; 5: + tcgen05.ld without the reduction (timing probes, no results).
-template <int KA>
+template <int KA, int BN_ = 256>
 struct I8X2Cfg {                                                 // KA = 128-byte K atoms per row: 1 (SIFT bytes), 2 (256-bit rows)
-  static constexpr int kKA = KA;
-  static constexpr int kBN = 256, kBNH = 128, kSets = 2;
-  static constexpr int kAStages = KA == 1 ? 2 : 1, kStages = KA == 1 ? 4 : 3;
+  static constexpr int kKA = KA;                                 // BN_ = 192: the fp4 form (TMEM columns 384.. hold the scale factors)
+  static constexpr int kBN = BN_, kBNH = BN_ / 2, kSets = 2;
+  static constexpr int kAStages = KA == 1 ? 2 : 1, kStages = KA == 1 ? (BN_ == 256 ? 4 : 5) : 3;
   static constexpr int kTile = KA * T2_ATOM + T2_EXT;            // 20 / 36 KB: 128 rows x (128 KA + 32) B
   static constexpr int kSmemA = kAStages * kSets * kTile;        // 80 / 72 KB
   static constexpr int kBAtom = kBNH * 128;
   static constexpr int kBTile = KA * kBAtom + kBNH * 32;         // 20 / 36 KB
   static constexpr int kSmemB = kStages * kBTile;                // 80 / 108 KB
-  static constexpr int kSlices = 4, kEpiWarps = 16, kThreads = 128 + 32 * kEpiWarps;
+  static constexpr int kSlices = BN_ / 64, kEpiWarps = 4 * kSlices, kThreads = 128 + 32 * kEpiWarps;
   static constexpr int kXchg = 4 * (kSlices - 1) * 32 * 32;
   static constexpr int kSmemBytes = kSmemA + kSmemB + 1024 + 256 + kXchg;
   static constexpr int kRows = kSets * T2_ROWS;                  // 512 query rows per work item
+  static constexpr uint32_t kSfCol = 2 * BN_;                    // fp4 form: first TMEM column of the scale factors
   static constexpr uint32_t kShape = ((kBN >> 3) << 17) | ((T2_ROWS >> 4) << 24);
   static constexpr uint32_t kIdesc = (2u << 4) | (1u << 10) | kShape;      // D = s32, A = u8, B = s8
   static constexpr uint32_t kIdescExt = (2u << 4) | kShape;                // norm block: A = B = u8
+  // kind::mxf4 (block-scaled instruction descriptor): A = B = E2M1 (format 1), scale factors UE8M0, K = 64, D = f32
+  static constexpr uint32_t kIdescFp4 = (1u << 7) | (1u << 10) | (1u << 23) | kShape;
 };
 using I8X2 = I8X2Cfg<1>;
 
-template <int MODE, bool LEAN, int KA = 1>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LEAN ? 1024 : I8X2Cfg<KA>::kThreads, 1)
+template <int MODE, bool LEAN, int KA = 1, int FP4 = 0>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LEAN ? 1024 : I8X2Cfg<KA, FP4 ? 192 : 256>::kThreads, 1)
 l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant__ CUtensorMap q_ext,
                const __grid_constant__ CUtensorMap t_main, const __grid_constant__ CUtensorMap t_ext,
                const PairJob* __restrict__ jobs, int n_jobs, int blocks_per_job, int2* __restrict__ knn_idx,
                float2* __restrict__ knn_dist, int stride) {
-  using C = I8X2Cfg<KA>;
+  using C = I8X2Cfg<KA, FP4 ? 192 : 256>;
   constexpr int BN = C::kBN, BNH = C::kBNH, ST = C::kStages, TILE = C::kTile, BTILE = C::kBTile, NSL = C::kSlices;
   constexpr int AST = C::kAStages, KDIM = 128 * KA, BATOM = C::kBAtom;
+  static_assert(!FP4 || KA == 1, "the fp4 form of a 256-bit row is one 128-byte K atom");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -850,6 +874,20 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (FP4) {
+    // kind::mxf4 is block-scaled: every scale factor is 1.0 (UE8M0 0x7F).  64 TMEM columns of all 128 lanes of both
+    // CTAs are filled with it once, so the scale-factor layout the instruction expects does not matter.
+    if (warp >= 4 && warp < 8) {
+      const uint32_t a = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + C::kSfCol;
+      tmem_st_32x32b_x32_fill(a, 0x7F7F7F7Fu);
+      tmem_st_32x32b_x32_fill(a + 32, 0x7F7F7F7Fu);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+  }
 
   const int n_items = n_jobs * blocks_per_job;
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
@@ -917,14 +955,26 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
             if (elect_one()) {
               const uint32_t d_tmem = tmem_base + set * BN;
               const uint32_t a_lo = a_lo0 + (a_st * 2 + set) * (TILE >> 4);
+              if (FP4) {
+                // 4 x 64 bit values of the row + the 64-value norm block: 5 K-steps of kind::mxf4 (K = 64)
+                const uint32_t sfa = tmem_base + C::kSfCol, sfb = tmem_base + C::kSfCol + 16;
 #pragma unroll
-              for (int k = 0; k < 4 * KA; ++k)
-                umma_f16_pair<2>(d_tmem,
-                                 (static_cast<uint64_t>(HI128) << 32) | (a_lo + (((k >> 2) * T2_ATOM + (k & 3) * 32) >> 4)),
-                                 (static_cast<uint64_t>(HI128) << 32) | (b_lo + (((k >> 2) * BATOM + (k & 3) * 32) >> 4)),
-                                 C::kIdesc, k > 0 ? 1u : 0u);
-              umma_f16_pair<2>(d_tmem, (static_cast<uint64_t>(HI32) << 32) | (a_lo + ((KA * T2_ATOM) >> 4)),
-                               (static_cast<uint64_t>(HI32) << 32) | (b_lo + ((KA * BATOM) >> 4)), C::kIdescExt, 1u);
+                for (int k = 0; k < 4; ++k)
+                  umma_mxf4_pair(d_tmem, (static_cast<uint64_t>(HI128) << 32) | (a_lo + ((k * 32) >> 4)),
+                                 (static_cast<uint64_t>(HI128) << 32) | (b_lo + ((k * 32) >> 4)), C::kIdescFp4, sfa, sfb,
+                                 k > 0 ? 1u : 0u);
+                umma_mxf4_pair(d_tmem, (static_cast<uint64_t>(HI32) << 32) | (a_lo + (T2_ATOM >> 4)),
+                               (static_cast<uint64_t>(HI32) << 32) | (b_lo + (BATOM >> 4)), C::kIdescFp4, sfa, sfb, 1u);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4 * KA; ++k)
+                  umma_f16_pair<2>(d_tmem,
+                                   (static_cast<uint64_t>(HI128) << 32) | (a_lo + (((k >> 2) * T2_ATOM + (k & 3) * 32) >> 4)),
+                                   (static_cast<uint64_t>(HI128) << 32) | (b_lo + (((k >> 2) * BATOM + (k & 3) * 32) >> 4)),
+                                   C::kIdesc, k > 0 ? 1u : 0u);
+                umma_f16_pair<2>(d_tmem, (static_cast<uint64_t>(HI32) << 32) | (a_lo + ((KA * T2_ATOM) >> 4)),
+                                 (static_cast<uint64_t>(HI32) << 32) | (b_lo + ((KA * BATOM) >> 4)), C::kIdescExt, 1u);
+              }
               umma_commit_pair(&acc_full[set]);
               if (set == nset - 1) umma_commit_pair(&b_empty[st]);
             }
@@ -998,7 +1048,9 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
               const int row = blk * C::kRows + set * T2_ROWS + rank * T2_BM + quarter * 32 + lane;
               if (row < job.nq) {
                 const size_t o = static_cast<size_t>(jb) * stride + row;
-                knn_idx[o] = make_int2(s.i1, -3);        // -3: D' values of the i8 form (l2_fixup_i8 follows)
+                // -3: integer values of the byte forms; -2: the fp4 form's accumulators are non-negative floats
+                // (integer order == float order), hamming_fixup reads them as floats
+                knn_idx[o] = make_int2(s.i1, FP4 ? -2 : -3);
                 knn_dist[o] = make_float2(__int_as_float(s.m1), __int_as_float(s.m2));
               }
             }
@@ -1018,12 +1070,12 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
   }
 }
 
-template <int MODE, bool LEAN, int KA = 1>
+template <int MODE, bool LEAN, int KA = 1, int FP4 = 0>
 static cudaError_t i8x2_attr() {
-  cudaError_t e = cudaFuncSetAttribute(l2_i8x2_kernel<MODE, LEAN, KA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       I8X2Cfg<KA>::kSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(l2_i8x2_kernel<MODE, LEAN, KA, FP4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       I8X2Cfg<KA, FP4 ? 192 : 256>::kSmemBytes);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(l2_i8x2_kernel<MODE, LEAN, KA>, cudaFuncAttributePreferredSharedMemoryCarveout,
+  return cudaFuncSetAttribute(l2_i8x2_kernel<MODE, LEAN, KA, FP4>, cudaFuncAttributePreferredSharedMemoryCarveout,
                               cudaSharedmemCarveoutMaxShared);
 }
 using T2S256 = T2Cfg<256, 2, 2>;  // quantised real-valued rows, 256-d: 256 bytes of K + norm block
@@ -1067,6 +1119,8 @@ cudaError_t i8x2_configure() {
   if ((e = i8x2_attr<1, false>()) != cudaSuccess) return e;
   if ((e = i8x2_attr<2, false, 2>()) != cudaSuccess) return e;
   if ((e = i8x2_attr<1, false, 2>()) != cudaSuccess) return e;
+  if ((e = i8x2_attr<2, false, 1, 1>()) != cudaSuccess) return e;
+  if ((e = i8x2_attr<1, false, 1, 1>()) != cudaSuccess) return e;
   return i8x2_attr<5, false>();
 }
 
@@ -1088,6 +1142,29 @@ cudaError_t launch_ham_i8x2(const TcMaps& maps, const PairJob* jobs, int n_jobs,
   else
     l2_i8x2_kernel<2, false, 2><<<grid, C::kThreads, C::kSmemBytes, st>>>(maps.q_main, maps.q_ext, maps.t_main, maps.t_ext,
                                                                           jobs, n_jobs, blocks_per_job, idx, dist, stride);
+  return cudaGetLastError();
+}
+
+// 256-bit binary rows as E2M1 values on kind::mxf4 (pack_bits_kernel: query bit -> 0 / 1, train bit -> +1 / -1, 64-value
+// norm block = popcount of the train row as products of representable digits): 64 values of K per instruction at the
+// instruction rate of kind::i8, so a train tile costs 5 K-steps instead of 9 and the fp32 accumulator IS the Hamming
+// distance (exact: every partial sum is an integer of magnitude <= 512).  192-column train tiles leave TMEM columns for
+// the (all-ones) scale factors.  hamming_fixup (32-column chunks, float inputs) follows.  probe: TMA + MMA timing probe.
+cudaError_t launch_ham_fp4x2(const TcMaps& maps, const PairJob* jobs, int n_jobs, int max_nq, int2* idx, float2* dist,
+                             int stride, int num_sms, int probe, cudaStream_t st) {
+  if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
+  using C = I8X2Cfg<1, 192>;
+  const int blocks_per_job = (max_nq + C::kRows - 1) / C::kRows;
+  const int n_items = n_jobs * blocks_per_job;
+  int clusters = num_sms / 2;
+  if (n_items < clusters) clusters = n_items;
+  const int grid = clusters * 2;
+  if (probe)
+    l2_i8x2_kernel<1, false, 1, 1><<<grid, C::kThreads, C::kSmemBytes, st>>>(
+        maps.q_main, maps.q_ext, maps.t_main96, maps.t_ext96, jobs, n_jobs, blocks_per_job, idx, dist, stride);
+  else
+    l2_i8x2_kernel<2, false, 1, 1><<<grid, C::kThreads, C::kSmemBytes, st>>>(
+        maps.q_main, maps.q_ext, maps.t_main96, maps.t_ext96, jobs, n_jobs, blocks_per_job, idx, dist, stride);
   return cudaGetLastError();
 }
 

@@ -638,17 +638,19 @@ def test_hamming_tensor_full_size_equals_popc():
 
 
 FORCE_E4M3 = 1 << 16
+FORCE_I8 = 1 << 18
 
 
 @pytest.mark.parametrize("mode", [api.UNIQUE_FIRST_WINS, api.MUTUAL_NN])
 def test_hamming_i8_two_set_kernel_sizes_around_row_sets(mode):
-    """256-bit rows as bytes on kind::i8 (default) vs the E4M3 form vs the XOR/popc kernel, with image sizes on both
-    sides of the 128 / 256 / 512-row boundaries of a work item (one or two resident query row sets) and of the
-    32-column fix-up chunks, duplicates inside and across chunks, all-zero and all-one rows."""
+    """256-bit rows as E2M1 values on kind::mxf4 (default) vs bytes on kind::i8 vs the E4M3 form vs the XOR/popc kernel,
+    with image sizes on both sides of the 128 / 256 / 512-row boundaries of a work item (one or two resident query row
+    sets), of the 192 / 256-column train tiles and of the 32-column fix-up chunks, duplicates inside and across chunks,
+    all-zero and all-one rows, and one image holding every popcount 0..256 (all digits of the norm block)."""
     rng = np.random.default_rng(77 + mode)
     base = rng.integers(0, 256, (1400, 32), dtype=np.uint8)
     imgs = []
-    for i, n in enumerate((1025, 769, 513, 512, 511, 257, 256, 33, 31, 1)):
+    for i, n in enumerate((1025, 769, 513, 512, 511, 385, 257, 256, 193, 192, 97, 33, 31, 1)):
         ids = rng.permutation(1400)[:n]
         d = base[ids].copy()
         flip = rng.random((n, 32)) < 0.05
@@ -657,8 +659,12 @@ def test_hamming_i8_two_set_kernel_sizes_around_row_sets(mode):
             d[40] = d[7]; d[41] = d[7]; d[300] = d[7]
             d[5] = 0; d[6] = 255
         imgs.append(d)
+    ramp = np.zeros((257, 256), np.uint8)
+    for k in range(257):
+        ramp[k, rng.permutation(256)[:k]] = 1                  # row k has exactly k set bits
+    imgs.insert(3, np.packbits(ramp, axis=1))
     outs = []
-    for flags in (0, FORCE_E4M3, FORCE_POPC):
+    for flags in (0, FORCE_I8, FORCE_E4M3, FORCE_POPC):
         with api.PairMatcher(unique_mode=mode, debug_flags=flags, do_filter=0, batch_pairs=7) as pm:
             for i, d in enumerate(imgs):
                 pm.set_image(i, d)
@@ -668,7 +674,7 @@ def test_hamming_i8_two_set_kernel_sizes_around_row_sets(mode):
             assert np.array_equal(outs[0][k], o[k]), (mode, k)
     res = outs[0]
     for p, (i, j) in enumerate(res["pair_ij"]):
-        if mode != api.UNIQUE_FIRST_WINS or p % 4:
+        if mode != api.UNIQUE_FIRST_WINS or p % 6:
             continue
         oi, od = orc.knn2_hamming(imgs[i], imgs[j])
         wq, wt = orc.ratio_unique(oi, od.astype(np.float32), imgs[j].shape[0])
