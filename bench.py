@@ -379,15 +379,23 @@ def main():
     except Exception:
         pass
     knn_s = st["knn_ms"] * 1e-3
-    if a.kind == "orb" and not (a.debug_flags & 1024):
-        # default binary path: Hamming = |a| + |b| - 2 a.b on the tensor cores (E4M3 {0,1} operands, exact); one popc32
-        # of the fixed numerator = 32 bit compares = 64 FLOP of the contraction
+    orb_form = "popc" if (a.debug_flags & 1024) else "e4m3" if (a.debug_flags & 65536) else "i8" if (a.debug_flags & 262144) else "fp4"
+    if a.kind == "orb" and orb_form != "popc":
+        # default binary path: Hamming = |a| + |b| - 2 a.b on the tensor cores (E2M1 {0,+-1} operands on kind::mxf4, exact);
+        # one popc32 of the fixed numerator = 32 bit compares = 64 FLOP of the contraction
         pk = peaks.get("bf16_tflops_sustained")
         popc_peak = pm.measure_popc_peak()
-        roof = dict(bound="tensor", achieved=64.0 * st["knn_work"] / knn_s / 1e12, peak=2.0 * (pk if pk else 1400.0),
+        mult = 4.0 if orb_form == "fp4" else 2.0
+        roof = dict(bound="tensor", achieved=64.0 * st["knn_work"] / knn_s / 1e12, peak=mult * (pk if pk else 1400.0),
                     unit="TFLOP/s",
-                    peak_source=("2 x MEASURED_PEAKS.json bf16_tflops_sustained (fp8 dense = 2 x bf16 on B200; no measured fp8 "
-                                 "figure in MEASURED_PEAKS.json)" if pk else "2 x fallback 1.4 PFLOP/s (B200_PROFILING.md)"),
+                    peak_source=(("%g x MEASURED_PEAKS.json bf16_tflops_sustained (%s; no measured figure of that kind in "
+                                  "MEASURED_PEAKS.json)" % (mult, "fp4 dense (kind::mxf4) = 4 x bf16 on B200" if orb_form == "fp4" else
+                                                            "fp8 / int8 dense = 2 x bf16 on B200")) if pk
+                                 else "%g x fallback 1.4 PFLOP/s (B200_PROFILING.md)" % mult),
+                    operands={"fp4": "E2M1 {0, +-1} values on tcgen05 kind::mxf4 (64 values of K per instruction, all-ones scale "
+                                     "factors), f32 accumulate, exact integers", "i8": "u8 x s8 on tcgen05 kind::i8, s32 accumulate",
+                              "e4m3": "E4M3 {0,1} values on tcgen05 kind::f8f6f4, f32 accumulate, exact integers"}[orb_form],
+                    frac_of_bf16_peak=64.0 * st["knn_work"] / knn_s / 1e12 / (pk if pk else 1400.0),
                     popc32_equiv=dict(achieved=st["knn_work"] / knn_s / 1e12, popc_pipe_peak=popc_peak / 1e12, unit="Tpopc32/s",
                                       note="the XOR/popc kernel of the north star (--debug-flags 1024) is bounded by popc_pipe_peak"))
     elif a.kind == "orb":
@@ -409,7 +417,7 @@ def main():
         roof["operands"] = ("int8 (tcgen05 kind::i8, rows quantised to s8 for the candidate stage; exact fp32 re-rank follows): "
                             "2 x the bf16 MMA rate the peak is quoted in")
         roof["frac_of_int8_peak"] = roof["frac"] / 2.0
-    roof["kernel"] = {"sift": "l2_top2_tc2_kernel" if (a.debug_flags & (2048 | 16384)) else "l2_i8x2_kernel", "orb": "hamming_top2_kernel" if (a.debug_flags & 1024) else "l2_top2_tc2_kernel<T2Cfg<256,2,2>,2,false,1>", "superpoint": "l2_top2_tc2_kernel<T2Cfg<256,2,4>,3>" if (a.debug_flags & 32768) else "l2_top2_tc2_kernel<T2Cfg<256,2,2>,3,true,3>"}[a.kind]
+    roof["kernel"] = {"sift": "l2_top2_tc2_kernel" if (a.debug_flags & (2048 | 16384)) else "l2_i8x2_kernel", "orb": {"popc": "hamming_top2_kernel", "e4m3": "l2_top2_tc2_kernel<T2Cfg<256,2,2>,2,false,1>", "i8": "l2_i8x2_kernel<2,false,2,0>", "fp4": "l2_i8x2_kernel<2,false,1,1>"}[orb_form], "superpoint": "l2_top2_tc2_kernel<T2Cfg<256,2,4>,3>" if (a.debug_flags & 32768) else "l2_top2_tc2_kernel<T2Cfg<256,2,2>,3,true,3>"}[a.kind]
     roof["launches"] = st["knn_launches"]
     roof["avg_launch_ms"] = st["knn_ms"] / max(st["knn_launches"], 1)
     roof["share_of_step"] = st["knn_ms"] / max(dev_ms, 1e-9) if world == 1 else None
@@ -495,7 +503,7 @@ def main():
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=n_gpus, steps=a.steps, warmup=a.warmup,
                     ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype={"sift": "f16 operands / f32 accumulate (exact integers)" if (a.debug_flags & 2048) else
-                           "u8 x s8 operands / s32 accumulate (kind::i8, exact integers)", "orb": "u32 popc" if (a.debug_flags & 1024) else "e4m3 {0,1} operands / f32 accumulate (exact integers)",
+                           "u8 x s8 operands / s32 accumulate (kind::i8, exact integers)", "orb": {"popc": "u32 popc", "e4m3": "e4m3 {0,1} operands / f32 accumulate (exact integers)", "i8": "u8 x s8 operands / s32 accumulate (exact integers)", "fp4": "e2m1 {0,+-1} operands (kind::mxf4) / f32 accumulate (exact integers)"}[orb_form],
                            "superpoint": "f16 operands / f32 accumulate candidates + exact f32 re-rank" if (a.debug_flags & 32768) else
                            "s8 operands / s32 accumulate candidates (kind::i8) + exact f32 re-rank"}[a.kind],
                     data="synthetic", config=cfg, wall_ms_per_step=wall_ms / a.steps,

@@ -209,7 +209,7 @@ struct DeviceCtx {
   TcMaps h8maps{};
   bool tch8_ready = false;
   uint8_t *hq4 = nullptr, *ht4 = nullptr;   // [rows][160] E2M1 forms of 256-bit rows (kind::mxf4 two-set kernel)
-  TcMaps h4maps{};
+  TcMaps h4maps{};                           // train boxes of 96 rows (192-column tiles)
   bool tch4_ready = false;
   unsigned int* d_fstats = nullptr;   // pack_float statistics of the image being ingested
   unsigned int* h_fstats = nullptr;   // pinned
@@ -770,7 +770,7 @@ struct DeviceCtx {
     //   bits12-13 kind::i8 kernel: 1 / 2 = timing probes (no matches): TMA + MMA only / + accumulator loads without
     //             the reduction; 3 = the 64-register build
     //   bit16     256-bit rows: kind::f8f6f4 kernel (E4M3 {0,1} forms) instead of the two-set kernels; bit17 = TMA + MMA probe
-    //   bit18     256-bit rows: kind::i8 two-set kernel (byte forms) instead of the kind::mxf4 two-set kernel (E2M1 forms)
+    //   bit18     256-bit rows: kind::i8 two-set kernel (byte forms) instead of the kind::mxf4 kernels (E2M1 forms)
     //   bit15     real-valued rows: fp16 forms (kind::f16) in the batched loop instead of the s8 forms (kind::i8)
     //   bit14     kind::i8: one query row set per cluster (l2_top2_tc2_kernel) instead of two (l2_i8x2_kernel)
     const int code = (prm.debug_flags >> 2) & 7;

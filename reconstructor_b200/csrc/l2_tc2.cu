@@ -30,6 +30,7 @@
 #define PM_PROBE_NOTMA 0
 #endif
 
+
 namespace pm {
 
 static constexpr int T2_BM = 128;               // query rows per CTA
@@ -1078,6 +1079,7 @@ static cudaError_t i8x2_attr() {
   return cudaFuncSetAttribute(l2_i8x2_kernel<MODE, LEAN, KA, FP4>, cudaFuncAttributePreferredSharedMemoryCarveout,
                               cudaSharedmemCarveoutMaxShared);
 }
+
 using T2S256 = T2Cfg<256, 2, 2>;  // quantised real-valued rows, 256-d: 256 bytes of K + norm block
 using T2S128 = T2Cfg<256, 2, 1>;  // 128-d
 cudaError_t s8_configure() {
