@@ -6,6 +6,7 @@
 // There is no CPU fallback anywhere in this file: without a CUDA device every compute entry
 // point returns PM_ERR_NO_DEVICE.
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdarg>
@@ -211,6 +212,9 @@ struct DeviceCtx {
   uint8_t *hq4 = nullptr, *ht4 = nullptr;   // [rows][160] E2M1 forms of 256-bit rows (kind::mxf4 two-set kernel)
   TcMaps h4maps{};                           // train boxes of 96 rows (192-column tiles)
   bool tch4_ready = false;
+  bool result_by_ce = true;                  // PM_RESULT_COPY=kernel: compacted matches leave by copy kernels too (development)
+  bool trace_on = false;                     // PM_TRACE: host-side timeline of run_pairs (development)
+  std::chrono::steady_clock::time_point trace_t0{};
   unsigned int* d_fstats = nullptr;   // pack_float statistics of the image being ingested
   unsigned int* h_fstats = nullptr;   // pinned
   unsigned long long* d_l2f = nullptr;   // l2f_fixup counters
@@ -478,7 +482,14 @@ struct DeviceCtx {
   // Waits for an asynchronously ingested image and reads its facts from the pinned record.
   int resolve(Image& im) {
     if (!im.pending) return PM_OK;
+    const auto t_w0 = std::chrono::steady_clock::now();
     PM_CUDA(cudaEventSynchronize(im.ready));
+    if (trace_on) {                            // development (PM_TRACE): when did the host see this image?
+      const auto t_w1 = std::chrono::steady_clock::now();
+      std::fprintf(stderr, "[pm trace] host: image at row %d ready at %.3f ms (waited %.3f ms)\n", im.row,
+                   std::chrono::duration<double, std::milli>(t_w1 - trace_t0).count(),
+                   std::chrono::duration<double, std::milli>(t_w1 - t_w0).count());
+    }
     const int* rec = h_recs + static_cast<size_t>(im.rec) * kRecInts;
     if (dtype != PM_DESC_U8_BITS && dim == TC_DIM) {
       im.integral = (rec[0] & 1) == 0;
@@ -742,9 +753,13 @@ struct DeviceCtx {
       s.h_rjobs[i] = PairJob{s.h_jobs[i].t_row, s.h_jobs[i].q_row, s.h_jobs[i].nt, s.h_jobs[i].nq,
                              s.h_jobs[i].t_maxn, s.h_jobs[i].q_maxn};
     }
-    PM_CUDA(cudaMemcpyAsync(s.d_jobs, s.h_jobs, sizeof(PairJob) * n, cudaMemcpyHostToDevice, s.stream));
-    if (want_rev)
-      PM_CUDA(cudaMemcpyAsync(s.d_rjobs, s.h_rjobs, sizeof(PairJob) * n, cudaMemcpyHostToDevice, s.stream));
+    // by a kernel, not the copy engine: an H2D copy would wait behind every image upload still queued there
+    PM_CUDA(launch_copy_pinned(s.h_jobs, s.d_jobs, sizeof(PairJob) * n, s.stream));
+    ++stats.kernel_launches;
+    if (want_rev) {
+      PM_CUDA(launch_copy_pinned(s.h_rjobs, s.d_rjobs, sizeof(PairJob) * n, s.stream));
+      ++stats.kernel_launches;
+    }
     if (dtype != PM_DESC_U8_BITS) {
       for (int i = 0; i < n && all_integral; ++i) all_integral = job_integral[i];
       for (int i = 0; i < n && all_i8; ++i) all_i8 = job_i8[i];
@@ -925,11 +940,13 @@ struct DeviceCtx {
     PM_CUDA(launch_compact(s.count, n, s.stride, s.match_q, s.match_t, s.mask, s.offsets, s.out_q,
                            s.out_t, s.out_mask, s.stream));
     stats.kernel_launches += 4;
-    PM_CUDA(cudaMemcpyAsync(s.h_offsets, s.offsets, 8 * (n + 1), cudaMemcpyDeviceToHost, s.stream));
-    PM_CUDA(cudaMemcpyAsync(s.h_F, s.F, 72 * n, cudaMemcpyDeviceToHost, s.stream));
-    PM_CUDA(cudaMemcpyAsync(s.h_status, s.status, 4 * n, cudaMemcpyDeviceToHost, s.stream));
-    PM_CUDA(cudaMemcpyAsync(s.h_ninl, s.n_inl, 4 * n, cudaMemcpyDeviceToHost, s.stream));
-    PM_CUDA(cudaMemcpyAsync(s.h_iters, s.iters, 4 * n, cudaMemcpyDeviceToHost, s.stream));
+    // by kernels writing pinned host memory, not the copy engine (see launch_copy_pinned)
+    PM_CUDA(launch_copy_pinned(s.offsets, s.h_offsets, 8 * static_cast<size_t>(n + 1), s.stream));
+    PM_CUDA(launch_copy_pinned(s.F, s.h_F, 72 * static_cast<size_t>(n), s.stream));
+    PM_CUDA(launch_copy_pinned(s.status, s.h_status, 4 * static_cast<size_t>(n), s.stream));
+    PM_CUDA(launch_copy_pinned(s.n_inl, s.h_ninl, 4 * static_cast<size_t>(n), s.stream));
+    PM_CUDA(launch_copy_pinned(s.iters, s.h_iters, 4 * static_cast<size_t>(n), s.stream));
+    stats.kernel_launches += 5;
     PM_CUDA(cudaEventRecord(s.ev_done, s.stream));
     stats.d2h_bytes += 8 * (n + 1) + 72 * n + 12 * n;
     return PM_OK;
@@ -950,9 +967,18 @@ struct DeviceCtx {
       if (!R.reserve(base + total)) return fail(PM_ERR_OOM, "pinned result buffers (%lld matches)", static_cast<long long>(base + total));
     }
     if (total > 0) {
-      PM_CUDA(cudaMemcpyAsync(R.q + base, s.out_q, 4 * total, cudaMemcpyDeviceToHost, s.stream));
-      PM_CUDA(cudaMemcpyAsync(R.t + base, s.out_t, 4 * total, cudaMemcpyDeviceToHost, s.stream));
-      PM_CUDA(cudaMemcpyAsync(R.inlier + base, s.out_mask, total, cudaMemcpyDeviceToHost, s.stream));
+      if (result_by_ce) {
+        // the compacted matches (MBs per batch) stay on the copy engine: as kernels they cost 3 % of the resident step
+        // (SM slots + PCIe writes) and measured no better end to end; PM_RESULT_COPY=kernel selects them (development)
+        PM_CUDA(cudaMemcpyAsync(R.q + base, s.out_q, 4 * total, cudaMemcpyDeviceToHost, s.stream));
+        PM_CUDA(cudaMemcpyAsync(R.t + base, s.out_t, 4 * total, cudaMemcpyDeviceToHost, s.stream));
+        PM_CUDA(cudaMemcpyAsync(R.inlier + base, s.out_mask, total, cudaMemcpyDeviceToHost, s.stream));
+      } else {
+        PM_CUDA(launch_copy_pinned(s.out_q, R.q + base, 4 * static_cast<size_t>(total), s.stream));
+        PM_CUDA(launch_copy_pinned(s.out_t, R.t + base, 4 * static_cast<size_t>(total), s.stream));
+        PM_CUDA(launch_copy_pinned(s.out_mask, R.inlier + base, static_cast<size_t>(total), s.stream));
+        stats.kernel_launches += 3;
+      }
       stats.d2h_bytes += 9 * total;
     }
     R.size = base + total;
@@ -1008,6 +1034,11 @@ struct DeviceCtx {
     if (!R.reserve(R.size + std::max<int64_t>(1024, n_pairs * static_cast<int64_t>(stride) * 3 / 10)))
       return fail(PM_ERR_OOM, "pinned result buffers");
     PM_CUDA(cudaEventRecord(ev_a, knn_stream));
+    const bool trace_host = std::getenv("PM_TRACE") != nullptr;
+    const auto t_host0 = std::chrono::steady_clock::now();
+    trace_on = trace_host;
+    trace_t0 = t_host0;
+    { const char* e = std::getenv("PM_RESULT_COPY"); result_by_ce = !(e && std::strcmp(e, "kernel") == 0); }
     int64_t done = 0;
     int b = 0;
     // results must be appended in pair order: retrieve slots in issue order
@@ -1023,8 +1054,15 @@ struct DeviceCtx {
         rc = fill_job(s, k, pairs[2 * (done + k)], pairs[2 * (done + k) + 1]);
         if (rc != PM_OK) return rc;
       }
+      const auto t_fill = std::chrono::steady_clock::now();
       if ((rc = enqueue_knn(s, n, mutual, true, nullptr, true)) != PM_OK) return rc;
       if ((rc = enqueue_tail(s, n, prm.do_filter != 0)) != PM_OK) return rc;
+      if (trace_host) {                      // development (PM_TRACE): when did the host get this batch out?
+        const auto t_q = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[pm trace] host: batch %d (pair0=%lld) retrieved+filled at %.3f ms, queued at %.3f ms\n", b,
+                     static_cast<long long>(first + done), std::chrono::duration<double, std::milli>(t_fill - t_host0).count(),
+                     std::chrono::duration<double, std::milli>(t_q - t_host0).count());
+      }
       s.busy = true; s.n_jobs = n; s.first_pair = first + done;
       done += n;
       ++b;

@@ -140,4 +140,7 @@ cudaError_t launch_ransac(const float2* pts1, const float2* pts2, const int32_t*
                           int stride, const RansacDev& prm, uint8_t* mask, double* F,
                           int32_t* status, int32_t* n_inliers, int32_t* iters, cudaStream_t st);
 
+// pinned host memory <-> device memory by a kernel (zero-copy), keeping the batched loop off the copy engines' queues
+cudaError_t launch_copy_pinned(const void* pinned_src, void* dst, size_t bytes, cudaStream_t st);
+
 }  // namespace pm

@@ -107,13 +107,17 @@ __device__ __forceinline__ bool ff_dist_below(const float* __restrict__ qs, cons
 }
 
 // One 16-column chunk by a half-warp, lane l = column cb + l, same fp32 chain per column as ff_dist -- but the rows
-// travel through shared memory in blocks of 32 dimensions: the half-warp fetches two rows per load instruction as
-// contiguous 128-byte pieces (4 cache lines per warp instruction instead of the 32 that one-row-per-lane loads
-// touch: the kernel was bound by L1 request throughput) and each lane then runs its own chain out of the staged
-// tile.  With THR a column stops as soon as its partial sum reaches thr (see ff_dist_below) and its row is no
-// longer fetched.  Returns true when the lane holds a finished chain (*out); false for abandoned / absent columns.
-static constexpr int FF_BLK = 32;                 // dimensions per staged block
-static constexpr int FF_TLD = FF_BLK + 4;         // padded row of the staged tile (conflict-free float4 reads)
+// travel through shared memory: the half-warp fetches each row as contiguous 256-byte pieces (one-row-per-lane loads
+// touch 32 cache lines per warp instruction and had the kernel bound by L1 request throughput) and each lane then
+// runs its own chain out of the staged tile.  The kernel is LATENCY bound (one row per half-warp at a time, every
+// fetch a round trip to L2), so the tile is fetched in few, long segments: 64 dimensions of every column first,
+// then 64 more of the columns still alive, then -- once at most 8 columns are left -- 128 dimensions at a time.
+// With THR a column stops at the end of the segment in which its partial sum reaches thr (see ff_dist_below) and its
+// row is no longer fetched: a typical first chunk (one true match among 15 other columns) costs three round trips
+// instead of the eight of a fixed 32-dimension pipeline.  Returns true when the lane holds a finished chain (*out);
+// false for abandoned / absent columns.  q_pending: the query row is still on its way into qs (cp.async by this
+// half-warp): it lands with the first segment.
+static constexpr int FF_TILE = 16 * 68;           // floats per half-warp: 16 rows x (64 + 4) or 8 rows x (128 + 4)
 __device__ __forceinline__ void ff_cp_async16(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
@@ -121,38 +125,36 @@ __device__ __forceinline__ void ff_cp_commit() { asm volatile("cp.async.commit_g
 template <int N>
 __device__ __forceinline__ void ff_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// ts: two staged tiles of 16 x FF_TLD floats (double buffer): block k + 1 is on its way (cp.async) while block k is
-// consumed, so the chain of the surviving column does not wait for memory at every block.
 template <bool THR>
 __device__ __forceinline__ bool ff_chunk_rows(float* __restrict__ ts, const float* __restrict__ qs,
                                               const float* __restrict__ tbase, int cb, int ncol, int dim, int l,
                                               unsigned hmask, float thr, float* out) {
   float acc = 0.f;
   bool alive = l < ncol;
-  const int sub = l >> 3, piece = l & 7;
   const int shift = (hmask & 1u) ? 0 : 16;
-  const float* src = tbase + static_cast<size_t>(cb) * dim + 4 * piece;
-  auto fetch = [&](int k0, int buf, unsigned am) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = 2 * i + sub;
-      if ((am >> r) & 1u) ff_cp_async16(ts + buf * (16 * FF_TLD) + r * FF_TLD + 4 * piece, src + static_cast<size_t>(r) * dim + k0);
+  const float* src = tbase + static_cast<size_t>(cb) * dim;
+  unsigned am = (__ballot_sync(hmask, alive) >> shift) & 0xFFFFu;
+  __syncwarp(hmask);                                 // the tile is free (previous chunk consumed)
+  int k0 = 0;
+  while (k0 < dim && am) {
+    const bool wide = __popc(am) <= 8 && dim - k0 >= 128;
+    const int len = wide ? 128 : 64, tld = len + 4;
+    for (unsigned m = am; m; m &= m - 1) {
+      const int r = __ffs(m) - 1;
+      const int slot = wide ? __popc(am & ((1u << r) - 1u)) : r;
+      const float* g = src + static_cast<size_t>(r) * dim + k0;
+      float* d = ts + slot * tld;
+      ff_cp_async16(d + 4 * l, g + 4 * l);
+      if (wide) ff_cp_async16(d + 64 + 4 * l, g + 64 + 4 * l);
     }
     ff_cp_commit();
-  };
-  unsigned am = (__ballot_sync(hmask, alive) >> shift) & 0xFFFFu;
-  __syncwarp(hmask);                                 // the tiles are free (previous chunk consumed)
-  if (am) fetch(0, 0, am);
-  int buf = 0;
-  for (int k0 = 0; k0 < dim && am; k0 += FF_BLK, buf ^= 1) {
-    const bool more = k0 + FF_BLK < dim;
-    if (more) fetch(k0 + FF_BLK, buf ^ 1, am);       // for every column still alive BEFORE this block's check
-    if (more) ff_cp_wait<1>(); else ff_cp_wait<0>();
+    ff_cp_wait<0>();                                 // (also the query row of this half-warp, if it was pending)
     __syncwarp(hmask);
     if (alive) {
-      const float* tl = ts + buf * (16 * FF_TLD) + l * FF_TLD;
-#pragma unroll
-      for (int k = 0; k < FF_BLK; k += 4) {
+      const int slot = wide ? __popc(am & ((1u << l) - 1u)) : l;
+      const float* tl = ts + slot * tld;
+#pragma unroll 4
+      for (int k = 0; k < len; k += 4) {
         const float4 b = *reinterpret_cast<const float4*>(tl + k);
         const float4 a = *reinterpret_cast<const float4*>(qs + k0 + k);
         float d = a.x - b.x; acc = fmaf(d, d, acc);
@@ -162,9 +164,11 @@ __device__ __forceinline__ bool ff_chunk_rows(float* __restrict__ ts, const floa
       }
       if (THR && acc >= thr) alive = false;
     }
-    am = (__ballot_sync(hmask, alive) >> shift) & 0xFFFFu;      // also: everyone is done with tile `buf`
+    k0 += len;
+    am = (__ballot_sync(hmask, alive) >> shift) & 0xFFFFu;      // also: everyone is done with the tile
   }
-  ff_cp_wait<0>();                                   // a prefetch for abandoned columns may still be in flight
+  ff_cp_wait<0>();                                   // the query row, when no column existed at all
+  __syncwarp(hmask);
   *out = acc;
   return alive;
 }
@@ -197,7 +201,7 @@ l2f_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm,
                  const float2* __restrict__ extra, int stride, float ratio, int need,
                  unsigned long long* __restrict__ counters, int e_mode) {
   __shared__ __align__(16) float qs[FF_HW][FF_MAXDIM];
-  extern __shared__ __align__(16) float ts_dyn[];       // [FF_HW][2][16 * FF_TLD]: double-buffered staged tiles
+  extern __shared__ __align__(16) float ts_dyn[];       // [FF_HW][FF_TILE]: staged tiles
   __shared__ float keys_s[FF_SPAN][6];
   __shared__ int list[FF_SPAN];
   __shared__ int ovf[FF_SPAN];
@@ -251,10 +255,8 @@ l2f_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm,
     const int r = list[e];
     const int row = span0 + r;
     const float* qrow = raw + (static_cast<size_t>(jb.q_row) + row) * dim;
-    __syncwarp(hmask);
-    for (int k = 4 * l; k < dim; k += 64)
-      *reinterpret_cast<float4*>(&qs[hw][k]) = __ldg(reinterpret_cast<const float4*>(qrow + k));
-    __syncwarp(hmask);
+    __syncwarp(hmask);                                // the previous row's chains are done with qs[hw]
+    for (int k = 4 * l; k < dim; k += 64) ff_cp_async16(&qs[hw][k], qrow + k);      // lands with the first segment
     const FfBound bd = ff_bound(fnorm[jb.q_row + row], jb.t_maxn, dim, e_mode);
     unsigned long long e1 = KEY_NONE64, e2 = KEY_NONE64;
     bool done = false;
@@ -280,8 +282,8 @@ l2f_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm,
       bool gave_up = false;
       {
         float d2;
-        const bool have = use_thr ? ff_chunk_rows<true>(ts_dyn + hw * (2 * 16 * FF_TLD), qs[hw], tbase, cb, ncol, dim, l, hmask, thr, &d2)
-                                  : ff_chunk_rows<false>(ts_dyn + hw * (2 * 16 * FF_TLD), qs[hw], tbase, cb, ncol, dim, l, hmask, thr, &d2);
+        const bool have = use_thr ? ff_chunk_rows<true>(ts_dyn + hw * FF_TILE, qs[hw], tbase, cb, ncol, dim, l, hmask, thr, &d2)
+                                  : ff_chunk_rows<false>(ts_dyn + hw * FF_TILE, qs[hw], tbase, cb, ncol, dim, l, hmask, thr, &d2);
         gave_up = l < ncol && !have;
         if (have)
           k1 = (static_cast<unsigned long long>(__float_as_uint(d2)) << 32) | static_cast<unsigned int>(cb + l);
@@ -388,7 +390,7 @@ l2f_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm,
   }
 }
 
-static constexpr int FF_DYN_SMEM = FF_HW * 2 * 16 * FF_TLD * static_cast<int>(sizeof(float));   // 36 KB
+static constexpr int FF_DYN_SMEM = FF_HW * FF_TILE * static_cast<int>(sizeof(float));   // 34 KB
 cudaError_t l2f_configure() {
   cudaError_t e = cudaFuncSetAttribute(l2f_fixup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_DYN_SMEM);
   if (e != cudaSuccess) return e;

@@ -8,6 +8,8 @@
 // The survivors are compacted in ascending query order (std::map iteration order at
 // SequentialReconstructor.cpp:243-247) and their pixel coordinates gathered as float
 // (featuresToCvPoints, utils.cpp:165-177) for the epipolar filter.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -181,6 +183,36 @@ cudaError_t select_configure() {
   if ((e = cudaFuncSetAttribute(ratio_unique_compact_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(scan_counts_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
   return cudaFuncSetAttribute(gather_slabs_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
+// Copies between pinned host memory and device memory by a KERNEL (zero-copy accesses over PCIe) instead of the copy
+// engines.  cudaMemcpyAsync copies of a stream are executed by the copy engine the driver bound that stream to, in the
+// order they were enqueued on that engine -- and pm_set_images_async enqueues every image upload up front.  Measured
+// (PM_TRACE, 100 x 8192 SIFT): the few KB of job lists / per-pair metadata of a slot whose stream shared its engine
+// with the ingest stream waited behind ~50 uploads still queued, and the next batch of that slot started 5.8 ms late
+// (end-to-end step 40 ms instead of 36.6).  Job lists and per-pair metadata therefore move by these kernels; the
+// compacted matches (MBs) stay on the copy engine.
+__global__ void copy_words_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, size_t n_words) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_words;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    dst[i] = src[i];
+}
+__global__ void copy_bytes_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, size_t n) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    dst[i] = src[i];
+}
+
+cudaError_t launch_copy_pinned(const void* src, void* dst, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return cudaSuccess;
+  const bool words = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | bytes) & 3) == 0;
+  const size_t n = words ? bytes >> 2 : bytes;
+  const unsigned grid = static_cast<unsigned>(std::min<size_t>((n + 255) / 256, 592));
+  if (words)
+    copy_words_kernel<<<grid, 256, 0, st>>>(static_cast<const uint32_t*>(src), static_cast<uint32_t*>(dst), n);
+  else
+    copy_bytes_kernel<<<grid, 256, 0, st>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), n);
+  return cudaGetLastError();
 }
 
 }  // namespace pm
