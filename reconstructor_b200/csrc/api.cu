@@ -131,6 +131,7 @@ struct Slot {
   bool mutual = false;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_done = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_jobs = nullptr, ev_knn = nullptr;
+  cudaEvent_t ev_tr[3] = {nullptr, nullptr, nullptr};   // PM_TRACE: after the fix-up / selection / RANSAC of the batch
   // device
   PairJob *d_jobs = nullptr, *d_rjobs = nullptr;
   int2 *knn_idx = nullptr, *rev_idx = nullptr;
@@ -176,6 +177,7 @@ struct Slot {
     if (ev_k1) cudaEventDestroy(ev_k1);
     if (ev_jobs) cudaEventDestroy(ev_jobs);
     if (ev_knn) cudaEventDestroy(ev_knn);
+    for (auto& e : ev_tr) if (e) { cudaEventDestroy(e); e = nullptr; }
     stream = nullptr; ev_done = ev_k0 = ev_k1 = ev_jobs = ev_knn = nullptr;
   }
 };
@@ -891,13 +893,18 @@ struct DeviceCtx {
     }
     if (use_tcf) {
       PM_CUDA(launch_l2f_fixup(raw, fnorm, dim, s.d_jobs, n, max_nq, s.knn_idx, s.knn_dist, s.knn_extra, s.stride,
-                               prm.ratio, fast ? L2F_NEED_RATIO : L2F_NEED_FULL, d_l2f, s.stream, use_tcs8 ? 1 : 0));
+                               prm.ratio, fast ? L2F_NEED_RATIO : L2F_NEED_FULL, d_l2f, s.stream, use_tcs8 ? 1 : 0,
+                               use_tcs8 ? sq8 : nullptr, use_tcs8 ? st8 : nullptr));
       ++stats.kernel_launches;
       if (want_rev) {
         PM_CUDA(launch_l2f_fixup(raw, fnorm, dim, s.d_rjobs, n, max_nt, s.rev_idx, s.rev_dist, s.rev_extra, s.stride,
                                  prm.ratio, fast ? L2F_NEED_NEAREST : L2F_NEED_FULL, d_l2f, s.stream));
         ++stats.kernel_launches;
       }
+    }
+    if (trace_on && timed) {
+      for (auto& e : s.ev_tr) if (!e) PM_CUDA(cudaEventCreate(&e));
+      PM_CUDA(cudaEventRecord(s.ev_tr[0], s.stream));
     }
     return PM_OK;
   }
@@ -935,8 +942,10 @@ struct DeviceCtx {
     PM_CUDA(launch_select(s.d_jobs, n, s.knn_idx, s.knn_dist, mutual ? s.rev_idx : nullptr, xy, s.stride,
                           prm.ratio, prm.unique_mode, s.owner, s.match_q, s.match_t, s.pts1, s.pts2,
                           s.count, s.stream));
+    if (trace_on && s.ev_tr[1]) PM_CUDA(cudaEventRecord(s.ev_tr[1], s.stream));
     PM_CUDA(launch_ransac(s.pts1, s.pts2, s.count, n, s.stride, ransac_dev(do_filter), s.mask, s.F,
                           s.status, s.n_inl, s.iters, s.stream));
+    if (trace_on && s.ev_tr[2]) PM_CUDA(cudaEventRecord(s.ev_tr[2], s.stream));
     PM_CUDA(launch_compact(s.count, n, s.stride, s.match_q, s.match_t, s.mask, s.offsets, s.out_q,
                            s.out_t, s.out_mask, s.stream));
     stats.kernel_launches += 4;
@@ -990,8 +999,10 @@ struct DeviceCtx {
         float t0 = 0, t1 = 0, t2 = 0;
         cudaEventElapsedTime(&t0, ev_a, s.ev_k0); cudaEventElapsedTime(&t1, ev_a, s.ev_k1);
         cudaEventElapsedTime(&t2, ev_a, s.ev_done);
-        std::fprintf(stderr, "[pm trace] batch pair0=%lld n=%d knn %.3f..%.3f ms tail done %.3f ms\n",
-                     static_cast<long long>(s.first_pair), s.n_jobs, t0, t1, t2);
+        float f0 = -1, f1 = -1, f2 = -1;
+        if (s.ev_tr[0]) { cudaEventElapsedTime(&f0, ev_a, s.ev_tr[0]); cudaEventElapsedTime(&f1, ev_a, s.ev_tr[1]); cudaEventElapsedTime(&f2, ev_a, s.ev_tr[2]); }
+        std::fprintf(stderr, "[pm trace] batch pair0=%lld n=%d knn %.3f..%.3f ms fix-up done %.3f select %.3f ransac %.3f tail done %.3f ms\n",
+                     static_cast<long long>(s.first_pair), s.n_jobs, t0, t1, f0, f1, f2, t2);
       }
       stats.knn_launches += 1;
       stats.knn_work += s.knn_work;

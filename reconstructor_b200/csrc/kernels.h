@@ -105,7 +105,8 @@ static constexpr int L2F_MAX_NT = 16384;   // chunk id = 10 bits of the key
 static constexpr float L2F_MAX_NORM2 = 1.01f;   // rows must satisfy |x|^2 <= this (scores stay positive)
 cudaError_t launch_l2f_fixup(const float* raw, const float* fnorm, int dim, const PairJob* jobs, int n_jobs,
                              int max_nq, int2* idx, float2* dist, const float2* extra, int stride, float ratio,
-                             int need, unsigned long long* counters, cudaStream_t st, int e_mode = 0);
+                             int need, unsigned long long* counters, cudaStream_t st, int e_mode = 0,
+                             const uint8_t* q8 = nullptr, const uint8_t* t8 = nullptr);
 
 // shared-memory carve-out of the small tail kernels = the tensor kernel's, so that they can be co-resident
 cudaError_t fixup_configure();

@@ -18,6 +18,8 @@
 //   * a row that six chunks cannot certify is scanned exhaustively by the whole block (exact, rare).
 // Ties resolve to the lowest train index (cv::BFMatcher's rule): certification is strict (<), so an
 // unevaluated column can never tie with a reported one.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -195,13 +197,24 @@ __device__ __forceinline__ void ff_write_exact(int2* knn_idx, float2* knn_dist, 
   knn_dist[o] = od;
 }
 
-__global__ void __launch_bounds__(FF_THREADS, 5)
+// PRE (rows quantised to s8, ratio-test rows, e_mode 1): before any fp32 work the columns of the first chunk are
+// screened with the QUANTISED rows the tensor kernel itself multiplied (sq8 / st8, 256 bytes per row instead of 1 KB):
+// lane l recomputes the integer dot product of its column with dp4a, which gives score'(c) = |b|^2 - 2 q_a.q_b / 254^2
+// + 2 within the same certified eps as the keys, hence a lower bound lb(score') of the exact d^2 of that column.  A
+// column with lb >= thr is "abandoned" before it starts (exactly the guarantee ff_dist_below gives: d^2 >= thr); the
+// one or two columns that survive run their fp32 chains straight from global memory.  No staged tiles: 13 KB of
+// shared memory and <= 64 registers, so that THREE blocks fit next to the tensor kernel (the staged variant: one) --
+// next to it the re-rank used to make no progress at all and ran in the gaps (PM_TRACE: tails done in bursts).
+template <bool PRE>
+__global__ void __launch_bounds__(FF_THREADS, PRE ? 8 : 5)
 l2f_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm, int dim,
                  const PairJob* __restrict__ jobs, int2* __restrict__ knn_idx, float2* __restrict__ knn_dist,
                  const float2* __restrict__ extra, int stride, float ratio, int need,
-                 unsigned long long* __restrict__ counters, int e_mode) {
+                 unsigned long long* __restrict__ counters, int e_mode, const uint8_t* __restrict__ q8,
+                 const uint8_t* __restrict__ t8) {
   __shared__ __align__(16) float qs[FF_HW][FF_MAXDIM];
-  extern __shared__ __align__(16) float ts_dyn[];       // [FF_HW][FF_TILE]: staged tiles
+  __shared__ __align__(16) uint4 qs8[PRE ? FF_HW : 1][FF_MAXDIM / 16];       // PRE: the query rows as s8
+  extern __shared__ __align__(16) float ts_dyn[];       // !PRE: [FF_HW][FF_TILE] staged tiles
   __shared__ float keys_s[FF_SPAN][6];
   __shared__ int list[FF_SPAN];
   __shared__ int ovf[FF_SPAN];
@@ -256,7 +269,16 @@ l2f_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm,
     const int row = span0 + r;
     const float* qrow = raw + (static_cast<size_t>(jb.q_row) + row) * dim;
     __syncwarp(hmask);                                // the previous row's chains are done with qs[hw]
-    for (int k = 4 * l; k < dim; k += 64) ff_cp_async16(&qs[hw][k], qrow + k);      // lands with the first segment
+    const int kp8 = dim + 32;
+    if (PRE) {
+      for (int k = 4 * l; k < dim; k += 64)
+        *reinterpret_cast<float4*>(&qs[hw][k]) = __ldg(reinterpret_cast<const float4*>(qrow + k));
+      if (16 * l < dim)
+        qs8[hw][l] = __ldg(reinterpret_cast<const uint4*>(q8 + (static_cast<size_t>(jb.q_row) + row) * kp8) + l);
+      __syncwarp(hmask);
+    } else {
+      for (int k = 4 * l; k < dim; k += 64) ff_cp_async16(&qs[hw][k], qrow + k);      // lands with the first segment
+    }
     const FfBound bd = ff_bound(fnorm[jb.q_row + row], jb.t_maxn, dim, e_mode);
     unsigned long long e1 = KEY_NONE64, e2 = KEY_NONE64;
     bool done = false;
@@ -281,9 +303,39 @@ l2f_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm,
       }
       bool gave_up = false;
       {
-        float d2;
-        const bool have = use_thr ? ff_chunk_rows<true>(ts_dyn + hw * FF_TILE, qs[hw], tbase, cb, ncol, dim, l, hmask, thr, &d2)
-                                  : ff_chunk_rows<false>(ts_dyn + hw * FF_TILE, qs[hw], tbase, cb, ncol, dim, l, hmask, thr, &d2);
+        float d2 = 0.f;
+        bool have;
+        if (PRE) {
+          bool alive = l < ncol;
+          if (use_thr && alive) {
+            const uint4* tq = reinterpret_cast<const uint4*>(t8 + (static_cast<size_t>(jb.t_row) + cb + l) * kp8);
+            int dotneg = 0;                                  // q_a . (-q_b): the train form stores -q
+            for (int w = 0; w < (dim >> 4); ++w) {
+              const uint4 b = __ldg(tq + w);
+              const uint4 a = qs8[hw][w];
+              dotneg = __dp4a(static_cast<int>(a.x), static_cast<int>(b.x), dotneg);
+              dotneg = __dp4a(static_cast<int>(a.y), static_cast<int>(b.y), dotneg);
+              dotneg = __dp4a(static_cast<int>(a.z), static_cast<int>(b.z), dotneg);
+              dotneg = __dp4a(static_cast<int>(a.w), static_cast<int>(b.w), dotneg);
+            }
+            const double sc = static_cast<double>(fnorm[jb.t_row + cb + l]) + 2.0 +
+                              static_cast<double>(dotneg) * (2.0 / (254.0 * 254.0));
+            if (bd.lb(__double2float_rd(sc)) >= thr) alive = false;          // d^2 of this column >= thr for certain
+          }
+          have = false;
+          if (alive) {
+            const float* trow = tbase + static_cast<size_t>(cb + l) * dim;
+            if (use_thr) {
+              have = ff_dist_below(qs[hw], trow, dim, thr, &d2);
+            } else {
+              d2 = ff_dist(qs[hw], trow, dim);
+              have = true;
+            }
+          }
+        } else {
+          have = use_thr ? ff_chunk_rows<true>(ts_dyn + hw * FF_TILE, qs[hw], tbase, cb, ncol, dim, l, hmask, thr, &d2)
+                         : ff_chunk_rows<false>(ts_dyn + hw * FF_TILE, qs[hw], tbase, cb, ncol, dim, l, hmask, thr, &d2);
+        }
         gave_up = l < ncol && !have;
         if (have)
           k1 = (static_cast<unsigned long long>(__float_as_uint(d2)) << 32) | static_cast<unsigned int>(cb + l);
@@ -392,19 +444,29 @@ l2f_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm,
 
 static constexpr int FF_DYN_SMEM = FF_HW * FF_TILE * static_cast<int>(sizeof(float));   // 34 KB
 cudaError_t l2f_configure() {
-  cudaError_t e = cudaFuncSetAttribute(l2f_fixup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_DYN_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(l2f_fixup_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_DYN_SMEM);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(l2f_fixup_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if ((e = cudaFuncSetAttribute(l2f_fixup_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(l2f_fixup_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
+// q8 / t8: the s8 forms of the rows (pack_float_kernel), rows of dim + 32 bytes; with them, e_mode 1 and need =
+// L2F_NEED_RATIO the prefiltering variant runs (PM_L2F_STAGED=1 keeps the staged one: development)
 cudaError_t launch_l2f_fixup(const float* raw, const float* fnorm, int dim, const PairJob* jobs, int n_jobs,
                              int max_nq, int2* idx, float2* dist, const float2* extra, int stride, float ratio,
-                             int need, unsigned long long* counters, cudaStream_t st, int e_mode) {
+                             int need, unsigned long long* counters, cudaStream_t st, int e_mode, const uint8_t* q8,
+                             const uint8_t* t8) {
   if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
   if (dim <= 0 || dim > FF_MAXDIM || (dim & 63)) return cudaErrorInvalidValue;
   dim3 grid((max_nq + FF_SPAN - 1) / FF_SPAN, n_jobs);
-  l2f_fixup_kernel<<<grid, FF_THREADS, FF_DYN_SMEM, st>>>(raw, fnorm, dim, jobs, idx, dist, extra, stride, ratio, need,
-                                                counters, e_mode);
+  static const bool staged_only = std::getenv("PM_L2F_STAGED") != nullptr;
+  if (e_mode == 1 && need == L2F_NEED_RATIO && q8 != nullptr && t8 != nullptr && !staged_only)
+    l2f_fixup_kernel<true><<<grid, FF_THREADS, 0, st>>>(raw, fnorm, dim, jobs, idx, dist, extra, stride, ratio, need, counters,
+                                                        e_mode, q8, t8);
+  else
+    l2f_fixup_kernel<false><<<grid, FF_THREADS, FF_DYN_SMEM, st>>>(raw, fnorm, dim, jobs, idx, dist, extra, stride, ratio, need,
+                                                                   counters, e_mode, nullptr, nullptr);
   return cudaGetLastError();
 }
 

@@ -114,14 +114,19 @@ namespace pm {
 
 // Exclusive scan of the per-slot counts (one block) and gather of the per-slot slabs into the
 // contiguous CSR staging arrays that are copied to the host with one D2H each.
-__global__ void __launch_bounds__(1024)
+// 256 threads (8 K registers): a 1024-thread block (32 K registers) does not fit next to a persistent tensor kernel, so
+// it ran only at the boundary between two of them -- every batch's tail stalled there, and behind the SuperPoint kernel
+// (2.8 ms per launch) the tails fell so far behind that the kNN stream ran out of slots (PM_TRACE stage events).
+static constexpr int SC_THREADS = 256;
+__global__ void __launch_bounds__(SC_THREADS)
 scan_counts_kernel(const int32_t* __restrict__ count, int n_jobs, int64_t* __restrict__ offsets) {
-  __shared__ long long warp_sum[32];
+  constexpr int NW = SC_THREADS / 32;
+  __shared__ long long warp_sum[NW];
   __shared__ long long carry;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) carry = 0;
   __syncthreads();
-  for (int c0 = 0; c0 < n_jobs; c0 += 1024) {
+  for (int c0 = 0; c0 < n_jobs; c0 += SC_THREADS) {
     const int i = c0 + tid;
     const long long v = i < n_jobs ? count[i] : 0;
     long long s = v;
@@ -133,20 +138,20 @@ scan_counts_kernel(const int32_t* __restrict__ count, int n_jobs, int64_t* __res
     if (lane == 31) warp_sum[warp] = s;
     __syncthreads();
     if (warp == 0) {
-      const long long w = warp_sum[lane];
+      const long long w = lane < NW ? warp_sum[lane] : 0;
       long long t = w;
 #pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
+      for (int off = 1; off < NW; off <<= 1) {
         const long long o = __shfl_up_sync(0xffffffffu, t, off);
         if (lane >= off) t += o;
       }
-      warp_sum[lane] = t - w;
+      if (lane < NW) warp_sum[lane] = t - w;
     }
     __syncthreads();
     const long long excl = carry + warp_sum[warp] + (s - v);
     if (i < n_jobs) offsets[i] = excl;
     __syncthreads();
-    if (tid == 1023) carry = excl + v;
+    if (tid == SC_THREADS - 1) carry = excl + v;
     __syncthreads();
   }
   if (tid == 0) offsets[n_jobs] = carry;
@@ -172,7 +177,7 @@ cudaError_t launch_compact(const int32_t* count, int n_jobs, int stride, const i
                            const int32_t* match_t, const uint8_t* mask, int64_t* offsets,
                            int32_t* out_q, int32_t* out_t, uint8_t* out_mask, cudaStream_t st) {
   if (n_jobs <= 0) return cudaSuccess;
-  scan_counts_kernel<<<1, 1024, 0, st>>>(count, n_jobs, offsets);
+  scan_counts_kernel<<<1, SC_THREADS, 0, st>>>(count, n_jobs, offsets);
   gather_slabs_kernel<<<n_jobs, 256, 0, st>>>(count, stride, match_q, match_t, mask, offsets, out_q,
                                               out_t, out_mask);
   return cudaGetLastError();
