@@ -28,6 +28,13 @@ namespace pm {
 static constexpr int FF_THREADS = 128;            // 8 half-warps
 static constexpr int FF_HW = FF_THREADS / 16;
 static constexpr int FF_SPAN = 128;               // query rows per block
+// block size of the s8-prefilter variant.  128 threads x 64 registers = 8 K: three blocks fit next to the SuperPoint tensor
+// kernel.  256 threads (16 K, the footprint of the selection and RANSAC blocks, so that no block size is favoured when a
+// hole opens) measured the same: 61.7 k vs 63.4 k pairs/s.
+#ifndef PM_FFP_THREADS
+#define PM_FFP_THREADS 128
+#endif
+static constexpr int FFP_THREADS = PM_FFP_THREADS;
 static constexpr int FF_MAXDIM = 256;
 static constexpr unsigned int FF_IDMASK = 0x3FFu;
 
@@ -206,23 +213,24 @@ __device__ __forceinline__ void ff_write_exact(int2* knn_idx, float2* knn_dist, 
 // shared memory and <= 64 registers, so that THREE blocks fit next to the tensor kernel (the staged variant: one) --
 // next to it the re-rank used to make no progress at all and ran in the gaps (PM_TRACE: tails done in bursts).
 template <bool PRE>
-__global__ void __launch_bounds__(FF_THREADS, PRE ? 8 : 5)
+__global__ void __launch_bounds__(PRE ? FFP_THREADS : FF_THREADS, PRE ? (1024 / FFP_THREADS) : 5)
 l2f_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm, int dim,
                  const PairJob* __restrict__ jobs, int2* __restrict__ knn_idx, float2* __restrict__ knn_dist,
                  const float2* __restrict__ extra, int stride, float ratio, int need,
                  unsigned long long* __restrict__ counters, int e_mode, const uint8_t* __restrict__ q8,
                  const uint8_t* __restrict__ t8) {
-  __shared__ __align__(16) float qs[FF_HW][FF_MAXDIM];
-  __shared__ __align__(16) uint4 qs8[PRE ? FF_HW : 1][FF_MAXDIM / 16];       // PRE: the query rows as s8
-  extern __shared__ __align__(16) float ts_dyn[];       // !PRE: [FF_HW][FF_TILE] staged tiles
-  __shared__ float keys_s[FF_SPAN][6];
-  __shared__ int list[FF_SPAN];
-  __shared__ int ovf[FF_SPAN];
-  __shared__ unsigned long long red[FF_HW][2];
+  constexpr int THREADS = PRE ? FFP_THREADS : FF_THREADS, HW = THREADS / 16, SPAN = THREADS;
+  __shared__ __align__(16) float qs[HW][FF_MAXDIM];
+  __shared__ __align__(16) uint4 qs8[PRE ? HW : 1][FF_MAXDIM / 16];       // PRE: the query rows as s8
+  extern __shared__ __align__(16) float ts_dyn[];       // !PRE: one FF_TILE per half-warp (staged tiles)
+  __shared__ float keys_s[SPAN][6];
+  __shared__ int list[SPAN];
+  __shared__ int ovf[SPAN];
+  __shared__ unsigned long long red[HW][2];
   __shared__ int cnt, n_ovf;
 
   const PairJob jb = jobs[blockIdx.y];
-  const int span0 = blockIdx.x * FF_SPAN;
+  const int span0 = blockIdx.x * SPAN;
   if (span0 >= jb.nq) return;
   const int tid = threadIdx.x, lane = tid & 31;
   const int hw = tid >> 4, l = lane & 15;
@@ -264,7 +272,7 @@ l2f_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm,
   float worst = 0.f;
 
   // ---- pass 2: one half-warp per surviving row, lane = column of the chunk under evaluation ---------
-  for (int e = hw; e < n_need; e += FF_HW) {
+  for (int e = hw; e < n_need; e += HW) {
     const int r = list[e];
     const int row = span0 + r;
     const float* qrow = raw + (static_cast<size_t>(jb.q_row) + row) * dim;
@@ -404,11 +412,11 @@ l2f_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm,
     const int row = span0 + ovf[e];
     const float* qrow = raw + (static_cast<size_t>(jb.q_row) + row) * dim;
     __syncthreads();
-    for (int k = 4 * tid; k < dim; k += 4 * FF_THREADS)
+    for (int k = 4 * tid; k < dim; k += 4 * THREADS)
       *reinterpret_cast<float4*>(&qs[0][k]) = __ldg(reinterpret_cast<const float4*>(qrow + k));
     __syncthreads();
     unsigned long long m1 = KEY_NONE64, m2 = KEY_NONE64;
-    for (int col = tid; col < jb.nt; col += FF_THREADS) {
+    for (int col = tid; col < jb.nt; col += THREADS) {
       const float d2 = ff_dist(qs[0], tbase + static_cast<size_t>(col) * dim, dim);
       const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(d2)) << 32) | static_cast<unsigned int>(col);
       const unsigned long long hi = key > m1 ? key : m1;
@@ -424,7 +432,7 @@ l2f_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm,
     if (l == 0) { red[hw][0] = m1; red[hw][1] = m2; }
     __syncthreads();
     if (tid == 0) {
-      for (int h = 1; h < FF_HW; ++h) ff_merge(m1, m2, red[h][0], red[h][1]);
+      for (int h = 1; h < HW; ++h) ff_merge(m1, m2, red[h][0], red[h][1]);
       ff_write_exact(knn_idx, knn_dist, base + row, m1, m2);
     }
   }
@@ -459,13 +467,12 @@ cudaError_t launch_l2f_fixup(const float* raw, const float* fnorm, int dim, cons
                              const uint8_t* t8) {
   if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
   if (dim <= 0 || dim > FF_MAXDIM || (dim & 63)) return cudaErrorInvalidValue;
-  dim3 grid((max_nq + FF_SPAN - 1) / FF_SPAN, n_jobs);
   static const bool staged_only = std::getenv("PM_L2F_STAGED") != nullptr;
   if (e_mode == 1 && need == L2F_NEED_RATIO && q8 != nullptr && t8 != nullptr && !staged_only)
-    l2f_fixup_kernel<true><<<grid, FF_THREADS, 0, st>>>(raw, fnorm, dim, jobs, idx, dist, extra, stride, ratio, need, counters,
+    l2f_fixup_kernel<true><<<dim3((max_nq + FFP_THREADS - 1) / FFP_THREADS, n_jobs), FFP_THREADS, 0, st>>>(raw, fnorm, dim, jobs, idx, dist, extra, stride, ratio, need, counters,
                                                         e_mode, q8, t8);
   else
-    l2f_fixup_kernel<false><<<grid, FF_THREADS, FF_DYN_SMEM, st>>>(raw, fnorm, dim, jobs, idx, dist, extra, stride, ratio, need,
+    l2f_fixup_kernel<false><<<dim3((max_nq + FF_SPAN - 1) / FF_SPAN, n_jobs), FF_THREADS, FF_DYN_SMEM, st>>>(raw, fnorm, dim, jobs, idx, dist, extra, stride, ratio, need,
                                                                    counters, e_mode, nullptr, nullptr);
   return cudaGetLastError();
 }
