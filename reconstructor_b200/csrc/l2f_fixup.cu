@@ -209,9 +209,9 @@ __device__ __forceinline__ void ff_write_exact(int2* knn_idx, float2* knn_dist, 
 // lane l recomputes the integer dot product of its column with dp4a, which gives score'(c) = |b|^2 - 2 q_a.q_b / 254^2
 // + 2 within the same certified eps as the keys, hence a lower bound lb(score') of the exact d^2 of that column.  A
 // column with lb >= thr is "abandoned" before it starts (exactly the guarantee ff_dist_below gives: d^2 >= thr); the
-// one or two columns that survive run their fp32 chains straight from global memory.  No staged tiles: 13 KB of
-// shared memory and <= 64 registers, so that THREE blocks fit next to the tensor kernel (the staged variant: one) --
-// next to it the re-rank used to make no progress at all and ran in the gaps (PM_TRACE: tails done in bursts).
+// one or two columns that survive run their fp32 chains straight from global memory.  No staged tiles: 14.5 KB of
+// shared memory and <= 64 registers, so that THREE blocks fit next to the tensor kernel (the staged variant: one).
+// Opt-in (see launch_l2f_fixup): it did not change the step and is slower alone.
 template <bool PRE>
 __global__ void __launch_bounds__(PRE ? FFP_THREADS : FF_THREADS, PRE ? (1024 / FFP_THREADS) : 5)
 l2f_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm, int dim,
@@ -459,16 +459,18 @@ cudaError_t l2f_configure() {
   return cudaFuncSetAttribute(l2f_fixup_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
-// q8 / t8: the s8 forms of the rows (pack_float_kernel), rows of dim + 32 bytes; with them, e_mode 1 and need =
-// L2F_NEED_RATIO the prefiltering variant runs (PM_L2F_STAGED=1 keeps the staged one: development)
+// q8 / t8: the s8 forms of the rows (pack_float_kernel), rows of dim + 32 bytes; with them, e_mode 1, need =
+// L2F_NEED_RATIO and PM_L2F_PREFILTER=1 in the environment the prefiltering variant runs.  The staged variant is the
+// default: alone it needs 0.99 ms per 256 pairs against 1.27 ms (the survivors' one-row-per-lane loads have few
+// requests in flight), and next to the tensor kernel the step is the same with either (63.7 k vs 62.6 k pairs/s).
 cudaError_t launch_l2f_fixup(const float* raw, const float* fnorm, int dim, const PairJob* jobs, int n_jobs,
                              int max_nq, int2* idx, float2* dist, const float2* extra, int stride, float ratio,
                              int need, unsigned long long* counters, cudaStream_t st, int e_mode, const uint8_t* q8,
                              const uint8_t* t8) {
   if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
   if (dim <= 0 || dim > FF_MAXDIM || (dim & 63)) return cudaErrorInvalidValue;
-  static const bool staged_only = std::getenv("PM_L2F_STAGED") != nullptr;
-  if (e_mode == 1 && need == L2F_NEED_RATIO && q8 != nullptr && t8 != nullptr && !staged_only)
+  static const bool prefilter = std::getenv("PM_L2F_PREFILTER") != nullptr;
+  if (e_mode == 1 && need == L2F_NEED_RATIO && q8 != nullptr && t8 != nullptr && prefilter)
     l2f_fixup_kernel<true><<<dim3((max_nq + FFP_THREADS - 1) / FFP_THREADS, n_jobs), FFP_THREADS, 0, st>>>(raw, fnorm, dim, jobs, idx, dist, extra, stride, ratio, need, counters,
                                                         e_mode, q8, t8);
   else
