@@ -219,3 +219,23 @@ def test_image_cache_numpy_roundtrip(tmp_path):
     assert [r["id"] for r in back] == [1, 3] and back[0]["xy"] is None
     assert np.array_equal(back[1]["desc"], imgs[3][0]) and np.array_equal(back[1]["xy"], imgs[3][1])
     assert back[1]["dim"] == 256 and back[1]["dtype"] == cache.DESC_U8_BITS
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the driver's CPU arm) prints one JSON line with the contract's keys; it runs the
+    cv2 restatement of the reference body on the host cores and needs no GPU."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--images", "6", "--kp", "512",
+                        "--steps", "1", "--warmup", "0", "--cpu-seconds", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["unit"] == "pairs/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in line["config"]
