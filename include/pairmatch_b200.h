@@ -61,9 +61,16 @@ enum { PM_UNIQUE_FIRST_WINS = 0, PM_MUTUAL_NN = 1, PM_UNIQUE_NONE = 2 };
  *   PM_RESID_SAMPSON             first-order geometric error (north-star wording). */
 enum { PM_RESID_SYMMETRIC_EPIPOLAR = 0, PM_RESID_SAMPSON = 1 };
 
-/* Hypothesis sampler.  PM_SAMPLER_OPENCV_MWC replays cv::findFundamentalMat's fixed-seed
- * multiply-with-carry stream, which makes inlier masks comparable with cv2 one to one. */
-enum { PM_SAMPLER_OPENCV_MWC = 0 };
+/* Hypothesis sampler.
+ *   PM_SAMPLER_OPENCV_MWC  replays cv::findFundamentalMat's fixed-seed multiply-with-carry stream, which makes
+ *                          inlier masks comparable with cv2 one to one (the default; GeometricFilter.cpp:47).
+ *   PM_SAMPLER_PHILOX      free-running counter-based sampler: the subset of iteration k is a pure
+ *                          function of (pm_params.seed, query image id, train image id, k) -- Philox4x32-10 -- so a
+ *                          pair's result does not depend on the batch / device / rank that ran it and all subsets of
+ *                          a round are drawn in parallel.  Everything else (7-point solver, residual, "strictly more
+ *                          inliers replaces", adaptive stop) is unchanged.  Parity: the repo's CPU filter with the
+ *                          same sampler (oracle/pm_oracle.c, ORC_SAMPLER_PHILOX). */
+enum { PM_SAMPLER_OPENCV_MWC = 0, PM_SAMPLER_PHILOX = 1 };
 
 /* Per-pair outcome (pm_csr_result.status / pm_pair_result.status). */
 enum {
@@ -87,7 +94,12 @@ typedef struct {
   int64_t reserve_keypoints;  /* device arena rows to preallocate, 0 = grow on demand       */
   int32_t debug_flags;        /* kernel-variant switches for parity cross-checks and probes;
                                  0 = product defaults (see enqueue_knn in csrc/api.cu)      */
-  int32_t reserved;
+  int32_t refit_8point;       /* != 0: F of a filtered pair (>= 8 inliers) is re-estimated from its
+                                 inliers with the normalised 8-point algorithm (what
+                                 cv::findFundamentalMat(FM_8POINT) computes); mask and counts
+                                 stay those of the winning RANSAC hypothesis.  Not reachable from
+                                 the reference's call (defaults), hence off by default.     */
+  uint64_t seed;              /* PM_SAMPLER_PHILOX: global seed (per-pair key = f(seed, i, j)) */
 } pm_params;
 
 /* One pair, caller-allocated outputs (capacity = number of query keypoints). */
@@ -174,6 +186,9 @@ int pm_set_image_device_async(pm_handle h, int img_id, const void* d_desc, int n
 /* Waits until every asynchronously ingested image is resident. */
 int pm_sync_images(pm_handle h);
 int pm_num_keypoints(pm_handle h, int img_id);
+/* Forgets an image and returns its device rows to the handle's free list (re-used by later pm_set_image calls of
+ * at most that many keypoints).  PM_ERR_STATE when the id is not set. */
+int pm_remove_image(pm_handle h, int img_id);
 
 /* Raw 2-NN rows of pair (i -> j): what knnMatch(desc_i, desc_j, 2) returns as DMatch rows
  * (FeatureMatcher.cpp:49).  idx/dist are [n_i][2]; missing neighbours are idx -1, dist +inf.
@@ -192,13 +207,22 @@ int pm_match_descriptors(pm_handle h, const void* desc1, int n1, const void* des
  * found (the reference then returns Zero() and an empty mask, GeometricFilter.cpp:50-53). */
 int pm_filter_pair_F(pm_handle h, const float* xy1, const float* xy2, int M,
                      double F[9], uint8_t* mask, int32_t* status, int32_t* iters);
+/* The same with an explicit Philox key for this one call (filter_pair_F(h, xy1, xy2, M, seed, ...)):
+ * with PM_SAMPLER_PHILOX the hypothesis stream is f(pair_key, iteration); with PM_SAMPLER_OPENCV_MWC the key is
+ * ignored.  pm_filter_pair_F uses pm_params.seed as the key.  pm_pair_seed gives the key the batched loop derives
+ * for pair (img_i, img_j), so a single pair can be re-run bit-identically. */
+int pm_filter_pair_F_seeded(pm_handle h, const float* xy1, const float* xy2, int M, uint64_t pair_key,
+                            double F[9], uint8_t* mask, int32_t* status, int32_t* iters);
+uint64_t pm_pair_seed(uint64_t seed, int32_t img_i, int32_t img_j);
 
 /* The whole pair body for one pair (match + gate + filter). */
 int pm_match_filter_pair(pm_handle h, int img_i, int img_j, pm_pair_result* out);
 
-/* The whole loop: pairs = [n_pairs][2] image ids (query, train), or NULL for all i < j over
- * the images set so far.  Runs kNN -> ratio -> uniqueness -> F-RANSAC batched on the device(s)
- * and returns CSR arrays in host memory. */
+/* The whole loop: pairs = [n_pairs][2] image ids (query, train).  pairs == NULL with n_pairs ==
+ * PM_ALL_PAIRS: all i < j over the images set so far (the FakeImgMatcher list, ImageMatcher.cpp:6-24);
+ * n_pairs == 0 is an empty list (an empty result), whatever `pairs` is.  Runs kNN -> ratio ->
+ * uniqueness -> F-RANSAC batched on the device(s) and returns CSR arrays in host memory. */
+#define PM_ALL_PAIRS ((int64_t)-1)
 int pm_match_all_pairs(pm_handle h, const int32_t* pairs, int64_t n_pairs, pm_csr_result** out);
 int pm_free_result(pm_csr_result* r);
 
@@ -221,6 +245,15 @@ int pm_reset_stats(pm_handle h);
 /* popc32 / fp32 pipe micro-benchmarks used to measure the roofline denominators that
  * MEASURED_PEAKS.json does not hold: returns ops per second. */
 int pm_measure_popc_peak(pm_handle h, double* popc32_per_s);
+/* Tensor-pipe peaks of the MMA kinds the kNN kernels use, measured live (TMA + tcgen05.mma only, operands resident in
+ * shared memory, no epilogue; M = 256, N = 256 per CTA pair): FLOP/s (2 per multiply-add).  MEASURED_PEAKS.json holds
+ * the bf16 figure only; the roofline fractions of bench.py divide by these same-kind numbers. */
+enum { PM_PEAK_KIND_F16 = 0, PM_PEAK_KIND_I8 = 1, PM_PEAK_KIND_MXF4 = 2 };
+int pm_measure_tensor_peak(pm_handle h, int kind, double* flop_per_s);
+
+/* Development aid of the tensor path (raw accumulators of the first 256 x 128 block next to the kNN rows of a pair);
+ * exported for the parity tests, not part of the drop-in surface. */
+int pm_debug_tc_dump(pm_handle h, int img_i, int img_j, int32_t* idx, float* dist, float* acc256x128);
 
 #ifdef __cplusplus
 }

@@ -17,9 +17,13 @@ UNIQUE_FIRST_WINS, MUTUAL_NN, UNIQUE_NONE = 0, 1, 2
 RESID_SYMMETRIC_EPIPOLAR, RESID_SAMPSON = 0, 1
 
 
+SAMPLER_OPENCV_MWC, SAMPLER_PHILOX = 0, 1
+
+
 class RansacParams(C.Structure):
     _fields_ = [("threshold", C.c_double), ("confidence", C.c_double),
-                ("max_iters", C.c_int), ("residual_mode", C.c_int)]
+                ("max_iters", C.c_int), ("residual_mode", C.c_int),
+                ("sampler", C.c_int), ("refit_8point", C.c_int), ("seed", C.c_uint64)]
 
 
 class RansacTrace(C.Structure):
@@ -67,8 +71,42 @@ def _p(a, t):
 
 
 def default_params(threshold=3.0, confidence=0.99, max_iters=1000,
-                   residual_mode=RESID_SYMMETRIC_EPIPOLAR) -> RansacParams:
-    return RansacParams(threshold, confidence, max_iters, residual_mode)
+                   residual_mode=RESID_SYMMETRIC_EPIPOLAR, sampler=SAMPLER_OPENCV_MWC, refit_8point=0,
+                   seed=0) -> RansacParams:
+    return RansacParams(threshold, confidence, max_iters, residual_mode, sampler, refit_8point, seed)
+
+
+def philox4x32_10(ctr, key):
+    c = (C.c_uint32 * 4)(*ctr)
+    lib().orc_philox4x32_10(c, C.c_uint32(key[0]), C.c_uint32(key[1]))
+    return list(c)
+
+
+def pair_seed(seed: int, i: int, j: int) -> int:
+    f = lib().orc_pair_seed
+    f.restype = C.c_uint64
+    f.argtypes = [C.c_uint64, C.c_int32, C.c_int32]
+    return int(f(seed, i, j))
+
+
+def philox_subset(xy1, xy2, seed: int, it: int):
+    xy1 = np.ascontiguousarray(xy1, np.float32); xy2 = np.ascontiguousarray(xy2, np.float32)
+    idx = np.zeros(7, np.int32)
+    f = lib().orc_philox_subset
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_void_p]
+    ok = f(xy1.ctypes.data, xy2.ctypes.data, xy1.shape[0], seed, it, idx.ctypes.data)
+    return bool(ok), idx
+
+
+def eight_point(xy1, xy2, mask=None):
+    xy1 = np.ascontiguousarray(xy1, np.float32); xy2 = np.ascontiguousarray(xy2, np.float32)
+    F = np.zeros(9, np.float64)
+    mp = None
+    if mask is not None:
+        mask = np.ascontiguousarray(mask, np.uint8)
+        mp = _p(mask, C.c_uint8)
+    ok = lib().orc_eight_point(_p(xy1, C.c_float), _p(xy2, C.c_float), xy1.shape[0], mp, _p(F, C.c_double))
+    return bool(ok), F.reshape(3, 3)
 
 
 def knn2_hamming(q: np.ndarray, t: np.ndarray):

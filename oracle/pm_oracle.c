@@ -381,6 +381,165 @@ void orc_residuals(const double F[9], const float* m1, const float* m2, int n,
   }
 }
 
+/* ---- Philox sampler ("PHILOX(seed,i,j) = free-running") -------------------------------------
+ * The subset of iteration k is a pure function of (pair seed, k): counter = (k, block, 0, 'PMRF'), key = seed.
+ * Each block yields four words; word w becomes the index floor(w * n / 2^32).  Slots are filled in order,
+ * duplicates are skipped, a complete 7-subset is tested like OpenCV's checkSubset (last point against all
+ * pairs, both images) and on rejection the filling restarts with the NEXT words of the same stream. */
+void orc_philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+static uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+uint64_t orc_pair_seed(uint64_t seed, int32_t i, int32_t j) {
+  return splitmix64(seed ^ splitmix64(((uint64_t)(uint32_t)i << 32) | (uint32_t)j));
+}
+static int philox_subset(const float* xy1, const float* xy2, int n, uint64_t seed, int iter,
+                         int32_t idx[7], float s1[14], float s2[14]) {
+  int filled = 0;
+  for (uint32_t blk = 0; blk < 256; ++blk) {
+    uint32_t c[4] = { (uint32_t)iter, blk, 0u, 0x504D5246u };
+    orc_philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    for (int w = 0; w < 4; ++w) {
+      const int v = (int)(((uint64_t)c[w] * (uint64_t)(uint32_t)n) >> 32);
+      int j = 0;
+      for (; j < filled; ++j) if (idx[j] == v) break;
+      if (j < filled) continue;
+      idx[filled] = v;
+      s1[2 * filled] = xy1[2 * v]; s1[2 * filled + 1] = xy1[2 * v + 1];
+      s2[2 * filled] = xy2[2 * v]; s2[2 * filled + 1] = xy2[2 * v + 1];
+      if (++filled == 7) {
+        if (!last_point_collinear(s1, 7) && !last_point_collinear(s2, 7)) return 1;
+        filled = 0;
+      }
+    }
+  }
+  return 0;
+}
+int orc_philox_subset(const float* xy1, const float* xy2, int n, uint64_t seed, int iter, int32_t idx[7]) {
+  float s1[14], s2[14];
+  return philox_subset(xy1, xy2, n, seed, iter, idx, s1, s2);
+}
+
+/* ---- normalised 8-point refit --------------------------------------------------------------------------------
+ * cv::findFundamentalMat(FM_8POINT) (run8Point, SURVEY App. A [R]); unreachable from the reference's own call
+ * (GeometricFilter.cpp:47 uses the defaults), offered as the optional refit the north star names.
+ * Cyclic Jacobi for the symmetric eigenproblems: fixed sweep order, so the CUDA kernel can follow it operation for
+ * operation. */
+static void jacobi_sym(double* A, double* V, int n, int sweeps) {     /* A: n x n symmetric (destroyed), V: eigenvectors in columns */
+  for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) V[i * n + j] = i == j ? 1.0 : 0.0;
+  for (int s = 0; s < sweeps; ++s) {
+    double off = 0;
+    for (int p = 0; p < n; ++p) for (int q = p + 1; q < n; ++q) off += A[p * n + q] * A[p * n + q];
+    if (off == 0.0) break;
+    for (int p = 0; p < n - 1; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        const double apq = A[p * n + q];
+        if (apq == 0.0) continue;
+        const double theta = (A[q * n + q] - A[p * n + p]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < n; ++k) {                   /* columns p, q of A */
+          const double akp = A[k * n + p], akq = A[k * n + q];
+          A[k * n + p] = c * akp - sn * akq;
+          A[k * n + q] = sn * akp + c * akq;
+        }
+        for (int k = 0; k < n; ++k) {                   /* rows p, q of A */
+          const double apk = A[p * n + k], aqk = A[q * n + k];
+          A[p * n + k] = c * apk - sn * aqk;
+          A[q * n + k] = sn * apk + c * aqk;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double vkp = V[k * n + p], vkq = V[k * n + q];
+          V[k * n + p] = c * vkp - sn * vkq;
+          V[k * n + q] = sn * vkp + c * vkq;
+        }
+      }
+  }
+}
+
+int orc_eight_point(const float* m1, const float* m2, int n, const uint8_t* mask, double F[9]) {
+  int cnt = 0;
+  double cx1 = 0, cy1 = 0, cx2 = 0, cy2 = 0;
+  for (int i = 0; i < n; ++i) {
+    if (mask && !mask[i]) continue;
+    cx1 += m1[2 * i]; cy1 += m1[2 * i + 1]; cx2 += m2[2 * i]; cy2 += m2[2 * i + 1];
+    ++cnt;
+  }
+  if (cnt < 8) return 0;
+  const double t = 1.0 / cnt;
+  cx1 *= t; cy1 *= t; cx2 *= t; cy2 *= t;
+  double sc1 = 0, sc2 = 0;
+  for (int i = 0; i < n; ++i) {
+    if (mask && !mask[i]) continue;
+    const double x1 = m1[2 * i] - cx1, y1 = m1[2 * i + 1] - cy1, x2 = m2[2 * i] - cx2, y2 = m2[2 * i + 1] - cy2;
+    sc1 += sqrt(x1 * x1 + y1 * y1);
+    sc2 += sqrt(x2 * x2 + y2 * y2);
+  }
+  sc1 *= t; sc2 *= t;
+  if (sc1 < FLT_EPSILON || sc2 < FLT_EPSILON) return 0;
+  sc1 = sqrt(2.0) / sc1; sc2 = sqrt(2.0) / sc2;
+  double A[81], V[81];
+  memset(A, 0, sizeof A);
+  for (int i = 0; i < n; ++i) {
+    if (mask && !mask[i]) continue;
+    const double x1 = (m1[2 * i] - cx1) * sc1, y1 = (m1[2 * i + 1] - cy1) * sc1;
+    const double x2 = (m2[2 * i] - cx2) * sc2, y2 = (m2[2 * i + 1] - cy2) * sc2;
+    const double r[9] = { x2 * x1, x2 * y1, x2, y2 * x1, y2 * y1, y2, x1, y1, 1.0 };
+    for (int j = 0; j < 9; ++j) for (int k = 0; k < 9; ++k) A[j * 9 + k] += r[j] * r[k];
+  }
+  jacobi_sym(A, V, 9, 60);
+  int lo = 0, nz = 0;
+  for (int i = 0; i < 9; ++i) {
+    if (A[i * 9 + i] < A[lo * 9 + lo]) lo = i;
+    if (fabs(A[i * 9 + i]) < DBL_EPSILON) ++nz;
+  }
+  if (nz > 1) return 0;                                  /* rank < 8: degenerate configuration */
+  double F0[9];
+  for (int i = 0; i < 9; ++i) F0[i] = V[i * 9 + lo];
+  /* rank 2: F0 <- F0 (I - v v^T), v = right singular vector of the smallest singular value */
+  double G[9], W[9];
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+    double sacc = 0;
+    for (int k = 0; k < 3; ++k) sacc += F0[k * 3 + i] * F0[k * 3 + j];
+    G[i * 3 + j] = sacc;
+  }
+  jacobi_sym(G, W, 3, 60);
+  int l3 = 0;
+  for (int i = 1; i < 3; ++i) if (G[i * 3 + i] < G[l3 * 3 + l3]) l3 = i;
+  const double v[3] = { W[0 * 3 + l3], W[1 * 3 + l3], W[2 * 3 + l3] };
+  for (int i = 0; i < 3; ++i) {
+    const double fv = F0[i * 3] * v[0] + F0[i * 3 + 1] * v[1] + F0[i * 3 + 2] * v[2];
+    for (int j = 0; j < 3; ++j) F0[i * 3 + j] -= fv * v[j];
+  }
+  /* F = T2^T F0 T1, T = [s 0 -s cx; 0 s -s cy; 0 0 1] */
+  const double T1[9] = { sc1, 0, -sc1 * cx1, 0, sc1, -sc1 * cy1, 0, 0, 1 };
+  const double T2[9] = { sc2, 0, -sc2 * cx2, 0, sc2, -sc2 * cy2, 0, 0, 1 };
+  double X[9];
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+    double sacc = 0;
+    for (int k = 0; k < 3; ++k) sacc += T2[k * 3 + i] * F0[k * 3 + j];
+    X[i * 3 + j] = sacc;
+  }
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+    double sacc = 0;
+    for (int k = 0; k < 3; ++k) sacc += X[i * 3 + k] * T1[k * 3 + j];
+    F[i * 3 + j] = sacc;
+  }
+  if (fabs(F[8]) > FLT_EPSILON) { const double inv = 1.0 / F[8]; for (int i = 0; i < 9; ++i) F[i] *= inv; }
+  return 1;
+}
+
 int orc_find_fundamental(const float* xy1, const float* xy2, int n,
                          const orc_ransac_params* prm, double* F, uint8_t* mask,
                          orc_ransac_trace* trace) {
@@ -403,7 +562,9 @@ int orc_find_fundamental(const float* xy1, const float* xy2, int n,
     int32_t idx[7];
     float s1[14], s2[14];
     double Fm[27];
-    if (!get_subset(xy1, xy2, n, &rng, 10000, idx, s1, s2)) {
+    const int got = prm->sampler == ORC_SAMPLER_PHILOX ? philox_subset(xy1, xy2, n, prm->seed, iter, idx, s1, s2)
+                                                       : get_subset(xy1, xy2, n, &rng, 10000, idx, s1, s2);
+    if (!got) {
       if (iter == 0) { free(err); free(cur); return 0; }
       break;
     }
@@ -425,6 +586,10 @@ int orc_find_fundamental(const float* xy1, const float* xy2, int n,
   tr.iters_run = iter; tr.niters_final = niters;
   if (trace) *trace = tr;
   free(err); free(cur);
+  if (best > 0 && prm->refit_8point && best >= 8) {
+    double Fr[9];
+    if (orc_eight_point(xy1, xy2, n, mask, Fr)) memcpy(F, Fr, sizeof Fr);
+  }
   return best > 0 ? 1 : 0;
 }
 

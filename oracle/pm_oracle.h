@@ -32,11 +32,18 @@ extern "C" {
 enum { ORC_UNIQUE_FIRST_WINS = 0, ORC_MUTUAL_NN = 1, ORC_UNIQUE_NONE = 2 };
 enum { ORC_RESID_SYMMETRIC_EPIPOLAR = 0, ORC_RESID_SAMPSON = 1 };
 
+enum { ORC_SAMPLER_OPENCV_MWC = 0, ORC_SAMPLER_PHILOX = 1 };
+
 typedef struct {
   double threshold;   /* pixels; OpenCV default 3.0          */
   double confidence;  /* OpenCV default 0.99                 */
   int max_iters;      /* OpenCV default 1000                 */
   int residual_mode;  /* ORC_RESID_*                         */
+  int sampler;        /* ORC_SAMPLER_*: OpenCV's fixed-seed stream (default) or the free-running Philox
+                         sampler of SURVEY App. B3 (subset of iteration k = f(seed, k), no sequential state) */
+  int refit_8point;   /* != 0: F is re-estimated from the inliers of the winning hypothesis with the
+                         normalised 8-point algorithm (the "8-point" of the north star; the mask is kept) */
+  uint64_t seed;      /* Philox key of this pair (see orc_pair_seed)                                      */
 } orc_ransac_params;
 
 typedef struct {
@@ -90,6 +97,20 @@ void orc_residuals(const double F[9], const float* xy1, const float* xy2, int n,
 int orc_update_num_iters(double p, double ep, int model_points, int max_iters);
 /* Replays the sampler: writes iters x 7 indices; returns number of subsets produced. */
 int orc_sample_subsets(const float* xy1, const float* xy2, int n, int iters, int32_t* out);
+
+/* Philox4x32-10 (Salmon et al., SC'11), the counter-based generator behind ORC_SAMPLER_PHILOX;
+ * exposed so that the published known-answer vectors pin it.  ctr is updated in place. */
+void orc_philox4x32_10(uint32_t ctr[4], uint32_t key0, uint32_t key1);
+/* Philox key of pair (i, j) under a global seed: the result of a pair must not depend on which GPU or
+ * batch ran it. */
+uint64_t orc_pair_seed(uint64_t seed, int32_t img_i, int32_t img_j);
+/* Subset of iteration `iter` under the Philox sampler (7 indices); returns 1, or 0 when no admissible
+ * subset was found in 1024 draws. */
+int orc_philox_subset(const float* xy1, const float* xy2, int n, uint64_t pair_seed, int iter, int32_t idx[7]);
+/* Normalised 8-point algorithm (Hartley) over the points with mask != 0 (mask NULL: all points), as
+ * cv::findFundamentalMat(..., FM_8POINT) computes it: per-image centroid / mean-distance scaling, 9x9
+ * normal matrix, smallest eigenvector, rank-2 enforcement, de-normalisation, F[8] = 1.  Returns 1 / 0. */
+int orc_eight_point(const float* xy1, const float* xy2, int n, const uint8_t* mask, double F[9]);
 
 /* Whole per-pair body (match -> >=7 gate -> filter -> keep inliers).
  * desc_kind: 0 = float L2 (dim floats per row), 1 = binary Hamming (dim bytes per row).

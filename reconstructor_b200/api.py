@@ -24,6 +24,9 @@ LIB_PATH = os.environ.get("PM_B200_LIB") or os.path.join(_HERE, "libpairmatch_b2
 DESC_F32, DESC_U8_BITS, DESC_U8 = 0, 1, 2
 UNIQUE_FIRST_WINS, MUTUAL_NN, UNIQUE_NONE = 0, 1, 2
 RESID_SYMMETRIC_EPIPOLAR, RESID_SAMPSON = 0, 1
+SAMPLER_OPENCV_MWC, SAMPLER_PHILOX = 0, 1
+PEAK_KIND_F16, PEAK_KIND_I8, PEAK_KIND_MXF4 = 0, 1, 2
+ALL_PAIRS = -1
 PAIR_UNFILTERED, PAIR_FILTERED, PAIR_DROPPED = 0, 1, 2
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_OOM, ERR_STATE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 
@@ -33,6 +36,7 @@ EXPORTS = [
     "pm_match_descriptors", "pm_filter_pair_F", "pm_match_filter_pair", "pm_match_all_pairs",
     "pm_free_result", "pm_get_stats", "pm_reset_stats", "pm_measure_popc_peak",
     "pm_save_images", "pm_load_images", "pm_save_result", "pm_load_result",
+    "pm_filter_pair_F_seeded", "pm_pair_seed", "pm_remove_image", "pm_measure_tensor_peak", "pm_debug_tc_dump",
 ]
 
 
@@ -41,7 +45,8 @@ class Params(C.Structure):
                 ("do_filter", C.c_int32), ("ransac_threshold", C.c_double),
                 ("ransac_confidence", C.c_double), ("ransac_max_iters", C.c_int32),
                 ("residual_mode", C.c_int32), ("sampler", C.c_int32), ("batch_pairs", C.c_int32),
-                ("reserve_keypoints", C.c_int64), ("debug_flags", C.c_int32), ("reserved", C.c_int32)]
+                ("reserve_keypoints", C.c_int64), ("debug_flags", C.c_int32), ("refit_8point", C.c_int32),
+                ("seed", C.c_uint64)]
 
 
 class PairResult(C.Structure):
@@ -107,6 +112,12 @@ def load_library() -> C.CDLL:
                                              C.c_int, C.POINTER(PairResult)]
         lib.pm_filter_pair_F.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                          C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        lib.pm_filter_pair_F_seeded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_void_p,
+                                                C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        lib.pm_pair_seed.argtypes = [C.c_uint64, C.c_int32, C.c_int32]
+        lib.pm_pair_seed.restype = C.c_uint64
+        lib.pm_remove_image.argtypes = [C.c_void_p, C.c_int]
+        lib.pm_measure_tensor_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
         lib.pm_match_all_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_int64,
                                            C.POINTER(C.POINTER(CsrResult))]
         lib.pm_free_result.argtypes = [C.POINTER(CsrResult)]
@@ -119,6 +130,11 @@ def load_library() -> C.CDLL:
         lib.pm_load_result.argtypes = [C.c_char_p, C.POINTER(C.POINTER(CsrResult))]
         _lib = lib
     return _lib
+
+
+def pair_seed(seed: int, i: int, j: int) -> int:
+    """The Philox key the batched loop derives for pair (i, j) under pm_params.seed."""
+    return int(load_library().pm_pair_seed(seed, i, j))
 
 
 def default_params() -> Params:
@@ -259,15 +275,24 @@ class PairMatcher:
         return self._pair(self.lib.pm_match_descriptors, a.ctypes.data, a.shape[0], b.ctypes.data,
                           b.shape[0], dim, dt, cap=a.shape[0])
 
-    def estimate_fundamental(self, xy1: np.ndarray, xy2: np.ndarray):
-        """GeometricFilter::estimateFundamental -> (F 3x3, mask uint8 [M], status, iters)."""
+    def estimate_fundamental(self, xy1: np.ndarray, xy2: np.ndarray, pair_key: int | None = None):
+        """GeometricFilter::estimateFundamental -> (F 3x3, mask uint8 [M], status, iters).
+        pair_key: explicit Philox key of this call (pm_filter_pair_F_seeded; only read with SAMPLER_PHILOX)."""
         p1 = np.ascontiguousarray(xy1, np.float32); p2 = np.ascontiguousarray(xy2, np.float32)
         m = p1.shape[0]
         F = np.zeros(9, np.float64); mask = np.zeros(max(m, 1), np.uint8)
         st = C.c_int32(0); it = C.c_int32(0)
-        self._check(self.lib.pm_filter_pair_F(self.h, p1.ctypes.data, p2.ctypes.data, m, F.ctypes.data,
-                                              mask.ctypes.data, C.byref(st), C.byref(it)))
+        if pair_key is None:
+            self._check(self.lib.pm_filter_pair_F(self.h, p1.ctypes.data, p2.ctypes.data, m, F.ctypes.data,
+                                                  mask.ctypes.data, C.byref(st), C.byref(it)))
+        else:
+            self._check(self.lib.pm_filter_pair_F_seeded(self.h, p1.ctypes.data, p2.ctypes.data, m, pair_key,
+                                                         F.ctypes.data, mask.ctypes.data, C.byref(st), C.byref(it)))
         return F.reshape(3, 3), mask[:m], st.value, it.value
+
+    def remove_image(self, img_id: int):
+        self._check(self.lib.pm_remove_image(self.h, img_id))
+        self._n.pop(img_id, None)
 
     # -- batched loop ----------------------------------------------------------------------------
     def match_all_pairs(self, pairs: np.ndarray | None = None, copy=True, save_to: str | None = None):
@@ -275,7 +300,7 @@ class PairMatcher:
         status, n_inliers, ransac_iters, device_ms.  save_to: also write the result cache file."""
         res = C.POINTER(CsrResult)()
         if pairs is None:
-            self._check(self.lib.pm_match_all_pairs(self.h, None, 0, C.byref(res)))
+            self._check(self.lib.pm_match_all_pairs(self.h, None, ALL_PAIRS, C.byref(res)))
         else:
             pairs = np.ascontiguousarray(pairs, np.int32)
             self._check(self.lib.pm_match_all_pairs(self.h, pairs.ctypes.data, pairs.shape[0], C.byref(res)))
@@ -309,6 +334,12 @@ class PairMatcher:
     def measure_popc_peak(self) -> float:
         v = C.c_double(0)
         self._check(self.lib.pm_measure_popc_peak(self.h, C.byref(v)))
+        return v.value
+
+    def measure_tensor_peak(self, kind: int) -> float:
+        """FLOP/s of the pure tcgen05.mma issue loop of one MMA kind (PEAK_KIND_*)."""
+        v = C.c_double(0)
+        self._check(self.lib.pm_measure_tensor_peak(self.h, kind, C.byref(v)))
         return v.value
 
 

@@ -9,10 +9,15 @@
 //
 // Per-image device cache: the reference hands over COPIES of the same vector<shared_ptr<Feature>>
 // for every pair an image takes part in (.cpp:213-214) and re-packs them every time
-// (featDescToCV, FeatureMatcher.cpp:11-25).  Here an image is packed + uploaded once, keyed by the
-// identity of its first Feature object and its size; call invalidate() if features are edited.
+// (featDescToCV, FeatureMatcher.cpp:11-25).  Here an image is packed + uploaded once.  The cache key is
+// the identity of EVERY Feature object of the vector (an order-sensitive hash of the shared_ptr targets,
+// the first and last pointer and the size): the copies the reference makes share those objects, while a
+// vector that was freed and rebuilt -- even at the same address and of the same size -- holds other objects.
+// The cache also keeps the shared_ptrs alive, so a cached address cannot be recycled under it.  Features
+// edited in place are not detected: call invalidate() (it also frees the device rows).
 #pragma once
 
+#include <atomic>
 #include <cstdint>
 #include <map>
 #include <mutex>
@@ -89,37 +94,59 @@ class CudaExhaustiveMatcher : public FeatureMatcher {
       a = resident(features1);
       b = resident(features2);
     }
-    if (a < 0 || b < 0) { last_status_ = PM_ERR_INVALID; return; }
+    if (a < 0 || b < 0) { fail(PM_ERR_INVALID); return; }
     std::vector<int32_t> q(features1.size()), t(features1.size());
     pm_pair_result r{};
     r.capacity = static_cast<int32_t>(features1.size());
     r.q = q.data(); r.t = t.data(); r.inlier = nullptr;
-    last_status_ = pm_match_pair(dev_->handle(), a, b, &r);
-    if (last_status_ != PM_OK) return;       // no exceptions inside the OpenMP region
+    const int rc = pm_match_pair(dev_->handle(), a, b, &r);
+    if (rc != PM_OK) { fail(rc); return; }    // no exceptions inside the OpenMP region
     for (int i = 0; i < r.n_matches; ++i) matches[q[i]] = t[i];
   }
 
-  void invalidate() { std::lock_guard<std::mutex> lk(mu_); cache_.clear(); }
-  int lastStatus() const { return last_status_; }
+  // Drops the cache AND the device rows behind it.
+  void invalidate() {
+    std::lock_guard<std::mutex> lk(mu_);
+    for (auto& kv : cache_) pm_remove_image(dev_->handle(), kv.second.id);
+    cache_.clear();
+  }
+  // First error any thread has seen since the last clearStatus() (PM_OK if none); the virtual call itself cannot
+  // report one (void, FeatureMatcher.h:18-22) and must not throw inside the OpenMP region.
+  int lastStatus() const { return first_error_.load(std::memory_order_acquire); }
+  void clearStatus() { first_error_.store(PM_OK, std::memory_order_release); }
   const std::shared_ptr<PairMatchDevice>& device() const { return dev_; }
 
  private:
+  void fail(int rc) {
+    int expected = PM_OK;
+    first_error_.compare_exchange_strong(expected, rc, std::memory_order_acq_rel);
+  }
+  struct Key {
+    const void *first, *last;
+    size_t n, h;
+    bool operator==(const Key& o) const { return first == o.first && last == o.last && n == o.n && h == o.h; }
+  };
+  struct KeyHash { size_t operator()(const Key& k) const { return k.h ^ (k.n * 1000003u); } };
+  struct Entry { int id; std::vector<FeaturePtr<>> keep; };
+  static Key key_of(const std::vector<FeaturePtr<>>& f) {
+    size_t h = 1469598103934665603ull;
+    for (const auto& p : f) { h ^= std::hash<const void*>{}(p.get()); h *= 1099511628211ull; }
+    return Key{f.front().get(), f.back().get(), f.size(), h};
+  }
   int resident(const std::vector<FeaturePtr<>>& f) {
-    const Key k{f[0].get(), f.size()};
+    const Key k = key_of(f);
     auto it = cache_.find(k);
-    if (it != cache_.end()) return it->second;
+    if (it != cache_.end()) return it->second.id;
     const int id = next_id_++;
     if (dev_->upload(id, f) != PM_OK) return -1;
-    cache_.emplace(k, id);
+    cache_.emplace(k, Entry{id, f});
     return id;
   }
-  using Key = std::pair<const void*, size_t>;
-  struct KeyHash { size_t operator()(const Key& k) const { return std::hash<const void*>{}(k.first) * 1000003u ^ k.second; } };
   std::shared_ptr<PairMatchDevice> dev_;
-  std::unordered_map<Key, int, KeyHash> cache_;
+  std::unordered_map<Key, Entry, KeyHash> cache_;
   std::mutex mu_;
   int next_id_ = 1 << 20;                   // away from the ids the batched loop uses
-  int last_status_ = PM_OK;
+  std::atomic<int> first_error_{PM_OK};
 };
 
 }  // namespace reconstructor::Core

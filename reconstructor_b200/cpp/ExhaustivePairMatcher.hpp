@@ -47,6 +47,7 @@ class ExhaustivePairMatcher {
                               std::find(back->second.begin(), back->second.end(), i) != back->second.end();
         if (i < j || !mirrored) { pairs.push_back(i); pairs.push_back(j); }   // canonical direction once
       }
+    if (pairs.empty()) { last_device_ms_ = 0; return PM_OK; }   // nothing to match (an empty list is NOT "all pairs")
     pm_csr_result* res = nullptr;
     const int rc = pm_match_all_pairs(dev_->handle(), pairs.data(), static_cast<int64_t>(pairs.size() / 2), &res);
     if (rc != PM_OK) return rc;

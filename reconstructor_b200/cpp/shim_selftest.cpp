@@ -92,6 +92,28 @@ int main() {
     total += m.size();
   }
   if (viaBatch.size() != static_cast<size_t>(n_img * (n_img - 1)) || total < 400) { std::printf("too few matches: %zu pairs, %zu matches\n", viaBatch.size(), total); return 1; }
+  if (matcher.lastStatus() != PM_OK) { std::printf("plugin reported status %d\n", matcher.lastStatus()); return 1; }
+
+  // (3) an empty image-match list is an empty job, not "all pairs of the handle"
+  {
+    FeatureMatchesT<> none;
+    std::unordered_map<int, std::vector<int>> noMatches;
+    if (loop.matchFeatures(features, noMatches, none) != PM_OK || !none.empty()) { std::printf("empty list ran pairs\n"); return 1; }
+  }
+  // (4) the plugin's image cache keys on the Feature objects: a rebuilt vector of the same size (same address or not)
+  //     is a new image; invalidate() frees the device rows
+  {
+    std::map<int, int> before, after, again;
+    matcher.matchFeatures(features[0], features[1], before, {0, 0}, {0, 0});
+    std::vector<FeaturePtr<>> rebuilt;                       // image 1 with the descriptors of image 2 (same size as ...)
+    for (size_t k = 0; k < features[1].size(); ++k)
+      rebuilt.push_back(std::make_shared<Feature<>>(features[1][k]->featCoord, features[2][k % features[2].size()]->featDesc));
+    matcher.matchFeatures(features[0], rebuilt, after, {0, 0}, {0, 0});
+    if (before == after) { std::printf("stale upload served for a rebuilt feature vector\n"); return 1; }
+    matcher.invalidate();
+    matcher.matchFeatures(features[0], features[1], again, {0, 0}, {0, 0});
+    if (before != again || matcher.lastStatus() != PM_OK) { std::printf("results changed after invalidate()\n"); return 1; }
+  }
   std::printf("SHIM_OK pairs=%zu matches=%zu device_ms=%.3f\n", viaBatch.size(), total, loop.lastDeviceMs());
   return 0;
 }

@@ -48,6 +48,16 @@ struct Image {
 
 constexpr int kTmpA = INT32_MIN, kTmpB = INT32_MIN + 1;
 
+inline uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+inline uint64_t pair_seed(uint64_t seed, int32_t i, int32_t j) {
+  return splitmix64(seed ^ splitmix64((static_cast<uint64_t>(static_cast<uint32_t>(i)) << 32) | static_cast<uint32_t>(j)));
+}
+
 // Pinned host buffers are expensive to create, so results recycle them through a pool that
 // outlives the handle if a result is freed late.
 struct PinnedPool {
@@ -137,6 +147,7 @@ struct Slot {
   int2 *knn_idx = nullptr, *rev_idx = nullptr;
   float2 *knn_dist = nullptr, *rev_dist = nullptr;
   float2 *knn_extra = nullptr, *rev_extra = nullptr;   // 5th / 6th candidate keys of the real-valued tensor path
+  uint8_t* rr_flag = nullptr;                           // rows l2f_rerank1_kernel left open (real-valued tensor path)
   int32_t *owner = nullptr, *match_q = nullptr, *match_t = nullptr, *count = nullptr;
   float2 *pts1 = nullptr, *pts2 = nullptr;
   uint8_t* mask = nullptr;
@@ -162,7 +173,7 @@ struct Slot {
   void release() {
     auto fd = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
     auto fh = [](auto*& p) { if (p) { cudaFreeHost(p); p = nullptr; } };
-    fd(d_jobs); fd(d_rjobs); fd(knn_idx); fd(rev_idx); fd(knn_dist); fd(rev_dist); fd(knn_extra); fd(rev_extra); fd(owner);
+    fd(d_jobs); fd(d_rjobs); fd(knn_idx); fd(rev_idx); fd(knn_dist); fd(rev_dist); fd(knn_extra); fd(rev_extra); fd(rr_flag); fd(owner);
     fd(match_q); fd(match_t); fd(count); fd(pts1); fd(pts2); fd(mask); fd(F); fd(status);
     fd(n_inl); fd(iters); fd(offsets); fd(out_q); fd(out_t); fd(out_mask);
     fh(h_jobs); fh(h_rjobs); fh(h_offsets); fh(h_q); fh(h_t); fh(h_status); fh(h_ninl);
@@ -214,8 +225,11 @@ struct DeviceCtx {
   uint8_t *hq4 = nullptr, *ht4 = nullptr;   // [rows][160] E2M1 forms of 256-bit rows (kind::mxf4 two-set kernel)
   TcMaps h4maps{};                           // train boxes of 96 rows (192-column tiles)
   bool tch4_ready = false;
-  bool result_by_ce = true;                  // PM_RESULT_COPY=kernel: compacted matches leave by copy kernels too (development)
-  bool trace_on = false;                     // PM_TRACE: host-side timeline of run_pairs (development)
+  // development switches, read from the environment ONCE in init() (never in the batch loop):
+  bool result_by_ce = true;                  // PM_RESULT_COPY=kernel: compacted matches leave by copy kernels too
+  bool trace_on = false;                     // PM_TRACE: device + host timeline of run_pairs
+  int opt_slots = 0;                         // PM_SLOTS: batches in flight (0 = default)
+  bool opt_prefilter = false;                // PM_L2F_PREFILTER: s8-prefilter variant of the re-rank
   std::chrono::steady_clock::time_point trace_t0{};
   unsigned int* d_fstats = nullptr;   // pack_float statistics of the image being ingested
   unsigned int* h_fstats = nullptr;   // pinned
@@ -237,6 +251,54 @@ struct DeviceCtx {
   size_t stage_bytes = 0;
 
   std::unordered_map<int, Image> images;
+  // released row ranges (pm_remove_image, images re-set with more keypoints), kept sorted by row and coalesced; a new
+  // image takes the smallest range that fits before the arena is bumped
+  std::vector<std::pair<int32_t, int32_t>> free_rows;   // (first row, rows)
+  void release_rows(int32_t row, int32_t cap) {
+    if (cap <= 0) return;
+    if (static_cast<int64_t>(row) + cap == used_rows) { used_rows = row; }      // the arena's tail: just step back
+    else free_rows.emplace_back(row, cap);
+    std::sort(free_rows.begin(), free_rows.end());
+    for (size_t k = 0; k + 1 < free_rows.size();) {
+      if (free_rows[k].first + free_rows[k].second == free_rows[k + 1].first) {
+        free_rows[k].second += free_rows[k + 1].second;
+        free_rows.erase(free_rows.begin() + k + 1);
+      } else ++k;
+    }
+    while (!free_rows.empty() && static_cast<int64_t>(free_rows.back().first) + free_rows.back().second == used_rows) {
+      used_rows = free_rows.back().first;
+      free_rows.pop_back();
+    }
+  }
+  bool take_rows(int32_t n, int32_t* row, int32_t* cap) {
+    size_t best = free_rows.size();
+    for (size_t k = 0; k < free_rows.size(); ++k)
+      if (free_rows[k].second >= n && (best == free_rows.size() || free_rows[k].second < free_rows[best].second)) best = k;
+    if (best == free_rows.size()) return false;
+    *row = free_rows[best].first;
+    // a much larger range is split, the remainder stays free
+    if (free_rows[best].second >= 2 * n && free_rows[best].second - n >= 256) {
+      *cap = n;
+      free_rows[best].first += n;
+      free_rows[best].second -= n;
+    } else {
+      *cap = free_rows[best].second;
+      free_rows.erase(free_rows.begin() + best);
+    }
+    return true;
+  }
+  int remove_image(int id) {
+    auto it = images.find(id);
+    if (it == images.end()) return fail(PM_ERR_STATE, "image id %d not set", id);
+    PM_CUDA(cudaSetDevice(dev));
+    // queued work may still read the rows: drain before they can be handed to another image
+    PM_CUDA(cudaDeviceSynchronize());
+    if (it->second.ready) cudaEventDestroy(it->second.ready);
+    release_rows(it->second.row, it->second.cap);
+    images.erase(it);
+    stats.n_images = static_cast<int32_t>(images.size());
+    return PM_OK;
+  }
   std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
   std::vector<Slot> slots;
   Slot single;
@@ -270,6 +332,10 @@ struct DeviceCtx {
       return fail(PM_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dev,
                   prop.major, prop.minor);
     num_sms = prop.multiProcessorCount;
+    trace_on = std::getenv("PM_TRACE") != nullptr;
+    if (const char* e = std::getenv("PM_SLOTS")) opt_slots = std::max(1, std::min(32, std::atoi(e)));
+    { const char* e = std::getenv("PM_RESULT_COPY"); result_by_ce = !(e && std::strcmp(e, "kernel") == 0); }
+    opt_prefilter = std::getenv("PM_L2F_PREFILTER") != nullptr;
     PM_CUDA(cudaStreamCreateWithFlags(&ingest, cudaStreamNonBlocking));
     {
       // the persistent kNN kernels go first whenever SMs free up; the small tail kernels of earlier batches
@@ -556,11 +622,22 @@ struct DeviceCtx {
     if (im.pending) { const int rc = resolve(im); if (rc != PM_OK) return rc; }
     if (async && (n == 0 || next_rec >= kRecCap || (dtype == PM_DESC_U8 && dim != TC_DIM))) async = false;
     if (n > im.cap) {
-      const int rc = ensure_rows(used_rows + n);
-      if (rc != PM_OK) { if (im.cap == 0) images.erase(id); return rc; }
-      im.row = static_cast<int32_t>(used_rows);
-      im.cap = n;
-      used_rows += n;
+      if (im.cap > 0) {
+        // the old rows may still be read by queued work (per-pair calls are synchronous, so only after async ingest)
+        PM_CUDA(cudaStreamSynchronize(ingest));
+        release_rows(im.row, im.cap);
+        im.cap = 0;
+      }
+      int32_t row = 0, cap = 0;
+      if (take_rows(n, &row, &cap)) {
+        im.row = row; im.cap = cap;
+      } else {
+        const int rc = ensure_rows(used_rows + n);
+        if (rc != PM_OK) { images.erase(id); return rc; }
+        im.row = static_cast<int32_t>(used_rows);
+        im.cap = n;
+        used_rows += n;
+      }
     }
     im.n = n;
     im.has_xy = xy_ != nullptr;
@@ -700,6 +777,7 @@ struct DeviceCtx {
     PM_CUDA(cudaMalloc(&s.knn_idx, sizeof(int2) * ps));
     PM_CUDA(cudaMalloc(&s.knn_dist, sizeof(float2) * ps));
     if (float_tc_shape()) PM_CUDA(cudaMalloc(&s.knn_extra, sizeof(float2) * ps));
+    if (float_tc_shape()) PM_CUDA(cudaMalloc(&s.rr_flag, ps));
     if (mutual) {
       PM_CUDA(cudaMalloc(&s.rev_idx, sizeof(int2) * ps));
       PM_CUDA(cudaMalloc(&s.rev_dist, sizeof(float2) * ps));
@@ -733,7 +811,10 @@ struct DeviceCtx {
   }
 
   RansacDev ransac_dev(bool do_filter) const {
-    RansacDev r;
+    RansacDev r{};
+    r.sampler = prm.sampler;
+    r.refit_8point = prm.refit_8point;
+    r.seed = prm.seed;
     r.confidence = prm.ransac_confidence;
     r.thr = static_cast<float>(prm.ransac_threshold * prm.ransac_threshold);
     r.max_iters = prm.ransac_max_iters;
@@ -753,7 +834,7 @@ struct DeviceCtx {
       max_nt = std::max(max_nt, s.h_jobs[i].nt);
       work += static_cast<double>(s.h_jobs[i].nq) * s.h_jobs[i].nt;
       s.h_rjobs[i] = PairJob{s.h_jobs[i].t_row, s.h_jobs[i].q_row, s.h_jobs[i].nt, s.h_jobs[i].nq,
-                             s.h_jobs[i].t_maxn, s.h_jobs[i].q_maxn};
+                             s.h_jobs[i].t_maxn, s.h_jobs[i].q_maxn, s.h_jobs[i].seed_lo, s.h_jobs[i].seed_hi};
     }
     // by a kernel, not the copy engine: an H2D copy would wait behind every image upload still queued there
     PM_CUDA(launch_copy_pinned(s.h_jobs, s.d_jobs, sizeof(PairJob) * n, s.stream));
@@ -790,6 +871,9 @@ struct DeviceCtx {
     //   bit18     256-bit rows: kind::i8 two-set kernel (byte forms) instead of the kind::mxf4 kernels (E2M1 forms)
     //   bit15     real-valued rows: fp16 forms (kind::f16) in the batched loop instead of the s8 forms (kind::i8)
     //   bit14     kind::i8: one query row set per cluster (l2_top2_tc2_kernel) instead of two (l2_i8x2_kernel)
+    //   bit19     real-valued rows, s8 forms: one query row set per cluster instead of two (six chunk keys + chunk re-rank)
+    //   bit20     real-valued rows, s8 forms: two row sets, six chunk keys + chunk re-rank (instead of the argmin epilogue
+    //             + one-column re-rank, the default)
     const int code = (prm.debug_flags >> 2) & 7;
     const int fcode = (prm.debug_flags >> 7) & 3;
     const int variant = ((prm.debug_flags >> 1) & 1) ^ 1;
@@ -805,6 +889,9 @@ struct DeviceCtx {
     // ... with the rows quantised to s8 on kind::i8 (half the K-steps) when only the outcome of the ratio test and
     // the nearest index of passing rows are needed (batched loop without the cross-check); debug bit15 keeps fp16
     const bool use_tcs8 = use_tcf && tcs_ready && all_s8 && fast && !want_rev && !((prm.debug_flags >> 15) & 1);
+    // ... and the epilogue reporting the exact argmin column + the second smallest score (one exact column per
+    // candidate row in l2f_rerank1 instead of a 16-column chunk); 13 column bits: train images of <= 8192 rows
+    const bool use_keys3 = use_tcs8 && max_nt <= L2S8_KEYS3_MAX_NT && !((prm.debug_flags >> 19) & 1) && !((prm.debug_flags >> 20) & 1);
     const int epi_of_code[5] = {3, 0, 1, 2, 4};
     // binary rows: Hamming = |a| + |b| - 2 a.b on the tensor cores (E4M3 {0,1} operands) in the batched loop;
     // debug_flags bit10 keeps the XOR/popc kernel there too (it always serves raw kNN rows / single pairs)
@@ -826,7 +913,11 @@ struct DeviceCtx {
       if (use_tch) return launch_ham_tc2(hmaps, words, qnorm, jobs_d, n, mq, oi, od, s.stride, num_sms, knn_stream);
       if (dtype == PM_DESC_U8_BITS)
         return launch_hamming_top2(bits, words, jobs_d, n, mq, oi, od, s.stride, variant, knn_stream);
-      if (use_tcs8) return launch_l2s8_tc2(smaps, dim, jobs_d, n, mq, oi, od, ox, s.stride, num_sms, knn_stream);
+      if (use_tcs8) {
+        if ((prm.debug_flags >> 19) & 1)
+          return launch_l2s8_tc2(smaps, dim, jobs_d, n, mq, oi, od, ox, s.stride, num_sms, knn_stream);
+        return launch_l2s8x2(smaps, dim, jobs_d, n, mq, oi, od, ox, s.stride, num_sms, knn_stream, use_keys3 ? 1 : 0);
+      }
       if (use_tcf) return launch_l2f_tc2(fmaps, dim, jobs_d, n, mq, oi, od, ox, s.stride, num_sms, knn_stream);
       if (!use_tc) return launch_l2_simt(raw, dim, jobs_d, n, mq, oi, od, s.stride, knn_stream);
       if (use_i8) {
@@ -891,10 +982,14 @@ struct DeviceCtx {
         ++stats.kernel_launches;
       }
     }
-    if (use_tcf) {
+    if (use_keys3) {
+      PM_CUDA(launch_l2f_rerank1(raw, fnorm, dim, s.d_jobs, n, max_nq, s.knn_idx, s.knn_dist, s.knn_extra, s.rr_flag, s.stride,
+                                 prm.ratio, d_l2f, sq8, st8, s.stream));
+      stats.kernel_launches += 2;
+    } else if (use_tcf) {
       PM_CUDA(launch_l2f_fixup(raw, fnorm, dim, s.d_jobs, n, max_nq, s.knn_idx, s.knn_dist, s.knn_extra, s.stride,
                                prm.ratio, fast ? L2F_NEED_RATIO : L2F_NEED_FULL, d_l2f, s.stream, use_tcs8 ? 1 : 0,
-                               use_tcs8 ? sq8 : nullptr, use_tcs8 ? st8 : nullptr));
+                               use_tcs8 && opt_prefilter ? sq8 : nullptr, use_tcs8 && opt_prefilter ? st8 : nullptr));
       ++stats.kernel_launches;
       if (want_rev) {
         PM_CUDA(launch_l2f_fixup(raw, fnorm, dim, s.d_rjobs, n, max_nt, s.rev_idx, s.rev_dist, s.rev_extra, s.stride,
@@ -919,7 +1014,11 @@ struct DeviceCtx {
       if (rc == PM_OK) rc = resolve(b->second);
       if (rc != PM_OK) return rc;
     }
-    s.h_jobs[k] = PairJob{a->second.row, b->second.row, a->second.n, b->second.n, a->second.maxn, b->second.maxn};
+    // Philox key of the pair: a function of (params.seed, image ids) only, so a pair's result does not depend on the
+    // batch, the device or the rank that ran it; the CPU filter of the parity tests mixes the same way
+    const uint64_t ps = pair_seed(prm.seed, i, j);
+    s.h_jobs[k] = PairJob{a->second.row, b->second.row, a->second.n, b->second.n, a->second.maxn, b->second.maxn,
+                          static_cast<uint32_t>(ps), static_cast<uint32_t>(ps >> 32)};
     if (static_cast<int>(job_integral.size()) <= k) { job_integral.resize(k + 1); job_unit.resize(k + 1); job_i8.resize(k + 1); job_s8.resize(k + 1); }
     // an empty image is compatible with every path (its pairs have no rows to search)
     const Image &ia = a->second, &ib = b->second;
@@ -944,7 +1043,8 @@ struct DeviceCtx {
                           s.count, s.stream));
     if (trace_on && s.ev_tr[1]) PM_CUDA(cudaEventRecord(s.ev_tr[1], s.stream));
     PM_CUDA(launch_ransac(s.pts1, s.pts2, s.count, n, s.stride, ransac_dev(do_filter), s.mask, s.F,
-                          s.status, s.n_inl, s.iters, s.stream));
+                          s.status, s.n_inl, s.iters, s.stream, s.d_jobs));
+    if (prm.refit_8point && do_filter) ++stats.kernel_launches;
     if (trace_on && s.ev_tr[2]) PM_CUDA(cudaEventRecord(s.ev_tr[2], s.stream));
     PM_CUDA(launch_compact(s.count, n, s.stride, s.match_q, s.match_t, s.mask, s.offsets, s.out_q,
                            s.out_t, s.out_mask, s.stream));
@@ -995,7 +1095,7 @@ struct DeviceCtx {
       float ms = 0;
       PM_CUDA(cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
       stats.knn_ms += ms;
-      if (std::getenv("PM_TRACE")) {      // development: timeline of the batch relative to the call's first event
+      if (trace_on) {                     // development: timeline of the batch relative to the call's first event
         float t0 = 0, t1 = 0, t2 = 0;
         cudaEventElapsedTime(&t0, ev_a, s.ev_k0); cudaEventElapsedTime(&t1, ev_a, s.ev_k1);
         cudaEventElapsedTime(&t2, ev_a, s.ev_done);
@@ -1023,10 +1123,33 @@ struct DeviceCtx {
   }
 
   // pairs: [n][2]; results appended at R positions [first, first+n)
+  // Error exits of run_pairs: nothing of the failed call may stay in flight (its Result -- the target of queued D2H
+  // copies -- is about to be destroyed, and a later call must not find slots that still look busy).
+  void abandon_batches() {
+    if (knn_stream) (void)cudaStreamSynchronize(knn_stream);
+    for (auto& s : slots) {
+      if (s.stream) (void)cudaStreamSynchronize(s.stream);
+      s.busy = false;
+    }
+    (void)cudaGetLastError();
+  }
+
   int run_pairs(const int32_t* pairs, int64_t n_pairs, int64_t first, Result& R, double* device_ms) {
+    const int rc = run_pairs_impl(pairs, n_pairs, first, R, device_ms);
+    if (rc != PM_OK) abandon_batches();
+    return rc;
+  }
+
+  int run_pairs_impl(const int32_t* pairs, int64_t n_pairs, int64_t first, Result& R, double* device_ms) {
     PM_CUDA(cudaSetDevice(dev));
     if (n_pairs == 0) return PM_OK;
     if (dtype < 0) return fail(PM_ERR_STATE, "no images set");
+    for (auto& s : slots) s.busy = false;              // (a failed earlier call drained them in abandon_batches)
+    // every image id is checked before the first batch is queued: an unknown id at pair 10,000 must not fail the call
+    // with batches in flight
+    for (int64_t k = 0; k < 2 * n_pairs; ++k)
+      if (images.find(pairs[k]) == images.end())
+        return fail(PM_ERR_STATE, "image id %d not set (pair %lld)", pairs[k], static_cast<long long>(k / 2));
     const int maxn = std::max(max_keypoints(), 1);
     const int stride = (maxn + 255) / 256 * 256;
     int B = prm.batch_pairs > 0 ? prm.batch_pairs : static_cast<int>(std::clamp<int64_t>((2 << 20) / stride, 32, 2048));
@@ -1034,8 +1157,7 @@ struct DeviceCtx {
     // batches in flight: the kNN kernels run back to back on their own stream, up to S batches ahead of the tails
     // (measured: 8 or 16 instead of 4 changes nothing -- where the tails cannot be co-resident at a useful occupancy
     // they are throughput-bound, not latency-bound, once they get the machine).  PM_SLOTS overrides (development).
-    int S = n_pairs > B ? 4 : 1;
-    if (const char* e = std::getenv("PM_SLOTS")) S = n_pairs > B ? std::max(1, std::min(32, std::atoi(e))) : 1;
+    const int S = n_pairs > B ? (opt_slots > 0 ? opt_slots : 4) : 1;
     const bool mutual = prm.unique_mode == PM_MUTUAL_NN;
     if (static_cast<int>(slots.size()) < S) slots.resize(S);
     for (int s = 0; s < S; ++s) {
@@ -1045,11 +1167,9 @@ struct DeviceCtx {
     if (!R.reserve(R.size + std::max<int64_t>(1024, n_pairs * static_cast<int64_t>(stride) * 3 / 10)))
       return fail(PM_ERR_OOM, "pinned result buffers");
     PM_CUDA(cudaEventRecord(ev_a, knn_stream));
-    const bool trace_host = std::getenv("PM_TRACE") != nullptr;
+    const bool trace_host = trace_on;
     const auto t_host0 = std::chrono::steady_clock::now();
-    trace_on = trace_host;
     trace_t0 = t_host0;
-    { const char* e = std::getenv("PM_RESULT_COPY"); result_by_ce = !(e && std::strcmp(e, "kernel") == 0); }
     int64_t done = 0;
     int b = 0;
     // results must be appended in pair order: retrieve slots in issue order
@@ -1146,7 +1266,7 @@ int pm_create(const pm_params* p, const int* device_ids, int n_dev, pm_handle* o
   *out = nullptr;
   pm_params prm;
   if (p) prm = *p; else pm_default_params(&prm);
-  if (prm.sampler != PM_SAMPLER_OPENCV_MWC) { g_create_error = "unknown sampler"; return PM_ERR_UNSUPPORTED; }
+  if (prm.sampler != PM_SAMPLER_OPENCV_MWC && prm.sampler != PM_SAMPLER_PHILOX) { g_create_error = "unknown sampler"; return PM_ERR_UNSUPPORTED; }
   if (prm.unique_mode < 0 || prm.unique_mode > 2 || prm.residual_mode < 0 || prm.residual_mode > 1 ||
       !(prm.ratio > 0.f) || prm.ransac_max_iters < 1 || prm.min_matches < 0) {
     g_create_error = "pm_create: invalid parameters";
@@ -1172,10 +1292,19 @@ int pm_create(const pm_params* p, const int* device_ids, int n_dev, pm_handle* o
   auto ctx = std::make_unique<pm_context>();
   ctx->prm = prm;
   for (int id : ids) {
-    if (id < 0 || id >= count) { g_create_error = "pm_create: bad device id"; return PM_ERR_INVALID; }
+    if (id < 0 || id >= count) {
+      g_create_error = "pm_create: bad device id";
+      for (auto& e2 : ctx->devs) e2->shutdown();
+      return PM_ERR_INVALID;
+    }
     auto d = std::make_unique<DeviceCtx>();
     const int rc = d->init(id, prm);
-    if (rc != PM_OK) { g_create_error = d->err; d->shutdown(); return rc; }
+    if (rc != PM_OK) {
+      g_create_error = d->err;
+      d->shutdown();
+      for (auto& e2 : ctx->devs) e2->shutdown();       // the devices initialised before this one
+      return rc;
+    }
     ctx->devs.push_back(std::move(d));
   }
   *out = ctx.release();
@@ -1262,6 +1391,17 @@ int pm_num_keypoints(pm_handle h, int img_id) {
   auto& im = h->devs[0]->images;
   auto it = im.find(img_id);
   return it == im.end() ? PM_ERR_STATE : it->second.n;
+}
+
+int pm_remove_image(pm_handle h, int img_id) {
+  if (!h) return PM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (img_id == kTmpA || img_id == kTmpB) return h->fail(PM_ERR_INVALID, "reserved image id");
+  for (auto& d : h->devs) {
+    const int rc = d->remove_image(img_id);
+    if (rc != PM_OK) return h->from(*d, rc);
+  }
+  return PM_OK;
 }
 
 static int knn_single(pm_context* h, DeviceCtx& d, int i, int j, int32_t* idx, float* dist, float* dump) {
@@ -1357,8 +1497,24 @@ int pm_match_descriptors(pm_handle h, const void* desc1, int n1, const void* des
   return pair_single(h, d, kTmpA, kTmpB, false, out);
 }
 
+uint64_t pm_pair_seed(uint64_t seed, int32_t img_i, int32_t img_j) { return pair_seed(seed, img_i, img_j); }
+
+static int filter_pair_F(pm_handle h, const float* xy1, const float* xy2, int M, uint64_t key, double F[9], uint8_t* mask,
+                         int32_t* status, int32_t* iters);
+
 int pm_filter_pair_F(pm_handle h, const float* xy1, const float* xy2, int M, double F[9], uint8_t* mask,
                      int32_t* status, int32_t* iters) {
+  if (!h) return PM_ERR_INVALID;
+  return filter_pair_F(h, xy1, xy2, M, h->prm.seed, F, mask, status, iters);
+}
+
+int pm_filter_pair_F_seeded(pm_handle h, const float* xy1, const float* xy2, int M, uint64_t pair_key, double F[9],
+                            uint8_t* mask, int32_t* status, int32_t* iters) {
+  return filter_pair_F(h, xy1, xy2, M, pair_key, F, mask, status, iters);
+}
+
+static int filter_pair_F(pm_handle h, const float* xy1, const float* xy2, int M, uint64_t key, double F[9], uint8_t* mask,
+                         int32_t* status, int32_t* iters) {
   if (!h || M < 0 || (M > 0 && (!xy1 || !xy2 || !mask)) || !F) return PM_ERR_INVALID;
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceCtx& d = *h->devs[0];
@@ -1375,6 +1531,7 @@ int pm_filter_pair_F(pm_handle h, const float* xy1, const float* xy2, int M, dou
     if ((rc = ck(cudaMemcpyAsync(s.pts2, xy2, 8ull * M, cudaMemcpyHostToDevice, s.stream), "pts2 H2D"))) return rc;
   }
   RansacDev rp = d.ransac_dev(true);
+  rp.seed = key;
   rp.min_matches = 7;   // estimateFundamental itself has no gate; < 7 points cannot be solved
   if ((rc = ck(launch_ransac(s.pts1, s.pts2, s.count, 1, s.stride, rp, s.mask, s.F, s.status, s.n_inl, s.iters,
                              s.stream), "ransac launch"))) return rc;
@@ -1401,7 +1558,10 @@ int pm_match_all_pairs(pm_handle h, const int32_t* pairs, int64_t n_pairs, pm_cs
   std::lock_guard<std::mutex> lk(h->mu);
   auto R = std::make_unique<Result>();
   R->pool = h->devs[0]->pool;
-  if (!pairs) {   // all i < j over the images set so far: the FakeImgMatcher pair list (ImageMatcher.cpp:6-24)
+  if (n_pairs == 0 || (!pairs && n_pairs != PM_ALL_PAIRS)) {
+    if (n_pairs != 0) return h->fail(PM_ERR_INVALID, "pairs is NULL: pass n_pairs = PM_ALL_PAIRS for the implicit all-pairs list");
+    n_pairs = 0;                                          // an empty list is an empty result, not "all pairs"
+  } else if (!pairs) {   // all i < j over the images set so far: the FakeImgMatcher pair list (ImageMatcher.cpp:6-24)
     std::vector<int> ids;
     for (auto& kv : h->devs[0]->images)
       if (kv.first != kTmpA && kv.first != kTmpB) ids.push_back(kv.first);
@@ -1547,6 +1707,29 @@ int pm_measure_popc_peak(pm_handle h, double* popc32_per_s) {
   }
   cudaFree(buf);
   *popc32_per_s = best;
+  return PM_OK;
+}
+
+int pm_measure_tensor_peak(pm_handle h, int kind, double* flop_per_s) {
+  if (!h || !flop_per_s || kind < 0 || kind > 2) return PM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceCtx& d = *h->devs[0];
+  cudaSetDevice(d.dev);
+  const int iters = 20000;        // x 4 instructions of 128 tensor-pipe cycles each: a few ms per launch
+  double best = 0;
+  for (int rep = 0; rep < 6; ++rep) {
+    double flop = 0;
+    cudaEventRecord(d.ev_a, d.ingest);
+    const cudaError_t e = launch_tensor_peak(kind, iters, d.num_sms, &flop, d.ingest);
+    cudaEventRecord(d.ev_b, d.ingest);
+    if (e != cudaSuccess || cudaEventSynchronize(d.ev_b) != cudaSuccess)
+      return h->from(d, d.fail(PM_ERR_CUDA, "tensor peak kernel failed: %s", cudaGetErrorString(cudaGetLastError())));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, d.ev_a, d.ev_b);
+    ++d.stats.kernel_launches;
+    if (rep > 0) best = std::max(best, flop / (ms * 1e-3));
+  }
+  *flop_per_s = best;
   return PM_OK;
 }
 
@@ -1729,6 +1912,13 @@ int pm_save_images(pm_handle h, const char* path) {
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceCtx& d = *h->devs[0];
   if (cudaSetDevice(d.dev) != cudaSuccess) return h->from(d, d.fail(PM_ERR_CUDA, "cudaSetDevice failed"));
+  // asynchronously ingested images must be resident before the arenas are read (the blocking copies below run on the
+  // legacy stream, which does not order against the non-blocking ingest stream)
+  {
+    const int rc = d.resolve_all();
+    if (rc != PM_OK) return h->from(d, rc);
+    if (cudaStreamSynchronize(d.ingest) != cudaSuccess) return h->from(d, d.fail(PM_ERR_CUDA, "ingest stream failed"));
+  }
   std::vector<int> ids;
   for (auto& kv : d.images)
     if (kv.first != kTmpA && kv.first != kTmpB) ids.push_back(kv.first);

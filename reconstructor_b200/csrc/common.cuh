@@ -14,6 +14,8 @@ struct PairJob {
   int32_t nt;
   float q_maxn;      // largest squared row norm of the query / train image (real-valued tensor path)
   float t_maxn;
+  uint32_t seed_lo;  // Philox key of the pair's hypothesis sampler (PM_SAMPLER_PHILOX): f(params.seed, img_i, img_j)
+  uint32_t seed_hi;
 };
 
 // Outputs of the kNN kernels, [batch slot][stride] rows:

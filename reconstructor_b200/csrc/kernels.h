@@ -17,6 +17,9 @@ struct RansacDev {
   int residual_mode;
   int min_matches;
   int do_filter;
+  int sampler;          // PM_SAMPLER_*
+  int refit_8point;     // re-estimate F from the inliers of the winner (normalised 8-point)
+  unsigned long long seed;   // Philox key when no per-pair jobs are given (pm_filter_pair_F_seeded)
 };
 
 // K1 -- hamming.cu
@@ -98,6 +101,12 @@ static constexpr float L2S8_MAX_ABS = 0.5f;
 cudaError_t s8_configure();
 cudaError_t launch_l2s8_tc2(const TcMaps& maps, int dim, const PairJob* jobs, int n_jobs, int max_nq, int2* idx,
                             float2* dist, float2* extra, int stride, int num_sms, cudaStream_t st);
+// ... with two query row sets per cluster (l2_i8x2_kernel MODE 3): half the L2 traffic; the batched loop's default
+// keys3 = 1 (default of the batched loop, needs nt <= L2S8_KEYS3_MAX_NT): per row (argmin key, 2nd, 3rd chunk key, second
+// smallest score of the argmin's chunk) for l2f_rerank1; keys3 = 0: six chunk keys for l2f_fixup (MODE 3)
+static constexpr int L2S8_KEYS3_MAX_NT = 8192;
+cudaError_t launch_l2s8x2(const TcMaps& maps, int dim, const PairJob* jobs, int n_jobs, int max_nq, int2* idx,
+                          float2* dist, float2* extra, int stride, int num_sms, cudaStream_t st, int keys3);
 // exact fp32 re-rank of the candidate chunks (l2f_fixup.cu).  need: 0 = rows that can pass the ratio test
 // (exact nearest index + exact test outcome), 1 = exact nearest index of every row, 2 = exact DMatch rows
 enum { L2F_NEED_RATIO = 0, L2F_NEED_NEAREST = 1, L2F_NEED_FULL = 2 };
@@ -107,6 +116,12 @@ cudaError_t launch_l2f_fixup(const float* raw, const float* fnorm, int dim, cons
                              int max_nq, int2* idx, float2* dist, const float2* extra, int stride, float ratio,
                              int need, unsigned long long* counters, cudaStream_t st, int e_mode = 0,
                              const uint8_t* q8 = nullptr, const uint8_t* t8 = nullptr);
+
+// the re-rank behind launch_l2s8x2(keys3 = 1): one exact column per candidate row (l2f_rerank1_kernel), then the
+// small-footprint l2f_fixup variant over the rows it left open.  flags: one byte per row of the batch (scratch).
+cudaError_t launch_l2f_rerank1(const float* raw, const float* fnorm, int dim, const PairJob* jobs, int n_jobs, int max_nq,
+                               int2* idx, float2* dist, float2* extra, uint8_t* flags, int stride, float ratio,
+                               unsigned long long* counters, const uint8_t* q8, const uint8_t* t8, cudaStream_t st);
 
 // shared-memory carve-out of the small tail kernels = the tensor kernel's, so that they can be co-resident
 cudaError_t fixup_configure();
@@ -137,9 +152,14 @@ cudaError_t launch_compact(const int32_t* count, int n_jobs, int stride, const i
                            int32_t* out_q, int32_t* out_t, uint8_t* out_mask, cudaStream_t st);
 
 // K5/K6 -- ransac.cu
+// jobs: per-pair Philox keys (PairJob::seed_lo/hi) of the batched loop, or nullptr (prm.seed is the key)
 cudaError_t launch_ransac(const float2* pts1, const float2* pts2, const int32_t* count, int n_jobs,
                           int stride, const RansacDev& prm, uint8_t* mask, double* F,
-                          int32_t* status, int32_t* n_inliers, int32_t* iters, cudaStream_t st);
+                          int32_t* status, int32_t* n_inliers, int32_t* iters, cudaStream_t st,
+                          const PairJob* jobs = nullptr);
+
+// tensor-pipe peak micro-benchmark (l2_tc2.cu, tensor_peak_kernel): kind 0 f16, 1 i8, 2 mxf4
+cudaError_t launch_tensor_peak(int kind, int iters, int num_sms, double* flop_per_launch, cudaStream_t st);
 
 // pinned host memory <-> device memory by a kernel (zero-copy), keeping the batched loop off the copy engines' queues
 cudaError_t launch_copy_pinned(const void* pinned_src, void* dst, size_t bytes, cudaStream_t st);

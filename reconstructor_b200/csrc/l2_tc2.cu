@@ -82,10 +82,46 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void wait_trap(uint64_t* bar, uint32_t parity) {
-  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
-    if (spin > (1u << 26)) __trap();
+// Waiting on an mbarrier WITHOUT burning issue slots.  The persistent kernels below share their SMs with the small tail
+// kernels of earlier batches (api.cu); a warp that polls in a tight loop is always eligible, and measured next to the
+// candidate-key kernels (whose epilogue warps wait for the tensor pipe ~45 % of the time) every co-resident kernel ran
+// 6-40x slower than alone.  So a failed poll puts the warp to sleep for NS nanoseconds (role-specific: the MMA issuer
+// sleeps least, it is on the critical path).  A wait that lasts longer than PM_WAIT_TIMEOUT_S seconds of %globaltimer
+// (a lost arrival: a bug, not load -- profilers and sanitizers stretch a wait by orders of magnitude less) traps
+// instead of hanging the device.
+#ifndef PM_WAIT_NS_EPI
+#define PM_WAIT_NS_EPI 96
+#endif
+#ifndef PM_WAIT_NS_MMA
+#define PM_WAIT_NS_MMA 24
+#endif
+#ifndef PM_WAIT_NS_TMA
+#define PM_WAIT_NS_TMA 96
+#endif
+#ifndef PM_WAIT_TIMEOUT_S
+#define PM_WAIT_TIMEOUT_S 20
+#endif
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
+template <int NS>
+__device__ __forceinline__ void wait_sleep(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  unsigned long long t0 = 0;
+  for (uint32_t spin = 1; !mbar_try_wait(bar, parity); ++spin) {
+    if (NS > 0) __nanosleep(NS);
+    if ((spin & 0xFFFu) == 0) {
+      const unsigned long long t = globaltimer_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > static_cast<unsigned long long>(PM_WAIT_TIMEOUT_S) * 1000000000ull) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void wait_epi(uint64_t* bar, uint32_t parity) { wait_sleep<PM_WAIT_NS_EPI>(bar, parity); }
+__device__ __forceinline__ void wait_mma(uint64_t* bar, uint32_t parity) { wait_sleep<PM_WAIT_NS_MMA>(bar, parity); }
+__device__ __forceinline__ void wait_tma(uint64_t* bar, uint32_t parity) { wait_sleep<PM_WAIT_NS_TMA>(bar, parity); }
 // TMA load whose completion bytes land on the leader CTA's mbarrier.
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar) {
   asm volatile(
@@ -362,6 +398,97 @@ __device__ __forceinline__ void keysi_chunk16(Keys6i& s, const uint32_t* r, int 
   const int cm = min(__vimin3_s32(a0, a1, a2), __vimin3_s32(a3, a4, static_cast<int>(r[15])));
   keysi_insert(s, (cm << 10) | (col >> 4));
 }
+// 32 columns starting at column c of the train image, of which the first `lim` exist (two 16-column chunks)
+__device__ __forceinline__ void keysi_chunk32(Keys6i& s, uint32_t (&v)[32], int c, int lim) {
+  if (lim < 32) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e)
+      if (e >= lim) v[e] = static_cast<uint32_t>(T2I_INF);
+  }
+  if (lim > 0) keysi_chunk16(s, v, c);
+  if (lim > 16) keysi_chunk16(s, v + 16, c + 16);
+}
+// ---- MODE 4 (quantised real-valued rows, the batched loop's default): exact argmin + second-smallest score -------
+// MODE 3 hands the re-rank a 16-column CHUNK per candidate row, and the re-rank has to evaluate all of it in fp32: a
+// latency-bound kernel that does not fit next to this persistent kernel at a useful occupancy (measured: the step cost
+// tensor kernel + tails).  Here the epilogue does the bookkeeping instead:
+//   * keys are (acc << 13) | column; the three smallest CHUNK keys k1 < k2 < k3 are kept branch-free (VIMNMX3 tree over
+//     the 16 accumulators + 5 min/max), with the chunk's base column in the low bits -- cheaper than MODE 3's six keys;
+//   * only when a chunk becomes the new row minimum AND its score is match-like (key < thresh: d^2 below ~0.9 for a
+//     unit-norm query -- a few times per row, a few percent of the chunks per warp) the chunk is REFINED on the spot:
+//     the column of its minimum goes into the key and the second smallest accumulator of the chunk into w2.  At the end
+//     min(w2, k2 >> 13) is the second smallest approximate score of the whole row, so every column but the argmin is
+//     bounded from below without looking at it again.  w2 == T2K_NONE marks a row whose minimum was never refined.
+// l2f_rerank1_kernel (l2f_fixup.cu) then evaluates ONE column per candidate row in fp32 and certifies the nearest
+// index and the outcome of Lowe's test; rows it cannot close (not refined but still a candidate, or a test that hinges
+// on the uncertainty of the second score; rare) go to l2f_fixup_kernel with the three chunk keys.  The threshold only
+// steers work between the two kernels, never a result.
+// Needs acc < 2^18 - 1 (holds: h <= 1.505 * 254^2, -q_a.q_b <= 1.01 * 254^2) and nt <= 8192 (13 column bits).
+struct Keys3w {
+  int k1, k2, k3, w2;             // keys = (acc << 13) | column; w2 = second smallest acc inside k1's chunk
+};
+static constexpr int T2K_COLBITS = 13;
+static constexpr int T2K_NONE = 0x7fffffff;
+static constexpr int T2K_ACC_NONE = (1 << 18) - 1;           // masks absent columns; == T2K_NONE >> T2K_COLBITS
+#ifndef PM_KEYS3_THRESH_SCORE
+#define PM_KEYS3_THRESH_SCORE 1.9f                            // score = d^2 - |a|^2 + 2
+#endif
+static constexpr int T2K_THRESH_KEY = static_cast<int>(PM_KEYS3_THRESH_SCORE * (T2S_SCALE * T2S_SCALE / 2.f)) << T2K_COLBITS;
+__device__ __forceinline__ void keys3_insert(Keys3w& s, int key) {
+  int lo = min(s.k1, key), hi = max(s.k1, key);
+  s.k1 = lo; key = hi;
+  lo = min(s.k2, key); hi = max(s.k2, key);
+  s.k2 = lo;
+  s.k3 = min(s.k3, hi);
+}
+// column of the minimum + second smallest value of a chunk (the rare path): values packed with their position,
+// p_j = v_j * 16 + j (distinct), tree -> minimum with its column; u_j = p_j - pm - 1 wraps to 0xFFFFFFFF for the minimum
+// itself and keeps the order of the others, so an unsigned tree yields the second smallest.
+__device__ __forceinline__ int2 keys3_refine(const int (&v)[16]) {
+  int p[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) p[j] = v[j] * 16 + j;
+  const int a0 = __vimin3_s32(p[0], p[1], p[2]), a1 = __vimin3_s32(p[3], p[4], p[5]);
+  const int a2 = __vimin3_s32(p[6], p[7], p[8]), a3 = __vimin3_s32(p[9], p[10], p[11]);
+  const int a4 = __vimin3_s32(p[12], p[13], p[14]);
+  const int pm = min(__vimin3_s32(a0, a1, a2), __vimin3_s32(a3, a4, p[15]));
+  const unsigned int d = static_cast<unsigned int>(-pm - 1);
+  unsigned int u[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) u[j] = static_cast<unsigned int>(p[j]) + d;
+  const unsigned int b0 = __vimin3_u32(u[0], u[1], u[2]), b1 = __vimin3_u32(u[3], u[4], u[5]);
+  const unsigned int b2 = __vimin3_u32(u[6], u[7], u[8]), b3 = __vimin3_u32(u[9], u[10], u[11]);
+  const unsigned int b4 = __vimin3_u32(u[12], u[13], u[14]);
+  const unsigned int um = min(__vimin3_u32(b0, b1, b2), __vimin3_u32(b3, b4, u[15]));
+  return make_int2(pm & 15, static_cast<int>((um - d) >> 4));      // (column inside the chunk, second smallest acc)
+}
+// 16 columns starting at train column c (multiple of 16); RAGGED: only the first `lim` (>= 1) exist
+template <bool RAGGED>
+__device__ __forceinline__ void keys3_chunk16(Keys3w& s, const uint32_t* r, int c, int lim) {
+  int v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = (RAGGED && j >= lim) ? T2K_ACC_NONE : static_cast<int>(r[j]);
+  const int a0 = __vimin3_s32(v[0], v[1], v[2]), a1 = __vimin3_s32(v[3], v[4], v[5]);
+  const int a2 = __vimin3_s32(v[6], v[7], v[8]), a3 = __vimin3_s32(v[9], v[10], v[11]);
+  const int a4 = __vimin3_s32(v[12], v[13], v[14]);
+  const int cm = min(__vimin3_s32(a0, a1, a2), __vimin3_s32(a3, a4, v[15]));
+  int key = (cm << T2K_COLBITS) + c;
+  if (key < min(s.k1, T2K_THRESH_KEY)) {             // new, match-like row minimum: refine (rare)
+    const int2 js = keys3_refine(v);
+    key += js.x;
+    s.w2 = js.y;
+  }
+  keys3_insert(s, key);
+}
+__device__ __forceinline__ void keys3_chunk32(Keys3w& s, const uint32_t (&v)[32], int c, int lim) {
+  if (lim >= 32) {                                   // warp-uniform: the whole 32-column piece exists
+    keys3_chunk16<false>(s, v, c, 16);
+    keys3_chunk16<false>(s, v + 16, c + 16, 16);
+  } else {
+    if (lim > 0) keys3_chunk16<true>(s, v, c, lim);
+    if (lim > 16) keys3_chunk16<true>(s, v + 16, c + 16, lim - 16);
+  }
+}
 // integer key -> the float key l2f_fixup.cu expects: score with the chunk id in the low 10 mantissa bits
 __device__ __forceinline__ float keysi_to_float(int key) {
   if (key == T2I_INF) return __int_as_float(0x7f800000);
@@ -461,7 +588,7 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
         if (r * T2_ROWS >= job.nq) continue;
         {
           const uint32_t as = ai % AST, use = ai / AST;
-          wait_trap(&a_empty[as], (use & 1) ^ 1);
+          wait_tma(&a_empty[as], (use & 1) ^ 1);
           if (leader) mbar_expect_tx(&a_full[as], 2 * T2_TILE);
           uint8_t* dstA = sA + as * T2_TILE;
           const int row = job.q_row + r * T2_ROWS + rank * T2_BM;
@@ -476,7 +603,7 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
 #pragma unroll
           for (int g = 0; g < NGRP; ++g, ++bi) {
             const uint32_t st = bi % T2_STAGES;
-            wait_trap(&b_empty[st], ((bi / T2_STAGES) & 1) ^ 1);
+            wait_tma(&b_empty[st], ((bi / T2_STAGES) & 1) ^ 1);
             const bool last = g == NGRP - 1;
             if (leader) mbar_expect_tx(&b_full[st], 2 * (AG * T2_BATOM + (last ? Cfg::kBExt : 0)));
             uint8_t* dst = sB + st * T2_BTILE;
@@ -501,18 +628,18 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
         const int job_nq = jobs[jb].nq, job_nt = jobs[jb].nt;
         if (r * T2_ROWS >= job_nq) continue;
         const uint32_t a_st = ai % AST;
-        wait_trap(&a_full[a_st], (ai / AST) & 1);
+        wait_mma(&a_full[a_st], (ai / AST) & 1);
         const uint32_t a_lo = a_lo0 + a_st * (T2_TILE >> 4);
         ++ai;
         const int n_tiles = (job_nt + T2_BN - 1) / T2_BN;
         for (int n = 0; n < n_tiles; ++n, ++ti) {
           const uint32_t as = ti & 1, use = ti >> 1;
-          if (!(MODE == 1 && PM_PROBE_NOACC)) wait_trap(&acc_empty[as], (use & 1) ^ 1);
+          if (!(MODE == 1 && PM_PROBE_NOACC)) wait_mma(&acc_empty[as], (use & 1) ^ 1);
           const uint32_t d_tmem = tmem_base + as * T2_BN;
 #pragma unroll
           for (int g = 0; g < NGRP; ++g, ++bi) {
             const uint32_t st = bi % T2_STAGES;
-            if (!(MODE == 1 && PM_PROBE_NOTMA)) wait_trap(&b_full[st], (bi / T2_STAGES) & 1);
+            if (!(MODE == 1 && PM_PROBE_NOTMA)) wait_mma(&b_full[st], (bi / T2_STAGES) & 1);
             tc_fence_after();
             if (elect_one()) {
               const uint32_t b_lo = b_lo0 + st * (T2_BTILE >> 4);
@@ -537,7 +664,7 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
         __syncwarp();
       }
       if (MODE == 1 && PM_PROBE_NOACC && ai > 0)     // drain before the dealloc
-        wait_trap(&a_empty[(ai - 1) % AST], ((ai - 1) / AST) & 1);
+        wait_mma(&a_empty[(ai - 1) % AST], ((ai - 1) / AST) & 1);
     }
   } else if (warp >= 4) {
     // ======================================= epilogue (both CTAs) =============================
@@ -561,7 +688,7 @@ l2_top2_tc2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_cons
       const int n_tiles = (job.nt + T2_BN - 1) / T2_BN;
       for (int n = 0; n < ((MODE == 1 && PM_PROBE_NOACC) ? 0 : n_tiles); ++n, ++ti) {
         const uint32_t as = ti & 1, use = ti >> 1;
-        wait_trap(&acc_full[as], use & 1);
+        wait_epi(&acc_full[as], use & 1);
         tc_fence_after();
         const uint32_t t0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * T2_BN + slice * (32 * CPW);
         const int c0 = n * T2_BN + slice * (32 * CPW);
@@ -805,11 +932,11 @@ cudaError_t launch_ham_tc2(const TcMaps& maps, int words, const int32_t* qnorm, 
 // MMAs of set 1 run, and vice versa.  Everything else as in l2_top2_tc2_kernel<T2I8, 2, *, 2>.
 //   smem per CTA: query tiles 2 items x 2 sets x 20 KB, train ring 4 x 20 KB, barriers, slice exchange.
 // MODE 2: product; 1: TMA + MMA only; 5: + tcgen05.ld without the reduction (timing probes, no results).
-template <int KA, int BN_ = 256>
+template <int KA, int BN_ = 256, int STG = 0>
 struct I8X2Cfg {                                                 // KA = 128-byte K atoms per row: 1 (SIFT bytes), 2 (256-bit rows)
   static constexpr int kKA = KA;                                 // BN_ = 192: the fp4 form (TMEM columns 384.. hold the scale factors)
   static constexpr int kBN = BN_, kBNH = BN_ / 2, kSets = 2;
-  static constexpr int kAStages = KA == 1 ? 2 : 1, kStages = KA == 1 ? (BN_ == 256 ? 4 : 5) : 3;
+  static constexpr int kAStages = KA == 1 ? 2 : 1, kStages = STG ? STG : (KA == 1 ? (BN_ == 256 ? 4 : 5) : 3);
   static constexpr int kTile = KA * T2_ATOM + T2_EXT;            // 20 / 36 KB: 128 rows x (128 KA + 32) B
   static constexpr int kSmemA = kAStages * kSets * kTile;        // 80 / 72 KB
   static constexpr int kBAtom = kBNH * 128;
@@ -823,18 +950,22 @@ struct I8X2Cfg {                                                 // KA = 128-byt
   static constexpr uint32_t kShape = ((kBN >> 3) << 17) | ((T2_ROWS >> 4) << 24);
   static constexpr uint32_t kIdesc = (2u << 4) | (1u << 10) | kShape;      // D = s32, A = u8, B = s8
   static constexpr uint32_t kIdescExt = (2u << 4) | kShape;                // norm block: A = B = u8
+  static constexpr uint32_t kIdescS8 = (2u << 4) | (1u << 7) | (1u << 10) | kShape;   // MODE 3: A = B = s8 (quantised rows)
   // kind::mxf4 (block-scaled instruction descriptor): A = B = E2M1 (format 1), scale factors UE8M0, K = 64, D = f32
   static constexpr uint32_t kIdescFp4 = (1u << 7) | (1u << 10) | (1u << 23) | kShape;
 };
 using I8X2 = I8X2Cfg<1>;
 
-template <int MODE, bool LEAN, int KA = 1, int FP4 = 0>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LEAN ? 1024 : I8X2Cfg<KA, FP4 ? 192 : 256>::kThreads, 1)
+// LEAN: 0 = no register cap, 1 = 64 registers (launch bound of 1024 threads), 2 = 72 registers (bound of 896 threads):
+// 640 threads x 72 leave 19 K registers for the tail kernels of earlier batches (the RANSAC block needs 16 K)
+template <int MODE, int LEAN, int KA = 1, int FP4 = 0, int STG = 0>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LEAN == 1 ? 1024 : LEAN == 2 ? 896 : I8X2Cfg<KA, FP4 ? 192 : 256>::kThreads, 1)
 l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant__ CUtensorMap q_ext,
                const __grid_constant__ CUtensorMap t_main, const __grid_constant__ CUtensorMap t_ext,
                const PairJob* __restrict__ jobs, int n_jobs, int blocks_per_job, int2* __restrict__ knn_idx,
-               float2* __restrict__ knn_dist, int stride) {
-  using C = I8X2Cfg<KA, FP4 ? 192 : 256>;
+               float2* __restrict__ knn_dist, int stride, float2* __restrict__ extra_keys = nullptr) {
+  using C = I8X2Cfg<KA, FP4 ? 192 : 256, STG>;
+  static_assert(MODE < 3 || MODE == 5 || !FP4, "candidate keys are integer keys of the kind::i8 accumulators");
   constexpr int BN = C::kBN, BNH = C::kBNH, ST = C::kStages, TILE = C::kTile, BTILE = C::kBTile, NSL = C::kSlices;
   constexpr int AST = C::kAStages, KDIM = 128 * KA, BATOM = C::kBAtom;
   static_assert(!FP4 || KA == 1, "the fp4 form of a 256-bit row is one 128-byte K atom");
@@ -904,7 +1035,7 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
         const int nset = blk * C::kRows + T2_ROWS < job.nq ? 2 : 1;
         {
           const uint32_t as = ai % AST, use = ai / AST;
-          wait_trap(&a_empty[as], (use & 1) ^ 1);
+          wait_tma(&a_empty[as], (use & 1) ^ 1);
           if (leader) mbar_expect_tx(&a_full[as], nset * 2 * TILE);
           for (int set = 0; set < nset; ++set) {
             uint8_t* dst = sA + (as * 2 + set) * TILE;
@@ -919,7 +1050,7 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
         for (int n = 0; n < n_tiles; ++n, ++bi) {
           const int row = job.t_row + n * BN + rank * BNH;        // this CTA's half of the train tile
           const uint32_t st = bi % ST;
-          wait_trap(&b_empty[st], ((bi / ST) & 1) ^ 1);
+          wait_tma(&b_empty[st], ((bi / ST) & 1) ^ 1);
           if (leader) mbar_expect_tx(&b_full[st], 2 * BTILE);
           uint8_t* dst = sB + st * BTILE;
 #pragma unroll
@@ -942,15 +1073,15 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
         if (blk * C::kRows >= job_nq) continue;
         const int nset = blk * C::kRows + T2_ROWS < job_nq ? 2 : 1;
         const uint32_t a_st = ai % AST;
-        wait_trap(&a_full[a_st], (ai / AST) & 1);
+        wait_mma(&a_full[a_st], (ai / AST) & 1);
         ++ai;
         const int n_tiles = (job_nt + BN - 1) / BN;
         for (int n = 0; n < n_tiles; ++n, ++bi) {
           const uint32_t st = bi % ST;
-          wait_trap(&b_full[st], (bi / ST) & 1);
+          wait_mma(&b_full[st], (bi / ST) & 1);
           const uint32_t b_lo = b_lo0 + st * (BTILE >> 4);
           for (int set = 0; set < nset; ++set) {
-            wait_trap(&acc_empty[set], (use[set] & 1) ^ 1);
+            wait_mma(&acc_empty[set], (use[set] & 1) ^ 1);
             ++use[set];
             tc_fence_after();
             if (elect_one()) {
@@ -972,7 +1103,7 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
                   umma_f16_pair<2>(d_tmem,
                                    (static_cast<uint64_t>(HI128) << 32) | (a_lo + (((k >> 2) * T2_ATOM + (k & 3) * 32) >> 4)),
                                    (static_cast<uint64_t>(HI128) << 32) | (b_lo + (((k >> 2) * BATOM + (k & 3) * 32) >> 4)),
-                                   C::kIdesc, k > 0 ? 1u : 0u);
+                                   MODE >= 3 ? C::kIdescS8 : C::kIdesc, k > 0 ? 1u : 0u);
                 umma_f16_pair<2>(d_tmem, (static_cast<uint64_t>(HI32) << 32) | (a_lo + ((KA * T2_ATOM) >> 4)),
                                  (static_cast<uint64_t>(HI32) << 32) | (b_lo + ((KA * BATOM) >> 4)), C::kIdescExt, 1u);
               }
@@ -999,6 +1130,12 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
       Top2i s0, s1;
       s0.m1 = s0.m2 = s1.m1 = s1.m2 = T2I_INF;
       s0.i1 = s1.i1 = -1;
+      Keys6i g0, g1;                                    // MODE 3: six candidate keys per row and row set
+      g0.k1 = g0.k2 = g0.k3 = g0.k4 = g0.k5 = g0.k6 = T2I_INF;
+      g1 = g0;
+      Keys3w h0, h1;                                    // MODE 4
+      h0.k1 = h0.k2 = h0.k3 = h0.w2 = T2K_NONE;
+      h1 = h0;
       const int n_tiles = (job.nt + BN - 1) / BN;
       for (int n = 0; n < n_tiles; ++n) {
         const int c0 = n * BN + slice * 64;
@@ -1006,7 +1143,7 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
 #pragma unroll
         for (int set = 0; set < 2; ++set) {
           if (set < nset) {
-            wait_trap(&acc_full[set], use[set] & 1);
+            wait_epi(&acc_full[set], use[set] & 1);
             ++use[set];
             tc_fence_after();
             if (MODE == 1) {
@@ -1016,11 +1153,78 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
               uint32_t v[32];
               tmem_ld_32x32b_x32(tq + set * BN, v);
               if (MODE == 2) t2i_chunk32(set ? s1 : s0, v, c0, lim);
+              if (MODE == 3) keysi_chunk32(set ? g1 : g0, v, c0, lim);
+              if (MODE == 4) keys3_chunk32(set ? h1 : h0, v, c0, lim);
               tmem_ld_32x32b_x32(tq + set * BN + 32, v);
               tc_fence_before();
               if (lane == 0) mbar_arrive_leader(&acc_empty[set]);
               if (MODE == 2) t2i_chunk32(set ? s1 : s0, v, c0 + 32, lim - 32);
+              if (MODE == 3) keysi_chunk32(set ? g1 : g0, v, c0 + 32, lim - 32);
+              if (MODE == 4) keys3_chunk32(set ? h1 : h0, v, c0 + 32, lim - 32);
             }
+          }
+        }
+      }
+      // MODE 3: merge the six keys of the column slices (slices 1.. publish, slice 0 merges and writes the keys in
+      // the layout of l2_top2_tc2_kernel<.., 3, .., 3>: knn_dist = k1,k2 | knn_idx = bits of k3,k4 | extra = k5,k6)
+      if (MODE == 3) {
+        float4* slot = xchg + ((quarter * (NSL - 1)) * 64 + lane);
+        const int bar_id = 1 + quarter;
+#pragma unroll
+        for (int set = 0; set < 2; ++set) {
+          if (set < nset) {
+            Keys6i& g = set ? g1 : g0;
+            if (slice > 0) {
+              slot[(slice - 1) * 64] = make_float4(__int_as_float(g.k1), __int_as_float(g.k2), __int_as_float(g.k3), __int_as_float(g.k4));
+              slot[(slice - 1) * 64 + 32] = make_float4(__int_as_float(g.k5), __int_as_float(g.k6), 0.f, 0.f);
+            }
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NSL) : "memory");
+            if (slice == 0) {
+#pragma unroll
+              for (int o = 0; o < NSL - 1; ++o) {
+                const float4 x = slot[o * 64], x2 = slot[o * 64 + 32];
+                keysi_insert(g, __float_as_int(x.x)); keysi_insert(g, __float_as_int(x.y));
+                keysi_insert(g, __float_as_int(x.z)); keysi_insert(g, __float_as_int(x.w));
+                keysi_insert(g, __float_as_int(x2.x)); keysi_insert(g, __float_as_int(x2.y));
+              }
+              const int row = blk * C::kRows + set * T2_ROWS + rank * T2_BM + quarter * 32 + lane;
+              if (row < job.nq) {
+                const size_t o = static_cast<size_t>(jb) * stride + row;
+                knn_dist[o] = make_float2(keysi_to_float(g.k1), keysi_to_float(g.k2));
+                knn_idx[o] = make_int2(__float_as_int(keysi_to_float(g.k3)), __float_as_int(keysi_to_float(g.k4)));
+                extra_keys[o] = make_float2(keysi_to_float(g.k5), keysi_to_float(g.k6));
+              }
+            }
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NSL) : "memory");
+          }
+        }
+      }
+      // MODE 4: merge (k1, k2, k3, w2) of the column slices; w2 follows the slice that holds the row minimum.  Per row:
+      // knn_idx = (k1, k2), knn_dist = bits of (k3, w2); l2f_rerank1_kernel follows.
+      if (MODE == 4) {
+        int4* slot = reinterpret_cast<int4*>(xchg) + ((quarter * (NSL - 1)) * 32 + lane);
+        const int bar_id = 1 + quarter;
+#pragma unroll
+        for (int set = 0; set < 2; ++set) {
+          if (set < nset) {
+            Keys3w& g = set ? h1 : h0;
+            if (slice > 0) slot[(slice - 1) * 32] = make_int4(g.k1, g.k2, g.k3, g.w2);
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NSL) : "memory");
+            if (slice == 0) {
+#pragma unroll
+              for (int o = 0; o < NSL - 1; ++o) {
+                const int4 x = slot[o * 32];
+                if (x.x < g.k1) g.w2 = x.w;
+                keys3_insert(g, x.x); keys3_insert(g, x.y); keys3_insert(g, x.z);
+              }
+              const int row = blk * C::kRows + set * T2_ROWS + rank * T2_BM + quarter * 32 + lane;
+              if (row < job.nq) {
+                const size_t o = static_cast<size_t>(jb) * stride + row;
+                knn_idx[o] = make_int2(g.k1, g.k2);
+                knn_dist[o] = make_float2(__int_as_float(g.k3), __int_as_float(g.w2));
+              }
+            }
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NSL) : "memory");
           }
         }
       }
@@ -1071,12 +1275,12 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
   }
 }
 
-template <int MODE, bool LEAN, int KA = 1, int FP4 = 0>
+template <int MODE, int LEAN, int KA = 1, int FP4 = 0, int STG = 0>
 static cudaError_t i8x2_attr() {
-  cudaError_t e = cudaFuncSetAttribute(l2_i8x2_kernel<MODE, LEAN, KA, FP4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       I8X2Cfg<KA, FP4 ? 192 : 256>::kSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(l2_i8x2_kernel<MODE, LEAN, KA, FP4, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       I8X2Cfg<KA, FP4 ? 192 : 256, STG>::kSmemBytes);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(l2_i8x2_kernel<MODE, LEAN, KA, FP4>, cudaFuncAttributePreferredSharedMemoryCarveout,
+  return cudaFuncSetAttribute(l2_i8x2_kernel<MODE, LEAN, KA, FP4, STG>, cudaFuncAttributePreferredSharedMemoryCarveout,
                               cudaSharedmemCarveoutMaxShared);
 }
 
@@ -1114,8 +1318,49 @@ cudaError_t launch_l2s8_tc2(const TcMaps& maps, int dim, const PairJob* jobs, in
   return cudaGetLastError();
 }
 
+// Quantised real-valued rows with TWO query row sets per cluster (l2_i8x2_kernel MODE 3): the one-set kernel above
+// streams the train image (8192 x 288 B) through L2 once per 256 query rows -- 75 MB per pair, 7.2 TB/s at the rate
+// kind::i8 consumes 9 K-steps, the measured L2 ceiling -- so the tensor pipe waits AND every co-resident tail kernel of
+// the previous batches starves on L2.  Two row sets halve that traffic.  Same candidate keys, same layout.
+#ifndef PM_S8X2_STAGES
+#define PM_S8X2_STAGES 3
+#endif
+#ifndef PM_S8X2_LEAN
+#define PM_S8X2_LEAN 2
+#endif
+cudaError_t launch_l2s8x2(const TcMaps& maps, int dim, const PairJob* jobs, int n_jobs, int max_nq, int2* idx,
+                          float2* dist, float2* extra, int stride, int num_sms, cudaStream_t st, int keys3) {
+  if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
+  using C2 = I8X2Cfg<2, 256, PM_S8X2_STAGES>;
+  using C1 = I8X2Cfg<1>;
+  const int blocks_per_job = (max_nq + C2::kRows - 1) / C2::kRows;
+  const int n_items = n_jobs * blocks_per_job;
+  int clusters = num_sms / 2;
+  if (n_items < clusters) clusters = n_items;
+  const int grid = clusters * 2;
+  if (dim == 256 && keys3)
+    l2_i8x2_kernel<4, PM_S8X2_LEAN, 2, 0, PM_S8X2_STAGES><<<grid, C2::kThreads, C2::kSmemBytes, st>>>(
+        maps.q_main, maps.q_ext, maps.t_main, maps.t_ext, jobs, n_jobs, blocks_per_job, idx, dist, stride, extra);
+  else if (dim == 128 && keys3)
+    l2_i8x2_kernel<4, PM_S8X2_LEAN, 1><<<grid, C1::kThreads, C1::kSmemBytes, st>>>(
+        maps.q_main, maps.q_ext, maps.t_main, maps.t_ext, jobs, n_jobs, blocks_per_job, idx, dist, stride, extra);
+  else if (dim == 256)
+    l2_i8x2_kernel<3, PM_S8X2_LEAN, 2, 0, PM_S8X2_STAGES><<<grid, C2::kThreads, C2::kSmemBytes, st>>>(
+        maps.q_main, maps.q_ext, maps.t_main, maps.t_ext, jobs, n_jobs, blocks_per_job, idx, dist, stride, extra);
+  else if (dim == 128)
+    l2_i8x2_kernel<3, PM_S8X2_LEAN, 1><<<grid, C1::kThreads, C1::kSmemBytes, st>>>(
+        maps.q_main, maps.q_ext, maps.t_main, maps.t_ext, jobs, n_jobs, blocks_per_job, idx, dist, stride, extra);
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
 cudaError_t i8x2_configure() {
   cudaError_t e;
+  if ((e = i8x2_attr<4, PM_S8X2_LEAN, 2, 0, PM_S8X2_STAGES>()) != cudaSuccess) return e;
+  if ((e = i8x2_attr<4, PM_S8X2_LEAN, 1>()) != cudaSuccess) return e;
+  if ((e = i8x2_attr<3, PM_S8X2_LEAN, 2, 0, PM_S8X2_STAGES>()) != cudaSuccess) return e;
+  if ((e = i8x2_attr<3, PM_S8X2_LEAN, 1>()) != cudaSuccess) return e;
   if ((e = i8x2_attr<2, false>()) != cudaSuccess) return e;
   if ((e = i8x2_attr<2, true>()) != cudaSuccess) return e;
   if ((e = i8x2_attr<1, false>()) != cudaSuccess) return e;
@@ -1213,6 +1458,97 @@ cudaError_t launch_l2i8_tc2(const TcMaps& maps, const PairJob* jobs, int n_jobs,
   else
     l2_top2_tc2_kernel<T2I8, 2, false, 2><<<grid, T2I8::kThreads, T2I8::kSmemBytes, st>>>(
         maps.q_main, maps.q_ext, maps.t_main, maps.t_ext, nullptr, jobs, n_jobs, tiles_per_job, idx, dist, stride, nullptr);
+  return cudaGetLastError();
+}
+
+// =========================================================================================================
+// Tensor-pipe peak of one MMA kind, measured live (pm_measure_tensor_peak): the issue loop of the kernels above with
+// nothing around it.  One CTA pair per two SMs, operands resident in shared memory (one 128-byte K atom of 128 rows per
+// CTA and operand, pseudo-random bytes so that the data path toggles like real operands), cta_group::2 M = 256, N = 256,
+// four K-steps per iteration alternating between two accumulators, no TMA, no epilogue, one commit at the end.
+//   KIND 0: kind::f16 (K = 16 per instruction), 2: kind::i8 (K = 32), 4: kind::mxf4 block-scaled (K = 64)
+// FLOP per instruction and cluster: 2 * 256 * 256 * K.
+template <int KIND>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+tensor_peak_kernel(int iters) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + T2_ATOM;
+  uint64_t* done = reinterpret_cast<uint64_t*>(smem + 2 * T2_ATOM);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool leader = cluster_ctarank() == 0;
+  for (int i = threadIdx.x; i < 2 * T2_ATOM / 4; i += blockDim.x) {
+    uint32_t x = static_cast<uint32_t>(i) * 2654435761u + blockIdx.x * 40503u;
+    x ^= x >> 15; x *= 2246822519u; x ^= x >> 13;
+    if (KIND == 0) x &= 0x3BFF3BFFu;                   // fp16 operands: finite values of magnitude < 1.5
+    reinterpret_cast<uint32_t*>(smem)[i] = x;
+  }
+  fence_proxy_async();
+  if (warp == 0 && lane == 0) { mbar_init(done, 1); fence_mbar_init(); }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(T2_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (KIND == 4) {                                       // all scale factors 1.0 (UE8M0 0x7F), as in l2_i8x2_kernel
+    const uint32_t a = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + 384;
+    tmem_st_32x32b_x32_fill(a, 0x7F7F7F7Fu);
+    tmem_st_32x32b_x32_fill(a + 32, 0x7F7F7F7Fu);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+  }
+  if (warp == 1 && leader) {
+    constexpr uint32_t HI128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+    constexpr int BN = KIND == 4 ? 192 : 256;          // the fp4 kernels use 192-column tiles (TMEM holds the scale factors)
+    constexpr uint32_t shape = ((BN >> 3) << 17) | ((T2_ROWS >> 4) << 24);
+    constexpr uint32_t idesc = KIND == 0 ? ((1u << 4) | shape) : KIND == 2 ? ((2u << 4) | (1u << 10) | shape)
+                                                                         : ((1u << 7) | (1u << 10) | (1u << 23) | shape);
+    const uint32_t a_lo = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t b_lo = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (1u << 16);
+    if (elect_one()) {
+      for (int it = 0; it < iters; ++it) {
+        const uint32_t d_tmem = tmem_base + (it & 1) * BN;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t ad = (static_cast<uint64_t>(HI128) << 32) | (a_lo + ((k * 32) >> 4));
+          const uint64_t bd = (static_cast<uint64_t>(HI128) << 32) | (b_lo + ((k * 32) >> 4));
+          if (KIND == 4) umma_mxf4_pair(d_tmem, ad, bd, idesc, tmem_base + 384, tmem_base + 384 + 16, (it > 1 || k > 0) ? 1u : 0u);
+          else umma_f16_pair<KIND>(d_tmem, ad, bd, idesc, (it > 1 || k > 0) ? 1u : 0u);
+        }
+      }
+      umma_commit_pair(done);
+    }
+    __syncwarp();
+  }
+  wait_sleep<64>(done, 0);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(T2_TMEM_COLS) : "memory");
+  }
+}
+// kind: 0 f16, 1 i8, 2 mxf4 (PM_PEAK_KIND_*).  flop_per_launch receives the FLOP of one launch.
+cudaError_t launch_tensor_peak(int kind, int iters, int num_sms, double* flop_per_launch, cudaStream_t st) {
+  const int grid = (num_sms / 2) * 2;
+  const int smem = 2 * T2_ATOM + 1024 + 64;
+  const int kvals = kind == 0 ? 16 : (kind == 1 ? 32 : 64);
+  const int bn = kind == 2 ? 192 : 256;
+  *flop_per_launch = static_cast<double>(grid / 2) * iters * 4.0 * 2.0 * 256.0 * bn * kvals;
+  if (kind == 0) tensor_peak_kernel<0><<<grid, 128, smem, st>>>(iters);
+  else if (kind == 1) tensor_peak_kernel<2><<<grid, 128, smem, st>>>(iters);
+  else if (kind == 2) tensor_peak_kernel<4><<<grid, 128, smem, st>>>(iters);
+  else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
 

@@ -18,8 +18,6 @@
 //   * a row that six chunks cannot certify is scanned exhaustively by the whole block (exact, rare).
 // Ties resolve to the lowest train index (cv::BFMatcher's rule): certification is strict (<), so an
 // unevaluated column can never tie with a reported one.
-#include <cstdlib>
-
 #include "common.cuh"
 #include "kernels.h"
 
@@ -218,7 +216,9 @@ l2f_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm,
                  const PairJob* __restrict__ jobs, int2* __restrict__ knn_idx, float2* __restrict__ knn_dist,
                  const float2* __restrict__ extra, int stride, float ratio, int need,
                  unsigned long long* __restrict__ counters, int e_mode, const uint8_t* __restrict__ q8,
-                 const uint8_t* __restrict__ t8) {
+                 const uint8_t* __restrict__ t8, const uint8_t* __restrict__ flags, int nkeys) {
+  // flags != nullptr: only the rows l2f_rerank1_kernel left open (flag 1) are processed, all others hold final results;
+  // nkeys: how many of the six key slots the candidate stage filled (3 behind l2f_rerank1_kernel)
   constexpr int THREADS = PRE ? FFP_THREADS : FF_THREADS, HW = THREADS / 16, SPAN = THREADS;
   __shared__ __align__(16) float qs[HW][FF_MAXDIM];
   __shared__ __align__(16) uint4 qs8[PRE ? HW : 1][FF_MAXDIM / 16];       // PRE: the query rows as s8
@@ -244,7 +244,7 @@ l2f_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm,
   __syncthreads();
   {
     const int row = span0 + tid;
-    if (row < jb.nq) {
+    if (row < jb.nq && (flags == nullptr || flags[base + row] != 0)) {
       const float2 k12 = knn_dist[base + row];
       const int2 k34 = knn_idx[base + row];
       const float2 k56 = extra[base + row];
@@ -293,7 +293,7 @@ l2f_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm,
     // first chunk of a ratio-test row: columns are abandoned as soon as their partial sum shows they cannot matter
     // (see thr below).  A row that the first chunk cannot close re-evaluates it in full (rare) and goes on as before.
     bool early = need == L2F_NEED_RATIO;
-    for (int j = 0; j < 6 && !done; ++j) {
+    for (int j = 0; j < nkeys && !done; ++j) {
       const float Kj = keys_s[r][j];
       if (Kj == inf) break;                              // (unreachable: the previous lbn was +inf)
       const int cb = static_cast<int>(__float_as_uint(Kj) & FF_IDMASK) * 16;
@@ -364,7 +364,7 @@ l2f_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm,
         worst = fmaxf(worst, static_cast<float>(err / bd.eps(Kj)));
       }
       ff_merge(e1, e2, k1, k2);
-      const float lbn = bd.lb(keys_s[r][j < 5 ? j + 1 : 5]);     // every column not evaluated so far is >= lbn
+      const float lbn = bd.lb(keys_s[r][j < nkeys - 1 ? j + 1 : nkeys - 1]);     // every column not evaluated so far is >= lbn
       const float d1sq = e1 == KEY_NONE64 ? inf : __uint_as_float(static_cast<unsigned int>(e1 >> 32));
       const float d2sq = e2 == KEY_NONE64 ? inf : __uint_as_float(static_cast<unsigned int>(e2 >> 32));
       const size_t o = base + row;
@@ -450,6 +450,129 @@ l2f_fixup_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm,
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// l2f_rerank1_kernel -- the re-rank behind l2_i8x2_kernel MODE 4 (batched loop, ratio-test rows): ONE exact column per
+// candidate row.  Input per query row (written by the tensor kernel): k1 = (acc << 13) | column of the smallest
+// approximate score, k2 / k3 = the next chunk keys, w2 = second smallest acc inside k1's chunk.  Hence
+//     K1 = score(k1),   K2 = score(min(w2, k2 >> 13)) = the second smallest approximate score of the whole row,
+// and with the certified bound of ff_bound(e_mode 1): every column but c1 has an exact d^2 >= lb(K2).
+//   level 0  the keys alone show that Lowe's test cannot pass                      -> closed, no neighbours reported
+//            (a candidate row whose minimum the tensor kernel did not refine -- w2 == 0x7fffffff -- goes to level 2)
+//   level 1  e1 = exact d^2 of column c1 (fp32 chain of ff_dist, bit-identical to the SIMT kernel):
+//              e1 < lb(K2) and sqrt(e1) < ratio * sqrt(lb(K2))   -> nearest certain, test passes whatever d2 is
+//              sqrt(min(e1, lb(K2))) >= ratio * sqrt(max(e1, ub(K2)))   -> the test fails whichever column is nearest
+//   level 2  anything else (the outcome hinges on the uncertainty of K2; rare) -> flag 1 and the three chunk keys in
+//            the float format of l2f_fixup_kernel, which then evaluates whole chunks / scans the row.
+// One thread per row, 64 registers, no shared memory: several blocks fit next to the persistent tensor kernel.
+static constexpr int R1_THREADS = 128;
+static constexpr int R1_COLBITS = 13;
+static constexpr int R1_ACC_NONE = 0x7fffffff >> R1_COLBITS;
+__device__ __forceinline__ float r1_score(int acc) { return static_cast<float>(acc) * (2.f / (254.f * 254.f)); }
+__device__ __forceinline__ float r1_float_key(int key) {        // chunk key -> the float key format of l2f_fixup_kernel
+  if (key == 0x7fffffff) return __int_as_float(0x7f800000);
+  const float sc = r1_score(key >> R1_COLBITS);
+  return __uint_as_float((__float_as_uint(sc) & 0xFFFFFC00u) | static_cast<uint32_t>((key & ((1 << R1_COLBITS) - 1)) >> 4));
+}
+__global__ void __launch_bounds__(R1_THREADS, 8)
+l2f_rerank1_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm, int dim,
+                   const PairJob* __restrict__ jobs, int2* __restrict__ knn_idx, float2* __restrict__ knn_dist,
+                   float2* __restrict__ extra, uint8_t* __restrict__ flags, int stride, float ratio,
+                   unsigned long long* __restrict__ counters) {
+  const PairJob jb = jobs[blockIdx.y];
+  const int row = blockIdx.x * R1_THREADS + threadIdx.x;
+  if (blockIdx.x * R1_THREADS >= jb.nq) return;
+  const float inf = __int_as_float(0x7f800000);
+  int n_cand = 0, n_open = 0;
+  float worst = 0.f;
+  if (row < jb.nq) {
+    const size_t o = static_cast<size_t>(blockIdx.y) * stride + row;
+    const int2 k12 = knn_idx[o];
+    const float2 kw = knn_dist[o];
+    const int k1 = k12.x, k2 = k12.y, k3 = __float_as_int(kw.x), w2 = __float_as_int(kw.y);
+    int2 oi = make_int2(-1, -1);
+    float2 od = make_float2(inf, inf);
+    uint8_t flag = 0;
+    if (k1 != 0x7fffffff) {                                  // (no train rows at all: no neighbours)
+      // refined: the tensor kernel resolved the column of the minimum and the second smallest score of its chunk; else
+      // k1 carries the chunk's base column and the second smallest score of the row is only known to be <= score(k2)
+      const bool refined = w2 != 0x7fffffff;
+      const int acc2 = min(refined ? w2 : R1_ACC_NONE, k2 >> R1_COLBITS);
+      const float K1 = r1_score(k1 >> R1_COLBITS), K2 = acc2 >= R1_ACC_NONE ? inf : r1_score(acc2);
+      const FfBound bd = ff_bound(fnorm[jb.q_row + row], jb.t_maxn, dim, 1);
+      // level 0: true d1^2 >= lb(K1), true d2^2 <= ub(K2) (K2 is at least an upper bound of the second smallest score)
+      if (__fsqrt_rn(bd.lb(K1)) >= __fmul_rn(ratio, __fsqrt_rn(bd.ub(K2)))) {
+        // closed: Lowe's test cannot pass
+      } else if (!refined) {
+        ++n_cand;
+        flag = 1;
+        od = make_float2(r1_float_key(k1), r1_float_key(k2));
+        oi = make_int2(__float_as_int(r1_float_key(k3)), __float_as_int(inf));
+        extra[o] = make_float2(inf, inf);
+      } else {
+        ++n_cand;
+        const int c1 = k1 & ((1 << R1_COLBITS) - 1);
+        const float4* qr = reinterpret_cast<const float4*>(raw + (static_cast<size_t>(jb.q_row) + row) * dim);
+        const float4* tr = reinterpret_cast<const float4*>(raw + (static_cast<size_t>(jb.t_row) + c1) * dim);
+        float e1 = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < (dim >> 2); ++k) {               // the SIMT kernel's chain: d = a - b; acc = fma(d, d, acc)
+          const float4 a = __ldg(qr + k), b = __ldg(tr + k);
+          float d = a.x - b.x; e1 = fmaf(d, d, e1);
+          d = a.y - b.y; e1 = fmaf(d, d, e1);
+          d = a.z - b.z; e1 = fmaf(d, d, e1);
+          d = a.w - b.w; e1 = fmaf(d, d, e1);
+        }
+        worst = static_cast<float>(fabs(static_cast<double>(K1) - (static_cast<double>(e1) - bd.c)) / bd.eps(K1));
+        const float D1 = __fsqrt_rn(e1);
+        const float rest = bd.lb(K2);                        // every column but c1 is >= rest
+        if (K2 == inf) {                                     // the train image has a single row
+          oi = make_int2(c1, -1);
+          od = make_float2(D1, inf);
+        } else if (e1 < rest && D1 < __fmul_rn(ratio, __fsqrt_rn(rest))) {
+          oi = make_int2(c1, 0x7ffffffe);                    // nearest certain; true d2 >= sqrt(rest): passes whatever it is
+          od = make_float2(D1, __fsqrt_rn(rest));
+        } else if (__fsqrt_rn(fminf(e1, rest)) >= __fmul_rn(ratio, __fsqrt_rn(fmaxf(e1, bd.ub(K2))))) {
+          // true d1^2 >= min(e1, rest) and true d2^2 <= max(e1, ub(K2)) whichever column is the nearest: fails
+        } else {
+          flag = 1;
+          ++n_open;
+          od = make_float2(r1_float_key(k1), r1_float_key(k2));
+          oi = make_int2(__float_as_int(r1_float_key(k3)), __float_as_int(inf));
+          extra[o] = make_float2(inf, inf);
+        }
+      }
+    }
+    knn_idx[o] = oi;
+    knn_dist[o] = od;
+    flags[o] = flag;
+  }
+  if (counters != nullptr) {
+    n_cand = __reduce_add_sync(0xffffffffu, n_cand);
+    n_open = __reduce_add_sync(0xffffffffu, n_open);
+    const unsigned int wb = __reduce_max_sync(0xffffffffu, __float_as_uint(worst));
+    if ((threadIdx.x & 31) == 0) {
+      if (n_cand) { atomicAdd(&counters[0], static_cast<unsigned long long>(n_cand)); atomicAdd(&counters[1], static_cast<unsigned long long>(n_cand)); }
+      if (wb > static_cast<unsigned int>(counters[3])) atomicMax(&counters[3], static_cast<unsigned long long>(wb));
+    }
+    (void)n_open;
+  }
+}
+
+cudaError_t launch_l2f_rerank1(const float* raw, const float* fnorm, int dim, const PairJob* jobs, int n_jobs, int max_nq,
+                               int2* idx, float2* dist, float2* extra, uint8_t* flags, int stride, float ratio,
+                               unsigned long long* counters, const uint8_t* q8, const uint8_t* t8, cudaStream_t st) {
+  if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
+  if (dim <= 0 || dim > FF_MAXDIM || (dim & 63)) return cudaErrorInvalidValue;
+  l2f_rerank1_kernel<<<dim3((max_nq + R1_THREADS - 1) / R1_THREADS, n_jobs), R1_THREADS, 0, st>>>(
+      raw, fnorm, dim, jobs, idx, dist, extra, flags, stride, ratio, counters);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  // the rows left open (flag 1), with three keys: the small-footprint variant, so that it too runs next to the tensor kernel
+  l2f_fixup_kernel<true><<<dim3((max_nq + FFP_THREADS - 1) / FFP_THREADS, n_jobs), FFP_THREADS, 0, st>>>(
+      raw, fnorm, dim, jobs, idx, dist, extra, stride, ratio, L2F_NEED_RATIO, counters, 1, q8, t8, flags, 3);
+  return cudaGetLastError();
+}
+
 static constexpr int FF_DYN_SMEM = FF_HW * FF_TILE * static_cast<int>(sizeof(float));   // 34 KB
 cudaError_t l2f_configure() {
   cudaError_t e = cudaFuncSetAttribute(l2f_fixup_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_DYN_SMEM);
@@ -459,8 +582,8 @@ cudaError_t l2f_configure() {
   return cudaFuncSetAttribute(l2f_fixup_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
-// q8 / t8: the s8 forms of the rows (pack_float_kernel), rows of dim + 32 bytes; with them, e_mode 1, need =
-// L2F_NEED_RATIO and PM_L2F_PREFILTER=1 in the environment the prefiltering variant runs.  The staged variant is the
+// q8 / t8: the s8 forms of the rows (pack_float_kernel), rows of dim + 32 bytes; with them, e_mode 1 and need =
+// L2F_NEED_RATIO the prefiltering variant runs (the caller passes them only when asked to: api.cu, opt_prefilter).  The staged variant is the
 // default: alone it needs 0.99 ms per 256 pairs against 1.27 ms (the survivors' one-row-per-lane loads have few
 // requests in flight), and next to the tensor kernel the step is the same with either (63.7 k vs 62.6 k pairs/s).
 cudaError_t launch_l2f_fixup(const float* raw, const float* fnorm, int dim, const PairJob* jobs, int n_jobs,
@@ -469,13 +592,12 @@ cudaError_t launch_l2f_fixup(const float* raw, const float* fnorm, int dim, cons
                              const uint8_t* t8) {
   if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
   if (dim <= 0 || dim > FF_MAXDIM || (dim & 63)) return cudaErrorInvalidValue;
-  static const bool prefilter = std::getenv("PM_L2F_PREFILTER") != nullptr;
-  if (e_mode == 1 && need == L2F_NEED_RATIO && q8 != nullptr && t8 != nullptr && prefilter)
+  if (e_mode == 1 && need == L2F_NEED_RATIO && q8 != nullptr && t8 != nullptr)
     l2f_fixup_kernel<true><<<dim3((max_nq + FFP_THREADS - 1) / FFP_THREADS, n_jobs), FFP_THREADS, 0, st>>>(raw, fnorm, dim, jobs, idx, dist, extra, stride, ratio, need, counters,
-                                                        e_mode, q8, t8);
+                                                        e_mode, q8, t8, nullptr, 6);
   else
     l2f_fixup_kernel<false><<<dim3((max_nq + FF_SPAN - 1) / FF_SPAN, n_jobs), FF_THREADS, FF_DYN_SMEM, st>>>(raw, fnorm, dim, jobs, idx, dist, extra, stride, ratio, need,
-                                                                   counters, e_mode, nullptr, nullptr);
+                                                                   counters, e_mode, nullptr, nullptr, nullptr, 6);
   return cudaGetLastError();
 }
 

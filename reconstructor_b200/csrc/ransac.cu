@@ -477,12 +477,199 @@ __device__ __forceinline__ bool pair_collinear(const float2* __restrict__ p, con
          static_cast<double>(FLT_EPSILON) * (fabs(dx1) + fabs(dy1) + fabs(dx2) + fabs(dy2));
 }
 
+// ---- PM_SAMPLER_PHILOX: the subset of iteration k is a pure function of (pair key, k) ---------------------------
+// Philox4x32-10 with counter (k, block, 0, 'PMRF'); word w -> index floor(w * n / 2^32); slots filled in order,
+// duplicates skipped, a complete subset checked like OpenCV's checkSubset (last point, both images), on rejection
+// the filling restarts with the next words.  The CPU filter of the parity tests follows the same rules.
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t lo0 = 0xD2511F53u * c[0], hi0 = __umulhi(0xD2511F53u, c[0]);
+    const uint32_t lo1 = 0xCD9E8D57u * c[2], hi1 = __umulhi(0xCD9E8D57u, c[2]);
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+__device__ bool philox_subset(const float2* __restrict__ p1, const float2* __restrict__ p2, int n,
+                              unsigned long long key, int iter, int* idx) {
+  int filled = 0;
+  int v7[7];
+  float2 s1[7], s2[7];
+  for (uint32_t blk = 0; blk < 256; ++blk) {
+    uint32_t c[4] = {static_cast<uint32_t>(iter), blk, 0u, 0x504D5246u};
+    philox4x32_10(c, static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32));
+    for (int w = 0; w < 4; ++w) {
+      const int v = static_cast<int>(__umulhi(c[w], static_cast<uint32_t>(n)));
+      bool dup = false;
+      for (int j = 0; j < filled; ++j) dup |= v7[j] == v;
+      if (dup) continue;
+      v7[filled] = v;
+      s1[filled] = p1[v]; s2[filled] = p2[v];
+      if (++filled == 7) {
+        if (!last_point_collinear(s1) && !last_point_collinear(s2)) {
+          for (int j = 0; j < 7; ++j) idx[j] = v7[j];
+          return true;
+        }
+        filled = 0;
+      }
+    }
+  }
+  return false;
+}
+
+// ---- optional refit: normalised 8-point over the inliers of the winner (cv::findFundamentalMat FM_8POINT) --------
+// Cyclic Jacobi, fixed sweep order (the CPU filter of the parity tests follows it operation for operation).
+__device__ void jacobi_sym(double* A, double* V, int n, int sweeps) {
+  for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) V[i * n + j] = i == j ? 1.0 : 0.0;
+  for (int s = 0; s < sweeps; ++s) {
+    double off = 0;
+    for (int p = 0; p < n; ++p) for (int q = p + 1; q < n; ++q) off += A[p * n + q] * A[p * n + q];
+    if (off == 0.0) break;
+    for (int p = 0; p < n - 1; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        const double apq = A[p * n + q];
+        if (apq == 0.0) continue;
+        const double theta = (A[q * n + q] - A[p * n + p]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < n; ++k) {
+          const double akp = A[k * n + p], akq = A[k * n + q];
+          A[k * n + p] = c * akp - sn * akq;
+          A[k * n + q] = sn * akp + c * akq;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double apk = A[p * n + k], aqk = A[q * n + k];
+          A[p * n + k] = c * apk - sn * aqk;
+          A[q * n + k] = sn * apk + c * aqk;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double vkp = V[k * n + p], vkq = V[k * n + q];
+          V[k * n + p] = c * vkp - sn * vkq;
+          V[k * n + q] = sn * vkp + c * vkq;
+        }
+      }
+  }
+}
+__device__ __forceinline__ double block_sum(double v, double* red, int tid) {     // red: [RS_THREADS / 32 + 1]
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0;
+    for (int w = 0; w < RS_THREADS / 32; ++w) s += red[w];
+    red[RS_THREADS / 32] = s;
+  }
+  __syncthreads();
+  return red[RS_THREADS / 32];
+}
+// Whole block; msk selects the points.  Returns true and writes F (shared or global, 9 doubles) on success.
+__device__ bool eight_point_refit(const float2* __restrict__ p1, const float2* __restrict__ p2, const uint8_t* msk,
+                                  int M, double* Fout, double* sA /* [81 + 81 + 8] shared */, int tid) {
+  double* red = sA + 162;
+  double cnt_d = 0, sx1 = 0, sy1 = 0, sx2 = 0, sy2 = 0;
+  for (int i = tid; i < M; i += RS_THREADS)
+    if (msk[i]) { cnt_d += 1.0; sx1 += p1[i].x; sy1 += p1[i].y; sx2 += p2[i].x; sy2 += p2[i].y; }
+  const double cnt = block_sum(cnt_d, red, tid);
+  if (cnt < 8.0) return false;
+  const double t = 1.0 / cnt;
+  const double cx1 = block_sum(sx1, red, tid) * t, cy1 = block_sum(sy1, red, tid) * t;
+  const double cx2 = block_sum(sx2, red, tid) * t, cy2 = block_sum(sy2, red, tid) * t;
+  double d1 = 0, d2 = 0;
+  for (int i = tid; i < M; i += RS_THREADS)
+    if (msk[i]) {
+      const double x1 = p1[i].x - cx1, y1 = p1[i].y - cy1, x2 = p2[i].x - cx2, y2 = p2[i].y - cy2;
+      d1 += sqrt(x1 * x1 + y1 * y1);
+      d2 += sqrt(x2 * x2 + y2 * y2);
+    }
+  double sc1 = block_sum(d1, red, tid) * t, sc2 = block_sum(d2, red, tid) * t;
+  if (sc1 < static_cast<double>(FLT_EPSILON) || sc2 < static_cast<double>(FLT_EPSILON)) return false;
+  sc1 = sqrt(2.0) / sc1; sc2 = sqrt(2.0) / sc2;
+  // upper triangle of the 9 x 9 normal matrix, 45 entries per thread, block-reduced entry by entry
+  double a[45];
+#pragma unroll
+  for (int e = 0; e < 45; ++e) a[e] = 0.0;
+  for (int i = tid; i < M; i += RS_THREADS)
+    if (msk[i]) {
+      const double x1 = (p1[i].x - cx1) * sc1, y1 = (p1[i].y - cy1) * sc1;
+      const double x2 = (p2[i].x - cx2) * sc2, y2 = (p2[i].y - cy2) * sc2;
+      const double r[9] = {x2 * x1, x2 * y1, x2, y2 * x1, y2 * y1, y2, x1, y1, 1.0};
+      int e = 0;
+#pragma unroll
+      for (int j = 0; j < 9; ++j)
+#pragma unroll
+        for (int k = j; k < 9; ++k) a[e++] += r[j] * r[k];
+    }
+  {
+    int e = 0;
+#pragma unroll
+    for (int j = 0; j < 9; ++j)
+#pragma unroll
+      for (int k = j; k < 9; ++k) {
+        const double v = block_sum(a[e++], red, tid);
+        if (tid == 0) { sA[j * 9 + k] = v; sA[k * 9 + j] = v; }
+      }
+  }
+  __syncthreads();
+  __shared__ int sOk;
+  if (tid == 0) {
+    double* A = sA;
+    double* V = sA + 81;
+    jacobi_sym(A, V, 9, 60);
+    int lo = 0, nz = 0;
+    for (int i = 0; i < 9; ++i) {
+      if (A[i * 9 + i] < A[lo * 9 + lo]) lo = i;
+      if (fabs(A[i * 9 + i]) < DBL_EPSILON) ++nz;
+    }
+    sOk = nz > 1 ? 0 : 1;
+    if (sOk) {
+      double F0[9], G[9], W[9];
+      for (int i = 0; i < 9; ++i) F0[i] = V[i * 9 + lo];
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+        double sacc = 0;
+        for (int k = 0; k < 3; ++k) sacc += F0[k * 3 + i] * F0[k * 3 + j];
+        G[i * 3 + j] = sacc;
+      }
+      jacobi_sym(G, W, 3, 60);
+      int l3 = 0;
+      for (int i = 1; i < 3; ++i) if (G[i * 3 + i] < G[l3 * 3 + l3]) l3 = i;
+      const double v[3] = {W[0 * 3 + l3], W[1 * 3 + l3], W[2 * 3 + l3]};
+      for (int i = 0; i < 3; ++i) {
+        const double fv = F0[i * 3] * v[0] + F0[i * 3 + 1] * v[1] + F0[i * 3 + 2] * v[2];
+        for (int j = 0; j < 3; ++j) F0[i * 3 + j] -= fv * v[j];
+      }
+      const double T1[9] = {sc1, 0, -sc1 * cx1, 0, sc1, -sc1 * cy1, 0, 0, 1};
+      const double T2[9] = {sc2, 0, -sc2 * cx2, 0, sc2, -sc2 * cy2, 0, 0, 1};
+      double X[9], Fr[9];
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+        double sacc = 0;
+        for (int k = 0; k < 3; ++k) sacc += T2[k * 3 + i] * F0[k * 3 + j];
+        X[i * 3 + j] = sacc;
+      }
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+        double sacc = 0;
+        for (int k = 0; k < 3; ++k) sacc += X[i * 3 + k] * T1[k * 3 + j];
+        Fr[i * 3 + j] = sacc;
+      }
+      if (fabs(Fr[8]) > static_cast<double>(FLT_EPSILON)) { const double inv = 1.0 / Fr[8]; for (int i = 0; i < 9; ++i) Fr[i] *= inv; }
+      for (int i = 0; i < 9; ++i) Fout[i] = Fr[i];
+    }
+  }
+  __syncthreads();
+  return sOk != 0;
+}
+
+// PHILOX is a template parameter and the refit a kernel of its own (fmat_refit8_kernel): compiled into the one hot
+// kernel, the sampler's local arrays and the refit's Jacobi sweeps cost the OpenCV-replay path 16x (measured).
+template <bool PHILOX>
 __global__ void __launch_bounds__(RS_THREADS, 512 / RS_THREADS)
 fmat_ransac_kernel(const float2* __restrict__ pts1, const float2* __restrict__ pts2,
                    const int32_t* __restrict__ count, int stride, RansacDev prm,
                    uint8_t* __restrict__ mask, double* __restrict__ F_out,
                    int32_t* __restrict__ status, int32_t* __restrict__ n_inliers,
-                   int32_t* __restrict__ iters_out) {
+                   int32_t* __restrict__ iters_out, const PairJob* __restrict__ jobs) {
   const int slot = blockIdx.x;
   const size_t base = static_cast<size_t>(slot) * stride;
   const float2* p1 = pts1 + base;
@@ -529,6 +716,8 @@ fmat_ransac_kernel(const float2* __restrict__ pts1, const float2* __restrict__ p
   if (tid == 0) { sRng = ~0ull; sIter = 0; sNiters = prm.max_iters; sBest = 0; sStop = 0; }
   __syncthreads();
   const unsigned int inv_m = 0xFFFFFFFFu / static_cast<unsigned int>(M);
+  const unsigned long long pkey = jobs ? ((static_cast<unsigned long long>(jobs[slot].seed_hi) << 32) | jobs[slot].seed_lo)
+                                       : prm.seed;
   // margin of the conservative classifier (see classify()): scaled by the largest |coordinate| of the pair
   __shared__ float sCmax;
   if (tid == 0) sCmax = 0.f;
@@ -554,6 +743,20 @@ fmat_ransac_kernel(const float2* __restrict__ pts1, const float2* __restrict__ p
   while (true) {
     // ---- sample: the sequential index stream (one thread), then the collinearity test of every
     //      subset in parallel; a rejected subset (rare) re-plays the stream from its start -------------
+    if constexpr (PHILOX) {
+      // free-running sampler: thread g draws the subset of iteration sIter + g on its own (collinearity test included)
+      if (tid == 0) sBad = 0x7fffffff;
+      __syncthreads();
+      const int want = min(round_size, sNiters - sIter);
+      if (tid < want && !philox_subset(p1, p2, M, pkey, sIter + tid, sSub[tid])) atomicMin(&sBad, tid);
+      __syncthreads();
+      if (tid == 0) {
+        sGen = sBad < want ? sBad : (want > 0 ? want : 0);       // no admissible subset: stop there (OpenCV's rule)
+        if (sBad < want) sStop = 1;
+        sBad = 0x7fffffff;
+      }
+      __syncthreads();
+    } else {
     if (tid == 0) {
       MwcRng rng{sRng};
       int g = 0;
@@ -572,6 +775,7 @@ fmat_ransac_kernel(const float2* __restrict__ pts1, const float2* __restrict__ p
       if (pair_collinear(t < 15 ? p1 : p2, sSub[h], t < 15 ? t : t - 15)) atomicMin(&sBad, h);
     }
     __syncthreads();
+    }
     if (sBad < sGen) {
       if (tid == 0) {
         MwcRng rng{sState[sBad]};
@@ -703,16 +907,42 @@ fmat_ransac_kernel(const float2* __restrict__ pts1, const float2* __restrict__ p
   }
 }
 
+// Optional refit (pm_params.refit_8point): F of every filtered pair with >= 8 inliers is replaced by the normalised
+// 8-point estimate over its inliers; mask, counts and status stay those of the winning RANSAC hypothesis.
+__global__ void __launch_bounds__(RS_THREADS)
+fmat_refit8_kernel(const float2* __restrict__ pts1, const float2* __restrict__ pts2, const int32_t* __restrict__ count,
+                   int stride, const uint8_t* __restrict__ mask, double* __restrict__ F_out,
+                   const int32_t* __restrict__ status, const int32_t* __restrict__ n_inliers) {
+  const int slot = blockIdx.x;
+  if (status[slot] != 1 || n_inliers[slot] < 8) return;          // uniform over the block
+  __shared__ double sA[81 + 81 + 8];
+  __shared__ double sFr[9];
+  const size_t base = static_cast<size_t>(slot) * stride;
+  const int tid = threadIdx.x;
+  const bool ok = eight_point_refit(pts1 + base, pts2 + base, mask + base, count[slot], sFr, sA, tid);
+  if (ok && tid < 9) F_out[9 * slot + tid] = sFr[tid];
+}
+
 cudaError_t ransac_configure() {
-  return cudaFuncSetAttribute(fmat_ransac_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaError_t e = cudaFuncSetAttribute(fmat_ransac_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(fmat_ransac_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 cudaError_t launch_ransac(const float2* pts1, const float2* pts2, const int32_t* count, int n_jobs,
                           int stride, const RansacDev& prm, uint8_t* mask, double* F,
-                          int32_t* status, int32_t* n_inliers, int32_t* iters, cudaStream_t st) {
+                          int32_t* status, int32_t* n_inliers, int32_t* iters, cudaStream_t st,
+                          const PairJob* jobs) {
   if (n_jobs <= 0) return cudaSuccess;
-  fmat_ransac_kernel<<<n_jobs, RS_THREADS, 0, st>>>(pts1, pts2, count, stride, prm, mask, F, status,
-                                                    n_inliers, iters);
+  if (prm.sampler == 1)
+    fmat_ransac_kernel<true><<<n_jobs, RS_THREADS, 0, st>>>(pts1, pts2, count, stride, prm, mask, F, status, n_inliers,
+                                                            iters, jobs);
+  else
+    fmat_ransac_kernel<false><<<n_jobs, RS_THREADS, 0, st>>>(pts1, pts2, count, stride, prm, mask, F, status, n_inliers,
+                                                             iters, jobs);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || !prm.refit_8point || !prm.do_filter) return e;
+  fmat_refit8_kernel<<<n_jobs, RS_THREADS, 0, st>>>(pts1, pts2, count, stride, mask, F, status, n_inliers);
   return cudaGetLastError();
 }
 

@@ -193,5 +193,26 @@ def main():
     print(man)
 
 
+def gen_eight_point():
+    """cv2.findFundamentalMat(FM_8POINT) over the inliers of cv2's own RANSAC mask, for the scenes of
+    fmat_scenes.npz (pins the optional normalised 8-point refit, pm_params.refit_8point)."""
+    z = np.load(os.path.join(HERE, "fmat_scenes.npz"))
+    out = {}
+    for k in range(int(z["n_scenes"])):
+        if not int(z[f"s{k}_ok"]):
+            continue
+        p1, p2, mask = z[f"s{k}_p1"], z[f"s{k}_p2"], z[f"s{k}_mask"].astype(bool)
+        if p1.shape[0] < 15 or mask.sum() < 8:
+            continue
+        F, _ = cv2.findFundamentalMat(p1[mask], p2[mask], cv2.FM_8POINT)
+        if F is not None and F.shape == (3, 3):
+            out[f"s{k}_F8"] = F
+    out["scenes"] = np.array(sorted(int(k[1:-3]) for k in out if k.endswith("_F8")), np.int32)
+    out["cv2_version"] = np.array(cv2.__version__)
+    np.savez_compressed(os.path.join(HERE, "eight_point.npz"), **out)
+
+
 if __name__ == "__main__":
-    main()
+    if "--eight-point" not in sys.argv:      # --eight-point: only (re)generate eight_point.npz from the committed scenes
+        main()
+    gen_eight_point()

@@ -4,6 +4,7 @@ Bar: bit-exact for integer / byte / index work (Hamming, integer-valued SIFT, ma
 inlier masks); L2 distances of real-valued descriptors within 1e-5 relative (tolerance of the
 north star), their indices equal to the fp64 brute force except at fp64 near-ties (< 1e-6 rel).
 """
+import ctypes as C
 import os
 
 import numpy as np
@@ -558,6 +559,17 @@ def test_float_tensor_full_size_superpoint():
     for r in np.nonzero((knn_rows[0][0] != oi).any(axis=1))[0]:
         assert abs(o2[r, 1] - o2[r, 0]) <= 1e-6 * o2[r, 1]
     assert outs[0]["offsets"][-1] > 6 * 1500
+    # the batched CSR of full-size pairs against the oracle's pair body (fp64 arbiter for the kNN stage), one clean
+    # pair and one with 30 % outliers
+    for p, (i, j) in enumerate(outs[0]["pair_ij"]):
+        if (i, j) not in ((0, 1), (1, 2)):
+            continue
+        ref = orc.match_pair(imgs[i][0], imgs[i][1], imgs[j][0], imgs[j][1])
+        a, b = outs[0]["offsets"][p], outs[0]["offsets"][p + 1]
+        keep = outs[0]["inlier"][a:b].astype(bool)
+        assert ref["status"] == "ok" and outs[0]["status"][p] == api.PAIR_FILTERED
+        assert b - a == ref["n_putative"], (i, j, b - a, ref["n_putative"])
+        assert np.array_equal(outs[0]["q"][a:b][keep], ref["q"]) and np.array_equal(outs[0]["t"][a:b][keep], ref["t"])
 
 
 # ---------------------------------------------------------------------------------------------
@@ -804,6 +816,8 @@ def test_async_ingest_gives_identical_results(kind):
 # real-valued rows quantised to s8 on kind::i8 (default batched SuperPoint path without cross-check) vs fp16 forms
 # ---------------------------------------------------------------------------------------------
 FORCE_FP16_FORMS = 1 << 15
+S8_ONE_ROW_SET = 1 << 19          # the s8 candidate kernel with one query row set per cluster (default: two)
+S8_SIX_KEYS = 1 << 20             # two row sets, six chunk keys + chunk re-rank (default: argmin epilogue + one-column re-rank)
 
 
 @pytest.mark.parametrize("dim", [128, 256])
@@ -822,16 +836,16 @@ def test_s8_quantised_candidates_equal_fp16_forms_and_simt(dim, mode):
             d[11] = d[5]; d[700] = d[5]                     # duplicates: ties in the candidate scores
         imgs.append(d)
     outs = []
-    for flags in (0, FORCE_FP16_FORMS, 1):
+    for flags in (0, FORCE_FP16_FORMS, 1, S8_ONE_ROW_SET, S8_SIX_KEYS):
         with api.PairMatcher(unique_mode=mode, batch_pairs=4, do_filter=0, debug_flags=flags) as pm:
             for i, d in enumerate(imgs):
                 pm.set_image(i, d)
             outs.append(pm.match_all_pairs())
             st = pm.stats()
-        if flags == 0 and mode != api.MUTUAL_NN:
+        if flags in (0, S8_ONE_ROW_SET, S8_SIX_KEYS) and mode != api.MUTUAL_NN:
             assert st["rerank_rows"] > 0 and st["rerank_worst_err"] < 1.0, st
-    _csr_equal(outs[0], outs[1], ("offsets", "q", "t", "status"))
-    _csr_equal(outs[0], outs[2], ("offsets", "q", "t", "status"))
+    for o in outs[1:]:
+        _csr_equal(outs[0], o, ("offsets", "q", "t", "status"))
     assert outs[0]["offsets"][-1] > 300
 
 
@@ -854,14 +868,15 @@ def test_s8_quantised_fallback_on_large_entries_and_full_size():
     w = synth.World("superpoint", 8192, seed=0xB200 + 9)
     imgs = [w.image(i, 100, outlier_frac=0.3 if i == 1 else 0.0)[:2] for i in range(4)]
     outs = []
-    for flags in (0, FORCE_FP16_FORMS):
+    for flags in (0, FORCE_FP16_FORMS, S8_ONE_ROW_SET, S8_SIX_KEYS):
         with api.PairMatcher(debug_flags=flags) as pm:
             for i, (d, xy) in enumerate(imgs):
                 pm.set_image(i, d, xy)
             outs.append(pm.match_all_pairs())
             st = pm.stats()
         assert st["rerank_worst_err"] < 1.0, st
-    _csr_equal(outs[0], outs[1])
+    for o in outs[1:]:
+        _csr_equal(outs[0], o)
     assert outs[0]["offsets"][-1] > 6 * 1000
 
 
@@ -975,3 +990,172 @@ def test_cache_resume_gives_identical_results(kind, tmp_path):
         pm.load_images(alt)
         third = pm.match_all_pairs()
     assert np.array_equal(first["q"], third["q"]) and np.array_equal(first["t"], third["t"])
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: Philox sampler + seed, 8-point refit, boundary behaviour (SURVEY 8b / 8c leg 5)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("resid", [api.RESID_SYMMETRIC_EPIPOLAR, api.RESID_SAMPSON])
+def test_philox_sampler_masks_identical_to_cpu_filter(scenes, resid):
+    """'with any other sampler: GPU <-> CPU-filter identity'.  Same Philox key -> same hypothesis stream ->
+    identical masks, iteration counts and F."""
+    n_sc = int(scenes["n_scenes"])
+    checked = 0
+    with api.PairMatcher(sampler=api.SAMPLER_PHILOX, residual_mode=resid, seed=5) as pm:
+        for k in range(n_sc):
+            p1, p2 = scenes[f"s{k}_p1"], scenes[f"s{k}_p2"]
+            for key in (0, 0xB200, 2**63 + 12345 + k):
+                F, mask, st, it = pm.estimate_fundamental(p1, p2, pair_key=key)
+                prm = orc.default_params(residual_mode=resid, sampler=orc.SAMPLER_PHILOX, seed=key)
+                ns, Fo, mo, tr = orc.find_fundamental(p1, p2, prm)
+                assert (st == api.PAIR_FILTERED) == (ns > 0), (k, key)
+                if ns > 0:
+                    assert np.array_equal(mask, mo), (k, key, int(mask.sum()), int(mo.sum()))
+                    if p1.shape[0] > 7:
+                        assert it == tr.iters_run, (k, key, it, tr.iters_run)
+                        np.testing.assert_allclose(F, Fo[0], rtol=0, atol=1e-9 * max(1.0, np.abs(Fo[0]).max()))
+                    checked += 1
+        # pm_filter_pair_F without an explicit key uses pm_params.seed
+        p1, p2 = scenes["s30_p1"], scenes["s30_p2"]
+        a = pm.estimate_fundamental(p1, p2)
+        b = pm.estimate_fundamental(p1, p2, pair_key=5)
+        assert np.array_equal(a[1], b[1]) and a[3] == b[3]
+    assert checked >= 150
+
+
+def test_philox_batched_loop_uses_pair_keys_and_is_partition_invariant():
+    """Per-pair key = f(seed, i, j): the batched result equals the CPU pair body run with orc.pair_seed, whatever the
+    batch size or the order / subset of the pair list (a pair's result does not depend on who ran it)."""
+    w = synth.World("sift", 700, seed=91)
+    imgs = [w.image(i, 6, outlier_frac=0.4)[:2] for i in range(5)]
+    assert api.pair_seed(77, 1, 3) == orc.pair_seed(77, 1, 3)
+    outs = []
+    for bp, order in ((0, None), (3, None), (2, "rev")):
+        with api.PairMatcher(sampler=api.SAMPLER_PHILOX, seed=77, batch_pairs=bp) as pm:
+            for i, (d, xy) in enumerate(imgs):
+                pm.set_image(i, d, xy)
+            pairs = np.array([(i, j) for j in range(5) for i in range(j)], np.int32)
+            if order == "rev":
+                pairs = pairs[::-1].copy()
+            outs.append(pm.match_all_pairs(pairs))
+    res = outs[0]
+    for p, (i, j) in enumerate(res["pair_ij"]):
+        prm = orc.default_params(sampler=orc.SAMPLER_PHILOX, seed=orc.pair_seed(77, int(i), int(j)))
+        ref = orc.match_pair(imgs[i][0], imgs[i][1], imgs[j][0], imgs[j][1], params=prm)
+        a, b = res["offsets"][p], res["offsets"][p + 1]
+        keep = res["inlier"][a:b].astype(bool)
+        assert ref["status"] == "ok" and res["status"][p] == api.PAIR_FILTERED
+        assert np.array_equal(res["q"][a:b][keep], ref["q"]) and np.array_equal(res["t"][a:b][keep], ref["t"]), (i, j)
+    _csr_equal(outs[0], outs[1])
+    rev = outs[2]
+    for p, (i, j) in enumerate(res["pair_ij"]):
+        r = len(res["pair_ij"]) - 1 - p
+        assert tuple(rev["pair_ij"][r]) == (i, j)
+        assert np.array_equal(rev["inlier"][rev["offsets"][r]:rev["offsets"][r + 1]],
+                              res["inlier"][res["offsets"][p]:res["offsets"][p + 1]])
+        assert rev["ransac_iters"][r] == res["ransac_iters"][p]
+
+
+def test_eight_point_refit_matches_cpu_filter_and_cv2(scenes, golden_dir):
+    g8 = np.load(os.path.join(golden_dir, "eight_point.npz"))
+    prm = orc.default_params(refit_8point=1)
+    with api.PairMatcher(refit_8point=1) as pm, api.PairMatcher() as pm0:
+        for k in g8["scenes"]:
+            p1, p2 = scenes[f"s{k}_p1"], scenes[f"s{k}_p2"]
+            F, mask, st, it = pm.estimate_fundamental(p1, p2)
+            F0, mask0, st0, it0 = pm0.estimate_fundamental(p1, p2)
+            ns, Fo, mo, tr = orc.find_fundamental(p1, p2, prm)
+            assert st == api.PAIR_FILTERED and ns == 1
+            assert np.array_equal(mask, mask0) and it == it0          # the refit changes F only
+            assert np.array_equal(mask, mo)
+            assert np.abs(F - Fo[0]).max() <= 1e-9 * np.abs(Fo[0]).max(), int(k)
+            # cv2's own FM_8POINT over the same inliers (the GPU mask equals cv2's for these scenes)
+            assert np.array_equal(mask, scenes[f"s{k}_mask"])
+            Fg = g8[f"s{k}_F8"]
+            assert np.abs(F - Fg).max() <= 1e-7 * np.abs(Fg).max(), int(k)
+    # batched loop: refit on every filtered pair, masks untouched
+    w = synth.World("orb", 600, seed=3)
+    imgs = [w.image(i, 4, outlier_frac=0.3)[:2] for i in range(4)]
+    outs = []
+    for refit in (0, 1):
+        with api.PairMatcher(refit_8point=refit) as pm:
+            for i, (d, xy) in enumerate(imgs):
+                pm.set_image(i, d, xy)
+            outs.append(pm.match_all_pairs())
+    _csr_equal(outs[0], outs[1], ("offsets", "q", "t", "inlier", "status", "n_inliers", "ransac_iters"))
+    assert not np.array_equal(outs[0]["F"], outs[1]["F"])
+    for p in range(outs[1]["n_pairs"]):
+        a, b = outs[1]["offsets"][p], outs[1]["offsets"][p + 1]
+        i, j = outs[1]["pair_ij"][p]
+        q, t, m = outs[1]["q"][a:b], outs[1]["t"][a:b], outs[1]["inlier"][a:b]
+        ok, Fo = orc.eight_point(imgs[i][1][q].astype(np.float32), imgs[j][1][t].astype(np.float32), m)
+        assert ok and np.abs(outs[1]["F"][p] - Fo).max() <= 1e-9 * np.abs(Fo).max()
+
+
+def test_failed_batched_call_leaves_no_stale_batches():
+    """an unknown image id deep in the pair list must fail the call without leaving slots busy; the next,
+    shorter call must return exactly its own pairs."""
+    w = synth.World("sift", 500, seed=12)
+    imgs = [w.image(i, 14)[:2] for i in range(14)]
+    with api.PairMatcher(batch_pairs=8) as pm:
+        for i, (d, xy) in enumerate(imgs):
+            pm.set_image(i, d, xy)
+        good = np.array([(i, j) for j in range(14) for i in range(j)], np.int32)
+        ref = pm.match_all_pairs(good)
+        bad = good.copy()
+        bad[70] = (3, 999)                                   # unknown id at pair index >= 64
+        with pytest.raises(api.PairMatchError) as e:
+            pm.match_all_pairs(bad)
+        assert e.value.code == api.ERR_STATE and "999" in str(e.value)
+        short = pm.match_all_pairs(good[:5])
+        assert short["n_pairs"] == 5
+        for k in ("q", "t", "inlier"):
+            assert np.array_equal(short[k], ref[k][:ref["offsets"][5]]), k
+        assert np.array_equal(short["offsets"], ref["offsets"][:6])
+        again = pm.match_all_pairs(good)
+        _csr_equal(again, ref)
+
+
+def test_all_pairs_sentinel_empty_list_and_remove_image():
+    w = synth.World("orb", 400, seed=8)
+    imgs = [w.image(i, 4)[:2] for i in range(4)]
+    with api.PairMatcher() as pm:
+        for i, (d, xy) in enumerate(imgs):
+            pm.set_image(i, d, xy)
+        allp = pm.match_all_pairs()                          # pairs = NULL, n_pairs = PM_ALL_PAIRS
+        assert allp["n_pairs"] == 6
+        empty = pm.match_all_pairs(np.zeros((0, 2), np.int32))
+        assert empty["n_pairs"] == 0 and len(empty["q"]) == 0
+        res = C.POINTER(api.CsrResult)()
+        assert pm.lib.pm_match_all_pairs(pm.h, None, 3, C.byref(res)) == api.ERR_INVALID
+        assert pm.lib.pm_match_all_pairs(pm.h, None, 0, C.byref(res)) == api.OK and res.contents.n_pairs == 0
+        pm.lib.pm_free_result(res)
+        # removing an image frees its rows; a later image re-uses them (the arena does not grow)
+        n_before = pm.stats()["n_images"]
+        pm.remove_image(1)
+        assert pm.stats()["n_images"] == n_before - 1
+        with pytest.raises(api.PairMatchError):
+            pm.match_pair(0, 1)
+        with pytest.raises(api.PairMatchError):
+            pm.remove_image(1)
+        pm.set_image(7, imgs[1][0], imgs[1][1])
+        again = pm.match_all_pairs(np.array([(0, 7), (7, 2), (7, 3)], np.int32))
+        ref = {(0, 1): 0, (1, 2): 3, (1, 3): 4}
+        for p, key in enumerate(((0, 1), (1, 2), (1, 3))):
+            r = ref[key]
+            assert np.array_equal(again["q"][again["offsets"][p]:again["offsets"][p + 1]],
+                                  allp["q"][allp["offsets"][r]:allp["offsets"][r + 1]])
+        # per-pair calls with growing temporary images re-use released rows too
+        for n in (50, 120, 300, 90):
+            r = pm.match_descriptors(imgs[0][0][:n], imgs[2][0][:n])
+            assert len(r["q"]) > 0
+
+
+def test_tensor_peaks_are_measured_and_plausible():
+    with api.PairMatcher() as pm:
+        f16 = pm.measure_tensor_peak(api.PEAK_KIND_F16)
+        i8 = pm.measure_tensor_peak(api.PEAK_KIND_I8)
+        fp4 = pm.measure_tensor_peak(api.PEAK_KIND_MXF4)
+    print("tensor peaks TFLOP/s: f16 %.0f  i8 %.0f  mxf4 %.0f" % (f16 / 1e12, i8 / 1e12, fp4 / 1e12))
+    assert 0.8e15 < f16 < 2.6e15 and 1.6e15 < i8 < 5.2e15 and 3.0e15 < fp4 < 10.5e15
+    assert 1.6 < i8 / f16 < 2.4 and 1.5 < fp4 / i8 < 2.4
