@@ -1,20 +1,30 @@
 #!/usr/bin/env python
 """bench.py -- image pairs/sec of the exhaustive pair-matching path (kNN k=2 + ratio + uniqueness +
-F-matrix RANSAC) on synthetic descriptor sets of BASELINE.json's shape.
+F-matrix RANSAC) on synthetic descriptor sets of BASELINE.json's shapes.
 
   python bench.py --gpus N --steps K --warmup W            our CUDA path (one process per GPU)
   python bench.py --impl reference --gpus N --steps K ...  the reference's CPU path (cv2 FLANN +
                                                            findFundamentalMat) on the host cores
 
-A step = one pass of the whole pair loop over the workload:
+A step = one pass of the whole pair loop over a workload.
+
+Headline line (`value`, `e2e`, `roofline`, `stages`, `cpu_baseline`):
   N=1   configs[1]: 100 images x 8192 SIFT keypoints (128-d), all 4,950 pairs.
-  N>1   weak scaling: the image count grows so that every GPU keeps ~4,950 pairs; the pair list is
-        split into contiguous shares, descriptors are replicated, no data-path collective.
+  N>1   weak scaling of that config: the image count grows so that every GPU keeps ~4,950 pairs.
+`configs` (same JSON line) carries the other BASELINE.json configurations, each with value / e2e / roofline / clocks:
+  orb500          configs[2]: 500 images x 8192 ORB keypoints (256 bit), 124,750 pairs        -- STRONG scaling over N
+  superpoint1000  configs[3]: 1,000 images x 8192 SuperPoint keypoints (256-d), 499,500 pairs -- STRONG scaling over N
+`stages.ransac_heavy` is the headline workload with 50 % outlier keypoints (RANSAC runs hundreds of iterations).
+
+The pair list is split into contiguous shares (one per rank), descriptors are replicated on every GPU, the timed loop
+has no data-path collective.
 `value`  = pairs/s with descriptors resident in HBM, results delivered to host memory (CSR);
-`e2e`    = the same through the C ABI with HOST buffers: per step every image is re-ingested from
-           pinned host memory (H2D + pack) and the CSR result is read back (D2H).
-Timing: CUDA events inside the library on its own streams (pm_csr_result.device_ms), max over ranks;
-the descriptor working set (100 x 4.7 MB fp16 operand forms + 400 MB fp32) exceeds the 126 MB L2.
+`e2e`    = the same through the C ABI with HOST buffers: per step every image is re-ingested from pinned host memory
+           (N=1: H2D + pack; N>1: extraction sharded by image id mod N -- every rank uploads only its own images and
+           pm_ingest_allgather replicates them over NVLink) and the CSR result is read back (D2H).
+Timing: CUDA events inside the library on its own streams (pm_csr_result.device_ms), max over ranks; the descriptor
+working sets exceed the 126 MB L2 (no flush needed).  Roofline peaks are MEASURED in the same run with the same MMA kind
+(pm_measure_tensor_peak); MEASURED_PEAKS.json's bf16 figure is reported next to them.
 """
 from __future__ import annotations
 
@@ -35,6 +45,7 @@ from reconstructor_b200 import shard, synth  # noqa: E402
 
 METRIC = "image pairs/sec (exhaustive kNN match + epipolar RANSAC)"
 UNIT = "pairs/s"
+DIM_TXT = {"sift": "128-d float", "orb": "256-bit binary", "superpoint": "256-d float"}
 
 
 def parse():
@@ -50,12 +61,13 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--sync-ingest", action="store_true", help="e2e leg: pm_set_image instead of pm_set_image_async")
-    ap.add_argument("--no-stages", action="store_true", help="skip the matcher-only / RANSAC attribution pass")
+    ap.add_argument("--no-stages", action="store_true", help="skip the matcher-only / RANSAC attribution passes")
+    ap.add_argument("--no-configs", action="store_true", help="skip the `configs` object (ORB-500, SuperPoint-1000)")
+    ap.add_argument("--orb-images", type=int, default=500, help="configs.orb500 (BASELINE configs[2])")
+    ap.add_argument("--sp-images", type=int, default=1000, help="configs.superpoint1000 (BASELINE configs[3])")
+    ap.add_argument("--cfg-steps", type=int, default=2, help="timed steps of the `configs` / ransac_heavy workloads")
     ap.add_argument("--replicated-ingest", action="store_true", help="N > 1: every rank uploads every image from its own "
                     "host copy instead of the sharded upload + all-gather")
-    ap.add_argument("--sharded-ingest", action="store_true",
-                    help="N>1: every rank owns images k = rank mod N, descriptors are all-gathered over NCCL and "
-                         "ingested from device memory (the exchange step of sharded extraction, SURVEY 8e)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--debug-flags", type=int, default=0, help="pm_params.debug_flags (kernel variants)")
     ap.add_argument("--batch-pairs", type=int, default=0)
@@ -67,9 +79,8 @@ def parse():
     return ap.parse_args()
 
 
-def workload_name(a, n_img, n_pairs):
-    dim = {"sift": "128-d float", "orb": "256-bit binary", "superpoint": "256-d float"}[a.kind]
-    return (f"{n_img} images {a.kind.upper()} {a.kp} kp ({dim}), exhaustive {n_pairs} pairs, "
+def workload_name(kind, n_img, kp, n_pairs):
+    return (f"{n_img} images {kind.upper()} {kp} kp ({DIM_TXT[kind]}), exhaustive {n_pairs} pairs, "
             f"kNN k=2 + ratio 0.7 + first-wins uniqueness + F-RANSAC")
 
 
@@ -159,8 +170,8 @@ def cpu_arm(imgs, pairs, seconds, steps=1, warmup=0, pairs_per_step=None, worker
     return dict(value=done_pairs / tot, unit=UNIT, cores=workers,
                 kind="port",
                 sample=(f"{done_pairs} random pairs of the workload in {len(times)} steps of {n_step}, "
-                        + ("cv2 %s FLANN knnMatch(k=2)+ratio+unique+findFundamentalMat, one process per core"
-                           % cv2_ref.cv2.__version__ if use_cv2 else
+                        + ("cv2 %s FLANN knnMatch(k=2)+ratio+unique+findFundamentalMat, one process per core (the DMatch "
+                           "rows are read from Python: ~1 %% of a pair)" % cv2_ref.cv2.__version__ if use_cv2 else
                            "oracle/pm_oracle.c exact brute force + RANSAC (cv2 not importable), OpenMP")),
                 ms_per_step=1e3 * tot / max(len(times), 1), pairs_per_step=n_step)
 
@@ -181,6 +192,7 @@ class ClockSampler:
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.p = None
+        return self
 
     def _read(self):
         for line in self.p.stdout:
@@ -205,6 +217,264 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm))
 
 
+# ------------------------------------------------------------------------------------------------
+class Dist:
+    """torch.distributed plumbing: barrier, max / sum over ranks, broadcast of a few bytes."""
+
+    def __init__(self, world, rank, local):
+        import torch
+        self.torch, self.world, self.rank, self.local = torch, world, rank, local
+        torch.cuda.set_device(local)
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            self.dist = dist
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def _red(self, x, op):
+        if not self.dist:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def allmax(self, x):
+        return self._red(x, self.dist.ReduceOp.MAX) if self.dist else x
+
+    def allsum(self, x):
+        return self._red(x, self.dist.ReduceOp.SUM) if self.dist else x
+
+    def bcast_bytes(self, b: bytes | None, n: int) -> bytes:
+        if not self.dist:
+            return b
+        t = self.torch.zeros(n, dtype=self.torch.uint8, device="cuda")
+        if self.rank == 0:
+            t.copy_(self.torch.frombuffer(bytearray(b), dtype=self.torch.uint8))
+        self.dist.broadcast(t, src=0)
+        return bytes(t.cpu().numpy().tobytes())
+
+    def close(self):
+        if self.dist:
+            self.dist.destroy_process_group()
+
+
+class Workload:
+    """One image set on this rank: pinned host copies of the images this rank 'extracted', a PairMatcher, the pair share."""
+
+    def __init__(self, a, D: Dist, kind, n_img, outlier_frac, pairs, images_np=None, **pm_kw):
+        import torch
+        from reconstructor_b200 import api
+        self.a, self.D, self.kind, self.n_img, self.api = a, D, kind, n_img, api
+        self.pairs_all = pairs
+        self.mine = shard.shard_pairs(pairs, D.rank, D.world)
+        self.sharded = D.world > 1 and not a.replicated_ingest
+        own = list(range(D.rank, n_img, D.world)) if self.sharded else list(range(n_img))
+        self.own = own
+        self.dt = api.DESC_U8_BITS if kind == "orb" else api.DESC_F32
+        # integer-valued SIFT rows travel as bytes between the ranks (4x fewer bytes); the rank's own upload is fp32,
+        # what FeatDesc holds (datatypes.h:70-71)
+        self.wire = api.DESC_U8 if kind == "sift" else self.dt
+        cols = 32 if kind == "orb" else (128 if kind == "sift" else 256)
+        self.dim = 256 if kind == "orb" else cols
+        self.d_own = torch.empty((max(len(own), 1), a.kp, cols), dtype=torch.uint8 if kind == "orb" else torch.float32,
+                                 pin_memory=True)
+        self.x_own = torch.empty((max(len(own), 1), a.kp, 2), dtype=torch.int32, pin_memory=True)
+        dn, xn = self.d_own.numpy(), self.x_own.numpy()
+        w = synth.World(kind, a.kp, seed=0xB200 + 2)
+        for k, i in enumerate(own):
+            d, xy = images_np[i] if images_np is not None else w.image(i, n_img, outlier_frac)[:2]
+            dn[k] = d; xn[k] = xy
+        self.pm = api.PairMatcher(devices=[D.local], reserve_keypoints=n_img * a.kp, debug_flags=a.debug_flags,
+                                  batch_pairs=a.batch_pairs, **pm_kw)
+        if self.sharded:
+            uid = D.bcast_bytes(api.comm_unique_id() if D.rank == 0 else None, 128)
+            self.pm.comm_init(uid, D.rank, D.world)
+
+    def ingest(self, asynchronous=False, pm=None):
+        pm = pm or self.pm
+        a = self.a
+        if self.sharded:
+            pm.ingest_allgather(self.n_img, a.kp, self.dim, self.dt, self.wire, self.d_own.data_ptr(), self.x_own.data_ptr())
+            if not asynchronous:
+                pm.sync_images()
+            return
+        ids = self.own
+        if asynchronous:
+            # pm_set_images_async from pinned buffers: the uploads are queued and the first batches of pm_match_all_pairs
+            # run while the later images are still on their way (the pair list is ordered image by image)
+            pm.set_images_ptr_async(ids, [self.d_own[k].data_ptr() for k in range(len(ids))], [a.kp] * len(ids), self.dim,
+                                    self.dt, [self.x_own[k].data_ptr() for k in range(len(ids))])
+            return
+        for k, i in enumerate(ids):
+            pm.set_image_ptr(i, self.d_own[k].data_ptr(), a.kp, self.dim, self.dt, self.x_own[k].data_ptr())
+
+    def run_resident(self, steps, warmup, sample_clocks=True):
+        """Device-timed steps with the images resident.  Returns dict(ms_per_step, wall_ms_per_step, stats, clocks, ...)."""
+        pm, D = self.pm, self.D
+        for _ in range(warmup):
+            r = pm.match_all_pairs(self.mine, copy=False); pm.free_result(r)
+        sampler = ClockSampler(D.local).start() if (D.rank == 0 and sample_clocks) else None
+        D.barrier()
+        pm.reset_stats()
+        dev_ms = 0.0
+        matches = inliers = 0
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            r = pm.match_all_pairs(self.mine, copy=False)
+            dev_ms += r["device_ms"]
+            matches = int(r["offsets"][-1]); inliers = int(r["n_inliers"].sum())
+            pm.free_result(r)
+        D.barrier()
+        wall_ms = 1e3 * (time.perf_counter() - t0)
+        clocks = sampler.stop() if sampler else None
+        st = pm.stats()
+        return dict(ms_per_step=D.allmax(dev_ms) / steps, wall_ms_per_step=D.allmax(wall_ms) / steps, stats=st, clocks=clocks,
+                    launches=D.allsum(st["kernel_launches"]), matches=matches, inliers=inliers)
+
+    def run_e2e(self, steps, warm=True):
+        pm, D, a = self.pm, self.D, self.a
+        use_async = not a.sync_ingest
+        if warm:
+            self.ingest(use_async); r = pm.match_all_pairs(self.mine, copy=False); pm.free_result(r)
+        D.barrier()
+        pm.reset_stats()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            self.ingest(use_async)
+            r = pm.match_all_pairs(self.mine, copy=False)
+            _ = int(r["n_inliers"].sum())                     # the step's result is read on the host
+            pm.free_result(r)
+        D.barrier()
+        e_ms = D.allmax(1e3 * (time.perf_counter() - t0)) / steps
+        st2 = pm.stats()
+        out = dict(value=len(self.pairs_all) / (e_ms * 1e-3), unit=UNIT, ms_per_step=e_ms,
+                   h2d_bytes_per_step=int(D.allsum(st2["h2d_bytes"]) / steps),
+                   d2h_bytes_per_step=int(D.allsum(st2["d2h_bytes"]) / steps),
+                   timing="host wall clock around %s + pm_match_all_pairs, max over ranks" %
+                          ("pm_ingest_allgather (own images H2D, NCCL all-gather in the wire dtype, device ingest)" if self.sharded
+                           else "pm_set_images_async" if use_async else "pm_set_image x images"))
+        if self.sharded:
+            row = {self.api.DESC_F32: 4 * self.dim, self.api.DESC_U8: self.dim, self.api.DESC_U8_BITS: self.dim // 8}[self.wire]
+            out["allgather_bytes_per_step"] = int(self.n_img * a.kp * (row + 8) * (D.world - 1))
+            out["wire_dtype"] = {self.api.DESC_F32: "f32", self.api.DESC_U8: "u8", self.api.DESC_U8_BITS: "bits"}[self.wire]
+        return out
+
+    def close(self):
+        self.pm.close()
+        self.d_own = self.x_own = None
+
+
+# ------------------------------------------------------------------------------------------------
+def kernel_name(kind, flags):
+    if kind == "sift":
+        return "l2_top2_tc2_kernel" if (flags & (2048 | 16384)) else "l2_i8x2_kernel"
+    if kind == "orb":
+        form = orb_form(flags)
+        return {"popc": "hamming_top2_kernel", "e4m3": "l2_top2_tc2_kernel<T2Cfg<256,2,2>,2,false,1>",
+                "i8": "l2_i8x2_kernel<2,false,2,0>", "fp4": "l2_i8x2_kernel<2,false,1,1>"}[form]
+    if flags & 32768:
+        return "l2_top2_tc2_kernel<T2Cfg<256,2,4>,3>"
+    if flags & 524288:
+        return "l2_top2_tc2_kernel<T2Cfg<256,2,2>,3,true,3>"
+    return "l2_i8x2_kernel<3,2,2,0,3>" if (flags & 1048576) else "l2_i8x2_kernel<4,2,2,0,3>"
+
+
+def orb_form(flags):
+    return "popc" if (flags & 1024) else "e4m3" if (flags & 65536) else "i8" if (flags & 262144) else "fp4"
+
+
+_PEAK_CACHE = {}
+
+
+def measured_peak(pm, api, kind_id):
+    """FLOP/s of the pure tcgen05.mma issue loop of one MMA kind, measured once per process."""
+    if kind_id not in _PEAK_CACHE:
+        _PEAK_CACHE[kind_id] = pm.measure_tensor_peak(kind_id)
+    return _PEAK_CACHE[kind_id]
+
+
+def roofline(wl: Workload, res, peaks, world):
+    """Roofline of the dominant (kNN) kernel of a resident run: algorithmic work / CUDA-event time of its launches."""
+    a, api, pm, st = wl.a, wl.api, wl.pm, res["stats"]
+    kind, flags = wl.kind, a.debug_flags
+    knn_s = max(st["knn_ms"] * 1e-3, 1e-12)
+    bf16 = peaks.get("bf16_tflops_sustained")
+    if kind == "orb" and orb_form(flags) == "popc":
+        pk = pm.measure_popc_peak()
+        roof = dict(bound="popc", achieved=st["knn_work"] / knn_s / 1e12, peak=pk / 1e12, unit="Tpopc32/s",
+                    peak_source="measured live: pm_measure_popc_peak (dependent-chain POPC micro-benchmark)")
+    else:
+        if kind == "orb":
+            # Hamming = |a| + |b| - 2 a.b on the tensor cores; one popc32 of the fixed numerator (SURVEY 8d) = 32 bit
+            # compares = 64 FLOP of the contraction
+            form = orb_form(flags)
+            ach = 64.0 * st["knn_work"] / knn_s / 1e12
+            kid, kname = (api.PEAK_KIND_MXF4, "kind::mxf4") if form == "fp4" else (api.PEAK_KIND_I8, "kind::i8 (= kind::f8f6f4 rate)")
+            ops = {"fp4": "E2M1 {0, +-1} values on tcgen05 kind::mxf4 (64 values of K per instruction, all-ones scale factors), "
+                          "f32 accumulate, exact integers", "i8": "u8 x s8 on tcgen05 kind::i8, s32 accumulate",
+                   "e4m3": "E4M3 {0,1} values on tcgen05 kind::f8f6f4, f32 accumulate, exact integers"}[form]
+        else:
+            ach = st["knn_work"] / knn_s / 1e12
+            fp16 = (kind == "sift" and (flags & 2048)) or (kind == "superpoint" and (flags & 32768))
+            kid, kname = (api.PEAK_KIND_F16, "kind::f16") if fp16 else (api.PEAK_KIND_I8, "kind::i8")
+            ops = ("f16 operands, f32 accumulate" if fp16 else
+                   "u8 x s8 -> s32 (exact integers)" if kind == "sift" else
+                   "rows quantised to s8 for the candidate stage (s8 x s8 -> s32); the exact fp32 re-rank follows")
+        pk = measured_peak(pm, api, kid) / 1e12
+        roof = dict(bound="tensor", achieved=ach, peak=pk, unit="TFLOP/s", operands=ops,
+                    peak_source=f"measured live in this run: pm_measure_tensor_peak({kname}) -- the tcgen05.mma issue loop of the "
+                                "kernel (cta_group::2, M=256, operands resident in shared memory), nothing else",
+                    bf16_sustained_peak=bf16, frac_of_bf16_sustained=(ach / bf16) if bf16 else None,
+                    bf16_peak_source="MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS, other MMA kind: a frac above 1 is expected "
+                                     "for kind::i8 (2x) and kind::mxf4 (4x))")
+        if kind == "orb":
+            roof["popc32_equiv"] = dict(achieved=st["knn_work"] / knn_s / 1e12, unit="Tpopc32/s",
+                                        note="the XOR/popc kernel of the north star (--debug-flags 1024) is bounded by the popc pipe")
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["kernel"] = kernel_name(kind, flags)
+    roof["launches"] = st["knn_launches"]
+    roof["avg_launch_ms"] = st["knn_ms"] / max(st["knn_launches"], 1)
+    roof["share_of_step"] = st["knn_ms"] / max(res["ms_per_step"] * max(res.get("steps", 1), 1), 1e-9) if world == 1 else None
+    if kind == "superpoint":
+        roof["rerank"] = {k[7:]: st[k] for k in st if k.startswith("rerank_")}
+    roof["traffic"] = None
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(roof["kernel"])
+        if t:
+            pairs_per_launch = len(wl.mine) * max(res.get("steps", 1), 1) / max(st["knn_launches"], 1)
+            roof["traffic"] = t["bytes_per_launch"] * pairs_per_launch / t["pairs_per_launch"]
+            roof["traffic_source"] = t["source"]
+    except Exception:
+        pass
+    return roof
+
+
+def run_config(a, D, peaks, kind, n_img, outlier_frac, steps, warmup, e2e_steps, tag):
+    """One entry of `configs`: the whole job on all N GPUs (strong scaling)."""
+    pairs = shard.all_pairs(n_img)
+    t0 = time.perf_counter()
+    wl = Workload(a, D, kind, n_img, outlier_frac, pairs)
+    t_gen = time.perf_counter() - t0
+    wl.ingest()
+    res = wl.run_resident(steps, warmup)
+    res["steps"] = steps
+    roof = roofline(wl, res, peaks, D.world)
+    e2e = wl.run_e2e(e2e_steps, warm=False) if e2e_steps > 0 else None
+    wl.close()
+    return dict(tag=tag, workload=workload_name(kind, n_img, a.kp, len(pairs)), kind=kind, images=n_img, keypoints=a.kp,
+                pairs=int(len(pairs)), n_gpus=D.world, scaling="strong", outlier_frac=outlier_frac,
+                value=len(pairs) / (res["ms_per_step"] * 1e-3), unit=UNIT, ms_per_step=res["ms_per_step"],
+                wall_ms_per_step=res["wall_ms_per_step"], steps=steps, warmup=warmup, putative_matches_per_step=res["matches"]
+                if D.world == 1 else None, e2e=e2e, roofline=roof, clocks=res["clocks"], gpu_launches=int(res["launches"]),
+                setup_s=round(t_gen, 1))
+
+
 def main():
     a = parse()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -219,7 +489,7 @@ def main():
         # pairs are iid here, so a random sample of the list is a steady-state sample of the whole job; sorted so that
         # the list keeps its image-by-image order
         pairs = pairs[np.sort(np.random.default_rng(0xB200).choice(n_all, a.max_pairs, replace=False))]
-    cfg = dict(workload=workload_name(a, n_img, n_all), images=n_img, keypoints=a.kp, kind=a.kind,
+    cfg = dict(workload=workload_name(a.kind, n_img, a.kp, n_all), images=n_img, keypoints=a.kp, kind=a.kind,
                pairs=int(len(pairs)), partition=f"pairs sharded over {n_gpus} GPU(s), descriptors replicated",
                l2="inputs larger than L2 (no flush needed)", outlier_frac=a.outlier_frac,
                debug_flags=a.debug_flags)
@@ -243,211 +513,59 @@ def main():
         print(json.dumps(line))
         return
 
-    # ---- CPU baseline first (fork before any CUDA context exists), rank 0 at N=1 only -----------
-    cpu = None
-    w = synth.World(a.kind, a.kp, seed=0xB200 + 2)
-    # N > 1: every rank uploads only its own share of the images and the rest arrives by one NCCL all-gather over
-    # NVLink (the exchange step of sharded extraction) -- replicating the upload would push the whole
-    # descriptor set through every rank's PCIe link each step (measured at N = 8: 24 ms of a 73 ms e2e step)
+    # ---- headline images as numpy first: the CPU baseline forks before any CUDA context exists (rank 0, N=1) -------
     sharded = world > 1 and not a.replicated_ingest
-    n_local = -(-n_img // world)                       # images per rank when extraction is sharded
-    own_ids = list(range(rank, n_local * world, world)) if sharded else list(range(n_img))
-    imgs = [w.image(i, n_img, a.outlier_frac)[:2] for i in own_ids]
+    w = synth.World(a.kind, a.kp, seed=0xB200 + 2)
+    own_ids = list(range(rank, n_img, world)) if sharded else list(range(n_img))
+    images_np = {i: w.image(i, n_img, a.outlier_frac)[:2] for i in own_ids}
+    cpu, flann = None, None
     if n_gpus == 1 and rank == 0 and not a.no_cpu_baseline:
         sub_ids = list(range(min(n_img, 24)))
         sub = np.array([(i, j) for x, i in enumerate(sub_ids) for j in sub_ids[x + 1:]], np.int32)
-        r = cpu_arm({i: imgs[i] for i in sub_ids}, sub, a.cpu_seconds)
+        r = cpu_arm({i: images_np[i] for i in sub_ids}, sub, a.cpu_seconds)
         cpu = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=r["sample"])
         if r["cores"] > 4:      # the reference's own thread cap (MAX_NUM_THREADS 4, SequentialReconstructor.h:17)
-            r4 = cpu_arm({i: imgs[i] for i in sub_ids}, sub, min(a.cpu_seconds, 6.0), workers=4)
+            r4 = cpu_arm({i: images_np[i] for i in sub_ids}, sub, min(a.cpu_seconds, 6.0), workers=4)
             cpu["at_4_workers"] = dict(value=r4["value"], unit=UNIT, cores=4, sample=r4["sample"])
-        flann = flann_samples({i: imgs[i] for i in sub_ids}, [tuple(int(x) for x in sub[k]) for k in (0, 1, len(sub) // 2, len(sub) - 1)][:len(sub)])
-    else:
-        flann = None
+        flann = flann_samples({i: images_np[i] for i in sub_ids},
+                              [tuple(int(x) for x in sub[k]) for k in (0, 1, len(sub) // 2, len(sub) - 1)][:len(sub)])
 
-    import torch
-    import torch.distributed as dist
+    D = Dist(world, rank, local)
     from reconstructor_b200 import api
-
-    torch.cuda.set_device(local)
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def allmax(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def allsum(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    mine = shard.shard_pairs(pairs, rank, world)
-    # pinned host copies of every image (what the reference-facing call is handed: float rows + int xy)
-    pinned = []
-    for d, xy in imgs:
-        td = torch.from_numpy(np.ascontiguousarray(d)).pin_memory()
-        tx = torch.from_numpy(np.ascontiguousarray(xy)).pin_memory()
-        pinned.append((td, tx))
-    dim = imgs[0][0].shape[1] * (8 if a.kind == "orb" else 1)
-    dt = api.DESC_U8_BITS if a.kind == "orb" else api.DESC_F32
-
-    dev_kw = {}
-    if a.dev_ratio is not None: dev_kw["ratio"] = a.dev_ratio
-    if a.dev_no_filter: dev_kw["do_filter"] = 0
-    pm = api.PairMatcher(devices=[local], reserve_keypoints=n_img * a.kp, debug_flags=a.debug_flags,
-                         batch_pairs=a.batch_pairs, **dev_kw)
-
-    if sharded:
-        # sharded extraction: this rank "extracted" images rank, rank + N, ...; descriptors and keypoints are
-        # all-gathered over NCCL (equal counts per image) and ingested from device memory
-        d_own = torch.stack([td for td, _ in pinned]).pin_memory()
-        x_own = torch.stack([tx for _, tx in pinned]).pin_memory()
-        cfg["partition"] += "; extraction sharded by image id mod N, one NCCL all-gather of descriptors + keypoints per step"
-
-    def ingest(asynchronous=False):
-        if not sharded:
-            # asynchronous: pm_set_image_async from pinned buffers -- the uploads are queued and the first batches
-            # of pm_match_all_pairs run while the later images are still on their way (the pair list is ordered)
-            if asynchronous:
-                pm.set_images_ptr_async(list(range(len(pinned))), [td.data_ptr() for td, _ in pinned],
-                                        [td.shape[0] for td, _ in pinned], dim, dt, [tx.data_ptr() for _, tx in pinned])
-                return
-            for i, (td, tx) in enumerate(pinned):
-                pm.set_image_ptr(i, td.data_ptr(), td.shape[0], dim, dt, tx.data_ptr())
-            return
-        d_dev = d_own.cuda(non_blocking=True); x_dev = x_own.cuda(non_blocking=True)
-        all_d = torch.empty((world,) + tuple(d_dev.shape), dtype=d_dev.dtype, device="cuda")
-        all_x = torch.empty((world,) + tuple(x_dev.shape), dtype=x_dev.dtype, device="cuda")
-        dist.all_gather_into_tensor(all_d, d_dev)
-        dist.all_gather_into_tensor(all_x, x_dev)
-        torch.cuda.synchronize()
-        for slot in range(n_local):
-            for r in range(world):
-                img = slot * world + r
-                if img < n_img:
-                    pm.set_image_ptr(img, all_d[r, slot].data_ptr(), a.kp, dim, dt, all_x[r, slot].data_ptr(), on_device=True,
-                                     asynchronous=asynchronous)
-        if asynchronous:
-            pm.sync_images()            # all_d / all_x go out of scope on return
-
-    ingest()
-    for _ in range(a.warmup):
-        r = pm.match_all_pairs(mine, copy=False); pm.free_result(r)
-
-    sampler = ClockSampler(local) if rank == 0 else None
-    barrier()
-    pm.reset_stats()
-    if sampler:
-        sampler.start()
-    dev_ms = 0.0
-    t0 = time.perf_counter()
-    matches = inliers = 0
-    for _ in range(a.steps):
-        r = pm.match_all_pairs(mine, copy=False)
-        dev_ms += r["device_ms"]
-        matches = int(r["offsets"][-1]); inliers = int(r["n_inliers"].sum())
-        pm.free_result(r)
-    barrier()
-    wall_ms = 1e3 * (time.perf_counter() - t0)
-    clocks = sampler.stop() if sampler else None
-    st = pm.stats()
-    dev_ms = allmax(dev_ms)
-    wall_ms = allmax(wall_ms)
-    launches = allsum(st["kernel_launches"])
-    total_pairs = len(pairs)
-    ms_per_step = dev_ms / a.steps
-    value = total_pairs / (ms_per_step * 1e-3)
-
-    # ---- roofline of the dominant kernel (kNN), rank 0 --------------------------------------------
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    knn_s = st["knn_ms"] * 1e-3
-    orb_form = "popc" if (a.debug_flags & 1024) else "e4m3" if (a.debug_flags & 65536) else "i8" if (a.debug_flags & 262144) else "fp4"
-    if a.kind == "orb" and orb_form != "popc":
-        # default binary path: Hamming = |a| + |b| - 2 a.b on the tensor cores (E2M1 {0,+-1} operands on kind::mxf4, exact);
-        # one popc32 of the fixed numerator = 32 bit compares = 64 FLOP of the contraction
-        pk = peaks.get("bf16_tflops_sustained")
-        popc_peak = pm.measure_popc_peak()
-        mult = 4.0 if orb_form == "fp4" else 2.0
-        roof = dict(bound="tensor", achieved=64.0 * st["knn_work"] / knn_s / 1e12, peak=mult * (pk if pk else 1400.0),
-                    unit="TFLOP/s",
-                    peak_source=(("%g x MEASURED_PEAKS.json bf16_tflops_sustained (%s; no measured figure of that kind in "
-                                  "MEASURED_PEAKS.json)" % (mult, "fp4 dense (kind::mxf4) = 4 x bf16 on B200" if orb_form == "fp4" else
-                                                            "fp8 / int8 dense = 2 x bf16 on B200")) if pk
-                                 else "%g x fallback 1.4 PFLOP/s (B200_PROFILING.md)" % mult),
-                    operands={"fp4": "E2M1 {0, +-1} values on tcgen05 kind::mxf4 (64 values of K per instruction, all-ones scale "
-                                     "factors), f32 accumulate, exact integers", "i8": "u8 x s8 on tcgen05 kind::i8, s32 accumulate",
-                              "e4m3": "E4M3 {0,1} values on tcgen05 kind::f8f6f4, f32 accumulate, exact integers"}[orb_form],
-                    frac_of_bf16_peak=64.0 * st["knn_work"] / knn_s / 1e12 / (pk if pk else 1400.0),
-                    popc32_equiv=dict(achieved=st["knn_work"] / knn_s / 1e12, popc_pipe_peak=popc_peak / 1e12, unit="Tpopc32/s",
-                                      note="the XOR/popc kernel of the north star (--debug-flags 1024) is bounded by popc_pipe_peak"))
-    elif a.kind == "orb":
-        popc_peak = pm.measure_popc_peak()
-        roof = dict(bound="popc", achieved=st["knn_work"] / knn_s / 1e12, peak=popc_peak / 1e12, unit="Tpopc32/s",
-                    peak_source="measured live: pm_measure_popc_peak (dependent-chain POPC micro-benchmark)")
-    else:
-        pk = peaks.get("bf16_tflops_sustained")
-        roof = dict(bound="tensor", achieved=st["knn_work"] / knn_s / 1e12, peak=pk if pk else 1400.0, unit="TFLOP/s",
-                    peak_source="MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if pk
-                    else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)")
-    roof["frac"] = roof["achieved"] / roof["peak"]
-    if a.kind == "sift" and not (a.debug_flags & 2048):
-        roof["operands"] = ("int8 (tcgen05 kind::i8, u8 x s8 -> s32): the MMA rate of this kind is 2 x the bf16 rate the peak "
-                            "is quoted in, so frac can reach 2; ncu: tensor pipe (imma) active 90.4 % of elapsed "
-                            "(profiles/r01_i8x2_kernel_ncu_full.md)")
-        roof["frac_of_int8_peak"] = roof["frac"] / 2.0
-    if a.kind == "superpoint" and not (a.debug_flags & 32768):
-        roof["operands"] = ("int8 (tcgen05 kind::i8, rows quantised to s8 for the candidate stage; exact fp32 re-rank follows): "
-                            "2 x the bf16 MMA rate the peak is quoted in")
-        roof["frac_of_int8_peak"] = roof["frac"] / 2.0
-    roof["kernel"] = {"sift": "l2_top2_tc2_kernel" if (a.debug_flags & (2048 | 16384)) else "l2_i8x2_kernel", "orb": {"popc": "hamming_top2_kernel", "e4m3": "l2_top2_tc2_kernel<T2Cfg<256,2,2>,2,false,1>", "i8": "l2_i8x2_kernel<2,false,2,0>", "fp4": "l2_i8x2_kernel<2,false,1,1>"}[orb_form], "superpoint": "l2_top2_tc2_kernel<T2Cfg<256,2,4>,3>" if (a.debug_flags & 32768) else "l2_top2_tc2_kernel<T2Cfg<256,2,2>,3,true,3>"}[a.kind]
-    roof["launches"] = st["knn_launches"]
-    roof["avg_launch_ms"] = st["knn_ms"] / max(st["knn_launches"], 1)
-    roof["share_of_step"] = st["knn_ms"] / max(dev_ms, 1e-9) if world == 1 else None
-    if a.kind == "superpoint":
-        roof["rerank"] = {k[7:]: st[k] for k in st if k.startswith("rerank_")}
-    # DRAM bytes per launch of that kernel from the committed ncu --set full capture, scaled to this
-    # run's pairs per launch (null when no capture exists for the kernel)
-    roof["traffic"] = None
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(roof["kernel"])
-        if t:
-            pairs_per_launch = len(mine) * a.steps / max(st["knn_launches"], 1)
-            roof["traffic"] = t["bytes_per_launch"] * pairs_per_launch / t["pairs_per_launch"]
-            roof["traffic_source"] = t["source"]
-    except Exception:
-        pass
 
-    # ---- attribution: the same workload with the epipolar filter switched off (matcher only); the filter's cost
-    #      is the difference ("matcher-only and RANSAC-only pairs/s") -----------------------------
+    dev_kw = {}
+    if a.dev_ratio is not None: dev_kw["ratio"] = a.dev_ratio
+    if a.dev_no_filter: dev_kw["do_filter"] = 0
+    wl = Workload(a, D, a.kind, n_img, a.outlier_frac, pairs, images_np=images_np, **dev_kw)
+    images_np = None
+    if sharded:
+        cfg["partition"] += ("; extraction sharded by image id mod N: per step every rank uploads its own images and "
+                             "pm_ingest_allgather (NCCL, wire dtype %s) replicates them" % ("u8" if a.kind == "sift" else "as ingested"))
+    wl.ingest()
+    res = wl.run_resident(a.steps, a.warmup)
+    res["steps"] = a.steps
+    ms_per_step = res["ms_per_step"]
+    total_pairs = len(pairs)
+    value = total_pairs / (ms_per_step * 1e-3)
+    roof = roofline(wl, res, peaks, world)
+
+    # ---- attribution: the same workload with the epipolar filter switched off (matcher only); the filter's cost is the
+    #      difference ("matcher-only and RANSAC-only pairs/s") -------------------------------------------
     stages = None
     if not a.no_stages and world == 1:
         pm2 = api.PairMatcher(devices=[local], reserve_keypoints=n_img * a.kp, debug_flags=a.debug_flags,
                               batch_pairs=a.batch_pairs, do_filter=0)
-        for i, (td, tx) in enumerate(pinned):
-            pm2.set_image_ptr(i, td.data_ptr(), td.shape[0], dim, dt, tx.data_ptr())
-        r = pm2.match_all_pairs(mine, copy=False); pm2.free_result(r)
-        torch.cuda.synchronize()
+        wl.ingest(pm=pm2)
+        r = pm2.match_all_pairs(wl.mine, copy=False); pm2.free_result(r)
+        D.torch.cuda.synchronize()
         m_ms = 0.0
         for _ in range(a.steps):
-            r = pm2.match_all_pairs(mine, copy=False)
+            r = pm2.match_all_pairs(wl.mine, copy=False)
             m_ms += r["device_ms"]
             pm2.free_result(r)
         pm2.close()
@@ -463,9 +581,9 @@ def main():
     if cpu is not None and flann:
         agree = tot = inter = union = 0
         for (i, j), (top1, final) in flann.items():
-            gi, _ = pm.knn_pair(i, j)
+            gi, _ = wl.pm.knn_pair(i, j)
             agree += int((gi[:, 0] == top1).sum()); tot += len(top1)
-            g = pm.match_filter_pair(i, j)
+            g = wl.pm.match_filter_pair(i, j)
             keep = g["inlier"].astype(bool)
             gs = set(zip(g["q"][keep].tolist(), g["t"][keep].tolist()))
             fs = set(map(tuple, final.tolist()))
@@ -475,44 +593,42 @@ def main():
                              note="reference FLANN (approximate) vs this library's exact search, same pairs")
 
     # ---- e2e: host buffers in, host CSR out, every step ---------------------------------------------
-    e2e = None
-    if not a.no_e2e:
-        use_async = not a.sync_ingest
-        ingest(use_async); r = pm.match_all_pairs(mine, copy=False); pm.free_result(r)      # warm
-        barrier()
-        pm.reset_stats()
-        t0 = time.perf_counter()
-        for _ in range(a.steps):
-            ingest(use_async)
-            r = pm.match_all_pairs(mine, copy=False)
-            _ = int(r["n_inliers"].sum())                     # the step's result is read on the host
-            pm.free_result(r)
-        barrier()
-        e_ms = allmax(1e3 * (time.perf_counter() - t0)) / a.steps
-        st2 = pm.stats()
-        e2e = dict(value=total_pairs / (e_ms * 1e-3), unit=UNIT, ms_per_step=e_ms,
-                   h2d_bytes_per_step=int(allsum(st2["h2d_bytes"]) / a.steps) +
-                   (int(allsum(d_own.numel() * d_own.element_size() + x_own.numel() * x_own.element_size())) if sharded else 0),
-                   d2h_bytes_per_step=int(allsum(st2["d2h_bytes"]) / a.steps),
-                   timing="host wall clock around %s x images + match_all_pairs, max over ranks" %
-                          ("set_images_async" if use_async and not sharded else "NCCL all-gather + set_image_device_async" if use_async else "set_image"))
-        if sharded:
-            e2e["allgather_bytes_per_step"] = int(world * (d_own.numel() * d_own.element_size() + x_own.numel() * x_own.element_size()))
+    e2e = None if a.no_e2e else wl.run_e2e(a.steps)
+    wl.close()
+
+    # ---- the headline workload with 50 % outlier keypoints: the filter runs hundreds of iterations ---------
+    if not a.no_stages and a.outlier_frac == 0.0:
+        rh = run_config(a, D, peaks, a.kind, n_img, 0.5, a.cfg_steps, 1, 0, "ransac_heavy")
+        heavy = dict(value=rh["value"], unit=UNIT, ms_per_step=rh["ms_per_step"], outlier_frac=0.5, steps=rh["steps"],
+                     what="the headline workload with half of the keypoints moved to random pixels",
+                     kNN_share_of_step=rh["roofline"]["share_of_step"], clocks=rh["clocks"])
+        stages = dict(stages or {}, ransac_heavy=heavy)
+
+    # ---- the other BASELINE.json configurations (strong scaling: the same job on all N GPUs) --------------------------
+    configs = None
+    if not a.no_configs:
+        configs = {}
+        configs["orb500"] = run_config(a, D, peaks, "orb", a.orb_images, 0.0, a.cfg_steps, 1, 1, "BASELINE.json configs[2]")
+        configs["superpoint1000"] = run_config(a, D, peaks, "superpoint", a.sp_images, 0.0, max(1, a.cfg_steps - 1), 1, 1,
+                                               "BASELINE.json configs[3]")
 
     if rank == 0:
+        flags = a.debug_flags
+        dtype = {"sift": "f16 operands / f32 accumulate (exact integers)" if (flags & 2048) else
+                 "u8 x s8 operands / s32 accumulate (kind::i8, exact integers)",
+                 "orb": {"popc": "u32 popc", "e4m3": "e4m3 {0,1} operands / f32 accumulate (exact integers)",
+                         "i8": "u8 x s8 operands / s32 accumulate (exact integers)",
+                         "fp4": "e2m1 {0,+-1} operands (kind::mxf4) / f32 accumulate (exact integers)"}[orb_form(flags)],
+                 "superpoint": "f16 operands / f32 accumulate candidates + exact f32 re-rank" if (flags & 32768) else
+                 "s8 operands / s32 accumulate candidates (kind::i8) + exact f32 re-rank"}[a.kind]
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=n_gpus, steps=a.steps, warmup=a.warmup,
-                    ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype={"sift": "f16 operands / f32 accumulate (exact integers)" if (a.debug_flags & 2048) else
-                           "u8 x s8 operands / s32 accumulate (kind::i8, exact integers)", "orb": {"popc": "u32 popc", "e4m3": "e4m3 {0,1} operands / f32 accumulate (exact integers)", "i8": "u8 x s8 operands / s32 accumulate (exact integers)", "fp4": "e2m1 {0,+-1} operands (kind::mxf4) / f32 accumulate (exact integers)"}[orb_form],
-                           "superpoint": "f16 operands / f32 accumulate candidates + exact f32 re-rank" if (a.debug_flags & 32768) else
-                           "s8 operands / s32 accumulate candidates (kind::i8) + exact f32 re-rank"}[a.kind],
-                    data="synthetic", config=cfg, wall_ms_per_step=wall_ms / a.steps,
-                    putative_matches_per_step=matches, inliers_per_step=inliers,
-                    roofline=roof, stages=stages, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks)
+                    ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype=dtype,
+                    data="synthetic", config=cfg, wall_ms_per_step=res["wall_ms_per_step"],
+                    putative_matches_per_step=res["matches"], inliers_per_step=res["inliers"],
+                    roofline=roof, stages=stages, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(res["launches"]),
+                    clocks=res["clocks"], configs=configs)
         print(json.dumps(line))
-    pm.close()
-    if world > 1:
-        dist.destroy_process_group()
+    D.close()
 
 
 if __name__ == "__main__":

@@ -190,6 +190,23 @@ int pm_num_keypoints(pm_handle h, int img_id);
  * at most that many keypoints).  PM_ERR_STATE when the id is not set. */
 int pm_remove_image(pm_handle h, int img_id);
 
+/* Collective ingest (SURVEY 8e "Collective"): feature extraction sharded over the ranks of one job, ONE process per
+ * GPU, image k (0 <= k < n_images_total) extracted by rank k % n_ranks.  Every rank hands over only its own images
+ * (ascending id order, n_keypoints rows each, host or device memory) and receives all of them: own images -> device ->
+ * ncclAllGather over NVLink / NVSwitch, slot by slot (slot s = images s*R .. s*R+R-1) -> asynchronous ingest, so that
+ * pm_match_all_pairs can start on the first slots while later ones are still on the wire.  Nothing waits for the
+ * device; pm_sync_images (or the first matching call that touches an image) does.
+ *   wire_dtype  what travels: == dtype, or PM_DESC_U8 for PM_DESC_F32 rows of dim 128 that hold byte values (SIFT,
+ *               FeatureDetector.cpp:20-24): 4x fewer bytes; the promise is checked on the device and reported by
+ *               pm_sync_images (PM_ERR_INVALID).
+ * The communicator is the library's own: rank 0 calls pm_comm_get_unique_id and ships the 128 bytes to the other
+ * ranks by any means (MPI, a file, torch.distributed), then every rank calls pm_comm_init on its single-device
+ * handle.  NCCL is bound at run time (dlopen of libnccl.so.2): PM_ERR_UNSUPPORTED when it is not installed. */
+int pm_comm_get_unique_id(uint8_t id[128]);
+int pm_comm_init(pm_handle h, const uint8_t id[128], int rank, int n_ranks);
+int pm_ingest_allgather(pm_handle h, int n_images_total, int n_keypoints, int dim, int dtype, int wire_dtype,
+                        const void* own_desc, const int32_t* own_xy, int own_on_device);
+
 /* Raw 2-NN rows of pair (i -> j): what knnMatch(desc_i, desc_j, 2) returns as DMatch rows
  * (FeatureMatcher.cpp:49).  idx/dist are [n_i][2]; missing neighbours are idx -1, dist +inf.
  * dist is the float L2 norm (sqrt) or the Hamming count as float, like cv::DMatch::distance. */

@@ -52,6 +52,12 @@ def knn2_bf(desc1: np.ndarray, desc2: np.ndarray):
 
 
 def _unpack(knn, nq):
+    """DMatch rows -> (idx, dist) arrays.  The DMatch objects are what cv2 hands back (the C++ reference reads the same
+    fields in place); flat generator expressions keep the Python share of the timed CPU arm at ~1 % of a pair."""
+    if nq and all(len(row) == 2 for row in knn):
+        idx = np.fromiter((m.trainIdx for row in knn for m in row), np.int32, 2 * nq).reshape(nq, 2)
+        dist = np.fromiter((m.distance for row in knn for m in row), np.float32, 2 * nq).reshape(nq, 2)
+        return idx, dist
     idx = np.full((nq, 2), -1, np.int32)
     dist = np.full((nq, 2), np.inf, np.float32)
     for i, row in enumerate(knn):
@@ -62,7 +68,20 @@ def _unpack(knn, nq):
 
 
 def ratio_unique(idx: np.ndarray, dist: np.ndarray, ratio=RATIO):
-    """FeatureMatcher.cpp:51-64 (float compare on non-squared distances, first query wins)."""
+    """FeatureMatcher.cpp:51-64 (float compare on non-squared distances, first query wins), vectorised:
+    the first occurrence of every train index among the rows that pass, in ascending query order."""
+    ratio = np.float32(ratio)
+    d = np.asarray(dist, np.float32)
+    ok = (idx[:, 0] >= 0) & (idx[:, 1] >= 0) & (d[:, 0] < (ratio * d[:, 1]).astype(np.float32))
+    q = np.nonzero(ok)[0]
+    t = idx[q, 0]
+    _, first = np.unique(t, return_index=True)
+    first.sort()
+    return q[first].astype(np.int32), t[first].astype(np.int32)
+
+
+def ratio_unique_loop(idx: np.ndarray, dist: np.ndarray, ratio=RATIO):
+    """The same as the literal loop of FeatureMatcher.cpp:51-64 (kept as the cross-check of ratio_unique)."""
     q_out, t_out, seen = [], [], set()
     ratio = np.float32(ratio)
     for i in range(idx.shape[0]):

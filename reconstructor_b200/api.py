@@ -37,6 +37,7 @@ EXPORTS = [
     "pm_free_result", "pm_get_stats", "pm_reset_stats", "pm_measure_popc_peak",
     "pm_save_images", "pm_load_images", "pm_save_result", "pm_load_result",
     "pm_filter_pair_F_seeded", "pm_pair_seed", "pm_remove_image", "pm_measure_tensor_peak", "pm_debug_tc_dump",
+    "pm_comm_get_unique_id", "pm_comm_init", "pm_ingest_allgather",
 ]
 
 
@@ -117,6 +118,10 @@ def load_library() -> C.CDLL:
         lib.pm_pair_seed.argtypes = [C.c_uint64, C.c_int32, C.c_int32]
         lib.pm_pair_seed.restype = C.c_uint64
         lib.pm_remove_image.argtypes = [C.c_void_p, C.c_int]
+        lib.pm_comm_get_unique_id.argtypes = [C.c_void_p]
+        lib.pm_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        lib.pm_ingest_allgather.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                            C.c_int]
         lib.pm_measure_tensor_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
         lib.pm_match_all_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_int64,
                                            C.POINTER(C.POINTER(CsrResult))]
@@ -135,6 +140,15 @@ def load_library() -> C.CDLL:
 def pair_seed(seed: int, i: int, j: int) -> int:
     """The Philox key the batched loop derives for pair (i, j) under pm_params.seed."""
     return int(load_library().pm_pair_seed(seed, i, j))
+
+
+def comm_unique_id() -> bytes:
+    """pm_comm_get_unique_id (rank 0); ship the bytes to the other ranks by any means."""
+    buf = (C.c_uint8 * 128)()
+    rc = load_library().pm_comm_get_unique_id(buf)
+    if rc != OK:
+        raise PairMatchError(rc, load_library().pm_last_error(None).decode())
+    return bytes(buf)
 
 
 def default_params() -> Params:
@@ -233,6 +247,21 @@ class PairMatcher:
 
     def sync_images(self):
         self._check(self.lib.pm_sync_images(self.h))
+
+    # -- collective ingest (extraction sharded over ranks, one process per GPU) --------------------
+    def comm_init(self, unique_id: bytes, rank: int, n_ranks: int):
+        """pm_comm_init: unique_id = the 128 bytes of comm_unique_id() from rank 0."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._check(self.lib.pm_comm_init(self.h, buf, rank, n_ranks))
+        self._comm = (rank, n_ranks)
+
+    def ingest_allgather(self, n_images_total: int, n_keypoints: int, dim: int, dtype: int, wire_dtype: int,
+                         own_desc_ptr: int, own_xy_ptr: int | None, own_on_device=False):
+        """pm_ingest_allgather: image k lives on rank k % n_ranks; own_* = this rank's images in ascending id order."""
+        self._check(self.lib.pm_ingest_allgather(self.h, n_images_total, n_keypoints, dim, dtype, wire_dtype,
+                                                 own_desc_ptr, own_xy_ptr, 1 if own_on_device else 0))
+        for i in range(n_images_total):
+            self._n[i] = n_keypoints
 
     # -- per-pair (compat path of the virtual calls) ---------------------------------------------
     def knn_pair(self, i: int, j: int):

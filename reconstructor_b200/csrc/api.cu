@@ -22,6 +22,7 @@
 
 #include "../../include/pairmatch_b200.h"
 #include "kernels.h"
+#include "nccl_dyn.h"
 
 namespace {
 
@@ -246,7 +247,7 @@ struct DeviceCtx {
   int* h_flag = nullptr;       // pinned
   static constexpr int kRecInts = 8, kRecCap = 1 << 16;
   int* h_recs = nullptr;       // pinned [kRecCap][kRecInts]: {flag, fstats[4]} of asynchronously ingested images
-  int next_rec = 0;
+  int next_rec = 0, n_pending = 0;   // records are recycled whenever no image is pending
   void* stage = nullptr;       // device staging for u8 uploads
   size_t stage_bytes = 0;
 
@@ -293,6 +294,7 @@ struct DeviceCtx {
     PM_CUDA(cudaSetDevice(dev));
     // queued work may still read the rows: drain before they can be handed to another image
     PM_CUDA(cudaDeviceSynchronize());
+    if (it->second.pending) { const int rc = resolve(it->second); if (rc != PM_OK) return rc; }
     if (it->second.ready) cudaEventDestroy(it->second.ready);
     release_rows(it->second.row, it->second.cap);
     images.erase(it);
@@ -336,13 +338,14 @@ struct DeviceCtx {
     if (const char* e = std::getenv("PM_SLOTS")) opt_slots = std::max(1, std::min(32, std::atoi(e)));
     { const char* e = std::getenv("PM_RESULT_COPY"); result_by_ce = !(e && std::strcmp(e, "kernel") == 0); }
     opt_prefilter = std::getenv("PM_L2F_PREFILTER") != nullptr;
-    PM_CUDA(cudaStreamCreateWithFlags(&ingest, cudaStreamNonBlocking));
     {
       // the persistent kNN kernels go first whenever SMs free up; the small tail kernels of earlier batches
       // (default priority) fill whatever registers / shared memory the kNN kernel leaves
       int prio_lo = 0, prio_hi = 0;
       PM_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
       PM_CUDA(cudaStreamCreateWithPriority(&knn_stream, cudaStreamNonBlocking, prio_hi));
+      // the ingest stream too: the (single) NCCL kernel of a collective ingest must not starve behind the kNN kernels
+      PM_CUDA(cudaStreamCreateWithPriority(&ingest, cudaStreamNonBlocking, prio_hi));
     }
     PM_CUDA(cudaEventCreate(&ev_a));
     PM_CUDA(cudaEventCreate(&ev_b));
@@ -374,6 +377,13 @@ struct DeviceCtx {
     auto fd = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
     fd(raw); fd(qf); fd(tf); fd(qnorm); fd(u8d); fd(bits); fd(xy); fd(d_flag); fd(stage); fd(d_dump);
     fd(fq); fd(ft); fd(fnorm); fd(d_fstats); fd(d_l2f); fd(hq); fd(ht); fd(iq); fd(it); fd(qoff); fd(sq8); fd(st8); fd(hq8); fd(ht8); fd(hq4); fd(ht4);
+    if (comm) { nccl_api().CommDestroy(comm); comm = nullptr; }
+    if (ag_own) cudaFree(ag_own);
+    if (ag_all) cudaFree(ag_all);
+    if (ag_flag) cudaFree(ag_flag);
+    if (h_agflag) cudaFreeHost(h_agflag);
+    h_agflag = nullptr;
+    ag_own = ag_all = nullptr; ag_flag = nullptr; ag_own_bytes = ag_all_bytes = 0;
     if (h_flag) cudaFreeHost(h_flag);
     if (h_recs) cudaFreeHost(h_recs);
     for (auto& kv : images) if (kv.second.ready) cudaEventDestroy(kv.second.ready);
@@ -564,6 +574,7 @@ struct DeviceCtx {
       im.i8_ok = rec[0] == 0;
     }
     im.pending = false;
+    if (--n_pending <= 0) { n_pending = 0; next_rec = 0; }     // (rec stays readable below: nothing is queued in between)
     if (float_tc_shape() && !im.integral) {
       if (dim == TC_DIM) {
         // 128-d rows that turned out not to be integer-valued: their fp16 forms were not packed on speculation
@@ -725,6 +736,7 @@ struct DeviceCtx {
       PM_CUDA(cudaEventRecord(im.ready, ingest));
       im.rec = next_rec++;
       im.pending = true;
+      ++n_pending;
       stats.n_images = static_cast<int32_t>(images.size());
       return PM_OK;
     }
@@ -1004,6 +1016,110 @@ struct DeviceCtx {
     return PM_OK;
   }
   std::vector<char> job_integral, job_unit, job_i8, job_s8;   // per job of the batch being built
+
+  // ---- collective ingest (SURVEY 8e "Collective", 2.2 C1): extraction sharded over ranks, one NCCL all-gather ----
+  NcclComm comm = nullptr;
+  int comm_rank = 0, comm_size = 1;
+  uint8_t *ag_own = nullptr, *ag_all = nullptr;       // device: this rank's images in wire form / the gathered set
+  size_t ag_own_bytes = 0, ag_all_bytes = 0;
+  int* ag_flag = nullptr;                             // not-integral flag of the f32 -> u8 wire conversion
+  int* h_agflag = nullptr;                            // pinned copy
+
+  int comm_init(const uint8_t id[128], int rank, int n_ranks) {
+    PM_CUDA(cudaSetDevice(dev));
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(PM_ERR_INVALID, "pm_comm_init: rank %d of %d", rank, n_ranks);
+    if (const char* why = nccl_api().load()) return fail(PM_ERR_UNSUPPORTED, "NCCL unavailable: %s", why);
+    if (comm) { nccl_api().CommDestroy(comm); comm = nullptr; }
+    NcclUniqueId uid;
+    std::memcpy(uid.internal, id, sizeof uid.internal);
+    const int rc = nccl_api().CommInitRank(&comm, n_ranks, uid, rank);
+    if (rc != kNcclSuccess) { comm = nullptr; return fail(PM_ERR_CUDA, "ncclCommInitRank: %s", nccl_api().GetErrorString(rc)); }
+    comm_rank = rank; comm_size = n_ranks;
+    return PM_OK;
+  }
+
+  // Image k (0 <= k < n_total) was extracted on rank k % R; own_desc / own_xy hold this rank's images in ascending
+  // id order (n_kp rows each).  Own images -> device (wire form) -> all-gather slot by slot (slot s = images
+  // s*R .. s*R+R-1, which land contiguously in id order) -> asynchronous ingest from the gathered buffer.  Everything is
+  // queued on the ingest stream; nothing here waits for the device.
+  int ingest_allgather(int n_total, int n_kp, int dim_, int dtype_, int wire, const void* own_desc, const int32_t* own_xy,
+                       bool own_on_device) {
+    PM_CUDA(cudaSetDevice(dev));
+    if (!comm) return fail(PM_ERR_STATE, "pm_ingest_allgather: no communicator (call pm_comm_init first)");
+    if (n_total < 0 || n_kp <= 0 || dim_ <= 0) return fail(PM_ERR_INVALID, "pm_ingest_allgather: bad arguments");
+    if (dtype_ != PM_DESC_F32 && dtype_ != PM_DESC_U8_BITS && dtype_ != PM_DESC_U8) return fail(PM_ERR_INVALID, "unknown dtype %d", dtype_);
+    if (wire != dtype_ && !(wire == PM_DESC_U8 && dtype_ == PM_DESC_F32))
+      return fail(PM_ERR_INVALID, "wire dtype %d not available for descriptors of dtype %d", wire, dtype_);
+    const int R = comm_size, n_slots = (n_total + R - 1) / R;
+    const int n_own = n_total > comm_rank ? (n_total - comm_rank + R - 1) / R : 0;
+    if (n_own > 0 && !own_desc) return fail(PM_ERR_INVALID, "pm_ingest_allgather: own_desc is NULL");
+    const size_t in_row = dtype_ == PM_DESC_F32 ? 4u * dim_ : (dtype_ == PM_DESC_U8 ? static_cast<size_t>(dim_) : static_cast<size_t>(dim_) / 8);
+    const size_t w_row = wire == PM_DESC_F32 ? 4u * dim_ : (wire == PM_DESC_U8 ? static_cast<size_t>(dim_) : static_cast<size_t>(dim_) / 8);
+    const bool has_xy = own_xy != nullptr || n_own == 0;
+    const size_t img_in = in_row * n_kp, img_w = w_row * n_kp, img_xy = 8u * n_kp;
+    const size_t slot_w = img_w + (has_xy ? img_xy : 0);          // wire bytes of one image: descriptors, then xy
+    // staging: [n_slots] own images in wire form (+ room for the raw fp32 rows when they are converted on the device)
+    const size_t own_need = static_cast<size_t>(n_slots) * slot_w + (wire != dtype_ ? static_cast<size_t>(n_slots) * img_in : 0);
+    const size_t all_need = static_cast<size_t>(n_slots) * R * slot_w;
+    if (own_need > ag_own_bytes || all_need > ag_all_bytes) {
+      PM_CUDA(cudaStreamSynchronize(ingest));                      // an earlier ingest may still read the buffers
+      if (own_need > ag_own_bytes) { if (ag_own) cudaFree(ag_own); ag_own = nullptr; ag_own_bytes = 0; PM_CUDA(cudaMalloc(&ag_own, own_need)); ag_own_bytes = own_need; }
+      if (all_need > ag_all_bytes) { if (ag_all) cudaFree(ag_all); ag_all = nullptr; ag_all_bytes = 0; PM_CUDA(cudaMalloc(&ag_all, all_need)); ag_all_bytes = all_need; }
+    }
+    if (!ag_flag) PM_CUDA(cudaMalloc(&ag_flag, sizeof(int)));
+    if (!h_agflag) PM_CUDA(cudaMallocHost(&h_agflag, sizeof(int)));
+    const cudaMemcpyKind up = own_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    uint8_t* raw_stage = ag_own + static_cast<size_t>(n_slots) * slot_w;
+    if (wire != dtype_) PM_CUDA(cudaMemsetAsync(ag_flag, 0, sizeof(int), ingest));
+    // Two chunks: the first few slots (the images the first, short batches of the pair loop need) and everything else.
+    // Per chunk: own images -> device, ONE grouped NCCL launch for all its slots, then the asynchronous ingest of its
+    // images.  The second chunk's upload runs on the copy engine under the first batches; its single NCCL kernel needs
+    // to be scheduled once between two persistent kNN kernels (the ingest stream has their priority).
+    const int first = std::min(n_slots, std::max(1, (32 + R - 1) / R));
+    for (int c = 0; c < 2; ++c) {
+      const int s0 = c == 0 ? 0 : first, s1 = c == 0 ? first : n_slots;
+      if (s0 >= s1) continue;
+      for (int sl = s0; sl < s1; ++sl) {
+        uint8_t* w = ag_own + static_cast<size_t>(sl) * slot_w;
+        if (sl < n_own) {
+          const uint8_t* src = static_cast<const uint8_t*>(own_desc) + static_cast<size_t>(sl) * img_in;
+          if (wire == dtype_) {
+            PM_CUDA(cudaMemcpyAsync(w, src, img_in, up, ingest));
+          } else {                                                 // f32 rows -> bytes on the device (checked integral)
+            uint8_t* st = raw_stage + static_cast<size_t>(sl) * img_in;
+            PM_CUDA(cudaMemcpyAsync(st, src, img_in, up, ingest));
+            PM_CUDA(launch_f32_to_u8(reinterpret_cast<const float*>(st), w, static_cast<size_t>(n_kp) * dim_, ag_flag, ingest));
+            ++stats.kernel_launches;
+          }
+          if (has_xy) PM_CUDA(cudaMemcpyAsync(w + img_w, own_xy + 2 * static_cast<size_t>(sl) * n_kp, img_xy, up, ingest));
+          if (!own_on_device) stats.h2d_bytes += img_in + (has_xy ? img_xy : 0);
+        } else {
+          PM_CUDA(cudaMemsetAsync(w, 0, slot_w, ingest));          // ranks without an image in the last slot send zeros
+        }
+      }
+      int rc = nccl_api().GroupStart();
+      for (int sl = s0; sl < s1 && rc == kNcclSuccess; ++sl)
+        rc = nccl_api().AllGather(ag_own + static_cast<size_t>(sl) * slot_w, ag_all + static_cast<size_t>(sl) * R * slot_w,
+                                  slot_w, kNcclUint8, comm, ingest);
+      const int rc_end = nccl_api().GroupEnd();
+      if (rc == kNcclSuccess) rc = rc_end;
+      if (rc != kNcclSuccess) return fail(PM_ERR_CUDA, "ncclAllGather: %s", nccl_api().GetErrorString(rc));
+      for (int sl = s0; sl < s1; ++sl)
+        for (int r = 0; r < R; ++r) {
+          const int img = sl * R + r;
+          if (img >= n_total) break;
+          const uint8_t* g = ag_all + (static_cast<size_t>(sl) * R + r) * slot_w;
+          const int rc2 = set_image(img, g, n_kp, dim_, wire, has_xy ? reinterpret_cast<const int32_t*>(g + img_w) : nullptr, true, true);
+          if (rc2 != PM_OK) return rc2;
+        }
+    }
+    if (wire != dtype_) {                                          // the caller promised integer-valued rows: verify
+      PM_CUDA(cudaMemcpyAsync(h_agflag, ag_flag, sizeof(int), cudaMemcpyDeviceToHost, ingest));
+      ag_check_pending = true;
+    }
+    return PM_OK;
+  }
+  bool ag_check_pending = false;
 
   int fill_job(Slot& s, int k, int i, int j) {
     auto a = images.find(i), b = images.find(j);
@@ -1365,6 +1481,10 @@ int pm_sync_images(pm_handle h) {
     const int rc = d->resolve_all();
     if (rc != PM_OK) return h->from(*d, rc);
     if (cudaStreamSynchronize(d->ingest) != cudaSuccess) return h->fail(PM_ERR_CUDA, "ingest stream failed");
+    if (d->ag_check_pending) {
+      d->ag_check_pending = false;
+      if (*d->h_agflag != 0) return h->from(*d, d->fail(PM_ERR_INVALID, "pm_ingest_allgather: wire dtype U8 was requested for rows that are not integer-valued in [0,255]"));
+    }
   }
   return PM_OK;
 }
@@ -1708,6 +1828,32 @@ int pm_measure_popc_peak(pm_handle h, double* popc32_per_s) {
   cudaFree(buf);
   *popc32_per_s = best;
   return PM_OK;
+}
+
+int pm_comm_get_unique_id(uint8_t id[128]) {
+  if (!id) return PM_ERR_INVALID;
+  if (const char* why = nccl_api().load()) { g_create_error = std::string("NCCL unavailable: ") + why; return PM_ERR_UNSUPPORTED; }
+  NcclUniqueId uid;
+  const int rc = nccl_api().GetUniqueId(&uid);
+  if (rc != kNcclSuccess) { g_create_error = std::string("ncclGetUniqueId: ") + nccl_api().GetErrorString(rc); return PM_ERR_CUDA; }
+  std::memcpy(id, uid.internal, sizeof uid.internal);
+  return PM_OK;
+}
+
+int pm_comm_init(pm_handle h, const uint8_t id[128], int rank, int n_ranks) {
+  if (!h || !id) return PM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (h->devs.size() != 1) return h->fail(PM_ERR_UNSUPPORTED, "pm_comm_init needs a single-device handle (one process per GPU)");
+  return h->from(*h->devs[0], h->devs[0]->comm_init(id, rank, n_ranks));
+}
+
+int pm_ingest_allgather(pm_handle h, int n_images_total, int n_keypoints, int dim, int dtype, int wire_dtype,
+                        const void* own_desc, const int32_t* own_xy, int own_on_device) {
+  if (!h) return PM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (h->devs.size() != 1) return h->fail(PM_ERR_UNSUPPORTED, "pm_ingest_allgather needs a single-device handle");
+  return h->from(*h->devs[0], h->devs[0]->ingest_allgather(n_images_total, n_keypoints, dim, dtype, wire_dtype, own_desc,
+                                                           own_xy, own_on_device != 0));
 }
 
 int pm_measure_tensor_peak(pm_handle h, int kind, double* flop_per_s) {

@@ -299,6 +299,31 @@ __global__ void u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restr
   if (i < n) dst[i] = static_cast<float>(src[i]);
 }
 
+// fp32 rows that hold byte values -> bytes (wire form of the collective ingest); *not_integral is set when a value is not
+// an integer in [0, 255]
+__global__ void f32_to_u8_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, size_t n, int* __restrict__ not_integral) {
+  const size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  const float4 v = *reinterpret_cast<const float4*>(src + i);
+  const float f[4] = {v.x, v.y, v.z, v.w};
+  uint32_t out = 0;
+  bool bad = false;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float r = rintf(f[k]);
+    bad |= !(r == f[k] && r >= 0.f && r <= 255.f);
+    out |= (static_cast<uint32_t>(fminf(fmaxf(r, 0.f), 255.f)) & 0xFFu) << (8 * k);
+  }
+  *reinterpret_cast<uint32_t*>(dst + i) = out;
+  if (bad) atomicOr(not_integral, 1);
+}
+cudaError_t launch_f32_to_u8(const float* src, uint8_t* dst, size_t n, int* not_integral, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  if (n & 3) return cudaErrorInvalidValue;
+  f32_to_u8_kernel<<<static_cast<unsigned>((n / 4 + 255) / 256), 256, 0, st>>>(src, dst, n, not_integral);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_u8_to_f32(const uint8_t* src, float* dst, size_t n, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
   u8_to_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(src, dst, n);
