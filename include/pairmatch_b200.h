@@ -100,6 +100,8 @@ typedef struct {
                                  stay those of the winning RANSAC hypothesis.  Not reachable from
                                  the reference's call (defaults), hence off by default.     */
   uint64_t seed;              /* PM_SAMPLER_PHILOX: global seed (per-pair key = f(seed, i, j)) */
+  double  essential_confidence; /* cv::findEssentialMat defaults (GeometricFilter.cpp:26-31): 0.999 */
+  double  essential_threshold;  /*                                                   1.0 px */
 } pm_params;
 
 /* One pair, caller-allocated outputs (capacity = number of query keypoints). */
@@ -231,6 +233,17 @@ int pm_filter_pair_F(pm_handle h, const float* xy1, const float* xy2, int M,
 int pm_filter_pair_F_seeded(pm_handle h, const float* xy1, const float* xy2, int M, uint64_t pair_key,
                             double F[9], uint8_t* mask, int32_t* status, int32_t* iters);
 uint64_t pm_pair_seed(uint64_t seed, int32_t img_i, int32_t img_j);
+
+/* GeometricFilter::estimateEssential (GeometricFilter.h:23-27, GeometricFilter.cpp:10-37) = cv::findEssentialMat(p1, p2,
+ * K1, dist1, K2, dist2) with its defaults: undistortion with each image's own camera, RANSAC (pm_params.
+ * essential_confidence / essential_threshold / ransac_max_iters, sampler as for F) with Nister's five-point solver
+ * and the Sampson residual.  The caller is SequentialReconstructor::chooseInitialPair (.cpp:355), once per
+ * reconstruction.  E is row-major, of unit Frobenius norm, its sign arbitrary (as cv2's); status PM_PAIR_FILTERED or
+ * PM_PAIR_DROPPED (M < 5 or no model: zeros).  The reference never passes a mask to cv::findEssentialMat
+ * (GeometricFilter.cpp:25-33), so ITS inlierMatchIds stays empty; here the mask is returned when `mask` is not NULL. */
+typedef struct { double fx, fy, cx, cy, k1, k2; } pm_camera;   /* PinholeCamera, Camera.h:127 */
+int pm_filter_pair_E(pm_handle h, const float* xy1, const float* xy2, int M, const pm_camera* cam1,
+                     const pm_camera* cam2, double E[9], uint8_t* mask, int32_t* status, int32_t* iters);
 
 /* The whole pair body for one pair (match + gate + filter). */
 int pm_match_filter_pair(pm_handle h, int img_i, int img_j, pm_pair_result* out);

@@ -36,6 +36,7 @@ def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "pm_oracle.c")
     stale = (not os.path.exists(_LIB_PATH)
              or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(src),
+                                                  os.path.getmtime(os.path.join(_HERE, "pm_essential.c")),
                                                   os.path.getmtime(os.path.join(_HERE, "pm_oracle.h"))))
     if force or stale:
         env = dict(os.environ)
@@ -233,3 +234,38 @@ def match_pair(desc1, xy1, desc2, xy2, ratio=0.7, unique_mode=UNIQUE_FIRST_WINS,
                     n_putative=nput.value, F=F.reshape(3, 3))
     return dict(status="ok", q=oq[:n].copy(), t=ot[:n].copy(), n_putative=nput.value,
                 F=F.reshape(3, 3))
+
+
+class Camera(C.Structure):
+    """PinholeCamera (Camera.h:127): fx, fy, cx, cy, k1, k2."""
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("k1", C.c_double), ("k2", C.c_double)]
+
+
+def five_point(m1, m2):
+    m1 = np.ascontiguousarray(m1, np.float64); m2 = np.ascontiguousarray(m2, np.float64)
+    Es = np.zeros(90, np.float64)
+    n = lib().orc_five_point(_p(m1, C.c_double), _p(m2, C.c_double), _p(Es, C.c_double))
+    return Es.reshape(10, 3, 3)[:n].copy()
+
+
+def normalize_for_essential(xy, own: Camera, c1: Camera, c2: Camera):
+    xy = np.ascontiguousarray(xy, np.float32)
+    out = np.zeros((xy.shape[0], 2), np.float64)
+    lib().orc_normalize_for_essential(_p(xy, C.c_float), xy.shape[0], C.byref(own), C.byref(c1), C.byref(c2),
+                                      _p(out, C.c_double))
+    return out
+
+
+def find_essential(xy1, xy2, cam1: Camera, cam2: Camera, prob=0.999, threshold=1.0, max_iters=1000,
+                   sampler=SAMPLER_OPENCV_MWC, seed=0):
+    """cv::findEssentialMat(p1, p2, K1, d1, K2, d2) restated.  Returns (ok, E 3x3, mask uint8 [n], trace)."""
+    xy1 = np.ascontiguousarray(xy1, np.float32); xy2 = np.ascontiguousarray(xy2, np.float32)
+    n = xy1.shape[0]
+    E = np.zeros(9, np.float64); mask = np.zeros(max(n, 1), np.uint8); tr = RansacTrace()
+    f = lib().orc_find_essential
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Camera), C.POINTER(Camera), C.c_double, C.c_double,
+                  C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(RansacTrace)]
+    ok = f(xy1.ctypes.data, xy2.ctypes.data, n, C.byref(cam1), C.byref(cam2), prob, threshold, max_iters, sampler,
+           seed, E.ctypes.data, mask.ctypes.data, C.byref(tr))
+    return bool(ok), E.reshape(3, 3), mask[:n].copy(), tr

@@ -112,6 +112,20 @@ int orc_philox_subset(const float* xy1, const float* xy2, int n, uint64_t pair_s
  * normal matrix, smallest eigenvector, rank-2 enforcement, de-normalisation, F[8] = 1.  Returns 1 / 0. */
 int orc_eight_point(const float* xy1, const float* xy2, int n, const uint8_t* mask, double F[9]);
 
+/* ---- GeometricFilter::estimateEssential (GeometricFilter.cpp:10-37) = cv::findEssentialMat(p1, p2, K1, d1, K2, d2) with
+ * its defaults (RANSAC, prob 0.999, threshold 1.0, 1000 iterations); restated in pm_essential.c. ---------------------- */
+typedef struct { double fx, fy, cx, cy, k1, k2; } orc_camera;     /* PinholeCamera, Camera.h:127 */
+/* Nister's five-point solver on 5 normalised correspondences (m: [5][2] doubles); Es receives up to 10 models. */
+int orc_five_point(const double* m1, const double* m2, double* Es /* [90] */);
+/* undistort with `own`, map to the mean camera of (c1, c2) in float, normalise in double: what the RANSAC sees. */
+void orc_normalize_for_essential(const float* xy, int n, const orc_camera* own, const orc_camera* c1, const orc_camera* c2,
+                                 double* out /* [n][2] */);
+void orc_essential_residuals(const double E[9], const double* m1, const double* m2, int n, float* err);
+/* Returns 1 and E (unit Frobenius norm, sign arbitrary) + mask, or 0 (n < 5 or no model). */
+int orc_find_essential(const float* xy1, const float* xy2, int n, const orc_camera* c1, const orc_camera* c2,
+                       double prob, double threshold, int max_iters, int sampler, uint64_t seed,
+                       double E[9], uint8_t* mask, orc_ransac_trace* trace);
+
 /* Whole per-pair body (match -> >=7 gate -> filter -> keep inliers).
  * desc_kind: 0 = float L2 (dim floats per row), 1 = binary Hamming (dim bytes per row).
  * Returns the number of surviving matches written to out_q/out_t, or -1 when the pair

@@ -37,7 +37,7 @@ EXPORTS = [
     "pm_free_result", "pm_get_stats", "pm_reset_stats", "pm_measure_popc_peak",
     "pm_save_images", "pm_load_images", "pm_save_result", "pm_load_result",
     "pm_filter_pair_F_seeded", "pm_pair_seed", "pm_remove_image", "pm_measure_tensor_peak", "pm_debug_tc_dump",
-    "pm_comm_get_unique_id", "pm_comm_init", "pm_ingest_allgather",
+    "pm_comm_get_unique_id", "pm_comm_init", "pm_ingest_allgather", "pm_filter_pair_E",
 ]
 
 
@@ -47,7 +47,13 @@ class Params(C.Structure):
                 ("ransac_confidence", C.c_double), ("ransac_max_iters", C.c_int32),
                 ("residual_mode", C.c_int32), ("sampler", C.c_int32), ("batch_pairs", C.c_int32),
                 ("reserve_keypoints", C.c_int64), ("debug_flags", C.c_int32), ("refit_8point", C.c_int32),
-                ("seed", C.c_uint64)]
+                ("seed", C.c_uint64), ("essential_confidence", C.c_double), ("essential_threshold", C.c_double)]
+
+
+class Camera(C.Structure):
+    """pm_camera = PinholeCamera of the reference (Camera.h:127)."""
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("k1", C.c_double), ("k2", C.c_double)]
 
 
 class PairResult(C.Structure):
@@ -115,6 +121,8 @@ def load_library() -> C.CDLL:
                                          C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         lib.pm_filter_pair_F_seeded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_void_p,
                                                 C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        lib.pm_filter_pair_E.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Camera), C.POINTER(Camera),
+                                         C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         lib.pm_pair_seed.argtypes = [C.c_uint64, C.c_int32, C.c_int32]
         lib.pm_pair_seed.restype = C.c_uint64
         lib.pm_remove_image.argtypes = [C.c_void_p, C.c_int]
@@ -318,6 +326,16 @@ class PairMatcher:
             self._check(self.lib.pm_filter_pair_F_seeded(self.h, p1.ctypes.data, p2.ctypes.data, m, pair_key,
                                                          F.ctypes.data, mask.ctypes.data, C.byref(st), C.byref(it)))
         return F.reshape(3, 3), mask[:m], st.value, it.value
+
+    def estimate_essential(self, xy1: np.ndarray, xy2: np.ndarray, cam1: Camera, cam2: Camera):
+        """GeometricFilter::estimateEssential -> (E 3x3 of unit norm, mask uint8 [M], status, iters)."""
+        p1 = np.ascontiguousarray(xy1, np.float32); p2 = np.ascontiguousarray(xy2, np.float32)
+        m = p1.shape[0]
+        E = np.zeros(9, np.float64); mask = np.zeros(max(m, 1), np.uint8)
+        st = C.c_int32(0); it = C.c_int32(0)
+        self._check(self.lib.pm_filter_pair_E(self.h, p1.ctypes.data, p2.ctypes.data, m, C.byref(cam1), C.byref(cam2),
+                                              E.ctypes.data, mask.ctypes.data, C.byref(st), C.byref(it)))
+        return E.reshape(3, 3), mask[:m], st.value, it.value
 
     def remove_image(self, img_id: int):
         self._check(self.lib.pm_remove_image(self.h, img_id))

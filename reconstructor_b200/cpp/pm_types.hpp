@@ -13,6 +13,7 @@
 
 #ifdef PM_USE_REFERENCE_HEADERS
 #include "datatypes.h"
+#include "Camera.h"
 namespace pmshim { using Matrix3d = Eigen::Matrix3d; }
 #else
 #ifndef CV_32F
@@ -50,6 +51,14 @@ struct Feature {
 template <typename coordType = int>
 using FeaturePtr = std::shared_ptr<Feature<coordType>>;
 }  // namespace reconstructor::Core
+
+// Camera.h:12-127: only the members estimateEssential reads (getMatrixCV / getDistortCV: fX, fY, cX, cY, k1, k2)
+class PinholeCamera {
+ public:
+  PinholeCamera() = default;
+  PinholeCamera(int height, int width, double fX_, double fY_) : fX(fX_), fY(fY_), cX(width / 2), cY(height / 2) {}
+  double fX = 1, fY = 1, cX = 0, cY = 0, k1 = 0, k2 = 0;
+};
 
 namespace pmshim {
 // Stand-in for Eigen::Matrix3d (column-major like Eigen, operator()(row, col)).

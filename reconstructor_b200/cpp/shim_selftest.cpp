@@ -1,6 +1,7 @@
 // shim_selftest.cpp -- exercises the C++ drop-in classes the way SequentialReconstructor uses its
 // plugins (per-pair virtual calls from several threads) and checks them against the batched loop.
 // Built by `make` (host compiler only); run on a GPU box by tests/test_gpu_shim.py.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <random>
@@ -113,6 +114,26 @@ int main() {
     matcher.invalidate();
     matcher.matchFeatures(features[0], features[1], again, {0, 0}, {0, 0});
     if (before != again || matcher.lastStatus() != PM_OK) { std::printf("results changed after invalidate()\n"); return 1; }
+  }
+  // (5) estimateEssential with the reference's signature: E of unit norm, x2' E x1 ~ 0 for the inliers of F; the
+  //     reference's inlierMatchIds stays empty (no mask is passed to cv::findEssentialMat) unless asked otherwise
+  {
+    auto f1 = features[0], f2 = features[1];
+    std::map<int, int> cur;
+    matcher.matchFeatures(f1, f2, cur, {0, 0}, {0, 0});
+    std::vector<FeaturePtr<>> m1, m2;
+    for (auto& [a, b] : cur) { m1.push_back(f1[a]); m2.push_back(f2[b]); }
+    PinholeCamera cam(1536, 2048, 1200.0, 1200.0);
+    std::vector<bool> inl;
+    auto E = filter.estimateEssential(m1, m2, cam, cam, inl);
+    if (!inl.empty() || E.isZero()) { std::printf("estimateEssential: reference behaviour not kept\n"); return 1; }
+    filter.setFillEssentialMask(true);
+    auto E2 = filter.estimateEssential(m1, m2, cam, cam, inl);
+    size_t n_in = 0;
+    for (bool b : inl) n_in += b;
+    double nrm = 0;
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { nrm += E2(r, c) * E2(r, c); if (E2(r, c) != E(r, c)) { std::printf("E not deterministic\n"); return 1; } }
+    if (inl.size() != m1.size() || n_in < m1.size() / 2 || std::fabs(nrm - 1.0) > 1e-9) { std::printf("estimateEssential: %zu of %zu inliers, |E|^2 = %g\n", n_in, m1.size(), nrm); return 1; }
   }
   std::printf("SHIM_OK pairs=%zu matches=%zu device_ms=%.3f\n", viaBatch.size(), total, loop.lastDeviceMs());
   return 0;

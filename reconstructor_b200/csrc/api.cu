@@ -308,6 +308,8 @@ struct DeviceCtx {
   cudaStream_t knn_stream = nullptr;   // all kNN kernels run back to back on this stream
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
   float* d_dump = nullptr;
+  void* e_scratch = nullptr;           // pm_filter_pair_E: normalised points + the models of a round
+  size_t e_scratch_bytes = 0;
 
   int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -375,7 +377,7 @@ struct DeviceCtx {
     for (auto& s : slots) s.destroy();
     single.destroy();
     auto fd = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
-    fd(raw); fd(qf); fd(tf); fd(qnorm); fd(u8d); fd(bits); fd(xy); fd(d_flag); fd(stage); fd(d_dump);
+    fd(raw); fd(qf); fd(tf); fd(qnorm); fd(u8d); fd(bits); fd(xy); fd(d_flag); fd(stage); fd(d_dump); fd(e_scratch);
     fd(fq); fd(ft); fd(fnorm); fd(d_fstats); fd(d_l2f); fd(hq); fd(ht); fd(iq); fd(it); fd(qoff); fd(sq8); fd(st8); fd(hq8); fd(ht8); fd(hq4); fd(ht4);
     if (comm) { nccl_api().CommDestroy(comm); comm = nullptr; }
     if (ag_own) cudaFree(ag_own);
@@ -1071,14 +1073,14 @@ struct DeviceCtx {
     const cudaMemcpyKind up = own_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     uint8_t* raw_stage = ag_own + static_cast<size_t>(n_slots) * slot_w;
     if (wire != dtype_) PM_CUDA(cudaMemsetAsync(ag_flag, 0, sizeof(int), ingest));
-    // Two chunks: the first few slots (the images the first, short batches of the pair loop need) and everything else.
-    // Per chunk: own images -> device, ONE grouped NCCL launch for all its slots, then the asynchronous ingest of its
-    // images.  The second chunk's upload runs on the copy engine under the first batches; its single NCCL kernel needs
-    // to be scheduled once between two persistent kNN kernels (the ingest stream has their priority).
+    // Chunks of doubling size: the first few slots (the images the first, short batches of the pair loop need), then
+    // twice as many, ...  Per chunk: own images -> device, ONE grouped NCCL launch for all its slots, then the
+    // asynchronous ingest of its images.  The pair list visits every image against all earlier ones, so the work
+    // unlocked by a chunk grows quadratically while the next chunk's upload (copy engine, PCIe) grows linearly: the
+    // matching stays ahead of the ingest.  A chunk's single NCCL kernel needs to be scheduled once between two
+    // persistent kNN kernels (the ingest stream has their priority).
     const int first = std::min(n_slots, std::max(1, (32 + R - 1) / R));
-    for (int c = 0; c < 2; ++c) {
-      const int s0 = c == 0 ? 0 : first, s1 = c == 0 ? first : n_slots;
-      if (s0 >= s1) continue;
+    for (int s0 = 0, s1 = first; s0 < n_slots; s0 = s1, s1 = std::min(n_slots, 2 * s1)) {
       for (int sl = s0; sl < s1; ++sl) {
         uint8_t* w = ag_own + static_cast<size_t>(sl) * slot_w;
         if (sl < n_own) {
@@ -1375,6 +1377,8 @@ void pm_default_params(pm_params* p) {
   p->ransac_max_iters = 1000;
   p->residual_mode = PM_RESID_SYMMETRIC_EPIPOLAR;
   p->sampler = PM_SAMPLER_OPENCV_MWC;
+  p->essential_confidence = 0.999; // cv::findEssentialMat defaults (GeometricFilter.cpp:26-31)
+  p->essential_threshold = 1.0;
 }
 
 int pm_create(const pm_params* p, const int* device_ids, int n_dev, pm_handle* out) {
@@ -1667,6 +1671,51 @@ static int filter_pair_F(pm_handle h, const float* xy1, const float* xy2, int M,
   if (M < 7) st = PM_PAIR_DROPPED;            // cv::findFundamentalMat returns an empty F for N < 7
   std::memcpy(F, s.h_F, 72);
   if (st != PM_PAIR_FILTERED) { std::memset(F, 0, 72); if (M > 0) std::memset(mask, 0, M); }
+  if (status) *status = st;
+  if (iters) *iters = s.h_iters[0];
+  return PM_OK;
+}
+
+int pm_filter_pair_E(pm_handle h, const float* xy1, const float* xy2, int M, const pm_camera* cam1, const pm_camera* cam2,
+                     double E[9], uint8_t* mask, int32_t* status, int32_t* iters) {
+  if (!h || M < 0 || (M > 0 && (!xy1 || !xy2)) || !E || !cam1 || !cam2) return PM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceCtx& d = *h->devs[0];
+  if (!(cam1->fx > 0) || !(cam1->fy > 0) || !(cam2->fx > 0) || !(cam2->fy > 0))
+    return h->from(d, d.fail(PM_ERR_INVALID, "pm_filter_pair_E: focal lengths must be positive"));
+  cudaSetDevice(d.dev);
+  const int stride = (std::max(M, 1) + 255) / 256 * 256;
+  int rc = d.ensure_slot(d.single, 1, stride, false);
+  if (rc != PM_OK) return h->from(d, rc);
+  Slot& s = d.single;
+  auto ck = [&](cudaError_t e, const char* what) { return e == cudaSuccess ? PM_OK : h->from(d, d.fail_cuda(e, what, __LINE__)); };
+  const size_t need = emat_scratch_bytes(M);
+  if (need > d.e_scratch_bytes) {
+    if (d.e_scratch) cudaFree(d.e_scratch);
+    d.e_scratch = nullptr; d.e_scratch_bytes = 0;
+    if ((rc = ck(cudaMalloc(&d.e_scratch, need), "essential scratch"))) return rc;
+    d.e_scratch_bytes = need;
+  }
+  if (M > 0) {
+    if ((rc = ck(cudaMemcpyAsync(s.pts1, xy1, 8ull * M, cudaMemcpyHostToDevice, s.stream), "pts1 H2D"))) return rc;
+    if ((rc = ck(cudaMemcpyAsync(s.pts2, xy2, 8ull * M, cudaMemcpyHostToDevice, s.stream), "pts2 H2D"))) return rc;
+  }
+  const double c1[6] = {cam1->fx, cam1->fy, cam1->cx, cam1->cy, cam1->k1, cam1->k2};
+  const double c2[6] = {cam2->fx, cam2->fy, cam2->cx, cam2->cy, cam2->k1, cam2->k2};
+  if ((rc = ck(launch_emat_ransac(s.pts1, s.pts2, M, c1, c2, d.prm.essential_confidence, d.prm.essential_threshold,
+                                  d.prm.ransac_max_iters, d.prm.sampler, d.prm.seed, d.e_scratch, s.mask, s.F, s.status,
+                                  s.n_inl, s.iters, s.stream), "essential launch"))) return rc;
+  ++d.stats.kernel_launches;
+  if (M > 0 && mask && (rc = ck(cudaMemcpyAsync(mask, s.mask, M, cudaMemcpyDeviceToHost, s.stream), "mask D2H"))) return rc;
+  if ((rc = ck(cudaMemcpyAsync(s.h_F, s.F, 72, cudaMemcpyDeviceToHost, s.stream), "E D2H"))) return rc;
+  if ((rc = ck(cudaMemcpyAsync(s.h_status, s.status, 4, cudaMemcpyDeviceToHost, s.stream), "status D2H"))) return rc;
+  if ((rc = ck(cudaMemcpyAsync(s.h_iters, s.iters, 4, cudaMemcpyDeviceToHost, s.stream), "iters D2H"))) return rc;
+  if ((rc = ck(cudaStreamSynchronize(s.stream), "sync"))) return rc;
+  d.stats.h2d_bytes += 16ll * M;
+  d.stats.d2h_bytes += (mask ? M : 0) + 80;
+  const int st = s.h_status[0];
+  std::memcpy(E, s.h_F, 72);
+  if (st != PM_PAIR_FILTERED) { std::memset(E, 0, 72); if (M > 0 && mask) std::memset(mask, 0, M); }
   if (status) *status = st;
   if (iters) *iters = s.h_iters[0];
   return PM_OK;

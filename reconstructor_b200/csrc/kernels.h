@@ -159,6 +159,14 @@ cudaError_t launch_ransac(const float2* pts1, const float2* pts2, const int32_t*
                           int32_t* status, int32_t* n_inliers, int32_t* iters, cudaStream_t st,
                           const PairJob* jobs = nullptr);
 
+// essential.cu -- GeometricFilter::estimateEssential: five-point RANSAC of one pair (cam = fx, fy, cx, cy, k1, k2).
+// scratch: emat_scratch_bytes(M) of device memory.
+size_t emat_scratch_bytes(int M);
+cudaError_t launch_emat_ransac(const float2* pts1, const float2* pts2, int M, const double cam1[6], const double cam2[6],
+                               double prob, double threshold, int max_iters, int sampler, unsigned long long seed,
+                               void* scratch, uint8_t* mask, double* E, int32_t* status, int32_t* n_inliers,
+                               int32_t* iters, cudaStream_t st);
+
 // tensor-pipe peak micro-benchmark (l2_tc2.cu, tensor_peak_kernel): kind 0 f16, 1 i8, 2 mxf4
 cudaError_t launch_tensor_peak(int kind, int iters, int num_sms, double* flop_per_launch, cudaStream_t st);
 

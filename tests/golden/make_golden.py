@@ -212,7 +212,49 @@ def gen_eight_point():
     np.savez_compressed(os.path.join(HERE, "eight_point.npz"), **out)
 
 
+
+
+def gen_essential():
+    """cv2.findEssentialMat(p1, p2, K1, d1, K2, d2) -- the call of GeometricFilter::estimateEssential
+    (GeometricFilter.cpp:26-31) with its defaults -- on seeded two-view scenes: equal and unequal cameras, with and
+    without the radial distortion of PinholeCamera (Camera.h:113-123), N from 5 to 2000, 0-50 % outliers."""
+    rng = np.random.default_rng(20261019)
+    out, k = {}, 0
+    for n in (5, 6, 8, 12, 20, 40, 100, 300, 1000, 2000):
+        for of in (0.0, 0.25, 0.5):
+            for cam_mode in (0, 1):
+                if n <= 8 and of > 0:
+                    continue
+                p1, p2 = two_view_scene(rng, n, of, subpixel=False)
+                if cam_mode == 0:          # the reference's cameras at chooseInitialPair: equal, no distortion
+                    c1 = c2 = np.array([1200.0, 1200.0, 1024.0, 768.0, 0.0, 0.0])
+                else:
+                    c1 = np.array([1180.0, 1210.0, 1000.0, 770.0, 0.03, -0.01])
+                    c2 = np.array([1230.0, 1195.0, 1040.0, 760.0, -0.02, 0.015])
+                K1 = np.array([[c1[0], 0, c1[2]], [0, c1[1], c1[3]], [0, 0, 1.0]])
+                K2 = np.array([[c2[0], 0, c2[2]], [0, c2[1], c2[3]], [0, 0, 1.0]])
+                d1 = np.array([c1[4], c1[5], 0.0, 0.0]).reshape(4, 1)
+                d2 = np.array([c2[4], c2[5], 0.0, 0.0]).reshape(4, 1)
+                E, mask = cv2.findEssentialMat(p1.reshape(-1, 1, 2), p2.reshape(-1, 1, 2), K1, d1, K2, d2)
+                ok = E is not None and E.shape[0] >= 3
+                out[f"e{k}_p1"] = p1; out[f"e{k}_p2"] = p2; out[f"e{k}_c1"] = c1; out[f"e{k}_c2"] = c2
+                out[f"e{k}_ok"] = np.array(int(ok))
+                out[f"e{k}_E"] = np.asarray(E[:3], np.float64) if ok else np.zeros((3, 3))
+                out[f"e{k}_mask"] = mask.reshape(-1).astype(np.uint8) if ok and mask is not None else np.zeros(n, np.uint8)
+                k += 1
+    out["n_scenes"] = np.array(k)
+    out["cv2_version"] = np.array(cv2.__version__)
+    np.savez_compressed(os.path.join(HERE, "essential.npz"), **out)
+    return k
+
+
 if __name__ == "__main__":
-    if "--eight-point" not in sys.argv:      # --eight-point: only (re)generate eight_point.npz from the committed scenes
+    # --eight-point / --essential: only (re)generate that file (the others stay as committed)
+    if "--eight-point" in sys.argv:
+        gen_eight_point()
+    elif "--essential" in sys.argv:
+        print("essential scenes:", gen_essential())
+    else:
         main()
-    gen_eight_point()
+        gen_eight_point()
+        gen_essential()

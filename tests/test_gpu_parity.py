@@ -1159,3 +1159,46 @@ def test_tensor_peaks_are_measured_and_plausible():
     print("tensor peaks TFLOP/s: f16 %.0f  i8 %.0f  mxf4 %.0f" % (f16 / 1e12, i8 / 1e12, fp4 / 1e12))
     assert 0.8e15 < f16 < 2.6e15 and 1.6e15 < i8 < 5.2e15 and 3.0e15 < fp4 < 10.5e15
     assert 1.6 < i8 / f16 < 2.4 and 1.5 < fp4 / i8 < 2.4
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: GeometricFilter::estimateEssential
+# ---------------------------------------------------------------------------------------------
+def test_essential_masks_identical_to_cv2_and_cpu_filter(golden_dir):
+    g = np.load(os.path.join(golden_dir, "essential.npz"))
+    n = int(g["n_scenes"])
+    checked = 0
+    with api.PairMatcher() as pm:
+        for k in range(n):
+            p1, p2, c1, c2 = g[f"e{k}_p1"], g[f"e{k}_p2"], g[f"e{k}_c1"], g[f"e{k}_c2"]
+            E, mask, st, it = pm.estimate_essential(p1, p2, api.Camera(*c1), api.Camera(*c2))
+            ok, Eo, mo, tr = orc.find_essential(p1, p2, orc.Camera(*c1), orc.Camera(*c2))
+            # GPU <-> repo CPU filter: identical masks, iteration counts, E
+            assert (st == api.PAIR_FILTERED) == ok, k
+            assert np.array_equal(mask, mo), (k, int(mask.sum()), int(mo.sum()))
+            if p1.shape[0] > 5:
+                assert it == tr.iters_run, (k, it, tr.iters_run)
+            assert np.abs(E - Eo).max() < 1e-9, (k, np.abs(E - Eo).max())
+            # GPU <-> cv2.findEssentialMat: identical masks; E up to sign (N = 5: cv2 keeps the first model of ITS order)
+            assert np.array_equal(mask, g[f"e{k}_mask"]), k
+            Eg = g[f"e{k}_E"]
+            if p1.shape[0] > 5:
+                assert min(np.abs(E - Eg).max(), np.abs(E + Eg).max()) < 1e-4, k
+            checked += 1
+        # too few points / degenerate input
+        cam = api.Camera(1200, 1200, 1024, 768, 0, 0)
+        E, mask, st, it = pm.estimate_essential(np.zeros((4, 2), np.float32), np.ones((4, 2), np.float32), cam, cam)
+        assert st == api.PAIR_DROPPED and not E.any()
+        E, mask, st, it = pm.estimate_essential(np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32), cam, cam)
+        assert st == api.PAIR_DROPPED
+        with pytest.raises(api.PairMatchError):
+            pm.estimate_essential(g["e10_p1"], g["e10_p2"], api.Camera(0, 1200, 1, 1, 0, 0), cam)
+    assert checked >= 40
+    # Philox sampler: GPU <-> CPU filter identity
+    with api.PairMatcher(sampler=api.SAMPLER_PHILOX, seed=4242) as pm:
+        for k in (10, 20, 30, 40, 45):
+            p1, p2, c1, c2 = g[f"e{k}_p1"], g[f"e{k}_p2"], g[f"e{k}_c1"], g[f"e{k}_c2"]
+            E, mask, st, it = pm.estimate_essential(p1, p2, api.Camera(*c1), api.Camera(*c2))
+            ok, Eo, mo, tr = orc.find_essential(p1, p2, orc.Camera(*c1), orc.Camera(*c2), sampler=orc.SAMPLER_PHILOX, seed=4242)
+            assert (st == api.PAIR_FILTERED) == ok and np.array_equal(mask, mo) and it == tr.iters_run, k
+            assert np.abs(E - Eo).max() < 1e-9

@@ -210,3 +210,63 @@ def test_eight_point_matches_cv2_golden(scenes, golden_dir):
     assert not orc.eight_point(scenes["s30_p1"][:7], scenes["s30_p2"][:7])[0]
     same = np.tile(np.array([[5.0, 9.0]], np.float32), (20, 1))
     assert not orc.eight_point(same, same)[0]
+
+
+# ---------------------------------------------------------------------------------------------
+# GeometricFilter::estimateEssential = cv::findEssentialMat
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def essential(golden_dir):
+    return np.load(os.path.join(golden_dir, "essential.npz"))
+
+
+def test_essential_oracle_matches_cv2_golden(essential):
+    """Masks identical to cv2.findEssentialMat on every golden scene (equal / unequal / distorted cameras, N = 5..2000,
+    up to 50 % outliers); E equal up to sign within 1e-4 (cv2's float undistortion is vectorised) whenever N > 5 -- for
+    N = 5 cv2 returns the first model of ITS solver order, which is not reproducible (any returned model must fit)."""
+    g = essential
+    n = int(g["n_scenes"])
+    assert n >= 40
+    for k in range(n):
+        p1, p2, c1, c2 = g[f"e{k}_p1"], g[f"e{k}_p2"], g[f"e{k}_c1"], g[f"e{k}_c2"]
+        ok, E, m, tr = orc.find_essential(p1, p2, orc.Camera(*c1), orc.Camera(*c2))
+        assert ok == bool(int(g[f"e{k}_ok"]))
+        assert np.array_equal(m, g[f"e{k}_mask"]), k
+        Eg = g[f"e{k}_E"]
+        if p1.shape[0] > 5:
+            assert min(np.abs(E - Eg).max(), np.abs(E + Eg).max()) < 1e-4, k
+        assert abs(np.linalg.norm(E) - 1.0) < 1e-12
+        # an essential matrix: two equal singular values and a zero one
+        sv = np.linalg.svd(E, compute_uv=False)
+        assert abs(sv[0] - sv[1]) < 1e-6 and sv[2] < 1e-6, (k, sv)
+
+
+def test_five_point_solver_exact_geometry():
+    """Noise-free normalised correspondences of a known motion: one of the models is [t]x R."""
+    rng = np.random.default_rng(5)
+    for trial in range(20):
+        X = rng.uniform(-1, 1, (5, 3)) + np.array([0, 0, 5.0])
+        a = 0.3 * rng.standard_normal(3)
+        th = np.linalg.norm(a); kx = a / th
+        Kx = np.array([[0, -kx[2], kx[1]], [kx[2], 0, -kx[0]], [-kx[1], kx[0], 0]])
+        R = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+        t = rng.standard_normal(3)
+        Y = X @ R.T + t
+        m1, m2 = X[:, :2] / X[:, 2:], Y[:, :2] / Y[:, 2:]
+        Es = orc.five_point(m1, m2)
+        tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+        Et = tx @ R; Et /= np.linalg.norm(Et)
+        assert 1 <= len(Es) <= 10
+        assert min(min(np.abs(E - Et).max(), np.abs(E + Et).max()) for E in Es) < 1e-8, trial
+        for E in Es:      # every model satisfies the five epipolar constraints
+            r = np.einsum("ni,ij,nj->n", np.c_[m2, np.ones(5)], E, np.c_[m1, np.ones(5)])
+            assert np.abs(r).max() < 1e-9
+
+
+def test_essential_small_and_degenerate(essential):
+    cam = orc.Camera(1200, 1200, 1024, 768, 0, 0)
+    ok, E, m, tr = orc.find_essential(np.zeros((4, 2), np.float32), np.ones((4, 2), np.float32), cam, cam)
+    assert not ok and not E.any()
+    same = np.tile(np.array([[700.0, 500.0]], np.float32), (30, 1))
+    ok, E, m, tr = orc.find_essential(same, same, cam, cam)      # all-identical points: whatever comes back is finite
+    assert np.isfinite(E).all()
