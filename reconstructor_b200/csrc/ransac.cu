@@ -36,6 +36,10 @@ namespace pm {
 #endif
 static constexpr int RS_THREADS = PM_RS_THREADS;   // 128: 16 K registers per block, co-resident with the persistent tensor kernel
 static constexpr int RS_ROUND = 32;
+#ifndef PM_RS_PPT
+#define PM_RS_PPT 4
+#endif
+static constexpr int RS_PPT = PM_RS_PPT;        // matches per thread and sweep of the scoring loop (early-drop granularity)
 
 struct MwcRng {
   unsigned long long s;
@@ -403,42 +407,128 @@ __device__ __forceinline__ int inlier_of(const double* F, float2 q1, float2 q2, 
   return c == 2 ? literal_inlier(F, q1, q2, mode, thr) : c;
 }
 
-// Adds, for every model of the round, the number of inliers among this thread's four points to sCnt.
-template <int MODE>
-__device__ __forceinline__ void score_models(const double (*sF)[27], const int* sNm, int (*sCnt)[3],
-                                             const unsigned* sDead, int gen, const float2 (&q1)[4],
-                                             const float2 (&q2)[4], const bool (&valid)[4], float thr, double lo,
-                                             double hi, int lane) {
-  Pt4 p[4];
+// ---- (optional, -DPM_RS_FP32=1) the hot classifier in fp32, certified by A-PRIORI per-model error bounds ----------------
+// The fp64 pipe is the bottleneck of outlier-heavy pairs (ncu: half of the kernel's instructions are DFMA / DMUL /
+// DSETP, B200 issues them at half the fp32 rate).  Pixel coordinates are exact in fp32, so only F is rounded; with
+// u = 2^-24, X = the largest |coordinate| of the pair and |F| the magnitudes, every fused fp32 evaluation obeys
+//     |a^ - a| <= 4u A,  A = (|F0| + |F1|) X + |F2|   (likewise B, C, and A1, B1 for the transposed products)
+//     |d^ - d| <= dd  = 16u (X (A + B) + C)            d = x2' F x1 -- ONE numerator: both point-to-line distances share it
+//     |g^ - g| <= dg  = 24u (A^2 + B^2)                 g = a^2 + b^2, per image
+// (derivation: forward error of the fma chains with factor-2 slack; the literal fp64 formula differs from the exact
+// values by ~1e-13 of the same sums, inside that slack).  These are constants of the MODEL, computed once per
+// hypothesis (model_f32), not running bounds per point.  A point is
+//     an inlier for sure   if (|d^| + dd)^2 <  thr (1 - 4e-6) (g^ - dg) for both images
+//     an outlier for sure  if |d^| > 2 dd (no cancellation in the next term) and (|d^| - dd)^2 >= thr (1 + 4e-6) (g^ + dg)
+//                          for either image
+// (the 4e-6 covers the float rounding of err and of these comparisons), otherwise it goes through literal_inlier(),
+// the arbiter: undecided points are those within ~1e-3 of the threshold, ~1e-4 of all.  NaN / inf / g = 0 fail both
+// tests and land in the literal formula's own behaviour.
+#ifdef PM_RANSAC_PROFILE
+__device__ unsigned long long g_prof_iters = 0, g_prof_lit_warps = 0, g_prof_lit_lanes = 0;
+#endif
+struct ModelF32 {
+  float F[9];
+  float dd2, dd_sq, dg1t_lo, dg2t_lo, dg1t_hi, dg2t_hi;          // 2 dd, dd^2, thr_lo dg_k, thr_hi dg_k
+};
+__device__ __forceinline__ void model_f32(const double* F, float X, float thr, ModelF32& o) {
+  const float U = 5.9604645e-8f, UP = 1.0001f;
+  float f[9];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) p[u] = Pt4{q1[u].x, q1[u].y, q2[u].x, q2[u].y};
+  for (int i = 0; i < 9; ++i) { o.F[i] = static_cast<float>(F[i]); f[i] = fabsf(o.F[i]) * UP; }
+  const float A2 = (f[0] + f[1]) * X + f[2], B2 = (f[3] + f[4]) * X + f[5], C2 = (f[6] + f[7]) * X + f[8];
+  const float A1 = (f[0] + f[3]) * X + f[6], B1 = (f[1] + f[4]) * X + f[7];
+  const float dd = 16.f * U * UP * (X * (A2 + B2) + C2);
+  const float dg2 = 24.f * U * UP * (A2 * A2 + B2 * B2), dg1 = 24.f * U * UP * (A1 * A1 + B1 * B1);
+  const float tlo = thr * (1.f - 4e-6f), thi = thr * (1.f + 4e-6f);
+  o.dd2 = 2.f * dd; o.dd_sq = dd * dd * UP;
+  o.dg1t_lo = tlo * dg1 * UP; o.dg2t_lo = tlo * dg2 * UP; o.dg1t_hi = thi * dg1 * UP; o.dg2t_hi = thi * dg2 * UP;
+}
+template <int MODE>
+__device__ __forceinline__ int classify32(const ModelF32& M, float x1, float y1, float x2, float y2, float tlo, float thi) {
+  const float a2 = fmaf(M.F[0], x1, fmaf(M.F[1], y1, M.F[2]));
+  const float b2 = fmaf(M.F[3], x1, fmaf(M.F[4], y1, M.F[5]));
+  const float c2 = fmaf(M.F[6], x1, fmaf(M.F[7], y1, M.F[8]));
+  const float g2 = fmaf(a2, a2, b2 * b2);
+  const float d = fabsf(fmaf(x2, a2, fmaf(y2, b2, c2)));
+  const float a1 = fmaf(M.F[0], x2, fmaf(M.F[3], y2, M.F[6]));
+  const float b1 = fmaf(M.F[1], x2, fmaf(M.F[4], y2, M.F[7]));
+  const float g1 = fmaf(a1, a1, b1 * b1);
+  const float up = fmaf(d, d + M.dd2, M.dd_sq);                    // (|d| + dd)^2, rounded; slack in tlo
+  const float dn = fmaf(d, d - M.dd2, M.dd_sq);                    // (|d| - dd)^2
+  if (MODE == 1) {
+    const float g = g1 + g2;
+    const bool in = up < fmaf(tlo, g, -(M.dg1t_lo + M.dg2t_lo));
+    const bool out = d > M.dd2 && dn >= fmaf(thi, g, M.dg1t_hi + M.dg2t_hi);
+    return in ? 1 : (out ? 0 : 2);
+  }
+  const bool in = up < fmaf(tlo, g1, -M.dg1t_lo) && up < fmaf(tlo, g2, -M.dg2t_lo);
+  const bool out = d > M.dd2 && (dn >= fmaf(thi, g1, M.dg1t_hi) || dn >= fmaf(thi, g2, M.dg2t_hi));
+  return in ? 1 : (out ? 0 : 2);
+}
+
+// Adds, for every model of the round, the number of inliers among this thread's PPT points to its warp's slots sCntW.
+// PM_RS_FP32 = 1 selects the fp32 classifier above.  Measured (B200, 100 x 8192 SIFT, half of the keypoints displaced: 1000
+// iterations per pair): 37.9 k pairs/s against 36.9 k with the fp64 classifier, 0 mismatches in the paranoid build --
+// the scoring loop is bound by the latency of its ~260-instruction body with four resident warps per scheduler, not by
+// the fp64 pipe, so the default stays the fp64 classifier that two rounds of parity runs have exercised.
+#ifndef PM_RS_FP32
+#define PM_RS_FP32 0
+#endif
+template <int MODE, int PPT>
+__device__ __forceinline__ void score_models(const double (*sF)[27], const ModelF32 (*sMf)[3], const int* sNm, int (*sCntW)[3],
+                                             const unsigned* sDead, int gen, const float2 (&q1)[PPT],
+                                             const float2 (&q2)[PPT], const bool (&valid)[PPT], float thr, double lo,
+                                             double hi, int lane) {
+  const float tlo = thr * (1.f - 4e-6f), thi = thr * (1.f + 4e-6f);
   for (int k = 0; k < gen; ++k) {
     const int nm = sNm[k];
     const unsigned dead = sDead[k];
     for (int m = 0; m < nm; ++m) {
       if ((dead >> m) & 1u) continue;                  // cannot beat the best model any more (see the caller)
+      int cls[PPT];
+#if PM_RS_FP32
+      const ModelF32& Mf = sMf[k][m];
+#pragma unroll
+      for (int u = 0; u < PPT; ++u) cls[u] = classify32<MODE>(Mf, q1[u].x, q1[u].y, q2[u].x, q2[u].y, tlo, thi);
+#else
       double F[9];
 #pragma unroll
       for (int i = 0; i < 9; ++i) F[i] = sF[k][9 * m + i];
-      int cls[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) cls[u] = classify<MODE>(F, p[u], lo, hi);
+      for (int u = 0; u < PPT; ++u) cls[u] = classify<MODE>(F, Pt4{q1[u].x, q1[u].y, q2[u].x, q2[u].y}, lo, hi);
+      (void)sMf; (void)tlo; (void)thi;
+#endif
 #ifdef PM_RANSAC_PARANOID      // development build: every decided point is re-checked against the literal formula
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (valid[u] && cls[u] != 2 && literal_inlier(F, q1[u], q2[u], MODE, thr) != cls[u])
+      for (int u = 0; u < PPT; ++u)
+        if (valid[u] && cls[u] != 2 && literal_inlier(&sF[k][9 * m], q1[u], q2[u], MODE, thr) != cls[u])
           printf("RANSAC PARANOID MISMATCH k %d m %d cls %d pt (%g,%g)-(%g,%g)\n", k, m, cls[u], q1[u].x, q1[u].y,
                  q2[u].x, q2[u].y);
       if (lane == 0 && k == 0 && m == 0 && blockIdx.x == 0 && threadIdx.x == 0) printf("paranoid build active\n");
 #endif
       int good = 0;
+#ifdef PM_RANSAC_PROFILE
+      {
+        int und = 0;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (cls[u] == 2 && valid[u]) cls[u] = literal_inlier(F, q1[u], q2[u], MODE, thr);
+        for (int u = 0; u < PPT; ++u) und += (cls[u] == 2 && valid[u]) ? 1 : 0;
+        const int tot_und = __reduce_add_sync(0xffffffffu, und);
+        if (lane == 0) { atomicAdd(&g_prof_iters, 1ull); if (tot_und) { atomicAdd(&g_prof_lit_warps, 1ull); atomicAdd(&g_prof_lit_lanes, static_cast<unsigned long long>(tot_und)); } }
+      }
+#endif
+#pragma unroll
+      for (int u = 0; u < PPT; ++u) {
+#if !defined(PM_RS_EXPERIMENT) || PM_RS_EXPERIMENT != 1
+        if (cls[u] == 2 && valid[u]) cls[u] = literal_inlier(&sF[k][9 * m], q1[u], q2[u], MODE, thr);
+#else
+        if (cls[u] == 2) cls[u] = 0;      // timing experiment only: no literal path
+#endif
         good += valid[u] ? cls[u] : 0;
       }
+      // per-warp slot, plain read-modify-write by lane 0: no atomic, no vote (the tail of this loop body is a chain of
+      // dependent warp-wide operations that one resident warp per scheduler cannot hide)
       const int total = __reduce_add_sync(0xffffffffu, good);
-      if (lane == 0 && total) atomicAdd(&sCnt[k][m], total);
+      if (lane == 0) sCntW[k][m] += total;
     }
   }
 }
@@ -663,8 +753,11 @@ __device__ bool eight_point_refit(const float2* __restrict__ p1, const float2* _
 
 // PHILOX is a template parameter and the refit a kernel of its own (fmat_refit8_kernel): compiled into the one hot
 // kernel, the sampler's local arrays and the refit's Jacobi sweeps cost the OpenCV-replay path 16x (measured).
+#ifndef PM_RS_MINBLOCKS
+#define PM_RS_MINBLOCKS (512 / RS_THREADS)
+#endif
 template <bool PHILOX>
-__global__ void __launch_bounds__(RS_THREADS, 512 / RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, PM_RS_MINBLOCKS)
 fmat_ransac_kernel(const float2* __restrict__ pts1, const float2* __restrict__ pts2,
                    const int32_t* __restrict__ count, int stride, RansacDev prm,
                    uint8_t* __restrict__ mask, double* __restrict__ F_out,
@@ -679,10 +772,12 @@ fmat_ransac_kernel(const float2* __restrict__ pts1, const float2* __restrict__ p
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   __shared__ double sF[RS_ROUND][27];
+  __shared__ ModelF32 sMf[PM_RS_FP32 ? RS_ROUND : 1][3];   // PM_RS_FP32: the models of the round in fp32 + their certified margins
   __shared__ double bestF[9];
   __shared__ int sSub[RS_ROUND][7];
   __shared__ int sNm[RS_ROUND];
   __shared__ int sCnt[RS_ROUND][3];
+  __shared__ int sCntW[RS_THREADS / 32][RS_ROUND][3];   // per-warp partial counts (summed into sCnt between the sweeps)
   __shared__ unsigned sDead[RS_ROUND];                  // bit m: model m of the hypothesis is out of the race
   __shared__ int sGen, sStop, sIter, sNiters, sBest;
 
@@ -805,10 +900,17 @@ fmat_ransac_kernel(const float2* __restrict__ pts1, const float2* __restrict__ p
     PM_PHASE(tV);
     // ---- score: every thread owns four matches at a time and visits all models of the round (the model
     //      is a shared-memory broadcast, the points stay in registers as doubles) ---------------------
-    for (int w = tid; w < gen * 3; w += RS_THREADS) sCnt[w / 3][w % 3] = 0;
+    for (int w = tid; w < gen * 3; w += RS_THREADS) {
+      sCnt[w / 3][w % 3] = 0;
+#pragma unroll
+      for (int wp = 0; wp < RS_THREADS / 32; ++wp) sCntW[wp][w / 3][w % 3] = 0;
+#if PM_RS_FP32
+      if (w % 3 < sNm[w / 3]) model_f32(&sF[w / 3][9 * (w % 3)], sCmax, prm.thr, sMf[w / 3][w % 3]);
+#endif
+    }
     for (int w = tid; w < gen; w += RS_THREADS) sDead[w] = 0u;
     __syncthreads();
-    for (int i0 = 0; i0 < M; i0 += 4 * RS_THREADS) {
+    for (int i0 = 0; i0 < M; i0 += RS_PPT * RS_THREADS) {
       if (i0 > 0) {
         // A model replaces the best one only with STRICTLY more inliers (and more than 6).  Once its count so far
         // plus all the matches not yet visited cannot exceed the best count from before this round, its exact
@@ -816,22 +918,33 @@ fmat_ransac_kernel(const float2* __restrict__ pts1, const float2* __restrict__ p
         // bound, so the selection below ignores it exactly as it would ignore the full count.
         __syncthreads();
         const int bound = sBest > 6 ? sBest : 6;
-        for (int w = tid; w < gen * 3; w += RS_THREADS)
-          if (w % 3 < sNm[w / 3] && sCnt[w / 3][w % 3] + (M - i0) <= bound) atomicOr(&sDead[w / 3], 1u << (w % 3));
+        for (int w = tid; w < gen * 3; w += RS_THREADS) {
+          int c = 0;
+#pragma unroll
+          for (int wp = 0; wp < RS_THREADS / 32; ++wp) c += sCntW[wp][w / 3][w % 3];
+          if (w % 3 < sNm[w / 3] && c + (M - i0) <= bound) atomicOr(&sDead[w / 3], 1u << (w % 3));
+        }
         __syncthreads();
       }
-      float2 q1[4], q2[4];
-      bool valid[4];
+      float2 q1[RS_PPT], q2[RS_PPT];
+      bool valid[RS_PPT];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < RS_PPT; ++u) {
         const int i = i0 + u * RS_THREADS + tid;
         valid[u] = i < M;
         const int ic = valid[u] ? i : M - 1;
         q1[u] = p1[ic];
         q2[u] = p2[ic];
       }
-      if (prm.residual_mode == 1) score_models<1>(sF, sNm, sCnt, sDead, gen, q1, q2, valid, prm.thr, thr_lo, thr_hi, lane);
-      else score_models<0>(sF, sNm, sCnt, sDead, gen, q1, q2, valid, prm.thr, thr_lo, thr_hi, lane);
+      if (prm.residual_mode == 1) score_models<1, RS_PPT>(sF, sMf, sNm, sCntW[warp], sDead, gen, q1, q2, valid, prm.thr, thr_lo, thr_hi, lane);
+      else score_models<0, RS_PPT>(sF, sMf, sNm, sCntW[warp], sDead, gen, q1, q2, valid, prm.thr, thr_lo, thr_hi, lane);
+    }
+    __syncthreads();
+    for (int w = tid; w < gen * 3; w += RS_THREADS) {
+      int c = 0;
+#pragma unroll
+      for (int wp = 0; wp < RS_THREADS / 32; ++wp) c += sCntW[wp][w / 3][w % 3];
+      sCnt[w / 3][w % 3] = c;
     }
     __syncthreads();
     PM_PHASE(tC);
@@ -886,8 +999,8 @@ fmat_ransac_kernel(const float2* __restrict__ pts1, const float2* __restrict__ p
 
 #ifdef PM_RANSAC_PROFILE
   if (tid == 0 && slot < 3)
-    printf("RANSAC slot %d M %d iters %d best %d | sample %lld solve %lld score %lld select %lld cycles\n", slot, M,
-           sIter, sBest, tS, tV, tC, tU);
+    printf("RANSAC slot %d M %d iters %d best %d | sample %lld solve %lld score %lld select %lld cycles | warp-iterations %llu with literal %llu undecided lanes %llu\n", slot, M,
+           sIter, sBest, tS, tV, tC, tU, g_prof_iters, g_prof_lit_warps, g_prof_lit_lanes);
 #endif
   const int best = sBest;
   if (best > 0) {
