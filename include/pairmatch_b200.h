@@ -196,7 +196,7 @@ int pm_remove_image(pm_handle h, int img_id);
  * GPU, image k (0 <= k < n_images_total) extracted by rank k % n_ranks.  Every rank hands over only its own images
  * (ascending id order, n_keypoints rows each, host or device memory) and receives all of them: own images -> device ->
  * ncclAllGather over NVLink / NVSwitch, slot by slot (slot s = images s*R .. s*R+R-1) -> asynchronous ingest, so that
- * pm_match_all_pairs can start on the first slots while later ones are still on the wire.  Nothing waits for the
+ * pm_match_all_pairs starts on the first images while the later ones are still being packed.  Nothing waits for the
  * device; pm_sync_images (or the first matching call that touches an image) does.
  *   wire_dtype  what travels: == dtype, or PM_DESC_U8 for PM_DESC_F32 rows of dim 128 that hold byte values (SIFT,
  *               FeatureDetector.cpp:20-24): 4x fewer bytes; the promise is checked on the device and reported by

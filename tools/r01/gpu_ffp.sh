@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 PY="python -m pytest tests/test_gpu_parity.py -q --timeout 600 -p no:cacheprovider"
 timeout 900 $PY -x -k "superpoint or float or s8 or fuzz" > gpurun_out/tests_ffp.log 2>&1; echo "sp tests exit $?"; tail -3 gpurun_out/tests_ffp.log
-source tools/gpu_misc_fn.sh
+source tools/r01/gpu_misc_fn.sh
 run ffp256 --kind superpoint --images 100 --steps 3 --warmup 2 --no-stages --no-e2e
 export PM_B200_LIB=$PWD/ab/libpm_ffp128.so
 run ffp128 --kind superpoint --images 100 --steps 3 --warmup 2 --no-stages --no-e2e

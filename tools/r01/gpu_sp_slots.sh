@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-source tools/gpu_misc_fn.sh
+source tools/r01/gpu_misc_fn.sh
 export PM_SLOTS=8
 run sp100_pre_s8 --kind superpoint --images 100 --steps 3 --warmup 2 --no-stages --no-e2e
 export PM_SLOTS=12

@@ -1,6 +1,6 @@
 #!/bin/bash
 # the default bench line (with configs) + the GPU tests that failed / are new
-source tools/gpu_fn.sh
+source tools/r02/gpu_fn.sh
 
 
 T0=$(date +%s); python bench.py > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err; echo "bench exit $? in $(( $(date +%s) - T0 )) s"; tail -5 gpurun_out/r2_bench_default.err

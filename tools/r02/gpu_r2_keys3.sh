@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 PY="python -m pytest tests/test_gpu_parity.py -q --timeout 900 -p no:cacheprovider"
 timeout 1200 $PY -x -k "superpoint or float or s8 or fuzz or ragged or ratio_unique or edge_sizes or async or fmat or fountain or golden" > gpurun_out/r2_tests_sp.log 2>&1; echo "sp tests exit $?"; tail -6 gpurun_out/r2_tests_sp.log
-source tools/gpu_misc_fn.sh
+source tools/r01/gpu_misc_fn.sh
 run r2k_sp100 --kind superpoint --images 100 --steps 3 --warmup 2 --no-stages
 run r2k_sp100_six --kind superpoint --images 100 --steps 3 --warmup 2 --no-stages --no-e2e --debug-flags 1048576
 run r2k_sp100_knnonly --kind superpoint --images 100 --steps 3 --warmup 2 --no-stages --no-e2e --dev-ratio 0.01 --dev-no-filter

@@ -1,6 +1,6 @@
 #!/bin/bash
 # 2 GPUs: multi-GPU tests, then the bench line at N=2 (torchrun), then N=1 on the same box for the scaling ratio
-source tools/gpu_fn.sh
+source tools/r02/gpu_fn.sh
 nvidia-smi -L
 timeout 1200 python -m pytest tests/test_gpu_multi.py tests/test_gpu_parity.py -q -m gpu -p no:cacheprovider -k "multi or collective" > gpurun_out/r2_tests_multi.log 2>&1; echo "multi tests exit $?"; tail -8 gpurun_out/r2_tests_multi.log
 N=${1:-2}

@@ -1,6 +1,6 @@
 #!/bin/bash
 # RANSAC under 50 % outliers: batch size, slots in flight, register cap of the RANSAC kernel
-source tools/gpu_fn.sh
+source tools/r02/gpu_fn.sh
 A="--kind sift --images 100 --steps 2 --warmup 1 --no-stages --no-configs --no-cpu-baseline --no-e2e --outlier-frac 0.5"
 run rs_base $A
 run rs_b512 $A --batch-pairs 512

@@ -1,5 +1,5 @@
 #!/bin/bash
-source tools/gpu_fn.sh
+source tools/r02/gpu_fn.sh
 PM_B200_LIB=$PWD/ab/libpm_prof.so python tools/ransac_prof.py 0.5 2>&1 | grep "RANSAC slot" | cut -c1-150
 timeout 600 python -m pytest tests/test_gpu_parity.py -q --timeout 900 -p no:cacheprovider -x -k "fmat or philox or eight_point or pair_body or fountain" > gpurun_out/r2_tests_rs.log 2>&1; echo "ransac tests exit $?"; tail -2 gpurun_out/r2_tests_rs.log
 A="--kind sift --images 100 --steps 2 --warmup 1 --no-stages --no-configs --no-cpu-baseline --no-e2e"
