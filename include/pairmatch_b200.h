@@ -256,6 +256,17 @@ int pm_match_filter_pair(pm_handle h, int img_i, int img_j, pm_pair_result* out)
 int pm_match_all_pairs(pm_handle h, const int32_t* pairs, int64_t n_pairs, pm_csr_result** out);
 int pm_free_result(pm_csr_result* r);
 
+/* Pair pre-selection by image retrieval: the plugin behind ImageMatcher::match (ImageMatcher.h:18-21)
+ * that the reference only has as FakeImgMatcher -- every image with every other one, ImageMatcher.cpp:6-24 -- and lists
+ * as a todo (README.md:40).  Every image of the handle gets a global descriptor (unit-length sum of its unit-length local
+ * descriptors; for binary rows of the +-1 bit vectors) and is paired with its top_k most similar other images (cosine
+ * similarity in fp64, ties to the lower image id).  The result is the canonical pair list pm_match_all_pairs takes:
+ * [n_pairs][2], query = lower image id, the union of both directions, ordered like the implicit all-pairs list.
+ * top_k <= 0 or >= n_images - 1: all pairs (= FakeImgMatcher).  scores (optional): receives the n_images x n_images
+ * similarity matrix in ascending image-id order (caller-allocated).  Free the list with pm_free_pairs. */
+int pm_select_pairs(pm_handle h, int top_k, int32_t** pairs_out, int64_t* n_pairs_out, double* scores);
+int pm_free_pairs(int32_t* pairs);
+
 /* On-disk cache (the reference's README lists "save intermediate steps" as a todo).
  * One little-endian container format (layout: reconstructor_b200/cache.py) with a checksum; a file that
  * fails magic / version / size / checksum validation is rejected with PM_ERR_INVALID.

@@ -38,6 +38,7 @@ EXPORTS = [
     "pm_save_images", "pm_load_images", "pm_save_result", "pm_load_result",
     "pm_filter_pair_F_seeded", "pm_pair_seed", "pm_remove_image", "pm_measure_tensor_peak", "pm_debug_tc_dump",
     "pm_comm_get_unique_id", "pm_comm_init", "pm_ingest_allgather", "pm_filter_pair_E",
+    "pm_select_pairs", "pm_free_pairs",
 ]
 
 
@@ -126,6 +127,8 @@ def load_library() -> C.CDLL:
         lib.pm_pair_seed.argtypes = [C.c_uint64, C.c_int32, C.c_int32]
         lib.pm_pair_seed.restype = C.c_uint64
         lib.pm_remove_image.argtypes = [C.c_void_p, C.c_int]
+        lib.pm_select_pairs.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int64), C.c_void_p]
+        lib.pm_free_pairs.argtypes = [C.POINTER(C.c_int32)]
         lib.pm_comm_get_unique_id.argtypes = [C.c_void_p]
         lib.pm_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         lib.pm_ingest_allgather.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
@@ -354,6 +357,19 @@ class PairMatcher:
         if save_to is not None:
             self._check(self.lib.pm_save_result(res, os.fsencode(save_to)))
         return _csr_to_dict(self.lib, res, copy)
+
+    def select_pairs(self, top_k: int, want_scores=False):
+        """pm_select_pairs: pair pre-selection by global-descriptor retrieval (the ImageMatcher plugin, ImageMatcher.h:18-21).
+        Returns pairs int32 [P, 2] (and the n x n similarity matrix in ascending image-id order)."""
+        ptr = C.POINTER(C.c_int32)(); n = C.c_int64(0)
+        scores = None
+        if want_scores:
+            k = len(self._n)
+            scores = np.zeros((k, k), np.float64)
+        self._check(self.lib.pm_select_pairs(self.h, top_k, C.byref(ptr), C.byref(n), scores.ctypes.data if want_scores else None))
+        pairs = np.ctypeslib.as_array(ptr, shape=(max(n.value, 1) * 2,))[:2 * n.value].copy().reshape(-1, 2)
+        self.lib.pm_free_pairs(ptr)
+        return (pairs, scores) if want_scores else pairs
 
     # -- on-disk cache ---------------------------------------------------------------------------
     def save_images(self, path: str):

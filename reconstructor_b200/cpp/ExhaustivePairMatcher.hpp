@@ -22,6 +22,39 @@ struct pm_pair_hash {      // not the reference's h1 ^ h2 (SequentialReconstruct
 template <class Hash = pm_pair_hash>
 using FeatureMatchesT = std::unordered_map<std::pair<int, int>, std::unordered_map<int, int>, Hash>;
 
+// ImageMatcher plugin (Mapper/libMapper/ImageMatcher.h:14-24): pair pre-selection by global-descriptor retrieval on the
+// device instead of FakeImgMatcher's "every image with every other one" (ImageMatcher.cpp:6-24; README.md:40 lists image
+// retrieval as a todo).  Same call shape as ImageMatcher::match minus the unused path map; imgMatches receives BOTH
+// directions of every selected pair, like FakeImgMatcher.  topK <= 0: all pairs (FakeImgMatcher's result).
+class CudaRetrievalImgMatcher {
+ public:
+  explicit CudaRetrievalImgMatcher(std::shared_ptr<PairMatchDevice> dev = nullptr, int topK = 0)
+      : dev_(dev ? std::move(dev) : std::make_shared<PairMatchDevice>()), top_k_(topK) {}
+  int match(const std::unordered_map<int, std::vector<FeaturePtr<>>>& features,
+            std::unordered_map<int, std::vector<int>>& imgMatches) {
+    for (const auto& kv : features) {
+      const int rc = dev_->upload(kv.first, kv.second);
+      if (rc != PM_OK) return rc;
+    }
+    int32_t* pairs = nullptr;
+    int64_t n = 0;
+    const int rc = pm_select_pairs(dev_->handle(), top_k_, &pairs, &n, nullptr);
+    if (rc != PM_OK) return rc;
+    for (const auto& kv : features) imgMatches[kv.first];                    // an entry for every image, as the reference
+    for (int64_t p = 0; p < n; ++p) {
+      imgMatches[pairs[2 * p]].push_back(pairs[2 * p + 1]);
+      imgMatches[pairs[2 * p + 1]].push_back(pairs[2 * p]);
+    }
+    pm_free_pairs(pairs);
+    return PM_OK;
+  }
+  const std::shared_ptr<PairMatchDevice>& device() const { return dev_; }
+
+ private:
+  std::shared_ptr<PairMatchDevice> dev_;
+  int top_k_;
+};
+
 class ExhaustivePairMatcher {
  public:
   explicit ExhaustivePairMatcher(std::shared_ptr<PairMatchDevice> dev = nullptr)

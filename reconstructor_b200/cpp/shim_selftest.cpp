@@ -135,6 +135,19 @@ int main() {
     for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { nrm += E2(r, c) * E2(r, c); if (E2(r, c) != E(r, c)) { std::printf("E not deterministic\n"); return 1; } }
     if (inl.size() != m1.size() || n_in < m1.size() / 2 || std::fabs(nrm - 1.0) > 1e-9) { std::printf("estimateEssential: %zu of %zu inliers, |E|^2 = %g\n", n_in, m1.size(), nrm); return 1; }
   }
+  // (6) the ImageMatcher plugin: top-k retrieval lists are symmetric, without self-matches; topK = 0 is FakeImgMatcher
+  {
+    CudaRetrievalImgMatcher fake(dev, 0), top1(dev, 1);
+    std::unordered_map<int, std::vector<int>> all, near;
+    if (fake.match(features, all) != PM_OK || top1.match(features, near) != PM_OK) { std::printf("retrieval failed\n"); return 1; }
+    for (int i = 0; i < n_img; ++i) {
+      if (all[i].size() != static_cast<size_t>(n_img - 1) || near[i].empty() || near[i].size() > all[i].size()) { std::printf("retrieval lists wrong for image %d\n", i); return 1; }
+      for (int j : near[i]) {
+        const auto& back = near[j];
+        if (j == i || std::find(back.begin(), back.end(), i) == back.end()) { std::printf("retrieval list not symmetric\n"); return 1; }
+      }
+    }
+  }
   std::printf("SHIM_OK pairs=%zu matches=%zu device_ms=%.3f\n", viaBatch.size(), total, loop.lastDeviceMs());
   return 0;
 }

@@ -1903,6 +1903,78 @@ int pm_ingest_allgather(pm_handle h, int n_images_total, int n_keypoints, int di
                                                            own_xy, own_on_device != 0));
 }
 
+int pm_select_pairs(pm_handle h, int top_k, int32_t** pairs_out, int64_t* n_pairs_out, double* scores) {
+  if (!h || !pairs_out || !n_pairs_out) return PM_ERR_INVALID;
+  *pairs_out = nullptr; *n_pairs_out = 0;
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceCtx& d = *h->devs[0];
+  if (cudaSetDevice(d.dev) != cudaSuccess) return h->from(d, d.fail(PM_ERR_CUDA, "cudaSetDevice failed"));
+  int rc = d.resolve_all();
+  if (rc != PM_OK) return h->from(d, rc);
+  if (cudaStreamSynchronize(d.ingest) != cudaSuccess) return h->from(d, d.fail(PM_ERR_CUDA, "ingest stream failed"));
+  std::vector<int> ids;
+  for (auto& kv : d.images)
+    if (kv.first != kTmpA && kv.first != kTmpB) ids.push_back(kv.first);
+  std::sort(ids.begin(), ids.end());
+  const int n = static_cast<int>(ids.size());
+  std::vector<int32_t> out;
+  const bool all = top_k <= 0 || top_k >= n - 1;
+  const int k = all ? 0 : top_k;
+  if (n >= 2 && (!all || scores)) {
+    const int gdim = d.dtype == PM_DESC_U8_BITS ? 32 * d.words : d.dim;
+    if (gdim > 512) return h->from(d, d.fail(PM_ERR_UNSUPPORTED, "pm_select_pairs: descriptors of more than 512 elements"));
+    std::vector<int2> himg(n);
+    for (int a = 0; a < n; ++a) { const Image& im = d.images[ids[a]]; himg[a] = make_int2(im.row, im.n); }
+    int2* dimg = nullptr; double *dg = nullptr, *dsim = nullptr; int32_t* dtop = nullptr;
+    auto freeall = [&] { cudaFree(dimg); cudaFree(dg); cudaFree(dsim); cudaFree(dtop); };
+    cudaError_t e = cudaMalloc(&dimg, sizeof(int2) * n);
+    if (e == cudaSuccess) e = cudaMalloc(&dg, sizeof(double) * static_cast<size_t>(n) * gdim);
+    if (e == cudaSuccess) e = cudaMalloc(&dsim, sizeof(double) * static_cast<size_t>(n) * n);
+    if (e == cudaSuccess && k > 0) e = cudaMalloc(&dtop, sizeof(int32_t) * static_cast<size_t>(n) * k);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dimg, himg.data(), sizeof(int2) * n, cudaMemcpyHostToDevice, d.ingest);
+    if (e == cudaSuccess) e = launch_retrieval(d.dtype == PM_DESC_U8_BITS ? nullptr : d.raw, d.dtype == PM_DESC_U8_BITS ? d.bits : nullptr,
+                                               d.dim, d.words, dimg, n, 0, dg, dsim, nullptr, d.ingest);
+    d.stats.kernel_launches += 2;
+    if (e == cudaSuccess && scores)          // the clean matrix, before the selection marks the entries it takes
+      e = cudaMemcpyAsync(scores, dsim, sizeof(double) * static_cast<size_t>(n) * n, cudaMemcpyDeviceToHost, d.ingest);
+    std::vector<int32_t> top(static_cast<size_t>(n) * std::max(k, 1));
+    if (e == cudaSuccess && k > 0) {
+      e = launch_topk(dsim, n, k, dtop, d.ingest);
+      ++d.stats.kernel_launches;
+      if (e == cudaSuccess) e = cudaMemcpyAsync(top.data(), dtop, sizeof(int32_t) * static_cast<size_t>(n) * k, cudaMemcpyDeviceToHost, d.ingest);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d.ingest);
+    freeall();
+    if (e != cudaSuccess) return h->from(d, d.fail_cuda(e, "pm_select_pairs", __LINE__));
+    if (!all) {
+      std::vector<std::pair<int32_t, int32_t>> pr;          // (j, i) with i < j: the order of the implicit all-pairs list
+      for (int a = 0; a < n; ++a)
+        for (int t = 0; t < k; ++t) {
+          const int b = top[static_cast<size_t>(a) * k + t];
+          if (b < 0 || b == a) continue;
+          pr.emplace_back(std::max(a, b), std::min(a, b));
+        }
+      std::sort(pr.begin(), pr.end());
+      pr.erase(std::unique(pr.begin(), pr.end()), pr.end());
+      for (auto& p : pr) { out.push_back(ids[p.second]); out.push_back(ids[p.first]); }
+    }
+  }
+  if (all)
+    for (int b = 1; b < n; ++b)
+      for (int a = 0; a < b; ++a) { out.push_back(ids[a]); out.push_back(ids[b]); }
+  int32_t* buf = static_cast<int32_t*>(std::malloc(std::max<size_t>(out.size(), 1) * sizeof(int32_t)));
+  if (!buf) return h->fail(PM_ERR_OOM, "pm_select_pairs: pair list");
+  if (!out.empty()) std::memcpy(buf, out.data(), out.size() * sizeof(int32_t));
+  *pairs_out = buf;
+  *n_pairs_out = static_cast<int64_t>(out.size() / 2);
+  return PM_OK;
+}
+
+int pm_free_pairs(int32_t* pairs) {
+  std::free(pairs);
+  return PM_OK;
+}
+
 int pm_measure_tensor_peak(pm_handle h, int kind, double* flop_per_s) {
   if (!h || !flop_per_s || kind < 0 || kind > 2) return PM_ERR_INVALID;
   std::lock_guard<std::mutex> lk(h->mu);

@@ -167,6 +167,11 @@ cudaError_t launch_emat_ransac(const float2* pts1, const float2* pts2, int M, co
                                void* scratch, uint8_t* mask, double* E, int32_t* status, int32_t* n_inliers,
                                int32_t* iters, cudaStream_t st);
 
+// retrieval.cu -- pair pre-selection: global descriptors, cosine similarity, top-k (d_img: (first row, n) per image)
+cudaError_t launch_retrieval(const float* raw, const uint32_t* bits, int dim, int words, const int2* d_img, int n_images,
+                             int top_k, double* d_gdesc, double* d_sim, int32_t* d_topk, cudaStream_t st);
+cudaError_t launch_topk(double* d_sim, int n_images, int top_k, int32_t* d_topk, cudaStream_t st);
+
 // tensor-pipe peak micro-benchmark (l2_tc2.cu, tensor_peak_kernel): kind 0 f16, 1 i8, 2 mxf4
 cudaError_t launch_tensor_peak(int kind, int iters, int num_sms, double* flop_per_launch, cudaStream_t st);
 

@@ -1202,3 +1202,61 @@ def test_essential_masks_identical_to_cv2_and_cpu_filter(golden_dir):
             ok, Eo, mo, tr = orc.find_essential(p1, p2, orc.Camera(*c1), orc.Camera(*c2), sampler=orc.SAMPLER_PHILOX, seed=4242)
             assert (st == api.PAIR_FILTERED) == ok and np.array_equal(mask, mo) and it == tr.iters_run, k
             assert np.abs(E - Eo).max() < 1e-9
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: pair pre-selection by retrieval (the ImageMatcher plugin)
+# ---------------------------------------------------------------------------------------------
+def _windowed_images(kind, n_img, n_kp, rng):
+    """Image i observes landmarks of a window around i on a line of landmarks: neighbours overlap, far images do not."""
+    L = 4 * n_kp
+    if kind == "orb":
+        base = rng.integers(0, 256, (L, 32), dtype=np.uint8)
+    elif kind == "sift":
+        base = rng.integers(0, 100, (L, 128)).astype(np.float32)
+    else:
+        base = _unit_rows(rng, L, 256)
+    imgs = []
+    for i in range(n_img):
+        lo = int(i * (L - 2 * n_kp) / max(n_img - 1, 1))
+        ids = lo + rng.permutation(2 * n_kp)[:n_kp]
+        d = base[ids].copy()
+        if kind == "orb":
+            d ^= ((rng.random(d.shape) < 0.03) * rng.integers(1, 256, d.shape)).astype(np.uint8)
+        elif kind == "sift":
+            d = np.clip(d + rng.integers(-2, 3, d.shape), 0, 255).astype(np.float32)
+        else:
+            d = d + 0.2 * rng.standard_normal(d.shape).astype(np.float32) / 16
+            d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+        imgs.append(d)
+    return imgs
+
+
+@pytest.mark.parametrize("kind", ["sift", "orb", "superpoint"])
+def test_pair_preselection_matches_cpu_restatement(kind):
+    from oracle import retrieval_ref
+    rng = np.random.default_rng(77)
+    imgs = _windowed_images(kind, 12, 300, rng)
+    with api.PairMatcher() as pm:
+        for i, d in enumerate(imgs):
+            pm.set_image(i, d)
+        for k in (1, 3, 5):
+            pairs, S = pm.select_pairs(k, want_scores=True)
+            ref = retrieval_ref.select_pairs(imgs, k)
+            assert np.array_equal(pairs, ref), (kind, k)
+            np.testing.assert_allclose(S, retrieval_ref.similarity(imgs), rtol=0, atol=1e-12)
+            assert len(pairs) >= 11 * k // 2
+        # neighbours on the line are what retrieval finds: every (i, i+1) is selected at k = 3
+        p3 = {tuple(p) for p in pm.select_pairs(3).tolist()}
+        assert all((i, i + 1) in p3 for i in range(11))
+        # top_k >= n - 1 (or <= 0): FakeImgMatcher's all-pairs list, in the order of the implicit list
+        allp = pm.select_pairs(0)
+        assert np.array_equal(allp, retrieval_ref.select_pairs(imgs, 0)) and len(allp) == 66
+        assert np.array_equal(pm.select_pairs(11), allp)
+        # the selected list drives the batched loop
+        res = pm.match_all_pairs(pm.select_pairs(2))
+        full = pm.match_all_pairs()
+        idx = {tuple(p): r for r, p in enumerate(full["pair_ij"].tolist())}
+        for p, ij in enumerate(res["pair_ij"].tolist()):
+            r = idx[tuple(ij)]
+            assert np.array_equal(res["q"][res["offsets"][p]:res["offsets"][p + 1]], full["q"][full["offsets"][r]:full["offsets"][r + 1]])

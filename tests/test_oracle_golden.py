@@ -270,3 +270,18 @@ def test_essential_small_and_degenerate(essential):
     same = np.tile(np.array([[700.0, 500.0]], np.float32), (30, 1))
     ok, E, m, tr = orc.find_essential(same, same, cam, cam)      # all-identical points: whatever comes back is finite
     assert np.isfinite(E).all()
+
+
+def test_retrieval_restatement_degenerates_to_fake_img_matcher():
+    """top_k >= n - 1 (or <= 0) gives FakeImgMatcher's list (every image with every other one, ImageMatcher.cpp:6-24) in
+    the canonical order of the pair loop; a finite top_k gives a subset without self-pairs or duplicates."""
+    from oracle import retrieval_ref
+    from reconstructor_b200 import shard
+    rng = np.random.default_rng(3)
+    imgs = [rng.integers(0, 256, (40, 32), dtype=np.uint8) for _ in range(7)]
+    allp = retrieval_ref.select_pairs(imgs, 0)
+    assert np.array_equal(allp, shard.all_pairs(7)) and np.array_equal(retrieval_ref.select_pairs(imgs, 6), allp)
+    p2 = retrieval_ref.select_pairs(imgs, 2)
+    assert len(p2) < len(allp) and (p2[:, 0] < p2[:, 1]).all() and len({tuple(p) for p in p2.tolist()}) == len(p2)
+    S = retrieval_ref.similarity(imgs)
+    assert np.allclose(np.diag(S), 1.0) and np.allclose(S, S.T)
