@@ -265,6 +265,11 @@ int pm_free_result(pm_csr_result* r);
  * top_k <= 0 or >= n_images - 1: all pairs (= FakeImgMatcher).  scores (optional): receives the n_images x n_images
  * similarity matrix in ascending image-id order (caller-allocated).  Free the list with pm_free_pairs. */
 int pm_select_pairs(pm_handle h, int top_k, int32_t** pairs_out, int64_t* n_pairs_out, double* scores);
+/* The same over a subset of the handle's images (img_ids: n_ids distinct ids, any order; NULL = every image): what a
+ * plugin sharing the handle with other users needs (the per-pair matcher keeps cached uploads under ids of its own).
+ * scores is n_ids x n_ids in ascending id order.  PM_ERR_STATE when an id is not set. */
+int pm_select_pairs_among(pm_handle h, const int32_t* img_ids, int n_ids, int top_k, int32_t** pairs_out,
+                          int64_t* n_pairs_out, double* scores);
 int pm_free_pairs(int32_t* pairs);
 
 /* On-disk cache (the reference's README lists "save intermediate steps" as a todo).

@@ -38,7 +38,7 @@ EXPORTS = [
     "pm_save_images", "pm_load_images", "pm_save_result", "pm_load_result",
     "pm_filter_pair_F_seeded", "pm_pair_seed", "pm_remove_image", "pm_measure_tensor_peak", "pm_debug_tc_dump",
     "pm_comm_get_unique_id", "pm_comm_init", "pm_ingest_allgather", "pm_filter_pair_E",
-    "pm_select_pairs", "pm_free_pairs",
+    "pm_select_pairs", "pm_select_pairs_among", "pm_free_pairs",
 ]
 
 
@@ -128,6 +128,8 @@ def load_library() -> C.CDLL:
         lib.pm_pair_seed.restype = C.c_uint64
         lib.pm_remove_image.argtypes = [C.c_void_p, C.c_int]
         lib.pm_select_pairs.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int64), C.c_void_p]
+        lib.pm_select_pairs_among.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.POINTER(C.c_int32)),
+                                              C.POINTER(C.c_int64), C.c_void_p]
         lib.pm_free_pairs.argtypes = [C.POINTER(C.c_int32)]
         lib.pm_comm_get_unique_id.argtypes = [C.c_void_p]
         lib.pm_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
@@ -358,15 +360,21 @@ class PairMatcher:
             self._check(self.lib.pm_save_result(res, os.fsencode(save_to)))
         return _csr_to_dict(self.lib, res, copy)
 
-    def select_pairs(self, top_k: int, want_scores=False):
-        """pm_select_pairs: pair pre-selection by global-descriptor retrieval (the ImageMatcher plugin, ImageMatcher.h:18-21).
+    def select_pairs(self, top_k: int, want_scores=False, ids=None):
+        """pm_select_pairs[_among]: pair pre-selection by global-descriptor retrieval (the ImageMatcher plugin,
+        ImageMatcher.h:18-21) over every image of the handle, or over `ids`.
         Returns pairs int32 [P, 2] (and the n x n similarity matrix in ascending image-id order)."""
         ptr = C.POINTER(C.c_int32)(); n = C.c_int64(0)
         scores = None
+        ids_a = None if ids is None else np.ascontiguousarray(ids, np.int32)
         if want_scores:
-            k = len(self._n)
+            k = len(self._n) if ids_a is None else len(ids_a)
             scores = np.zeros((k, k), np.float64)
-        self._check(self.lib.pm_select_pairs(self.h, top_k, C.byref(ptr), C.byref(n), scores.ctypes.data if want_scores else None))
+        sp = scores.ctypes.data if want_scores else None
+        if ids_a is None:
+            self._check(self.lib.pm_select_pairs(self.h, top_k, C.byref(ptr), C.byref(n), sp))
+        else:
+            self._check(self.lib.pm_select_pairs_among(self.h, ids_a.ctypes.data, len(ids_a), top_k, C.byref(ptr), C.byref(n), sp))
         pairs = np.ctypeslib.as_array(ptr, shape=(max(n.value, 1) * 2,))[:2 * n.value].copy().reshape(-1, 2)
         self.lib.pm_free_pairs(ptr)
         return (pairs, scores) if want_scores else pairs

@@ -38,7 +38,9 @@ class CudaRetrievalImgMatcher {
     }
     int32_t* pairs = nullptr;
     int64_t n = 0;
-    const int rc = pm_select_pairs(dev_->handle(), top_k_, &pairs, &n, nullptr);
+    std::vector<int32_t> ids;                     // only the images handed over: the handle may hold other uploads
+    for (const auto& kv : features) ids.push_back(kv.first);
+    const int rc = pm_select_pairs_among(dev_->handle(), ids.data(), static_cast<int>(ids.size()), top_k_, &pairs, &n, nullptr);
     if (rc != PM_OK) return rc;
     for (const auto& kv : features) imgMatches[kv.first];                    // an entry for every image, as the reference
     for (int64_t p = 0; p < n; ++p) {

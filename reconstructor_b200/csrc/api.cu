@@ -157,6 +157,7 @@ struct Slot {
   int64_t* offsets = nullptr;
   int32_t *out_q = nullptr, *out_t = nullptr;
   uint8_t* out_mask = nullptr;
+  void* rs_ws = nullptr;                                // staged continuation of the epipolar filter (ransac.cu)
   // pinned host
   PairJob *h_jobs = nullptr, *h_rjobs = nullptr;
   int64_t* h_offsets = nullptr;
@@ -176,7 +177,7 @@ struct Slot {
     auto fh = [](auto*& p) { if (p) { cudaFreeHost(p); p = nullptr; } };
     fd(d_jobs); fd(d_rjobs); fd(knn_idx); fd(rev_idx); fd(knn_dist); fd(rev_dist); fd(knn_extra); fd(rev_extra); fd(rr_flag); fd(owner);
     fd(match_q); fd(match_t); fd(count); fd(pts1); fd(pts2); fd(mask); fd(F); fd(status);
-    fd(n_inl); fd(iters); fd(offsets); fd(out_q); fd(out_t); fd(out_mask);
+    fd(n_inl); fd(iters); fd(offsets); fd(out_q); fd(out_t); fd(out_mask); fd(rs_ws);
     fh(h_jobs); fh(h_rjobs); fh(h_offsets); fh(h_q); fh(h_t); fh(h_status); fh(h_ninl);
     fh(h_iters); fh(h_count); fh(h_mask); fh(h_F);
     cap_pairs = stride = 0;
@@ -812,6 +813,7 @@ struct DeviceCtx {
     PM_CUDA(cudaMalloc(&s.n_inl, 4 * pairs));
     PM_CUDA(cudaMalloc(&s.iters, 4 * pairs));
     PM_CUDA(cudaMalloc(&s.offsets, 8 * (pairs + 1)));
+    PM_CUDA(cudaMalloc(&s.rs_ws, ransac_workspace_bytes(pairs)));
     PM_CUDA(cudaMallocHost(&s.h_jobs, sizeof(PairJob) * pairs));
     PM_CUDA(cudaMallocHost(&s.h_rjobs, sizeof(PairJob) * pairs));
     PM_CUDA(cudaMallocHost(&s.h_offsets, 8 * (pairs + 1)));
@@ -888,6 +890,7 @@ struct DeviceCtx {
     //   bit19     real-valued rows, s8 forms: one query row set per cluster instead of two (six chunk keys + chunk re-rank)
     //   bit20     real-valued rows, s8 forms: two row sets, six chunk keys + chunk re-rank (instead of the argmin epilogue
     //             + one-column re-rank, the default)
+    //   bit21     epipolar filter: every iteration in the one-block-per-pair kernel (no staged continuation, ransac.cu)
     const int code = (prm.debug_flags >> 2) & 7;
     const int fcode = (prm.debug_flags >> 7) & 3;
     const int variant = ((prm.debug_flags >> 1) & 1) ^ 1;
@@ -1158,9 +1161,11 @@ struct DeviceCtx {
                           prm.ratio, prm.unique_mode, s.owner, s.match_q, s.match_t, s.pts1, s.pts2,
                           s.count, s.stream));
     if (trace_on && s.ev_tr[1]) PM_CUDA(cudaEventRecord(s.ev_tr[1], s.stream));
+    int rs_launches = 0;
     PM_CUDA(launch_ransac(s.pts1, s.pts2, s.count, n, s.stride, ransac_dev(do_filter), s.mask, s.F,
-                          s.status, s.n_inl, s.iters, s.stream, s.d_jobs));
-    if (prm.refit_8point && do_filter) ++stats.kernel_launches;
+                          s.status, s.n_inl, s.iters, s.stream, s.d_jobs, ((prm.debug_flags >> 21) & 1) ? nullptr : s.rs_ws,
+                          &rs_launches));
+    stats.kernel_launches += rs_launches - 1;            // (the per-pair kernel is part of the 4 below)
     if (trace_on && s.ev_tr[2]) PM_CUDA(cudaEventRecord(s.ev_tr[2], s.stream));
     PM_CUDA(launch_compact(s.count, n, s.stride, s.match_q, s.match_t, s.mask, s.offsets, s.out_q,
                            s.out_t, s.out_mask, s.stream));
@@ -1655,9 +1660,11 @@ static int filter_pair_F(pm_handle h, const float* xy1, const float* xy2, int M,
   RansacDev rp = d.ransac_dev(true);
   rp.seed = key;
   rp.min_matches = 7;   // estimateFundamental itself has no gate; < 7 points cannot be solved
+  int rs_launches = 0;
   if ((rc = ck(launch_ransac(s.pts1, s.pts2, s.count, 1, s.stride, rp, s.mask, s.F, s.status, s.n_inl, s.iters,
-                             s.stream), "ransac launch"))) return rc;
-  ++d.stats.kernel_launches;
+                             s.stream, nullptr, ((d.prm.debug_flags >> 21) & 1) ? nullptr : s.rs_ws, &rs_launches),
+               "ransac launch"))) return rc;
+  d.stats.kernel_launches += rs_launches;
   if (M > 0 && (rc = ck(cudaMemcpyAsync(mask, s.mask, M, cudaMemcpyDeviceToHost, s.stream), "mask D2H"))) return rc;
   if ((rc = ck(cudaMemcpyAsync(s.h_F, s.F, 72, cudaMemcpyDeviceToHost, s.stream), "F D2H"))) return rc;
   if ((rc = ck(cudaMemcpyAsync(s.h_status, s.status, 4, cudaMemcpyDeviceToHost, s.stream), "status D2H"))) return rc;
@@ -1904,7 +1911,12 @@ int pm_ingest_allgather(pm_handle h, int n_images_total, int n_keypoints, int di
 }
 
 int pm_select_pairs(pm_handle h, int top_k, int32_t** pairs_out, int64_t* n_pairs_out, double* scores) {
-  if (!h || !pairs_out || !n_pairs_out) return PM_ERR_INVALID;
+  return pm_select_pairs_among(h, nullptr, 0, top_k, pairs_out, n_pairs_out, scores);
+}
+
+int pm_select_pairs_among(pm_handle h, const int32_t* img_ids, int n_ids, int top_k, int32_t** pairs_out,
+                          int64_t* n_pairs_out, double* scores) {
+  if (!h || !pairs_out || !n_pairs_out || n_ids < 0 || (n_ids > 0 && !img_ids)) return PM_ERR_INVALID;
   *pairs_out = nullptr; *n_pairs_out = 0;
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceCtx& d = *h->devs[0];
@@ -1913,9 +1925,19 @@ int pm_select_pairs(pm_handle h, int top_k, int32_t** pairs_out, int64_t* n_pair
   if (rc != PM_OK) return h->from(d, rc);
   if (cudaStreamSynchronize(d.ingest) != cudaSuccess) return h->from(d, d.fail(PM_ERR_CUDA, "ingest stream failed"));
   std::vector<int> ids;
-  for (auto& kv : d.images)
-    if (kv.first != kTmpA && kv.first != kTmpB) ids.push_back(kv.first);
-  std::sort(ids.begin(), ids.end());
+  if (img_ids) {
+    ids.assign(img_ids, img_ids + n_ids);
+    std::sort(ids.begin(), ids.end());
+    if (std::adjacent_find(ids.begin(), ids.end()) != ids.end())
+      return h->from(d, d.fail(PM_ERR_INVALID, "pm_select_pairs_among: duplicate image id"));
+    for (int id : ids)
+      if (id == kTmpA || id == kTmpB || !d.images.count(id))
+        return h->from(d, d.fail(PM_ERR_STATE, "pm_select_pairs_among: image %d not set", id));
+  } else {
+    for (auto& kv : d.images)
+      if (kv.first != kTmpA && kv.first != kTmpB) ids.push_back(kv.first);
+    std::sort(ids.begin(), ids.end());
+  }
   const int n = static_cast<int>(ids.size());
   std::vector<int32_t> out;
   const bool all = top_k <= 0 || top_k >= n - 1;

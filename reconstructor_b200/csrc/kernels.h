@@ -154,10 +154,21 @@ cudaError_t launch_compact(const int32_t* count, int n_jobs, int stride, const i
 
 // K5/K6 -- ransac.cu
 // jobs: per-pair Philox keys (PairJob::seed_lo/hi) of the batched loop, or nullptr (prm.seed is the key)
+// workspace: ransac_workspace_bytes(n_jobs) of device memory for the staged continuation of pairs that need more than
+// the first rounds (nullptr: everything stays in the per-pair kernel); n_launches receives the number of kernels queued.
+struct RsState {            // per pair, between the kernels of the staged filter (ransac.cu)
+  unsigned long long rng, key;
+  double bestF[9];
+  int iter, niters, best, gen;
+  int active, handed, halt;
+  float cmax;
+  int nmod, pad;            // live models of the current mega-round (rs_solve_kernel appends to the list)
+};
+size_t ransac_workspace_bytes(int pairs);
 cudaError_t launch_ransac(const float2* pts1, const float2* pts2, const int32_t* count, int n_jobs,
                           int stride, const RansacDev& prm, uint8_t* mask, double* F,
                           int32_t* status, int32_t* n_inliers, int32_t* iters, cudaStream_t st,
-                          const PairJob* jobs = nullptr);
+                          const PairJob* jobs = nullptr, void* workspace = nullptr, int* n_launches = nullptr);
 
 // essential.cu -- GeometricFilter::estimateEssential: five-point RANSAC of one pair (cam = fx, fy, cx, cy, k1, k2).
 // scratch: emat_scratch_bytes(M) of device memory.

@@ -466,6 +466,32 @@ __device__ __forceinline__ int classify32(const ModelF32& M, float x1, float y1,
   return in ? 1 : (out ? 0 : 2);
 }
 
+// Symmetric-epipolar mode, two steps (rs_score_kernel): a point is an outlier as soon as ONE of its two distances is, and
+// for a wrong model almost every point is far from its line in image 2.  Step 1 evaluates that side only (line F x1,
+// numerator d, g2) and its certain-outlier test -- the same inequality as in classify32<0>; only when some lane of the
+// warp cannot be dismissed does step 2 add the other side and the remaining tests.  Same decisions as classify32<0>.
+struct Side2 { float d, g2, dn; bool out; };
+__device__ __forceinline__ Side2 classify32_side2(const ModelF32& M, float x1, float y1, float x2, float y2, float thi) {
+  Side2 r;
+  const float a2 = fmaf(M.F[0], x1, fmaf(M.F[1], y1, M.F[2]));
+  const float b2 = fmaf(M.F[3], x1, fmaf(M.F[4], y1, M.F[5]));
+  const float c2 = fmaf(M.F[6], x1, fmaf(M.F[7], y1, M.F[8]));
+  r.g2 = fmaf(a2, a2, b2 * b2);
+  r.d = fabsf(fmaf(x2, a2, fmaf(y2, b2, c2)));
+  r.dn = fmaf(r.d, r.d - M.dd2, M.dd_sq);                          // (|d| - dd)^2
+  r.out = r.d > M.dd2 && r.dn >= fmaf(thi, r.g2, M.dg2t_hi);
+  return r;
+}
+__device__ __forceinline__ int classify32_rest(const ModelF32& M, const Side2& s, float x2, float y2, float tlo, float thi) {
+  const float a1 = fmaf(M.F[0], x2, fmaf(M.F[3], y2, M.F[6]));
+  const float b1 = fmaf(M.F[1], x2, fmaf(M.F[4], y2, M.F[7]));
+  const float g1 = fmaf(a1, a1, b1 * b1);
+  const float up = fmaf(s.d, s.d + M.dd2, M.dd_sq);                // (|d| + dd)^2
+  const bool in = up < fmaf(tlo, g1, -M.dg1t_lo) && up < fmaf(tlo, s.g2, -M.dg2t_lo);
+  const bool out = s.out || (s.d > M.dd2 && s.dn >= fmaf(thi, g1, M.dg1t_hi));
+  return in ? 1 : (out ? 0 : 2);
+}
+
 // Adds, for every model of the round, the number of inliers among this thread's PPT points to its warp's slots sCntW.
 // PM_RS_FP32 = 1 selects the fp32 classifier above.  Measured (B200, 100 x 8192 SIFT, half of the keypoints displaced: 1000
 // iterations per pair): 37.9 k pairs/s against 36.9 k with the fp64 classifier, 0 mismatches in the paranoid build --
@@ -530,6 +556,79 @@ __device__ __forceinline__ void score_models(const double (*sF)[27], const Model
       const int total = __reduce_add_sync(0xffffffffu, good);
       if (lane == 0) sCntW[k][m] += total;
     }
+  }
+}
+
+// ---- model-major scoring (PM_RS_MM = 1, the default) --------------------------------------------------------------
+// Lane = MODEL (its fp32 entries and certified margins stay in registers), the matches of a staged chunk are
+// shared-memory broadcasts: no per-model reduction, no per-model shared-memory traffic, ~30 fp32 instructions per
+// (model, match) instead of ~65 half-rate fp64 ones.  The classifier is classify32() above (a-priori per-model error
+// bounds); a point it cannot certify goes through literal_inlier(), the arbiter, so every count is the literal one.
+// A chunk of RS_CHUNK matches is split over the warps of the block; every warp visits all model groups (32 models each).
+// Early drop as before: a model whose count so far plus all matches not yet visited cannot exceed the best count from
+// before the round is skipped once all models of its group are in that state (its partial count stays <= the bound,
+// so the selection ignores it exactly as it would ignore the full count).
+#ifndef PM_RS_MM
+#define PM_RS_MM 1
+#endif
+static constexpr int RS_CHUNK = 256;
+template <int MODE>
+__device__ __forceinline__ void score_chunk_mm(const double (*sF)[27], const ModelF32* sMf, const int* sList, int nmod,
+                                               int (*sCnt)[3], const float4* sPts, int j0, int j1, int bound, int rest,
+                                               bool first, float thr, int lane) {
+  const float tlo = thr * (1.f - 4e-6f), thi = thr * (1.f + 4e-6f);
+  for (int g0 = 0; g0 < nmod; g0 += 32) {
+    const int t = g0 + lane;
+    const bool act = t < nmod;
+    const int w = act ? sList[t] : 0;
+    const int k = w / 3, m = w - 3 * k;
+    const bool dead = !act || (!first && sCnt[k][m] + rest <= bound);
+    if (__all_sync(0xffffffffu, dead)) continue;
+    const ModelF32 Mf = sMf[act ? t : 0];
+    int cnt = 0;
+    int j = j0;
+    for (; j + 4 <= j1; j += 4) {
+      int cls[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 q = sPts[j + u];
+        cls[u] = classify32<MODE>(Mf, q.x, q.y, q.z, q.w, tlo, thi);
+      }
+#ifdef PM_RANSAC_PARANOID      // development build: every decided point is re-checked against the literal formula
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 q = sPts[j + u];
+        if (act && cls[u] != 2 && literal_inlier(&sF[k][9 * m], make_float2(q.x, q.y), make_float2(q.z, q.w), MODE, thr) != cls[u])
+          printf("RANSAC PARANOID MISMATCH (model-major) k %d m %d cls %d pt (%g,%g)-(%g,%g)\n", k, m, cls[u], q.x, q.y, q.z, q.w);
+      }
+      if (blockIdx.x == 0 && threadIdx.x == 0 && j == 0 && g0 == 0 && first) printf("paranoid build active (model-major)\n");
+#endif
+#ifdef PM_RANSAC_PROFILE
+      {
+        int und = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) und += (cls[u] == 2 && act) ? 1 : 0;
+        const int tot_und = __reduce_add_sync(0xffffffffu, und);
+        if (lane == 0) { atomicAdd(&g_prof_iters, 4ull); if (tot_und) { atomicAdd(&g_prof_lit_warps, 1ull); atomicAdd(&g_prof_lit_lanes, static_cast<unsigned long long>(tot_und)); } }
+      }
+#endif
+      if (((cls[0] | cls[1] | cls[2] | cls[3]) & 2) && act) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (cls[u] == 2) {
+            const float4 q = sPts[j + u];
+            cls[u] = literal_inlier(&sF[k][9 * m], make_float2(q.x, q.y), make_float2(q.z, q.w), MODE, thr);
+          }
+      }
+      cnt += (cls[0] & 1) + (cls[1] & 1) + (cls[2] & 1) + (cls[3] & 1);
+    }
+    for (; j < j1; ++j) {
+      const float4 q = sPts[j];
+      int c = classify32<MODE>(Mf, q.x, q.y, q.z, q.w, tlo, thi);
+      if (c == 2 && act) c = literal_inlier(&sF[k][9 * m], make_float2(q.x, q.y), make_float2(q.z, q.w), MODE, thr);
+      cnt += c & 1;
+    }
+    if (act && cnt) atomicAdd(&sCnt[k][m], cnt);
   }
 }
 
@@ -762,7 +861,8 @@ fmat_ransac_kernel(const float2* __restrict__ pts1, const float2* __restrict__ p
                    const int32_t* __restrict__ count, int stride, RansacDev prm,
                    uint8_t* __restrict__ mask, double* __restrict__ F_out,
                    int32_t* __restrict__ status, int32_t* __restrict__ n_inliers,
-                   int32_t* __restrict__ iters_out, const PairJob* __restrict__ jobs) {
+                   int32_t* __restrict__ iters_out, const PairJob* __restrict__ jobs,
+                   int cut_iters, RsState* __restrict__ hand) {
   const int slot = blockIdx.x;
   const size_t base = static_cast<size_t>(slot) * stride;
   const float2* p1 = pts1 + base;
@@ -770,14 +870,21 @@ fmat_ransac_kernel(const float2* __restrict__ pts1, const float2* __restrict__ p
   uint8_t* msk = mask + base;
   const int M = count[slot];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (hand && tid == 0) { hand[slot].active = 0; hand[slot].handed = 0; }
 
   __shared__ double sF[RS_ROUND][27];
-  __shared__ ModelF32 sMf[PM_RS_FP32 ? RS_ROUND : 1][3];   // PM_RS_FP32: the models of the round in fp32 + their certified margins
+#if PM_RS_MM
+  __shared__ ModelF32 sMm[RS_ROUND * 3];                // the live models of the round in fp32 + their certified margins
+  __shared__ float4 sPts[RS_CHUNK];                     // staged matches (x1, y1, x2, y2)
+  __shared__ int sList[RS_ROUND * 3];                   // live model t -> 3 * hypothesis + solution
+  __shared__ int sNmod;
+#endif
+  __shared__ ModelF32 sMf[(PM_RS_FP32 && !PM_RS_MM) ? RS_ROUND : 1][3];   // PM_RS_FP32 (match-major build): fp32 models + margins
   __shared__ double bestF[9];
   __shared__ int sSub[RS_ROUND][7];
   __shared__ int sNm[RS_ROUND];
   __shared__ int sCnt[RS_ROUND][3];
-  __shared__ int sCntW[RS_THREADS / 32][RS_ROUND][3];   // per-warp partial counts (summed into sCnt between the sweeps)
+  __shared__ int sCntW[RS_THREADS / 32][PM_RS_MM ? 1 : RS_ROUND][3];   // match-major build: per-warp partial counts
   __shared__ unsigned sDead[RS_ROUND];                  // bit m: model m of the hypothesis is out of the race
   __shared__ int sGen, sStop, sIter, sNiters, sBest;
 
@@ -900,6 +1007,38 @@ fmat_ransac_kernel(const float2* __restrict__ pts1, const float2* __restrict__ p
     PM_PHASE(tV);
     // ---- score: every thread owns four matches at a time and visits all models of the round (the model
     //      is a shared-memory broadcast, the points stay in registers as doubles) ---------------------
+#if PM_RS_MM
+    if (tid == 0) sNmod = 0;
+    for (int w = tid; w < gen * 3; w += RS_THREADS) sCnt[w / 3][w % 3] = 0;
+    __syncthreads();
+    for (int w = tid; w < gen * 3; w += RS_THREADS)
+      if (w % 3 < sNm[w / 3]) {
+        const int t = atomicAdd(&sNmod, 1);              // any order: the counts go back to (hypothesis, solution)
+        sList[t] = w;
+        model_f32(&sF[w / 3][9 * (w % 3)], sCmax, prm.thr, sMm[t]);
+      }
+    __syncthreads();
+    {
+      const int nmod = sNmod;
+      const int bound = sBest > 6 ? sBest : 6;
+      for (int i0 = 0; i0 < M && nmod > 0; i0 += RS_CHUNK) {
+        if (i0 > 0) __syncthreads();                     // the previous chunk is consumed, its counts are in sCnt
+        const int n_here = min(RS_CHUNK, M - i0);
+        for (int i = tid; i < n_here; i += RS_THREADS) {
+          const float2 a = p1[i0 + i], b = p2[i0 + i];
+          sPts[i] = make_float4(a.x, a.y, b.x, b.y);
+        }
+        __syncthreads();
+        constexpr int SL = RS_CHUNK / (RS_THREADS / 32);
+        const int j0 = warp * SL, j1 = min(j0 + SL, n_here);
+        if (j0 < j1) {
+          if (prm.residual_mode == 1) score_chunk_mm<1>(sF, sMm, sList, nmod, sCnt, sPts, j0, j1, bound, M - i0, i0 == 0, prm.thr, lane);
+          else score_chunk_mm<0>(sF, sMm, sList, nmod, sCnt, sPts, j0, j1, bound, M - i0, i0 == 0, prm.thr, lane);
+        }
+      }
+    }
+    __syncthreads();
+#else
     for (int w = tid; w < gen * 3; w += RS_THREADS) {
       sCnt[w / 3][w % 3] = 0;
 #pragma unroll
@@ -947,6 +1086,7 @@ fmat_ransac_kernel(const float2* __restrict__ pts1, const float2* __restrict__ p
       sCnt[w / 3][w % 3] = c;
     }
     __syncthreads();
+#endif   // PM_RS_MM
     PM_PHASE(tC);
     // ---- select: (iteration, model)-ordered "strictly more inliers replaces" with the adaptive bound.
     //      Improvements are rare, so warp 0 jumps from one improving iteration to the next. -----------
@@ -993,6 +1133,18 @@ fmat_ransac_kernel(const float2* __restrict__ pts1, const float2* __restrict__ p
     __syncthreads();
     PM_PHASE(tU);
     if (sStop) break;
+    if (hand && sIter >= cut_iters) {
+      // Not finished after the first rounds: the remaining iterations run as device-wide stages (rs_*_kernel below),
+      // where thousands of hypotheses of many pairs are solved and scored at once instead of 32 per resident block.
+      if (tid == 0) {
+        RsState& o = hand[slot];
+        o.rng = sRng; o.key = pkey; o.iter = sIter; o.niters = sNiters; o.best = sBest; o.cmax = sCmax;
+        o.gen = 0; o.halt = 0;
+        for (int i = 0; i < 9; ++i) o.bestF[i] = sBest > 0 ? bestF[i] : 0.0;
+        o.handed = 1; o.active = 1;
+      }
+      return;
+    }
     round_size = round_size < RS_ROUND ? round_size * 2 : RS_ROUND;
   }
   __syncthreads();
@@ -1020,6 +1172,318 @@ fmat_ransac_kernel(const float2* __restrict__ pts1, const float2* __restrict__ p
   }
 }
 
+// ==== staged continuation: iterations beyond the first rounds as device-wide kernels ==============================
+// A pair whose adaptive bound is still far away after RS_CUT iterations (few inliers: hundreds of iterations, ~2.3 models
+// each, every one scored against every match) is latency-bound in the one-block-per-pair kernel above: 32 hypotheses
+// per round, one resident block per SM next to the persistent kNN kernel.  Such pairs are handed over (RsState) and
+// continue in "mega-rounds" of up to RS_MEGA iterations, each four small kernels over ALL handed-over pairs of the batch:
+//   rs_sample_kernel   the same index stream (OpenCV MWC replay by one thread + parallel collinearity test + serial
+//                      re-play of a rejected subset; or Philox, one subset per thread), RS_MEGA subsets at once;
+//   rs_solve_kernel    one THREAD per hypothesis: the scalar 7-point solver with the 9 x 7 system in registers -- the
+//                      same operations in the same order as the cooperative half-warp solver (bit-identical), but
+//                      thousands of them in flight and no shuffles;
+//   rs_score_kernel    lane = model, block = 32 models x all matches of the pair (score_chunk_mm's classifier);
+//   rs_select_kernel   one warp per pair replays the (iteration, model)-ordered "strictly more inliers replaces" rule
+//                      with the adaptive bound over the mega-round, 32 iterations at a time -- identical to the
+//                      sequential loop because hypotheses at or beyond the shrunken bound are discarded.
+// rs_finalize_kernel writes mask / F / status of the handed-over pairs.  Results are identical to the single-kernel
+// path by construction (same subsets, same models, same counts, same selection order); tests compare both.
+static constexpr int RS_CUT = 56;        // 8 + 16 + 32 iterations in the per-pair kernel
+static constexpr int RS_MEGA = 256;      // iterations per mega-round
+static constexpr int RS_SOLVE_THREADS = 32;   // 152 registers per thread: small blocks pack next to the kNN kernel
+
+struct RsWs {                            // views into the workspace of one slot
+  RsState* state; int* sub; int* nm; int* cnt; int* list; double* models;
+};
+__host__ __device__ inline RsWs rs_views(void* ws, int pairs) {
+  RsWs v;
+  char* p = static_cast<char*>(ws);
+  v.state = reinterpret_cast<RsState*>(p);  p += sizeof(RsState) * static_cast<size_t>(pairs);
+  v.models = reinterpret_cast<double*>(p);  p += sizeof(double) * 27 * RS_MEGA * static_cast<size_t>(pairs);
+  v.sub = reinterpret_cast<int*>(p);        p += sizeof(int) * 7 * RS_MEGA * static_cast<size_t>(pairs);
+  v.nm = reinterpret_cast<int*>(p);         p += sizeof(int) * RS_MEGA * static_cast<size_t>(pairs);
+  v.cnt = reinterpret_cast<int*>(p);        p += sizeof(int) * 3 * RS_MEGA * static_cast<size_t>(pairs);
+  v.list = reinterpret_cast<int*>(p);
+  return v;
+}
+size_t ransac_workspace_bytes(int pairs) {
+  return (sizeof(RsState) + (sizeof(double) * 27 + sizeof(int) * (7 + 1 + 3 + 3)) * RS_MEGA) * static_cast<size_t>(pairs);
+}
+
+template <bool PHILOX>
+__global__ void __launch_bounds__(RS_THREADS)
+rs_sample_kernel(const float2* __restrict__ pts1, const float2* __restrict__ pts2, const int32_t* __restrict__ count,
+                 int stride, RsWs ws) {
+  const int slot = blockIdx.x, tid = threadIdx.x;
+  RsState& st = ws.state[slot];
+  if (!st.active) return;
+  const size_t base = static_cast<size_t>(slot) * stride;
+  const float2* p1 = pts1 + base;
+  const float2* p2 = pts2 + base;
+  const int M = count[slot];
+  int* sub = ws.sub + static_cast<size_t>(slot) * RS_MEGA * 7;
+  __shared__ int sSub[RS_MEGA][7];
+  __shared__ unsigned long long sState[RS_MEGA + 1];
+  __shared__ int sBad, sGen, sHalt;
+  const int want = min(RS_MEGA, st.niters - st.iter);
+  if (tid == 0) { sBad = 0x7fffffff; sHalt = 0; sGen = want > 0 ? want : 0; }
+  __syncthreads();
+  if constexpr (PHILOX) {
+    for (int h = tid; h < want; h += RS_THREADS)
+      if (!philox_subset(p1, p2, M, st.key, st.iter + h, sSub[h])) atomicMin(&sBad, h);
+    __syncthreads();
+    if (tid == 0 && sBad < want) { sGen = sBad; sHalt = 1; }      // no admissible subset: stop there (OpenCV's rule)
+    __syncthreads();
+  } else {
+    // One thread replays the index stream (no point loads), all threads test the subsets for collinearity.  A rejected
+    // subset b (a few per mega-round with integer pixel coordinates) is re-drawn by the sequential sampler, which also
+    // yields the stream position behind it; the subsets after b are then drawn again from there and tested again.
+    const unsigned int inv_m = 0xFFFFFFFFu / static_cast<unsigned int>(M);
+    __shared__ int sFrom;
+    if (tid == 0) { sFrom = 0; sState[0] = st.rng; }
+    __syncthreads();
+    while (true) {
+      const int from = sFrom;
+      if (tid == 0) {
+        MwcRng rng{sState[from]};
+        for (int g = from; g < want; ++g) {
+          sState[g] = rng.s;
+          draw7(rng, static_cast<unsigned int>(M), inv_m, sSub[g]);
+        }
+        sState[want > 0 ? want : 0] = rng.s;
+        sBad = 0x7fffffff;
+      }
+      __syncthreads();
+      for (int w = from * 30 + tid; w < want * 30; w += RS_THREADS) {
+        const int h = w / 30, t = w - 30 * h;
+        if (pair_collinear(t < 15 ? p1 : p2, sSub[h], t < 15 ? t : t - 15)) atomicMin(&sBad, h);
+      }
+      __syncthreads();
+      const int bad = sBad;
+      if (bad >= want) break;
+      if (tid == 0) {
+        MwcRng rng{sState[bad]};
+        if (!get_subset(p1, p2, M, rng, 10000, sSub[bad])) { sHalt = 1; sGen = bad; }
+        sState[bad + 1] = rng.s;
+        sFrom = bad + 1;
+      }
+      __syncthreads();
+      if (sHalt) break;
+    }
+    if (tid == 0) st.rng = sState[sHalt ? sGen : (want > 0 ? want : 0)];
+    __syncthreads();
+  }
+  const int gen = sGen;
+  for (int w = tid; w < gen * 7; w += RS_THREADS) sub[w] = sSub[w / 7][w % 7];
+  if (tid == 0) { st.gen = gen; st.halt = sHalt; st.nmod = 0; }
+}
+
+__global__ void __launch_bounds__(RS_SOLVE_THREADS)
+rs_solve_kernel(const float2* __restrict__ pts1, const float2* __restrict__ pts2, int stride, RsWs ws) {
+  const int slot = blockIdx.y;
+  const RsState& st = ws.state[slot];
+  const int h = blockIdx.x * RS_SOLVE_THREADS + threadIdx.x;
+  if (!st.active || h >= st.gen) return;
+  const size_t base = static_cast<size_t>(slot) * stride;
+  const int* idx = ws.sub + (static_cast<size_t>(slot) * RS_MEGA + h) * 7;
+  float2 m1[7], m2[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) { const int i = idx[k]; m1[k] = pts1[base + i]; m2[k] = pts2[base + i]; }
+  double F[27];
+  const int n = seven_point(m1, m2, F);
+  double* out = ws.models + (static_cast<size_t>(slot) * RS_MEGA + h) * 27;
+  for (int i = 0; i < 9 * n; ++i) out[i] = F[i];
+  ws.nm[static_cast<size_t>(slot) * RS_MEGA + h] = n;
+  if (n > 0) {                                         // live-model list of the pair, any order (counts go back by slot)
+    const int at = atomicAdd(&ws.state[slot].nmod, n);
+    int* list = ws.list + static_cast<size_t>(slot) * RS_MEGA * 3;
+    for (int k = 0; k < n; ++k) list[at + k] = 3 * h + k;
+  }
+}
+
+#ifndef PM_RS_SCORE_MINB
+#define PM_RS_SCORE_MINB 8
+#endif
+template <int MODE>
+__global__ void __launch_bounds__(RS_THREADS, PM_RS_SCORE_MINB)
+rs_score_kernel(const float2* __restrict__ pts1, const float2* __restrict__ pts2, const int32_t* __restrict__ count,
+                int stride, float thr, RsWs ws) {
+  const int slot = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const RsState& st = ws.state[slot];
+  if (!st.active) return;
+  const int nmod = st.nmod;
+  if (blockIdx.x * 32 >= nmod) return;
+  const int t = blockIdx.x * 32 + lane;
+  const bool act = t < nmod;
+  const int w = ws.list[static_cast<size_t>(slot) * RS_MEGA * 3 + (act ? t : blockIdx.x * 32)];   // 3 * hypothesis + solution
+  const double* Fd = ws.models + static_cast<size_t>(slot) * RS_MEGA * 27 + 9 * w;
+  __shared__ float4 sPts[RS_CHUNK];
+  __shared__ int sC[32];
+  if (tid < 32) sC[tid] = 0;
+  ModelF32 Mf;
+  model_f32(Fd, st.cmax, thr, Mf);
+  const float tlo = thr * (1.f - 4e-6f), thi = thr * (1.f + 4e-6f);
+  const size_t base = static_cast<size_t>(slot) * stride;
+  const float2* p1 = pts1 + base;
+  const float2* p2 = pts2 + base;
+  const int M = count[slot];
+  int cnt = 0;
+  for (int i0 = 0; i0 < M; i0 += RS_CHUNK) {
+    __syncthreads();
+    const int n_here = min(RS_CHUNK, M - i0);
+    for (int i = tid; i < n_here; i += RS_THREADS) {
+      const float2 a = p1[i0 + i], b = p2[i0 + i];
+      sPts[i] = make_float4(a.x, a.y, b.x, b.y);
+    }
+    __syncthreads();
+    constexpr int SL = RS_CHUNK / (RS_THREADS / 32);
+    const int j0 = warp * SL, j1 = min(j0 + SL, n_here);
+    if (MODE == 0) {
+#pragma unroll 2
+      for (int j = j0; j < j1; ++j) {
+        const float4 q = sPts[j];
+        const Side2 s2 = classify32_side2(Mf, q.x, q.y, q.z, q.w, thi);
+        int c = 0;
+        if (__any_sync(0xffffffffu, !s2.out && act)) {          // rare for wrong models: the other side + the inlier test
+          c = classify32_rest(Mf, s2, q.z, q.w, tlo, thi);
+          if (c == 2 && act) c = literal_inlier(Fd, make_float2(q.x, q.y), make_float2(q.z, q.w), MODE, thr);
+        }
+#ifdef PM_RANSAC_PARANOID
+        if (act && literal_inlier(Fd, make_float2(q.x, q.y), make_float2(q.z, q.w), MODE, thr) != (c & 1))
+          printf("RANSAC PARANOID MISMATCH (staged) w %d cls %d pt (%g,%g)-(%g,%g)\n", w, c, q.x, q.y, q.z, q.w);
+        if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0 && i0 == 0 && j == 0) printf("paranoid build active (staged)\n");
+#endif
+        cnt += c & 1;
+      }
+    } else {
+      int j = j0;
+      for (; j + 4 <= j1; j += 4) {
+        int cls[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4 q = sPts[j + u];
+          cls[u] = classify32<MODE>(Mf, q.x, q.y, q.z, q.w, tlo, thi);
+        }
+#ifdef PM_RANSAC_PARANOID
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4 q = sPts[j + u];
+          if (act && cls[u] != 2 && literal_inlier(Fd, make_float2(q.x, q.y), make_float2(q.z, q.w), MODE, thr) != cls[u])
+            printf("RANSAC PARANOID MISMATCH (staged) w %d cls %d pt (%g,%g)-(%g,%g)\n", w, cls[u], q.x, q.y, q.z, q.w);
+        }
+        if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0 && i0 == 0 && j == 0) printf("paranoid build active (staged)\n");
+#endif
+        if (((cls[0] | cls[1] | cls[2] | cls[3]) & 2) && act) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (cls[u] == 2) {
+              const float4 q = sPts[j + u];
+              cls[u] = literal_inlier(Fd, make_float2(q.x, q.y), make_float2(q.z, q.w), MODE, thr);
+            }
+        }
+        cnt += (cls[0] & 1) + (cls[1] & 1) + (cls[2] & 1) + (cls[3] & 1);
+      }
+      for (; j < j1; ++j) {
+        const float4 q = sPts[j];
+        int c = classify32<MODE>(Mf, q.x, q.y, q.z, q.w, tlo, thi);
+        if (c == 2 && act) c = literal_inlier(Fd, make_float2(q.x, q.y), make_float2(q.z, q.w), MODE, thr);
+        cnt += c & 1;
+      }
+    }
+  }
+  if (act && cnt) atomicAdd(&sC[lane], cnt);
+  __syncthreads();
+  if (warp == 0 && act) ws.cnt[static_cast<size_t>(slot) * RS_MEGA * 3 + w] = sC[lane];
+}
+
+__global__ void __launch_bounds__(32)
+rs_select_kernel(const int32_t* __restrict__ count, double confidence, RsWs ws) {
+  const int slot = blockIdx.x, lane = threadIdx.x;
+  RsState& st = ws.state[slot];
+  if (!st.active) return;
+  const int M = count[slot];
+  const int gen = st.gen;
+  const int* nmv = ws.nm + static_cast<size_t>(slot) * RS_MEGA;
+  const int* cntv = ws.cnt + static_cast<size_t>(slot) * RS_MEGA * 3;
+  int best = st.best, niters = st.niters, iter = st.iter;
+  int win_h = -1, win_m = -1;
+  bool stop = gen == 0;
+  for (int b0 = 0; b0 < gen && !stop; b0 += 32) {
+    const int g32 = min(32, gen - b0);
+    const int nm = lane < g32 ? nmv[b0 + lane] : 0;
+    const int c0 = nm > 0 ? cntv[3 * (b0 + lane)] : -1, c1 = nm > 1 ? cntv[3 * (b0 + lane) + 1] : -1,
+              c2 = nm > 2 ? cntv[3 * (b0 + lane) + 2] : -1;
+    const int cmax = max(c0, max(c1, c2));
+    const int iter0 = iter;
+    int best_k = -1;
+    unsigned alive = 0xffffffffu;
+    while (true) {
+      const unsigned imp = __ballot_sync(0xffffffffu, cmax > (best > 6 ? best : 6)) & alive;
+      if (!imp) break;
+      const int k = __ffs(imp) - 1;
+      if (iter0 + k >= niters) break;               // iteration k lies beyond the (shrunken) bound
+      int nb = best, nn = niters, bm = -1;
+      if (lane == k) {
+        for (int mm = 0; mm < nm; ++mm) {
+          const int c = mm == 0 ? c0 : (mm == 1 ? c1 : c2);
+          if (c > (nb > 6 ? nb : 6)) {
+            nb = c; bm = mm;
+            nn = update_num_iters(confidence, static_cast<double>(M - c) / M, 7, nn);
+          }
+        }
+      }
+      best = __shfl_sync(0xffffffffu, nb, k);
+      niters = __shfl_sync(0xffffffffu, nn, k);
+      win_m = __shfl_sync(0xffffffffu, bm, k);
+      win_h = b0 + k;
+      best_k = k;
+      alive = k >= 31 ? 0u : ~((2u << k) - 1u);
+    }
+    int kend = niters - iter0;
+    kend = kend < best_k + 1 ? best_k + 1 : kend;
+    kend = kend > g32 ? g32 : kend;
+    iter = iter0 + kend;
+    if (iter >= niters) stop = true;
+  }
+  if (win_h >= 0 && lane < 9) st.bestF[lane] = ws.models[(static_cast<size_t>(slot) * RS_MEGA + win_h) * 27 + 9 * win_m + lane];
+  if (lane == 0) {
+    st.best = best; st.niters = niters; st.iter = iter;
+    if (stop || st.halt) st.active = 0;
+  }
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+rs_finalize_kernel(const float2* __restrict__ pts1, const float2* __restrict__ pts2, const int32_t* __restrict__ count,
+                   int stride, RansacDev prm, uint8_t* __restrict__ mask, double* __restrict__ F_out,
+                   int32_t* __restrict__ status, int32_t* __restrict__ n_inliers, int32_t* __restrict__ iters_out, RsWs ws) {
+  const int slot = blockIdx.x, tid = threadIdx.x;
+  const RsState& st = ws.state[slot];
+  if (!st.handed) return;                         // finished in the per-pair kernel, which wrote its own outputs
+  const size_t base = static_cast<size_t>(slot) * stride;
+  const float2* p1 = pts1 + base;
+  const float2* p2 = pts2 + base;
+  uint8_t* msk = mask + base;
+  const int M = count[slot];
+  const double margin = 1e-9 + 4e-14 * static_cast<double>(st.cmax);
+  const double thr_d = prm.thr, thr_lo = thr_d * (1.0 - margin), thr_hi = thr_d * (1.0 + 2.5e-7) * (1.0 + margin);
+  const int best = st.best;
+  if (best > 0) {
+    double F[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) F[i] = st.bestF[i];
+    for (int i = tid; i < M; i += RS_THREADS)
+      msk[i] = static_cast<uint8_t>(inlier_of(F, p1[i], p2[i], prm.residual_mode, prm.thr, thr_lo, thr_hi));
+  } else {
+    for (int i = tid; i < M; i += RS_THREADS) msk[i] = 0;
+  }
+  if (tid == 0) {
+    status[slot] = best > 0 ? 1 : 2;
+    n_inliers[slot] = best;
+    iters_out[slot] = st.iter;
+    for (int i = 0; i < 9; ++i) F_out[9 * slot + i] = best > 0 ? st.bestF[i] : 0.0;
+  }
+}
+
 // Optional refit (pm_params.refit_8point): F of every filtered pair with >= 8 inliers is replaced by the normalised
 // 8-point estimate over its inliers; mask, counts and status stay those of the winning RANSAC hypothesis.
 __global__ void __launch_bounds__(RS_THREADS)
@@ -1042,21 +1506,53 @@ cudaError_t ransac_configure() {
   return cudaFuncSetAttribute(fmat_ransac_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
+int ransac_mega_rounds(int max_iters) {
+  if (max_iters <= RS_CUT) return 0;
+  const int n = (max_iters - RS_CUT + RS_MEGA - 1) / RS_MEGA;
+  return n > 16 ? 0 : n;                      // very long bounds stay in the per-pair kernel
+}
+
 cudaError_t launch_ransac(const float2* pts1, const float2* pts2, const int32_t* count, int n_jobs,
                           int stride, const RansacDev& prm, uint8_t* mask, double* F,
                           int32_t* status, int32_t* n_inliers, int32_t* iters, cudaStream_t st,
-                          const PairJob* jobs) {
+                          const PairJob* jobs, void* workspace, int* n_launches) {
   if (n_jobs <= 0) return cudaSuccess;
+  const int n_mega = (workspace && prm.do_filter) ? ransac_mega_rounds(prm.max_iters) : 0;
+  RsWs ws{};
+  if (n_mega > 0) ws = rs_views(workspace, n_jobs);
+  RsState* hand = n_mega > 0 ? ws.state : nullptr;
+  int launches = 1;
   if (prm.sampler == 1)
     fmat_ransac_kernel<true><<<n_jobs, RS_THREADS, 0, st>>>(pts1, pts2, count, stride, prm, mask, F, status, n_inliers,
-                                                            iters, jobs);
+                                                            iters, jobs, RS_CUT, hand);
   else
     fmat_ransac_kernel<false><<<n_jobs, RS_THREADS, 0, st>>>(pts1, pts2, count, stride, prm, mask, F, status, n_inliers,
-                                                             iters, jobs);
+                                                             iters, jobs, RS_CUT, hand);
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess || !prm.refit_8point || !prm.do_filter) return e;
-  fmat_refit8_kernel<<<n_jobs, RS_THREADS, 0, st>>>(pts1, pts2, count, stride, mask, F, status, n_inliers);
-  return cudaGetLastError();
+  for (int r = 0; r < n_mega && e == cudaSuccess; ++r) {
+    if (prm.sampler == 1) rs_sample_kernel<true><<<n_jobs, RS_THREADS, 0, st>>>(pts1, pts2, count, stride, ws);
+    else rs_sample_kernel<false><<<n_jobs, RS_THREADS, 0, st>>>(pts1, pts2, count, stride, ws);
+    rs_solve_kernel<<<dim3(RS_MEGA / RS_SOLVE_THREADS, n_jobs), RS_SOLVE_THREADS, 0, st>>>(pts1, pts2, stride, ws);
+    if (prm.residual_mode == 1)
+      rs_score_kernel<1><<<dim3(RS_MEGA * 3 / 32, n_jobs), RS_THREADS, 0, st>>>(pts1, pts2, count, stride, prm.thr, ws);
+    else
+      rs_score_kernel<0><<<dim3(RS_MEGA * 3 / 32, n_jobs), RS_THREADS, 0, st>>>(pts1, pts2, count, stride, prm.thr, ws);
+    rs_select_kernel<<<n_jobs, 32, 0, st>>>(count, prm.confidence, ws);
+    launches += 4;
+    e = cudaGetLastError();
+  }
+  if (n_mega > 0 && e == cudaSuccess) {
+    rs_finalize_kernel<<<n_jobs, RS_THREADS, 0, st>>>(pts1, pts2, count, stride, prm, mask, F, status, n_inliers, iters, ws);
+    ++launches;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess && prm.refit_8point && prm.do_filter) {
+    fmat_refit8_kernel<<<n_jobs, RS_THREADS, 0, st>>>(pts1, pts2, count, stride, mask, F, status, n_inliers);
+    ++launches;
+    e = cudaGetLastError();
+  }
+  if (n_launches) *n_launches = launches;
+  return e;
 }
 
 }  // namespace pm
