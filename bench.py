@@ -382,7 +382,10 @@ def kernel_name(kind, flags):
         return "l2_top2_tc2_kernel<T2Cfg<256,2,4>,3>"
     if flags & 524288:
         return "l2_top2_tc2_kernel<T2Cfg<256,2,2>,3,true,3>"
-    return "l2_i8x2_kernel<3,2,2,0,3>" if (flags & 1048576) else "l2_i8x2_kernel<4,2,2,0,3>"
+    if flags & 1048576:
+        return "l2_i8x2_kernel<3,2,2,0,3>"
+    # unit-norm rows (SuperPoint, the synthetic set): the form without the norm K-step; debug bit 23 keeps it
+    return "l2_i8x2_kernel<4,2,2,0,3>" if (flags & 8388608) else "l2_i8x2_kernel<4,2,2,0,3,1>"
 
 
 def orb_form(flags):

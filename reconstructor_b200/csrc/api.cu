@@ -38,6 +38,7 @@ struct Image {
   bool i8_ok = false;    // ... and every row norm fits the byte form's norm block (kind::i8 path allowed)
   bool unit_ok = false;  // finite real-valued rows with |x|^2 <= L2F_MAX_NORM2 and fp16 forms packed
   bool s8_ok = false;    // ... and max |x| <= L2S8_MAX_ABS: the quantised s8 forms are valid (kind::i8 path)
+  bool unit1_ok = false; // ... and every squared row norm within L2S8_UNIT_TOL of 1: the search may drop the norm K-step
   float maxn = 0.f;      // largest squared row norm
   bool has_xy = false;
   // asynchronous ingest (pm_set_image_async): the upload + packing kernels are queued on the ingest stream and
@@ -140,6 +141,7 @@ struct Result {  // owner of a pm_csr_result
 struct Slot {
   int cap_pairs = 0, stride = 0;
   bool mutual = false;
+  bool unit1 = false;                                   // the batch's kNN kernel ran without the norm K-step (e_mode 2 re-rank)
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_done = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_jobs = nullptr, ev_knn = nullptr;
   cudaEvent_t ev_tr[3] = {nullptr, nullptr, nullptr};   // PM_TRACE: after the fix-up / selection / RANSAC of the batch
@@ -230,6 +232,7 @@ struct DeviceCtx {
   // development switches, read from the environment ONCE in init() (never in the batch loop):
   bool result_by_ce = true;                  // PM_RESULT_COPY=kernel: compacted matches leave by copy kernels too
   bool trace_on = false;                     // PM_TRACE: device + host timeline of run_pairs
+  bool staged_hint = false;                  // the last retrieved batch held pairs that ran past the filter's first rounds
   int opt_slots = 0;                         // PM_SLOTS: batches in flight (0 = default)
   bool opt_prefilter = false;                // PM_L2F_PREFILTER: s8-prefilter variant of the re-rank
   std::chrono::steady_clock::time_point trace_t0{};
@@ -597,6 +600,9 @@ struct DeviceCtx {
       float amax;
       std::memcpy(&amax, &rec[1], sizeof(float));
       im.s8_ok = im.unit_ok && amax <= L2S8_MAX_ABS;
+      float dev1;
+      std::memcpy(&dev1, &rec[4], sizeof(float));
+      im.unit1_ok = im.s8_ok && dev1 <= L2S8_UNIT_TOL;
     }
     return PM_OK;
   }
@@ -659,6 +665,7 @@ struct DeviceCtx {
     im.i8_ok = false;
     im.unit_ok = false;
     im.s8_ok = false;
+    im.unit1_ok = false;
     im.maxn = 0.f;
     const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     if (n > 0) {
@@ -764,6 +771,9 @@ struct DeviceCtx {
       float amax;
       std::memcpy(&amax, &h_fstats[0], sizeof(float));
       im.s8_ok = im.unit_ok && amax <= L2S8_MAX_ABS;
+      float dev1;
+      std::memcpy(&dev1, &h_fstats[3], sizeof(float));
+      im.unit1_ok = im.s8_ok && dev1 <= L2S8_UNIT_TOL;
     }
     stats.n_images = static_cast<int32_t>(images.size());
     return PM_OK;
@@ -843,7 +853,7 @@ struct DeviceCtx {
   // Queues the kNN kernel(s) of a batch whose jobs are already in s.h_jobs[0..n).
   int enqueue_knn(Slot& s, int n, bool want_rev, bool timed, float* dump = nullptr, bool fast = false) {
     int max_nq = 0, max_nt = 0;
-    bool all_integral = true, all_unit = true, all_i8 = true, all_s8 = true;
+    bool all_integral = true, all_unit = true, all_i8 = true, all_s8 = true, all_u1 = true;
     double work = 0;
     for (int i = 0; i < n; ++i) {
       max_nq = std::max(max_nq, s.h_jobs[i].nq);
@@ -863,6 +873,7 @@ struct DeviceCtx {
       for (int i = 0; i < n && all_integral; ++i) all_integral = job_integral[i];
       for (int i = 0; i < n && all_i8; ++i) all_i8 = job_i8[i];
       for (int i = 0; i < n && all_s8; ++i) all_s8 = job_s8[i];
+      for (int i = 0; i < n && all_u1; ++i) all_u1 = job_u1[i];
       for (int i = 0; i < n && all_unit; ++i) all_unit = job_unit[i];
     }
     // The kNN kernels of all batches are serialised on one stream (they fill the machine anyway);
@@ -891,6 +902,8 @@ struct DeviceCtx {
     //   bit20     real-valued rows, s8 forms: two row sets, six chunk keys + chunk re-rank (instead of the argmin epilogue
     //             + one-column re-rank, the default)
     //   bit21     epipolar filter: every iteration in the one-block-per-pair kernel (no staged continuation, ransac.cu)
+    //   bit22     epipolar filter: always queue the staged continuation (default: while recent batches needed it)
+    //   bit23     real-valued rows of unit norm: keep the norm K-step of the s8 search (default: dropped, l2_i8x2_kernel NX)
     const int code = (prm.debug_flags >> 2) & 7;
     const int fcode = (prm.debug_flags >> 7) & 3;
     const int variant = ((prm.debug_flags >> 1) & 1) ^ 1;
@@ -909,6 +922,9 @@ struct DeviceCtx {
     // ... and the epilogue reporting the exact argmin column + the second smallest score (one exact column per
     // candidate row in l2f_rerank1 instead of a 16-column chunk); 13 column bits: train images of <= 8192 rows
     const bool use_keys3 = use_tcs8 && max_nt <= L2S8_KEYS3_MAX_NT && !((prm.debug_flags >> 19) & 1) && !((prm.debug_flags >> 20) & 1);
+    // ... without the norm K-step when every train row of the batch has unit norm (SuperPoint); debug bit23 keeps it
+    const bool use_unit1 = use_keys3 && all_u1 && !((prm.debug_flags >> 23) & 1);
+    s.unit1 = use_unit1;
     const int epi_of_code[5] = {3, 0, 1, 2, 4};
     // binary rows: Hamming = |a| + |b| - 2 a.b on the tensor cores (E4M3 {0,1} operands) in the batched loop;
     // debug_flags bit10 keeps the XOR/popc kernel there too (it always serves raw kNN rows / single pairs)
@@ -933,7 +949,7 @@ struct DeviceCtx {
       if (use_tcs8) {
         if ((prm.debug_flags >> 19) & 1)
           return launch_l2s8_tc2(smaps, dim, jobs_d, n, mq, oi, od, ox, s.stride, num_sms, knn_stream);
-        return launch_l2s8x2(smaps, dim, jobs_d, n, mq, oi, od, ox, s.stride, num_sms, knn_stream, use_keys3 ? 1 : 0);
+        return launch_l2s8x2(smaps, dim, jobs_d, n, mq, oi, od, ox, s.stride, num_sms, knn_stream, use_unit1 ? 2 : (use_keys3 ? 1 : 0));
       }
       if (use_tcf) return launch_l2f_tc2(fmaps, dim, jobs_d, n, mq, oi, od, ox, s.stride, num_sms, knn_stream);
       if (!use_tc) return launch_l2_simt(raw, dim, jobs_d, n, mq, oi, od, s.stride, knn_stream);
@@ -1001,7 +1017,7 @@ struct DeviceCtx {
     }
     if (use_keys3) {
       PM_CUDA(launch_l2f_rerank1(raw, fnorm, dim, s.d_jobs, n, max_nq, s.knn_idx, s.knn_dist, s.knn_extra, s.rr_flag, s.stride,
-                                 prm.ratio, d_l2f, sq8, st8, s.stream));
+                                 prm.ratio, d_l2f, sq8, st8, s.stream, s.unit1 ? 2 : 1));
       stats.kernel_launches += 2;
     } else if (use_tcf) {
       PM_CUDA(launch_l2f_fixup(raw, fnorm, dim, s.d_jobs, n, max_nq, s.knn_idx, s.knn_dist, s.knn_extra, s.stride,
@@ -1020,7 +1036,7 @@ struct DeviceCtx {
     }
     return PM_OK;
   }
-  std::vector<char> job_integral, job_unit, job_i8, job_s8;   // per job of the batch being built
+  std::vector<char> job_integral, job_unit, job_i8, job_s8, job_u1;   // per job of the batch being built
 
   // ---- collective ingest (SURVEY 8e "Collective", 2.2 C1): extraction sharded over ranks, one NCCL all-gather ----
   NcclComm comm = nullptr;
@@ -1138,13 +1154,14 @@ struct DeviceCtx {
     const uint64_t ps = pair_seed(prm.seed, i, j);
     s.h_jobs[k] = PairJob{a->second.row, b->second.row, a->second.n, b->second.n, a->second.maxn, b->second.maxn,
                           static_cast<uint32_t>(ps), static_cast<uint32_t>(ps >> 32)};
-    if (static_cast<int>(job_integral.size()) <= k) { job_integral.resize(k + 1); job_unit.resize(k + 1); job_i8.resize(k + 1); job_s8.resize(k + 1); }
+    if (static_cast<int>(job_integral.size()) <= k) { job_integral.resize(k + 1); job_unit.resize(k + 1); job_i8.resize(k + 1); job_s8.resize(k + 1); job_u1.resize(k + 1); }
     // an empty image is compatible with every path (its pairs have no rows to search)
     const Image &ia = a->second, &ib = b->second;
     job_integral[k] = (ia.integral || ia.n == 0) && (ib.integral || ib.n == 0);
     job_unit[k] = (ia.unit_ok || ia.n == 0) && (ib.unit_ok || ib.n == 0);
     job_i8[k] = (ia.i8_ok || ia.n == 0) && (ib.i8_ok || ib.n == 0);
     job_s8[k] = (ia.s8_ok || ia.n == 0) && (ib.s8_ok || ib.n == 0);
+    job_u1[k] = ib.unit1_ok || ib.n == 0;              // the TRAIN image's norms are the ones the search would add
     return PM_OK;
   }
 
@@ -1162,9 +1179,9 @@ struct DeviceCtx {
                           s.count, s.stream));
     if (trace_on && s.ev_tr[1]) PM_CUDA(cudaEventRecord(s.ev_tr[1], s.stream));
     int rs_launches = 0;
+    const bool staged = !((prm.debug_flags >> 21) & 1) && (staged_hint || ((prm.debug_flags >> 22) & 1));
     PM_CUDA(launch_ransac(s.pts1, s.pts2, s.count, n, s.stride, ransac_dev(do_filter), s.mask, s.F,
-                          s.status, s.n_inl, s.iters, s.stream, s.d_jobs, ((prm.debug_flags >> 21) & 1) ? nullptr : s.rs_ws,
-                          &rs_launches));
+                          s.status, s.n_inl, s.iters, s.stream, s.d_jobs, staged ? s.rs_ws : nullptr, &rs_launches));
     stats.kernel_launches += rs_launches - 1;            // (the per-pair kernel is part of the 4 below)
     if (trace_on && s.ev_tr[2]) PM_CUDA(cudaEventRecord(s.ev_tr[2], s.stream));
     PM_CUDA(launch_compact(s.count, n, s.stride, s.match_q, s.match_t, s.mask, s.offsets, s.out_q,
@@ -1228,17 +1245,22 @@ struct DeviceCtx {
       stats.knn_launches += 1;
       stats.knn_work += s.knn_work;
     }
+    int long_runs = 0;
     for (int k = 0; k < n; ++k) {
       const int64_t p = s.first_pair + k;
       R.offsets[p + 1] = base + s.h_offsets[k + 1];
       R.status[p] = s.h_status[k];
       R.n_inliers[p] = s.h_ninl[k];
       R.iters[p] = s.h_iters[k];
+      long_runs += s.h_iters[k] > ransac_stage_cut() ? 1 : 0;
       std::memcpy(&R.F[9 * p], &s.h_F[9 * k], 72);
       stats.putative_matches += s.h_offsets[k + 1] - s.h_offsets[k];
       stats.inlier_matches += s.h_status[k] == PM_PAIR_DROPPED ? 0 : s.h_ninl[k];
     }
     stats.pairs_matched += n;
+    // Scheduling hint only (both forms of the filter give identical results): the staged continuation costs a dozen
+    // nearly empty launches per batch, so it is queued while recent batches held pairs that ran past the first rounds.
+    staged_hint = long_runs > 0;
     s.busy = false;
     return PM_OK;
   }

@@ -98,6 +98,8 @@ cudaError_t launch_pack_float(const float* raw, int n, int dim, __half* qh, __ha
 // the same search with rows quantised to s8 (|x| <= L2S8_MAX_ABS) on kind::i8: half the K-steps; l2f_fixup with
 // e_mode = 1 (the wider error bound of the quantised scores) follows.  maps: UINT8 maps over rows of dim + 32 bytes.
 static constexpr float L2S8_MAX_ABS = 0.5f;
+// rows with | |x|^2 - 1 | <= L2S8_UNIT_TOL everywhere: the s8 search drops the norm K-step (keys3 = 2, e_mode 2 in the re-rank)
+static constexpr float L2S8_UNIT_TOL = 9.765625e-4f;
 cudaError_t s8_configure();
 cudaError_t launch_l2s8_tc2(const TcMaps& maps, int dim, const PairJob* jobs, int n_jobs, int max_nq, int2* idx,
                             float2* dist, float2* extra, int stride, int num_sms, cudaStream_t st);
@@ -121,7 +123,8 @@ cudaError_t launch_l2f_fixup(const float* raw, const float* fnorm, int dim, cons
 // small-footprint l2f_fixup variant over the rows it left open.  flags: one byte per row of the batch (scratch).
 cudaError_t launch_l2f_rerank1(const float* raw, const float* fnorm, int dim, const PairJob* jobs, int n_jobs, int max_nq,
                                int2* idx, float2* dist, float2* extra, uint8_t* flags, int stride, float ratio,
-                               unsigned long long* counters, const uint8_t* q8, const uint8_t* t8, cudaStream_t st);
+                               unsigned long long* counters, const uint8_t* q8, const uint8_t* t8, cudaStream_t st,
+                               int e_mode = 1);
 
 // shared-memory carve-out of the small tail kernels = the tensor kernel's, so that they can be co-resident
 cudaError_t fixup_configure();
@@ -165,6 +168,7 @@ struct RsState {            // per pair, between the kernels of the staged filte
   int nmod, pad;            // live models of the current mega-round (rs_solve_kernel appends to the list)
 };
 size_t ransac_workspace_bytes(int pairs);
+int ransac_stage_cut();      // iterations that always run in the per-pair kernel
 cudaError_t launch_ransac(const float2* pts1, const float2* pts2, const int32_t* count, int n_jobs,
                           int stride, const RansacDev& prm, uint8_t* mask, double* F,
                           int32_t* status, int32_t* n_inliers, int32_t* iters, cudaStream_t st,

@@ -460,33 +460,36 @@ __device__ __forceinline__ int2 keys3_refine(const int (&v)[16]) {
   const unsigned int b2 = __vimin3_u32(u[6], u[7], u[8]), b3 = __vimin3_u32(u[9], u[10], u[11]);
   const unsigned int b4 = __vimin3_u32(u[12], u[13], u[14]);
   const unsigned int um = min(__vimin3_u32(b0, b1, b2), __vimin3_u32(b3, b4, u[15]));
-  return make_int2(pm & 15, static_cast<int>((um - d) >> 4));      // (column inside the chunk, second smallest acc)
-}
+  return make_int2(pm & 15, static_cast<int>(um - d) >> 4);        // (column inside the chunk, second smallest acc;
+}                                                                   //  arithmetic shift: accumulators may be negative)
 // 16 columns starting at train column c (multiple of 16); RAGGED: only the first `lim` (>= 1) exist
-template <bool RAGGED>
+// OFF: constant added to every accumulator of the tile (the norm term of the unit-norm form, which has no norm K-step:
+// see l2_i8x2_kernel NX); it enters the chunk key and the refined second score, not the 16 values
+template <bool RAGGED, int OFF = 0>
 __device__ __forceinline__ void keys3_chunk16(Keys3w& s, const uint32_t* r, int c, int lim) {
   int v[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = (RAGGED && j >= lim) ? T2K_ACC_NONE : static_cast<int>(r[j]);
+  for (int j = 0; j < 16; ++j) v[j] = (RAGGED && j >= lim) ? T2K_ACC_NONE - OFF : static_cast<int>(r[j]);
   const int a0 = __vimin3_s32(v[0], v[1], v[2]), a1 = __vimin3_s32(v[3], v[4], v[5]);
   const int a2 = __vimin3_s32(v[6], v[7], v[8]), a3 = __vimin3_s32(v[9], v[10], v[11]);
   const int a4 = __vimin3_s32(v[12], v[13], v[14]);
   const int cm = min(__vimin3_s32(a0, a1, a2), __vimin3_s32(a3, a4, v[15]));
-  int key = (cm << T2K_COLBITS) + c;
+  int key = cm * (1 << T2K_COLBITS) + (c + OFF * (1 << T2K_COLBITS));
   if (key < min(s.k1, T2K_THRESH_KEY)) {             // new, match-like row minimum: refine (rare)
     const int2 js = keys3_refine(v);
     key += js.x;
-    s.w2 = js.y;
+    s.w2 = js.y + OFF;
   }
   keys3_insert(s, key);
 }
+template <int OFF = 0>
 __device__ __forceinline__ void keys3_chunk32(Keys3w& s, const uint32_t (&v)[32], int c, int lim) {
   if (lim >= 32) {                                   // warp-uniform: the whole 32-column piece exists
-    keys3_chunk16<false>(s, v, c, 16);
-    keys3_chunk16<false>(s, v + 16, c + 16, 16);
+    keys3_chunk16<false, OFF>(s, v, c, 16);
+    keys3_chunk16<false, OFF>(s, v + 16, c + 16, 16);
   } else {
-    if (lim > 0) keys3_chunk16<true>(s, v, c, lim);
-    if (lim > 16) keys3_chunk16<true>(s, v + 16, c + 16, lim - 16);
+    if (lim > 0) keys3_chunk16<true, OFF>(s, v, c, lim);
+    if (lim > 16) keys3_chunk16<true, OFF>(s, v + 16, c + 16, lim - 16);
   }
 }
 // integer key -> the float key l2f_fixup.cu expects: score with the chunk id in the low 10 mantissa bits
@@ -958,7 +961,13 @@ using I8X2 = I8X2Cfg<1>;
 
 // LEAN: 0 = no register cap, 1 = 64 registers (launch bound of 1024 threads), 2 = 72 registers (bound of 896 threads):
 // 640 threads x 72 leave 19 K registers for the tail kernels of earlier batches (the RANSAC block needs 16 K)
-template <int MODE, int LEAN, int KA = 1, int FP4 = 0, int STG = 0>
+// NX = 1 (MODE 4 only, real-valued rows whose squared norms are all within L2S8_UNIT_TOL of 1 -- SuperPoint rows are
+// L2-normalised, FeatureSuperPoint.cpp:195-205): the norm term of the score is the same constant for every train row, so
+// the norm block is neither loaded nor multiplied -- 4 KA K-steps per tile instead of 4 KA + 1 -- and the constant
+// T2K_UNIT_OFF = 254^2 (1/2 + 1) enters the chunk keys in the epilogue.  The scores are those of rows of norm exactly 1;
+// the re-rank's certified bound carries the tolerance (ff_bound e_mode 2).
+static constexpr int T2K_UNIT_OFF = 96774;                      // 254^2 * 1.5, exact
+template <int MODE, int LEAN, int KA = 1, int FP4 = 0, int STG = 0, int NX = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LEAN == 1 ? 1024 : LEAN == 2 ? 896 : I8X2Cfg<KA, FP4 ? 192 : 256>::kThreads, 1)
 l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant__ CUtensorMap q_ext,
                const __grid_constant__ CUtensorMap t_main, const __grid_constant__ CUtensorMap t_ext,
@@ -969,6 +978,7 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
   constexpr int BN = C::kBN, BNH = C::kBNH, ST = C::kStages, TILE = C::kTile, BTILE = C::kBTile, NSL = C::kSlices;
   constexpr int AST = C::kAStages, KDIM = 128 * KA, BATOM = C::kBAtom;
   static_assert(!FP4 || KA == 1, "the fp4 form of a 256-bit row is one 128-byte K atom");
+  static_assert(!NX || MODE == 4, "the unit-norm form exists for the argmin epilogue only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -1036,13 +1046,13 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
         {
           const uint32_t as = ai % AST, use = ai / AST;
           wait_tma(&a_empty[as], (use & 1) ^ 1);
-          if (leader) mbar_expect_tx(&a_full[as], nset * 2 * TILE);
+          if (leader) mbar_expect_tx(&a_full[as], nset * 2 * (NX ? TILE - T2_EXT : TILE));
           for (int set = 0; set < nset; ++set) {
             uint8_t* dst = sA + (as * 2 + set) * TILE;
             const int row = job.q_row + blk * C::kRows + set * T2_ROWS + rank * T2_BM;
 #pragma unroll
             for (int a = 0; a < KA; ++a) tma_load_2d_pair(dst + a * T2_ATOM, &q_main, 128 * a, row, &a_full[as]);
-            tma_load_2d_pair(dst + KA * T2_ATOM, &q_ext, KDIM, row, &a_full[as]);
+            if (!NX) tma_load_2d_pair(dst + KA * T2_ATOM, &q_ext, KDIM, row, &a_full[as]);
           }
         }
         ++ai;
@@ -1051,11 +1061,11 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
           const int row = job.t_row + n * BN + rank * BNH;        // this CTA's half of the train tile
           const uint32_t st = bi % ST;
           wait_tma(&b_empty[st], ((bi / ST) & 1) ^ 1);
-          if (leader) mbar_expect_tx(&b_full[st], 2 * BTILE);
+          if (leader) mbar_expect_tx(&b_full[st], 2 * (NX ? BTILE - BNH * 32 : BTILE));
           uint8_t* dst = sB + st * BTILE;
 #pragma unroll
           for (int a = 0; a < KA; ++a) tma_load_2d_pair(dst + a * BATOM, &t_main, 128 * a, row, &b_full[st]);
-          tma_load_2d_pair(dst + KA * BATOM, &t_ext, KDIM, row, &b_full[st]);
+          if (!NX) tma_load_2d_pair(dst + KA * BATOM, &t_ext, KDIM, row, &b_full[st]);
         }
       }
     }
@@ -1104,8 +1114,9 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
                                    (static_cast<uint64_t>(HI128) << 32) | (a_lo + (((k >> 2) * T2_ATOM + (k & 3) * 32) >> 4)),
                                    (static_cast<uint64_t>(HI128) << 32) | (b_lo + (((k >> 2) * BATOM + (k & 3) * 32) >> 4)),
                                    MODE >= 3 ? C::kIdescS8 : C::kIdesc, k > 0 ? 1u : 0u);
-                umma_f16_pair<2>(d_tmem, (static_cast<uint64_t>(HI32) << 32) | (a_lo + ((KA * T2_ATOM) >> 4)),
-                                 (static_cast<uint64_t>(HI32) << 32) | (b_lo + ((KA * BATOM) >> 4)), C::kIdescExt, 1u);
+                if (!NX)
+                  umma_f16_pair<2>(d_tmem, (static_cast<uint64_t>(HI32) << 32) | (a_lo + ((KA * T2_ATOM) >> 4)),
+                                   (static_cast<uint64_t>(HI32) << 32) | (b_lo + ((KA * BATOM) >> 4)), C::kIdescExt, 1u);
               }
               umma_commit_pair(&acc_full[set]);
               if (set == nset - 1) umma_commit_pair(&b_empty[st]);
@@ -1154,13 +1165,13 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
               tmem_ld_32x32b_x32(tq + set * BN, v);
               if (MODE == 2) t2i_chunk32(set ? s1 : s0, v, c0, lim);
               if (MODE == 3) keysi_chunk32(set ? g1 : g0, v, c0, lim);
-              if (MODE == 4) keys3_chunk32(set ? h1 : h0, v, c0, lim);
+              if (MODE == 4) keys3_chunk32<NX ? T2K_UNIT_OFF : 0>(set ? h1 : h0, v, c0, lim);
               tmem_ld_32x32b_x32(tq + set * BN + 32, v);
               tc_fence_before();
               if (lane == 0) mbar_arrive_leader(&acc_empty[set]);
               if (MODE == 2) t2i_chunk32(set ? s1 : s0, v, c0 + 32, lim - 32);
               if (MODE == 3) keysi_chunk32(set ? g1 : g0, v, c0 + 32, lim - 32);
-              if (MODE == 4) keys3_chunk32(set ? h1 : h0, v, c0 + 32, lim - 32);
+              if (MODE == 4) keys3_chunk32<NX ? T2K_UNIT_OFF : 0>(set ? h1 : h0, v, c0 + 32, lim - 32);
             }
           }
         }
@@ -1275,12 +1286,12 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
   }
 }
 
-template <int MODE, int LEAN, int KA = 1, int FP4 = 0, int STG = 0>
+template <int MODE, int LEAN, int KA = 1, int FP4 = 0, int STG = 0, int NX = 0>
 static cudaError_t i8x2_attr() {
-  cudaError_t e = cudaFuncSetAttribute(l2_i8x2_kernel<MODE, LEAN, KA, FP4, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(l2_i8x2_kernel<MODE, LEAN, KA, FP4, STG, NX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        I8X2Cfg<KA, FP4 ? 192 : 256, STG>::kSmemBytes);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(l2_i8x2_kernel<MODE, LEAN, KA, FP4, STG>, cudaFuncAttributePreferredSharedMemoryCarveout,
+  return cudaFuncSetAttribute(l2_i8x2_kernel<MODE, LEAN, KA, FP4, STG, NX>, cudaFuncAttributePreferredSharedMemoryCarveout,
                               cudaSharedmemCarveoutMaxShared);
 }
 
@@ -1338,7 +1349,13 @@ cudaError_t launch_l2s8x2(const TcMaps& maps, int dim, const PairJob* jobs, int 
   int clusters = num_sms / 2;
   if (n_items < clusters) clusters = n_items;
   const int grid = clusters * 2;
-  if (dim == 256 && keys3)
+  if (dim == 256 && keys3 == 2)       // every train row of unit norm: no norm K-step (NX)
+    l2_i8x2_kernel<4, PM_S8X2_LEAN, 2, 0, PM_S8X2_STAGES, 1><<<grid, C2::kThreads, C2::kSmemBytes, st>>>(
+        maps.q_main, maps.q_ext, maps.t_main, maps.t_ext, jobs, n_jobs, blocks_per_job, idx, dist, stride, extra);
+  else if (dim == 128 && keys3 == 2)
+    l2_i8x2_kernel<4, PM_S8X2_LEAN, 1, 0, 0, 1><<<grid, C1::kThreads, C1::kSmemBytes, st>>>(
+        maps.q_main, maps.q_ext, maps.t_main, maps.t_ext, jobs, n_jobs, blocks_per_job, idx, dist, stride, extra);
+  else if (dim == 256 && keys3)
     l2_i8x2_kernel<4, PM_S8X2_LEAN, 2, 0, PM_S8X2_STAGES><<<grid, C2::kThreads, C2::kSmemBytes, st>>>(
         maps.q_main, maps.q_ext, maps.t_main, maps.t_ext, jobs, n_jobs, blocks_per_job, idx, dist, stride, extra);
   else if (dim == 128 && keys3)
@@ -1359,6 +1376,8 @@ cudaError_t i8x2_configure() {
   cudaError_t e;
   if ((e = i8x2_attr<4, PM_S8X2_LEAN, 2, 0, PM_S8X2_STAGES>()) != cudaSuccess) return e;
   if ((e = i8x2_attr<4, PM_S8X2_LEAN, 1>()) != cudaSuccess) return e;
+  if ((e = i8x2_attr<4, PM_S8X2_LEAN, 2, 0, PM_S8X2_STAGES, 1>()) != cudaSuccess) return e;
+  if ((e = i8x2_attr<4, PM_S8X2_LEAN, 1, 0, 0, 1>()) != cudaSuccess) return e;
   if ((e = i8x2_attr<3, PM_S8X2_LEAN, 2, 0, PM_S8X2_STAGES>()) != cudaSuccess) return e;
   if ((e = i8x2_attr<3, PM_S8X2_LEAN, 1>()) != cudaSuccess) return e;
   if ((e = i8x2_attr<2, false>()) != cudaSuccess) return e;

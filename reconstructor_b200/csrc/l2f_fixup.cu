@@ -51,7 +51,8 @@ struct FfBound {          // per query row: exact_d2(col) is within [K - eps(K) 
   }
 };
 
-// e_mode 0: fp16 operand forms (l2_tc2.cu MODE 3, kind::f16); 1: rows quantised to s8 with scale 254 (KIND 3)
+// e_mode 0: fp16 operand forms (l2_tc2.cu MODE 3, kind::f16); 1: rows quantised to s8 with scale 254 (KIND 3);
+// 2: as 1, train norms taken as exactly 1 (unit-norm images, no norm K-step)
 __device__ __forceinline__ FfBound ff_bound(float na2, float nb2max, int dim, int e_mode) {
   FfBound b;
   const double na = sqrt(static_cast<double>(na2)) * (1.0 + 1e-6);
@@ -63,7 +64,7 @@ __device__ __forceinline__ FfBound ff_bound(float na2, float nb2max, int dim, in
   const double e_nrm = 3.814697265625e-6 * (na * na + nb * nb);                         // 2^-18: fp32 norms, fp16 split
   const double e_f32 = 1.01 * (dim + 3) * u24 * (na + nb) * (na + nb);                  // exact side is fp32 too
   b.e0 = e_op + e_acc + e_nrm + e_f32;
-  if (e_mode == 1) {
+  if (e_mode >= 1) {
     // q = rint(254 x): |q - 254 x| <= 1/2 per element, so |q_a.q_b - 254^2 a.b| <= 127 (|a|_1 + |b|_1) + D / 4
     // <= 127 sqrt(D) (|a| + |b|) + D / 4; the score is 2 / 254^2 times the integer accumulator (exact), whose
     // norm term was rounded to an integer (1/2) from an fp32 norm (2^-22 relative incl. its accumulation)
@@ -71,6 +72,9 @@ __device__ __forceinline__ FfBound ff_bound(float na2, float nb2max, int dim, in
     const double e_q = (2.0 / (S * S)) * (0.5 * S * sD * (na + nb) + 0.25 * dim + 0.75);
     const double e_n = 2.4e-7 * (dim + 3) * (nb * nb + 2.0) + 4.0 * u24 * (nb * nb + 2.0 * na * nb + 2.0);
     b.e0 = 1.001 * e_q + e_n + e_f32;
+    // e_mode 2: the candidate stage scored every train row as if |b|^2 were exactly 1 (l2_i8x2_kernel NX); the rows are
+    // within L2S8_UNIT_TOL of that (checked at ingest, fp32 norms: their own error is part of e_n)
+    if (e_mode == 2) b.e0 += 1.001 * static_cast<double>(L2S8_UNIT_TOL);
   }
   b.c = static_cast<double>(na2) - 2.0;
   return b;
@@ -477,7 +481,7 @@ __global__ void __launch_bounds__(R1_THREADS, 8)
 l2f_rerank1_kernel(const float* __restrict__ raw, const float* __restrict__ fnorm, int dim,
                    const PairJob* __restrict__ jobs, int2* __restrict__ knn_idx, float2* __restrict__ knn_dist,
                    float2* __restrict__ extra, uint8_t* __restrict__ flags, int stride, float ratio,
-                   unsigned long long* __restrict__ counters) {
+                   unsigned long long* __restrict__ counters, int e_mode) {
   const PairJob jb = jobs[blockIdx.y];
   const int row = blockIdx.x * R1_THREADS + threadIdx.x;
   if (blockIdx.x * R1_THREADS >= jb.nq) return;
@@ -498,7 +502,7 @@ l2f_rerank1_kernel(const float* __restrict__ raw, const float* __restrict__ fnor
       const bool refined = w2 != 0x7fffffff;
       const int acc2 = min(refined ? w2 : R1_ACC_NONE, k2 >> R1_COLBITS);
       const float K1 = r1_score(k1 >> R1_COLBITS), K2 = acc2 >= R1_ACC_NONE ? inf : r1_score(acc2);
-      const FfBound bd = ff_bound(fnorm[jb.q_row + row], jb.t_maxn, dim, 1);
+      const FfBound bd = ff_bound(fnorm[jb.q_row + row], jb.t_maxn, dim, e_mode);
       // level 0: true d1^2 >= lb(K1), true d2^2 <= ub(K2) (K2 is at least an upper bound of the second smallest score)
       if (__fsqrt_rn(bd.lb(K1)) >= __fmul_rn(ratio, __fsqrt_rn(bd.ub(K2)))) {
         // closed: Lowe's test cannot pass
@@ -560,16 +564,16 @@ l2f_rerank1_kernel(const float* __restrict__ raw, const float* __restrict__ fnor
 
 cudaError_t launch_l2f_rerank1(const float* raw, const float* fnorm, int dim, const PairJob* jobs, int n_jobs, int max_nq,
                                int2* idx, float2* dist, float2* extra, uint8_t* flags, int stride, float ratio,
-                               unsigned long long* counters, const uint8_t* q8, const uint8_t* t8, cudaStream_t st) {
+                               unsigned long long* counters, const uint8_t* q8, const uint8_t* t8, cudaStream_t st, int e_mode) {
   if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
   if (dim <= 0 || dim > FF_MAXDIM || (dim & 63)) return cudaErrorInvalidValue;
   l2f_rerank1_kernel<<<dim3((max_nq + R1_THREADS - 1) / R1_THREADS, n_jobs), R1_THREADS, 0, st>>>(
-      raw, fnorm, dim, jobs, idx, dist, extra, flags, stride, ratio, counters);
+      raw, fnorm, dim, jobs, idx, dist, extra, flags, stride, ratio, counters, e_mode);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   // the rows left open (flag 1), with three keys: the small-footprint variant, so that it too runs next to the tensor kernel
   l2f_fixup_kernel<true><<<dim3((max_nq + FFP_THREADS - 1) / FFP_THREADS, n_jobs), FFP_THREADS, 0, st>>>(
-      raw, fnorm, dim, jobs, idx, dist, extra, stride, ratio, L2F_NEED_RATIO, counters, 1, q8, t8, flags, 3);
+      raw, fnorm, dim, jobs, idx, dist, extra, stride, ratio, L2F_NEED_RATIO, counters, e_mode, q8, t8, flags, 3);
   return cudaGetLastError();
 }
 

@@ -117,7 +117,8 @@ cudaError_t launch_pack_sift(const float* raw_f32, const uint8_t* raw_u8, int n,
 // descriptor of 128 / 256 elements with moderate magnitudes) -> fp16 operand forms of dim + 16 halfs:
 //   query form [ -2*a | 1, 1, 1, 1, 0 x12 ]      train form [ b | p0, p1, p2, 2, 0 x12 ]
 // with |b|^2 = p0 + p1 + p2 up to 2^-33 (three fp16 pieces of the fp32 norm) and +2 keeping every score
-// positive.  stats[0] = max |x| (float bits), stats[1] = max |row|^2 (float bits), stats[2] = non-finite seen.
+// positive.  stats[0] = max |x| (float bits), stats[1] = max |row|^2 (float bits), stats[2] = non-finite seen,
+// stats[3] = max | |row|^2 - 1 | (float bits).
 // The same rows quantised for kind::i8 (l2_tc2.cu KIND 3), dim + 32 bytes per row, when q8 != nullptr:
 //   query form [ q_k = rint(254 x_k) (s8) | 1, 255 x31 (u8) ]      train form [ -q_k (s8) | digits of h, base 255 ]
 // with h = rint(254^2 (|b|^2 / 2 + 1)) from the fp32 norm.  Valid when max |x| <= 0.5 (stats[0]).
@@ -189,6 +190,7 @@ pack_float_kernel(const float* __restrict__ raw, int n, int dim, __half* __restr
     fnorm[row] = nrm;
     atomicMax(&stats[0], __float_as_uint(amax));
     atomicMax(&stats[1], __float_as_uint(nrm));
+    atomicMax(&stats[3], __float_as_uint(fabsf(nrm - 1.f)));     // how far the image is from unit-norm rows
     if (bad) atomicOr(&stats[2], 1u);
   }
 }

@@ -39,7 +39,7 @@ static constexpr int RS_ROUND = 32;
 #ifndef PM_RS_PPT
 #define PM_RS_PPT 4
 #endif
-static constexpr int RS_PPT = PM_RS_PPT;        // matches per thread and sweep of the scoring loop (early-drop granularity)
+[[maybe_unused]] static constexpr int RS_PPT = PM_RS_PPT;        // match-major build: matches per thread and sweep of the scoring loop
 
 struct MwcRng {
   unsigned long long s;
@@ -878,14 +878,15 @@ fmat_ransac_kernel(const float2* __restrict__ pts1, const float2* __restrict__ p
   __shared__ float4 sPts[RS_CHUNK];                     // staged matches (x1, y1, x2, y2)
   __shared__ int sList[RS_ROUND * 3];                   // live model t -> 3 * hypothesis + solution
   __shared__ int sNmod;
+#else
+  __shared__ ModelF32 sMf[PM_RS_FP32 ? RS_ROUND : 1][3];                // PM_RS_FP32 (match-major build): fp32 models + margins
+  __shared__ int sCntW[RS_THREADS / 32][RS_ROUND][3];   // match-major build: per-warp partial counts
+  __shared__ unsigned sDead[RS_ROUND];                  // bit m: model m of the hypothesis is out of the race
 #endif
-  __shared__ ModelF32 sMf[(PM_RS_FP32 && !PM_RS_MM) ? RS_ROUND : 1][3];   // PM_RS_FP32 (match-major build): fp32 models + margins
   __shared__ double bestF[9];
   __shared__ int sSub[RS_ROUND][7];
   __shared__ int sNm[RS_ROUND];
   __shared__ int sCnt[RS_ROUND][3];
-  __shared__ int sCntW[RS_THREADS / 32][PM_RS_MM ? 1 : RS_ROUND][3];   // match-major build: per-warp partial counts
-  __shared__ unsigned sDead[RS_ROUND];                  // bit m: model m of the hypothesis is out of the race
   __shared__ int sGen, sStop, sIter, sNiters, sBest;
 
   if (!prm.do_filter || M < prm.min_matches) {
@@ -1193,7 +1194,7 @@ static constexpr int RS_MEGA = 256;      // iterations per mega-round
 static constexpr int RS_SOLVE_THREADS = 32;   // 152 registers per thread: small blocks pack next to the kNN kernel
 
 struct RsWs {                            // views into the workspace of one slot
-  RsState* state; int* sub; int* nm; int* cnt; int* list; double* models;
+  RsState* state; int* sub; int* nm; int* cnt; int* list; int* handed; double* models;   // handed: [0] = n, [1 + k] = slot
 };
 __host__ __device__ inline RsWs rs_views(void* ws, int pairs) {
   RsWs v;
@@ -1203,18 +1204,42 @@ __host__ __device__ inline RsWs rs_views(void* ws, int pairs) {
   v.sub = reinterpret_cast<int*>(p);        p += sizeof(int) * 7 * RS_MEGA * static_cast<size_t>(pairs);
   v.nm = reinterpret_cast<int*>(p);         p += sizeof(int) * RS_MEGA * static_cast<size_t>(pairs);
   v.cnt = reinterpret_cast<int*>(p);        p += sizeof(int) * 3 * RS_MEGA * static_cast<size_t>(pairs);
-  v.list = reinterpret_cast<int*>(p);
+  v.list = reinterpret_cast<int*>(p);       p += sizeof(int) * 3 * RS_MEGA * static_cast<size_t>(pairs);
+  v.handed = reinterpret_cast<int*>(p);
   return v;
 }
 size_t ransac_workspace_bytes(int pairs) {
-  return (sizeof(RsState) + (sizeof(double) * 27 + sizeof(int) * (7 + 1 + 3 + 3)) * RS_MEGA) * static_cast<size_t>(pairs);
+  return (sizeof(RsState) + (sizeof(double) * 27 + sizeof(int) * (7 + 1 + 3 + 3)) * RS_MEGA + sizeof(int)) * static_cast<size_t>(pairs) + 64;
+}
+
+// The list of handed-over pairs of the batch (slot order): every staged kernel loops over it with a bounded grid, so a
+// batch without such pairs (the common case) costs a handful of blocks per kernel instead of one per pair and stage.
+__global__ void __launch_bounds__(256) rs_list_kernel(int n_jobs, RsWs ws) {
+  __shared__ int sWarp[8];
+  __shared__ int sBase;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) sBase = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < n_jobs; b0 += 256) {
+    const int slot = b0 + tid;
+    const bool f = slot < n_jobs && ws.state[slot].handed != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) sWarp[warp] = __popc(bal);
+    __syncthreads();
+    int off = sBase;
+    for (int w = 0; w < warp; ++w) off += sWarp[w];
+    if (f) ws.handed[1 + off + __popc(bal & ((1u << lane) - 1u))] = slot;
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += sWarp[w]; sBase += t; }
+    __syncthreads();
+  }
+  if (tid == 0) ws.handed[0] = sBase;
 }
 
 template <bool PHILOX>
-__global__ void __launch_bounds__(RS_THREADS)
-rs_sample_kernel(const float2* __restrict__ pts1, const float2* __restrict__ pts2, const int32_t* __restrict__ count,
-                 int stride, RsWs ws) {
-  const int slot = blockIdx.x, tid = threadIdx.x;
+__device__ __forceinline__ void rs_sample_body(int slot, const float2* __restrict__ pts1, const float2* __restrict__ pts2,
+                                               const int32_t* __restrict__ count, int stride, const RsWs& ws) {
+  const int tid = threadIdx.x;
   RsState& st = ws.state[slot];
   if (!st.active) return;
   const size_t base = static_cast<size_t>(slot) * stride;
@@ -1277,10 +1302,19 @@ rs_sample_kernel(const float2* __restrict__ pts1, const float2* __restrict__ pts
   for (int w = tid; w < gen * 7; w += RS_THREADS) sub[w] = sSub[w / 7][w % 7];
   if (tid == 0) { st.gen = gen; st.halt = sHalt; st.nmod = 0; }
 }
+template <bool PHILOX>
+__global__ void __launch_bounds__(RS_THREADS)
+rs_sample_kernel(const float2* __restrict__ pts1, const float2* __restrict__ pts2, const int32_t* __restrict__ count,
+                 int stride, RsWs ws) {
+  const int n = ws.handed[0];
+  for (int li = blockIdx.x; li < n; li += gridDim.x) {
+    rs_sample_body<PHILOX>(ws.handed[1 + li], pts1, pts2, count, stride, ws);
+    __syncthreads();
+  }
+}
 
-__global__ void __launch_bounds__(RS_SOLVE_THREADS)
-rs_solve_kernel(const float2* __restrict__ pts1, const float2* __restrict__ pts2, int stride, RsWs ws) {
-  const int slot = blockIdx.y;
+__device__ __forceinline__ void rs_solve_body(int slot, const float2* __restrict__ pts1, const float2* __restrict__ pts2,
+                                              int stride, const RsWs& ws) {
   const RsState& st = ws.state[slot];
   const int h = blockIdx.x * RS_SOLVE_THREADS + threadIdx.x;
   if (!st.active || h >= st.gen) return;
@@ -1300,15 +1334,19 @@ rs_solve_kernel(const float2* __restrict__ pts1, const float2* __restrict__ pts2
     for (int k = 0; k < n; ++k) list[at + k] = 3 * h + k;
   }
 }
+__global__ void __launch_bounds__(RS_SOLVE_THREADS)
+rs_solve_kernel(const float2* __restrict__ pts1, const float2* __restrict__ pts2, int stride, RsWs ws) {
+  const int n = ws.handed[0];
+  for (int li = blockIdx.y; li < n; li += gridDim.y) rs_solve_body(ws.handed[1 + li], pts1, pts2, stride, ws);
+}
 
 #ifndef PM_RS_SCORE_MINB
 #define PM_RS_SCORE_MINB 8
 #endif
 template <int MODE>
-__global__ void __launch_bounds__(RS_THREADS, PM_RS_SCORE_MINB)
-rs_score_kernel(const float2* __restrict__ pts1, const float2* __restrict__ pts2, const int32_t* __restrict__ count,
-                int stride, float thr, RsWs ws) {
-  const int slot = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+__device__ __forceinline__ void rs_score_body(int slot, const float2* __restrict__ pts1, const float2* __restrict__ pts2,
+                                              const int32_t* __restrict__ count, int stride, float thr, const RsWs& ws) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const RsState& st = ws.state[slot];
   if (!st.active) return;
   const int nmod = st.nmod;
@@ -1395,10 +1433,19 @@ rs_score_kernel(const float2* __restrict__ pts1, const float2* __restrict__ pts2
   __syncthreads();
   if (warp == 0 && act) ws.cnt[static_cast<size_t>(slot) * RS_MEGA * 3 + w] = sC[lane];
 }
+template <int MODE>
+__global__ void __launch_bounds__(RS_THREADS, PM_RS_SCORE_MINB)
+rs_score_kernel(const float2* __restrict__ pts1, const float2* __restrict__ pts2, const int32_t* __restrict__ count,
+                int stride, float thr, RsWs ws) {
+  const int n = ws.handed[0];
+  for (int li = blockIdx.y; li < n; li += gridDim.y) {
+    rs_score_body<MODE>(ws.handed[1 + li], pts1, pts2, count, stride, thr, ws);
+    __syncthreads();
+  }
+}
 
-__global__ void __launch_bounds__(32)
-rs_select_kernel(const int32_t* __restrict__ count, double confidence, RsWs ws) {
-  const int slot = blockIdx.x, lane = threadIdx.x;
+__device__ __forceinline__ void rs_select_body(int slot, const int32_t* __restrict__ count, double confidence, const RsWs& ws) {
+  const int lane = threadIdx.x;
   RsState& st = ws.state[slot];
   if (!st.active) return;
   const int M = count[slot];
@@ -1451,12 +1498,18 @@ rs_select_kernel(const int32_t* __restrict__ count, double confidence, RsWs ws) 
     if (stop || st.halt) st.active = 0;
   }
 }
+__global__ void __launch_bounds__(32)
+rs_select_kernel(const int32_t* __restrict__ count, double confidence, RsWs ws) {
+  const int n = ws.handed[0];
+  for (int li = blockIdx.x; li < n; li += gridDim.x) { rs_select_body(ws.handed[1 + li], count, confidence, ws); __syncwarp(); }
+}
 
-__global__ void __launch_bounds__(RS_THREADS)
-rs_finalize_kernel(const float2* __restrict__ pts1, const float2* __restrict__ pts2, const int32_t* __restrict__ count,
-                   int stride, RansacDev prm, uint8_t* __restrict__ mask, double* __restrict__ F_out,
-                   int32_t* __restrict__ status, int32_t* __restrict__ n_inliers, int32_t* __restrict__ iters_out, RsWs ws) {
-  const int slot = blockIdx.x, tid = threadIdx.x;
+__device__ __forceinline__ void rs_finalize_body(int slot, const float2* __restrict__ pts1, const float2* __restrict__ pts2,
+                                                 const int32_t* __restrict__ count, int stride, const RansacDev& prm,
+                                                 uint8_t* __restrict__ mask, double* __restrict__ F_out,
+                                                 int32_t* __restrict__ status, int32_t* __restrict__ n_inliers,
+                                                 int32_t* __restrict__ iters_out, const RsWs& ws) {
+  const int tid = threadIdx.x;
   const RsState& st = ws.state[slot];
   if (!st.handed) return;                         // finished in the per-pair kernel, which wrote its own outputs
   const size_t base = static_cast<size_t>(slot) * stride;
@@ -1483,6 +1536,14 @@ rs_finalize_kernel(const float2* __restrict__ pts1, const float2* __restrict__ p
     for (int i = 0; i < 9; ++i) F_out[9 * slot + i] = best > 0 ? st.bestF[i] : 0.0;
   }
 }
+__global__ void __launch_bounds__(RS_THREADS)
+rs_finalize_kernel(const float2* __restrict__ pts1, const float2* __restrict__ pts2, const int32_t* __restrict__ count,
+                   int stride, RansacDev prm, uint8_t* __restrict__ mask, double* __restrict__ F_out,
+                   int32_t* __restrict__ status, int32_t* __restrict__ n_inliers, int32_t* __restrict__ iters_out, RsWs ws) {
+  const int n = ws.handed[0];
+  for (int li = blockIdx.x; li < n; li += gridDim.x)
+    rs_finalize_body(ws.handed[1 + li], pts1, pts2, count, stride, prm, mask, F_out, status, n_inliers, iters_out, ws);
+}
 
 // Optional refit (pm_params.refit_8point): F of every filtered pair with >= 8 inliers is replaced by the normalised
 // 8-point estimate over its inliers; mask, counts and status stay those of the winning RANSAC hypothesis.
@@ -1506,6 +1567,7 @@ cudaError_t ransac_configure() {
   return cudaFuncSetAttribute(fmat_ransac_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
+int ransac_stage_cut() { return RS_CUT; }
 int ransac_mega_rounds(int max_iters) {
   if (max_iters <= RS_CUT) return 0;
   const int n = (max_iters - RS_CUT + RS_MEGA - 1) / RS_MEGA;
@@ -1529,20 +1591,28 @@ cudaError_t launch_ransac(const float2* pts1, const float2* pts2, const int32_t*
     fmat_ransac_kernel<false><<<n_jobs, RS_THREADS, 0, st>>>(pts1, pts2, count, stride, prm, mask, F, status, n_inliers,
                                                              iters, jobs, RS_CUT, hand);
   cudaError_t e = cudaGetLastError();
+  // bounded grids: the kernels loop over the list of handed-over pairs
+  const int gp = n_jobs < 148 ? n_jobs : 148;                    // one block per pair and stage
+  const int gy = n_jobs < 128 ? n_jobs : 128;                    // x (hypothesis / model groups of a pair)
+  if (n_mega > 0 && e == cudaSuccess) {
+    rs_list_kernel<<<1, 256, 0, st>>>(n_jobs, ws);
+    ++launches;
+    e = cudaGetLastError();
+  }
   for (int r = 0; r < n_mega && e == cudaSuccess; ++r) {
-    if (prm.sampler == 1) rs_sample_kernel<true><<<n_jobs, RS_THREADS, 0, st>>>(pts1, pts2, count, stride, ws);
-    else rs_sample_kernel<false><<<n_jobs, RS_THREADS, 0, st>>>(pts1, pts2, count, stride, ws);
-    rs_solve_kernel<<<dim3(RS_MEGA / RS_SOLVE_THREADS, n_jobs), RS_SOLVE_THREADS, 0, st>>>(pts1, pts2, stride, ws);
+    if (prm.sampler == 1) rs_sample_kernel<true><<<gp, RS_THREADS, 0, st>>>(pts1, pts2, count, stride, ws);
+    else rs_sample_kernel<false><<<gp, RS_THREADS, 0, st>>>(pts1, pts2, count, stride, ws);
+    rs_solve_kernel<<<dim3(RS_MEGA / RS_SOLVE_THREADS, gy), RS_SOLVE_THREADS, 0, st>>>(pts1, pts2, stride, ws);
     if (prm.residual_mode == 1)
-      rs_score_kernel<1><<<dim3(RS_MEGA * 3 / 32, n_jobs), RS_THREADS, 0, st>>>(pts1, pts2, count, stride, prm.thr, ws);
+      rs_score_kernel<1><<<dim3(RS_MEGA * 3 / 32, gy), RS_THREADS, 0, st>>>(pts1, pts2, count, stride, prm.thr, ws);
     else
-      rs_score_kernel<0><<<dim3(RS_MEGA * 3 / 32, n_jobs), RS_THREADS, 0, st>>>(pts1, pts2, count, stride, prm.thr, ws);
-    rs_select_kernel<<<n_jobs, 32, 0, st>>>(count, prm.confidence, ws);
+      rs_score_kernel<0><<<dim3(RS_MEGA * 3 / 32, gy), RS_THREADS, 0, st>>>(pts1, pts2, count, stride, prm.thr, ws);
+    rs_select_kernel<<<gp, 32, 0, st>>>(count, prm.confidence, ws);
     launches += 4;
     e = cudaGetLastError();
   }
   if (n_mega > 0 && e == cudaSuccess) {
-    rs_finalize_kernel<<<n_jobs, RS_THREADS, 0, st>>>(pts1, pts2, count, stride, prm, mask, F, status, n_inliers, iters, ws);
+    rs_finalize_kernel<<<gp, RS_THREADS, 0, st>>>(pts1, pts2, count, stride, prm, mask, F, status, n_inliers, iters, ws);
     ++launches;
     e = cudaGetLastError();
   }

@@ -818,6 +818,7 @@ def test_async_ingest_gives_identical_results(kind):
 FORCE_FP16_FORMS = 1 << 15
 S8_ONE_ROW_SET = 1 << 19          # the s8 candidate kernel with one query row set per cluster (default: two)
 S8_SIX_KEYS = 1 << 20             # two row sets, six chunk keys + chunk re-rank (default: argmin epilogue + one-column re-rank)
+S8_WITH_NORM = 1 << 23      # unit-norm rows: keep the norm K-step of the s8 search (default: dropped)
 
 
 @pytest.mark.parametrize("dim", [128, 256])
@@ -836,13 +837,13 @@ def test_s8_quantised_candidates_equal_fp16_forms_and_simt(dim, mode):
             d[11] = d[5]; d[700] = d[5]                     # duplicates: ties in the candidate scores
         imgs.append(d)
     outs = []
-    for flags in (0, FORCE_FP16_FORMS, 1, S8_ONE_ROW_SET, S8_SIX_KEYS):
+    for flags in (0, FORCE_FP16_FORMS, 1, S8_ONE_ROW_SET, S8_SIX_KEYS, S8_WITH_NORM):
         with api.PairMatcher(unique_mode=mode, batch_pairs=4, do_filter=0, debug_flags=flags) as pm:
             for i, d in enumerate(imgs):
                 pm.set_image(i, d)
             outs.append(pm.match_all_pairs())
             st = pm.stats()
-        if flags in (0, S8_ONE_ROW_SET, S8_SIX_KEYS) and mode != api.MUTUAL_NN:
+        if flags in (0, S8_ONE_ROW_SET, S8_SIX_KEYS, S8_WITH_NORM) and mode != api.MUTUAL_NN:
             assert st["rerank_rows"] > 0 and st["rerank_worst_err"] < 1.0, st
     for o in outs[1:]:
         _csr_equal(outs[0], o, ("offsets", "q", "t", "status"))
@@ -868,7 +869,7 @@ def test_s8_quantised_fallback_on_large_entries_and_full_size():
     w = synth.World("superpoint", 8192, seed=0xB200 + 9)
     imgs = [w.image(i, 100, outlier_frac=0.3 if i == 1 else 0.0)[:2] for i in range(4)]
     outs = []
-    for flags in (0, FORCE_FP16_FORMS, S8_ONE_ROW_SET, S8_SIX_KEYS):
+    for flags in (0, FORCE_FP16_FORMS, S8_ONE_ROW_SET, S8_SIX_KEYS, S8_WITH_NORM):
         with api.PairMatcher(debug_flags=flags) as pm:
             for i, (d, xy) in enumerate(imgs):
                 pm.set_image(i, d, xy)
@@ -878,6 +879,33 @@ def test_s8_quantised_fallback_on_large_entries_and_full_size():
     for o in outs[1:]:
         _csr_equal(outs[0], o)
     assert outs[0]["offsets"][-1] > 6 * 1000
+
+
+def test_s8_unit_norm_form_only_for_unit_norm_train_images():
+    """The s8 search drops its norm K-step when every TRAIN row of the batch has |b|^2 within 2^-10 of 1 (SuperPoint's
+    L2-normalised rows); images that are not normalised (here: rows scaled to norms 0.8 .. 1.0) keep it.  Whatever
+    the mix, the output equals the fp16 forms and the fp32 SIMT search."""
+    rng = np.random.default_rng(77)
+    base = _unit_rows(rng, 2500, 256)
+    def img(n, scaled):
+        ids = rng.permutation(2500)[:n]
+        d = base[ids] + 0.3 * rng.standard_normal((n, 256)).astype(np.float32) / 16
+        d = d / np.linalg.norm(d, axis=1, keepdims=True)
+        if scaled:
+            d = d * rng.uniform(0.8, 1.0, (n, 1))
+        return d.astype(np.float32)
+    imgs = [img(900, False), img(800, True), img(700, False), img(600, True), img(520, False)]
+    outs = []
+    for flags in (0, S8_WITH_NORM, FORCE_FP16_FORMS, 1):
+        for bp in ((0, 1) if flags == 0 else (0,)):              # batch of one pair: the form is chosen per batch
+            with api.PairMatcher(do_filter=0, debug_flags=flags, batch_pairs=bp) as pm:
+                for i, d in enumerate(imgs):
+                    pm.set_image(i, d)
+                outs.append(pm.match_all_pairs())
+                assert pm.stats()["rerank_worst_err"] < 1.0
+    for o in outs[1:]:
+        _csr_equal(outs[0], o, ("offsets", "q", "t", "status"))
+    assert outs[0]["offsets"][-1] > 1000
 
 
 @pytest.mark.parametrize("kind", ["sift", "superpoint", "orb"])
@@ -1090,12 +1118,13 @@ def test_staged_filter_batched_loop_with_outliers_equals_one_kernel_filter():
     w = synth.World("sift", 1500, seed=17)
     imgs = [w.image(i, 8, outlier_frac=0.5)[:2] for i in range(6)]
     outs = []
-    for flags in (0, 1 << 21):
+    for flags in (1 << 22, 1 << 21, 0):       # always staged / never staged / by the scheduling hint
         with api.PairMatcher(debug_flags=flags, batch_pairs=4) as pm:
             for i, (d, xy) in enumerate(imgs):
                 pm.set_image(i, d, xy)
             outs.append(pm.match_all_pairs())
     _csr_equal(outs[0], outs[1])
+    _csr_equal(outs[0], outs[2])
     assert np.array_equal(outs[0]["ransac_iters"], outs[1]["ransac_iters"]) and np.array_equal(outs[0]["F"], outs[1]["F"])
     assert (outs[0]["ransac_iters"] > 56).sum() >= 10
 
