@@ -226,7 +226,7 @@ struct DeviceCtx {
   uint8_t *hq8 = nullptr, *ht8 = nullptr;   // [rows][288] byte forms of 256-bit rows (kind::i8 two-set kernel)
   TcMaps h8maps{};
   bool tch8_ready = false;
-  uint8_t *hq4 = nullptr, *ht4 = nullptr;   // [rows][160] E2M1 forms of 256-bit rows (kind::mxf4 two-set kernel)
+  uint8_t *hq4 = nullptr, *ht4 = nullptr;   // [rows][160 / 288] E2M1 forms of 256- / 512-bit rows (kind::mxf4 two-set kernel)
   TcMaps h4maps{};                           // train boxes of 96 rows (192-column tiles)
   bool tch4_ready = false;
   // development switches, read from the environment ONCE in init() (never in the batch loop):
@@ -457,7 +457,9 @@ struct DeviceCtx {
             (r = mkb(&h8maps.t_ext, ht8, 32, CU_TENSOR_MAP_SWIZZLE_32B)) != CUDA_SUCCESS)
           return fail(PM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
         tch8_ready = true;
-        kb = TC_FP4_ROW;
+      }
+      if (words == 8 || words == 16) {      // E2M1 forms on kind::mxf4: one 128-byte K atom per 256 bits
+        kb = tc_fp4_row(words);
         if ((r = mkb(&h4maps.q_main, hq4, 128, CU_TENSOR_MAP_SWIZZLE_128B)) != CUDA_SUCCESS ||
             (r = mkb(&h4maps.q_ext, hq4, 32, CU_TENSOR_MAP_SWIZZLE_32B)) != CUDA_SUCCESS ||
             (r = mkb(&h4maps.t_main96, ht4, 128, CU_TENSOR_MAP_SWIZZLE_128B, 96)) != CUDA_SUCCESS ||
@@ -534,8 +536,10 @@ struct DeviceCtx {
         if (words == 8) {
           if ((rc = grow(hq8, 32 * words + 32, nc)) != PM_OK) return rc;
           if ((rc = grow(ht8, 32 * words + 32, nc)) != PM_OK) return rc;
-          if ((rc = grow(hq4, TC_FP4_ROW, nc)) != PM_OK) return rc;
-          if ((rc = grow(ht4, TC_FP4_ROW, nc)) != PM_OK) return rc;
+        }
+        if (words == 8 || words == 16) {
+          if ((rc = grow(hq4, tc_fp4_row(words), nc)) != PM_OK) return rc;
+          if ((rc = grow(ht4, tc_fp4_row(words), nc)) != PM_OK) return rc;
         }
         if ((rc = grow(qnorm, 1, nc)) != PM_OK) return rc;
       }
@@ -678,8 +682,8 @@ struct DeviceCtx {
           PM_CUDA(launch_pack_bits(bits + static_cast<size_t>(im.row) * words, n, words, hq + im.row * kb,
                                    ht + im.row * kb, qnorm + im.row, words == 8 ? hq8 + im.row * kb : nullptr,
                                    words == 8 ? ht8 + im.row * kb : nullptr,
-                                   words == 8 ? hq4 + static_cast<size_t>(im.row) * TC_FP4_ROW : nullptr,
-                                   words == 8 ? ht4 + static_cast<size_t>(im.row) * TC_FP4_ROW : nullptr, ingest));
+                                   (words == 8 || words == 16) ? hq4 + static_cast<size_t>(im.row) * tc_fp4_row(words) : nullptr,
+                                   (words == 8 || words == 16) ? ht4 + static_cast<size_t>(im.row) * tc_fp4_row(words) : nullptr, ingest));
           ++stats.kernel_launches;
         }
       } else {
@@ -940,7 +944,7 @@ struct DeviceCtx {
           cudaError_t e = cudaMemsetAsync(oi, 0xFF, sizeof(int2) * static_cast<size_t>(n) * s.stride, knn_stream);
           if (e != cudaSuccess) return e;
         }
-        if (use_tch4) return launch_ham_fp4x2(h4maps, jobs_d, n, mq, oi, od, s.stride, num_sms, probe, knn_stream);
+        if (use_tch4) return launch_ham_fp4x2(h4maps, jobs_d, n, mq, oi, od, s.stride, num_sms, probe, knn_stream, words);
         return launch_ham_i8x2(h8maps, jobs_d, n, mq, oi, od, s.stride, num_sms, probe, knn_stream);
       }
       if (use_tch) return launch_ham_tc2(hmaps, words, qnorm, jobs_d, n, mq, oi, od, s.stride, num_sms, knn_stream);

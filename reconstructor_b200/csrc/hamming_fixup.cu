@@ -104,6 +104,8 @@ cudaError_t launch_hamming_fixup(const uint32_t* bits, int words, const PairJob*
   dim3 grid((max_nq + HF_SPAN - 1) / HF_SPAN, n_jobs);
   if (ints == 2 && words == 8)
     hamming_fixup_kernel<8, 32, false><<<grid, HF_THREADS, 0, st>>>(bits, jobs, idx, dist, stride, ratio, all_rows);
+  else if (ints == 2 && words == 16)
+    hamming_fixup_kernel<16, 32, false><<<grid, HF_THREADS, 0, st>>>(bits, jobs, idx, dist, stride, ratio, all_rows);
   else if (ints == 1 && words == 8)
     hamming_fixup_kernel<8, 32, true><<<grid, HF_THREADS, 0, st>>>(bits, jobs, idx, dist, stride, ratio, all_rows);
   else if (ints)

@@ -40,6 +40,8 @@ static constexpr int TC_KPAD = 144;       // 128 + one K=16 step carrying the tr
 #endif
 static constexpr int TC_I8_CHUNK = PM_I8_CHUNK;   // columns per candidate chunk of the i8 epilogue (16 or 32)
 static constexpr int TC_FP4_ROW = 160;    // 256-bit rows as E2M1 values: 128 bytes + a 64-value (32-byte) norm block
+static constexpr int TC_FP4_ROW2 = 288;   // 512-bit rows: two 128-byte K atoms + the norm block
+constexpr int tc_fp4_row(int words) { return words == 16 ? TC_FP4_ROW2 : TC_FP4_ROW; }
 static constexpr int TC_I8_ROW = 160;     // byte form: 128 x u8/s8 + one K=32 step carrying floor(|b|^2 / 2)
 struct TcMaps {
   CUtensorMap q_main, q_ext, t_main, t_ext;   // boxes of 128 rows
@@ -87,7 +89,7 @@ cudaError_t launch_ham_i8x2(const TcMaps& maps, const PairJob* jobs, int n_jobs,
 // 256-bit rows as E2M1 values on kind::mxf4, 192-column train tiles (l2_tc2.cu, l2_i8x2_kernel<.., 1, 1>); maps: rows of
 // 160 bytes (128 bytes = 256 four-bit values + 32 bytes = 64-value norm block), t_main96 / t_ext96 boxes for the train side
 cudaError_t launch_ham_fp4x2(const TcMaps& maps, const PairJob* jobs, int n_jobs, int max_nq, int2* idx, float2* dist,
-                             int stride, int num_sms, int probe, cudaStream_t st);
+                             int stride, int num_sms, int probe, cudaStream_t st, int words = 8);
 cudaError_t hamming_fixup_configure();
 
 // real-valued rows on the tensor cores: l2_tc2.cu (MODE 3) + l2f_fixup.cu

@@ -86,14 +86,14 @@ __device__ __forceinline__ void cluster_sync_all() {
 // kernels of earlier batches (api.cu); a warp that polls in a tight loop is always eligible, and measured next to the
 // candidate-key kernels (whose epilogue warps wait for the tensor pipe ~45 % of the time) every co-resident kernel ran
 // 6-40x slower than alone.  So a failed poll puts the warp to sleep for NS nanoseconds (role-specific: the MMA issuer
-// sleeps least, it is on the critical path).  A wait that lasts longer than PM_WAIT_TIMEOUT_S seconds of %globaltimer
+// does not sleep, it is on the critical path).  A wait that lasts longer than PM_WAIT_TIMEOUT_S seconds of %globaltimer
 // (a lost arrival: a bug, not load -- profilers and sanitizers stretch a wait by orders of magnitude less) traps
 // instead of hanging the device.
 #ifndef PM_WAIT_NS_EPI
 #define PM_WAIT_NS_EPI 96
 #endif
 #ifndef PM_WAIT_NS_MMA
-#define PM_WAIT_NS_MMA 24
+#define PM_WAIT_NS_MMA 0     // one warp per CTA pair, on the critical hand-over path: measured +1 % (ORB) .. +3 % (SuperPoint) over 24 ns
 #endif
 #ifndef PM_WAIT_NS_TMA
 #define PM_WAIT_NS_TMA 96
@@ -977,7 +977,7 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
   static_assert(MODE < 3 || MODE == 5 || !FP4, "candidate keys are integer keys of the kind::i8 accumulators");
   constexpr int BN = C::kBN, BNH = C::kBNH, ST = C::kStages, TILE = C::kTile, BTILE = C::kBTile, NSL = C::kSlices;
   constexpr int AST = C::kAStages, KDIM = 128 * KA, BATOM = C::kBAtom;
-  static_assert(!FP4 || KA == 1, "the fp4 form of a 256-bit row is one 128-byte K atom");
+  static_assert(!FP4 || KA <= 2, "fp4 forms: one 128-byte K atom per 256 bits (256- and 512-bit rows)");
   static_assert(!NX || MODE == 4, "the unit-norm form exists for the argmin epilogue only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1098,15 +1098,16 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
               const uint32_t d_tmem = tmem_base + set * BN;
               const uint32_t a_lo = a_lo0 + (a_st * 2 + set) * (TILE >> 4);
               if (FP4) {
-                // 4 x 64 bit values of the row + the 64-value norm block: 5 K-steps of kind::mxf4 (K = 64)
+                // 4 KA x 64 bit values of the row + the 64-value norm block: 5 / 9 K-steps of kind::mxf4 (K = 64)
                 const uint32_t sfa = tmem_base + C::kSfCol, sfb = tmem_base + C::kSfCol + 16;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_mxf4_pair(d_tmem, (static_cast<uint64_t>(HI128) << 32) | (a_lo + ((k * 32) >> 4)),
-                                 (static_cast<uint64_t>(HI128) << 32) | (b_lo + ((k * 32) >> 4)), C::kIdescFp4, sfa, sfb,
-                                 k > 0 ? 1u : 0u);
-                umma_mxf4_pair(d_tmem, (static_cast<uint64_t>(HI32) << 32) | (a_lo + (T2_ATOM >> 4)),
-                               (static_cast<uint64_t>(HI32) << 32) | (b_lo + (BATOM >> 4)), C::kIdescFp4, sfa, sfb, 1u);
+                for (int k = 0; k < 4 * KA; ++k)
+                  umma_mxf4_pair(d_tmem,
+                                 (static_cast<uint64_t>(HI128) << 32) | (a_lo + (((k >> 2) * T2_ATOM + (k & 3) * 32) >> 4)),
+                                 (static_cast<uint64_t>(HI128) << 32) | (b_lo + (((k >> 2) * BATOM + (k & 3) * 32) >> 4)),
+                                 C::kIdescFp4, sfa, sfb, k > 0 ? 1u : 0u);
+                umma_mxf4_pair(d_tmem, (static_cast<uint64_t>(HI32) << 32) | (a_lo + ((KA * T2_ATOM) >> 4)),
+                               (static_cast<uint64_t>(HI32) << 32) | (b_lo + ((KA * BATOM) >> 4)), C::kIdescFp4, sfa, sfb, 1u);
               } else {
 #pragma unroll
                 for (int k = 0; k < 4 * KA; ++k)
@@ -1387,6 +1388,8 @@ cudaError_t i8x2_configure() {
   if ((e = i8x2_attr<1, false, 2>()) != cudaSuccess) return e;
   if ((e = i8x2_attr<2, false, 1, 1>()) != cudaSuccess) return e;
   if ((e = i8x2_attr<1, false, 1, 1>()) != cudaSuccess) return e;
+  if ((e = i8x2_attr<2, false, 2, 1>()) != cudaSuccess) return e;
+  if ((e = i8x2_attr<1, false, 2, 1>()) != cudaSuccess) return e;
   return i8x2_attr<5, false>();
 }
 
@@ -1417,14 +1420,25 @@ cudaError_t launch_ham_i8x2(const TcMaps& maps, const PairJob* jobs, int n_jobs,
 // distance (exact: every partial sum is an integer of magnitude <= 512).  192-column train tiles leave TMEM columns for
 // the (all-ones) scale factors.  hamming_fixup (32-column chunks, float inputs) follows.  probe: TMA + MMA timing probe.
 cudaError_t launch_ham_fp4x2(const TcMaps& maps, const PairJob* jobs, int n_jobs, int max_nq, int2* idx, float2* dist,
-                             int stride, int num_sms, int probe, cudaStream_t st) {
+                             int stride, int num_sms, int probe, cudaStream_t st, int words) {
   if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
   using C = I8X2Cfg<1, 192>;
+  using C2 = I8X2Cfg<2, 192>;
   const int blocks_per_job = (max_nq + C::kRows - 1) / C::kRows;
   const int n_items = n_jobs * blocks_per_job;
   int clusters = num_sms / 2;
   if (n_items < clusters) clusters = n_items;
   const int grid = clusters * 2;
+  if (words == 16) {                  // 512-bit rows: two K atoms, 9 K-steps (the E4M3 form needs 17)
+    if (probe)
+      l2_i8x2_kernel<1, false, 2, 1><<<grid, C2::kThreads, C2::kSmemBytes, st>>>(
+          maps.q_main, maps.q_ext, maps.t_main96, maps.t_ext96, jobs, n_jobs, blocks_per_job, idx, dist, stride);
+    else
+      l2_i8x2_kernel<2, false, 2, 1><<<grid, C2::kThreads, C2::kSmemBytes, st>>>(
+          maps.q_main, maps.q_ext, maps.t_main96, maps.t_ext96, jobs, n_jobs, blocks_per_job, idx, dist, stride);
+    return cudaGetLastError();
+  }
+  if (words != 8) return cudaErrorInvalidValue;
   if (probe)
     l2_i8x2_kernel<1, false, 1, 1><<<grid, C::kThreads, C::kSmemBytes, st>>>(
         maps.q_main, maps.q_ext, maps.t_main96, maps.t_ext96, jobs, n_jobs, blocks_per_job, idx, dist, stride);

@@ -219,14 +219,16 @@ __device__ __forceinline__ unsigned long long spread_bits8(unsigned int b) {    
 //   query form [ bit ? 1 : 0 | 6 x9, 1 x2, 0 x53 ]      train form [ bit ? -1 : +1 | d_0 .. d_10, 0 x53 ]
 // with |b| = 36 n + 6 u + v: d_0..6 = 6 for the first n slots, d_7 + d_8 = u, d_9 + d_10 = v (every digit one of the
 // E2M1 values 0, 1, 2, 3, 4, 6), so that the fp32 accumulator is sum a (1 - 2 b) + |b| = the Hamming distance.
+// 512-bit rows (|b| <= 512): the same with NS6 = 14 slots of 36 (query weights 6 x16, 1 x2).
+template <int NS6 = 7>
 __device__ __forceinline__ uint32_t fp4_norm_digit(int slot, int cnt) {       // E2M1 code of train digit `slot`
-  const int n36 = min(cnt / 36, 7), r = cnt - 36 * n36, u = r / 6, v = r - 6 * u;
+  const int n36 = min(cnt / 36, NS6), r = cnt - 36 * n36, u = r / 6, v = r - 6 * u;
   int d = 0;
-  if (slot < 7) d = slot < n36 ? 6 : 0;
-  else if (slot == 7) d = min(u, 4);
-  else if (slot == 8) d = u - min(u, 4);
-  else if (slot == 9) d = min(v, 4);
-  else if (slot == 10) d = v - min(v, 4);
+  if (slot < NS6) d = slot < n36 ? 6 : 0;
+  else if (slot == NS6) d = min(u, 4);
+  else if (slot == NS6 + 1) d = u - min(u, 4);
+  else if (slot == NS6 + 2) d = min(v, 4);
+  else if (slot == NS6 + 3) d = v - min(v, 4);
   // value -> code: 0 -> 0, 1 -> 2, 2 -> 4, 3 -> 5, 4 -> 6, 6 -> 7
   return d == 0 ? 0u : (d == 1 ? 2u : (d == 2 ? 4u : (d == 3 ? 5u : (d == 4 ? 6u : 7u))));
 }
@@ -256,19 +258,27 @@ pack_bits_kernel(const uint32_t* __restrict__ bits, int n, int words, uint8_t* _
       *reinterpret_cast<unsigned long long*>(t8 + static_cast<size_t>(row) * kp + 8 * j) = 0x0101010101010101ull + ones * 0xFEull;
     }
   }
-  if (q4) {                                              // words == 8: lane = byte of the row -> 8 four-bit values
-    const uint32_t wj = __shfl_sync(0xffffffffu, w, lane >> 2);
-    const uint32_t byte = (wj >> (8 * (lane & 3))) & 0xFFu;
-    uint32_t nib = 0;
+  if (q4) {                                              // words == 8 / 16: byte of the row -> 8 four-bit values
+    const int row_b = words == 16 ? TC_FP4_ROW2 : TC_FP4_ROW;
+    uint8_t* q4row = q4 + static_cast<size_t>(row) * row_b;
+    uint8_t* t4row = t4 + static_cast<size_t>(row) * row_b;
+    for (int j = lane; j < 4 * words; j += 32) {
+      const uint32_t wj = __shfl_sync(0xffffffffu, w, j >> 2);
+      const uint32_t byte = (wj >> (8 * (j & 3))) & 0xFFu;
+      uint32_t nib = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) nib |= ((byte >> k) & 1u) << (4 * k);
-    uint8_t* q4row = q4 + static_cast<size_t>(row) * TC_FP4_ROW;
-    uint8_t* t4row = t4 + static_cast<size_t>(row) * TC_FP4_ROW;
-    *reinterpret_cast<uint32_t*>(q4row + 4 * lane) = nib * 0x2u;                   // 1.0 = 0b0010
-    *reinterpret_cast<uint32_t*>(t4row + 4 * lane) = 0x22222222u + nib * 0x8u;     // -1.0 = 0b1010
+      for (int k = 0; k < 8; ++k) nib |= ((byte >> k) & 1u) << (4 * k);
+      *reinterpret_cast<uint32_t*>(q4row + 4 * j) = nib * 0x2u;                   // 1.0 = 0b0010
+      *reinterpret_cast<uint32_t*>(t4row + 4 * j) = 0x22222222u + nib * 0x8u;     // -1.0 = 0b1010
+    }
     // norm block: byte L = slots 2L (low nibble), 2L + 1 (high nibble)
-    q4row[128 + lane] = lane < 4 ? 0x77 : (lane == 4 ? 0x27 : (lane == 5 ? 0x02 : 0x00));
-    t4row[128 + lane] = static_cast<uint8_t>(fp4_norm_digit(2 * lane, cnt) | (fp4_norm_digit(2 * lane + 1, cnt) << 4));
+    if (words == 16) {
+      q4row[256 + lane] = lane < 8 ? 0x77 : (lane == 8 ? 0x22 : 0x00);
+      t4row[256 + lane] = static_cast<uint8_t>(fp4_norm_digit<14>(2 * lane, cnt) | (fp4_norm_digit<14>(2 * lane + 1, cnt) << 4));
+    } else {
+      q4row[128 + lane] = lane < 4 ? 0x77 : (lane == 4 ? 0x27 : (lane == 5 ? 0x02 : 0x00));
+      t4row[128 + lane] = static_cast<uint8_t>(fp4_norm_digit<7>(2 * lane, cnt) | (fp4_norm_digit<7>(2 * lane + 1, cnt) << 4));
+    }
   }
   if (q8) {
     q8[static_cast<size_t>(row) * kp + 32 * words + lane] = lane == 0 ? 1 : 255;
@@ -291,7 +301,8 @@ pack_bits_kernel(const uint32_t* __restrict__ bits, int n, int words, uint8_t* _
 cudaError_t launch_pack_bits(const uint32_t* bits, int n, int words, uint8_t* qb, uint8_t* tb, int32_t* popc,
                              uint8_t* q8, uint8_t* t8, uint8_t* q4, uint8_t* t4, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
-  if (words != 8) q8 = t8 = q4 = t4 = nullptr;
+  if (words != 8) q8 = t8 = nullptr;
+  if (words != 8 && words != 16) q4 = t4 = nullptr;
   pack_bits_kernel<<<(n + 7) / 8, 256, 0, st>>>(bits, n, words, qb, tb, popc, q8, t8, q4, t4);
   return cudaGetLastError();
 }

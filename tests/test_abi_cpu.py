@@ -104,9 +104,17 @@ def test_shards_cover_pairs_once():
     assert len(pairs) == 37 * 36 // 2 and (pairs[:, 0] < pairs[:, 1]).all()
     for world in (1, 2, 3, 8):
         parts = [shard.shard_pairs(pairs, r, world) for r in range(world)]
-        assert np.array_equal(np.concatenate(parts), pairs)
+        idx = [shard.shard_index(len(pairs), r, world) for r in range(world)]
+        assert np.array_equal(np.sort(np.concatenate(idx)), np.arange(len(pairs)))      # every pair exactly once
+        assert all((np.diff(i) > 0).all() for i in idx if len(i) > 1)                   # image order kept inside a share
+        assert all(np.array_equal(pairs[i], p) for i, p in zip(idx, parts))
         sizes = [len(p) for p in parts]
         assert max(sizes) - min(sizes) <= 1
+    # block-cyclic: every rank's share starts among the first pairs (early images), for the overlap with the ingest
+    big = shard.all_pairs(142)
+    for r in range(8):
+        assert shard.shard_index(len(big), r, 8)[0] == r * shard.SHARD_BLOCK
+        assert shard.shard_pairs(big, r, 8)[0, 1] <= 33
 
 
 _GLOO_WORKER = r"""

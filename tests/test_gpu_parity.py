@@ -576,6 +576,7 @@ def test_float_tensor_full_size_superpoint():
 # binary descriptors on the tensor cores (E4M3 {0,1} operands, exact) vs the XOR/popc kernel and the oracle
 # ---------------------------------------------------------------------------------------------
 FORCE_POPC = 1 << 10
+FORCE_E4M3_512 = 1 << 16          # binary rows: the kind::f8f6f4 kernel (E4M3 forms) instead of the kind::mxf4 one
 
 
 @pytest.mark.parametrize("mode", [api.UNIQUE_FIRST_WINS, api.MUTUAL_NN, api.UNIQUE_NONE])
@@ -633,6 +634,43 @@ def test_hamming_tensor_512_bit_and_ragged():
         a, b = res["offsets"][p], res["offsets"][p + 1]
         assert np.array_equal(res["q"][a:b], wq) and np.array_equal(res["t"][a:b], wt), (i, j)
     assert res["offsets"][-1] > 300
+
+
+def test_hamming_512_bit_fp4_form_every_popcount_and_sizes():
+    """512-bit rows as E2M1 values on kind::mxf4 (two K atoms, 9 K-steps; the default since round 2) vs the E4M3 form
+    (17 K-steps) vs the XOR/popc kernel: image sizes around the row-set / tile / chunk boundaries, and train rows of
+    EVERY popcount 0..512 (the norm block encodes |b| = 36 n + 6 u + v in E2M1 digits)."""
+    rng = np.random.default_rng(21)
+    pops = np.concatenate([np.arange(513), rng.integers(0, 513, 400)])
+    every = np.zeros((len(pops), 512), np.uint8)
+    for r, c in enumerate(pops):
+        every[r, rng.permutation(512)[:c]] = 1
+    every = np.packbits(every, axis=1, bitorder="little")
+    base = rng.integers(0, 256, (1400, 64), dtype=np.uint8)
+    imgs = [every]
+    for n in (769, 513, 512, 193, 192, 97, 33):
+        ids = rng.permutation(1400)[:n]
+        d = base[ids].copy()
+        d ^= ((rng.random((n, 64)) < 0.04) * rng.integers(1, 256, (n, 64))).astype(np.uint8)
+        imgs.append(d)
+    imgs.append(every[rng.permutation(len(every))[:600]] ^ np.uint8(1))     # near-duplicates of the popcount rows
+    outs = []
+    for flags in (0, FORCE_E4M3_512, FORCE_POPC):
+        with api.PairMatcher(debug_flags=flags, do_filter=0, batch_pairs=5, unique_mode=api.UNIQUE_NONE) as pm:
+            for i, d in enumerate(imgs):
+                pm.set_image(i, d)
+            outs.append(pm.match_all_pairs())
+    for o in outs[1:]:
+        for k in ("offsets", "q", "t", "status"):
+            assert np.array_equal(outs[0][k], o[k]), k
+    res = outs[0]
+    for p in (0, 7, len(res["pair_ij"]) - 1):
+        i, j = res["pair_ij"][p]
+        oi, od = orc.knn2_hamming(imgs[i], imgs[j])
+        wq, wt = orc.ratio_unique(oi, od.astype(np.float32), imgs[j].shape[0], mode=orc.UNIQUE_NONE)
+        a, b = res["offsets"][p], res["offsets"][p + 1]
+        assert np.array_equal(res["q"][a:b], wq) and np.array_equal(res["t"][a:b], wt), (i, j)
+    assert res["offsets"][-1] > 1000
 
 
 def test_hamming_tensor_full_size_equals_popc():
