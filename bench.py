@@ -16,7 +16,7 @@ Headline line (`value`, `e2e`, `roofline`, `stages`, `cpu_baseline`):
   superpoint1000  configs[3]: 1,000 images x 8192 SuperPoint keypoints (256-d), 499,500 pairs -- STRONG scaling over N
 `stages.ransac_heavy` is the headline workload with 50 % outlier keypoints (RANSAC runs hundreds of iterations).
 
-The pair list is split into contiguous shares (one per rank), descriptors are replicated on every GPU, the timed loop
+The pair list is dealt in equal block-cyclic shares (one per rank; shard.py), descriptors are replicated on every GPU, the timed loop
 has no data-path collective.
 `value`  = pairs/s with descriptors resident in HBM, results delivered to host memory (CSR);
 `e2e`    = the same through the C ABI with HOST buffers: per step every image is re-ingested from pinned host memory
@@ -493,7 +493,7 @@ def main():
         # the list keeps its image-by-image order
         pairs = pairs[np.sort(np.random.default_rng(0xB200).choice(n_all, a.max_pairs, replace=False))]
     cfg = dict(workload=workload_name(a.kind, n_img, a.kp, n_all), images=n_img, keypoints=a.kp, kind=a.kind,
-               pairs=int(len(pairs)), partition=f"pairs sharded over {n_gpus} GPU(s), descriptors replicated",
+               pairs=int(len(pairs)), partition=f"pairs sharded over {n_gpus} GPU(s) (equal block-cyclic shares), descriptors replicated",
                l2="inputs larger than L2 (no flush needed)", outlier_frac=a.outlier_frac,
                debug_flags=a.debug_flags)
     if len(pairs) < n_all:

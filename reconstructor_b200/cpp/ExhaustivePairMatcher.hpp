@@ -50,11 +50,21 @@ class CudaRetrievalImgMatcher {
     pm_free_pairs(pairs);
     return PM_OK;
   }
+  // The reference's call shape, ImageMatcher::match(imgIds2Paths, features, imgMatches) (ImageMatcher.h:18-21,
+  // SequentialReconstructor.cpp:114): the path map is not read (FakeImgMatcher does not read it either); void like the
+  // reference, the status is kept in lastStatus().
+  template <class PathMap>
+  void match(const PathMap& /*imgIds2Paths*/, const std::unordered_map<int, std::vector<FeaturePtr<>>>& features,
+             std::unordered_map<int, std::vector<int>>& imgMatches) {
+    last_status_ = match(features, imgMatches);
+  }
+  int lastStatus() const { return last_status_; }
   const std::shared_ptr<PairMatchDevice>& device() const { return dev_; }
 
  private:
   std::shared_ptr<PairMatchDevice> dev_;
   int top_k_;
+  int last_status_ = PM_OK;
 };
 
 class ExhaustivePairMatcher {

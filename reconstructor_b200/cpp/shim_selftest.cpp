@@ -139,7 +139,9 @@ int main() {
   {
     CudaRetrievalImgMatcher fake(dev, 0), top1(dev, 1);
     std::unordered_map<int, std::vector<int>> all, near;
-    if (fake.match(features, all) != PM_OK || top1.match(features, near) != PM_OK) { std::printf("retrieval failed\n"); return 1; }
+    std::unordered_map<int, std::string> paths;            // the reference's first argument (never read)
+    fake.match(paths, features, all);                       // the reference's call shape (ImageMatcher.h:18-21)
+    if (fake.lastStatus() != PM_OK || top1.match(features, near) != PM_OK) { std::printf("retrieval failed\n"); return 1; }
     for (int i = 0; i < n_img; ++i) {
       if (all[i].size() != static_cast<size_t>(n_img - 1) || near[i].empty() || near[i].size() > all[i].size()) { std::printf("retrieval lists wrong for image %d\n", i); return 1; }
       for (int j : near[i]) {
