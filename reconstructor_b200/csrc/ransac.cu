@@ -1365,15 +1365,23 @@ __device__ __forceinline__ void rs_score_body(int slot, const float2* __restrict
   const float2* p1 = pts1 + base;
   const float2* p2 = pts2 + base;
   const int M = count[slot];
-  int cnt = 0;
+  // Early drop (exact): a model replaces the best one only with STRICTLY more inliers (and more than 6), and the best
+  // count only grows during the mega-round.  Once a model's count so far plus all matches not yet visited cannot
+  // exceed the best count from BEFORE the mega-round, its exact count no longer matters; when that holds for all 32
+  // models of the block the remaining chunks are skipped (the partial counts stay <= the bound, so the selection
+  // ignores them exactly as it would ignore the full counts).
+  const int bound = st.best > 6 ? st.best : 6;
   for (int i0 = 0; i0 < M; i0 += RS_CHUNK) {
-    __syncthreads();
+    __syncthreads();                                  // the previous chunk is consumed, its counts are in sC
+    const bool dead_w = __all_sync(0xffffffffu, !act || sC[lane] + (M - i0) <= bound);
     const int n_here = min(RS_CHUNK, M - i0);
     for (int i = tid; i < n_here; i += RS_THREADS) {
       const float2 a = p1[i0 + i], b = p2[i0 + i];
       sPts[i] = make_float4(a.x, a.y, b.x, b.y);
     }
-    __syncthreads();
+    if (__syncthreads_and(dead_w ? 1 : 0)) break;     // block-uniform
+    if (dead_w) continue;
+    int cnt = 0;
     constexpr int SL = RS_CHUNK / (RS_THREADS / 32);
     const int j0 = warp * SL, j1 = min(j0 + SL, n_here);
     if (MODE == 0) {
@@ -1428,8 +1436,8 @@ __device__ __forceinline__ void rs_score_body(int slot, const float2* __restrict
         cnt += c & 1;
       }
     }
+    if (act && cnt) atomicAdd(&sC[lane], cnt);
   }
-  if (act && cnt) atomicAdd(&sC[lane], cnt);
   __syncthreads();
   if (warp == 0 && act) ws.cnt[static_cast<size_t>(slot) * RS_MEGA * 3 + w] = sC[lane];
 }
@@ -1592,7 +1600,7 @@ cudaError_t launch_ransac(const float2* pts1, const float2* pts2, const int32_t*
                                                              iters, jobs, RS_CUT, hand);
   cudaError_t e = cudaGetLastError();
   // bounded grids: the kernels loop over the list of handed-over pairs
-  const int gp = n_jobs < 148 ? n_jobs : 148;                    // one block per pair and stage
+  const int gp = n_jobs;                                         // one block per pair and stage (serial latency per pair: no looping)
   const int gy = n_jobs < 128 ? n_jobs : 128;                    // x (hypothesis / model groups of a pair)
   if (n_mega > 0 && e == cudaSuccess) {
     rs_list_kernel<<<1, 256, 0, st>>>(n_jobs, ws);
