@@ -345,10 +345,17 @@ class Workload:
         D.barrier()
         pm.reset_stats()
         t0 = time.perf_counter()
+        trace = os.environ.get("PM_BENCH_TRACE")
         for _ in range(steps):
+            ta = time.perf_counter()
             self.ingest(use_async)
+            tb = time.perf_counter()
             r = pm.match_all_pairs(self.mine, copy=False)
+            tc = time.perf_counter()
             _ = int(r["n_inliers"].sum())                     # the step's result is read on the host
+            if trace:                                         # development: host-side split of the end-to-end step
+                print("[bench trace] rank %d: ingest call %.2f ms, match call %.2f ms (device %.2f ms)" %
+                      (D.rank, 1e3 * (tb - ta), 1e3 * (tc - tb), r["device_ms"]), file=sys.stderr)
             pm.free_result(r)
         D.barrier()
         e_ms = D.allmax(1e3 * (time.perf_counter() - t0)) / steps

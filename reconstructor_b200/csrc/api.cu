@@ -908,6 +908,7 @@ struct DeviceCtx {
     //   bit21     epipolar filter: every iteration in the one-block-per-pair kernel (no staged continuation, ransac.cu)
     //   bit22     epipolar filter: always queue the staged continuation (default: while recent batches needed it)
     //   bit23     real-valued rows of unit norm: keep the norm K-step of the s8 search (default: dropped, l2_i8x2_kernel NX)
+    //   bit24     pm_ingest_allgather: all gathers first, then all ingests (default: head of the image set first)
     const int code = (prm.debug_flags >> 2) & 7;
     const int fcode = (prm.debug_flags >> 7) & 3;
     const int variant = ((prm.debug_flags >> 1) & 1) ^ 1;
@@ -1096,13 +1097,15 @@ struct DeviceCtx {
     const cudaMemcpyKind up = own_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     uint8_t* raw_stage = ag_own + static_cast<size_t>(n_slots) * slot_w;
     if (wire != dtype_) PM_CUDA(cudaMemsetAsync(ag_flag, 0, sizeof(int), ingest));
-    // Phase 1, the wire: own images -> device (copy engine) and, chunk by chunk (doubling sizes, so that the NCCL launches
-    // pipeline with the upload), ONE grouped all-gather per chunk.  Nothing else of this handle runs on the GPU yet -- the
-    // first batch of the pair loop needs images whose ingest (phase 2) is queued behind the last gather -- so the NCCL
-    // kernels, which do not fit next to the persistent kNN kernels, never have to wait for a gap between two of them
-    // (interleaving gathers and ingest per chunk measured 21 ms of exposed ingest at 8 GPUs, this order ~6 ms).
-    const int first = std::min(n_slots, std::max(1, (32 + R - 1) / R));
-    for (int s0 = 0, s1 = first; s0 < n_slots; s0 = s1, s1 = std::min(n_slots, 2 * s1)) {
+    // The wire: own images -> device (copy engine), one grouped all-gather per chunk of slots, asynchronous ingest of the
+    // gathered images in id order.  The NCCL kernels do not fit next to the persistent kNN kernels, so a gather that is
+    // queued while the pair loop runs has to wait for a gap between two of them.  Order (default): the HEAD -- the first
+    // ~32 images -- is uploaded, gathered and ingested first, so that every rank starts matching (block-cyclic shares begin
+    // with pairs of the first images) while the copy engine brings in the rest of its own images; ONE gather for all the
+    // remaining slots follows and finds its gap when the kNN stream runs out of batches whose images are resident.
+    // debug_flags bit 24 keeps the earlier order (all gathers in chunks of doubling size, then all ingests: the whole
+    // upload of the rank's own images is exposed -- 6 ms of a 41 ms step at 2 GPUs).
+    auto wire_chunk = [&](int s0, int s1) -> int {
       for (int sl = s0; sl < s1; ++sl) {
         uint8_t* w = ag_own + static_cast<size_t>(sl) * slot_w;
         if (sl < n_own) {
@@ -1128,14 +1131,28 @@ struct DeviceCtx {
       const int rc_end = nccl_api().GroupEnd();
       if (rc == kNcclSuccess) rc = rc_end;
       if (rc != kNcclSuccess) return fail(PM_ERR_CUDA, "ncclAllGather: %s", nccl_api().GetErrorString(rc));
+      return PM_OK;
+    };
+    auto ingest_images = [&](int img0, int img1) -> int {
+      for (int img = img0; img < img1; ++img) {
+        const uint8_t* g = ag_all + static_cast<size_t>(img) * slot_w;   // slot s, rank r sits at (s R + r) = image id
+        const int rc2 = set_image(img, g, n_kp, dim_, wire, has_xy ? reinterpret_cast<const int32_t*>(g + img_w) : nullptr, true, true);
+        if (rc2 != PM_OK) return rc2;
+      }
+      return PM_OK;
+    };
+    const int first = std::min(n_slots, std::max(1, (32 + R - 1) / R));
+    int rcw = PM_OK;
+    if ((prm.debug_flags >> 24) & 1) {
+      for (int s0 = 0, s1 = first; s0 < n_slots && rcw == PM_OK; s0 = s1, s1 = std::min(n_slots, 2 * s1)) rcw = wire_chunk(s0, s1);
+      if (rcw == PM_OK) rcw = ingest_images(0, n_total);
+    } else {
+      rcw = wire_chunk(0, first);
+      if (rcw == PM_OK) rcw = ingest_images(0, std::min(n_total, first * R));
+      if (rcw == PM_OK && first < n_slots) rcw = wire_chunk(first, n_slots);
+      if (rcw == PM_OK && first * R < n_total) rcw = ingest_images(first * R, n_total);
     }
-    // Phase 2, the ingest: every image from the gathered buffer, asynchronously, in id order (the pair loop starts on the
-    // first images while the later ones are still being packed).
-    for (int img = 0; img < n_total; ++img) {
-      const uint8_t* g = ag_all + static_cast<size_t>(img) * slot_w;   // slot s, rank r sits at (s R + r) = image id
-      const int rc2 = set_image(img, g, n_kp, dim_, wire, has_xy ? reinterpret_cast<const int32_t*>(g + img_w) : nullptr, true, true);
-      if (rc2 != PM_OK) return rc2;
-    }
+    if (rcw != PM_OK) return rcw;
     if (wire != dtype_) {                                          // the caller promised integer-valued rows: verify
       PM_CUDA(cudaMemcpyAsync(h_agflag, ag_flag, sizeof(int), cudaMemcpyDeviceToHost, ingest));
       ag_check_pending = true;
