@@ -715,14 +715,24 @@ struct DeviceCtx {
           if (!on_device) stats.h2d_bytes += bytes;
         }
         if (dim == TC_DIM) {
-          PM_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), ingest));
+          // asynchronous ingest: the kernel stores the image's facts straight into its pinned record (zero-copy), so
+          // there is no flag memset and no device-to-host copy per image (host-side enqueue cost of a 282-image
+          // collective ingest: 5.4 ms before, the device idle behind it)
+          uint8_t* host_flags = nullptr;
+          if (async) {
+            int* rec = h_recs + static_cast<size_t>(next_rec) * kRecInts;
+            rec[0] = 0; rec[1] = rec[2] = rec[3] = rec[4] = 0;
+            host_flags = reinterpret_cast<uint8_t*>(rec);
+          } else {
+            PM_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), ingest));
+          }
           PM_CUDA(launch_pack_sift(u8src ? nullptr : rdst, u8src, n, qf + static_cast<size_t>(im.row) * TC_KPAD,
                                    tf + static_cast<size_t>(im.row) * TC_KPAD, qnorm + im.row,
                                    u8src ? rdst : nullptr, u8d + static_cast<size_t>(im.row) * 32, d_flag,
                                    iq + static_cast<size_t>(im.row) * TC_I8_ROW,
-                                   it + static_cast<size_t>(im.row) * TC_I8_ROW, qoff + im.row, ingest));
+                                   it + static_cast<size_t>(im.row) * TC_I8_ROW, qoff + im.row, ingest, host_flags));
           ++stats.kernel_launches;
-          PM_CUDA(cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ingest));
+          if (!async) PM_CUDA(cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ingest));
         }
       }
       if (xy_) {
@@ -733,9 +743,8 @@ struct DeviceCtx {
     if (async) {
       // no host synchronisation: facts go to this image's pinned record, an event marks completion
       int* rec = h_recs + static_cast<size_t>(next_rec) * kRecInts;
-      rec[0] = 0; rec[1] = rec[2] = rec[3] = rec[4] = 0;
-      if (dtype != PM_DESC_U8_BITS && dim == TC_DIM)
-        PM_CUDA(cudaMemcpyAsync(rec, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ingest));
+      if (!(dtype != PM_DESC_U8_BITS && dim == TC_DIM && n > 0)) { rec[0] = 0; rec[1] = rec[2] = rec[3] = rec[4] = 0; }
+      // (128-d rows: the record was cleared before pack_sift_kernel, which writes its flags into it)
       if (float_tc_shape() && dtype == PM_DESC_F32 && dim != TC_DIM) {     // 128-d: packed in resolve() if needed
         const int kp = dim + 16;
         PM_CUDA(cudaMemsetAsync(d_fstats, 0, 4 * sizeof(unsigned int), ingest));
@@ -908,7 +917,8 @@ struct DeviceCtx {
     //   bit21     epipolar filter: every iteration in the one-block-per-pair kernel (no staged continuation, ransac.cu)
     //   bit22     epipolar filter: always queue the staged continuation (default: while recent batches needed it)
     //   bit23     real-valued rows of unit norm: keep the norm K-step of the s8 search (default: dropped, l2_i8x2_kernel NX)
-    //   bit24     pm_ingest_allgather: all gathers first, then all ingests (default: head of the image set first)
+    //   bit24     pm_ingest_allgather: all gathers first, then all ingests; bit25: head first, then ONE gather for the rest
+    //             (default: chunks of doubling size, each gathered and ingested in turn)
     const int code = (prm.debug_flags >> 2) & 7;
     const int fcode = (prm.debug_flags >> 7) & 3;
     const int variant = ((prm.debug_flags >> 1) & 1) ^ 1;
@@ -1146,11 +1156,18 @@ struct DeviceCtx {
     if ((prm.debug_flags >> 24) & 1) {
       for (int s0 = 0, s1 = first; s0 < n_slots && rcw == PM_OK; s0 = s1, s1 = std::min(n_slots, 2 * s1)) rcw = wire_chunk(s0, s1);
       if (rcw == PM_OK) rcw = ingest_images(0, n_total);
-    } else {
+    } else if ((prm.debug_flags >> 25) & 1) {
       rcw = wire_chunk(0, first);
       if (rcw == PM_OK) rcw = ingest_images(0, std::min(n_total, first * R));
       if (rcw == PM_OK && first < n_slots) rcw = wire_chunk(first, n_slots);
       if (rcw == PM_OK && first * R < n_total) rcw = ingest_images(first * R, n_total);
+    } else {
+      // chunks of doubling size, each gathered and ingested before the next one is uploaded: the pairs among the first
+      // k images take longer to match than the next k images take to arrive (quadratic against linear)
+      for (int s0 = 0, s1 = first; s0 < n_slots && rcw == PM_OK; s0 = s1, s1 = std::min(n_slots, 2 * s1)) {
+        rcw = wire_chunk(s0, s1);
+        if (rcw == PM_OK) rcw = ingest_images(s0 * R, std::min(n_total, s1 * R));
+      }
     }
     if (rcw != PM_OK) return rcw;
     if (wire != dtype_) {                                          // the caller promised integer-valued rows: verify

@@ -142,7 +142,8 @@ cudaError_t launch_l2_fixup(const uint32_t* u8desc, const int32_t* qnorm, const 
 // pack.cu
 cudaError_t launch_pack_sift(const float* raw_f32, const uint8_t* raw_u8, int n, __half* qf,
                              __half* tf, int32_t* qnorm, float* raw_out, uint32_t* u8_out,
-                             int* not_integral, uint8_t* iq, uint8_t* it, int32_t* qoff, cudaStream_t st);
+                             int* not_integral, uint8_t* iq, uint8_t* it, int32_t* qoff, cudaStream_t st,
+                             uint8_t* host_flags = nullptr);
 cudaError_t launch_u8_to_f32(const uint8_t* src, float* dst, size_t n, cudaStream_t st);
 cudaError_t launch_f32_to_u8(const float* src, uint8_t* dst, size_t n, int* not_integral, cudaStream_t st);
 

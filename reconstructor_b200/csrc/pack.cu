@@ -24,7 +24,11 @@ __global__ void __launch_bounds__(256)
 pack_sift_kernel(const float* __restrict__ raw_f32, const uint8_t* __restrict__ raw_u8, int n,
                  __half* __restrict__ qf, __half* __restrict__ tf, int32_t* __restrict__ qnorm,
                  float* __restrict__ raw_out, uint32_t* __restrict__ u8_out, int* __restrict__ not_integral,
-                 uint8_t* __restrict__ iq, uint8_t* __restrict__ it, int32_t* __restrict__ qoff) {
+                 uint8_t* __restrict__ iq, uint8_t* __restrict__ it, int32_t* __restrict__ qoff,
+                 volatile uint8_t* __restrict__ host_flags) {
+  // host_flags (asynchronous ingest): the two facts are stored straight into the image's pinned record (byte 0: some
+  // value is not an integer in [0, 255]; byte 1: a squared norm beyond the byte form's range) -- no flag memset and no
+  // device-to-host copy per image; every writer stores the same value, the record is read after the image's event
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
@@ -56,7 +60,7 @@ pack_sift_kernel(const float* __restrict__ raw_f32, const uint8_t* __restrict__ 
     sum += iv;
   }
   if (__any_sync(0xffffffffu, bad)) {
-    if (lane == 0) atomicOr(not_integral, 1);
+    if (lane == 0) { if (host_flags) host_flags[0] = 1; else atomicOr(not_integral, 1); }
   }
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) {
@@ -79,7 +83,7 @@ pack_sift_kernel(const float* __restrict__ raw_f32, const uint8_t* __restrict__ 
     trow[TC_DIM + lane] = static_cast<uint8_t>(e);
     if (lane == 0) {
       qoff[row] = nrm - 254 * sum;
-      if (qd > 31 * 255) atomicOr(not_integral, 2);
+      if (qd > 31 * 255) { if (host_flags) host_flags[1] = 1; else atomicOr(not_integral, 2); }
     }
   }
 
@@ -106,10 +110,11 @@ pack_sift_kernel(const float* __restrict__ raw_f32, const uint8_t* __restrict__ 
 
 cudaError_t launch_pack_sift(const float* raw_f32, const uint8_t* raw_u8, int n, __half* qf,
                              __half* tf, int32_t* qnorm, float* raw_out, uint32_t* u8_out,
-                             int* not_integral, uint8_t* iq, uint8_t* it, int32_t* qoff, cudaStream_t st) {
+                             int* not_integral, uint8_t* iq, uint8_t* it, int32_t* qoff, cudaStream_t st,
+                             uint8_t* host_flags) {
   if (n <= 0) return cudaSuccess;
   pack_sift_kernel<<<(n + 7) / 8, 256, 0, st>>>(raw_f32, raw_u8, n, qf, tf, qnorm, raw_out, u8_out,
-                                                not_integral, iq, it, qoff);
+                                                not_integral, iq, it, qoff, host_flags);
   return cudaGetLastError();
 }
 
