@@ -1189,7 +1189,10 @@ fmat_ransac_kernel(const float2* __restrict__ pts1, const float2* __restrict__ p
 //                      sequential loop because hypotheses at or beyond the shrunken bound are discarded.
 // rs_finalize_kernel writes mask / F / status of the handed-over pairs.  Results are identical to the single-kernel
 // path by construction (same subsets, same models, same counts, same selection order); tests compare both.
-static constexpr int RS_CUT = 56;        // 8 + 16 + 32 iterations in the per-pair kernel
+#ifndef PM_RS_CUT
+#define PM_RS_CUT 56
+#endif
+static constexpr int RS_CUT = PM_RS_CUT;   // 8 + 16 + 32 iterations in the per-pair kernel (24 = 8 + 16 measured: see DESIGN)
 static constexpr int RS_MEGA = 256;      // iterations per mega-round
 static constexpr int RS_SOLVE_THREADS = 32;   // 152 registers per thread: small blocks pack next to the kNN kernel
 
