@@ -232,6 +232,7 @@ struct DeviceCtx {
   // development switches, read from the environment ONCE in init() (never in the batch loop):
   bool result_by_ce = true;                  // PM_RESULT_COPY=kernel: compacted matches leave by copy kernels too
   bool trace_on = false;                     // PM_TRACE: device + host timeline of run_pairs
+  bool opt_rampdown = true;                  // PM_RAMPDOWN=0 (development): the last batches keep the full size
   bool staged_hint = false;                  // the last retrieved batch held pairs that ran past the filter's first rounds
   int opt_slots = 0;                         // PM_SLOTS: batches in flight (0 = default)
   bool opt_prefilter = false;                // PM_L2F_PREFILTER: s8-prefilter variant of the re-rank
@@ -344,6 +345,7 @@ struct DeviceCtx {
     if (const char* e = std::getenv("PM_SLOTS")) opt_slots = std::max(1, std::min(32, std::atoi(e)));
     { const char* e = std::getenv("PM_RESULT_COPY"); result_by_ce = !(e && std::strcmp(e, "kernel") == 0); }
     opt_prefilter = std::getenv("PM_L2F_PREFILTER") != nullptr;
+    { const char* e = std::getenv("PM_RAMPDOWN"); opt_rampdown = !(e && e[0] == '0'); }
     {
       // the persistent kNN kernels go first whenever SMs free up; the small tail kernels of earlier batches
       // (default priority) fill whatever registers / shared memory the kNN kernel leaves
@@ -1336,9 +1338,10 @@ struct DeviceCtx {
     int B = prm.batch_pairs > 0 ? prm.batch_pairs : static_cast<int>(std::clamp<int64_t>((2 << 20) / stride, 32, 2048));
     B = static_cast<int>(std::min<int64_t>(B, n_pairs));
     // batches in flight: the kNN kernels run back to back on their own stream, up to S batches ahead of the tails
-    // (measured: 8 or 16 instead of 4 changes nothing -- where the tails cannot be co-resident at a useful occupancy
+    // (6: outlier-heavy pairs have a long chain of staged filter kernels per batch, +3 % there over 4; otherwise
+    // measured: 8 or 16 instead of 4 changes nothing -- where the tails cannot be co-resident at a useful occupancy
     // they are throughput-bound, not latency-bound, once they get the machine).  PM_SLOTS overrides (development).
-    const int S = n_pairs > B ? (opt_slots > 0 ? opt_slots : 4) : 1;
+    const int S = n_pairs > B ? (opt_slots > 0 ? opt_slots : 6) : 1;
     const bool mutual = prm.unique_mode == PM_MUTUAL_NN;
     if (static_cast<int>(slots.size()) < S) slots.resize(S);
     for (int s = 0; s < S; ++s) {
@@ -1361,7 +1364,12 @@ struct DeviceCtx {
       // the first batches are short: with asynchronous ingest they need only the first few images (pair lists run
       // image by image), so the device starts after a fraction of the upload
       const int ramp = b < 3 ? std::max(16, B >> (3 - b)) : B;
-      const int n = static_cast<int>(std::min<int64_t>(std::min(B, ramp), n_pairs - done));
+      // ... and the last batches shrink again (halving, down to 32 pairs): what follows the last kNN kernel of the call
+      // -- fix-up, selection, filter, compaction, D2H of its batch -- overlaps nothing, so that batch is kept small
+      const int64_t rem = n_pairs - done;
+      int64_t want = std::min(B, ramp);
+      if (opt_rampdown && rem < 2 * static_cast<int64_t>(B)) want = std::min<int64_t>(want, std::max<int64_t>(32, (rem + 1) / 2));
+      const int n = static_cast<int>(std::min<int64_t>(want, rem));
       for (int k = 0; k < n; ++k) {
         rc = fill_job(s, k, pairs[2 * (done + k)], pairs[2 * (done + k) + 1]);
         if (rc != PM_OK) return rc;
