@@ -1364,6 +1364,13 @@ __device__ __forceinline__ void rs_score_body(int slot, const float2* __restrict
   if (tid < 32) sC[tid] = 0;
   ModelF32 Mf;
   model_f32(Fd, st.cmax, thr, Mf);
+  if (!act) {
+    // a lane without a model (last block of a pair only) holds constants for which every point is "an outlier for sure"
+    // (|d| = 0 > 2 dd = -1 and (|d| - dd)^2 := 1 >= thr * 0 + 0), so the hot loop needs no test for it
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Mf.F[i] = 0.f;
+    Mf.dd2 = -1.f; Mf.dd_sq = 1.f; Mf.dg1t_lo = Mf.dg2t_lo = Mf.dg1t_hi = Mf.dg2t_hi = 0.f;
+  }
   const float tlo = thr * (1.f - 4e-6f), thi = thr * (1.f + 4e-6f);
   const size_t base = static_cast<size_t>(slot) * stride;
   const float2* p1 = pts1 + base;
@@ -1393,17 +1400,22 @@ __device__ __forceinline__ void rs_score_body(int slot, const float2* __restrict
       for (int j = j0; j < j1; ++j) {
         const float4 q = sPts[j];
         const Side2 s2 = classify32_side2(Mf, q.x, q.y, q.z, q.w, thi);
-        int c = 0;
-        if (__any_sync(0xffffffffu, !s2.out && act)) {          // rare for wrong models: the other side + the inlier test
-          c = classify32_rest(Mf, s2, q.z, q.w, tlo, thi);
+#ifdef PM_RANSAC_PARANOID
+        int c_chk = 0;
+#endif
+        if (__any_sync(0xffffffffu, !s2.out)) {                 // rare for wrong models: the other side + the inlier test
+          int c = classify32_rest(Mf, s2, q.z, q.w, tlo, thi);
           if (c == 2 && act) c = literal_inlier(Fd, make_float2(q.x, q.y), make_float2(q.z, q.w), MODE, thr);
+          cnt += c & 1;                                         // (lanes without a model always read "outlier for sure")
+#ifdef PM_RANSAC_PARANOID
+          c_chk = c;
+#endif
         }
 #ifdef PM_RANSAC_PARANOID
-        if (act && literal_inlier(Fd, make_float2(q.x, q.y), make_float2(q.z, q.w), MODE, thr) != (c & 1))
-          printf("RANSAC PARANOID MISMATCH (staged) w %d cls %d pt (%g,%g)-(%g,%g)\n", w, c, q.x, q.y, q.z, q.w);
+        if (act && literal_inlier(Fd, make_float2(q.x, q.y), make_float2(q.z, q.w), MODE, thr) != (c_chk & 1))
+          printf("RANSAC PARANOID MISMATCH (staged) w %d cls %d pt (%g,%g)-(%g,%g)\n", w, c_chk, q.x, q.y, q.z, q.w);
         if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0 && i0 == 0 && j == 0) printf("paranoid build active (staged)\n");
 #endif
-        cnt += c & 1;
       }
     } else {
       int j = j0;
