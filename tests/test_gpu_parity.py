@@ -1167,6 +1167,54 @@ def test_staged_filter_batched_loop_with_outliers_equals_one_kernel_filter():
     assert (outs[0]["ransac_iters"] > 24).sum() >= 10
 
 
+def _random_two_view(rng, n, of, subpixel, scale, shift):
+    def rot(rx, ry, rz):
+        cx, sx, cy, sy, cz, sz = np.cos(rx), np.sin(rx), np.cos(ry), np.sin(ry), np.cos(rz), np.sin(rz)
+        Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]); Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+        return np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]]) @ Ry @ Rx
+    X = rng.uniform(-1, 1, (n, 3)) * np.array([1.0, 0.8, 0.6]) + np.array([0, 0, 5.0])
+    f, cx, cy = 1200.0, 1024.0, 768.0
+    R = rot(0.1 * rng.standard_normal(), rng.uniform(0.05, 0.35) * rng.choice([-1, 1]), 0.05 * rng.standard_normal())
+    t = np.array([rng.uniform(0.3, 1.0), 0.1 * rng.standard_normal(), 0.1 * rng.standard_normal()])
+    proj = lambda P: np.stack([f * P[:, 0] / P[:, 2] + cx, f * P[:, 1] / P[:, 2] + cy], 1)
+    p1 = proj(X) + 0.5 * rng.standard_normal((n, 2))
+    p2 = proj(X @ R.T + t) + 0.5 * rng.standard_normal((n, 2))
+    bad = rng.random(n) < of
+    p2[bad] = rng.uniform(0, 1, (int(bad.sum()), 2)) * np.array([2048, 1536])
+    if not subpixel:
+        p1, p2 = np.trunc(p1), np.trunc(p2)
+    return (p1 * scale + shift).astype(np.float32), (p2 * scale + shift).astype(np.float32)
+
+
+def test_fuzz_epipolar_filter_staged_per_pair_and_cpu_filter():
+    """Random two-view scenes (8..3000 matches, 0..80 % outliers, integer / sub-pixel / shifted / scaled coordinates, both
+    samplers, both residual modes, several iteration caps): the staged filter, the per-pair kernel and the CPU filter agree
+    on status, mask, iteration count (and the two GPU forms on F bit for bit).  tools/r02/fuzz_ransac.py ran 300 more."""
+    n_long = 0
+    for seed in range(40):
+        rng = np.random.default_rng(777 + seed)
+        sampler = int(rng.integers(0, 2)); resid = int(rng.integers(0, 2))
+        cap = int(rng.choice([1000, 1000, 1000, 300, 2000, 25, 281]))
+        n = int(rng.choice([8, 9, 15, 40, 100, 333, 1000, 2050, 3000]))
+        of = float(rng.choice([0.0, 0.2, 0.4, 0.5, 0.6, 0.8]))
+        scale, shift = [(1.0, 0.0), (1.0, 0.0), (0.37, 0.0), (1.0, 50000.0), (31.0, 0.0)][int(rng.integers(0, 5))]
+        p1, p2 = _random_two_view(rng, n, of, bool(rng.integers(0, 2)), scale, shift)
+        osamp = orc.SAMPLER_PHILOX if sampler else orc.SAMPLER_OPENCV_MWC
+        prm = orc.default_params(residual_mode=resid, sampler=osamp, seed=seed, max_iters=cap)
+        ns, Fo, mo, tr = orc.find_fundamental(p1, p2, prm)
+        res = []
+        for flags in (0, 1 << 21):
+            with api.PairMatcher(sampler=sampler, residual_mode=resid, seed=seed, ransac_max_iters=cap, debug_flags=flags) as pm:
+                res.append(pm.estimate_fundamental(p1, p2))
+        (F, mask, st, it), (F1, mask1, st1, it1) = res
+        assert st == st1 and it == it1 and np.array_equal(mask, mask1) and np.array_equal(F, F1), (seed, it, it1)
+        assert (st == api.PAIR_FILTERED) == (ns > 0) and it == tr.iters_run, (seed, it, tr.iters_run)
+        if ns > 0:
+            assert np.array_equal(mask, mo), seed
+        n_long += it > 24
+    assert n_long >= 15
+
+
 def test_eight_point_refit_matches_cpu_filter_and_cv2(scenes, golden_dir):
     g8 = np.load(os.path.join(golden_dir, "eight_point.npz"))
     prm = orc.default_params(refit_8point=1)
