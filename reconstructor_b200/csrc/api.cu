@@ -921,6 +921,8 @@ struct DeviceCtx {
     //   bit23     real-valued rows of unit norm: keep the norm K-step of the s8 search (default: dropped, l2_i8x2_kernel NX)
     //   bit24     pm_ingest_allgather: all gathers first, then all ingests; bit25: head first, then ONE gather for the rest
     //             (default: chunks of doubling size, each gathered and ingested in turn)
+    //   bit26     256-bit rows on kind::mxf4: one train row per accumulator column (the round-1 form) instead of two
+    //             (l2_i8x2_kernel PK, the default)
     const int code = (prm.debug_flags >> 2) & 7;
     const int fcode = (prm.debug_flags >> 7) & 3;
     const int variant = ((prm.debug_flags >> 1) & 1) ^ 1;
@@ -957,7 +959,9 @@ struct DeviceCtx {
           cudaError_t e = cudaMemsetAsync(oi, 0xFF, sizeof(int2) * static_cast<size_t>(n) * s.stride, knn_stream);
           if (e != cudaSuccess) return e;
         }
-        if (use_tch4) return launch_ham_fp4x2(h4maps, jobs_d, n, mq, oi, od, s.stride, num_sms, probe, knn_stream, words);
+        if (use_tch4)
+          return launch_ham_fp4x2(h4maps, jobs_d, n, mq, oi, od, s.stride, num_sms, probe, knn_stream, words,
+                                  words == 8 && !((prm.debug_flags >> 26) & 1));
         return launch_ham_i8x2(h8maps, jobs_d, n, mq, oi, od, s.stride, num_sms, probe, knn_stream);
       }
       if (use_tch) return launch_ham_tc2(hmaps, words, qnorm, jobs_d, n, mq, oi, od, s.stride, num_sms, knn_stream);

@@ -89,7 +89,7 @@ cudaError_t launch_ham_i8x2(const TcMaps& maps, const PairJob* jobs, int n_jobs,
 // 256-bit rows as E2M1 values on kind::mxf4, 192-column train tiles (l2_tc2.cu, l2_i8x2_kernel<.., 1, 1>); maps: rows of
 // 160 bytes (128 bytes = 256 four-bit values + 32 bytes = 64-value norm block), t_main96 / t_ext96 boxes for the train side
 cudaError_t launch_ham_fp4x2(const TcMaps& maps, const PairJob* jobs, int n_jobs, int max_nq, int2* idx, float2* dist,
-                             int stride, int num_sms, int probe, cudaStream_t st, int words = 8);
+                             int stride, int num_sms, int probe, cudaStream_t st, int words = 8, int packed = 0);
 cudaError_t hamming_fixup_configure();
 
 // real-valued rows on the tensor cores: l2_tc2.cu (MODE 3) + l2f_fixup.cu

@@ -337,6 +337,53 @@ __device__ __forceinline__ void t2i_chunk32(Top2i& s, uint32_t (&v)[32], int c, 
     if (lim > 16) t2i_fast16(s, v + 16, c + 16);
   }
 }
+// ---- packed pairs (l2_i8x2_kernel PK): two Hamming distances per fp32 accumulator ------------------------
+// v = 2^19 + 1024 H(c) + (512 + H(c + 192)) (see the kernel): bit pattern 0x49000000 | n << 4 with the high field
+// n[10..18] = H(c) and the low field n[0..9] = 512 + H(c + 192).  One multiplication by 4 (fma pipe; the minima keep the
+// alu pipe busy, and each pipe issues one warp instruction per two cycles) drops the top exponent bits and puts the two
+// fields into the two 16-bit HALVES of the word -- high half 0x2400 | H(c), low half (512 + H(c + 192)) << 6 -- so that
+// ONE tree of three-input unsigned 16x2 minima (VIMNMX3.U16x2) reduces both at once: 32 fma + 16 alu instructions for
+// the 64 distances of 32 columns (the one-row form: 16 alu instructions for 32 distances).
+static constexpr uint32_t T2P_SF_BIG = 0x89898989u;             // UE8M0 2^10, four scale factors per TMEM column
+static constexpr float T2P_BIAS = 512.f;                        // what the bias slots of the norm block add (pack.cu)
+__device__ __forceinline__ uint32_t t2_umin32x2(const uint32_t (&r)[32]) {
+  uint32_t a[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) a[k] = __vimin3_u16x2(r[3 * k], r[3 * k + 1], r[3 * k + 2]);
+  const uint32_t b0 = __vimin3_u16x2(a[0], a[1], a[2]), b1 = __vimin3_u16x2(a[3], a[4], a[5]);
+  const uint32_t b2 = __vimin3_u16x2(a[6], a[7], a[8]), b3 = __vimin3_u16x2(a[9], r[30], r[31]);
+  return __vminu2(__vimin3_u16x2(b0, b1, b2), b3);
+}
+// v: 32 columns, of which the first lim_hi / lim_lo carry a row behind the high / low field; m_hi / m_lo: the smallest H
+// of those rows (garbage when lim <= 0: not used)
+__device__ __forceinline__ void t2p_chunk32(const uint32_t* v, int lim_hi, int lim_lo, int& m_hi, int& m_lo) {
+  uint32_t four;
+  asm volatile("mov.u32 %0, 4;" : "=r"(four));
+  uint32_t w[32];
+#pragma unroll
+  for (int e = 0; e < 32; ++e) w[e] = v[e] * four;
+  if (lim_lo < 32) {                                   // ragged / absent second sub-tile
+#pragma unroll
+    for (int e = 0; e < 32; ++e)
+      if (e >= lim_lo) w[e] |= 0x0000FFFFu;
+  }
+  if (lim_hi < 32) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e)
+      if (e >= lim_hi) w[e] = 0xFFFFFFFFu;
+  }
+  const uint32_t m = t2_umin32x2(w);
+  m_hi = static_cast<int>((m >> 16) & 0x1FFu);
+  m_lo = static_cast<int>((m & 0xFFFFu) >> 6) - 512;
+}
+__device__ __forceinline__ void t2i_update(Top2i& s, int cm, int cbase) {
+  bool keep;                                         // m1 <= cm: the earlier chunk stays the winner
+  const int nm1 = __vibmin_s32(s.m1, cm, &keep);
+  const int t = max(cm, s.m1);
+  s.i1 = keep ? s.i1 : cbase;
+  s.m1 = nm1;
+  s.m2 = min(s.m2, t);
+}
 // ---- MODE 3: six smallest chunk minima as keys ---------------------------------------------------
 // key = positive fp32 score with the low 10 mantissa bits replaced by the 16-column chunk id (the
 // scores are approximate anyway; l2f_fixup.cu widens its error bound by the 2^-13 relative truncation).
@@ -935,15 +982,18 @@ cudaError_t launch_ham_tc2(const TcMaps& maps, int words, const int32_t* qnorm, 
 // MMAs of set 1 run, and vice versa.  Everything else as in l2_top2_tc2_kernel<T2I8, 2, *, 2>.
 //   smem per CTA: query tiles 2 items x 2 sets x 20 KB, train ring 4 x 20 KB, barriers, slice exchange.
 // MODE 2: product; 1: TMA + MMA only; 5: + tcgen05.ld without the reduction (timing probes, no results).
-template <int KA, int BN_ = 256, int STG = 0>
+template <int KA, int BN_ = 256, int STG = 0, int PK = 0>
 struct I8X2Cfg {                                                 // KA = 128-byte K atoms per row: 1 (SIFT bytes), 2 (256-bit rows)
   static constexpr int kKA = KA;                                 // BN_ = 192: the fp4 form (TMEM columns 384.. hold the scale factors)
   static constexpr int kBN = BN_, kBNH = BN_ / 2, kSets = 2;
-  static constexpr int kAStages = KA == 1 ? 2 : 1, kStages = STG ? STG : (KA == 1 ? (BN_ == 256 ? 4 : 5) : 3);
+  static constexpr int kSub = PK ? 2 : 1;                        // PK: a stage holds TWO train sub-tiles (rows c and c + BN share a column)
+  static constexpr int kAStages = KA == 1 ? 2 : 1, kStages = STG ? STG : (PK ? 3 : (KA == 1 ? (BN_ == 256 ? 4 : 5) : 3));
   static constexpr int kTile = KA * T2_ATOM + T2_EXT;            // 20 / 36 KB: 128 rows x (128 KA + 32) B
   static constexpr int kSmemA = kAStages * kSets * kTile;        // 80 / 72 KB
   static constexpr int kBAtom = kBNH * 128;
-  static constexpr int kBTile = KA * kBAtom + kBNH * 32;         // 20 / 36 KB
+  static constexpr int kBSub = KA * kBAtom + kBNH * 32;          // 20 / 36 KB (15 KB for 96-row halves)
+  static constexpr int kBTile = kSub * kBSub;
+  static constexpr int kTileRows = kSub * BN_;                   // train rows per stage
   static constexpr int kSmemB = kStages * kBTile;                // 80 / 108 KB
   static constexpr int kSlices = BN_ / 64, kEpiWarps = 4 * kSlices, kThreads = 128 + 32 * kEpiWarps;
   static constexpr int kXchg = 4 * (kSlices - 1) * 32 * 32;
@@ -959,7 +1009,8 @@ struct I8X2Cfg {                                                 // KA = 128-byt
 };
 using I8X2 = I8X2Cfg<1>;
 
-// LEAN: 0 = no register cap, 1 = 64 registers (launch bound of 1024 threads), 2 = 72 registers (bound of 896 threads):
+// LEAN: 0 = no register cap, 1 = 64 registers (launch bound of 1024 threads), 3 = 96 registers (bound of 640 threads: the
+// packed form's 512 threads then leave the 16 K registers of one RANSAC block), 2 = 72 registers (bound of 896 threads):
 // 640 threads x 72 leave 19 K registers for the tail kernels of earlier batches (the RANSAC block needs 16 K)
 // NX = 1 (MODE 4 only, real-valued rows whose squared norms are all within L2S8_UNIT_TOL of 1 -- SuperPoint rows are
 // L2-normalised, FeatureSuperPoint.cpp:195-205): the norm term of the score is the same constant for every train row, so
@@ -967,14 +1018,26 @@ using I8X2 = I8X2Cfg<1>;
 // T2K_UNIT_OFF = 254^2 (1/2 + 1) enters the chunk keys in the epilogue.  The scores are those of rows of norm exactly 1;
 // the re-rank's certified bound carries the tolerance (ff_bound e_mode 2).
 static constexpr int T2K_UNIT_OFF = 96774;                      // 254^2 * 1.5, exact
-template <int MODE, int LEAN, int KA = 1, int FP4 = 0, int STG = 0, int NX = 0>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LEAN == 1 ? 1024 : LEAN == 2 ? 896 : I8X2Cfg<KA, FP4 ? 192 : 256>::kThreads, 1)
+// PK = 1 (256-bit rows on kind::mxf4, MODE 1 / 2): TWO train rows per accumulator column.  Draining a 192-column
+// accumulator through tcgen05.ld (64 B/clk per scheduler) takes 80 % of the time the tensor pipe needs for the other row
+// set's 5 K-steps, so the hand-over commit -> wake -> ld -> arrive -> issue never hid.  The
+// block scale factors of kind::mxf4 halve the drain: a stage holds two train sub-tiles (rows c.. and c + 192..), the
+// K-steps of the FIRST one run with UE8M0 scale 2^10 on the B side, those of the second with scale 1, all into one
+// accumulator.  Every packed row carries bias slots in its norm block worth 512 (pack.cu), so a column ends as
+//     1024 (512 + H(c)) + (512 + H(c + 192)) = 2^19 + 1024 H(c) + (512 + H(c + 192)):
+// every value lies in the binade of 2^19 (the first sub-tile's row exists whenever the second one's does; an absent or
+// zero second row adds 0), so the fp32 bit pattern is 0x49000000 | n << 4 and both Hamming distances (<= 256; exact:
+// every partial sum is an integer below 2^20) are read with shifts and masks.  Ten K-steps between hand-overs instead of
+// five, for half as many accumulator reads; both 32-column loads of a warp are issued before anything is reduced.
+template <int MODE, int LEAN, int KA = 1, int FP4 = 0, int STG = 0, int NX = 0, int PK = 0>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LEAN == 1 ? 1024 : LEAN == 2 ? 896 : LEAN == 3 ? 640 : I8X2Cfg<KA, FP4 ? 192 : 256>::kThreads, 1)
 l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant__ CUtensorMap q_ext,
                const __grid_constant__ CUtensorMap t_main, const __grid_constant__ CUtensorMap t_ext,
                const PairJob* __restrict__ jobs, int n_jobs, int blocks_per_job, int2* __restrict__ knn_idx,
                float2* __restrict__ knn_dist, int stride, float2* __restrict__ extra_keys = nullptr) {
-  using C = I8X2Cfg<KA, FP4 ? 192 : 256, STG>;
+  using C = I8X2Cfg<KA, FP4 ? 192 : 256, STG, PK>;
   static_assert(MODE < 3 || MODE == 5 || !FP4, "candidate keys are integer keys of the kind::i8 accumulators");
+  static_assert(!PK || (FP4 && KA == 1 && (MODE == 1 || MODE == 2)), "packed pairs: 256-bit rows on kind::mxf4");
   constexpr int BN = C::kBN, BNH = C::kBNH, ST = C::kStages, TILE = C::kTile, BTILE = C::kBTile, NSL = C::kSlices;
   constexpr int AST = C::kAStages, KDIM = 128 * KA, BATOM = C::kBAtom;
   static_assert(!FP4 || KA <= 2, "fp4 forms: one 128-byte K atom per 256 bits (256- and 512-bit rows)");
@@ -1023,6 +1086,10 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
       const uint32_t a = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + C::kSfCol;
       tmem_st_32x32b_x32_fill(a, 0x7F7F7F7Fu);
       tmem_st_32x32b_x32_fill(a + 32, 0x7F7F7F7Fu);
+      if (PK) {                                          // columns 448..511: scale 2^10 for the first sub-tile's B rows
+        tmem_st_32x32b_x32_fill(a + 64, T2P_SF_BIG);
+        tmem_st_32x32b_x32_fill(a + 96, T2P_SF_BIG);
+      }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -1056,16 +1123,20 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
           }
         }
         ++ai;
-        const int n_tiles = (job.nt + BN - 1) / BN;
+        const int n_tiles = (job.nt + C::kTileRows - 1) / C::kTileRows;
         for (int n = 0; n < n_tiles; ++n, ++bi) {
-          const int row = job.t_row + n * BN + rank * BNH;        // this CTA's half of the train tile
           const uint32_t st = bi % ST;
           wait_tma(&b_empty[st], ((bi / ST) & 1) ^ 1);
-          if (leader) mbar_expect_tx(&b_full[st], 2 * (NX ? BTILE - BNH * 32 : BTILE));
-          uint8_t* dst = sB + st * BTILE;
+          // PK: the second sub-tile (rows + BN) is neither loaded nor multiplied when it lies past the image
+          const int nsub = PK && n * C::kTileRows + BN < job.nt ? 2 : 1;
+          if (leader) mbar_expect_tx(&b_full[st], 2 * (PK ? nsub * C::kBSub : (NX ? BTILE - BNH * 32 : BTILE)));
+          for (int sub = 0; sub < nsub; ++sub) {
+            const int row = job.t_row + n * C::kTileRows + sub * BN + rank * BNH;   // this CTA's half of the train (sub-)tile
+            uint8_t* dst = sB + st * BTILE + sub * C::kBSub;
 #pragma unroll
-          for (int a = 0; a < KA; ++a) tma_load_2d_pair(dst + a * BATOM, &t_main, 128 * a, row, &b_full[st]);
-          if (!NX) tma_load_2d_pair(dst + KA * BATOM, &t_ext, KDIM, row, &b_full[st]);
+            for (int a = 0; a < KA; ++a) tma_load_2d_pair(dst + a * BATOM, &t_main, 128 * a, row, &b_full[st]);
+            if (!NX) tma_load_2d_pair(dst + KA * BATOM, &t_ext, KDIM, row, &b_full[st]);
+          }
         }
       }
     }
@@ -1085,11 +1156,12 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
         const uint32_t a_st = ai % AST;
         wait_mma(&a_full[a_st], (ai / AST) & 1);
         ++ai;
-        const int n_tiles = (job_nt + BN - 1) / BN;
+        const int n_tiles = (job_nt + C::kTileRows - 1) / C::kTileRows;
         for (int n = 0; n < n_tiles; ++n, ++bi) {
           const uint32_t st = bi % ST;
           wait_mma(&b_full[st], (bi / ST) & 1);
           const uint32_t b_lo = b_lo0 + st * (BTILE >> 4);
+          const int nsub = PK && n * C::kTileRows + BN < job_nt ? 2 : 1;
           for (int set = 0; set < nset; ++set) {
             wait_mma(&acc_empty[set], (use[set] & 1) ^ 1);
             ++use[set];
@@ -1097,7 +1169,22 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
             if (elect_one()) {
               const uint32_t d_tmem = tmem_base + set * BN;
               const uint32_t a_lo = a_lo0 + (a_st * 2 + set) * (TILE >> 4);
-              if (FP4) {
+              if (PK) {
+                // two sub-tiles into ONE accumulator: 5 K-steps with B scale 2^10 (TMEM columns kSfCol + 64..), then 5
+                // with B scale 1
+                const uint32_t sfa = tmem_base + C::kSfCol;
+                for (int sub = 0; sub < nsub; ++sub) {
+                  const uint32_t sfb = tmem_base + C::kSfCol + (sub ? 16 : 64);
+                  const uint32_t bl = b_lo + sub * (C::kBSub >> 4);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_mxf4_pair(d_tmem, (static_cast<uint64_t>(HI128) << 32) | (a_lo + ((k * 32) >> 4)),
+                                   (static_cast<uint64_t>(HI128) << 32) | (bl + ((k * 32) >> 4)), C::kIdescFp4, sfa, sfb,
+                                   (sub | k) > 0 ? 1u : 0u);
+                  umma_mxf4_pair(d_tmem, (static_cast<uint64_t>(HI32) << 32) | (a_lo + (T2_ATOM >> 4)),
+                                 (static_cast<uint64_t>(HI32) << 32) | (bl + (BATOM >> 4)), C::kIdescFp4, sfa, sfb, 1u);
+                }
+              } else if (FP4) {
                 // 4 KA x 64 bit values of the row + the 64-value norm block: 5 / 9 K-steps of kind::mxf4 (K = 64)
                 const uint32_t sfa = tmem_base + C::kSfCol, sfb = tmem_base + C::kSfCol + 16;
 #pragma unroll
@@ -1148,9 +1235,9 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
       Keys3w h0, h1;                                    // MODE 4
       h0.k1 = h0.k2 = h0.k3 = h0.w2 = T2K_NONE;
       h1 = h0;
-      const int n_tiles = (job.nt + BN - 1) / BN;
+      const int n_tiles = (job.nt + C::kTileRows - 1) / C::kTileRows;
       for (int n = 0; n < n_tiles; ++n) {
-        const int c0 = n * BN + slice * 64;
+        const int c0 = n * C::kTileRows + slice * 64;
         const int lim = job.nt - c0;
 #pragma unroll
         for (int set = 0; set < 2; ++set) {
@@ -1161,6 +1248,23 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
             if (MODE == 1) {
               tc_fence_before();
               if (lane == 0) mbar_arrive_leader(&acc_empty[set]);
+            } else if (PK) {
+              // column e of this slice: high field = train row c0 + e, low field = train row c0 + BN + e.  Both loads,
+              // the hand-back, then the chunk minima of both fields and the four updates in ascending order of the
+              // chunk base (ties keep the earlier chunk).
+              Top2i& s = set ? s1 : s0;
+              uint32_t v[64];
+              int hi0, lo0, hi1, lo1;
+              tmem_ld_32x32b_x64_async(tq + set * BN, v);
+              tmem_wait_pin(v);
+              tc_fence_before();
+              if (lane == 0) mbar_arrive_leader(&acc_empty[set]);
+              t2p_chunk32(v, lim, lim - BN, hi0, lo0);
+              t2p_chunk32(v + 32, lim - 32, lim - BN - 32, hi1, lo1);
+              if (lim > 0) t2i_update(s, hi0, c0);
+              if (lim > 32) t2i_update(s, hi1, c0 + 32);
+              if (lim > BN) t2i_update(s, lo0, c0 + BN);
+              if (lim > BN + 32) t2i_update(s, lo1, c0 + BN + 32);
             } else {
               uint32_t v[32];
               tmem_ld_32x32b_x32(tq + set * BN, v);
@@ -1268,7 +1372,14 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
                 // -3: integer values of the byte forms; -2: the fp4 form's accumulators are non-negative floats
                 // (integer order == float order), hamming_fixup reads them as floats
                 knn_idx[o] = make_int2(s.i1, FP4 ? -2 : -3);
-                knn_dist[o] = make_float2(__int_as_float(s.m1), __int_as_float(s.m2));
+                if (PK)                             // integer distances -> the floats hamming_fixup reads
+                  knn_dist[o] = make_float2(s.m1 == T2I_INF ? __int_as_float(T2I_INF) : static_cast<float>(s.m1),
+                                            s.m2 == T2I_INF ? __int_as_float(T2I_INF) : static_cast<float>(s.m2));
+                else if (FP4 && KA == 1)            // 256-bit E2M1 rows: the bias slots of the norm block added 512
+                  knn_dist[o] = make_float2(s.m1 == T2I_INF ? __int_as_float(T2I_INF) : __int_as_float(s.m1) - T2P_BIAS,
+                                            s.m2 == T2I_INF ? __int_as_float(T2I_INF) : __int_as_float(s.m2) - T2P_BIAS);
+                else
+                  knn_dist[o] = make_float2(__int_as_float(s.m1), __int_as_float(s.m2));
               }
             }
             asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NSL) : "memory");
@@ -1287,12 +1398,12 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
   }
 }
 
-template <int MODE, int LEAN, int KA = 1, int FP4 = 0, int STG = 0, int NX = 0>
+template <int MODE, int LEAN, int KA = 1, int FP4 = 0, int STG = 0, int NX = 0, int PK = 0>
 static cudaError_t i8x2_attr() {
-  cudaError_t e = cudaFuncSetAttribute(l2_i8x2_kernel<MODE, LEAN, KA, FP4, STG, NX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       I8X2Cfg<KA, FP4 ? 192 : 256, STG>::kSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(l2_i8x2_kernel<MODE, LEAN, KA, FP4, STG, NX, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       I8X2Cfg<KA, FP4 ? 192 : 256, STG, PK>::kSmemBytes);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(l2_i8x2_kernel<MODE, LEAN, KA, FP4, STG, NX>, cudaFuncAttributePreferredSharedMemoryCarveout,
+  return cudaFuncSetAttribute(l2_i8x2_kernel<MODE, LEAN, KA, FP4, STG, NX, PK>, cudaFuncAttributePreferredSharedMemoryCarveout,
                               cudaSharedmemCarveoutMaxShared);
 }
 
@@ -1390,6 +1501,8 @@ cudaError_t i8x2_configure() {
   if ((e = i8x2_attr<1, false, 1, 1>()) != cudaSuccess) return e;
   if ((e = i8x2_attr<2, false, 2, 1>()) != cudaSuccess) return e;
   if ((e = i8x2_attr<1, false, 2, 1>()) != cudaSuccess) return e;
+  if ((e = i8x2_attr<2, 3, 1, 1, 0, 0, 1>()) != cudaSuccess) return e;
+  if ((e = i8x2_attr<1, false, 1, 1, 0, 0, 1>()) != cudaSuccess) return e;
   return i8x2_attr<5, false>();
 }
 
@@ -1419,8 +1532,9 @@ cudaError_t launch_ham_i8x2(const TcMaps& maps, const PairJob* jobs, int n_jobs,
 // instruction rate of kind::i8, so a train tile costs 5 K-steps instead of 9 and the fp32 accumulator IS the Hamming
 // distance (exact: every partial sum is an integer of magnitude <= 512).  192-column train tiles leave TMEM columns for
 // the (all-ones) scale factors.  hamming_fixup (32-column chunks, float inputs) follows.  probe: TMA + MMA timing probe.
+// packed (256-bit rows): two train rows per accumulator column (l2_i8x2_kernel PK), same results.
 cudaError_t launch_ham_fp4x2(const TcMaps& maps, const PairJob* jobs, int n_jobs, int max_nq, int2* idx, float2* dist,
-                             int stride, int num_sms, int probe, cudaStream_t st, int words) {
+                             int stride, int num_sms, int probe, cudaStream_t st, int words, int packed) {
   if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
   using C = I8X2Cfg<1, 192>;
   using C2 = I8X2Cfg<2, 192>;
@@ -1439,6 +1553,16 @@ cudaError_t launch_ham_fp4x2(const TcMaps& maps, const PairJob* jobs, int n_jobs
     return cudaGetLastError();
   }
   if (words != 8) return cudaErrorInvalidValue;
+  if (packed) {
+    using CP = I8X2Cfg<1, 192, 0, 1>;
+    if (probe)
+      l2_i8x2_kernel<1, false, 1, 1, 0, 0, 1><<<grid, CP::kThreads, CP::kSmemBytes, st>>>(
+          maps.q_main, maps.q_ext, maps.t_main96, maps.t_ext96, jobs, n_jobs, blocks_per_job, idx, dist, stride);
+    else
+      l2_i8x2_kernel<2, 3, 1, 1, 0, 0, 1><<<grid, CP::kThreads, CP::kSmemBytes, st>>>(
+          maps.q_main, maps.q_ext, maps.t_main96, maps.t_ext96, jobs, n_jobs, blocks_per_job, idx, dist, stride);
+    return cudaGetLastError();
+  }
   if (probe)
     l2_i8x2_kernel<1, false, 1, 1><<<grid, C::kThreads, C::kSmemBytes, st>>>(
         maps.q_main, maps.q_ext, maps.t_main96, maps.t_ext96, jobs, n_jobs, blocks_per_job, idx, dist, stride);

@@ -221,9 +221,10 @@ __device__ __forceinline__ unsigned long long spread_bits8(unsigned int b) {    
 // so that the s32 accumulator is sum a (1 - 2 b) + |b| = |a| + |b| - 2 a.b, the Hamming distance itself.
 // With q4 / t4 (256-bit rows only) also as E2M1 values, two per byte, rows of 160 bytes, for kind::mxf4
 // (l2_i8x2_kernel<.., 1, 1>): 256 values = 128 bytes = ONE 128-byte K atom, then a 64-value norm block:
-//   query form [ bit ? 1 : 0 | 6 x9, 1 x2, 0 x53 ]      train form [ bit ? -1 : +1 | d_0 .. d_10, 0 x53 ]
+//   query form [ bit ? 1 : 0 | 6 x9, 1 x2, 6 x14, 2, 0 x38 ]      train form [ bit ? -1 : +1 | d_0 .. d_10, 6 x14, 4, 0 x38 ]
 // with |b| = 36 n + 6 u + v: d_0..6 = 6 for the first n slots, d_7 + d_8 = u, d_9 + d_10 = v (every digit one of the
-// E2M1 values 0, 1, 2, 3, 4, 6), so that the fp32 accumulator is sum a (1 - 2 b) + |b| = the Hamming distance.
+// E2M1 values 0, 1, 2, 3, 4, 6), so that the fp32 accumulator is sum a (1 - 2 b) + |b| + 512 = the Hamming distance plus
+// the constant of the bias slots 11..25 (what puts the packed-pair kernel's accumulators into one binade, l2_tc2.cu).
 // 512-bit rows (|b| <= 512): the same with NS6 = 14 slots of 36 (query weights 6 x16, 1 x2).
 template <int NS6 = 7>
 __device__ __forceinline__ uint32_t fp4_norm_digit(int slot, int cnt) {       // E2M1 code of train digit `slot`
@@ -281,8 +282,13 @@ pack_bits_kernel(const uint32_t* __restrict__ bits, int n, int words, uint8_t* _
       q4row[256 + lane] = lane < 8 ? 0x77 : (lane == 8 ? 0x22 : 0x00);
       t4row[256 + lane] = static_cast<uint8_t>(fp4_norm_digit<14>(2 * lane, cnt) | (fp4_norm_digit<14>(2 * lane + 1, cnt) << 4));
     } else {
-      q4row[128 + lane] = lane < 4 ? 0x77 : (lane == 4 ? 0x27 : (lane == 5 ? 0x02 : 0x00));
-      t4row[128 + lane] = static_cast<uint8_t>(fp4_norm_digit<7>(2 * lane, cnt) | (fp4_norm_digit<7>(2 * lane + 1, cnt) << 4));
+      // slots 11..25: the BIAS of the packed-pair kernel (l2_i8x2_kernel PK), 14 x 6 * 6 + 2 * 4 = 512 in every product of a
+      // query row with a train row; the one-row kernel subtracts it when it writes a distance
+      const uint8_t qb = lane == 5 ? 0x72 : (lane >= 6 && lane <= 11 ? 0x77 : (lane == 12 ? 0x47 : 0x00));
+      const uint8_t tb = lane == 5 ? 0x70 : (lane >= 6 && lane <= 11 ? 0x77 : (lane == 12 ? 0x67 : 0x00));
+      q4row[128 + lane] = lane < 4 ? 0x77 : (lane == 4 ? 0x27 : qb);
+      t4row[128 + lane] =
+          static_cast<uint8_t>(fp4_norm_digit<7>(2 * lane, cnt) | (fp4_norm_digit<7>(2 * lane + 1, cnt) << 4) | tb);
     }
   }
   if (q8) {

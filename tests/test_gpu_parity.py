@@ -677,30 +677,34 @@ def test_hamming_tensor_full_size_equals_popc():
     w = synth.World("orb", 8192, seed=0xB200 + 3)
     imgs = [w.image(i, 100, outlier_frac=0.3 if i == 2 else 0.0)[:2] for i in range(5)]
     outs = []
-    for flags in (0, FORCE_POPC):
+    for flags in (0, FORCE_POPC, 1 << 26):
         with api.PairMatcher(debug_flags=flags) as pm:
             for i, (d, xy) in enumerate(imgs):
                 pm.set_image(i, d, xy)
             outs.append(pm.match_all_pairs())
-    for k in ("offsets", "q", "t", "inlier", "status", "n_inliers", "ransac_iters", "F"):
-        assert np.array_equal(outs[0][k], outs[1][k]), k
+    for o in outs[1:]:
+        for k in ("offsets", "q", "t", "inlier", "status", "n_inliers", "ransac_iters", "F"):
+            assert np.array_equal(outs[0][k], o[k]), k
     assert outs[0]["offsets"][-1] > 10 * 1500
 
 
 FORCE_E4M3 = 1 << 16
 FORCE_I8 = 1 << 18
+FORCE_FP4_UNPACKED = 1 << 26      # kind::mxf4 with one train row per accumulator column (default: packed pairs)
 
 
 @pytest.mark.parametrize("mode", [api.UNIQUE_FIRST_WINS, api.MUTUAL_NN])
 def test_hamming_i8_two_set_kernel_sizes_around_row_sets(mode):
-    """256-bit rows as E2M1 values on kind::mxf4 (default) vs bytes on kind::i8 vs the E4M3 form vs the XOR/popc kernel,
-    with image sizes on both sides of the 128 / 256 / 512-row boundaries of a work item (one or two resident query row
-    sets), of the 192 / 256-column train tiles and of the 32-column fix-up chunks, duplicates inside and across chunks,
-    all-zero and all-one rows, and one image holding every popcount 0..256 (all digits of the norm block)."""
+    """256-bit rows as E2M1 values on kind::mxf4 (default: two train rows per accumulator column, scale factors 1 and
+    2^10; also the one-row form) vs bytes on kind::i8 vs the E4M3 form vs the XOR/popc kernel, with image sizes on both
+    sides of the 128 / 256 / 512-row boundaries of a work item (one or two resident query row sets), of the 192 / 256 /
+    384-row train tiles (packed form: 192 + 192, second half absent or ragged) and of the 32-column fix-up chunks,
+    duplicates inside and across chunks, all-zero and all-one rows (Hamming distance 256 in either packed field), and one
+    image holding every popcount 0..256 (all digits of the norm block)."""
     rng = np.random.default_rng(77 + mode)
     base = rng.integers(0, 256, (1400, 32), dtype=np.uint8)
     imgs = []
-    for i, n in enumerate((1025, 769, 513, 512, 511, 385, 257, 256, 193, 192, 97, 33, 31, 1)):
+    for i, n in enumerate((1025, 769, 577, 513, 512, 511, 385, 384, 257, 256, 225, 193, 192, 97, 33, 31, 1)):
         ids = rng.permutation(1400)[:n]
         d = base[ids].copy()
         flip = rng.random((n, 32)) < 0.05
@@ -714,7 +718,7 @@ def test_hamming_i8_two_set_kernel_sizes_around_row_sets(mode):
         ramp[k, rng.permutation(256)[:k]] = 1                  # row k has exactly k set bits
     imgs.insert(3, np.packbits(ramp, axis=1))
     outs = []
-    for flags in (0, FORCE_I8, FORCE_E4M3, FORCE_POPC):
+    for flags in (0, FORCE_FP4_UNPACKED, FORCE_I8, FORCE_E4M3, FORCE_POPC):
         with api.PairMatcher(unique_mode=mode, debug_flags=flags, do_filter=0, batch_pairs=7) as pm:
             for i, d in enumerate(imgs):
                 pm.set_image(i, d)
