@@ -344,6 +344,9 @@ __device__ __forceinline__ void t2i_chunk32(Top2i& s, uint32_t (&v)[32], int c, 
 // fields into the two 16-bit HALVES of the word -- high half 0x2400 | H(c), low half (512 + H(c + 192)) << 6 -- so that
 // ONE tree of three-input unsigned 16x2 minima (VIMNMX3.U16x2) reduces both at once: 32 fma + 16 alu instructions for
 // the 64 distances of 32 columns (the one-row form: 16 alu instructions for 32 distances).
+#ifndef PM_PK_PROBE
+#define PM_PK_PROBE 0        // development: 1 = no field shift, 2 = XOR tree instead of the minima (timing only, wrong results)
+#endif
 static constexpr uint32_t T2P_SF_BIG = 0x89898989u;             // UE8M0 2^10, four scale factors per TMEM column
 static constexpr float T2P_BIAS = 512.f;                        // what the bias slots of the norm block add (pack.cu)
 __device__ __forceinline__ uint32_t t2_umin32x2(const uint32_t (&r)[32]) {
@@ -356,23 +359,31 @@ __device__ __forceinline__ uint32_t t2_umin32x2(const uint32_t (&r)[32]) {
 }
 // v: 32 columns, of which the first lim_hi / lim_lo carry a row behind the high / low field; m_hi / m_lo: the smallest H
 // of those rows (garbage when lim <= 0: not used)
+template <bool FULL>
 __device__ __forceinline__ void t2p_chunk32(const uint32_t* v, int lim_hi, int lim_lo, int& m_hi, int& m_lo) {
   uint32_t four;
   asm volatile("mov.u32 %0, 4;" : "=r"(four));
   uint32_t w[32];
 #pragma unroll
-  for (int e = 0; e < 32; ++e) w[e] = v[e] * four;
-  if (lim_lo < 32) {                                   // ragged / absent second sub-tile
+  for (int e = 0; e < 32; ++e) w[e] = PM_PK_PROBE == 1 ? v[e] : v[e] * four;
+  if (!FULL && lim_lo < 32) {                          // ragged / absent second sub-tile
 #pragma unroll
     for (int e = 0; e < 32; ++e)
       if (e >= lim_lo) w[e] |= 0x0000FFFFu;
   }
-  if (lim_hi < 32) {
+  if (!FULL && lim_hi < 32) {
 #pragma unroll
     for (int e = 0; e < 32; ++e)
       if (e >= lim_hi) w[e] = 0xFFFFFFFFu;
   }
-  const uint32_t m = t2_umin32x2(w);
+  uint32_t m = t2_umin32x2(w);
+  if (PM_PK_PROBE == 2) {                                // timing probe: a tree of three-input XORs instead of the minima
+    uint32_t a[11];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) a[k] = w[3 * k] ^ w[3 * k + 1] ^ w[3 * k + 2];
+    a[10] = w[30] ^ w[31];
+    m = (a[0] ^ a[1] ^ a[2]) ^ (a[3] ^ a[4] ^ a[5]) ^ (a[6] ^ a[7] ^ a[8]) ^ (a[9] ^ a[10]);
+  }
   m_hi = static_cast<int>((m >> 16) & 0x1FFu);
   m_lo = static_cast<int>((m & 0xFFFFu) >> 6) - 512;
 }
@@ -1221,6 +1232,9 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
     const int quarter = warp & 3, slice = (warp - 4) >> 2;       // 64-column slice of the tile
     uint32_t use[2] = {0, 0};
     const uint32_t tq = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + slice * 64;
+    uint32_t rem_empty0, rem_empty1;                             // the leader's acc_empty barriers (PK: mapped once)
+    asm("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(rem_empty0) : "r"(smem_u32(&acc_empty[0])));
+    asm("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(rem_empty1) : "r"(smem_u32(&acc_empty[1])));
     for (int item = cluster_id; item < n_items; item += n_clusters) {
       const int jb = item / blocks_per_job, blk = item - jb * blocks_per_job;
       const PairJob job = jobs[jb];
@@ -1258,13 +1272,23 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
               tmem_ld_32x32b_x64_async(tq + set * BN, v);
               tmem_wait_pin(v);
               tc_fence_before();
-              if (lane == 0) mbar_arrive_leader(&acc_empty[set]);
-              t2p_chunk32(v, lim, lim - BN, hi0, lo0);
-              t2p_chunk32(v + 32, lim - 32, lim - BN - 32, hi1, lo1);
-              if (lim > 0) t2i_update(s, hi0, c0);
-              if (lim > 32) t2i_update(s, hi1, c0 + 32);
-              if (lim > BN) t2i_update(s, lo0, c0 + BN);
-              if (lim > BN + 32) t2i_update(s, lo1, c0 + BN + 32);
+              if (lane == 0)
+                asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(set ? rem_empty1 : rem_empty0) : "memory");
+              if (lim >= BN + 64) {                      // every column of both fields carries a row: one straight block
+                t2p_chunk32<true>(v, 32, 32, hi0, lo0);
+                t2p_chunk32<true>(v + 32, 32, 32, hi1, lo1);
+                t2i_update(s, hi0, c0);
+                t2i_update(s, hi1, c0 + 32);
+                t2i_update(s, lo0, c0 + BN);
+                t2i_update(s, lo1, c0 + BN + 32);
+              } else {
+                t2p_chunk32<false>(v, lim, lim - BN, hi0, lo0);
+                t2p_chunk32<false>(v + 32, lim - 32, lim - BN - 32, hi1, lo1);
+                if (lim > 0) t2i_update(s, hi0, c0);
+                if (lim > 32) t2i_update(s, hi1, c0 + 32);
+                if (lim > BN) t2i_update(s, lo0, c0 + BN);
+                if (lim > BN + 32) t2i_update(s, lo1, c0 + BN + 32);
+              }
             } else {
               uint32_t v[32];
               tmem_ld_32x32b_x32(tq + set * BN, v);
