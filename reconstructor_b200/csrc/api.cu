@@ -226,6 +226,7 @@ struct DeviceCtx {
   uint8_t *hq8 = nullptr, *ht8 = nullptr;   // [rows][288] byte forms of 256-bit rows (kind::i8 two-set kernel)
   TcMaps h8maps{};
   bool tch8_ready = false;
+  uint8_t* ht4x = nullptr;                   // [rows][32] pair norm blocks of the 256-bit E2M1 forms (l2_i8x2_kernel PK)
   uint8_t *hq4 = nullptr, *ht4 = nullptr;   // [rows][160 / 288] E2M1 forms of 256- / 512-bit rows (kind::mxf4 two-set kernel)
   TcMaps h4maps{};                           // train boxes of 96 rows (192-column tiles)
   bool tch4_ready = false;
@@ -384,7 +385,7 @@ struct DeviceCtx {
     single.destroy();
     auto fd = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
     fd(raw); fd(qf); fd(tf); fd(qnorm); fd(u8d); fd(bits); fd(xy); fd(d_flag); fd(stage); fd(d_dump); fd(e_scratch);
-    fd(fq); fd(ft); fd(fnorm); fd(d_fstats); fd(d_l2f); fd(hq); fd(ht); fd(iq); fd(it); fd(qoff); fd(sq8); fd(st8); fd(hq8); fd(ht8); fd(hq4); fd(ht4);
+    fd(fq); fd(ft); fd(fnorm); fd(d_fstats); fd(d_l2f); fd(hq); fd(ht); fd(iq); fd(it); fd(qoff); fd(sq8); fd(st8); fd(hq8); fd(ht8); fd(hq4); fd(ht4); fd(ht4x);
     if (comm) { nccl_api().CommDestroy(comm); comm = nullptr; }
     if (ag_own) cudaFree(ag_own);
     if (ag_all) cudaFree(ag_all);
@@ -467,6 +468,11 @@ struct DeviceCtx {
             (r = mkb(&h4maps.t_main96, ht4, 128, CU_TENSOR_MAP_SWIZZLE_128B, 96)) != CUDA_SUCCESS ||
             (r = mkb(&h4maps.t_ext96, ht4, 32, CU_TENSOR_MAP_SWIZZLE_32B, 96)) != CUDA_SUCCESS)
           return fail(PM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+        if (words == 8) {      // packed-pair kernel: one 32-byte norm row for both train rows of an accumulator column
+          kb = 32;
+          if ((r = mkb(&h4maps.t_ext2x96, ht4x, 32, CU_TENSOR_MAP_SWIZZLE_32B, 96)) != CUDA_SUCCESS)
+            return fail(PM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+        }
         tch4_ready = true;
       }
       return PM_OK;
@@ -542,6 +548,7 @@ struct DeviceCtx {
         if (words == 8 || words == 16) {
           if ((rc = grow(hq4, tc_fp4_row(words), nc)) != PM_OK) return rc;
           if ((rc = grow(ht4, tc_fp4_row(words), nc)) != PM_OK) return rc;
+          if (words == 8 && (rc = grow(ht4x, 32, nc)) != PM_OK) return rc;
         }
         if ((rc = grow(qnorm, 1, nc)) != PM_OK) return rc;
       }
@@ -685,7 +692,8 @@ struct DeviceCtx {
                                    ht + im.row * kb, qnorm + im.row, words == 8 ? hq8 + im.row * kb : nullptr,
                                    words == 8 ? ht8 + im.row * kb : nullptr,
                                    (words == 8 || words == 16) ? hq4 + static_cast<size_t>(im.row) * tc_fp4_row(words) : nullptr,
-                                   (words == 8 || words == 16) ? ht4 + static_cast<size_t>(im.row) * tc_fp4_row(words) : nullptr, ingest));
+                                   (words == 8 || words == 16) ? ht4 + static_cast<size_t>(im.row) * tc_fp4_row(words) : nullptr, ingest,
+                                   words == 8 ? ht4x + static_cast<size_t>(im.row) * 32 : nullptr));
           ++stats.kernel_launches;
         }
       } else {

@@ -46,6 +46,7 @@ static constexpr int TC_I8_ROW = 160;     // byte form: 128 x u8/s8 + one K=32 s
 struct TcMaps {
   CUtensorMap q_main, q_ext, t_main, t_ext;   // boxes of 128 rows
   CUtensorMap t_main96, t_ext96;              // boxes of 96 rows (pair kernel, 192-column tiles)
+  CUtensorMap t_ext2x96;                      // 256-bit E2M1 forms: pair norm blocks (pack_bits_kernel t4x), 96-row boxes
 };
 cudaError_t tc_configure();               // one-time function attributes
 cudaError_t launch_l2_tc(const TcMaps& maps, const int32_t* qnorm, const PairJob* jobs, int n_jobs,
@@ -76,7 +77,7 @@ cudaError_t launch_l2_fixup_i8(const uint32_t* u8desc, const int32_t* qnorm, con
 cudaError_t launch_ham_tc2(const TcMaps& maps, int words, const int32_t* qnorm, const PairJob* jobs, int n_jobs,
                            int max_nq, int2* idx, float2* dist, int stride, int num_sms, cudaStream_t st);
 cudaError_t launch_pack_bits(const uint32_t* bits, int n, int words, uint8_t* qb, uint8_t* tb, int32_t* popc,
-                             uint8_t* q8, uint8_t* t8, uint8_t* q4, uint8_t* t4, cudaStream_t st);
+                             uint8_t* q8, uint8_t* t8, uint8_t* q4, uint8_t* t4, cudaStream_t st, uint8_t* t4x = nullptr);
 // ints = 0: float (m1, m2') of 16-column chunks (marker -2, kind::f8f6f4 kernel); ints = 1: integer values of
 // 32-column chunks (marker -3, kind::i8 two-set kernel, words == 8 only); ints = 2: float values of 32-column chunks
 // (marker -2, kind::mxf4 two-set kernel, words == 8 only)

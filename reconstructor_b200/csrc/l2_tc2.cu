@@ -180,6 +180,15 @@ __device__ __forceinline__ void tmem_st_32x32b_x32_fill(uint32_t taddr, uint32_t
       "r"(v)
       : "memory");
 }
+// ... <- one value in the even columns, another in the odd ones
+__device__ __forceinline__ void tmem_st_32x32b_x32_fill2(uint32_t taddr, uint32_t ve, uint32_t vo) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %1, %2, %1, %2, %1, %2, %1, %2, %1, %2, %1, %2, %1, %2, "
+      "%1, %2, %1, %2, %1, %2, %1, %2, %1, %2, %1, %2, %1, %2, %1, %2};" ::"r"(taddr),
+      "r"(ve), "r"(vo)
+      : "memory");
+}
 // Arrives (once all prior MMAs of this thread completed) on the barrier at the same offset in both CTAs.
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
   asm volatile(
@@ -348,6 +357,13 @@ __device__ __forceinline__ void t2i_chunk32(Top2i& s, uint32_t (&v)[32], int c, 
 #define PM_PK_PROBE 0        // development: 1 = no field shift, 2 = XOR tree instead of the minima (timing only, wrong results)
 #endif
 static constexpr uint32_t T2P_SF_BIG = 0x89898989u;             // UE8M0 2^10, four scale factors per TMEM column
+#ifndef PM_PK_SFMODE
+#define PM_PK_SFMODE 0       // where scale_vec::2X reads the scale of a row's two K blocks: 0 = bytes 0 | 1 of a column,
+#endif                       // 1 = bytes 1 | 0, 2 = even | odd columns, 3 = odd | even columns (development)
+static constexpr uint32_t T2P_SF_MIX_E = PM_PK_SFMODE == 0 ? 0x7F897F89u : PM_PK_SFMODE == 1 ? 0x897F897Fu
+                                         : PM_PK_SFMODE == 2 ? 0x89898989u : 0x7F7F7F7Fu;
+static constexpr uint32_t T2P_SF_MIX_O = PM_PK_SFMODE == 0 ? 0x7F897F89u : PM_PK_SFMODE == 1 ? 0x897F897Fu
+                                         : PM_PK_SFMODE == 2 ? 0x7F7F7F7Fu : 0x89898989u;
 static constexpr float T2P_BIAS = 512.f;                        // what the bias slots of the norm block add (pack.cu)
 __device__ __forceinline__ uint32_t t2_umin32x2(const uint32_t (&r)[32]) {
   uint32_t a[10];
@@ -1003,7 +1019,8 @@ struct I8X2Cfg {                                                 // KA = 128-byt
   static constexpr int kSmemA = kAStages * kSets * kTile;        // 80 / 72 KB
   static constexpr int kBAtom = kBNH * 128;
   static constexpr int kBSub = KA * kBAtom + kBNH * 32;          // 20 / 36 KB (15 KB for 96-row halves)
-  static constexpr int kBTile = kSub * kBSub;
+  static constexpr int kBMain = KA * kBAtom;                     // PK: the sub-tiles' main atoms, then ONE shared norm tile
+  static constexpr int kBTile = PK ? 2 * kBMain + kBNH * 32 : kBSub;
   static constexpr int kTileRows = kSub * BN_;                   // train rows per stage
   static constexpr int kSmemB = kStages * kBTile;                // 80 / 108 KB
   static constexpr int kSlices = BN_ / 64, kEpiWarps = 4 * kSlices, kThreads = 128 + 32 * kEpiWarps;
@@ -1097,9 +1114,9 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
       const uint32_t a = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + C::kSfCol;
       tmem_st_32x32b_x32_fill(a, 0x7F7F7F7Fu);
       tmem_st_32x32b_x32_fill(a + 32, 0x7F7F7F7Fu);
-      if (PK) {                                          // columns 448..511: scale 2^10 for the first sub-tile's B rows
-        tmem_st_32x32b_x32_fill(a + 64, T2P_SF_BIG);
-        tmem_st_32x32b_x32_fill(a + 96, T2P_SF_BIG);
+      if (PK) {                                          // columns 448..479: scale 2^10 for the first sub-tile's B rows;
+        tmem_st_32x32b_x32_fill(a + 64, T2P_SF_BIG);     // 480..511: 2^10 for the first K block, 1 for the second (norm step)
+        tmem_st_32x32b_x32_fill2(a + 96, T2P_SF_MIX_E, T2P_SF_MIX_O);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
@@ -1140,14 +1157,17 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
           wait_tma(&b_empty[st], ((bi / ST) & 1) ^ 1);
           // PK: the second sub-tile (rows + BN) is neither loaded nor multiplied when it lies past the image
           const int nsub = PK && n * C::kTileRows + BN < job.nt ? 2 : 1;
-          if (leader) mbar_expect_tx(&b_full[st], 2 * (PK ? nsub * C::kBSub : (NX ? BTILE - BNH * 32 : BTILE)));
+          if (leader)
+            mbar_expect_tx(&b_full[st], 2 * (PK ? nsub * C::kBMain + BNH * 32 : (NX ? BTILE - BNH * 32 : BTILE)));
           for (int sub = 0; sub < nsub; ++sub) {
             const int row = job.t_row + n * C::kTileRows + sub * BN + rank * BNH;   // this CTA's half of the train (sub-)tile
-            uint8_t* dst = sB + st * BTILE + sub * C::kBSub;
+            uint8_t* dst = sB + st * BTILE + sub * (PK ? C::kBMain : C::kBSub);
 #pragma unroll
             for (int a = 0; a < KA; ++a) tma_load_2d_pair(dst + a * BATOM, &t_main, 128 * a, row, &b_full[st]);
-            if (!NX) tma_load_2d_pair(dst + KA * BATOM, &t_ext, KDIM, row, &b_full[st]);
+            if (!NX && !PK) tma_load_2d_pair(dst + KA * BATOM, &t_ext, KDIM, row, &b_full[st]);
           }
+          // PK: t_ext is the map of the pair norm blocks -- rows r and r + BN side by side in one 32-byte operand row
+          if (PK) tma_load_2d_pair(sB + st * BTILE + 2 * C::kBMain, &t_ext, 0, job.t_row + n * C::kTileRows + rank * BNH, &b_full[st]);
         }
       }
     }
@@ -1181,20 +1201,21 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
               const uint32_t d_tmem = tmem_base + set * BN;
               const uint32_t a_lo = a_lo0 + (a_st * 2 + set) * (TILE >> 4);
               if (PK) {
-                // two sub-tiles into ONE accumulator: 5 K-steps with B scale 2^10 (TMEM columns kSfCol + 64..), then 5
-                // with B scale 1
+                // two sub-tiles into ONE accumulator: 4 K-steps with B scale 2^10 (TMEM columns kSfCol + 64..), 4 with B
+                // scale 1, and ONE norm K-step whose two K blocks are the norm blocks of the two rows (scales 2^10 | 1)
                 const uint32_t sfa = tmem_base + C::kSfCol;
                 for (int sub = 0; sub < nsub; ++sub) {
                   const uint32_t sfb = tmem_base + C::kSfCol + (sub ? 16 : 64);
-                  const uint32_t bl = b_lo + sub * (C::kBSub >> 4);
+                  const uint32_t bl = b_lo + sub * (C::kBMain >> 4);
 #pragma unroll
                   for (int k = 0; k < 4; ++k)
                     umma_mxf4_pair(d_tmem, (static_cast<uint64_t>(HI128) << 32) | (a_lo + ((k * 32) >> 4)),
                                    (static_cast<uint64_t>(HI128) << 32) | (bl + ((k * 32) >> 4)), C::kIdescFp4, sfa, sfb,
                                    (sub | k) > 0 ? 1u : 0u);
-                  umma_mxf4_pair(d_tmem, (static_cast<uint64_t>(HI32) << 32) | (a_lo + (T2_ATOM >> 4)),
-                                 (static_cast<uint64_t>(HI32) << 32) | (bl + (BATOM >> 4)), C::kIdescFp4, sfa, sfb, 1u);
                 }
+                umma_mxf4_pair(d_tmem, (static_cast<uint64_t>(HI32) << 32) | (a_lo + (T2_ATOM >> 4)),
+                               (static_cast<uint64_t>(HI32) << 32) | (b_lo + ((2 * C::kBMain) >> 4)), C::kIdescFp4, sfa,
+                               tmem_base + C::kSfCol + 96, 1u);
               } else if (FP4) {
                 // 4 KA x 64 bit values of the row + the 64-value norm block: 5 / 9 K-steps of kind::mxf4 (K = 64)
                 const uint32_t sfa = tmem_base + C::kSfCol, sfb = tmem_base + C::kSfCol + 16;
@@ -1581,10 +1602,10 @@ cudaError_t launch_ham_fp4x2(const TcMaps& maps, const PairJob* jobs, int n_jobs
     using CP = I8X2Cfg<1, 192, 0, 1>;
     if (probe)
       l2_i8x2_kernel<1, false, 1, 1, 0, 0, 1><<<grid, CP::kThreads, CP::kSmemBytes, st>>>(
-          maps.q_main, maps.q_ext, maps.t_main96, maps.t_ext96, jobs, n_jobs, blocks_per_job, idx, dist, stride);
+          maps.q_main, maps.q_ext, maps.t_main96, maps.t_ext2x96, jobs, n_jobs, blocks_per_job, idx, dist, stride);
     else
       l2_i8x2_kernel<2, 3, 1, 1, 0, 0, 1><<<grid, CP::kThreads, CP::kSmemBytes, st>>>(
-          maps.q_main, maps.q_ext, maps.t_main96, maps.t_ext96, jobs, n_jobs, blocks_per_job, idx, dist, stride);
+          maps.q_main, maps.q_ext, maps.t_main96, maps.t_ext2x96, jobs, n_jobs, blocks_per_job, idx, dist, stride);
     return cudaGetLastError();
   }
   if (probe)

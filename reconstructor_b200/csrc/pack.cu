@@ -241,7 +241,8 @@ __device__ __forceinline__ uint32_t fp4_norm_digit(int slot, int cnt) {       //
 __global__ void __launch_bounds__(256)
 pack_bits_kernel(const uint32_t* __restrict__ bits, int n, int words, uint8_t* __restrict__ qb,
                  uint8_t* __restrict__ tb, int32_t* __restrict__ popc, uint8_t* __restrict__ q8,
-                 uint8_t* __restrict__ t8, uint8_t* __restrict__ q4, uint8_t* __restrict__ t4) {
+                 uint8_t* __restrict__ t8, uint8_t* __restrict__ q4, uint8_t* __restrict__ t4,
+                 uint8_t* __restrict__ t4x) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
@@ -284,11 +285,31 @@ pack_bits_kernel(const uint32_t* __restrict__ bits, int n, int words, uint8_t* _
     } else {
       // slots 11..25: the BIAS of the packed-pair kernel (l2_i8x2_kernel PK), 14 x 6 * 6 + 2 * 4 = 512 in every product of a
       // query row with a train row; the one-row kernel subtracts it when it writes a distance
-      const uint8_t qb = lane == 5 ? 0x72 : (lane >= 6 && lane <= 11 ? 0x77 : (lane == 12 ? 0x47 : 0x00));
       const uint8_t tb = lane == 5 ? 0x70 : (lane >= 6 && lane <= 11 ? 0x77 : (lane == 12 ? 0x67 : 0x00));
-      q4row[128 + lane] = lane < 4 ? 0x77 : (lane == 4 ? 0x27 : qb);
+      // the query weights once more in the second K block (slots 32..): the packed-pair kernel multiplies them with the
+      // norm block of the second train row there (t_ext2x96); every train row keeps zeros in its own second block
+      const int l16 = lane & 15;
+      const uint8_t qb = l16 == 5 ? 0x72 : (l16 >= 6 && l16 <= 11 ? 0x77 : (l16 == 12 ? 0x47 : 0x00));
+      q4row[128 + lane] = l16 < 4 ? 0x77 : (l16 == 4 ? 0x27 : qb);
       t4row[128 + lane] =
           static_cast<uint8_t>(fp4_norm_digit<7>(2 * lane, cnt) | (fp4_norm_digit<7>(2 * lane + 1, cnt) << 4) | tb);
+      // t4x (32 bytes per row): the norm block the packed-pair kernel multiplies in ONE K-step for both train rows of an
+      // accumulator column -- first K block = this row, second K block = row + 192 of the same image (bias only past its end).
+      // Only rows in the first half of a 384-row tile are ever read (l2_i8x2_kernel PK).
+      if (t4x && row % 384 < 192) {
+        int cnt2 = 0;
+        const bool has2 = row + 192 < n;
+        if (has2 && lane < 8) cnt2 = __popc(bits[static_cast<size_t>(row + 192) * 8 + lane]);
+#pragma unroll
+        for (int off = 4; off >= 1; off >>= 1) cnt2 += __shfl_xor_sync(0xffffffffu, cnt2, off);
+        cnt2 = __shfl_sync(0xffffffffu, cnt2, 0);
+        const int l16 = lane & 15, c = lane < 16 ? cnt : cnt2;
+        const uint8_t tb16 = l16 == 5 ? 0x70 : (l16 >= 6 && l16 <= 11 ? 0x77 : (l16 == 12 ? 0x67 : 0x00));
+        const uint8_t d = static_cast<uint8_t>(fp4_norm_digit<7>(2 * l16, c) | (fp4_norm_digit<7>(2 * l16 + 1, c) << 4) | tb16);
+        // past the end of the image the second block still carries the bias (c = 0 there): whatever row the main K-steps
+        // find 192 rows further on, the low field stays within 512 +- 256 and never borrows from the high field
+        t4x[static_cast<size_t>(row) * 32 + lane] = d;
+      }
     }
   }
   if (q8) {
@@ -310,11 +331,12 @@ pack_bits_kernel(const uint32_t* __restrict__ bits, int n, int words, uint8_t* _
 }
 
 cudaError_t launch_pack_bits(const uint32_t* bits, int n, int words, uint8_t* qb, uint8_t* tb, int32_t* popc,
-                             uint8_t* q8, uint8_t* t8, uint8_t* q4, uint8_t* t4, cudaStream_t st) {
+                             uint8_t* q8, uint8_t* t8, uint8_t* q4, uint8_t* t4, cudaStream_t st, uint8_t* t4x) {
   if (n <= 0) return cudaSuccess;
   if (words != 8) q8 = t8 = nullptr;
   if (words != 8 && words != 16) q4 = t4 = nullptr;
-  pack_bits_kernel<<<(n + 7) / 8, 256, 0, st>>>(bits, n, words, qb, tb, popc, q8, t8, q4, t4);
+  if (words != 8) t4x = nullptr;
+  pack_bits_kernel<<<(n + 7) / 8, 256, 0, st>>>(bits, n, words, qb, tb, popc, q8, t8, q4, t4, t4x);
   return cudaGetLastError();
 }
 
