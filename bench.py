@@ -384,7 +384,7 @@ def kernel_name(kind, flags):
     if kind == "orb":
         form = orb_form(flags)
         return {"popc": "hamming_top2_kernel", "e4m3": "l2_top2_tc2_kernel<T2Cfg<256,2,2>,2,false,1>",
-                "i8": "l2_i8x2_kernel<2,false,2,0>", "fp4": "l2_i8x2_kernel<2,false,1,1>"}[form]
+                "i8": "l2_i8x2_kernel<2,false,2,0>", "fp4": "l2_i8x2_kernel<2,3,1,1,0,0,1>", "fp4-1row": "l2_i8x2_kernel<2,false,1,1>"}[form]
     if flags & 32768:
         return "l2_top2_tc2_kernel<T2Cfg<256,2,4>,3>"
     if flags & 524288:
@@ -396,7 +396,9 @@ def kernel_name(kind, flags):
 
 
 def orb_form(flags):
-    return "popc" if (flags & 1024) else "e4m3" if (flags & 65536) else "i8" if (flags & 262144) else "fp4"
+    # fp4 = the packed-pair form (two train rows per accumulator column, the default); debug bit 26 keeps one row per column
+    return ("popc" if (flags & 1024) else "e4m3" if (flags & 65536) else "i8" if (flags & 262144) else
+            "fp4-1row" if (flags & 67108864) else "fp4")
 
 
 _PEAK_CACHE = {}
@@ -425,9 +427,12 @@ def roofline(wl: Workload, res, peaks, world):
             # compares = 64 FLOP of the contraction
             form = orb_form(flags)
             ach = 64.0 * st["knn_work"] / knn_s / 1e12
-            kid, kname = (api.PEAK_KIND_MXF4, "kind::mxf4") if form == "fp4" else (api.PEAK_KIND_I8, "kind::i8 (= kind::f8f6f4 rate)")
-            ops = {"fp4": "E2M1 {0, +-1} values on tcgen05 kind::mxf4 (64 values of K per instruction, all-ones scale factors), "
-                          "f32 accumulate, exact integers", "i8": "u8 x s8 on tcgen05 kind::i8, s32 accumulate",
+            kid, kname = ((api.PEAK_KIND_MXF4, "kind::mxf4") if form.startswith("fp4") else
+                          (api.PEAK_KIND_I8, "kind::i8 (= kind::f8f6f4 rate)"))
+            ops = {"fp4": "E2M1 {0, +-1} values on tcgen05 kind::mxf4 (64 values of K per instruction); two train rows per f32 "
+                          "accumulator column through the UE8M0 block scales 2^10 | 1 (9 K-steps per 384 train rows), exact integers",
+                   "fp4-1row": "E2M1 {0, +-1} values on tcgen05 kind::mxf4 (64 values of K per instruction, all-ones scale factors), "
+                               "f32 accumulate, exact integers", "i8": "u8 x s8 on tcgen05 kind::i8, s32 accumulate",
                    "e4m3": "E4M3 {0,1} values on tcgen05 kind::f8f6f4, f32 accumulate, exact integers"}[form]
         else:
             ach = st["knn_work"] / knn_s / 1e12
@@ -628,7 +633,8 @@ def main():
                  "u8 x s8 operands / s32 accumulate (kind::i8, exact integers)",
                  "orb": {"popc": "u32 popc", "e4m3": "e4m3 {0,1} operands / f32 accumulate (exact integers)",
                          "i8": "u8 x s8 operands / s32 accumulate (exact integers)",
-                         "fp4": "e2m1 {0,+-1} operands (kind::mxf4) / f32 accumulate (exact integers)"}[orb_form(flags)],
+                         "fp4": "e2m1 {0,+-1} operands (kind::mxf4) / f32 accumulate (exact integers)",
+                         "fp4-1row": "e2m1 {0,+-1} operands (kind::mxf4) / f32 accumulate (exact integers)"}[orb_form(flags)],
                  "superpoint": "f16 operands / f32 accumulate candidates + exact f32 re-rank" if (flags & 32768) else
                  "s8 operands / s32 accumulate candidates (kind::i8) + exact f32 re-rank"}[a.kind]
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=n_gpus, steps=a.steps, warmup=a.warmup,
