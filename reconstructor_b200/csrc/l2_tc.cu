@@ -66,9 +66,16 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo, uint
 }
 
 __device__ __forceinline__ void wait_bounded(uint64_t* bar, uint32_t parity) {
-  // A protocol bug must fault, not hang the GPU: ~seconds of spinning, then trap.
-  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
-    if (spin > (1u << 26)) __trap();
+  // A protocol bug must fault, not hang the GPU -- but only a lost arrival may trap: the bound is 20 s of %globaltimer
+  // (read every 4096 polls), orders of magnitude above what a profiler, a sanitizer or co-resident kernels add to a wait.
+  unsigned long long t0 = 0;
+  for (uint32_t spin = 1; !mbar_try_wait(bar, parity); ++spin) {
+    if ((spin & 0xFFFu) == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 20ull * 1000000000ull) __trap();
+    }
   }
 }
 

@@ -180,15 +180,6 @@ __device__ __forceinline__ void tmem_st_32x32b_x32_fill(uint32_t taddr, uint32_t
       "r"(v)
       : "memory");
 }
-// ... <- one value in the even columns, another in the odd ones
-__device__ __forceinline__ void tmem_st_32x32b_x32_fill2(uint32_t taddr, uint32_t ve, uint32_t vo) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %1, %2, %1, %2, %1, %2, %1, %2, %1, %2, %1, %2, %1, %2, "
-      "%1, %2, %1, %2, %1, %2, %1, %2, %1, %2, %1, %2, %1, %2, %1, %2};" ::"r"(taddr),
-      "r"(ve), "r"(vo)
-      : "memory");
-}
 // Arrives (once all prior MMAs of this thread completed) on the barrier at the same offset in both CTAs.
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
   asm volatile(
@@ -357,13 +348,9 @@ __device__ __forceinline__ void t2i_chunk32(Top2i& s, uint32_t (&v)[32], int c, 
 #define PM_PK_PROBE 0        // development: 1 = no field shift, 2 = XOR tree instead of the minima (timing only, wrong results)
 #endif
 static constexpr uint32_t T2P_SF_BIG = 0x89898989u;             // UE8M0 2^10, four scale factors per TMEM column
-#ifndef PM_PK_SFMODE
-#define PM_PK_SFMODE 0       // where scale_vec::2X reads the scale of a row's two K blocks: 0 = bytes 0 | 1 of a column,
-#endif                       // 1 = bytes 1 | 0, 2 = even | odd columns, 3 = odd | even columns (development)
-static constexpr uint32_t T2P_SF_MIX_E = PM_PK_SFMODE == 0 ? 0x7F897F89u : PM_PK_SFMODE == 1 ? 0x897F897Fu
-                                         : PM_PK_SFMODE == 2 ? 0x89898989u : 0x7F7F7F7Fu;
-static constexpr uint32_t T2P_SF_MIX_O = PM_PK_SFMODE == 0 ? 0x7F897F89u : PM_PK_SFMODE == 1 ? 0x897F897Fu
-                                         : PM_PK_SFMODE == 2 ? 0x7F7F7F7Fu : 0x89898989u;
+// scale_vec::2X reads the scales of a row's two K blocks from bytes 0 | 1 of its scale column (sf_id 0): 2^10 | 1.  (Bytes 1 | 0
+// and scales split over even | odd columns were tried on the device: wrong results.)
+static constexpr uint32_t T2P_SF_MIX = 0x7F897F89u;
 static constexpr float T2P_BIAS = 512.f;                        // what the bias slots of the norm block add (pack.cu)
 __device__ __forceinline__ uint32_t t2_umin32x2(const uint32_t (&r)[32]) {
   uint32_t a[10];
@@ -1116,7 +1103,7 @@ l2_i8x2_kernel(const __grid_constant__ CUtensorMap q_main, const __grid_constant
       tmem_st_32x32b_x32_fill(a + 32, 0x7F7F7F7Fu);
       if (PK) {                                          // columns 448..479: scale 2^10 for the first sub-tile's B rows;
         tmem_st_32x32b_x32_fill(a + 64, T2P_SF_BIG);     // 480..511: 2^10 for the first K block, 1 for the second (norm step)
-        tmem_st_32x32b_x32_fill2(a + 96, T2P_SF_MIX_E, T2P_SF_MIX_O);
+        tmem_st_32x32b_x32_fill(a + 96, T2P_SF_MIX);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
