@@ -1,5 +1,6 @@
 #!/bin/bash
 # packed-pair kernel with ONE norm K-step for both rows (pair norm blocks, per-K-block scale factors): where does
+# (historical: the -DPM_PK_SFMODE build switch behind ab/libpm_pk_sf*.so was removed once layout 0 -- bytes 0 | 1 of a column -- proved to be the one)
 # scale_vec::2X read the two scales of a row?  tests with each candidate layout, then the ORB-100 A/B with the one that passes
 source tools/r02/gpu_fn.sh
 T="timeout 600 python -m pytest tests -q -m gpu --timeout 300 -p no:cacheprovider -x -k test_hamming_i8_two_set_kernel_sizes_around_row_sets"
